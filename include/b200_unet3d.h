@@ -1,0 +1,149 @@
+/* b200_unet3d.h — C ABI of the B200-native (sm_100a) 3D U-Net hot path.
+ *
+ * The reference (qwertyhgb/Prostate-Cancer-Multimodal-Segmentation) has no FFI: every op on its hot path is a
+ * stock torch.nn call.  Each entry point below replaces one of those call sites (cited per function, paths
+ * relative to the reference root) and is what a ctypes binding in the reference would bind — see INTEGRATION.md.
+ *
+ * Conventions
+ *   - Activations are NDHWC bf16 "views": a base pointer to channel 0 of voxel (0,0,0,0), extents, and `ld`, the
+ *     number of bf16 elements between consecutive voxels (ld >= c; ld > c addresses one half of a concat buffer).
+ *   - All device memory is owned by the caller; nothing is allocated or freed here.  All work is enqueued on the
+ *     given CUDA stream (a cudaStream_t passed as void*), no host synchronisation, CUDA-graph capturable.
+ *   - Every function returns 0 on success, else a b200_status; b200_last_error() gives the thread-local message.
+ *   - There is no CPU path and no cuDNN/cuBLAS path behind any of these.
+ */
+#ifndef B200_UNET3D_H
+#define B200_UNET3D_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    B200_OK = 0,
+    B200_ERR_BAD_ARG = 1,
+    B200_ERR_UNSUPPORTED_SHAPE = 2,
+    B200_ERR_CUDA = 3,
+    B200_ERR_DRIVER = 4
+} b200_status;
+
+typedef struct {
+    void* ptr;   /* bf16* */
+    int64_t n, d, h, w, c;
+    int64_t ld;  /* voxel pitch in elements */
+} b200_act;
+
+/* conv3d fprop epilogue modes */
+enum { B200_EPI_PLAIN = 0, B200_EPI_BIAS_STATS = 1, B200_EPI_AFFINE_RELU = 2, B200_EPI_BIAS = 3 };
+
+const char* b200_last_error(void);
+int b200_abi_version(void);
+/* number of SMs of the current device (grid sizing), or <0 on error */
+int b200_sm_count(void);
+
+/* ---- layout packing ------------------------------------------------------------------------------------ */
+/* (N,C,D,H,W) fp32 -> NDHWC bf16 view, channels c..out->c-1 zero (input of UNet3D.forward, models/unet3d.py:247) */
+int b200_pack_input(const float* x_ncdhw, int64_t n, int64_t c, int64_t d, int64_t h, int64_t w,
+                    const b200_act* out, void* stream);
+/* Conv3d weight (Cout,Cin,3,3,3) fp32 -> w_fprop bf16 [27][Cout][cin_pad], w_dgrad bf16 [27][cin_pad][Cout]
+ * (either may be NULL).  models/unet3d.py:29,35 */
+int b200_pack_conv_weight(const float* w, int cout, int cin, int cin_pad, void* w_fprop, void* w_dgrad, void* stream);
+/* ConvTranspose3d weight (Cin,Cout,2,2,2) fp32 -> w_fwd bf16 [8*Cout][Cin], w_dgrad bf16 [8][Cin][Cout],
+ * bias (Cout) -> bias8 fp32 [8*Cout].  models/unet3d.py:120 */
+int b200_pack_convt_weight(const float* w, const float* bias, int cin, int cout, void* w_fwd, void* w_dgrad,
+                           float* bias8, void* stream);
+
+/* ---- 3x3x3 convolution, padding 1 (nn.Conv3d, models/unet3d.py:29,35), tcgen05 implicit GEMM ------------ */
+/* number of 128-voxel output bricks of a volume */
+int64_t b200_conv3d_mtiles(int64_t n, int64_t d, int64_t h, int64_t w);
+/* rows of stats_partial that fprop(BIAS_STATS) writes for this problem (one per persistent CTA), <0 on error */
+int b200_conv3d_stat_rows(int64_t n, int64_t d, int64_t h, int64_t w, int64_t cout);
+/* mode BIAS_STATS : y = bf16(conv + bias); stats_partial[row][Cout][2] = (sum, sum of squares) of stored y
+ * mode AFFINE_RELU: y = relu(conv * scale + shift)   (eval-mode BatchNorm + bias folded)
+ * mode BIAS / PLAIN likewise without statistics. */
+int b200_conv3d_fprop(const b200_act* x, const void* w_fprop, const float* bias, const b200_act* y,
+                      float* stats_partial, int mode, const float* scale, const float* shift, void* stream);
+int b200_conv3d_dgrad(const b200_act* dy, const void* w_dgrad, const b200_act* dx, void* stream);
+/* dw fp32 (Cout, cin_real, 3,3,3) += ; x->c may exceed cin_real (zero padded channels) */
+int b200_conv3d_wgrad(const b200_act* x, const b200_act* dy, float* dw, int cin_real, void* stream);
+
+/* ---- ConvTranspose3d k=2 s=2 (models/unet3d.py:120,134) + F.pad + cat written in place (:143-156) -------- */
+/* y: view (upper channel half of the concat buffer) with the skip's extents; output voxel (2d+i+pad_d, ...) */
+int b200_convt2x_fwd(const b200_act* x, const void* w_fwd, const float* bias8, const b200_act* y, int pad_d,
+                     int pad_h, int pad_w, void* stream);
+int b200_convt2x_dgrad(const b200_act* dy, int pad_d, int pad_h, int pad_w, const void* w_dgrad,
+                       const b200_act* dx, void* stream);
+/* dw fp32 (Cin, Cout, 2,2,2) += */
+int b200_convt2x_wgrad(const b200_act* x, const b200_act* dy, int pad_d, int pad_h, int pad_w, float* dw,
+                       void* stream);
+
+/* ---- BatchNorm3d + ReLU (models/unet3d.py:31-33,37-39) -------------------------------------------------- */
+/* reduce conv-epilogue partials; train-mode batch statistics, running-stat update (momentum, unbiased var),
+ * scale = gamma*rstd, shift = beta - mean*scale.  running_* may be NULL. */
+int b200_bn_finalize(const float* stats_partial, int64_t rows, int64_t count, int c, const float* gamma,
+                     const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                     float* mean, float* rstd, float* scale, float* shift, void* stream);
+/* eval mode: scale = gamma/sqrt(rv+eps), shift = beta + (conv_bias - rm)*scale */
+int b200_bn_fold_eval(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                      const float* conv_bias, float eps, int c, float* scale, float* shift, void* stream);
+/* out = relu(y*scale + shift) */
+int b200_bn_apply_relu(const b200_act* y, const float* scale, const float* shift, const b200_act* out, void* stream);
+/* backward, pass 1: partial[blk][c][2] = (sum dy_m, sum dy_m*xhat), dy_m = dout * (y*scale+shift > 0).
+ * returns number of partial rows written through *nblk (<= b200_bn_bwd_max_blocks()). */
+int b200_bn_bwd_max_blocks(void);
+int b200_bn_bwd_reduce(const b200_act* dout, const b200_act* y, const float* scale, const float* shift,
+                       const float* mean, const float* rstd, float* partial, int* nblk, void* stream);
+/* dgamma += sum dy_m*xhat ; dbeta += sum dy_m ; coef[c][2] = (sum dy_m / count, sum dy_m*xhat / count) */
+int b200_bn_bwd_finalize(const float* partial, int nblk, int c, int64_t count, float* dgamma, float* dbeta,
+                         float* coef, void* stream);
+/* pass 2: dy = gamma*rstd*(dy_m - coef0 - xhat*coef1) (bf16) ; dbias[c] += sum of stored dy */
+int b200_bn_bwd_apply(const b200_act* dout, const b200_act* y, const float* scale, const float* shift,
+                      const float* mean, const float* rstd, const float* gamma, const float* coef,
+                      const b200_act* dy, float* dbias, void* stream);
+
+/* ---- MaxPool3d(2) (models/unet3d.py:80) ---------------------------------------------------------------- */
+int b200_maxpool3d_fwd(const b200_act* x, const b200_act* y, void* stream);
+/* dx = dskip (may be NULL) + scatter(dy) to the first maximum in d,h,w scan order; voxels not covered by a
+ * window (odd extents) get dskip only. */
+int b200_maxpool3d_bwd(const b200_act* x, const b200_act* y, const b200_act* dy, const b200_act* dskip,
+                       const b200_act* dx, void* stream);
+
+/* ---- head Conv3d 1x1x1 (models/unet3d.py:222,295) ------------------------------------------------------ */
+/* logits fp32 (N,ncls,D,H,W) = w (ncls,C) . x + b ; if probs != NULL also sigmoid(logits) (predict, :298-318) */
+int b200_head_fwd(const b200_act* x, const float* w, const float* b, int ncls, float* logits, float* probs,
+                  void* stream);
+/* dx bf16 = dlogits . w ; dw += dlogits^T x ; db += sum dlogits */
+int b200_head_bwd(const b200_act* x, const float* w, int ncls, const float* dlogits, const b200_act* dx, float* dw,
+                  float* db, void* stream);
+
+/* ---- sigmoid-BCE + Dice (utils/losses.py:44-92,107-152) ------------------------------------------------ */
+/* sums[4] = (sum softplus(z)-z*t, sum sigmoid(z)*t, sum sigmoid(z), sum t) over all elements;
+ * loss[0] = bce_w * sums0/n + dice_w * (1 - (2*sums1+smooth)/(sums2+sums3+smooth)).  workspace: >= 4*1024 floats */
+int b200_loss_fwd(const float* logits, const float* target, int64_t n, float bce_w, float dice_w, float smooth,
+                  float* workspace, float* sums, float* loss, void* stream);
+/* dlogits = gout[0] * dL/dz using sums from the forward */
+int b200_loss_bwd(const float* logits, const float* target, int64_t n, float bce_w, float dice_w, float smooth,
+                  const float* sums, const float* gout, float* dlogits, void* stream);
+
+/* ---- optimizer (torch.optim.Adam, utils/trainer.py:113-117,192) ---------------------------------------- */
+/* fused over a flat fp32 buffer: g = grad*grad_scale + wd*p ; Adam moments ; bias-corrected update.
+ * step is the 1-based step count.  If found_inf != NULL and *found_inf != 0 the update is skipped. */
+int b200_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                   float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
+                   const float* found_inf, void* stream);
+/* sum of squares of a flat fp32 buffer -> out[0] (+=) ; nonfinite flag -> out[1] (clip_grad_norm_/GradScaler) */
+int b200_sumsq(const float* x, int64_t n, float* out, void* stream);
+
+/* ---- misc bandwidth helpers ---------------------------------------------------------------------------- */
+int b200_fill_zero(const b200_act* v, void* stream);
+/* out[c] += sum over voxels of v[.,c]  (ConvTranspose3d bias gradient) */
+int b200_channel_sum(const b200_act* v, float* out, void* stream);
+/* NDHWC bf16 view -> (N,C,D,H,W) fp32 (debug / per-layer parity taps) */
+int b200_unpack_act(const b200_act* v, float* out_ncdhw, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,10 @@
+"""B200-native (sm_100a) hot path of the 5-modality prostate-MRI 3D U-Net: drop-in for the reference's
+``models/unet3d.py`` (UNet3D), ``utils/losses.py`` (DiceLoss, BCEDiceLoss) and its trainer / predict entry points.
+
+Host code is Python/PyTorch (device memory, streams, torch.distributed); all arithmetic on the path runs in the
+hand-written CUDA kernels behind the C ABI of ``include/b200_unet3d.h`` (``libb200unet3d.so``, built in-tree).
+"""
+from ._lib import B200Error, load as load_library, lib_path  # noqa: F401
+from . import ops  # noqa: F401
+
+__all__ = ["B200Error", "load_library", "lib_path", "ops"]

@@ -1,0 +1,98 @@
+"""ctypes binding of the C ABI in include/b200_unet3d.h.
+
+There is no fallback: if the library is missing, or a call fails, an exception is raised.
+"""
+import ctypes as C
+import os
+
+import torch
+
+from . import build as _build
+
+_i64, _i32, _f32, _vp = C.c_int64, C.c_int, C.c_float, C.c_void_p
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+class Act(C.Structure):
+    """b200_act: NDHWC bf16 view (pointer to channel 0 of voxel 0, extents, voxel pitch)."""
+    _fields_ = [("ptr", _vp), ("n", _i64), ("d", _i64), ("h", _i64), ("w", _i64), ("c", _i64), ("ld", _i64)]
+
+
+_AP = C.POINTER(Act)
+
+# name -> (restype, argtypes); mirrors include/b200_unet3d.h one to one
+SIGNATURES = {
+    "b200_last_error": (C.c_char_p, []),
+    "b200_abi_version": (_i32, []),
+    "b200_sm_count": (_i32, []),
+    "b200_pack_input": (_i32, [_vp, _i64, _i64, _i64, _i64, _i64, _AP, _vp]),
+    "b200_pack_conv_weight": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "b200_pack_convt_weight": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "b200_conv3d_mtiles": (_i64, [_i64, _i64, _i64, _i64]),
+    "b200_conv3d_stat_rows": (_i32, [_i64, _i64, _i64, _i64, _i64]),
+    "b200_conv3d_fprop": (_i32, [_AP, _vp, _vp, _AP, _vp, _i32, _vp, _vp, _vp]),
+    "b200_conv3d_dgrad": (_i32, [_AP, _vp, _AP, _vp]),
+    "b200_conv3d_wgrad": (_i32, [_AP, _AP, _vp, _i32, _vp]),
+    "b200_convt2x_fwd": (_i32, [_AP, _vp, _vp, _AP, _i32, _i32, _i32, _vp]),
+    "b200_convt2x_dgrad": (_i32, [_AP, _i32, _i32, _i32, _vp, _AP, _vp]),
+    "b200_convt2x_wgrad": (_i32, [_AP, _AP, _i32, _i32, _i32, _vp, _vp]),
+    "b200_bn_finalize": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200_bn_fold_eval": (_i32, [_vp, _vp, _vp, _vp, _vp, _f32, _i32, _vp, _vp, _vp]),
+    "b200_bn_apply_relu": (_i32, [_AP, _vp, _vp, _AP, _vp]),
+    "b200_bn_bwd_max_blocks": (_i32, []),
+    "b200_bn_bwd_reduce": (_i32, [_AP, _AP, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i32), _vp]),
+    "b200_bn_bwd_finalize": (_i32, [_vp, _i32, _i32, _i64, _vp, _vp, _vp, _vp]),
+    "b200_bn_bwd_apply": (_i32, [_AP, _AP, _vp, _vp, _vp, _vp, _vp, _vp, _AP, _vp, _vp]),
+    "b200_maxpool3d_fwd": (_i32, [_AP, _AP, _vp]),
+    "b200_maxpool3d_bwd": (_i32, [_AP, _AP, _AP, _AP, _AP, _vp]),
+    "b200_head_fwd": (_i32, [_AP, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "b200_head_bwd": (_i32, [_AP, _vp, _i32, _vp, _AP, _vp, _vp, _vp]),
+    "b200_loss_fwd": (_i32, [_vp, _vp, _i64, _f32, _f32, _f32, _vp, _vp, _vp, _vp]),
+    "b200_loss_bwd": (_i32, [_vp, _vp, _i64, _f32, _f32, _f32, _vp, _vp, _vp, _vp]),
+    "b200_adam_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i64, _f32, _vp, _vp]),
+    "b200_sumsq": (_i32, [_vp, _i64, _vp, _vp]),
+    "b200_fill_zero": (_i32, [_AP, _vp]),
+    "b200_channel_sum": (_i32, [_AP, _vp, _vp]),
+    "b200_unpack_act": (_i32, [_AP, _vp, _vp]),
+}
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load():
+    """dlopen the C-ABI library (building it first if nvcc is present and it is missing)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if not os.path.exists(path):
+        path = _build.build()
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().b200_last_error().decode("utf-8", "replace")
+        raise B200Error(f"{what or 'b200 call'} failed (status {rc}): {msg}")
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t) -> int:
+    """device pointer of a tensor (None -> NULL)"""
+    return 0 if t is None else t.data_ptr()

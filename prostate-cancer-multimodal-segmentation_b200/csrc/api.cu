@@ -1,0 +1,662 @@
+// C ABI (include/b200_unet3d.h): argument validation, TMA tensor-map construction, kernel launches.
+// Nothing here allocates device memory or synchronises; errors never cross the boundary as C++ exceptions.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "../../include/b200_unet3d.h"
+#include "bandwidth.cuh"
+#include "igemm.cuh"
+
+namespace b200 {
+extern "C" __global__ void igemm_kernel(const __grid_constant__ IgemmParams p);
+extern "C" __global__ void wgrad_kernel(const __grid_constant__ WgradParams p);
+}  // namespace b200
+
+using namespace b200;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CUDA_TRY(expr)                                                                               \
+    do {                                                                                             \
+        cudaError_t e__ = (expr);                                                                    \
+        if (e__ != cudaSuccess) return fail(B200_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+    } while (0)
+#define REQUIRE(cond, ...)                                   \
+    do {                                                     \
+        if (!(cond)) return fail(B200_ERR_BAD_ARG, __VA_ARGS__); \
+    } while (0)
+
+extern "C" const char* b200_last_error(void) { return g_err; }
+extern "C" int b200_abi_version(void) { return 1; }
+
+// ------------------------------------------------------------------------------------------------ device info
+static int g_sms[64];
+static std::mutex g_mu;
+static int sm_count() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+    if (g_sms[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+        g_sms[dev] = n;
+    }
+    return g_sms[dev];
+}
+extern "C" int b200_sm_count(void) { return sm_count(); }
+
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+static int get_encode() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_encode) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+        return fail(B200_ERR_DRIVER, "cuTensorMapEncodeTiled not available from the driver (%s)",
+                    cudaGetErrorString(e));
+    g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    return 0;
+}
+
+static View to_view(const b200_act* a) {
+    View v;
+    v.p = reinterpret_cast<__nv_bfloat16*>(a->ptr);
+    v.n = a->n; v.d = a->d; v.h = a->h; v.w = a->w; v.c = a->c; v.ld = a->ld;
+    return v;
+}
+static int check_view(const b200_act* a, const char* name) {
+    REQUIRE(a != nullptr && a->ptr != nullptr, "%s: null view", name);
+    REQUIRE(a->n > 0 && a->d > 0 && a->h > 0 && a->w > 0 && a->c > 0, "%s: empty extent", name);
+    REQUIRE(a->c % 8 == 0 && a->ld % 8 == 0 && a->ld >= a->c, "%s: c=%lld ld=%lld must be multiples of 8, ld >= c",
+            name, (long long)a->c, (long long)a->ld);
+    REQUIRE((reinterpret_cast<uintptr_t>(a->ptr) & 15) == 0, "%s: pointer not 16-byte aligned", name);
+    REQUIRE(a->c <= 2048, "%s: more than 2048 channels", name);
+    return 0;
+}
+#define CHECK_VIEW(a)                       \
+    do {                                    \
+        int rc__ = check_view(a, #a);       \
+        if (rc__) return rc__;              \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------ tensor maps
+// 5-D map over an NDHWC bf16 view (c, w, h, d, n) with optional sub-sampling (stride `mul` voxels, origin off_*):
+// box = (64 channels, tw, th, td, 1), 128-byte swizzle, out-of-range elements read as zero.
+static int make_act_map(CUtensorMap* map, const __nv_bfloat16* base, long long c, long long w, long long h,
+                        long long d, long long n, long long ld, long long src_w, long long src_h, long long src_d,
+                        int mul, int tw, int th, int td) {
+    cuuint64_t dims[5] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)d, (cuuint64_t)n};
+    cuuint64_t strides[4] = {(cuuint64_t)(mul * ld * 2), (cuuint64_t)(mul * src_w * ld * 2),
+                             (cuuint64_t)(mul * src_h * src_w * ld * 2), (cuuint64_t)(src_d * src_h * src_w * ld * 2)};
+    cuuint32_t box[5] = {64, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)td, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<__nv_bfloat16*>(base), dims, strides,
+                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(B200_ERR_DRIVER,
+                    "cuTensorMapEncodeTiled(act) failed: %d (c=%lld w=%lld h=%lld d=%lld n=%lld ld=%lld mul=%d box=%d,%d,%d)",
+                    (int)r, c, w, h, d, n, ld, mul, tw, th, td);
+    return 0;
+}
+// 3-D map over packed weights [taps][rows][k] (k contiguous): box = (64, box_rows, 1)
+static int make_weight_map(CUtensorMap* map, const void* base, long long k, long long rows, long long taps,
+                           int box_rows) {
+    cuuint64_t dims[3] = {(cuuint64_t)k, (cuuint64_t)rows, (cuuint64_t)taps};
+    cuuint64_t strides[2] = {(cuuint64_t)(k * 2), (cuuint64_t)(rows * k * 2)};
+    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(B200_ERR_DRIVER, "cuTensorMapEncodeTiled(weight) failed: %d (k=%lld rows=%lld taps=%lld box=%d)",
+                    (int)r, k, rows, taps, box_rows);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ brick geometry
+struct Brick {
+    int tw, th, td;
+    int lw, lh, ld;
+    long long nbw, nbh, nbd;
+};
+// 128 voxels = 2^lw x 2^lh x 2^ld minimising the number of bricks (ties: longest w run)
+static Brick choose_brick(long long w, long long h, long long d) {
+    Brick best{};
+    long long best_n = -1;
+    for (int lw = 7; lw >= 0; --lw)
+        for (int lh = 7 - lw; lh >= 0; --lh) {
+            const int ldp = 7 - lw - lh;
+            const long long tw = 1LL << lw, th = 1LL << lh, td = 1LL << ldp;
+            const long long nb = ((w + tw - 1) / tw) * ((h + th - 1) / th) * ((d + td - 1) / td);
+            if (best_n < 0 || nb < best_n) {
+                best_n = nb;
+                best.tw = (int)tw; best.th = (int)th; best.td = (int)td;
+                best.lw = lw; best.lh = lh; best.ld = ldp;
+                best.nbw = (w + tw - 1) / tw; best.nbh = (h + th - 1) / th; best.nbd = (d + td - 1) / td;
+            }
+        }
+    return best;
+}
+
+static int igemm_block_n(long long ncols) { return ncols >= 256 ? 256 : (int)((ncols + 15) / 16 * 16); }
+static int igemm_stages(int block_n) {
+    const int per_stage = kBoxBytes + block_n * 128;
+    int st = (200 * 1024) / per_stage;
+    if (st > 8) st = 8;
+    if (st < 2) st = 2;
+    return st;
+}
+static size_t igemm_smem(int stages, int block_n) {
+    return 1024 + (size_t)stages * (kBoxBytes + block_n * 128) + 8 * (2 * stages + 4) + 32 + 4 * 256 * 2 * 4 +
+           (size_t)kMaxStatCols * 2 * 4;
+}
+
+static int launch_igemm(IgemmParams& p, cudaStream_t s, int* grid_out) {
+    const int sms = sm_count();
+    if (sms <= 0) return fail(B200_ERR_CUDA, "no CUDA device");
+    static size_t attr_smem = 0;
+    const size_t smem = igemm_smem(p.stages, p.block_n);
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (smem > attr_smem) {
+            CUDA_TRY(cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            attr_smem = 227 * 1024;
+        }
+    }
+    const long long tiles = (long long)p.nbw * p.nbh * p.nbd * p.nbatch * p.n_tiles;
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    if (grid_out) *grid_out = grid;
+    igemm_kernel<<<grid, kThreads, smem, s>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int64_t b200_conv3d_mtiles(int64_t n, int64_t d, int64_t h, int64_t w) {
+    const Brick b = choose_brick(w, h, d);
+    return n * b.nbw * b.nbh * b.nbd;
+}
+
+static void set_m_grid(IgemmParams& p, const Brick& b, long long n, long long w, long long h, long long d) {
+    p.nbw = (int)b.nbw; p.nbh = (int)b.nbh; p.nbd = (int)b.nbd; p.nbatch = (int)n;
+    p.tw_log2 = b.lw; p.th_log2 = b.lh; p.td_log2 = b.ld;
+    p.W = (int)w; p.H = (int)h; p.D = (int)d;
+}
+static void set_out(IgemmParams& p, const b200_act* y) {
+    p.out = reinterpret_cast<__nv_bfloat16*>(y->ptr);
+    p.out_sw = y->ld;
+    p.out_sh = y->w * y->ld;
+    p.out_sd = y->h * y->w * y->ld;
+    p.out_sn = y->d * y->h * y->w * y->ld;
+}
+
+// shared by fprop (sign = +1) and dgrad (sign = -1): 27 taps over one activation map
+static int conv3_igemm(const b200_act* in, const void* w_packed, const b200_act* out, int sign, int mode,
+                       const float* v0, const float* v1, float* stats, cudaStream_t s) {
+    int rc = get_encode();
+    if (rc) return rc;
+    REQUIRE(in->n == out->n && in->d == out->d && in->h == out->h && in->w == out->w, "conv3d: extent mismatch");
+    REQUIRE(out->c % 16 == 0, "conv3d: output channels (%lld) must be a multiple of 16", (long long)out->c);
+    REQUIRE(in->c % 16 == 0, "conv3d: input channels (%lld) must be a multiple of 16", (long long)in->c);
+    REQUIRE(in->n * in->d * in->h * in->w < (1LL << 31), "conv3d: too many voxels");
+    IgemmParams p;
+    memset(&p, 0, sizeof(p));
+    const Brick b = choose_brick(in->w, in->h, in->d);
+    rc = make_act_map(&p.a_map[0], reinterpret_cast<const __nv_bfloat16*>(in->ptr), in->c, in->w, in->h, in->d, in->n,
+                      in->ld, in->w, in->h, in->d, 1, b.tw, b.th, b.td);
+    if (rc) return rc;
+    p.block_n = igemm_block_n(out->c);
+    rc = make_weight_map(&p.b_map, w_packed, in->c, out->c, 27, p.block_n);
+    if (rc) return rc;
+    p.ntaps = 27;
+    for (int t = 0; t < 27; ++t) {
+        p.a_map_of_tap[t] = 0;
+        p.tap_dd[t] = sign * (t / 9 - 1);
+        p.tap_dh[t] = sign * ((t / 3) % 3 - 1);
+        p.tap_dw[t] = sign * (t % 3 - 1);
+    }
+    p.cin = (int)in->c;
+    p.kc_blocks = (int)((in->c + 63) / 64);
+    p.ncols = (int)out->c;
+    p.n_tiles = (p.ncols + p.block_n - 1) / p.block_n;
+    set_m_grid(p, b, in->n, in->w, in->h, in->d);
+    p.stages = igemm_stages(p.block_n);
+    p.mode = mode;
+    p.vec0 = v0; p.vec1 = v1; p.stats = stats;
+    set_out(p, out);
+    p.out_mul = 1;
+    p.cols_per_group = p.ncols;
+    return launch_igemm(p, s, nullptr);
+}
+
+extern "C" int b200_conv3d_stat_rows(int64_t n, int64_t d, int64_t h, int64_t w, int64_t cout) {
+    const int sms = sm_count();
+    if (sms <= 0) return -1;
+    const int bn = igemm_block_n(cout);
+    const long long tiles = b200_conv3d_mtiles(n, d, h, w) * ((cout + bn - 1) / bn);
+    return (int)(tiles < sms ? tiles : sms);
+}
+
+extern "C" int b200_conv3d_fprop(const b200_act* x, const void* w_fprop, const float* bias, const b200_act* y,
+                                 float* stats_partial, int mode, const float* scale, const float* shift,
+                                 void* stream) {
+    CHECK_VIEW(x);
+    CHECK_VIEW(y);
+    REQUIRE(w_fprop != nullptr, "conv3d_fprop: null weights");
+    const float *v0 = nullptr, *v1 = nullptr;
+    switch (mode) {
+        case B200_EPI_PLAIN: break;
+        case B200_EPI_BIAS_STATS:
+            REQUIRE(bias && stats_partial, "conv3d_fprop: BIAS_STATS needs bias and stats_partial");
+            REQUIRE(y->c <= kMaxStatCols, "conv3d_fprop: BIAS_STATS supports at most %d output channels", kMaxStatCols);
+            v0 = bias;
+            break;
+        case B200_EPI_AFFINE_RELU:
+            REQUIRE(scale && shift, "conv3d_fprop: AFFINE_RELU needs scale and shift");
+            v0 = scale; v1 = shift;
+            break;
+        case B200_EPI_BIAS:
+            REQUIRE(bias, "conv3d_fprop: BIAS needs bias");
+            v0 = bias;
+            break;
+        default: return fail(B200_ERR_BAD_ARG, "conv3d_fprop: unknown mode %d", mode);
+    }
+    return conv3_igemm(x, w_fprop, y, +1, mode, v0, v1, stats_partial, (cudaStream_t)stream);
+}
+
+extern "C" int b200_conv3d_dgrad(const b200_act* dy, const void* w_dgrad, const b200_act* dx, void* stream) {
+    CHECK_VIEW(dy);
+    CHECK_VIEW(dx);
+    REQUIRE(w_dgrad != nullptr, "conv3d_dgrad: null weights");
+    // dx[v, ci] = sum_t sum_co dy[v - off(t), co] * w[co, ci, t]
+    return conv3_igemm(dy, w_dgrad, dx, -1, B200_EPI_PLAIN, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------ transposed conv
+static int check_convt(const b200_act* x, const b200_act* y, int pd, int ph, int pw, const char* who) {
+    REQUIRE(pd >= 0 && ph >= 0 && pw >= 0, "%s: negative pad", who);
+    REQUIRE(x->n == y->n && 2 * x->d + pd <= y->d && 2 * x->h + ph <= y->h && 2 * x->w + pw <= y->w,
+            "%s: upsampled extent (2*%lld+%d, 2*%lld+%d, 2*%lld+%d) exceeds target (%lld,%lld,%lld)", who,
+            (long long)x->d, pd, (long long)x->h, ph, (long long)x->w, pw, (long long)y->d, (long long)y->h,
+            (long long)y->w);
+    return 0;
+}
+
+extern "C" int b200_convt2x_fwd(const b200_act* x, const void* w_fwd, const float* bias8, const b200_act* y,
+                                int pad_d, int pad_h, int pad_w, void* stream) {
+    CHECK_VIEW(x);
+    CHECK_VIEW(y);
+    REQUIRE(w_fwd && bias8, "convt2x_fwd: null weights/bias");
+    int rc = check_convt(x, y, pad_d, pad_h, pad_w, "convt2x_fwd");
+    if (rc) return rc;
+    REQUIRE(x->c % 16 == 0 && y->c % 16 == 0, "convt2x_fwd: channels must be multiples of 16");
+    rc = get_encode();
+    if (rc) return rc;
+    IgemmParams p;
+    memset(&p, 0, sizeof(p));
+    const Brick b = choose_brick(x->w, x->h, x->d);
+    rc = make_act_map(&p.a_map[0], reinterpret_cast<const __nv_bfloat16*>(x->ptr), x->c, x->w, x->h, x->d, x->n,
+                      x->ld, x->w, x->h, x->d, 1, b.tw, b.th, b.td);
+    if (rc) return rc;
+    const long long ncols = 8 * y->c;
+    p.block_n = igemm_block_n(ncols);
+    // a 256-column tile must not straddle a tap group unless the group size divides it
+    REQUIRE(p.block_n % 16 == 0 && (y->c % 16 == 0), "convt2x_fwd: bad column tiling");
+    rc = make_weight_map(&p.b_map, w_fwd, x->c, ncols, 1, p.block_n);
+    if (rc) return rc;
+    p.ntaps = 1;
+    p.cin = (int)x->c;
+    p.kc_blocks = (int)((x->c + 63) / 64);
+    p.ncols = (int)ncols;
+    p.n_tiles = (int)((ncols + p.block_n - 1) / p.block_n);
+    set_m_grid(p, b, x->n, x->w, x->h, x->d);
+    p.stages = igemm_stages(p.block_n);
+    p.mode = EPI_BIAS;
+    p.vec0 = bias8;
+    set_out(p, y);
+    p.out_mul = 2;
+    p.cols_per_group = (int)y->c;
+    for (int t = 0; t < 8; ++t) {
+        p.out_od[t] = pad_d + ((t >> 2) & 1);
+        p.out_oh[t] = pad_h + ((t >> 1) & 1);
+        p.out_ow[t] = pad_w + (t & 1);
+    }
+    return launch_igemm(p, (cudaStream_t)stream, nullptr);
+}
+
+extern "C" int b200_convt2x_dgrad(const b200_act* dy, int pad_d, int pad_h, int pad_w, const void* w_dgrad,
+                                  const b200_act* dx, void* stream) {
+    CHECK_VIEW(dy);
+    CHECK_VIEW(dx);
+    REQUIRE(w_dgrad, "convt2x_dgrad: null weights");
+    int rc = check_convt(dx, dy, pad_d, pad_h, pad_w, "convt2x_dgrad");
+    if (rc) return rc;
+    REQUIRE(dx->c % 16 == 0 && dy->c % 16 == 0, "convt2x_dgrad: channels must be multiples of 16");
+    rc = get_encode();
+    if (rc) return rc;
+    IgemmParams p;
+    memset(&p, 0, sizeof(p));
+    const Brick b = choose_brick(dx->w, dx->h, dx->d);
+    const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(dy->ptr);
+    for (int t = 0; t < 8; ++t) {
+        const long long od = pad_d + ((t >> 2) & 1), oh = pad_h + ((t >> 1) & 1), ow = pad_w + (t & 1);
+        const __nv_bfloat16* bt = base + ((od * dy->h + oh) * dy->w + ow) * dy->ld;
+        rc = make_act_map(&p.a_map[t], bt, dy->c, dx->w, dx->h, dx->d, dx->n, dy->ld, dy->w, dy->h, dy->d, 2, b.tw,
+                          b.th, b.td);
+        if (rc) return rc;
+        p.a_map_of_tap[t] = t;
+    }
+    p.block_n = igemm_block_n(dx->c);
+    rc = make_weight_map(&p.b_map, w_dgrad, dy->c, dx->c, 8, p.block_n);
+    if (rc) return rc;
+    p.ntaps = 8;
+    p.cin = (int)dy->c;
+    p.kc_blocks = (int)((dy->c + 63) / 64);
+    p.ncols = (int)dx->c;
+    p.n_tiles = (p.ncols + p.block_n - 1) / p.block_n;
+    set_m_grid(p, b, dx->n, dx->w, dx->h, dx->d);
+    p.stages = igemm_stages(p.block_n);
+    p.mode = EPI_PLAIN;
+    set_out(p, dx);
+    p.out_mul = 1;
+    p.cols_per_group = p.ncols;
+    return launch_igemm(p, (cudaStream_t)stream, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------------ weight gradients
+static int launch_wgrad(WgradParams& p, cudaStream_t s) {
+    const int sms = sm_count();
+    if (sms <= 0) return fail(B200_ERR_CUDA, "no CUDA device");
+    static bool attr = false;
+    const size_t smem = 1024 + 2 * 2 * kBoxBytes + 2 * 4 * kBoxBytes + 128;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (!attr) {
+            CUDA_TRY(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr = true;
+        }
+    }
+    p.n_colblocks = p.ntaps * p.q_chunks;
+    p.cb_per_group = p.n_colblocks < 8 ? p.n_colblocks : 8;
+    p.n_groups = (p.n_colblocks + p.cb_per_group - 1) / p.cb_per_group;
+    p.p_tiles = (p.p_extent + 127) / 128;
+    const long long base_ctas = (long long)p.n_groups * p.p_tiles;
+    const long long nbricks = (long long)p.nbw * p.nbh * p.nbd * p.nbatch;
+    long long splits = (2LL * sms + base_ctas - 1) / base_ctas;  // about two waves of CTAs
+    if (splits > nbricks) splits = nbricks;
+    if (splits < 1) splits = 1;
+    p.splits = (int)splits;
+    const long long grid = base_ctas * splits;
+    wgrad_kernel<<<(int)grid, kThreads, smem, s>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b200_conv3d_wgrad(const b200_act* x, const b200_act* dy, float* dw, int cin_real, void* stream) {
+    CHECK_VIEW(x);
+    CHECK_VIEW(dy);
+    REQUIRE(dw != nullptr, "conv3d_wgrad: null dw");
+    REQUIRE(x->n == dy->n && x->d == dy->d && x->h == dy->h && x->w == dy->w, "conv3d_wgrad: extent mismatch");
+    REQUIRE(cin_real > 0 && cin_real <= x->c, "conv3d_wgrad: cin_real out of range");
+    int rc = get_encode();
+    if (rc) return rc;
+    WgradParams p;
+    memset(&p, 0, sizeof(p));
+    const Brick b = choose_brick(x->w, x->h, x->d);
+    // dw[co, ci, t] = sum_v dy[v, co] * x[v + off(t), ci]   (P = dy unshifted, Q_t = x shifted by off(t))
+    rc = make_act_map(&p.p_map, reinterpret_cast<const __nv_bfloat16*>(dy->ptr), dy->c, dy->w, dy->h, dy->d, dy->n,
+                      dy->ld, dy->w, dy->h, dy->d, 1, b.tw, b.th, b.td);
+    if (rc) return rc;
+    rc = make_act_map(&p.q_map[0], reinterpret_cast<const __nv_bfloat16*>(x->ptr), x->c, x->w, x->h, x->d, x->n,
+                      x->ld, x->w, x->h, x->d, 1, b.tw, b.th, b.td);
+    if (rc) return rc;
+    p.ntaps = 27;
+    for (int t = 0; t < 27; ++t) {
+        p.q_map_of_tap[t] = 0;
+        p.tap_dd[t] = t / 9 - 1;
+        p.tap_dh[t] = (t / 3) % 3 - 1;
+        p.tap_dw[t] = t % 3 - 1;
+    }
+    p.p_extent = (int)dy->c;
+    p.q_extent = cin_real;
+    p.q_chunks = (cin_real + 63) / 64;
+    p.nbw = (int)b.nbw; p.nbh = (int)b.nbh; p.nbd = (int)b.nbd; p.nbatch = (int)x->n;
+    p.tw = b.tw; p.th = b.th; p.td = b.td;
+    p.out = dw;
+    p.st = 1;
+    p.sp = (long long)cin_real * 27;
+    p.sq = 27;
+    return launch_wgrad(p, (cudaStream_t)stream);
+}
+
+extern "C" int b200_convt2x_wgrad(const b200_act* x, const b200_act* dy, int pad_d, int pad_h, int pad_w, float* dw,
+                                  void* stream) {
+    CHECK_VIEW(x);
+    CHECK_VIEW(dy);
+    REQUIRE(dw != nullptr, "convt2x_wgrad: null dw");
+    int rc = check_convt(x, dy, pad_d, pad_h, pad_w, "convt2x_wgrad");
+    if (rc) return rc;
+    rc = get_encode();
+    if (rc) return rc;
+    WgradParams p;
+    memset(&p, 0, sizeof(p));
+    const Brick b = choose_brick(x->w, x->h, x->d);
+    // dw[ci, co, t] = sum_v x[v, ci] * dy[2v + t + pad, co]
+    rc = make_act_map(&p.p_map, reinterpret_cast<const __nv_bfloat16*>(x->ptr), x->c, x->w, x->h, x->d, x->n, x->ld,
+                      x->w, x->h, x->d, 1, b.tw, b.th, b.td);
+    if (rc) return rc;
+    const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(dy->ptr);
+    for (int t = 0; t < 8; ++t) {
+        const long long od = pad_d + ((t >> 2) & 1), oh = pad_h + ((t >> 1) & 1), ow = pad_w + (t & 1);
+        const __nv_bfloat16* bt = base + ((od * dy->h + oh) * dy->w + ow) * dy->ld;
+        rc = make_act_map(&p.q_map[t], bt, dy->c, x->w, x->h, x->d, x->n, dy->ld, dy->w, dy->h, dy->d, 2, b.tw, b.th,
+                          b.td);
+        if (rc) return rc;
+        p.q_map_of_tap[t] = t;
+    }
+    p.ntaps = 8;
+    p.p_extent = (int)x->c;
+    p.q_extent = (int)dy->c;
+    p.q_chunks = (int)((dy->c + 63) / 64);
+    p.nbw = (int)b.nbw; p.nbh = (int)b.nbh; p.nbd = (int)b.nbd; p.nbatch = (int)x->n;
+    p.tw = b.tw; p.th = b.th; p.td = b.td;
+    p.out = dw;
+    p.st = 1;
+    p.sp = dy->c * 8;
+    p.sq = 8;
+    return launch_wgrad(p, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------ bandwidth ops
+extern "C" int b200_pack_input(const float* x, int64_t n, int64_t c, int64_t d, int64_t h, int64_t w,
+                               const b200_act* out, void* stream) {
+    CHECK_VIEW(out);
+    REQUIRE(x != nullptr, "pack_input: null input");
+    REQUIRE(out->n == n && out->d == d && out->h == h && out->w == w && out->c >= c, "pack_input: extent mismatch");
+    CUDA_TRY(launch_pack_input(x, n, c, d, h, w, to_view(out), (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int b200_pack_conv_weight(const float* w, int cout, int cin, int cin_pad, void* w_fprop, void* w_dgrad,
+                                     void* stream) {
+    REQUIRE(w && cout > 0 && cin > 0 && cin_pad >= cin, "pack_conv_weight: bad arguments");
+    CUDA_TRY(launch_pack_conv_weight(w, cout, cin, cin_pad, reinterpret_cast<__nv_bfloat16*>(w_fprop),
+                                     reinterpret_cast<__nv_bfloat16*>(w_dgrad), (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int b200_pack_convt_weight(const float* w, const float* bias, int cin, int cout, void* w_fwd,
+                                      void* w_dgrad, float* bias8, void* stream) {
+    REQUIRE(w && bias && w_fwd && w_dgrad && bias8 && cin > 0 && cout > 0, "pack_convt_weight: bad arguments");
+    CUDA_TRY(launch_pack_convt_weight(w, bias, cin, cout, reinterpret_cast<__nv_bfloat16*>(w_fwd),
+                                      reinterpret_cast<__nv_bfloat16*>(w_dgrad), bias8, (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int b200_bn_finalize(const float* stats_partial, int64_t rows, int64_t count, int c, const float* gamma,
+                                const float* beta, float eps, float momentum, float* running_mean,
+                                float* running_var, float* mean, float* rstd, float* scale, float* shift,
+                                void* stream) {
+    REQUIRE(stats_partial && gamma && beta && mean && rstd && scale && shift && rows > 0 && count > 0 && c > 0,
+            "bn_finalize: bad arguments");
+    CUDA_TRY(launch_bn_finalize(stats_partial, rows, count, c, gamma, beta, eps, momentum, running_mean, running_var,
+                                mean, rstd, scale, shift, (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int b200_bn_fold_eval(const float* gamma, const float* beta, const float* running_mean,
+                                 const float* running_var, const float* conv_bias, float eps, int c, float* scale,
+                                 float* shift, void* stream) {
+    REQUIRE(gamma && beta && running_mean && running_var && scale && shift && c > 0, "bn_fold_eval: bad arguments");
+    CUDA_TRY(launch_bn_fold_eval(gamma, beta, running_mean, running_var, conv_bias, eps, c, scale, shift,
+                                 (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int b200_bn_apply_relu(const b200_act* y, const float* scale, const float* shift, const b200_act* out,
+                                  void* stream) {
+    CHECK_VIEW(y);
+    CHECK_VIEW(out);
+    REQUIRE(scale && shift, "bn_apply_relu: null scale/shift");
+    REQUIRE(y->n == out->n && y->d == out->d && y->h == out->h && y->w == out->w && y->c == out->c,
+            "bn_apply_relu: extent mismatch");
+    CUDA_TRY(launch_bn_apply_relu(to_view(y), scale, shift, to_view(out), sm_count(), (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int b200_bn_bwd_max_blocks(void) { return kBwdMaxBlocks; }
+extern "C" int b200_bn_bwd_reduce(const b200_act* dout, const b200_act* y, const float* scale, const float* shift,
+                                  const float* mean, const float* rstd, float* partial, int* nblk, void* stream) {
+    CHECK_VIEW(dout);
+    CHECK_VIEW(y);
+    REQUIRE(scale && shift && mean && rstd && partial && nblk, "bn_bwd_reduce: null argument");
+    REQUIRE(dout->c == y->c && dout->n == y->n && dout->d == y->d && dout->h == y->h && dout->w == y->w,
+            "bn_bwd_reduce: extent mismatch");
+    CUDA_TRY(launch_bn_bwd_reduce(to_view(dout), to_view(y), scale, shift, mean, rstd, partial, nblk,
+                                  (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int b200_bn_bwd_finalize(const float* partial, int nblk, int c, int64_t count, float* dgamma,
+                                    float* dbeta, float* coef, void* stream) {
+    REQUIRE(partial && coef && nblk > 0 && c > 0 && count > 0, "bn_bwd_finalize: bad arguments");
+    CUDA_TRY(launch_bn_bwd_finalize(partial, nblk, c, count, dgamma, dbeta, coef, (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int b200_bn_bwd_apply(const b200_act* dout, const b200_act* y, const float* scale, const float* shift,
+                                 const float* mean, const float* rstd, const float* gamma, const float* coef,
+                                 const b200_act* dy, float* dbias, void* stream) {
+    (void)gamma;  // gamma * rstd == scale
+    CHECK_VIEW(dout);
+    CHECK_VIEW(y);
+    CHECK_VIEW(dy);
+    REQUIRE(scale && shift && mean && rstd && coef, "bn_bwd_apply: null argument");
+    REQUIRE(dout->c == y->c && dy->c == y->c && dy->n == y->n && dy->d == y->d && dy->h == y->h && dy->w == y->w,
+            "bn_bwd_apply: extent mismatch");
+    CUDA_TRY(launch_bn_bwd_apply(to_view(dout), to_view(y), scale, shift, mean, rstd, coef, to_view(dy), dbias,
+                                 (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int b200_maxpool3d_fwd(const b200_act* x, const b200_act* y, void* stream) {
+    CHECK_VIEW(x);
+    CHECK_VIEW(y);
+    REQUIRE(y->n == x->n && y->c == x->c && y->d == x->d / 2 && y->h == x->h / 2 && y->w == x->w / 2,
+            "maxpool3d_fwd: output extent must be floor(input/2)");
+    CUDA_TRY(launch_maxpool_fwd(to_view(x), to_view(y), sm_count(), (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int b200_maxpool3d_bwd(const b200_act* x, const b200_act* y, const b200_act* dy, const b200_act* dskip,
+                                  const b200_act* dx, void* stream) {
+    (void)y;  // the window maximum is recomputed from x
+    CHECK_VIEW(x);
+    CHECK_VIEW(dy);
+    CHECK_VIEW(dx);
+    REQUIRE(dy->n == x->n && dy->c == x->c && dy->d == x->d / 2 && dy->h == x->h / 2 && dy->w == x->w / 2,
+            "maxpool3d_bwd: dy extent must be floor(input/2)");
+    REQUIRE(dx->n == x->n && dx->c == x->c && dx->d == x->d && dx->h == x->h && dx->w == x->w,
+            "maxpool3d_bwd: dx extent mismatch");
+    View sk;
+    if (dskip) {
+        CHECK_VIEW(dskip);
+        REQUIRE(dskip->c == x->c && dskip->d == x->d && dskip->h == x->h && dskip->w == x->w,
+                "maxpool3d_bwd: dskip extent mismatch");
+        sk = to_view(dskip);
+    }
+    CUDA_TRY(launch_maxpool_bwd(to_view(x), to_view(dy), dskip ? &sk : nullptr, to_view(dx), sm_count(),
+                                (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int b200_head_fwd(const b200_act* x, const float* w, const float* b, int ncls, float* logits,
+                             float* probs, void* stream) {
+    CHECK_VIEW(x);
+    REQUIRE(w && b && logits, "head_fwd: null argument");
+    REQUIRE(ncls >= 1 && ncls <= 8 && x->c <= 256, "head_fwd: supports 1..8 classes and <= 256 channels");
+    CUDA_TRY(launch_head_fwd(to_view(x), w, b, ncls, logits, probs, (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int b200_head_bwd(const b200_act* x, const float* w, int ncls, const float* dlogits, const b200_act* dx,
+                             float* dw, float* db, void* stream) {
+    CHECK_VIEW(x);
+    CHECK_VIEW(dx);
+    REQUIRE(w && dlogits && dw && db, "head_bwd: null argument");
+    REQUIRE(ncls >= 1 && ncls <= 4, "head_bwd: supports 1..4 classes");
+    REQUIRE(dx->c == x->c, "head_bwd: channel mismatch");
+    CUDA_TRY(launch_head_bwd(to_view(x), w, ncls, dlogits, to_view(dx), dw, db, (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int b200_loss_fwd(const float* logits, const float* target, int64_t n, float bce_w, float dice_w,
+                             float smooth, float* workspace, float* sums, float* loss, void* stream) {
+    REQUIRE(logits && target && workspace && sums && loss && n > 0, "loss_fwd: bad arguments");
+    REQUIRE(((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(target)) & 15) == 0,
+            "loss_fwd: logits/target must be 16-byte aligned");
+    CUDA_TRY(launch_loss_fwd(logits, target, n, bce_w, dice_w, smooth, workspace, sums, loss, sm_count(),
+                             (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int b200_loss_bwd(const float* logits, const float* target, int64_t n, float bce_w, float dice_w,
+                             float smooth, const float* sums, const float* gout, float* dlogits, void* stream) {
+    REQUIRE(logits && target && sums && gout && dlogits && n > 0, "loss_bwd: bad arguments");
+    CUDA_TRY(launch_loss_bwd(logits, target, n, bce_w, dice_w, smooth, sums, gout, dlogits, sm_count(),
+                             (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int b200_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                              float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
+                              float grad_scale, const float* found_inf, void* stream) {
+    REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, "adam_step: bad arguments");
+    REQUIRE(((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) |
+              reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) == 0,
+            "adam_step: buffers must be 16-byte aligned");
+    CUDA_TRY(launch_adam(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale,
+                         found_inf, sm_count(), (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int b200_sumsq(const float* x, int64_t n, float* out, void* stream) {
+    REQUIRE(x && out && n > 0, "sumsq: bad arguments");
+    CUDA_TRY(launch_sumsq(x, n, out, sm_count(), (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int b200_fill_zero(const b200_act* v, void* stream) {
+    CHECK_VIEW(v);
+    CUDA_TRY(launch_fill_zero(to_view(v), sm_count(), (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int b200_channel_sum(const b200_act* v, float* out, void* stream) {
+    CHECK_VIEW(v);
+    REQUIRE(out, "channel_sum: null output");
+    CUDA_TRY(launch_channel_sum(to_view(v), out, (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int b200_unpack_act(const b200_act* v, float* out, void* stream) {
+    CHECK_VIEW(v);
+    REQUIRE(out, "unpack_act: null output");
+    CUDA_TRY(launch_unpack_act(to_view(v), out, (cudaStream_t)stream));
+    return 0;
+}

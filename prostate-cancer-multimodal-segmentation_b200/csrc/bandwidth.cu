@@ -1,0 +1,883 @@
+// HBM-bound kernels of the 3D U-Net hot path (sm_100a): BatchNorm finalize / apply / backward, ReLU, MaxPool3d,
+// 1x1x1 head, sigmoid-BCE+Dice loss, fused Adam, layout packing.  All of them stream NDHWC bf16 activations with
+// 16-byte vector accesses (8 channels per thread), grid sized in multiples of the SM count, fp32 arithmetic.
+//
+// Reference call sites replaced: nn.BatchNorm3d / nn.ReLU (models/unet3d.py:31-33,37-39), nn.MaxPool3d(2) (:80),
+// outc Conv3d k=1 (:222), DiceLoss / BCEDiceLoss (utils/losses.py:44-92,107-152), optim.Adam (utils/trainer.py:113).
+#include "bandwidth.cuh"
+
+namespace b200 {
+
+#define DEV __device__ __forceinline__
+
+struct alignas(16) Bf8 {
+    __nv_bfloat162 v[4];
+};
+
+DEV Bf8 ld8(const __nv_bfloat16* p) {
+    Bf8 r;
+    *reinterpret_cast<uint4*>(&r) = __ldg(reinterpret_cast<const uint4*>(p));
+    return r;
+}
+DEV Bf8 ld8_stream(const __nv_bfloat16* p) {
+    Bf8 r;
+    uint4 u;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+                 : "l"(p));
+    *reinterpret_cast<uint4*>(&r) = u;
+    return r;
+}
+DEV void st8(__nv_bfloat16* p, const Bf8& v) { *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(&v); }
+DEV void unpack8(const Bf8& b, float (&f)[8]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 t = __bfloat1622float2(b.v[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+DEV Bf8 pack8(const float (&f)[8]) {
+    Bf8 b;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) b.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    return b;
+}
+DEV void ldf8(const float* p, float (&f)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+    f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+static int grid_for(long long work_items, int threads, int sms, int waves) {
+    long long blocks = (work_items + threads - 1) / threads;
+    const long long cap = (long long)sms * waves;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+// ------------------------------------------------------------------------------------------------ pack input
+__global__ void pack_input_kernel(const float* __restrict__ x, long long nvox_per_n, int c_in, View out) {
+    const long long total = out.n * nvox_per_n;
+    for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < total;
+         v += (long long)gridDim.x * blockDim.x) {
+        const long long nb = v / nvox_per_n, sp = v - nb * nvox_per_n;
+        const float* src = x + nb * c_in * nvox_per_n + sp;
+        __nv_bfloat16* dst = out.p + v * out.ld;
+        for (int c0 = 0; c0 < (int)out.c; c0 += 8) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = (c0 + j < c_in) ? __ldg(src + (long long)(c0 + j) * nvox_per_n) : 0.f;
+            st8(dst + c0, pack8(f));
+        }
+    }
+}
+cudaError_t launch_pack_input(const float* x, long long n, long long c, long long d, long long h, long long w,
+                              View out, cudaStream_t s) {
+    const long long total = n * d * h * w;
+    pack_input_kernel<<<grid_for(total, 256, 148, 16), 256, 0, s>>>(x, d * h * w, (int)c, out);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ pack weights
+// one block = 32 output channels x 32 input channels x 27 taps staged through shared memory
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, int cout, int cin, int cin_pad,
+                                        __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd) {
+    extern __shared__ float tile[];  // [32 co][32 ci][27]
+    const int co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
+    const int tid = threadIdx.x;
+    for (int r = 0; r < 32; ++r) {
+        const int co = co0 + r;
+        for (int i = tid; i < 32 * 27; i += blockDim.x) {
+            const int ci = ci0 + i / 27;
+            float v = 0.f;
+            if (co < cout && ci < cin) v = __ldg(w + ((long long)co * cin + ci0) * 27 + i);
+            tile[r * 864 + i] = v;
+        }
+    }
+    __syncthreads();
+    const int lane = tid & 31, wrp = tid >> 5, nw = blockDim.x >> 5;
+    if (wf) {  // [27][cout][cin_pad], ci contiguous
+        for (int job = wrp; job < 27 * 32; job += nw) {
+            const int t = job / 32, r = job - t * 32;
+            const int co = co0 + r, ci = ci0 + lane;
+            if (co < cout && ci < cin_pad)
+                wf[((long long)t * cout + co) * cin_pad + ci] = __float2bfloat16_rn(tile[r * 864 + lane * 27 + t]);
+        }
+    }
+    if (wd) {  // [27][cin_pad][cout], co contiguous
+        for (int job = wrp; job < 27 * 32; job += nw) {
+            const int t = job / 32, r = job - t * 32;
+            const int ci = ci0 + r, co = co0 + lane;
+            if (co < cout && ci < cin_pad)
+                wd[((long long)t * cin_pad + ci) * cout + co] = __float2bfloat16_rn(tile[lane * 864 + r * 27 + t]);
+        }
+    }
+}
+cudaError_t launch_pack_conv_weight(const float* w, int cout, int cin, int cin_pad, __nv_bfloat16* wf,
+                                    __nv_bfloat16* wd, cudaStream_t s) {
+    const int smem = 32 * 32 * 27 * 4;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e =
+            cudaFuncSetAttribute(pack_conv_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    dim3 grid((cin_pad + 31) / 32, (cout + 31) / 32);
+    pack_conv_weight_kernel<<<grid, 256, smem, s>>>(w, cout, cin, cin_pad, wf, wd);
+    return cudaGetLastError();
+}
+
+// w (cin, cout, 8) -> wf [8*cout][cin] (ci contiguous), wd [8][cin][cout] (co contiguous)
+__global__ void pack_convt_weight_kernel(const float* __restrict__ w, const float* __restrict__ bias, int cin,
+                                         int cout, __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd,
+                                         float* __restrict__ bias8) {
+    const long long total = (long long)cin * cout * 8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        {  // wf index: (t, co, ci)
+            const int ci = (int)(i % cin);
+            const long long r = i / cin;
+            const int co = (int)(r % cout), t = (int)(r / cout);
+            wf[i] = __float2bfloat16_rn(__ldg(w + ((long long)ci * cout + co) * 8 + t));
+        }
+        {  // wd index: (t, ci, co)
+            const int co = (int)(i % cout);
+            const long long r = i / cout;
+            const int ci = (int)(r % cin), t = (int)(r / cin);
+            wd[i] = __float2bfloat16_rn(__ldg(w + ((long long)ci * cout + co) * 8 + t));
+        }
+        if (i < 8LL * cout) bias8[i] = __ldg(bias + (i % cout));
+    }
+}
+cudaError_t launch_pack_convt_weight(const float* w, const float* bias, int cin, int cout, __nv_bfloat16* wf,
+                                     __nv_bfloat16* wd, float* bias8, cudaStream_t s) {
+    pack_convt_weight_kernel<<<grid_for((long long)cin * cout * 8, 256, 148, 8), 256, 0, s>>>(w, bias, cin, cout, wf,
+                                                                                             wd, bias8);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ BN finalize
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int rows, double inv_count, double unbias,
+                                   int c, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float momentum, float* rm, float* rv, float* mean, float* rstd, float* scale,
+                                   float* shift) {
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= c) return;
+    double s = 0.0, q = 0.0;
+    for (int r = 0; r < rows; ++r) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(partial) + (long long)r * c + ch);
+        s += v.x;
+        q += v.y;
+    }
+    const double mu = s * inv_count;
+    double var = q * inv_count - mu * mu;
+    if (var < 0.0) var = 0.0;
+    const float rs = (float)(1.0 / sqrt(var + (double)eps));
+    const float muf = (float)mu;
+    mean[ch] = muf;
+    rstd[ch] = rs;
+    const float sc = gamma[ch] * rs;
+    scale[ch] = sc;
+    shift[ch] = beta[ch] - muf * sc;
+    if (rm) rm[ch] = (1.f - momentum) * rm[ch] + momentum * muf;
+    if (rv) rv[ch] = (1.f - momentum) * rv[ch] + momentum * (float)(var * unbias);
+}
+cudaError_t launch_bn_finalize(const float* partial, long long rows, long long count, int c, const float* gamma,
+                               const float* beta, float eps, float momentum, float* rm, float* rv, float* mean,
+                               float* rstd, float* scale, float* shift, cudaStream_t s) {
+    const double unbias = count > 1 ? (double)count / (double)(count - 1) : 1.0;
+    bn_finalize_kernel<<<(c + 127) / 128, 128, 0, s>>>(partial, (int)rows, 1.0 / (double)count, unbias, c, gamma,
+                                                      beta, eps, momentum, rm, rv, mean, rstd, scale, shift);
+    return cudaGetLastError();
+}
+
+__global__ void bn_fold_eval_kernel(const float* gamma, const float* beta, const float* rm, const float* rv,
+                                    const float* cbias, float eps, int c, float* scale, float* shift) {
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= c) return;
+    const float sc = gamma[ch] / sqrtf(rv[ch] + eps);
+    scale[ch] = sc;
+    shift[ch] = beta[ch] + ((cbias ? cbias[ch] : 0.f) - rm[ch]) * sc;
+}
+cudaError_t launch_bn_fold_eval(const float* gamma, const float* beta, const float* rm, const float* rv,
+                                const float* cbias, float eps, int c, float* scale, float* shift, cudaStream_t s) {
+    bn_fold_eval_kernel<<<(c + 127) / 128, 128, 0, s>>>(gamma, beta, rm, rv, cbias, eps, c, scale, shift);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ BN apply + ReLU
+__global__ void __launch_bounds__(256) bn_apply_relu_kernel(View y, const float* __restrict__ scale,
+                                                            const float* __restrict__ shift, View out, FastDiv c8d,
+                                                            uint32_t total) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t vox = c8d.quot(i);
+        const uint32_t c0 = (i - vox * c8d.div) * 8;
+        float f[8], sc[8], sh[8];
+        unpack8(ld8_stream(y.p + (long long)vox * y.ld + c0), f);
+        ldf8(scale + c0, sc);
+        ldf8(shift + c0, sh);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
+        st8(out.p + (long long)vox * out.ld + c0, pack8(f));
+    }
+}
+cudaError_t launch_bn_apply_relu(View y, const float* scale, const float* shift, View out, int sms, cudaStream_t s) {
+    const long long total = y.voxels() * (y.c / 8);
+    if (total >= (1LL << 31)) return cudaErrorInvalidValue;
+    bn_apply_relu_kernel<<<grid_for(total, 256, sms, 16), 256, 0, s>>>(y, scale, shift, out,
+                                                                      FastDiv((uint32_t)(y.c / 8)), (uint32_t)total);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ channel-lane skeleton
+// 256 threads = rows x c8 lanes; a thread owns 8 fixed channels and walks voxels, so per-channel sums stay in
+// registers; one shared-memory reduction per block at the end.
+struct LaneMap {
+    int c8, rows;
+};
+static LaneMap lane_map(long long c) {
+    LaneMap m;
+    m.c8 = (int)(c / 8);
+    m.rows = 256 / m.c8;
+    return m;
+}
+
+template <int NACC>
+DEV void block_reduce_store(float (&acc)[NACC][8], int c8, int rows, int row, int cv, bool active, float* smem,
+                            float* dst /* [c][NACC] or atomics */, int c, bool atomic) {
+    // smem [rows][c8][NACC*8]
+    if (active) {
+#pragma unroll
+        for (int a = 0; a < NACC; ++a)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) smem[((row * c8 + cv) * NACC + a) * 8 + j] = acc[a][j];
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < c * NACC; t += blockDim.x) {
+        const int ch = t / NACC, a = t - ch * NACC;
+        const int cvv = ch >> 3, j = ch & 7;
+        float s = 0.f;
+        for (int r = 0; r < rows; ++r) s += smem[((r * c8 + cvv) * NACC + a) * 8 + j];
+        if (atomic)
+            atomicAdd(dst + ch * NACC + a, s);
+        else
+            dst[ch * NACC + a] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ BN backward
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(View dout, View y, const float* __restrict__ scale,
+                                                            const float* __restrict__ shift,
+                                                            const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, float* partial, int c8,
+                                                            int rows, long long nvox) {
+    extern __shared__ float smem[];
+    const int row = threadIdx.x / c8, cv = threadIdx.x - row * c8;
+    const bool active = row < rows;
+    float acc[2][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+    if (active) {
+        float sc[8], sh[8], mu[8], rs[8];
+        ldf8(scale + cv * 8, sc);
+        ldf8(shift + cv * 8, sh);
+        ldf8(mean + cv * 8, mu);
+        ldf8(rstd + cv * 8, rs);
+        for (long long v = (long long)blockIdx.x * rows + row; v < nvox; v += (long long)gridDim.x * rows) {
+            float g[8], x[8];
+            unpack8(ld8_stream(dout.p + v * dout.ld + cv * 8), g);
+            unpack8(ld8_stream(y.p + v * y.ld + cv * 8), x);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float gm = fmaf(x[j], sc[j], sh[j]) > 0.f ? g[j] : 0.f;
+                acc[0][j] += gm;
+                acc[1][j] += gm * ((x[j] - mu[j]) * rs[j]);
+            }
+        }
+    }
+    block_reduce_store<2>(acc, c8, rows, row, cv, active, smem, partial + (long long)blockIdx.x * y.c * 2, (int)y.c,
+                          false);
+}
+cudaError_t launch_bn_bwd_reduce(View dout, View y, const float* scale, const float* shift, const float* mean,
+                                 const float* rstd, float* partial, int* nblk, cudaStream_t s) {
+    const LaneMap m = lane_map(y.c);
+    const long long nvox = y.voxels();
+    long long blocks = (nvox + m.rows * 8LL - 1) / (m.rows * 8LL);
+    if (blocks > kBwdMaxBlocks) blocks = kBwdMaxBlocks;
+    if (blocks < 1) blocks = 1;
+    *nblk = (int)blocks;
+    const size_t smem = (size_t)m.rows * m.c8 * 16 * sizeof(float);
+    bn_bwd_reduce_kernel<<<(int)blocks, 256, smem, s>>>(dout, y, scale, shift, mean, rstd, partial, m.c8, m.rows,
+                                                       nvox);
+    return cudaGetLastError();
+}
+
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int c, double inv_count,
+                                       float* dgamma, float* dbeta, float* coef) {
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= c) return;
+    double s1 = 0.0, s2 = 0.0;
+    for (int b = 0; b < nblk; ++b) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(partial) + (long long)b * c + ch);
+        s1 += v.x;
+        s2 += v.y;
+    }
+    if (dbeta) dbeta[ch] += (float)s1;
+    if (dgamma) dgamma[ch] += (float)s2;
+    coef[2 * ch] = (float)(s1 * inv_count);
+    coef[2 * ch + 1] = (float)(s2 * inv_count);
+}
+cudaError_t launch_bn_bwd_finalize(const float* partial, int nblk, int c, long long count, float* dgamma,
+                                   float* dbeta, float* coef, cudaStream_t s) {
+    bn_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, s>>>(partial, nblk, c, 1.0 / (double)count, dgamma, dbeta, coef);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(View dout, View y, const float* __restrict__ scale,
+                                                           const float* __restrict__ shift,
+                                                           const float* __restrict__ mean,
+                                                           const float* __restrict__ rstd,
+                                                           const float* __restrict__ coef, View dy, float* dbias,
+                                                           int c8, int rows, long long nvox) {
+    extern __shared__ float smem[];
+    const int row = threadIdx.x / c8, cv = threadIdx.x - row * c8;
+    const bool active = row < rows;
+    float acc[1][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[0][j] = 0.f;
+    if (active) {
+        float sc[8], sh[8], mu[8], rs[8], k0[8], k1[8];
+        ldf8(scale + cv * 8, sc);
+        ldf8(shift + cv * 8, sh);
+        ldf8(mean + cv * 8, mu);
+        ldf8(rstd + cv * 8, rs);
+        {
+            float t[8], u[8];
+            ldf8(coef + cv * 16, t);
+            ldf8(coef + cv * 16 + 8, u);
+            k0[0] = t[0]; k1[0] = t[1]; k0[1] = t[2]; k1[1] = t[3]; k0[2] = t[4]; k1[2] = t[5]; k0[3] = t[6]; k1[3] = t[7];
+            k0[4] = u[0]; k1[4] = u[1]; k0[5] = u[2]; k1[5] = u[3]; k0[6] = u[4]; k1[6] = u[5]; k0[7] = u[6]; k1[7] = u[7];
+        }
+        for (long long v = (long long)blockIdx.x * rows + row; v < nvox; v += (long long)gridDim.x * rows) {
+            float g[8], x[8], o[8];
+            unpack8(ld8_stream(dout.p + v * dout.ld + cv * 8), g);
+            unpack8(ld8_stream(y.p + v * y.ld + cv * 8), x);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float gm = fmaf(x[j], sc[j], sh[j]) > 0.f ? g[j] : 0.f;
+                const float xh = (x[j] - mu[j]) * rs[j];
+                o[j] = sc[j] * (gm - k0[j] - xh * k1[j]);
+            }
+            const Bf8 ob = pack8(o);
+            st8(dy.p + v * dy.ld + cv * 8, ob);
+            float r[8];
+            unpack8(ob, r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[0][j] += r[j];
+        }
+    }
+    if (dbias) block_reduce_store<1>(acc, c8, rows, row, cv, active, smem, dbias, (int)y.c, true);
+}
+cudaError_t launch_bn_bwd_apply(View dout, View y, const float* scale, const float* shift, const float* mean,
+                                const float* rstd, const float* coef, View dy, float* dbias, cudaStream_t s) {
+    const LaneMap m = lane_map(y.c);
+    const long long nvox = y.voxels();
+    long long blocks = (nvox + m.rows * 8LL - 1) / (m.rows * 8LL);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    const size_t smem = (size_t)m.rows * m.c8 * 8 * sizeof(float);
+    bn_bwd_apply_kernel<<<(int)blocks, 256, smem, s>>>(dout, y, scale, shift, mean, rstd, coef, dy, dbias, m.c8, m.rows,
+                                                      nvox);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ channel sum
+__global__ void __launch_bounds__(256) channel_sum_kernel(View v, float* out, int c8, int rows, long long nvox) {
+    extern __shared__ float smem[];
+    const int row = threadIdx.x / c8, cv = threadIdx.x - row * c8;
+    const bool active = row < rows;
+    float acc[1][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[0][j] = 0.f;
+    if (active) {
+        for (long long i = (long long)blockIdx.x * rows + row; i < nvox; i += (long long)gridDim.x * rows) {
+            float x[8];
+            unpack8(ld8_stream(v.p + i * v.ld + cv * 8), x);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[0][j] += x[j];
+        }
+    }
+    block_reduce_store<1>(acc, c8, rows, row, cv, active, smem, out, (int)v.c, true);
+}
+cudaError_t launch_channel_sum(View v, float* out, cudaStream_t s) {
+    const LaneMap m = lane_map(v.c);
+    const long long nvox = v.voxels();
+    long long blocks = (nvox + m.rows * 8LL - 1) / (m.rows * 8LL);
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    if (blocks < 1) blocks = 1;
+    const size_t smem = (size_t)m.rows * m.c8 * 8 * sizeof(float);
+    channel_sum_kernel<<<(int)blocks, 256, smem, s>>>(v, out, m.c8, m.rows, nvox);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ MaxPool3d(2)
+// torch semantics: window max with NaN propagation; backward routes the gradient to the first maximum in
+// d, h, w scan order (ATen max_pool3d_with_indices: `val > max || isnan(val)` keeps the earliest equal value).
+DEV __nv_bfloat162 max2_nan(__nv_bfloat162 a, __nv_bfloat162 b) { return __hmax2_nan(a, b); }
+
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(View x, View y, FastDiv c8d, FastDiv owd, FastDiv ohd,
+                                                          FastDiv odd, uint32_t total) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        uint32_t r = c8d.quot(i);
+        const uint32_t c0 = (i - r * c8d.div) * 8;
+        const uint32_t ovox = r;
+        uint32_t q = owd.quot(r);
+        const uint32_t ow = r - q * owd.div;
+        r = q; q = ohd.quot(r);
+        const uint32_t oh = r - q * ohd.div;
+        r = q; q = odd.quot(r);
+        const uint32_t od = r - q * odd.div;
+        const uint32_t nb = q;
+        const long long base = (((long long)nb * x.d + 2 * od) * x.h + 2 * oh) * x.w + 2 * ow;
+        Bf8 m = ld8_stream(x.p + base * x.ld + c0);
+#pragma unroll
+        for (int k = 1; k < 8; ++k) {
+            const long long off = base + ((k >> 2) & 1) * x.h * x.w + ((k >> 1) & 1) * x.w + (k & 1);
+            const Bf8 t = ld8_stream(x.p + off * x.ld + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) m.v[j] = max2_nan(m.v[j], t.v[j]);
+        }
+        st8(y.p + (long long)ovox * y.ld + c0, m);
+    }
+}
+cudaError_t launch_maxpool_fwd(View x, View y, int sms, cudaStream_t s) {
+    const long long total = y.voxels() * (y.c / 8);
+    if (total >= (1LL << 31)) return cudaErrorInvalidValue;
+    if (total == 0) return cudaSuccess;
+    maxpool_fwd_kernel<<<grid_for(total, 256, sms, 16), 256, 0, s>>>(x, y, FastDiv((uint32_t)(y.c / 8)),
+                                                                    FastDiv((uint32_t)y.w), FastDiv((uint32_t)y.h),
+                                                                    FastDiv((uint32_t)y.d), (uint32_t)total);
+    return cudaGetLastError();
+}
+
+// one thread = one 2x2x2 cell of the input grid (cells cover ceil(dim/2)) x 8 channels
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(View x, View dy, View dskip, int has_skip, View dx,
+                                                          FastDiv c8d, FastDiv cwd, FastDiv chd, FastDiv cdd,
+                                                          uint32_t total) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        uint32_t r = c8d.quot(i);
+        const uint32_t c0 = (i - r * c8d.div) * 8;
+        uint32_t q = cwd.quot(r);
+        const uint32_t cw = r - q * cwd.div;
+        r = q; q = chd.quot(r);
+        const uint32_t ch = r - q * chd.div;
+        r = q; q = cdd.quot(r);
+        const uint32_t cd = r - q * cdd.div;
+        const uint32_t nb = q;
+        const bool full = (2 * cd + 1 < x.d) && (2 * ch + 1 < x.h) && (2 * cw + 1 < x.w);
+        float xin[8][8];
+        float g[8];
+        if (full) {
+            const long long ov = (((long long)nb * dy.d + cd) * dy.h + ch) * dy.w + cw;
+            unpack8(ld8_stream(dy.p + ov * dy.ld + c0), g);
+        }
+        float mx[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int kd = (k >> 2) & 1, kh = (k >> 1) & 1, kw = k & 1;
+            if (full) {
+                const long long v = (((long long)nb * x.d + 2 * cd + kd) * x.h + 2 * ch + kh) * x.w + 2 * cw + kw;
+                unpack8(ld8_stream(x.p + v * x.ld + c0), xin[k]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) mx[j] = (k == 0) ? xin[0][j] : fmaxf(mx[j], xin[k][j]);
+            }
+        }
+        bool taken[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) taken[j] = false;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int kd = (k >> 2) & 1, kh = (k >> 1) & 1, kw = k & 1;
+            const uint32_t d = 2 * cd + kd, h = 2 * ch + kh, w = 2 * cw + kw;
+            if (d < x.d && h < x.h && w < x.w) {
+                const long long v = (((long long)nb * x.d + d) * x.h + h) * x.w + w;
+                float o[8];
+                if (has_skip)
+                    unpack8(ld8_stream(dskip.p + v * dskip.ld + c0), o);
+                else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[j] = 0.f;
+                }
+                if (full) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const bool hit = !taken[j] && xin[k][j] == mx[j];
+                        if (hit) { o[j] += g[j]; taken[j] = true; }
+                    }
+                }
+                st8(dx.p + v * dx.ld + c0, pack8(o));
+            }
+        }
+    }
+}
+cudaError_t launch_maxpool_bwd(View x, View dy, const View* dskip, View dx, int sms, cudaStream_t s) {
+    const long long cw = (x.w + 1) / 2, ch = (x.h + 1) / 2, cd = (x.d + 1) / 2;
+    const long long total = x.n * cd * ch * cw * (x.c / 8);
+    if (total >= (1LL << 31)) return cudaErrorInvalidValue;
+    View sk = dskip ? *dskip : dx;
+    maxpool_bwd_kernel<<<grid_for(total, 256, sms, 16), 256, 0, s>>>(
+        x, dy, sk, dskip ? 1 : 0, dx, FastDiv((uint32_t)(x.c / 8)), FastDiv((uint32_t)cw), FastDiv((uint32_t)ch),
+        FastDiv((uint32_t)cd), (uint32_t)total);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ head 1x1x1
+constexpr int kMaxCls = 8;
+constexpr int kMaxHeadC = 256;
+__global__ void __launch_bounds__(256) head_fwd_kernel(View x, const float* __restrict__ w,
+                                                       const float* __restrict__ b, int ncls, float* logits,
+                                                       float* probs, long long nvox_per_n) {
+    __shared__ float ws[kMaxCls * kMaxHeadC];
+    __shared__ float bs[kMaxCls];
+    const int c = (int)x.c;
+    for (int i = threadIdx.x; i < ncls * c; i += blockDim.x) ws[i] = w[i];
+    if (threadIdx.x < ncls) bs[threadIdx.x] = b[threadIdx.x];
+    __syncthreads();
+    const long long total = x.voxels();
+    for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < total;
+         v += (long long)gridDim.x * blockDim.x) {
+        float acc[kMaxCls];
+#pragma unroll
+        for (int k = 0; k < kMaxCls; ++k) acc[k] = 0.f;
+        const __nv_bfloat16* src = x.p + v * x.ld;
+        for (int c0 = 0; c0 < c; c0 += 8) {
+            float f[8];
+            unpack8(ld8_stream(src + c0), f);
+#pragma unroll
+            for (int k = 0; k < kMaxCls; ++k) {
+                if (k < ncls) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[k] = fmaf(f[j], ws[k * c + c0 + j], acc[k]);
+                }
+            }
+        }
+        const long long nb = v / nvox_per_n, sp = v - nb * nvox_per_n;
+#pragma unroll
+        for (int k = 0; k < kMaxCls; ++k) {
+            if (k < ncls) {
+                const float z = acc[k] + bs[k];
+                const long long o = (nb * ncls + k) * nvox_per_n + sp;
+                logits[o] = z;
+                if (probs) probs[o] = 1.f / (1.f + __expf(-z));
+            }
+        }
+    }
+}
+cudaError_t launch_head_fwd(View x, const float* w, const float* b, int ncls, float* logits, float* probs,
+                            cudaStream_t s) {
+    head_fwd_kernel<<<grid_for(x.voxels(), 256, 148, 16), 256, 0, s>>>(x, w, b, ncls, logits, probs,
+                                                                      x.d * x.h * x.w);
+    return cudaGetLastError();
+}
+
+// dx[v, c] = sum_k dl[v,k] w[k,c] ; dw[k,c] += sum_v dl[v,k] x[v,c] ; db[k] += sum_v dl[v,k]
+template <int NCLS>
+__global__ void __launch_bounds__(256) head_bwd_kernel(View x, const float* __restrict__ w,
+                                                       const float* __restrict__ dl, View dx, float* dw, float* db,
+                                                       int c8, int rows, long long nvox, long long nvox_per_n) {
+    extern __shared__ float smem[];
+    const int row = threadIdx.x / c8, cv = threadIdx.x - row * c8;
+    const bool active = row < rows;
+    const int c = (int)x.c;
+    float acc[NCLS][8];
+    float dbacc[NCLS];
+#pragma unroll
+    for (int k = 0; k < NCLS; ++k) {
+        dbacc[k] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
+    }
+    if (active) {
+        float wk[NCLS][8];
+#pragma unroll
+        for (int k = 0; k < NCLS; ++k) ldf8(w + k * c + cv * 8, wk[k]);
+        for (long long v = (long long)blockIdx.x * rows + row; v < nvox; v += (long long)gridDim.x * rows) {
+            const long long nb = v / nvox_per_n, sp = v - nb * nvox_per_n;
+            float g[NCLS];
+#pragma unroll
+            for (int k = 0; k < NCLS; ++k) g[k] = __ldg(dl + (nb * NCLS + k) * nvox_per_n + sp);
+            float a[8], o[8];
+            unpack8(ld8_stream(x.p + v * x.ld + cv * 8), a);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = 0.f;
+#pragma unroll
+            for (int k = 0; k < NCLS; ++k) {
+                if (cv == 0) dbacc[k] += g[k];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    o[j] = fmaf(g[k], wk[k][j], o[j]);
+                    acc[k][j] = fmaf(g[k], a[j], acc[k][j]);
+                }
+            }
+            st8(dx.p + v * dx.ld + cv * 8, pack8(o));
+        }
+    }
+    // reduce dw: smem [rows][c8][NCLS*8]
+    if (active) {
+#pragma unroll
+        for (int k = 0; k < NCLS; ++k)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) smem[((row * c8 + cv) * NCLS + k) * 8 + j] = acc[k][j];
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < c * NCLS; t += blockDim.x) {
+        const int k = t / c, ch = t - k * c;
+        float s = 0.f;
+        for (int r = 0; r < rows; ++r) s += smem[((r * c8 + (ch >> 3)) * NCLS + k) * 8 + (ch & 7)];
+        atomicAdd(dw + k * c + ch, s);
+    }
+    __syncthreads();
+    if (active && cv == 0) {
+#pragma unroll
+        for (int k = 0; k < NCLS; ++k) smem[row * NCLS + k] = dbacc[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < NCLS) {
+        float s = 0.f;
+        for (int r = 0; r < rows; ++r) s += smem[r * NCLS + threadIdx.x];
+        atomicAdd(db + threadIdx.x, s);
+    }
+}
+template <int NCLS>
+static cudaError_t head_bwd_launch(View x, const float* w, const float* dl, View dx, float* dw, float* db,
+                                   cudaStream_t s) {
+    const LaneMap m = lane_map(x.c);
+    const long long nvox = x.voxels();
+    long long blocks = (nvox + m.rows * 8LL - 1) / (m.rows * 8LL);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    const size_t smem = (size_t)m.rows * m.c8 * NCLS * 8 * sizeof(float);
+    head_bwd_kernel<NCLS><<<(int)blocks, 256, smem, s>>>(x, w, dl, dx, dw, db, m.c8, m.rows, nvox, x.d * x.h * x.w);
+    return cudaGetLastError();
+}
+cudaError_t launch_head_bwd(View x, const float* w, int ncls, const float* dlogits, View dx, float* dw, float* db,
+                            cudaStream_t s) {
+    switch (ncls) {
+        case 1: return head_bwd_launch<1>(x, w, dlogits, dx, dw, db, s);
+        case 2: return head_bwd_launch<2>(x, w, dlogits, dx, dw, db, s);
+        case 3: return head_bwd_launch<3>(x, w, dlogits, dx, dw, db, s);
+        case 4: return head_bwd_launch<4>(x, w, dlogits, dx, dw, db, s);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ loss
+DEV float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+DEV float sigmoidf_(float z) { return 1.f / (1.f + expf(-z)); }
+
+__global__ void __launch_bounds__(256) loss_partial_kernel(const float* __restrict__ z, const float* __restrict__ t,
+                                                           long long n, float* ws) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    const long long n4 = n >> 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+         i += (long long)gridDim.x * blockDim.x) {
+        const float4 zz = __ldg(reinterpret_cast<const float4*>(z) + i);
+        const float4 tt = __ldg(reinterpret_cast<const float4*>(t) + i);
+        const float zs[4] = {zz.x, zz.y, zz.z, zz.w}, ts[4] = {tt.x, tt.y, tt.z, tt.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float sg = sigmoidf_(zs[j]);
+            s[0] += fmaxf(zs[j], 0.f) - zs[j] * ts[j] + log1pf(expf(-fabsf(zs[j])));
+            s[1] += sg * ts[j];
+            s[2] += sg;
+            s[3] += ts[j];
+        }
+    }
+    if (blockIdx.x == 0) {
+        for (long long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
+            const float zj = z[i], tj = t[i], sg = sigmoidf_(zj);
+            s[0] += fmaxf(zj, 0.f) - zj * tj + log1pf(expf(-fabsf(zj)));
+            s[1] += sg * tj;
+            s[2] += sg;
+            s[3] += tj;
+        }
+    }
+    __shared__ float red[8][4];
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float v = warp_sum(s[j]);
+        if (lane == 0) red[wrp][j] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        float v = 0.f;
+        for (int k = 0; k < 8; ++k) v += red[k][threadIdx.x];
+        ws[blockIdx.x * 4 + threadIdx.x] = v;
+    }
+}
+__global__ void loss_finalize_kernel(const float* __restrict__ ws, int nblk, double inv_n, float bce_w, float dice_w,
+                                     float smooth, float* sums, float* loss) {
+    __shared__ double red[4][4];
+    const int j = threadIdx.x & 3, part = threadIdx.x >> 2;  // 16 threads: 4 sums x 4 parts
+    double a = 0.0;
+    for (int b = part; b < nblk; b += 4) a += ws[b * 4 + j];
+    red[part][j] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s[4];
+        for (int k = 0; k < 4; ++k) s[k] = red[0][k] + red[1][k] + red[2][k] + red[3][k];
+        for (int k = 0; k < 4; ++k) sums[k] = (float)s[k];
+        const double dice = (2.0 * s[1] + smooth) / (s[2] + s[3] + smooth);
+        loss[0] = (float)(bce_w * s[0] * inv_n + dice_w * (1.0 - dice));
+    }
+}
+cudaError_t launch_loss_fwd(const float* z, const float* t, long long n, float bce_w, float dice_w, float smooth,
+                            float* ws, float* sums, float* loss, int sms, cudaStream_t s) {
+    int blocks = grid_for(n / 4 + 1, 256, sms, 4);
+    if (blocks > kLossMaxBlocks) blocks = kLossMaxBlocks;
+    loss_partial_kernel<<<blocks, 256, 0, s>>>(z, t, n, ws);
+    loss_finalize_kernel<<<1, 16, 0, s>>>(ws, blocks, 1.0 / (double)n, bce_w, dice_w, smooth, sums, loss);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) loss_bwd_kernel(const float* __restrict__ z, const float* __restrict__ t,
+                                                       long long n, float bce_w, float dice_w, float smooth,
+                                                       const float* __restrict__ sums, const float* __restrict__ gout,
+                                                       float* dz) {
+    const float g = gout[0];
+    const float I = sums[1], P = sums[2], T = sums[3];
+    const float B = P + T + smooth, A = 2.f * I + smooth;
+    const float kb = g * bce_w / (float)n;
+    const float k1 = g * dice_w * (-2.f / B), k2 = g * dice_w * (A / (B * B));
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const float zj = __ldg(z + i), tj = __ldg(t + i);
+        const float sg = sigmoidf_(zj);
+        dz[i] = kb * (sg - tj) + sg * (1.f - sg) * (k1 * tj + k2);
+    }
+}
+cudaError_t launch_loss_bwd(const float* z, const float* t, long long n, float bce_w, float dice_w, float smooth,
+                            const float* sums, const float* gout, float* dz, int sms, cudaStream_t s) {
+    loss_bwd_kernel<<<grid_for(n, 256, sms, 8), 256, 0, s>>>(z, t, n, bce_w, dice_w, smooth, sums, gout, dz);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ Adam
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                   float* __restrict__ m, float* __restrict__ v, long long n,
+                                                   float lr, float b1, float b2, float eps, float wd, float bc1,
+                                                   float bc2_sqrt, float gscale, const float* found_inf) {
+    if (found_inf && *found_inf != 0.f) return;
+    const float step_size = lr / bc1;
+    const long long n4 = n >> 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+         i += (long long)gridDim.x * blockDim.x) {
+        float4 pp = reinterpret_cast<float4*>(p)[i];
+        const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + i);
+        float4 mm = reinterpret_cast<float4*>(m)[i];
+        float4 vv = reinterpret_cast<float4*>(v)[i];
+        float* pa = reinterpret_cast<float*>(&pp);
+        const float* ga = reinterpret_cast<const float*>(&gg);
+        float* ma = reinterpret_cast<float*>(&mm);
+        float* va = reinterpret_cast<float*>(&vv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float gr = fmaf(wd, pa[j], ga[j] * gscale);
+            ma[j] = fmaf(b1, ma[j], (1.f - b1) * gr);  // torch: lerp(m, g, 1-b1)
+            va[j] = fmaf(b2, va[j], (1.f - b2) * gr * gr);
+            const float denom = sqrtf(va[j]) / bc2_sqrt + eps;
+            pa[j] -= step_size * (ma[j] / denom);
+        }
+        reinterpret_cast<float4*>(p)[i] = pp;
+        reinterpret_cast<float4*>(m)[i] = mm;
+        reinterpret_cast<float4*>(v)[i] = vv;
+    }
+    if (blockIdx.x == 0) {
+        for (long long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
+            const float gr = fmaf(wd, p[i], g[i] * gscale);
+            m[i] = fmaf(b1, m[i], (1.f - b1) * gr);
+            v[i] = fmaf(b2, v[i], (1.f - b2) * gr * gr);
+            const float denom = sqrtf(v[i]) / bc2_sqrt + eps;
+            p[i] -= step_size * (m[i] / denom);
+        }
+    }
+}
+cudaError_t launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2,
+                        float eps, float wd, long long step, float gscale, const float* found_inf, int sms,
+                        cudaStream_t s) {
+    const double bc1 = 1.0 - pow((double)b1, (double)step);
+    const double bc2 = 1.0 - pow((double)b2, (double)step);
+    adam_kernel<<<grid_for(n / 4 + 1, 256, sms, 8), 256, 0, s>>>(p, g, m, v, n, lr, b1, b2, eps, wd, (float)bc1,
+                                                                (float)sqrt(bc2), gscale, found_inf);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, long long n, float* out) {
+    float s = 0.f;
+    bool bad = false;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const float v = __ldg(x + i);
+        s = fmaf(v, v, s);
+        bad |= !isfinite(v);
+    }
+    s = warp_sum(s);
+    __shared__ float red[8];
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    if (lane == 0) red[wrp] = s;
+    if (__any_sync(0xffffffffu, bad) && lane == 0) out[1] = 1.f;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f;
+        for (int k = 0; k < 8; ++k) a += red[k];
+        atomicAdd(out, a);
+    }
+}
+cudaError_t launch_sumsq(const float* x, long long n, float* out, int sms, cudaStream_t s) {
+    sumsq_kernel<<<grid_for(n, 256, sms, 4), 256, 0, s>>>(x, n, out);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ helpers
+__global__ void __launch_bounds__(256) fill_zero_kernel(View v, FastDiv c8d, uint32_t total) {
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t vox = c8d.quot(i);
+        const uint32_t c0 = (i - vox * c8d.div) * 8;
+        *reinterpret_cast<uint4*>(v.p + (long long)vox * v.ld + c0) = z;
+    }
+}
+cudaError_t launch_fill_zero(View v, int sms, cudaStream_t s) {
+    const long long total = v.voxels() * (v.c / 8);
+    if (total >= (1LL << 31)) return cudaErrorInvalidValue;
+    if (total == 0) return cudaSuccess;
+    fill_zero_kernel<<<grid_for(total, 256, sms, 16), 256, 0, s>>>(v, FastDiv((uint32_t)(v.c / 8)), (uint32_t)total);
+    return cudaGetLastError();
+}
+
+__global__ void unpack_act_kernel(View v, float* out, long long nvox_per_n) {
+    const long long total = v.voxels() * v.c;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        // i indexes the NCDHW output
+        const long long sp = i % nvox_per_n;
+        const long long r = i / nvox_per_n;
+        const long long ch = r % v.c, nb = r / v.c;
+        out[i] = __bfloat162float(v.p[(nb * nvox_per_n + sp) * v.ld + ch]);
+    }
+}
+cudaError_t launch_unpack_act(View v, float* out, cudaStream_t s) {
+    unpack_act_kernel<<<grid_for(v.voxels() * v.c, 256, 148, 16), 256, 0, s>>>(v, out, v.d * v.h * v.w);
+    return cudaGetLastError();
+}
+
+}  // namespace b200

@@ -1,0 +1,70 @@
+// Launch declarations of the HBM-bound kernels (bandwidth.cu), called from api.cu.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200 {
+
+struct View {
+    __nv_bfloat16* p;
+    long long n, d, h, w, c, ld;
+    __host__ __device__ long long voxels() const { return n * d * h * w; }
+};
+
+// 32-bit divide by a runtime constant (numerator < 2^31)
+struct FastDiv {
+    uint32_t div, mul, shr;
+    __host__ FastDiv() : div(1), mul(0), shr(0) {}
+    __host__ explicit FastDiv(uint32_t d) : div(d), mul(0), shr(0) {
+        if (d != 1) {
+            uint32_t lg = 0;
+            while ((1ull << lg) < d) ++lg;
+            const uint32_t pw = 31 + lg;
+            mul = (uint32_t)(((1ull << pw) + d - 1) / d);
+            shr = pw - 32;
+        }
+    }
+    __device__ __forceinline__ uint32_t quot(uint32_t x) const { return div != 1 ? (__umulhi(x, mul) >> shr) : x; }
+};
+
+constexpr int kBwdMaxBlocks = 148 * 4;  // rows of the BatchNorm-backward partial buffer
+constexpr int kLossMaxBlocks = 1024;
+
+cudaError_t launch_pack_input(const float* x, long long n, long long c, long long d, long long h, long long w,
+                              View out, cudaStream_t s);
+cudaError_t launch_pack_conv_weight(const float* w, int cout, int cin, int cin_pad, __nv_bfloat16* wf,
+                                    __nv_bfloat16* wd, cudaStream_t s);
+cudaError_t launch_pack_convt_weight(const float* w, const float* bias, int cin, int cout, __nv_bfloat16* wf,
+                                     __nv_bfloat16* wd, float* bias8, cudaStream_t s);
+cudaError_t launch_bn_finalize(const float* partial, long long m_tiles, long long count, int c, const float* gamma,
+                               const float* beta, float eps, float momentum, float* rm, float* rv, float* mean,
+                               float* rstd, float* scale, float* shift, cudaStream_t s);
+cudaError_t launch_bn_fold_eval(const float* gamma, const float* beta, const float* rm, const float* rv,
+                                const float* cbias, float eps, int c, float* scale, float* shift, cudaStream_t s);
+cudaError_t launch_bn_apply_relu(View y, const float* scale, const float* shift, View out, int sms, cudaStream_t s);
+cudaError_t launch_bn_bwd_reduce(View dout, View y, const float* scale, const float* shift, const float* mean,
+                                 const float* rstd, float* partial, int* nblk, cudaStream_t s);
+cudaError_t launch_bn_bwd_finalize(const float* partial, int nblk, int c, long long count, float* dgamma,
+                                   float* dbeta, float* coef, cudaStream_t s);
+cudaError_t launch_bn_bwd_apply(View dout, View y, const float* scale, const float* shift, const float* mean,
+                                const float* rstd, const float* coef, View dy, float* dbias, cudaStream_t s);
+cudaError_t launch_maxpool_fwd(View x, View y, int sms, cudaStream_t s);
+cudaError_t launch_maxpool_bwd(View x, View dy, const View* dskip, View dx, int sms, cudaStream_t s);
+cudaError_t launch_head_fwd(View x, const float* w, const float* b, int ncls, float* logits, float* probs,
+                            cudaStream_t s);
+cudaError_t launch_head_bwd(View x, const float* w, int ncls, const float* dlogits, View dx, float* dw, float* db,
+                            cudaStream_t s);
+cudaError_t launch_loss_fwd(const float* z, const float* t, long long n, float bce_w, float dice_w, float smooth,
+                            float* ws, float* sums, float* loss, int sms, cudaStream_t s);
+cudaError_t launch_loss_bwd(const float* z, const float* t, long long n, float bce_w, float dice_w, float smooth,
+                            const float* sums, const float* gout, float* dz, int sms, cudaStream_t s);
+cudaError_t launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2,
+                        float eps, float wd, long long step, float gscale, const float* found_inf, int sms,
+                        cudaStream_t s);
+cudaError_t launch_sumsq(const float* x, long long n, float* out, int sms, cudaStream_t s);
+cudaError_t launch_fill_zero(View v, int sms, cudaStream_t s);
+cudaError_t launch_channel_sum(View v, float* out, cudaStream_t s);
+cudaError_t launch_unpack_act(View v, float* out, cudaStream_t s);
+
+}  // namespace b200

@@ -1,0 +1,408 @@
+// tcgen05 / TMEM / TMA implicit-GEMM kernels for sm_100a.
+//
+//   igemm_kernel : 3x3x3 conv fprop and dgrad, 2x2x2-stride-2 transposed conv forward and dgrad
+//                  (reference: nn.Conv3d / nn.ConvTranspose3d call sites, models/unet3d.py:29,35,120).
+//   wgrad_kernel : weight gradients of both (autograd of the same call sites).
+//
+// Warp roles (256 threads, 1 CTA / SM): warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one
+// lane), warp 2 = TMEM allocator, warps 4..7 = epilogue (TMEM lane quarter = warp % 4).
+#include <cuda_bf16.h>
+#include "igemm.cuh"
+#include "ptx.cuh"
+
+namespace b200 {
+
+// ------------------------------------------------------------------------------------------------
+// Shared-memory carve-up helpers
+// ------------------------------------------------------------------------------------------------
+struct PipeState {
+    uint32_t stage = 0, phase = 0;
+    DEV void advance(uint32_t nstages) {
+        if (++stage == nstages) { stage = 0; phase ^= 1; }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// igemm_kernel
+// ------------------------------------------------------------------------------------------------
+// smem: [stages x A box 16 KB][stages x B tile block_n x 128 B][barriers][tmem ptr][stats scratch][column sums]
+extern "C" __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t nst = p.stages;
+    const uint32_t b_bytes = p.block_n * 128;
+    const uint32_t smem_a = smem_base;
+    const uint32_t smem_b = smem_a + nst * kBoxBytes;
+    const uint32_t bar_base = smem_b + nst * b_bytes;  // 8-byte aligned (multiple of 1024)
+    // barrier layout: full[nst], empty[nst], tmem_full[2], tmem_empty[2]
+    auto full_bar = [&](uint32_t s) { return bar_base + 8 * s; };
+    auto empty_bar = [&](uint32_t s) { return bar_base + 8 * (nst + s); };
+    auto tfull_bar = [&](uint32_t s) { return bar_base + 8 * (2 * nst + s); };
+    auto tempty_bar = [&](uint32_t s) { return bar_base + 8 * (2 * nst + 2 + s); };
+    const uint32_t tmem_ptr_smem = bar_base + 8 * (2 * nst + 4);
+    const uint32_t scratch_off = (tmem_ptr_smem + 16 - smem_base + 15u) & ~15u;
+    float* scratch = reinterpret_cast<float*>(smem_gen + scratch_off);  // [4 warps][256 cols][2]
+    float* colacc = scratch + 4 * 256 * 2;                              // [ncols <= kMaxStatCols][2], per-CTA running sums
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&p.b_map);
+        prefetch_tmap(&p.a_map[0]);
+    }
+    if (warp == 1 && lane == 0) {
+        for (uint32_t s = 0; s < nst; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (uint32_t s = 0; s < 2; ++s) {
+            mbar_init(tfull_bar(s), 1);
+            mbar_init(tempty_bar(s), 128);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_ptr_smem, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_smem - smem_base));
+
+    const int m_tiles = p.nbw * p.nbh * p.nbd * p.nbatch;
+    const int total_tiles = m_tiles * p.n_tiles;
+    const int kblocks = p.ntaps * p.kc_blocks;
+
+    if (warp == 0 && lane == 0) {
+        // ===================================================================== TMA producer
+        PipeState ps;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int mt = tile / p.n_tiles;
+            const int n_tile = tile - mt * p.n_tiles;
+            const int bw = mt % p.nbw; mt /= p.nbw;
+            const int bh = mt % p.nbh; mt /= p.nbh;
+            const int bd = mt % p.nbd; mt /= p.nbd;
+            const int nb = mt;
+            const int w0 = bw << p.tw_log2, h0 = bh << p.th_log2, d0 = bd << p.td_log2;
+            const int n0 = n_tile * p.block_n;
+            for (int tap = 0; tap < p.ntaps; ++tap) {
+                const void* amap = &p.a_map[p.a_map_of_tap[tap]];
+                const int cw = w0 + p.tap_dw[tap], ch = h0 + p.tap_dh[tap], cd = d0 + p.tap_dd[tap];
+                for (int kc = 0; kc < p.kc_blocks; ++kc) {
+                    mbar_wait(empty_bar(ps.stage), ps.phase ^ 1);
+                    mbar_arrive_expect_tx(full_bar(ps.stage), kBoxBytes + b_bytes);
+                    tma_load_5d(smem_a + ps.stage * kBoxBytes, amap, full_bar(ps.stage), kc * 64, cw, ch, cd, nb);
+                    tma_load_3d(smem_b + ps.stage * b_bytes, &p.b_map, full_bar(ps.stage), kc * 64, n0, tap);
+                    ps.advance(nst);
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===================================================================== MMA issuer
+        const uint32_t idesc = make_idesc_bf16(128, p.block_n, 0, 0);
+        PipeState ps;
+        int iter = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+            const uint32_t acc = iter & 1, acc_phase = (iter >> 1) & 1;
+            mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * p.block_n;
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const int kc = kb % p.kc_blocks;
+                const int krem = p.cin - kc * 64;
+                const int nk = krem >= 64 ? 4 : ((krem + 15) >> 4);
+                mbar_wait(full_bar(ps.stage), ps.phase);
+                tc_fence_after();
+                const uint64_t a_desc = make_smem_desc_sw128(smem_a + ps.stage * kBoxBytes, 0, 1024);
+                const uint64_t b_desc = make_smem_desc_sw128(smem_b + ps.stage * b_bytes, 0, 1024);
+                for (int k = 0; k < nk; ++k) {
+                    // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (>>4) address field
+                    umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(empty_bar(ps.stage));
+                ps.advance(nst);
+            }
+            umma_commit(tfull_bar(acc));
+        }
+    } else if (warp >= 4) {
+        // ===================================================================== epilogue
+        const int q = warp - 4;  // == warp % 4: TMEM lane quarter
+        const int row = q * 32 + lane;
+        const int et = threadIdx.x - 128;  // 0..127
+        const int rw = row & ((1 << p.tw_log2) - 1);
+        const int rh = (row >> p.tw_log2) & ((1 << p.th_log2) - 1);
+        const int rd = row >> (p.tw_log2 + p.th_log2);
+        if (p.mode == EPI_BIAS_STATS) {
+            for (int i = et; i < 2 * p.ncols; i += 128) colacc[i] = 0.f;
+            named_bar_sync(1, 128);
+        }
+        int iter = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+            const uint32_t acc = iter & 1, acc_phase = (iter >> 1) & 1;
+            const int m_tile = tile / p.n_tiles;
+            const int n_tile = tile - m_tile * p.n_tiles;
+            int mt = m_tile;
+            const int bw = mt % p.nbw; mt /= p.nbw;
+            const int bh = mt % p.nbh; mt /= p.nbh;
+            const int bd = mt % p.nbd; mt /= p.nbd;
+            const int nb = mt;
+            const int gw = (bw << p.tw_log2) + rw, gh = (bh << p.th_log2) + rh, gd = (bd << p.td_log2) + rd;
+            const bool row_ok = gw < p.W && gh < p.H && gd < p.D;
+            const int n0 = n_tile * p.block_n;
+
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.block_n;
+            const int nchunks = p.block_n >> 4;
+            for (int c = 0; c < nchunks; ++c) {
+                uint32_t v[16];
+                tmem_ld16(t_addr + c * 16, v);
+                tmem_ld_wait();
+                const int col0 = n0 + c * 16;
+                const bool col_ok = col0 < p.ncols;
+                float f[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+                if (p.mode == EPI_BIAS_STATS || p.mode == EPI_BIAS) {
+                    if (col_ok) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) f[j] += __ldg(p.vec0 + col0 + j);
+                    }
+                } else if (p.mode == EPI_AFFINE_RELU) {
+                    if (col_ok) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            f[j] = fmaxf(fmaf(f[j], __ldg(p.vec0 + col0 + j), __ldg(p.vec1 + col0 + j)), 0.f);
+                    }
+                }
+                uint32_t pk[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+                if (row_ok && col_ok) {
+                    const int g = col0 / p.cols_per_group;
+                    const int cc = col0 - g * p.cols_per_group;
+                    const long long off = nb * p.out_sn + (long long)(gd * p.out_mul + p.out_od[g]) * p.out_sd +
+                                          (long long)(gh * p.out_mul + p.out_oh[g]) * p.out_sh +
+                                          (long long)(gw * p.out_mul + p.out_ow[g]) * p.out_sw + cc;
+                    uint4* dst = reinterpret_cast<uint4*>(p.out + off);
+                    dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                }
+                if (p.mode == EPI_BIAS_STATS) {
+                    // statistics of the *stored* (bf16-rounded) values, rows outside the volume excluded
+                    float s[16], ss[16];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        __nv_bfloat162 b2 = *reinterpret_cast<__nv_bfloat162*>(&pk[j]);
+                        const float lo = row_ok ? __low2float(b2) : 0.f, hi = row_ok ? __high2float(b2) : 0.f;
+                        s[2 * j] = lo; s[2 * j + 1] = hi;
+                        ss[2 * j] = lo * lo; ss[2 * j + 1] = hi * hi;
+                    }
+                    // transpose-reduce over the 32 lanes: 16 -> 8 -> 4 -> 2 -> 1 values per lane
+#pragma unroll
+                    for (int width = 8, bit = 16; width >= 1; width >>= 1, bit >>= 1) {
+                        const bool up = (lane & bit) != 0;
+#pragma unroll
+                        for (int j = 0; j < width; ++j) {
+                            const float keep_s = up ? s[j + width] : s[j], send_s = up ? s[j] : s[j + width];
+                            const float keep_q = up ? ss[j + width] : ss[j], send_q = up ? ss[j] : ss[j + width];
+                            s[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, bit);
+                            ss[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, bit);
+                        }
+                    }
+                    s[0] += __shfl_xor_sync(0xffffffffu, s[0], 1);
+                    ss[0] += __shfl_xor_sync(0xffffffffu, ss[0], 1);
+                    // lanes 2c and 2c+1 now hold column c of this 16-column chunk
+                    const int cl = c * 16 + (lane >> 1);
+                    scratch[(q * 256 + cl) * 2 + (lane & 1)] = (lane & 1) ? ss[0] : s[0];
+                }
+            }
+            // TMEM stage drained: hand it back to the MMA warp
+            tc_fence_before();
+            mbar_arrive(tempty_bar(acc));
+
+            if (p.mode == EPI_BIAS_STATS) {
+                named_bar_sync(1, 128);
+                for (int cl = et; cl < p.block_n; cl += 128) {
+                    const int col = n0 + cl;
+                    if (col < p.ncols) {
+                        float a = 0.f, b = 0.f;
+#pragma unroll
+                        for (int w4 = 0; w4 < 4; ++w4) {
+                            a += scratch[(w4 * 256 + cl) * 2 + 0];
+                            b += scratch[(w4 * 256 + cl) * 2 + 1];
+                        }
+                        colacc[2 * col] += a;  // column `col` of a tile is always reduced by thread cl % 128
+                        colacc[2 * col + 1] += b;
+                    }
+                }
+                named_bar_sync(1, 128);
+            }
+        }
+        if (p.mode == EPI_BIAS_STATS) {
+            // one partial row per CTA: stats[blockIdx.x][ncols][2]
+            named_bar_sync(1, 128);
+            float* dst = p.stats + (long long)blockIdx.x * p.ncols * 2;
+            for (int i = et; i < 2 * p.ncols; i += 128) dst[i] = colacc[i];
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// wgrad_kernel
+// ------------------------------------------------------------------------------------------------
+// smem: [2 x P slot 32 KB (two 64-channel boxes)][2 x Q slot 64 KB (up to four boxes)][barriers][tmem ptr]
+// One CTA = (p tile of 128 channels, group of <= 8 column blocks, voxel split); accumulators for the whole
+// group stay in TMEM (<= 512 columns) across all bricks of the split, then are added atomically to G.
+extern "C" __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    constexpr uint32_t kPSlot = 2 * kBoxBytes, kQSlot = 4 * kBoxBytes, kNP = 2, kNQ = 2;
+    const uint32_t smem_p = smem_base;
+    const uint32_t smem_q = smem_p + kNP * kPSlot;
+    const uint32_t bar_base = smem_q + kNQ * kQSlot;
+    auto pfull = [&](uint32_t s) { return bar_base + 8 * s; };
+    auto pempty = [&](uint32_t s) { return bar_base + 8 * (kNP + s); };
+    auto qfull = [&](uint32_t s) { return bar_base + 8 * (2 * kNP + s); };
+    auto qempty = [&](uint32_t s) { return bar_base + 8 * (2 * kNP + kNQ + s); };
+    const uint32_t tfull = bar_base + 8 * (2 * kNP + 2 * kNQ);
+    const uint32_t tmem_ptr_smem = tfull + 8;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&p.p_map);
+        prefetch_tmap(&p.q_map[0]);
+    }
+    if (warp == 1 && lane == 0) {
+        for (uint32_t s = 0; s < kNP; ++s) { mbar_init(pfull(s), 1); mbar_init(pempty(s), 1); }
+        for (uint32_t s = 0; s < kNQ; ++s) { mbar_init(qfull(s), 1); mbar_init(qempty(s), 1); }
+        mbar_init(tfull, 1);
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_ptr_smem, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_smem - smem_base));
+
+    // work decode: blockIdx = (split * n_groups + group) * p_tiles + ptile
+    int bid = blockIdx.x;
+    const int ptile = bid % p.p_tiles; bid /= p.p_tiles;
+    const int group = bid % p.n_groups; bid /= p.n_groups;
+    const int split = bid;
+    const int p0 = ptile * 128;
+    const int cb0 = group * p.cb_per_group;
+    const int ncb = min(p.cb_per_group, p.n_colblocks - cb0);
+    const int nsg = (ncb + 3) >> 2;  // slot groups of up to 4 column blocks (UMMA N up to 256)
+    const int nbricks = p.nbw * p.nbh * p.nbd * p.nbatch;
+
+    if (warp == 0 && lane == 0) {
+        // ===================================================================== TMA producer
+        PipeState pp, qp;
+        for (int b = split; b < nbricks; b += p.splits) {
+            int mt = b;
+            const int bw = mt % p.nbw; mt /= p.nbw;
+            const int bh = mt % p.nbh; mt /= p.nbh;
+            const int bd = mt % p.nbd; mt /= p.nbd;
+            const int nb = mt;
+            const int w0 = bw * p.tw, h0 = bh * p.th, d0 = bd * p.td;
+            mbar_wait(pempty(pp.stage), pp.phase ^ 1);
+            mbar_arrive_expect_tx(pfull(pp.stage), 2 * kBoxBytes);
+            tma_load_5d(smem_p + pp.stage * kPSlot, &p.p_map, pfull(pp.stage), p0, w0, h0, d0, nb);
+            tma_load_5d(smem_p + pp.stage * kPSlot + kBoxBytes, &p.p_map, pfull(pp.stage), p0 + 64, w0, h0, d0, nb);
+            pp.advance(kNP);
+            for (int sg = 0; sg < nsg; ++sg) {
+                const int nb4 = min(4, ncb - sg * 4);
+                mbar_wait(qempty(qp.stage), qp.phase ^ 1);
+                mbar_arrive_expect_tx(qfull(qp.stage), nb4 * kBoxBytes);
+                for (int i = 0; i < nb4; ++i) {
+                    const int cb = cb0 + sg * 4 + i;
+                    const int tap = cb / p.q_chunks;
+                    const int qc = cb - tap * p.q_chunks;
+                    tma_load_5d(smem_q + qp.stage * kQSlot + i * kBoxBytes, &p.q_map[p.q_map_of_tap[tap]],
+                                qfull(qp.stage), qc * 64, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap],
+                                d0 + p.tap_dd[tap], nb);
+                }
+                qp.advance(kNQ);
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===================================================================== MMA issuer
+        PipeState pp, qp;
+        int it = 0;
+        for (int b = split; b < nbricks; b += p.splits, ++it) {
+            mbar_wait(pfull(pp.stage), pp.phase);
+            tc_fence_after();
+            // MN-major SWIZZLE_128B operands: 64-channel atoms (16 KB boxes) LBO apart, 8-voxel groups SBO apart
+            const uint64_t a_desc = make_smem_desc_sw128(smem_p + pp.stage * kPSlot, kBoxBytes, 1024);
+            for (int sg = 0; sg < nsg; ++sg) {
+                const int nb4 = min(4, ncb - sg * 4);
+                const uint32_t idesc = make_idesc_bf16(128, 64 * nb4, 1, 1);
+                mbar_wait(qfull(qp.stage), qp.phase);
+                tc_fence_after();
+                const uint64_t b_desc = make_smem_desc_sw128(smem_q + qp.stage * kQSlot, kBoxBytes, 1024);
+                for (int k = 0; k < 8; ++k) {
+                    // 16 voxels = 16 rows x 128 B = 2048 B along K: +128 in the (>>4) address field
+                    umma_f16(tmem_base + sg * 256, a_desc + 128 * k, b_desc + 128 * k, idesc,
+                             (it > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(qempty(qp.stage));
+                qp.advance(kNQ);
+            }
+            umma_commit(pempty(pp.stage));
+            pp.advance(kNP);
+        }
+        umma_commit(tfull);
+    } else if (warp >= 4) {
+        // ===================================================================== epilogue
+        const int q = warp - 4;
+        const int row = q * 32 + lane;
+        const int pidx = p0 + row;
+        mbar_wait(tfull, 0);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        for (int i = 0; i < ncb; ++i) {
+            const int cb = cb0 + i;
+            const int tap = cb / p.q_chunks;
+            const int qc = cb - tap * p.q_chunks;
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[16];
+                tmem_ld16(t_addr + i * 64 + c * 16, v);
+                tmem_ld_wait();
+                if (pidx < p.p_extent) {
+                    float* dst = p.out + tap * p.st + (long long)pidx * p.sp;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int qi = qc * 64 + c * 16 + j;
+                        if (qi < p.q_extent) atomicAdd(dst + (long long)qi * p.sq, __uint_as_float(v[j]));
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+}  // namespace b200

@@ -1,0 +1,73 @@
+// Parameter blocks shared between the host-side launchers (api.cu) and the tcgen05 kernels.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace b200 {
+
+constexpr int kMaxTaps = 27;
+constexpr int kMaxMaps = 8;
+constexpr int kBrickRows = 128;          // output voxels per M tile (one TMA box of TW x TH x TD)
+constexpr int kBoxBytes = 128 * 128;     // one TMA box: 128 rows x 64 bf16
+constexpr int kMaxStatCols = 1024;       // widest Cout whose BatchNorm partial sums fit the CTA's smem
+constexpr int kThreads = 256;            // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 4..7 epilogue
+
+enum EpilogueMode : int {
+    EPI_PLAIN = 0,       // out = acc                         (dgrad)
+    EPI_BIAS_STATS = 1,  // out = bf16(acc + bias); per-tile sum / sum-of-squares of out (train fprop)
+    EPI_AFFINE_RELU = 2, // out = relu(acc * scale + shift)   (eval fprop, BatchNorm folded)
+    EPI_BIAS = 3,        // out = acc + bias                  (transposed conv forward)
+};
+
+// Implicit GEMM  D[m, n] = sum_{tap, c} A_tap[m, c] * B[tap][n][c]
+//   m : output voxel (row of a TW x TH x TD brick, w fastest), n : output column, c : input channel.
+// A_tap is read by TMA from an NDHWC bf16 tensor through a_map[a_map_of_tap[tap]] at the brick origin
+// shifted by (tap_dw, tap_dh, tap_dd); out-of-range coordinates are zero-filled by the TMA unit, which is
+// the convolution's zero padding.  B is the packed weight [taps][n][c] (c contiguous).
+struct alignas(64) IgemmParams {
+    CUtensorMap a_map[kMaxMaps];
+    CUtensorMap b_map;
+    int ntaps;
+    int a_map_of_tap[kMaxTaps];
+    int tap_dw[kMaxTaps], tap_dh[kMaxTaps], tap_dd[kMaxTaps];
+    int cin;        // channels per tap (K extent of one tap)
+    int kc_blocks;  // ceil(cin / 64)
+    int block_n;    // UMMA N (multiple of 16, <= 256)
+    int n_tiles;    // ceil(ncols / block_n)
+    int ncols;      // valid output columns
+    int nbw, nbh, nbd, nbatch;  // bricks per axis, batch
+    int tw_log2, th_log2, td_log2;
+    int W, H, D;    // extent of the M grid
+    int stages;
+    int mode;
+    const float* vec0;  // bias (modes 1,3) or scale (mode 2)
+    const float* vec1;  // shift (mode 2)
+    float* stats;       // mode 1: [gridDim.x][ncols][2]  (sum, sum of squares) per CTA
+    __nv_bfloat16* out;
+    long long out_sn, out_sd, out_sh, out_sw;  // element strides of the output tensor
+    int out_mul;        // output coordinate = m coordinate * out_mul + offset[group]
+    int cols_per_group; // columns sharing one output offset (transposed conv: Cout per tap)
+    int out_od[kMaxMaps], out_oh[kMaxMaps], out_ow[kMaxMaps];
+};
+
+// Weight-gradient GEMM  G[tap][p][q] += sum_{voxel} P[voxel][p] * Q_tap[voxel][q]
+// Both operands are voxel-major in memory (channel contiguous), i.e. MN-major UMMA operands.
+struct alignas(64) WgradParams {
+    CUtensorMap p_map;
+    CUtensorMap q_map[kMaxMaps];
+    int ntaps;
+    int q_map_of_tap[kMaxTaps];
+    int tap_dw[kMaxTaps], tap_dh[kMaxTaps], tap_dd[kMaxTaps];
+    int p_extent, q_extent;
+    int q_chunks;      // ceil(q_extent / 64)
+    int n_colblocks;   // ntaps * q_chunks
+    int cb_per_group;  // column blocks (64 wide) accumulated by one CTA (<= 8 -> 512 TMEM columns)
+    int n_groups, p_tiles, splits;
+    int nbw, nbh, nbd, nbatch;
+    int tw, th, td;
+    float* out;
+    long long st, sp, sq;  // element strides of G for (tap, p, q)
+};
+
+}  // namespace b200

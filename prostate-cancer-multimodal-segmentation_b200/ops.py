@@ -1,0 +1,200 @@
+"""Python faces of the C-ABI entry points (include/b200_unet3d.h), one function per entry point.
+
+Tensors are only carriers of device memory here: every function takes torch tensors, passes their device pointers
+and the current CUDA stream to the sm_100a kernels and returns nothing (outputs are caller-allocated).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import Act, check, ptr, stream_ptr
+
+EPI_PLAIN, EPI_BIAS_STATS, EPI_AFFINE_RELU, EPI_BIAS = 0, 1, 2, 3
+
+
+class ActView:
+    """Channel slice [c_off, c_off + c) of an NDHWC bf16 buffer of shape (N, D, H, W, LD)."""
+
+    __slots__ = ("t", "c_off", "c", "_s")
+
+    def __init__(self, t: torch.Tensor, c_off: int = 0, c: int = None):
+        if t.dtype != torch.bfloat16 or t.dim() != 5 or not t.is_contiguous():
+            raise ValueError("ActView needs a contiguous bf16 (N,D,H,W,C) tensor")
+        if not t.is_cuda:
+            raise _lib.B200Error("b200 kernels need CUDA tensors: there is no CPU path")
+        self.t = t
+        self.c_off = c_off
+        self.c = t.shape[4] - c_off if c is None else c
+        n, d, h, w, ld = t.shape
+        self._s = Act(t.data_ptr() + 2 * c_off, n, d, h, w, self.c, ld)
+
+    @property
+    def ref(self):
+        return C.byref(self._s)
+
+    @property
+    def shape(self):
+        n, d, h, w, _ = self.t.shape
+        return (n, d, h, w, self.c)
+
+    @property
+    def voxels(self) -> int:
+        n, d, h, w, _ = self.t.shape
+        return n * d * h * w
+
+    def as_torch(self):
+        """(N,D,H,W,c) strided torch view (debug / tests)"""
+        return self.t[..., self.c_off:self.c_off + self.c]
+
+    def to_ncdhw(self) -> torch.Tensor:
+        n, d, h, w, c = self.shape
+        out = torch.empty((n, c, d, h, w), device=self.t.device, dtype=torch.float32)
+        check(_lib.load().b200_unpack_act(self.ref, ptr(out), stream_ptr()), "unpack_act")
+        return out
+
+
+def new_act(n, d, h, w, c, device, zero=False) -> torch.Tensor:
+    f = torch.zeros if zero else torch.empty
+    return f((n, d, h, w, c), device=device, dtype=torch.bfloat16)
+
+
+def sm_count() -> int:
+    return _lib.load().b200_sm_count()
+
+
+def pack_input(x: torch.Tensor, out: ActView):
+    n, c, d, h, w = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    check(_lib.load().b200_pack_input(ptr(x), n, c, d, h, w, out.ref, stream_ptr()), "pack_input")
+
+
+def pack_conv_weight(w: torch.Tensor, cin_pad: int, w_fprop, w_dgrad):
+    cout, cin = w.shape[0], w.shape[1]
+    assert w.dtype == torch.float32 and w.is_contiguous()
+    check(_lib.load().b200_pack_conv_weight(ptr(w), cout, cin, cin_pad, ptr(w_fprop), ptr(w_dgrad), stream_ptr()),
+          "pack_conv_weight")
+
+
+def pack_convt_weight(w: torch.Tensor, bias: torch.Tensor, w_fwd, w_dgrad, bias8):
+    cin, cout = w.shape[0], w.shape[1]
+    assert w.dtype == torch.float32 and w.is_contiguous()
+    check(_lib.load().b200_pack_convt_weight(ptr(w), ptr(bias), cin, cout, ptr(w_fwd), ptr(w_dgrad), ptr(bias8),
+                                             stream_ptr()), "pack_convt_weight")
+
+
+def conv3d_stat_rows(n, d, h, w, cout) -> int:
+    r = _lib.load().b200_conv3d_stat_rows(n, d, h, w, cout)
+    if r <= 0:
+        raise _lib.B200Error("b200_conv3d_stat_rows failed (no CUDA device?)")
+    return r
+
+
+def conv3d_fprop(x: ActView, w_fprop, bias, y: ActView, stats=None, mode=EPI_BIAS_STATS, scale=None, shift=None):
+    check(_lib.load().b200_conv3d_fprop(x.ref, ptr(w_fprop), ptr(bias), y.ref, ptr(stats), mode, ptr(scale),
+                                        ptr(shift), stream_ptr()), "conv3d_fprop")
+
+
+def conv3d_dgrad(dy: ActView, w_dgrad, dx: ActView):
+    check(_lib.load().b200_conv3d_dgrad(dy.ref, ptr(w_dgrad), dx.ref, stream_ptr()), "conv3d_dgrad")
+
+
+def conv3d_wgrad(x: ActView, dy: ActView, dw: torch.Tensor, cin_real: int):
+    check(_lib.load().b200_conv3d_wgrad(x.ref, dy.ref, ptr(dw), cin_real, stream_ptr()), "conv3d_wgrad")
+
+
+def convt2x_fwd(x: ActView, w_fwd, bias8, y: ActView, pads=(0, 0, 0)):
+    check(_lib.load().b200_convt2x_fwd(x.ref, ptr(w_fwd), ptr(bias8), y.ref, pads[0], pads[1], pads[2],
+                                       stream_ptr()), "convt2x_fwd")
+
+
+def convt2x_dgrad(dy: ActView, pads, w_dgrad, dx: ActView):
+    check(_lib.load().b200_convt2x_dgrad(dy.ref, pads[0], pads[1], pads[2], ptr(w_dgrad), dx.ref, stream_ptr()),
+          "convt2x_dgrad")
+
+
+def convt2x_wgrad(x: ActView, dy: ActView, pads, dw: torch.Tensor):
+    check(_lib.load().b200_convt2x_wgrad(x.ref, dy.ref, pads[0], pads[1], pads[2], ptr(dw), stream_ptr()),
+          "convt2x_wgrad")
+
+
+def bn_finalize(stats, rows, count, c, gamma, beta, eps, momentum, running_mean, running_var, mean, rstd, scale,
+                shift):
+    check(_lib.load().b200_bn_finalize(ptr(stats), rows, count, c, ptr(gamma), ptr(beta), eps, momentum,
+                                       ptr(running_mean), ptr(running_var), ptr(mean), ptr(rstd), ptr(scale),
+                                       ptr(shift), stream_ptr()), "bn_finalize")
+
+
+def bn_fold_eval(gamma, beta, running_mean, running_var, conv_bias, eps, scale, shift):
+    check(_lib.load().b200_bn_fold_eval(ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var), ptr(conv_bias),
+                                        eps, gamma.numel(), ptr(scale), ptr(shift), stream_ptr()), "bn_fold_eval")
+
+
+def bn_apply_relu(y: ActView, scale, shift, out: ActView):
+    check(_lib.load().b200_bn_apply_relu(y.ref, ptr(scale), ptr(shift), out.ref, stream_ptr()), "bn_apply_relu")
+
+
+def bn_bwd_max_blocks() -> int:
+    return _lib.load().b200_bn_bwd_max_blocks()
+
+
+def bn_bwd(dout: ActView, y: ActView, scale, shift, mean, rstd, gamma, partial, coef, dgamma, dbeta, dy: ActView,
+           dbias):
+    """BatchNorm3d(train)+ReLU backward: reduce -> finalize -> apply (three launches)."""
+    lib = _lib.load()
+    nblk = C.c_int(0)
+    s = stream_ptr()
+    check(lib.b200_bn_bwd_reduce(dout.ref, y.ref, ptr(scale), ptr(shift), ptr(mean), ptr(rstd), ptr(partial),
+                                 C.byref(nblk), s), "bn_bwd_reduce")
+    check(lib.b200_bn_bwd_finalize(ptr(partial), nblk.value, y.c, y.voxels, ptr(dgamma), ptr(dbeta), ptr(coef), s),
+          "bn_bwd_finalize")
+    check(lib.b200_bn_bwd_apply(dout.ref, y.ref, ptr(scale), ptr(shift), ptr(mean), ptr(rstd), ptr(gamma), ptr(coef),
+                                dy.ref, ptr(dbias), s), "bn_bwd_apply")
+
+
+def maxpool3d_fwd(x: ActView, y: ActView):
+    check(_lib.load().b200_maxpool3d_fwd(x.ref, y.ref, stream_ptr()), "maxpool3d_fwd")
+
+
+def maxpool3d_bwd(x: ActView, dy: ActView, dskip, dx: ActView):
+    check(_lib.load().b200_maxpool3d_bwd(x.ref, None, dy.ref, dskip.ref if dskip is not None else None, dx.ref,
+                                         stream_ptr()), "maxpool3d_bwd")
+
+
+def head_fwd(x: ActView, w, b, logits, probs=None):
+    check(_lib.load().b200_head_fwd(x.ref, ptr(w), ptr(b), w.shape[0], ptr(logits), ptr(probs), stream_ptr()),
+          "head_fwd")
+
+
+def head_bwd(x: ActView, w, dlogits, dx: ActView, dw, db):
+    check(_lib.load().b200_head_bwd(x.ref, ptr(w), w.shape[0], ptr(dlogits), dx.ref, ptr(dw), ptr(db), stream_ptr()),
+          "head_bwd")
+
+
+def loss_fwd(logits, target, bce_w, dice_w, smooth, workspace, sums, loss):
+    check(_lib.load().b200_loss_fwd(ptr(logits), ptr(target), logits.numel(), bce_w, dice_w, smooth, ptr(workspace),
+                                    ptr(sums), ptr(loss), stream_ptr()), "loss_fwd")
+
+
+def loss_bwd(logits, target, bce_w, dice_w, smooth, sums, gout, dlogits):
+    check(_lib.load().b200_loss_bwd(ptr(logits), ptr(target), logits.numel(), bce_w, dice_w, smooth, ptr(sums),
+                                    ptr(gout), ptr(dlogits), stream_ptr()), "loss_bwd")
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0,
+              found_inf=None):
+    check(_lib.load().b200_adam_step(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), lr, beta1,
+                                     beta2, eps, weight_decay, step, grad_scale, ptr(found_inf), stream_ptr()),
+          "adam_step")
+
+
+def sumsq(x, out):
+    check(_lib.load().b200_sumsq(ptr(x), x.numel(), ptr(out), stream_ptr()), "sumsq")
+
+
+def fill_zero(v: ActView):
+    check(_lib.load().b200_fill_zero(v.ref, stream_ptr()), "fill_zero")
+
+
+def channel_sum(v: ActView, out):
+    check(_lib.load().b200_channel_sum(v.ref, ptr(out), stream_ptr()), "channel_sum")

@@ -1,0 +1,355 @@
+"""Per-kernel GPU parity: every C-ABI entry point against the torch fp32 op the reference calls at that site
+(nn.Conv3d / BatchNorm3d / ReLU / MaxPool3d / ConvTranspose3d / losses / Adam) on identical bf16-rounded inputs.
+
+Tolerances: bf16 outputs with fp32 accumulation -> relative L2 <= 2e-2 (north_star); here the inputs are already
+bf16-exact so the only error is the output rounding (~4e-3) and accumulation order. Index/mask work is bit-exact.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import bf16_round, empty_act, from_act, rel_l2, to_act
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-2
+
+
+def _conv_inputs(dev, n, cin, cout, d, h, w, seed=0, cin_real=None):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    cin_real = cin_real or cin
+    x = torch.zeros(n, cin, d, h, w)
+    x[:, :cin_real] = torch.randn(n, cin_real, d, h, w, generator=g)
+    wt = torch.randn(cout, cin_real, 3, 3, 3, generator=g) * (2.0 / (cin_real * 27)) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    return bf16_round(x).to(dev), bf16_round(wt).to(dev), b.to(dev)
+
+
+CONV_CASES = [
+    # n, cin(padded), cin_real, cout, d, h, w
+    (1, 16, 16, 64, 8, 8, 16),
+    (1, 16, 5, 64, 16, 16, 16),      # first layer: 5 modalities padded to 16
+    (2, 64, 64, 128, 12, 10, 18),    # odd extents, partial bricks
+    (1, 128, 128, 64, 8, 16, 16),    # concat input (2 K blocks), narrow N
+    (1, 256, 256, 512, 4, 4, 4),     # two N tiles, volume smaller than a brick
+    (2, 32, 32, 32, 2, 2, 2),        # tiny
+    (1, 96, 96, 48, 6, 6, 6),        # K tail (96 = 64 + 32), N = 48
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv3d_fprop_bias_stats(ops, cuda_dev, case):
+    n, cin, cin_real, cout, d, h, w = case
+    x, wt, b = _conv_inputs(cuda_dev, n, cin, cout, d, h, w, cin_real=cin_real)
+    wf = torch.empty(27, cout, cin, device=cuda_dev, dtype=torch.bfloat16)
+    wd = torch.empty(27, cin, cout, device=cuda_dev, dtype=torch.bfloat16)
+    ops.pack_conv_weight(wt.contiguous(), cin, wf, wd)
+    # packing is exact
+    ref_wf = torch.zeros(27, cout, cin, device=cuda_dev)
+    ref_wf[:, :, :cin_real] = wt.reshape(cout, cin_real, 27).permute(2, 0, 1)
+    assert torch.equal(wf.float(), ref_wf)
+    assert torch.equal(wd.float(), ref_wf.permute(0, 2, 1))
+
+    xv = to_act(ops, x)
+    yv = empty_act(ops, n, cout, d, h, w, cuda_dev)
+    rows = ops.conv3d_stat_rows(n, d, h, w, cout)
+    stats = torch.full((rows, cout, 2), float("nan"), device=cuda_dev)
+    ops.conv3d_fprop(xv, wf, b, yv, stats, ops.EPI_BIAS_STATS)
+    torch.cuda.synchronize()
+    ref = F.conv3d(x[:, :cin_real], wt, b, padding=1)
+    got = from_act(yv)
+    assert torch.isfinite(got).all()
+    err = rel_l2(got, ref)
+    assert err < TOL, f"fprop rel-L2 {err}"
+    s = stats.double().sum(0)
+    gd = got.double()
+    assert torch.allclose(s[:, 0], gd.sum((0, 2, 3, 4)), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(s[:, 1], (gd * gd).sum((0, 2, 3, 4)), rtol=1e-4, atol=1e-2)
+
+
+def test_conv3d_fprop_affine_relu_and_views(ops, cuda_dev):
+    """eval-mode epilogue; input and output are channel halves of wider (concat) buffers."""
+    n, cin, cout, d, h, w = 1, 64, 64, 8, 8, 8
+    x, wt, _ = _conv_inputs(cuda_dev, n, cin, cout, d, h, w, seed=3)
+    wf = torch.empty(27, cout, cin, device=cuda_dev, dtype=torch.bfloat16)
+    ops.pack_conv_weight(wt.contiguous(), cin, wf, None)
+    scale = torch.rand(cout, device=cuda_dev) + 0.5
+    shift = torch.randn(cout, device=cuda_dev) * 0.2
+    xv = to_act(ops, x, ld=128, c_off=64)
+    yv = empty_act(ops, n, cout, d, h, w, cuda_dev, ld=128, c_off=0)
+    ops.conv3d_fprop(xv, wf, None, yv, None, ops.EPI_AFFINE_RELU, scale, shift)
+    torch.cuda.synchronize()
+    ref = torch.relu(F.conv3d(x, wt, None, padding=1) * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1))
+    err = rel_l2(from_act(yv), ref)
+    assert err < TOL, f"affine-relu rel-L2 {err}"
+    # the other half of the output buffer was not touched
+    assert torch.isnan(yv.t[..., 64:].float()).all()
+
+
+@pytest.mark.parametrize("case", CONV_CASES[2:])
+def test_conv3d_dgrad(ops, cuda_dev, case):
+    n, cin, cin_real, cout, d, h, w = case
+    _, wt, _ = _conv_inputs(cuda_dev, n, cin, cout, d, h, w, seed=1)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    dy = bf16_round(torch.randn(n, cout, d, h, w, generator=g)).to(cuda_dev)
+    wd = torch.empty(27, cin, cout, device=cuda_dev, dtype=torch.bfloat16)
+    ops.pack_conv_weight(wt.contiguous(), cin, None, wd)
+    dyv = to_act(ops, dy)
+    dxv = empty_act(ops, n, cin, d, h, w, cuda_dev)
+    ops.conv3d_dgrad(dyv, wd, dxv)
+    torch.cuda.synchronize()
+    ref = torch.nn.grad.conv3d_input((n, cin, d, h, w), wt, dy, padding=1)
+    err = rel_l2(from_act(dxv), ref)
+    assert err < TOL, f"dgrad rel-L2 {err}"
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv3d_wgrad(ops, cuda_dev, case):
+    n, cin, cin_real, cout, d, h, w = case
+    x, _, _ = _conv_inputs(cuda_dev, n, cin, cout, d, h, w, seed=2, cin_real=cin_real)
+    g = torch.Generator(device="cpu").manual_seed(7)
+    dy = bf16_round(torch.randn(n, cout, d, h, w, generator=g)).to(cuda_dev)
+    dw = torch.zeros(cout, cin_real, 3, 3, 3, device=cuda_dev)
+    ops.conv3d_wgrad(to_act(ops, x), to_act(ops, dy), dw, cin_real)
+    torch.cuda.synchronize()
+    ref = torch.nn.grad.conv3d_weight(x[:, :cin_real], (cout, cin_real, 3, 3, 3), dy, padding=1)
+    err = rel_l2(dw, ref)
+    assert err < 2e-3, f"wgrad rel-L2 {err}"
+    # accumulates (+=)
+    ops.conv3d_wgrad(to_act(ops, x), to_act(ops, dy), dw, cin_real)
+    torch.cuda.synchronize()
+    assert rel_l2(dw, 2 * ref) < 2e-3
+
+
+CONVT_CASES = [
+    # n, cin, d, h, w, pads, (D2,H2,W2)
+    (1, 128, 4, 4, 8, (0, 0, 0), None),
+    (2, 64, 3, 5, 6, (0, 0, 0), None),
+    (1, 256, 2, 2, 2, (0, 0, 0), None),
+    (1, 128, 5, 9, 4, (0, 0, 1), (10, 18, 9)),   # F.pad path: skip 10x18x9 vs upsampled 10x18x8, pad front 0 / back 1
+    (1, 64, 4, 4, 4, (1, 0, 1), (10, 9, 11)),
+]
+
+
+@pytest.mark.parametrize("case", CONVT_CASES)
+def test_convt2x_fwd_dgrad_wgrad(ops, cuda_dev, case):
+    n, cin, d, h, w, pads, tgt = case
+    cout = cin // 2
+    D2, H2, W2 = tgt or (2 * d, 2 * h, 2 * w)
+    g = torch.Generator(device="cpu").manual_seed(11)
+    x = bf16_round(torch.randn(n, cin, d, h, w, generator=g)).to(cuda_dev)
+    wt = bf16_round(torch.randn(cin, cout, 2, 2, 2, generator=g) * (1.0 / cin) ** 0.5).to(cuda_dev)
+    b = (torch.randn(cout, generator=g) * 0.1).to(cuda_dev)
+    wf = torch.empty(8 * cout, cin, device=cuda_dev, dtype=torch.bfloat16)
+    wd = torch.empty(8, cin, cout, device=cuda_dev, dtype=torch.bfloat16)
+    b8 = torch.empty(8 * cout, device=cuda_dev)
+    ops.pack_convt_weight(wt.contiguous(), b, wf, wd, b8)
+    # forward into the upper half of a concat buffer
+    cat = torch.full((n, D2, H2, W2, 2 * cout), float("nan"), device=cuda_dev, dtype=torch.bfloat16)
+    up = ops.ActView(cat, cout, cout)
+    ops.fill_zero(up)
+    ops.convt2x_fwd(to_act(ops, x), wf, b8, up, pads)
+    torch.cuda.synchronize()
+    ref = F.conv_transpose3d(x, wt, b, stride=2)
+    pd, ph, pw = pads
+    ref = F.pad(ref, [pw, W2 - 2 * w - pw, ph, H2 - 2 * h - ph, pd, D2 - 2 * d - pd])
+    got = from_act(up)
+    err = rel_l2(got, ref)
+    assert err < TOL, f"convT fwd rel-L2 {err}"
+    assert torch.isnan(cat[..., :cout].float()).all()
+
+    # dgrad / wgrad from a gradient living in the same kind of view
+    dyf = bf16_round(torch.randn(n, cout, D2, H2, W2, generator=g)).to(cuda_dev)
+    dyv = to_act(ops, dyf, ld=2 * cout, c_off=cout)
+    dxv = empty_act(ops, n, cin, d, h, w, cuda_dev)
+    ops.convt2x_dgrad(dyv, pads, wd, dxv)
+    dw = torch.zeros(cin, cout, 2, 2, 2, device=cuda_dev)
+    ops.convt2x_wgrad(to_act(ops, x), dyv, pads, dw)
+    torch.cuda.synchronize()
+    dy_core = dyf[:, :, pd:pd + 2 * d, ph:ph + 2 * h, pw:pw + 2 * w].contiguous()
+    ref_dx = F.conv3d(dy_core, wt, None, stride=2)  # adjoint of conv_transpose3d
+    err = rel_l2(from_act(dxv), ref_dx)
+    assert err < TOL, f"convT dgrad rel-L2 {err}"
+    xr = x.clone().requires_grad_(True)
+    wr = wt.clone().requires_grad_(True)
+    F.conv_transpose3d(xr, wr, None, stride=2).backward(dy_core)
+    err = rel_l2(dw, wr.grad)
+    assert err < 2e-3, f"convT wgrad rel-L2 {err}"
+    bsum = torch.zeros(cout, device=cuda_dev)
+    ops.channel_sum(dyv, bsum)
+    torch.cuda.synchronize()
+    assert torch.allclose(bsum, dyf.sum((0, 2, 3, 4)), rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 8, 8, 8), (1, 32, 5, 7, 9), (2, 512, 2, 2, 2), (1, 96, 4, 4, 6)])
+def test_batchnorm_relu_fwd_bwd(ops, cuda_dev, shape):
+    n, c, d, h, w = shape
+    g = torch.Generator(device="cpu").manual_seed(13)
+    y = bf16_round(torch.randn(n, c, d, h, w, generator=g) * 1.5 + 0.3).to(cuda_dev)
+    gamma = (torch.rand(c, generator=g) + 0.5).to(cuda_dev)
+    beta = (torch.randn(c, generator=g) * 0.2).to(cuda_dev)
+    rm = torch.zeros(c, device=cuda_dev)
+    rv = torch.ones(c, device=cuda_dev)
+    count = n * d * h * w
+    # statistics as the conv epilogue would deliver them (2 partial rows)
+    yd = y.double()
+    half = yd[:, :, : d // 2 + 1]
+    rest = yd[:, :, d // 2 + 1:]
+    stats = torch.stack([
+        torch.stack([half.sum((0, 2, 3, 4)), (half * half).sum((0, 2, 3, 4))], -1),
+        torch.stack([rest.sum((0, 2, 3, 4)), (rest * rest).sum((0, 2, 3, 4))], -1)]).float().contiguous()
+    mean, rstd, scale, shift = (torch.empty(c, device=cuda_dev) for _ in range(4))
+    ops.bn_finalize(stats, 2, count, c, gamma, beta, 1e-5, 0.1, rm, rv, mean, rstd, scale, shift)
+    yv = to_act(ops, y)
+    av = empty_act(ops, n, c, d, h, w, cuda_dev)
+    ops.bn_apply_relu(yv, scale, shift, av)
+    torch.cuda.synchronize()
+
+    bn = torch.nn.BatchNorm3d(c).to(cuda_dev)
+    with torch.no_grad():
+        bn.weight.copy_(gamma)
+        bn.bias.copy_(beta)
+    yr = y.clone().requires_grad_(True)
+    ref = torch.relu(bn(yr))
+    assert rel_l2(from_act(av), ref) < 5e-3
+    assert torch.allclose(rm, bn.running_mean, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(rv, bn.running_var, rtol=1e-4, atol=1e-5)
+    # ReLU mask is exact given the same pre-activation
+    zf = y * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1)
+    assert torch.equal(from_act(av) > 0, bf16_round(torch.relu(zf)) > 0)
+
+    dout = bf16_round(torch.randn(n, c, d, h, w, generator=g)).to(cuda_dev)
+    ref.backward(dout)
+    partial = torch.empty(ops.bn_bwd_max_blocks(), c, 2, device=cuda_dev)
+    coef = torch.empty(c, 2, device=cuda_dev)
+    dgamma, dbeta, dbias = (torch.zeros(c, device=cuda_dev) for _ in range(3))
+    dyv = empty_act(ops, n, c, d, h, w, cuda_dev)
+    ops.bn_bwd(to_act(ops, dout), yv, scale, shift, mean, rstd, gamma, partial, coef, dgamma, dbeta, dyv, dbias)
+    torch.cuda.synchronize()
+    assert rel_l2(from_act(dyv), yr.grad) < TOL
+    assert rel_l2(dgamma, bn.weight.grad) < 1e-3
+    assert rel_l2(dbeta, bn.bias.grad) < 1e-3
+    assert torch.allclose(dbias, from_act(dyv).sum((0, 2, 3, 4)), rtol=1e-3, atol=1e-2)
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 8, 8, 8), (1, 16, 5, 7, 9), (1, 128, 2, 4, 6)])
+def test_maxpool_fwd_bwd_bit_exact(ops, cuda_dev, shape):
+    n, c, d, h, w = shape
+    g = torch.Generator(device="cpu").manual_seed(17)
+    # few distinct values -> many ties: exercises first-max-wins
+    x = (torch.randint(0, 4, (n, c, d, h, w), generator=g).float() - 1.0).to(cuda_dev)
+    xv = to_act(ops, x)
+    yv = empty_act(ops, n, c, d // 2, h // 2, w // 2, cuda_dev)
+    ops.maxpool3d_fwd(xv, yv)
+    xr = x.clone().requires_grad_(True)
+    ref = F.max_pool3d(xr, 2)
+    torch.cuda.synchronize()
+    assert torch.equal(from_act(yv), ref)
+    dy = bf16_round(torch.randn(ref.shape, generator=g)).to(cuda_dev)
+    dskip = bf16_round(torch.randn(x.shape, generator=g)).to(cuda_dev)
+    ref.backward(dy)
+    dxv = empty_act(ops, n, c, d, h, w, cuda_dev)
+    ops.maxpool3d_bwd(xv, to_act(ops, dy), to_act(ops, dskip), dxv)
+    torch.cuda.synchronize()
+    assert torch.equal(from_act(dxv), bf16_round(dskip + xr.grad))
+    dxv2 = empty_act(ops, n, c, d, h, w, cuda_dev)
+    ops.maxpool3d_bwd(xv, to_act(ops, dy), None, dxv2)
+    torch.cuda.synchronize()
+    assert torch.equal(from_act(dxv2), xr.grad)
+
+
+@pytest.mark.parametrize("ncls", [1, 2])
+def test_head_fwd_bwd(ops, cuda_dev, ncls):
+    n, c, d, h, w = 2, 64, 6, 5, 7
+    g = torch.Generator(device="cpu").manual_seed(19)
+    x = bf16_round(torch.randn(n, c, d, h, w, generator=g)).to(cuda_dev)
+    wt = (torch.randn(ncls, c, generator=g) * 0.2).to(cuda_dev)
+    b = torch.randn(ncls, generator=g).to(cuda_dev)
+    logits = torch.empty(n, ncls, d, h, w, device=cuda_dev)
+    probs = torch.empty_like(logits)
+    xv = to_act(ops, x)
+    ops.head_fwd(xv, wt, b, logits, probs)
+    torch.cuda.synchronize()
+    xr = x.clone().requires_grad_(True)
+    wr = wt.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    ref = F.conv3d(xr, wr.view(ncls, c, 1, 1, 1), br)
+    assert torch.allclose(logits, ref, rtol=1e-4, atol=1e-4)
+    assert torch.allclose(probs, torch.sigmoid(ref), rtol=1e-4, atol=1e-5)
+    dl = torch.randn(ref.shape, generator=g).to(cuda_dev)
+    ref.backward(dl)
+    dxv = empty_act(ops, n, c, d, h, w, cuda_dev)
+    dw = torch.zeros(ncls, c, device=cuda_dev)
+    db = torch.zeros(ncls, device=cuda_dev)
+    ops.head_bwd(xv, wt, dl.contiguous(), dxv, dw, db)
+    torch.cuda.synchronize()
+    assert rel_l2(from_act(dxv), xr.grad) < 5e-3
+    assert rel_l2(dw, wr.grad) < 1e-4
+    assert rel_l2(db, br.grad) < 1e-4
+
+
+@pytest.mark.parametrize("n_el,weights", [(4 * 1000 + 3, (0.5, 0.5)), (2 * 64 * 64 * 64, (0.0, 1.0)),
+                                          (128 * 128, (0.3, 0.7))])
+def test_loss_fwd_bwd(ops, cuda_dev, n_el, weights):
+    bw, dw_ = weights
+    g = torch.Generator(device="cpu").manual_seed(23)
+    z = (torch.randn(n_el, generator=g) * 3).to(cuda_dev)
+    t = (torch.rand(n_el, generator=g) < 0.1).float().to(cuda_dev)
+    ws = torch.empty(4 * 1024, device=cuda_dev)
+    sums = torch.empty(4, device=cuda_dev)
+    loss = torch.empty(1, device=cuda_dev)
+    ops.loss_fwd(z, t, bw, dw_, 1.0, ws, sums, loss)
+    zr = z.clone().requires_grad_(True)
+    p = torch.sigmoid(zr)
+    dice = (2 * (p * t).sum() + 1.0) / (p.sum() + t.sum() + 1.0)
+    ref = bw * F.binary_cross_entropy_with_logits(zr, t) + dw_ * (1 - dice)
+    torch.cuda.synchronize()
+    assert abs(loss.item() - ref.item()) < 1e-5
+    gout = torch.tensor([0.7], device=cuda_dev)
+    (ref * 0.7).backward()
+    dz = torch.empty_like(z)
+    ops.loss_bwd(z, t, bw, dw_, 1.0, sums, gout, dz)
+    torch.cuda.synchronize()
+    assert rel_l2(dz, zr.grad) < 1e-4
+
+
+def test_adam_matches_torch(ops, cuda_dev):
+    n = 100003
+    g = torch.Generator(device="cpu").manual_seed(29)
+    p0 = torch.randn(n, generator=g).to(cuda_dev)
+    pr = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([pr], lr=1e-3, weight_decay=1e-5)
+    p = p0.clone()
+    m = torch.zeros_like(p)
+    v = torch.zeros_like(p)
+    for step in range(1, 4):
+        grad = torch.randn(n, generator=g).to(cuda_dev)
+        pr.grad = grad.clone()
+        opt.step()
+        ops.adam_step(p, grad, m, v, 1e-3, 0.9, 0.999, 1e-8, 1e-5, step)
+    torch.cuda.synchronize()
+    assert torch.allclose(p, pr.detach(), rtol=1e-5, atol=1e-6)
+    st = opt.state[pr]
+    assert torch.allclose(m, st["exp_avg"], rtol=1e-5, atol=1e-7)
+    assert torch.allclose(v, st["exp_avg_sq"], rtol=1e-5, atol=1e-9)
+
+
+def test_pack_input_and_unpack(ops, cuda_dev):
+    n, c, d, h, w = 2, 5, 4, 6, 5
+    x = torch.randn(n, c, d, h, w, device=cuda_dev)
+    out = empty_act(ops, n, 16, d, h, w, cuda_dev)
+    ops.pack_input(x, out)
+    torch.cuda.synchronize()
+    got = from_act(out)
+    assert torch.equal(got[:, :5], bf16_round(x))
+    assert (got[:, 5:] == 0).all()
+    assert torch.equal(out.to_ncdhw(), got)
+
+
+def test_bad_arguments_raise(ops, pkg, cuda_dev):
+    """error convention: non-zero status -> exception carrying b200_last_error()"""
+    x = empty_act(ops, 1, 24, 4, 4, 4, cuda_dev)   # 24 channels: not a multiple of 16
+    y = empty_act(ops, 1, 32, 4, 4, 4, cuda_dev)
+    wf = torch.empty(27, 32, 24, device=cuda_dev, dtype=torch.bfloat16)
+    with pytest.raises(pkg.B200Error, match="multiple of 16"):
+        ops.conv3d_fprop(x, wf, None, y, None, ops.EPI_PLAIN)
