@@ -130,8 +130,9 @@ int b200_loss_bwd(const float* logits, const float* target, int64_t n, float bce
 /* ---- optimizer (torch.optim.Adam, utils/trainer.py:113-117,192) ---------------------------------------- */
 /* fused over a flat fp32 buffer: g = grad*grad_scale + wd*p ; Adam moments ; bias-corrected update.
  * step is the 1-based step count.  If found_inf != NULL and *found_inf != 0 the update is skipped. */
-int b200_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
-                   float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
+int b200_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                   double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step,
+                   double grad_scale,
                    const float* found_inf, void* stream);
 /* sum of squares of a flat fp32 buffer -> out[0] (+=) ; nonfinite flag -> out[1] (clip_grad_norm_/GradScaler) */
 int b200_sumsq(const float* x, int64_t n, float* out, void* stream);

@@ -1,0 +1,193 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  Never imported by the product package.
+
+CPU (or any-device) fp32 restatement, in plain torch functional ops, of the reference hot path:
+  * UNet3D graph                  — reference models/unet3d.py:27-40, 78-83, 120-158, 247-296
+  * predict / inference           — reference models/unet3d.py:298-344
+  * DiceLoss / BCEDiceLoss        — reference utils/losses.py:44-92, 107-152
+  * one training step             — reference utils/trainer.py:177-195 (zero_grad, forward, loss, backward, Adam.step)
+  * Adam update                   — torch.optim.Adam as constructed at utils/trainer.py:113-117
+  * data-parallel step (new capability): per-shard forward/backward, mean of gradients, one Adam step
+  * sliding-window inference (new capability, SURVEY.md 8d cfg #4): uniform averaging of window logits
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module.
+
+Pinning: the reference ships no golden vectors or assertions for this path.  This restatement is
+pinned against the *reference itself*: oracle/make_golden.py imports /root/reference (models/unet3d.py,
+utils/losses.py) in the build container and writes tests/golden/*.pt; tests/test_oracle_cpu.py checks this file
+against those vectors.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+def _double_conv(x, sd, prefix, training, taps):
+    """Conv3d(3,p1)+BN+ReLU twice.  sd: state-dict-like mapping; running stats are updated in place when training."""
+    for conv_i, bn_i in ((0, 1), (3, 4)):
+        x = F.conv3d(x, sd[f"{prefix}.{conv_i}.weight"], sd[f"{prefix}.{conv_i}.bias"], padding=1)
+        if taps is not None:
+            taps[f"{prefix}.{conv_i}"] = x
+        rm, rv = sd[f"{prefix}.{bn_i}.running_mean"], sd[f"{prefix}.{bn_i}.running_var"]
+        x = F.batch_norm(x, rm, rv, sd[f"{prefix}.{bn_i}.weight"], sd[f"{prefix}.{bn_i}.bias"], training,
+                         BN_MOMENTUM, BN_EPS)
+        if training:
+            sd[f"{prefix}.{bn_i}.num_batches_tracked"] += 1
+        x = F.relu(x)
+        if taps is not None:
+            taps[f"{prefix}.{bn_i + 1}"] = x
+    return x
+
+
+def unet3d_forward(x, sd, training=False, taps=None):
+    """logits = UNet3D(x).  `sd` has the reference's 136 state_dict keys; `taps` (dict) collects per-layer outputs
+    keyed by the reference module path (conv outputs at '.0'/'.3', post-ReLU at '.2'/'.5')."""
+    skips = []
+    h = _double_conv(x, sd, "inc.conv", training, taps)
+    skips.append(h)
+    for k in (1, 2, 3, 4):
+        h = F.max_pool3d(h, 2)
+        h = _double_conv(h, sd, f"down{k}.maxpool_conv.1.conv", training, taps)
+        if k < 4:
+            skips.append(h)
+    for j in (1, 2, 3, 4):
+        skip = skips[4 - j]
+        h = F.conv_transpose3d(h, sd[f"up{j}.up.weight"], sd[f"up{j}.up.bias"], stride=2)
+        if taps is not None:
+            taps[f"up{j}.up"] = h
+        dz, dy, dx = (skip.shape[2] - h.shape[2], skip.shape[3] - h.shape[3], skip.shape[4] - h.shape[4])
+        h = F.pad(h, [dx // 2, dx - dx // 2, dy // 2, dy - dy // 2, dz // 2, dz - dz // 2])
+        h = torch.cat([skip, h], dim=1)
+        h = _double_conv(h, sd, f"up{j}.conv.conv", training, taps)
+    return F.conv3d(h, sd["outc.weight"], sd["outc.bias"])
+
+
+def predict(x, sd):
+    with torch.no_grad():
+        return torch.sigmoid(unet3d_forward(x, sd, training=False))
+
+
+def inference(x, sd, threshold=0.5):
+    return (predict(x, sd) > threshold).float()
+
+
+def dice_loss(pred, target, smooth=1.0):
+    if pred.shape != target.shape:
+        raise ValueError(f"shape mismatch: pred.shape={pred.shape}, target.shape={target.shape}")
+    p = torch.sigmoid(pred).reshape(-1)
+    t = target.reshape(-1)
+    inter = (p * t).sum()
+    return 1 - (2.0 * inter + smooth) / (p.sum() + t.sum() + smooth)
+
+
+def bce_dice_loss(pred, target, bce_weight=0.5, dice_weight=0.5, smooth=1.0):
+    bce = F.binary_cross_entropy_with_logits(pred, target)
+    return bce_weight * bce + dice_weight * dice_loss(pred, target, smooth)
+
+
+def loss_grad_closed_form(pred, target, bce_weight=0.5, dice_weight=0.5, smooth=1.0):
+    """dL/dz in closed form — cross-check of autograd in the CPU tests."""
+    s = torch.sigmoid(pred)
+    n = pred.numel()
+    inter, p_sum, t_sum = (s * target).sum(), s.sum(), target.sum()
+    b = p_sum + t_sum + smooth
+    a = 2 * inter + smooth
+    return bce_weight * (s - target) / n + dice_weight * s * (1 - s) * (-2 * target / b + a / (b * b))
+
+
+def param_names(sd):
+    return [k for k in sd if not (k.endswith("running_mean") or k.endswith("running_var")
+                                  or k.endswith("num_batches_tracked"))]
+
+
+def adam_update(p, g, m, v, step, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+    """in-place Adam with coupled L2 decay, as torch.optim.Adam(amsgrad=False)"""
+    b1, b2 = betas
+    if weight_decay:
+        g = g + weight_decay * p
+    m.mul_(b1).add_(g, alpha=1 - b1)
+    v.mul_(b2).addcmul_(g, g, value=1 - b2)
+    bc1 = 1 - b1 ** step
+    bc2 = 1 - b2 ** step
+    denom = (v.sqrt() / math.sqrt(bc2)).add_(eps)
+    p.addcdiv_(m, denom, value=-lr / bc1)
+
+
+def train_step(sd, opt_state, x, y, lr=1e-4, weight_decay=1e-5, loss="bce_dice", taps=None):
+    """zero_grad -> forward -> loss -> backward -> Adam.step on `sd` in place.  Returns (loss, grads, logits)."""
+    names = param_names(sd)
+    leaves = {k: sd[k].detach().clone().requires_grad_(True) for k in names}
+    work = dict(sd)
+    work.update(leaves)
+    logits = unet3d_forward(x, work, training=True, taps=taps)
+    lval = bce_dice_loss(logits, y) if loss == "bce_dice" else dice_loss(logits, y)
+    grads = dict(zip(names, torch.autograd.grad(lval, [leaves[k] for k in names])))
+    apply_adam(sd, opt_state, grads, lr, weight_decay)
+    return lval.detach(), grads, logits.detach()
+
+
+def apply_adam(sd, opt_state, grads, lr=1e-4, weight_decay=1e-5):
+    opt_state["step"] = opt_state.get("step", 0) + 1
+    with torch.no_grad():
+        for k, g in grads.items():
+            m = opt_state.setdefault(("m", k), torch.zeros_like(sd[k]))
+            v = opt_state.setdefault(("v", k), torch.zeros_like(sd[k]))
+            adam_update(sd[k], g, m, v, opt_state["step"], lr, weight_decay=weight_decay)
+
+
+def dp_train_step(sd, opt_state, x_shards, y_shards, lr=1e-4, weight_decay=1e-5, loss="bce_dice"):
+    """Data-parallel semantics: every rank runs forward/backward on its shard from the same weights
+    with rank-local BatchNorm statistics and rank-local loss; parameter gradients are averaged; one Adam step.
+    Running statistics follow rank 0 (DDP broadcast_buffers behaviour).  Returns (mean loss, averaged grads)."""
+    names = param_names(sd)
+    total, losses = None, []
+    sd_rank0 = None
+    for r, (xs, ys) in enumerate(zip(x_shards, y_shards)):
+        work = {k: (v.clone() if not k in names else v) for k, v in sd.items()}
+        leaves = {k: sd[k].detach().clone().requires_grad_(True) for k in names}
+        work.update(leaves)
+        logits = unet3d_forward(xs, work, training=True)
+        lval = bce_dice_loss(logits, ys) if loss == "bce_dice" else dice_loss(logits, ys)
+        gr = torch.autograd.grad(lval, [leaves[k] for k in names])
+        total = list(gr) if total is None else [a + b for a, b in zip(total, gr)]
+        losses.append(lval.detach())
+        if r == 0:
+            sd_rank0 = work
+    world = len(x_shards)
+    grads = {k: g / world for k, g in zip(names, total)}
+    for k in sd:
+        if k not in names:
+            sd[k].copy_(sd_rank0[k])
+    apply_adam(sd, opt_state, grads, lr, weight_decay)
+    return torch.stack(losses).mean(), grads
+
+
+def window_origins(extent, window, stride):
+    """start offsets of sliding windows along one axis: regular stride, last window flush with the end"""
+    if extent <= window:
+        return [0]
+    o = list(range(0, extent - window + 1, stride))
+    if o[-1] != extent - window:
+        o.append(extent - window)
+    return o
+
+
+def sliding_window_logits(x, sd, window, stride):
+    """uniform-weight average of per-window logits, windows visited in (d, h, w) order (SURVEY.md 8d cfg #4)"""
+    n, _, D, H, W = x.shape
+    wd, wh, ww = (min(window[0], D), min(window[1], H), min(window[2], W))
+    out = None
+    cnt = torch.zeros(1, 1, D, H, W, dtype=x.dtype, device=x.device)
+    with torch.no_grad():
+        for d0 in window_origins(D, wd, stride[0]):
+            for h0 in window_origins(H, wh, stride[1]):
+                for w0 in window_origins(W, ww, stride[2]):
+                    lg = unet3d_forward(x[:, :, d0:d0 + wd, h0:h0 + wh, w0:w0 + ww], sd, training=False)
+                    if out is None:
+                        out = torch.zeros(n, lg.shape[1], D, H, W, dtype=x.dtype, device=x.device)
+                    out[:, :, d0:d0 + wd, h0:h0 + wh, w0:w0 + ww] += lg
+                    cnt[:, :, d0:d0 + wd, h0:h0 + wh, w0:w0 + ww] += 1
+    return out / cnt

@@ -6,5 +6,9 @@ hand-written CUDA kernels behind the C ABI of ``include/b200_unet3d.h`` (``libb2
 """
 from ._lib import B200Error, load as load_library, lib_path  # noqa: F401
 from . import ops  # noqa: F401
+from .unet3d import UNet3D, DoubleConv3D, Down3D, Up3D  # noqa: F401
+from .losses import DiceLoss, BCEDiceLoss  # noqa: F401
+from .optim import FusedAdam  # noqa: F401
 
-__all__ = ["B200Error", "load_library", "lib_path", "ops"]
+__all__ = ["B200Error", "load_library", "lib_path", "ops", "UNet3D", "DoubleConv3D", "Down3D", "Up3D", "DiceLoss",
+           "BCEDiceLoss", "FusedAdam"]

@@ -9,7 +9,7 @@ import torch
 
 from . import build as _build
 
-_i64, _i32, _f32, _vp = C.c_int64, C.c_int, C.c_float, C.c_void_p
+_i64, _i32, _f32, _f64, _vp = C.c_int64, C.c_int, C.c_float, C.c_double, C.c_void_p
 
 
 class B200Error(RuntimeError):
@@ -52,7 +52,7 @@ SIGNATURES = {
     "b200_head_bwd": (_i32, [_AP, _vp, _i32, _vp, _AP, _vp, _vp, _vp]),
     "b200_loss_fwd": (_i32, [_vp, _vp, _i64, _f32, _f32, _f32, _vp, _vp, _vp, _vp]),
     "b200_loss_bwd": (_i32, [_vp, _vp, _i64, _f32, _f32, _f32, _vp, _vp, _vp, _vp]),
-    "b200_adam_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i64, _f32, _vp, _vp]),
+    "b200_adam_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _f64, _f64, _f64, _f64, _f64, _i64, _f64, _vp, _vp]),
     "b200_sumsq": (_i32, [_vp, _i64, _vp, _vp]),
     "b200_fill_zero": (_i32, [_AP, _vp]),
     "b200_channel_sum": (_i32, [_AP, _vp, _vp]),

@@ -628,8 +628,8 @@ extern "C" int b200_loss_bwd(const float* logits, const float* target, int64_t n
     return 0;
 }
 extern "C" int b200_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
-                              float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
-                              float grad_scale, const float* found_inf, void* stream) {
+                   double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step,
+                   double grad_scale, const float* found_inf, void* stream) {
     REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, "adam_step: bad arguments");
     REQUIRE(((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) |
               reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) == 0,

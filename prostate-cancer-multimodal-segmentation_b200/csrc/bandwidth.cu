@@ -774,10 +774,10 @@ cudaError_t launch_loss_bwd(const float* z, const float* t, long long n, float b
 // ------------------------------------------------------------------------------------------------ Adam
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, long long n,
-                                                   float lr, float b1, float b2, float eps, float wd, float bc1,
-                                                   float bc2_sqrt, float gscale, const float* found_inf) {
+                                                   float step_size, float b2, float w1, float w2, float eps,
+                                                   float wd, float bc2_sqrt, float gscale, const float* found_inf) {
+    // torch.optim.Adam arithmetic: m.lerp_(g, 1-b1); v.mul_(b2).addcmul_(g, g, 1-b2); p.addcdiv_(m, sqrt(v)/bc2+eps)
     if (found_inf && *found_inf != 0.f) return;
-    const float step_size = lr / bc1;
     const long long n4 = n >> 2;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
          i += (long long)gridDim.x * blockDim.x) {
@@ -792,8 +792,8 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float gr = fmaf(wd, pa[j], ga[j] * gscale);
-            ma[j] = fmaf(b1, ma[j], (1.f - b1) * gr);  // torch: lerp(m, g, 1-b1)
-            va[j] = fmaf(b2, va[j], (1.f - b2) * gr * gr);
+            ma[j] = fmaf(w1, gr - ma[j], ma[j]);
+            va[j] = fmaf(w2 * gr, gr, b2 * va[j]);
             const float denom = sqrtf(va[j]) / bc2_sqrt + eps;
             pa[j] -= step_size * (ma[j] / denom);
         }
@@ -804,20 +804,21 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     if (blockIdx.x == 0) {
         for (long long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
             const float gr = fmaf(wd, p[i], g[i] * gscale);
-            m[i] = fmaf(b1, m[i], (1.f - b1) * gr);
-            v[i] = fmaf(b2, v[i], (1.f - b2) * gr * gr);
+            m[i] = fmaf(w1, gr - m[i], m[i]);
+            v[i] = fmaf(w2 * gr, gr, b2 * v[i]);
             const float denom = sqrtf(v[i]) / bc2_sqrt + eps;
             p[i] -= step_size * (m[i] / denom);
         }
     }
 }
-cudaError_t launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2,
-                        float eps, float wd, long long step, float gscale, const float* found_inf, int sms,
+cudaError_t launch_adam(float* p, const float* g, float* m, float* v, long long n, double lr, double b1, double b2,
+                        double eps, double wd, long long step, double gscale, const float* found_inf, int sms,
                         cudaStream_t s) {
-    const double bc1 = 1.0 - pow((double)b1, (double)step);
-    const double bc2 = 1.0 - pow((double)b2, (double)step);
-    adam_kernel<<<grid_for(n / 4 + 1, 256, sms, 8), 256, 0, s>>>(p, g, m, v, n, lr, b1, b2, eps, wd, (float)bc1,
-                                                                (float)sqrt(bc2), gscale, found_inf);
+    const double bc1 = 1.0 - pow(b1, (double)step);
+    const double bc2 = 1.0 - pow(b2, (double)step);
+    adam_kernel<<<grid_for(n / 4 + 1, 256, sms, 8), 256, 0, s>>>(p, g, m, v, n, (float)(lr / bc1), (float)b2,
+                                                                (float)(1.0 - b1), (float)(1.0 - b2), (float)eps,
+                                                                (float)wd, (float)sqrt(bc2), (float)gscale, found_inf);
     return cudaGetLastError();
 }
 

@@ -1,0 +1,423 @@
+"""Execution engine of the B200 U-Net: a static schedule of C-ABI kernel launches for the forward, the backward and
+the weight packing of one ``UNet3D`` (reference graph: models/unet3d.py:247-296; autograd of it: utils/trainer.py:191).
+
+Data layout in HBM
+  * activations: NDHWC bf16.  Every encoder level k owns one *concat buffer* (N, Dk, Hk, Wk, 2*Ck): the encoder's
+    DoubleConv writes the skip into channels [0, Ck), the decoder's transposed conv writes the upsampled map into
+    [Ck, 2*Ck) — ``F.pad`` + ``torch.cat`` (models/unet3d.py:143-156) never run as copies.
+  * parameters: one flat fp32 buffer (all 82 tensors, reverse-forward order, nn.Parameter.data are views into it) and
+    one flat fp32 gradient buffer of the same layout (Parameter.grad are views) so that the optimizer is one launch
+    and data-parallel buckets are contiguous ranges that complete in order during backward.
+  * packed bf16 weight shadows per conv: [27][Cout][Cin] (fprop, K-major B operand) and [27][Cin][Cout] (dgrad).
+"""
+import math
+
+import torch
+
+from . import ops
+from ._lib import B200Error
+from .ops import ActView, new_act
+
+BN_EPS_DEFAULT = 1e-5
+
+
+def _pad16(c: int) -> int:
+    return (c + 15) // 16 * 16
+
+
+class _ConvPack:
+    """bf16 operand shadows of one Conv3d 3x3x3"""
+
+    def __init__(self, conv, device):
+        self.conv = conv
+        self.cout, self.cin = conv.out_channels, conv.in_channels
+        self.cin_pad = _pad16(self.cin)
+        self.wf = torch.empty(27, self.cout, self.cin_pad, device=device, dtype=torch.bfloat16)
+        self.wd = torch.empty(27, self.cin_pad, self.cout, device=device, dtype=torch.bfloat16)
+
+    def pack(self):
+        ops.pack_conv_weight(self.conv.weight.data, self.cin_pad, self.wf, self.wd)
+
+
+class _ConvTPack:
+    def __init__(self, up, device):
+        self.up = up
+        self.cin, self.cout = up.in_channels, up.out_channels
+        self.wf = torch.empty(8 * self.cout, self.cin, device=device, dtype=torch.bfloat16)
+        self.wd = torch.empty(8, self.cin, self.cout, device=device, dtype=torch.bfloat16)
+        self.bias8 = torch.empty(8 * self.cout, device=device, dtype=torch.float32)
+
+    def pack(self):
+        ops.pack_convt_weight(self.up.weight.data, self.up.bias.data, self.wf, self.wd, self.bias8)
+
+
+class _DCState:
+    """what one DoubleConv3D saves for its backward"""
+    __slots__ = ("xin", "y1", "a1", "y2", "bn1", "bn2")
+
+
+class _DoubleConv:
+    """Conv3d -> BatchNorm3d -> ReLU, twice (models/unet3d.py:27-40)"""
+
+    def __init__(self, seq, device):
+        self.conv1, self.bn1, self.conv2, self.bn2 = seq[0], seq[1], seq[3], seq[4]
+        self.p1 = _ConvPack(self.conv1, device)
+        self.p2 = _ConvPack(self.conv2, device)
+        self.cout = self.conv1.out_channels
+
+    def pack(self):
+        self.p1.pack()
+        self.p2.pack()
+
+    # ---- forward
+    def _conv_bn_relu_train(self, xin: ActView, pack, bn, out: ActView):
+        n, d, h, w, _ = xin.shape
+        dev = xin.t.device
+        cout = pack.cout
+        if n * d * h * w <= 1:  # same contract as torch.nn.functional.batch_norm in training mode
+            raise ValueError(f"Expected more than 1 value per channel when training, got input size "
+                             f"{(n, cout, d, h, w)}")
+        y = ActView(new_act(n, d, h, w, cout, dev))
+        rows = ops.conv3d_stat_rows(n, d, h, w, cout)
+        stats = torch.empty(rows, cout, 2, device=dev, dtype=torch.float32)
+        ops.conv3d_fprop(xin, pack.wf, pack.conv.bias.data, y, stats, ops.EPI_BIAS_STATS, k_real=pack.cin)
+        vec = torch.empty(4, cout, device=dev, dtype=torch.float32)  # mean, rstd, scale, shift
+        momentum = bn.momentum
+        if bn.track_running_stats:
+            bn.num_batches_tracked.add_(1)
+            if momentum is None:  # cumulative moving average, as torch
+                momentum = 1.0 / float(bn.num_batches_tracked.item())
+        ops.bn_finalize(stats, rows, n * d * h * w, cout, bn.weight.data, bn.bias.data, bn.eps,
+                        momentum if momentum is not None else 0.0,
+                        bn.running_mean if bn.track_running_stats else None,
+                        bn.running_var if bn.track_running_stats else None, vec[0], vec[1], vec[2], vec[3])
+        ops.bn_apply_relu(y, vec[2], vec[3], out)
+        return y, vec
+
+    def _conv_bn_relu_eval(self, xin: ActView, pack, bn, out: ActView):
+        dev = xin.t.device
+        vec = torch.empty(2, pack.cout, device=dev, dtype=torch.float32)
+        ops.bn_fold_eval(bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var, pack.conv.bias.data, bn.eps,
+                         vec[0], vec[1])
+        ops.conv3d_fprop(xin, pack.wf, None, out, None, ops.EPI_AFFINE_RELU, vec[0], vec[1], k_real=pack.cin)
+
+    def forward(self, xin: ActView, out: ActView, training: bool):
+        n, d, h, w, _ = xin.shape
+        dev = xin.t.device
+        a1 = ActView(new_act(n, d, h, w, self.cout, dev))
+        if not (training or not self.bn1.track_running_stats):
+            self._conv_bn_relu_eval(xin, self.p1, self.bn1, a1)
+            self._conv_bn_relu_eval(a1, self.p2, self.bn2, out)
+            return None
+        st = _DCState()
+        st.xin, st.a1 = xin, a1
+        st.y1, st.bn1 = self._conv_bn_relu_train(xin, self.p1, self.bn1, a1)
+        st.y2, st.bn2 = self._conv_bn_relu_train(a1, self.p2, self.bn2, out)
+        return st
+
+    # ---- backward
+    def backward(self, st: _DCState, dout: ActView, dxin, grads, scratch):
+        """dout: gradient w.r.t. the block output; dxin: view to receive the input gradient (None: not needed)"""
+        n, d, h, w, _ = dout.shape
+        dev = dout.t.device
+        g = grads
+        # second conv
+        dy2 = ActView(new_act(n, d, h, w, self.cout, dev))
+        ops.bn_bwd(dout, st.y2, st.bn2[2], st.bn2[3], st.bn2[0], st.bn2[1], self.bn2.weight.data, scratch.partial,
+                   scratch.coef, g(self.bn2.weight), g(self.bn2.bias), dy2, g(self.conv2.bias))
+        ops.conv3d_wgrad(st.a1, dy2, g(self.conv2.weight), self.p2.cin)
+        da1 = ActView(new_act(n, d, h, w, self.cout, dev))
+        ops.conv3d_dgrad(dy2, self.p2.wd, da1)
+        st.y2 = None
+        # first conv (dy1 reuses dy2's buffer)
+        dy1 = dy2
+        ops.bn_bwd(da1, st.y1, st.bn1[2], st.bn1[3], st.bn1[0], st.bn1[1], self.bn1.weight.data, scratch.partial,
+                   scratch.coef, g(self.bn1.weight), g(self.bn1.bias), dy1, g(self.conv1.bias))
+        ops.conv3d_wgrad(st.xin, dy1, g(self.conv1.weight), self.p1.cin)
+        if dxin is not None:
+            ops.conv3d_dgrad(dy1, self.p1.wd, dxin)
+
+
+class _Scratch:
+    def __init__(self, device, cmax):
+        self.partial = torch.empty(ops.bn_bwd_max_blocks(), cmax, 2, device=device, dtype=torch.float32)
+        self.coef = torch.empty(cmax, 2, device=device, dtype=torch.float32)
+
+
+class _Tape:
+    """activations kept between forward and backward of one step"""
+    __slots__ = ("dims", "pads", "cats", "dcs", "pooled", "dec_in", "last", "x_shape")
+
+
+class Engine:
+    def __init__(self, model):
+        self.model = model
+        self.device = None
+        self._pack_key = None
+        self.external_epoch = 0  # bumped by anything that writes parameter memory behind torch's back (FusedAdam)
+        self.grad_sync = None    # optional data-parallel hook: object with .ready(lo, hi) and .finish()
+        self.flat_param = None
+        self.flat_grad = None
+        self._slots = None       # id(param) -> (offset, numel)
+
+    # ------------------------------------------------------------------ parameters
+    def ordered_params(self):
+        """(name, parameter) in reverse-forward order: the order in which backward completes their gradients"""
+        m = self.model
+        out = [("outc.weight", m.outc.weight), ("outc.bias", m.outc.bias)]
+
+        def dc(prefix, seq):
+            return [(f"{prefix}.4.weight", seq[4].weight), (f"{prefix}.4.bias", seq[4].bias),
+                    (f"{prefix}.3.weight", seq[3].weight), (f"{prefix}.3.bias", seq[3].bias),
+                    (f"{prefix}.1.weight", seq[1].weight), (f"{prefix}.1.bias", seq[1].bias),
+                    (f"{prefix}.0.weight", seq[0].weight), (f"{prefix}.0.bias", seq[0].bias)]
+
+        for j in (4, 3, 2, 1):
+            up = getattr(m, f"up{j}")
+            out += dc(f"up{j}.conv.conv", up.conv.conv)
+            out += [(f"up{j}.up.weight", up.up.weight), (f"up{j}.up.bias", up.up.bias)]
+        for k in (4, 3, 2, 1):
+            out += dc(f"down{k}.maxpool_conv.1.conv", getattr(m, f"down{k}").maxpool_conv[1].conv)
+        out += dc("inc.conv", m.inc.conv)
+        return out
+
+    def _is_flat(self) -> bool:
+        if self.flat_param is None:
+            return False
+        base = self.flat_param.data_ptr()
+        for _, p in self.ordered_params():
+            off, n = self._slots[id(p)]
+            if p.data.data_ptr() != base + 4 * off or p.data.numel() != n or p.data.dtype != torch.float32:
+                return False
+        return True
+
+    def flatten(self, device):
+        """re-home every parameter into one flat fp32 buffer (values preserved) and allocate the flat gradient"""
+        params = self.ordered_params()
+        slots, off = {}, 0
+        for _, p in params:
+            slots[id(p)] = (off, p.numel())
+            off += (p.numel() + 3) // 4 * 4
+        flat = torch.zeros(off, device=device, dtype=torch.float32)
+        for _, p in params:
+            o, n = slots[id(p)]
+            view = flat[o:o + n].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+            p.grad = None
+        self._slots = slots
+        self.flat_param = flat
+        self.flat_grad = torch.zeros(off, device=device, dtype=torch.float32)
+        self._pack_key = None
+
+    def grad_view(self, p):
+        o, n = self._slots[id(p)]
+        return self.flat_grad[o:o + n].view(p.shape)
+
+    def _build(self, device):
+        m = self.model
+        self.device = device
+        self.inc = _DoubleConv(m.inc.conv, device)
+        self.downs = [_DoubleConv(getattr(m, f"down{k}").maxpool_conv[1].conv, device) for k in (1, 2, 3, 4)]
+        self.ups = [(_ConvTPack(getattr(m, f"up{j}").up, device), _DoubleConv(getattr(m, f"up{j}").conv.conv, device))
+                    for j in (1, 2, 3, 4)]
+        cmax = max([self.inc.cout] + [d.cout for d in self.downs])
+        self.scratch = _Scratch(device, cmax)
+        self._pack_key = None
+
+    def prepare(self, device):
+        if device.type != "cuda":
+            raise B200Error("UNet3D (B200) runs on CUDA tensors only: there is no CPU path. "
+                            "Move the model and its input to a cuda device.")
+        if self.device != device:
+            self._build(device)
+        if not self._is_flat():
+            self.flatten(device)
+        key = (self.external_epoch, self.flat_param.data_ptr(),
+               tuple(p._version for _, p in self.ordered_params()))
+        if key != self._pack_key:
+            self.inc.pack()
+            for d in self.downs:
+                d.pack()
+            for t, d in self.ups:
+                t.pack()
+                d.pack()
+            self._pack_key = key
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x: torch.Tensor, training: bool, want_probs: bool = False):
+        m = self.model
+        if x.dim() != 5:
+            raise ValueError(f"expected a 5-D input (N, C, D, H, W), got shape {tuple(x.shape)}")
+        n, c, D, H, W = x.shape
+        if c != m.n_modalities:
+            raise RuntimeError(f"expected input with {m.n_modalities} channels, got {c} (shape {tuple(x.shape)})")
+        if min(D, H, W) < 16:
+            raise RuntimeError(f"every spatial extent must be >= 16 (four 2x poolings), got {(D, H, W)}")
+        dev = x.device
+        self.prepare(dev)
+        x = x.detach()
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.float().contiguous()
+        f = m.init_features
+        ch = [f, 2 * f, 4 * f, 8 * f, 16 * f]
+        dims = [(D, H, W)]
+        for _ in range(4):
+            d, h, w = dims[-1]
+            dims.append((d // 2, h // 2, w // 2))
+
+        tape = _Tape()
+        tape.dims, tape.x_shape = dims, tuple(x.shape)
+        x0 = ActView(new_act(n, D, H, W, self.inc.p1.cin_pad, dev))
+        ops.pack_input(x, x0)
+        # encoder: skip of level k lives in the lower half of cats[k]
+        cats = [new_act(n, *dims[k], 2 * ch[k], dev) for k in range(4)]
+        dcs = {}
+        dcs["inc"] = self.inc.forward(x0, ActView(cats[0], 0, ch[0]), training)
+        pooled = []
+        bottom = None
+        for k in range(1, 5):
+            src = ActView(cats[k - 1], 0, ch[k - 1])
+            pk = ActView(new_act(n, *dims[k], ch[k - 1], dev))
+            ops.maxpool3d_fwd(src, pk)
+            pooled.append(pk)
+            if k < 4:
+                out = ActView(cats[k], 0, ch[k])
+            else:
+                bottom = out = ActView(new_act(n, *dims[4], ch[4], dev))
+            dcs[f"down{k}"] = self.downs[k - 1].forward(pk, out, training)
+        # decoder
+        cur = bottom
+        dec_in, pads = [], []
+        for j in range(1, 5):
+            k = 4 - j
+            tp, dc = self.ups[j - 1]
+            (d2, h2, w2), (d1, h1, w1) = dims[k], cur.shape[1:4]
+            dd, dh, dw = d2 - 2 * d1, h2 - 2 * h1, w2 - 2 * w1
+            pad = (dd // 2, dh // 2, dw // 2)
+            upper = ActView(cats[k], ch[k], ch[k])
+            if dd or dh or dw:
+                ops.fill_zero(upper)  # F.pad border (models/unet3d.py:149-151)
+            ops.convt2x_fwd(cur, tp.wf, tp.bias8, upper, pad)
+            dec_in.append(cur)
+            pads.append(pad)
+            out = ActView(new_act(n, *dims[k], ch[k], dev))
+            dcs[f"up{j}"] = dc.forward(ActView(cats[k]), out, training)
+            cur = out
+        logits = torch.empty(n, m.n_classes, D, H, W, device=dev, dtype=torch.float32)
+        probs = torch.empty_like(logits) if want_probs else None
+        ops.head_fwd(cur, m.outc.weight.data.view(m.n_classes, -1), m.outc.bias.data, logits, probs)
+        tape.cats, tape.dcs, tape.pooled, tape.dec_in, tape.pads, tape.last = cats, dcs, pooled, dec_in, pads, cur
+        return logits, probs, tape
+
+    # ------------------------------------------------------------------ backward
+    def _begin_grads(self):
+        """Parameter.grad protocol: grads accumulate into views of the flat gradient buffer.
+        Returns g(param) -> fp32 tensor that kernels accumulate into, and a list of foreign grads to fold back."""
+        params = self.ordered_params()
+        ours, none_count = {}, 0
+        for _, p in params:
+            if p.grad is None:
+                none_count += 1
+        foreign = []
+        if none_count == len(params):
+            self.flat_grad.zero_()
+        for _, p in params:
+            gv = self.grad_view(p)
+            if p.grad is None:
+                if none_count != len(params):
+                    gv.zero_()
+                p.grad = gv
+                ours[id(p)] = gv
+            elif p.grad.data_ptr() == gv.data_ptr() and p.grad.dtype == torch.float32:
+                ours[id(p)] = p.grad  # accumulate in place (zero_grad(set_to_none=False) or gradient accumulation)
+            else:
+                tmp = torch.zeros_like(gv)
+                ours[id(p)] = tmp
+                foreign.append((p, tmp))
+        return (lambda p: ours[id(p)]), foreign
+
+    def backward(self, tape: _Tape, dlogits: torch.Tensor):
+        m = self.model
+        dev = dlogits.device
+        n = tape.x_shape[0]
+        dims = tape.dims
+        f = m.init_features
+        ch = [f, 2 * f, 4 * f, 8 * f, 16 * f]
+        g, foreign = self._begin_grads()
+        sync = self.grad_sync
+        if dlogits.dtype != torch.float32 or not dlogits.is_contiguous():
+            dlogits = dlogits.float().contiguous()
+
+        def mark(p):
+            if sync is not None:
+                o, cnt = self._slots[id(p)]
+                sync.ready(o + cnt)
+
+        dcur = ActView(new_act(n, *dims[0], ch[0], dev))
+        ops.head_bwd(tape.last, m.outc.weight.data.view(m.n_classes, -1), dlogits, dcur,
+                     g(m.outc.weight).view(m.n_classes, -1), g(m.outc.bias))
+        tape.last = None
+        mark(m.outc.bias)
+        dcats = [None] * 4
+        for j in (4, 3, 2, 1):
+            k = 4 - j
+            tp, dc = self.ups[j - 1]
+            dcat = new_act(n, *dims[k], 2 * ch[k], dev)
+            dcats[k] = dcat
+            dc.backward(tape.dcs[f"up{j}"], dcur, ActView(dcat), g, self.scratch)
+            tape.dcs[f"up{j}"] = None
+            mark(dc.conv1.bias)
+            dupper = ActView(dcat, ch[k], ch[k])
+            x_in = tape.dec_in[j - 1]
+            pad = tape.pads[j - 1]
+            d1, h1, w1 = x_in.shape[1:4]
+            if (2 * d1, 2 * h1, 2 * w1) == dims[k]:
+                ops.channel_sum(dupper, g(tp.up.bias))
+            else:  # F.pad border carries no bias gradient: reduce the un-padded core only
+                core = dupper.as_torch()[:, pad[0]:pad[0] + 2 * d1, pad[1]:pad[1] + 2 * h1, pad[2]:pad[2] + 2 * w1]
+                g(tp.up.bias).add_(core.float().sum((0, 1, 2, 3)))
+            ops.convt2x_wgrad(x_in, dupper, pad, g(tp.up.weight))
+            dprev = ActView(new_act(*x_in.shape, dev))
+            ops.convt2x_dgrad(dupper, pad, tp.wd, dprev)
+            mark(tp.up.bias)
+            dcur = dprev
+        tape.dec_in = None
+        for k in (4, 3, 2, 1):
+            dcobj = self.downs[k - 1]
+            dpool = ActView(new_act(n, *dims[k], ch[k - 1], dev))
+            dcobj.backward(tape.dcs[f"down{k}"], dcur, dpool, g, self.scratch)
+            tape.dcs[f"down{k}"] = None
+            mark(dcobj.conv1.bias)
+            skip_act = ActView(tape.cats[k - 1], 0, ch[k - 1])
+            dskip = ActView(dcats[k - 1], 0, ch[k - 1])
+            ops.maxpool3d_bwd(skip_act, dpool, dskip, dskip)  # in place: dskip += scatter(dpool)
+            dcur = dskip
+        self.inc.backward(tape.dcs["inc"], dcur, None, g, self.scratch)
+        mark(self.inc.conv1.bias)
+        tape.dcs = tape.cats = tape.pooled = None
+        for p, tmp in foreign:
+            p.grad.add_(tmp.to(p.grad.dtype))
+        if sync is not None:
+            sync.finish()
+
+
+def total_flops_per_voxel(init_features: int = 64, n_modalities: int = 5, n_classes: int = 1):
+    """algorithmic conv FLOPs per input voxel: (forward, forward+backward); SURVEY.md 8(d) accounting"""
+    f = init_features
+    fwd = 0.0
+    first = 2.0 * 27 * n_modalities * f
+    fwd += first + 2.0 * 27 * f * f
+    c = f
+    for k in range(1, 5):
+        s = 8.0 ** -k
+        fwd += s * 2.0 * 27 * (c * 2 * c + 2 * c * 2 * c)
+        c *= 2
+    for j in range(1, 5):
+        k = 4 - j
+        s = 8.0 ** -k
+        fwd += (8.0 ** -(k + 1)) * 2.0 * c * (c // 2) * 8   # transposed conv, per coarse voxel
+        fwd += s * 2.0 * 27 * (c * (c // 2) + (c // 2) * (c // 2))
+        c //= 2
+    fwd += 2.0 * f * n_classes
+    return fwd, 3.0 * fwd - first

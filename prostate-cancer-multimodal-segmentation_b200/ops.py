@@ -12,6 +12,26 @@ from ._lib import Act, check, ptr, stream_ptr
 
 EPI_PLAIN, EPI_BIAS_STATS, EPI_AFFINE_RELU, EPI_BIAS = 0, 1, 2, 3
 
+# ---- instrumentation (bench.py): kernel launch counter and an optional per-launch timing hook for the GEMM kernels
+launch_count = 0
+profile_hook = None  # callable(kernel_name, tag, algorithmic_flops, start_event, end_event)
+
+
+def _launched(n: int = 1):
+    global launch_count
+    launch_count += n
+
+
+def _gemm(kernel, tag, flops, call):
+    _launched(1)
+    if profile_hook is None:
+        return call()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    call()
+    e1.record()
+    profile_hook(kernel, tag, flops, e0, e1)
+
 
 class ActView:
     """Channel slice [c_off, c_off + c) of an NDHWC bf16 buffer of shape (N, D, H, W, LD)."""
@@ -64,12 +84,14 @@ def sm_count() -> int:
 
 
 def pack_input(x: torch.Tensor, out: ActView):
+    _launched(1)
     n, c, d, h, w = x.shape
     assert x.dtype == torch.float32 and x.is_contiguous()
     check(_lib.load().b200_pack_input(ptr(x), n, c, d, h, w, out.ref, stream_ptr()), "pack_input")
 
 
 def pack_conv_weight(w: torch.Tensor, cin_pad: int, w_fprop, w_dgrad):
+    _launched(1)
     cout, cin = w.shape[0], w.shape[1]
     assert w.dtype == torch.float32 and w.is_contiguous()
     check(_lib.load().b200_pack_conv_weight(ptr(w), cout, cin, cin_pad, ptr(w_fprop), ptr(w_dgrad), stream_ptr()),
@@ -77,6 +99,7 @@ def pack_conv_weight(w: torch.Tensor, cin_pad: int, w_fprop, w_dgrad):
 
 
 def pack_convt_weight(w: torch.Tensor, bias: torch.Tensor, w_fwd, w_dgrad, bias8):
+    _launched(1)
     cin, cout = w.shape[0], w.shape[1]
     assert w.dtype == torch.float32 and w.is_contiguous()
     check(_lib.load().b200_pack_convt_weight(ptr(w), ptr(bias), cin, cout, ptr(w_fwd), ptr(w_dgrad), ptr(bias8),
@@ -90,47 +113,63 @@ def conv3d_stat_rows(n, d, h, w, cout) -> int:
     return r
 
 
-def conv3d_fprop(x: ActView, w_fprop, bias, y: ActView, stats=None, mode=EPI_BIAS_STATS, scale=None, shift=None):
-    check(_lib.load().b200_conv3d_fprop(x.ref, ptr(w_fprop), ptr(bias), y.ref, ptr(stats), mode, ptr(scale),
-                                        ptr(shift), stream_ptr()), "conv3d_fprop")
+def conv3d_fprop(x: ActView, w_fprop, bias, y: ActView, stats=None, mode=EPI_BIAS_STATS, scale=None, shift=None,
+                 k_real=None):
+    lib = _lib.load()
+    _gemm("igemm_kernel", "conv3d_fprop", 2.0 * x.voxels * y.c * (k_real or x.c) * 27,
+          lambda: check(lib.b200_conv3d_fprop(x.ref, ptr(w_fprop), ptr(bias), y.ref, ptr(stats), mode, ptr(scale),
+                                              ptr(shift), stream_ptr()), "conv3d_fprop"))
 
 
 def conv3d_dgrad(dy: ActView, w_dgrad, dx: ActView):
-    check(_lib.load().b200_conv3d_dgrad(dy.ref, ptr(w_dgrad), dx.ref, stream_ptr()), "conv3d_dgrad")
+    lib = _lib.load()
+    _gemm("igemm_kernel", "conv3d_dgrad", 2.0 * dy.voxels * dy.c * dx.c * 27,
+          lambda: check(lib.b200_conv3d_dgrad(dy.ref, ptr(w_dgrad), dx.ref, stream_ptr()), "conv3d_dgrad"))
 
 
 def conv3d_wgrad(x: ActView, dy: ActView, dw: torch.Tensor, cin_real: int):
-    check(_lib.load().b200_conv3d_wgrad(x.ref, dy.ref, ptr(dw), cin_real, stream_ptr()), "conv3d_wgrad")
+    lib = _lib.load()
+    _gemm("wgrad_kernel", "conv3d_wgrad", 2.0 * x.voxels * dy.c * cin_real * 27,
+          lambda: check(lib.b200_conv3d_wgrad(x.ref, dy.ref, ptr(dw), cin_real, stream_ptr()), "conv3d_wgrad"))
 
 
 def convt2x_fwd(x: ActView, w_fwd, bias8, y: ActView, pads=(0, 0, 0)):
-    check(_lib.load().b200_convt2x_fwd(x.ref, ptr(w_fwd), ptr(bias8), y.ref, pads[0], pads[1], pads[2],
-                                       stream_ptr()), "convt2x_fwd")
+    lib = _lib.load()
+    _gemm("igemm_kernel", "convt2x_fwd", 2.0 * x.voxels * x.c * y.c * 8,
+          lambda: check(lib.b200_convt2x_fwd(x.ref, ptr(w_fwd), ptr(bias8), y.ref, pads[0], pads[1], pads[2],
+                                             stream_ptr()), "convt2x_fwd"))
 
 
 def convt2x_dgrad(dy: ActView, pads, w_dgrad, dx: ActView):
-    check(_lib.load().b200_convt2x_dgrad(dy.ref, pads[0], pads[1], pads[2], ptr(w_dgrad), dx.ref, stream_ptr()),
-          "convt2x_dgrad")
+    lib = _lib.load()
+    _gemm("igemm_kernel", "convt2x_dgrad", 2.0 * dx.voxels * dx.c * dy.c * 8,
+          lambda: check(lib.b200_convt2x_dgrad(dy.ref, pads[0], pads[1], pads[2], ptr(w_dgrad), dx.ref,
+                                               stream_ptr()), "convt2x_dgrad"))
 
 
 def convt2x_wgrad(x: ActView, dy: ActView, pads, dw: torch.Tensor):
-    check(_lib.load().b200_convt2x_wgrad(x.ref, dy.ref, pads[0], pads[1], pads[2], ptr(dw), stream_ptr()),
-          "convt2x_wgrad")
+    lib = _lib.load()
+    _gemm("wgrad_kernel", "convt2x_wgrad", 2.0 * x.voxels * x.c * dy.c * 8,
+          lambda: check(lib.b200_convt2x_wgrad(x.ref, dy.ref, pads[0], pads[1], pads[2], ptr(dw), stream_ptr()),
+                        "convt2x_wgrad"))
 
 
 def bn_finalize(stats, rows, count, c, gamma, beta, eps, momentum, running_mean, running_var, mean, rstd, scale,
                 shift):
+    _launched(1)
     check(_lib.load().b200_bn_finalize(ptr(stats), rows, count, c, ptr(gamma), ptr(beta), eps, momentum,
                                        ptr(running_mean), ptr(running_var), ptr(mean), ptr(rstd), ptr(scale),
                                        ptr(shift), stream_ptr()), "bn_finalize")
 
 
 def bn_fold_eval(gamma, beta, running_mean, running_var, conv_bias, eps, scale, shift):
+    _launched(1)
     check(_lib.load().b200_bn_fold_eval(ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var), ptr(conv_bias),
                                         eps, gamma.numel(), ptr(scale), ptr(shift), stream_ptr()), "bn_fold_eval")
 
 
 def bn_apply_relu(y: ActView, scale, shift, out: ActView):
+    _launched(1)
     check(_lib.load().b200_bn_apply_relu(y.ref, ptr(scale), ptr(shift), out.ref, stream_ptr()), "bn_apply_relu")
 
 
@@ -141,6 +180,7 @@ def bn_bwd_max_blocks() -> int:
 def bn_bwd(dout: ActView, y: ActView, scale, shift, mean, rstd, gamma, partial, coef, dgamma, dbeta, dy: ActView,
            dbias):
     """BatchNorm3d(train)+ReLU backward: reduce -> finalize -> apply (three launches)."""
+    _launched(3)
     lib = _lib.load()
     nblk = C.c_int(0)
     s = stream_ptr()
@@ -153,48 +193,58 @@ def bn_bwd(dout: ActView, y: ActView, scale, shift, mean, rstd, gamma, partial, 
 
 
 def maxpool3d_fwd(x: ActView, y: ActView):
+    _launched(1)
     check(_lib.load().b200_maxpool3d_fwd(x.ref, y.ref, stream_ptr()), "maxpool3d_fwd")
 
 
 def maxpool3d_bwd(x: ActView, dy: ActView, dskip, dx: ActView):
+    _launched(1)
     check(_lib.load().b200_maxpool3d_bwd(x.ref, None, dy.ref, dskip.ref if dskip is not None else None, dx.ref,
                                          stream_ptr()), "maxpool3d_bwd")
 
 
 def head_fwd(x: ActView, w, b, logits, probs=None):
+    _launched(1)
     check(_lib.load().b200_head_fwd(x.ref, ptr(w), ptr(b), w.shape[0], ptr(logits), ptr(probs), stream_ptr()),
           "head_fwd")
 
 
 def head_bwd(x: ActView, w, dlogits, dx: ActView, dw, db):
+    _launched(1)
     check(_lib.load().b200_head_bwd(x.ref, ptr(w), w.shape[0], ptr(dlogits), dx.ref, ptr(dw), ptr(db), stream_ptr()),
           "head_bwd")
 
 
 def loss_fwd(logits, target, bce_w, dice_w, smooth, workspace, sums, loss):
+    _launched(2)
     check(_lib.load().b200_loss_fwd(ptr(logits), ptr(target), logits.numel(), bce_w, dice_w, smooth, ptr(workspace),
                                     ptr(sums), ptr(loss), stream_ptr()), "loss_fwd")
 
 
 def loss_bwd(logits, target, bce_w, dice_w, smooth, sums, gout, dlogits):
+    _launched(1)
     check(_lib.load().b200_loss_bwd(ptr(logits), ptr(target), logits.numel(), bce_w, dice_w, smooth, ptr(sums),
                                     ptr(gout), ptr(dlogits), stream_ptr()), "loss_bwd")
 
 
 def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0,
               found_inf=None):
+    _launched(1)
     check(_lib.load().b200_adam_step(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), lr, beta1,
                                      beta2, eps, weight_decay, step, grad_scale, ptr(found_inf), stream_ptr()),
           "adam_step")
 
 
 def sumsq(x, out):
+    _launched(1)
     check(_lib.load().b200_sumsq(ptr(x), x.numel(), ptr(out), stream_ptr()), "sumsq")
 
 
 def fill_zero(v: ActView):
+    _launched(1)
     check(_lib.load().b200_fill_zero(v.ref, stream_ptr()), "fill_zero")
 
 
 def channel_sum(v: ActView, out):
+    _launched(1)
     check(_lib.load().b200_channel_sum(v.ref, ptr(out), stream_ptr()), "channel_sum")

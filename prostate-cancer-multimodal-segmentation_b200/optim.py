@@ -1,0 +1,71 @@
+"""Fused Adam over the engine's flat parameter buffer (torch.optim.Adam semantics, utils/trainer.py:113-117):
+coupled L2 weight decay, bias correction, eps outside the sqrt, no amsgrad.  One kernel launch per step."""
+import torch
+
+from . import ops
+from .unet3d import UNet3D
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """``FusedAdam(model)`` or ``FusedAdam(model.parameters(), model=model)``; lr is re-read from ``param_groups``
+    every step so torch LR schedulers (ReduceLROnPlateau) keep working."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, model=None):
+        if isinstance(params, UNet3D):
+            model, params = params, params.parameters()
+        if model is None:
+            raise ValueError("FusedAdam needs the UNet3D whose flat parameter buffer it updates (model=...)")
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        super().__init__(params, defaults)
+        if len(self.param_groups) != 1:
+            raise ValueError("FusedAdam supports a single param group (the whole model)")
+        self.model = model
+        self._step = 0
+        self.exp_avg = None
+        self.exp_avg_sq = None
+        self.grad_scale = 1.0     # multiply gradients on the fly (1/world for DP sums, 1/loss_scale, clip coefficient)
+        self.found_inf = None     # optional device flag: skip the update when non-zero
+
+    def _ensure_state(self):
+        eng = self.model.engine
+        dev = next(self.model.parameters()).device
+        eng.prepare(dev)
+        if self.exp_avg is None or self.exp_avg.numel() != eng.flat_param.numel() or self.exp_avg.device != dev:
+            self.exp_avg = torch.zeros_like(eng.flat_param)
+            self.exp_avg_sq = torch.zeros_like(eng.flat_param)
+        return eng
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        eng = self._ensure_state()
+        g = self.param_groups[0]
+        self._step += 1
+        ops.adam_step(eng.flat_param, eng.flat_grad, self.exp_avg, self.exp_avg_sq, g["lr"], g["betas"][0],
+                      g["betas"][1], g["eps"], g["weight_decay"], self._step, self.grad_scale, self.found_inf)
+        eng.external_epoch += 1
+        return loss
+
+    def zero_grad(self, set_to_none: bool = True):
+        # gradients live in the flat buffer; dropping the views lets the next backward zero it with one memset
+        super().zero_grad(set_to_none=set_to_none)
+
+    def state_dict(self):
+        sd = super().state_dict()
+        sd["b200"] = {"step": self._step,
+                      "exp_avg": None if self.exp_avg is None else self.exp_avg.clone(),
+                      "exp_avg_sq": None if self.exp_avg_sq is None else self.exp_avg_sq.clone()}
+        return sd
+
+    def load_state_dict(self, sd):
+        extra = sd.get("b200")
+        super().load_state_dict({k: v for k, v in sd.items() if k != "b200"})
+        if extra is not None:
+            self._step = extra["step"]
+            self._ensure_state()
+            if extra["exp_avg"] is not None:
+                self.exp_avg.copy_(extra["exp_avg"])
+                self.exp_avg_sq.copy_(extra["exp_avg_sq"])
