@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--base", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile-pass", action="store_true")
+    ap.add_argument("--dump-kernels", default=None, help="write the per-launch GEMM timing table of the profile pass")
     return ap.parse_args()
 
 
@@ -257,6 +258,12 @@ def main():
         step(x, y)
         torch.cuda.synchronize()
         ops.profile_hook = None
+        if args.dump_kernels and rank == 0:
+            with open(args.dump_kernels, "w") as f:
+                f.write("kernel tag gflop ms tflops\n")
+                for k, tag, fl, a, b in recs:
+                    ms = a.elapsed_time(b)
+                    f.write(f"{k} {tag} {fl / 1e9:.1f} {ms:.4f} {fl / (ms * 1e-3) / 1e12:.1f}\n")
         agg = {}
         for k, tag, fl, a, b in recs:
             d = agg.setdefault(k, {"ms": 0.0, "flops": 0.0, "launches": 0})

@@ -1,0 +1,87 @@
+"""Per-layer (block-level) GPU parity with IDENTICAL inputs: one DoubleConv3D / Down3D-style / Up3D-style block of the
+engine against the fp32 oracle ops on the same bf16-exact input and upstream gradient.  This is where the north-star
+per-layer bound applies: outputs and gradients within 2e-2 relative L2 (bf16 storage, fp32 accumulation)."""
+import importlib
+import os
+import sys
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import ROOT
+from helpers import bf16_round, empty_act, from_act, rel_l2, to_act
+
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import unet3d_oracle as oracle  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-2
+
+
+class _Grads:
+    def __init__(self):
+        self.d = {}
+
+    def __call__(self, p):
+        if id(p) not in self.d:
+            self.d[id(p)] = torch.zeros_like(p.data)
+        return self.d[id(p)]
+
+
+@pytest.mark.parametrize("cin,cout,shape", [(5, 64, (1, 16, 16, 16)), (128, 64, (1, 8, 16, 16)),
+                                            (64, 128, (2, 8, 8, 8)), (256, 128, (1, 6, 10, 4))])
+def test_double_conv_block(pkg, ops, cuda_dev, cin, cout, shape):
+    eng = importlib.import_module(pkg.__name__ + ".engine")
+    n, d, h, w = shape
+    torch.manual_seed(1)
+    block = pkg.DoubleConv3D(cin, cout).to(cuda_dev)
+    with torch.no_grad():
+        for m in block.modules():  # bf16-exact weights so that both sides see identical operands
+            if isinstance(m, torch.nn.Conv3d):
+                m.weight.copy_(bf16_round(m.weight))
+                m.bias.copy_(torch.randn_like(m.bias) * 0.1)
+            if isinstance(m, torch.nn.BatchNorm3d):
+                m.weight.copy_(torch.rand_like(m.weight) + 0.5)
+                m.bias.copy_(torch.randn_like(m.bias) * 0.1)
+    sd = {"b." + k: v.detach().clone() for k, v in block.conv.state_dict().items()}
+    dc = eng._DoubleConv(block.conv, cuda_dev)
+    dc.pack()
+    cpad = dc.p1.cin_pad
+    g = torch.Generator().manual_seed(2)
+    x = bf16_round(torch.randn(n, cin, d, h, w, generator=g)).to(cuda_dev)
+    xp = torch.zeros(n, cpad, d, h, w, device=cuda_dev)
+    xp[:, :cin] = x
+    xin = to_act(ops, xp)
+    out = empty_act(ops, n, cout, d, h, w, cuda_dev)
+    st = dc.forward(xin, out, training=True)
+    dout = bf16_round(torch.randn(n, cout, d, h, w, generator=g)).to(cuda_dev)
+    dxin = empty_act(ops, n, cpad, d, h, w, cuda_dev) if cin % 16 == 0 else None
+    grads = _Grads()
+    scratch = eng._Scratch(cuda_dev, cout)
+    dc.backward(st, to_act(ops, dout), dxin, grads, scratch)
+    torch.cuda.synchronize()
+
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items() if "running" not in k and "num_batches" not in k}
+    work = dict(sd)
+    work.update(leaves)
+    xr = x.clone().requires_grad_(True)
+    ref = oracle._double_conv(xr, work, "b", True, None)
+    names = list(leaves)
+    gr = torch.autograd.grad(ref, [xr] + [leaves[k] for k in names], dout)
+    assert rel_l2(from_act(out), ref) < TOL
+    if dxin is not None:
+        assert rel_l2(from_act(dxin)[:, :cin], gr[0]) < TOL
+    mods = {"b.0": block.conv[0], "b.1": block.conv[1], "b.3": block.conv[3], "b.4": block.conv[4]}
+    for k, gref in zip(names, gr[1:]):
+        mod, attr = k.rsplit(".", 1)
+        got = grads(getattr(mods[mod], attr))
+        if attr == "bias" and mod in ("b.0", "b.3"):
+            assert got.norm().item() <= 2e-2 * gr[1 + names.index(mod + ".weight")].norm().item()
+            continue
+        e = rel_l2(got, gref)
+        assert e < TOL, f"{k}: {e}"
+    # running statistics and batch counter
+    assert rel_l2(block.conv[1].running_mean, work["b.1.running_mean"]) < 1e-2
+    assert rel_l2(block.conv[4].running_var, work["b.4.running_var"]) < 1e-2
+    assert block.conv[4].num_batches_tracked.item() == 1
