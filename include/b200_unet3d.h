@@ -55,6 +55,18 @@ int b200_pack_conv_weight(const float* w, int cout, int cin, int cin_pad, void* 
 int b200_pack_convt_weight(const float* w, const float* bias, int cin, int cout, void* w_fwd, void* w_dgrad,
                            float* bias8, void* stream);
 
+/* First conv (Cin = 5 modalities): the 27*Cin-wide receptive field is expanded once into rows of k_pad bf16
+ * (column k = c*27 + tap, i.e. the flattened (Cin,3,3,3) weight order) so that the layer runs as a plain GEMM:
+ * b200_im2col_input + b200_pack_rows + b200_conv1_fprop / b200_conv1_wgrad.  models/unet3d.py:29 (inc.conv.0) */
+int b200_im2col_input(const float* x_ncdhw, int64_t n, int64_t c, int64_t d, int64_t h, int64_t w,
+                      const b200_act* out, void* stream);
+/* fp32 [rows][k] -> bf16 [rows][k_pad], zero padded */
+int b200_pack_rows(const float* w, int rows, int k, int k_pad, void* out, void* stream);
+/* pointwise (1 tap) forms of b200_conv3d_fprop / b200_conv3d_wgrad: y = x . w_rows^T (+ epilogue); dw (Cout,k_real) += */
+int b200_conv1_fprop(const b200_act* x, const void* w_rows, const float* bias, const b200_act* y,
+                     float* stats_partial, int mode, const float* scale, const float* shift, void* stream);
+int b200_conv1_wgrad(const b200_act* x, const b200_act* dy, float* dw, int k_real, void* stream);
+
 /* ---- 3x3x3 convolution, padding 1 (nn.Conv3d, models/unet3d.py:29,35), tcgen05 implicit GEMM ------------ */
 /* number of 128-voxel output bricks of a volume */
 int64_t b200_conv3d_mtiles(int64_t n, int64_t d, int64_t h, int64_t w);

@@ -25,10 +25,47 @@ BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 
 
-def _double_conv(x, sd, prefix, training, taps):
+# ---- optional "bf16 storage" mode -----------------------------------------------------------------------------
+# The same graph with every tensor that the B200 engine keeps in HBM as bf16 rounded to bf16 at that point (forward
+# value and, through the straight-through backward, its gradient), all arithmetic still fp32.  With store=None (the
+# default) nothing is rounded: that is the pinned fp32 oracle.  The per-layer 2e-2 bound of north_star ("fp32-
+# accumulated bf16 outputs and gradients") is checked against this mode; end-to-end fp32 comparisons are reported too.
+class _StoreBF16(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(torch.float32)
+
+
+class _OperandBF16(torch.autograd.Function):
+    """weights are fp32 masters read through a bf16 shadow; their gradients stay fp32"""
+
+    @staticmethod
+    def forward(ctx, w):
+        return w.to(torch.bfloat16).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def store_bf16(x):
+    return _StoreBF16.apply(x)
+
+
+def _ident(x):
+    return x
+
+
+def _double_conv(x, sd, prefix, training, taps, store=None):
     """Conv3d(3,p1)+BN+ReLU twice.  sd: state-dict-like mapping; running stats are updated in place when training."""
+    wop = _OperandBF16.apply if store is not None else _ident
+    store = store or _ident
     for conv_i, bn_i in ((0, 1), (3, 4)):
-        x = F.conv3d(x, sd[f"{prefix}.{conv_i}.weight"], sd[f"{prefix}.{conv_i}.bias"], padding=1)
+        x = store(F.conv3d(x, wop(sd[f"{prefix}.{conv_i}.weight"]), sd[f"{prefix}.{conv_i}.bias"], padding=1))
         if taps is not None:
             taps[f"{prefix}.{conv_i}"] = x
         rm, rv = sd[f"{prefix}.{bn_i}.running_mean"], sd[f"{prefix}.{bn_i}.running_var"]
@@ -36,32 +73,34 @@ def _double_conv(x, sd, prefix, training, taps):
                          BN_MOMENTUM, BN_EPS)
         if training:
             sd[f"{prefix}.{bn_i}.num_batches_tracked"] += 1
-        x = F.relu(x)
+        x = store(F.relu(x))
         if taps is not None:
             taps[f"{prefix}.{bn_i + 1}"] = x
     return x
 
 
-def unet3d_forward(x, sd, training=False, taps=None):
+def unet3d_forward(x, sd, training=False, taps=None, store=None):
     """logits = UNet3D(x).  `sd` has the reference's 136 state_dict keys; `taps` (dict) collects per-layer outputs
-    keyed by the reference module path (conv outputs at '.0'/'.3', post-ReLU at '.2'/'.5')."""
+    keyed by the reference module path (conv outputs at '.0'/'.3', post-ReLU at '.2'/'.5').  store: see above."""
+    wop = _OperandBF16.apply if store is not None else _ident
+    st = store or _ident
     skips = []
-    h = _double_conv(x, sd, "inc.conv", training, taps)
+    h = _double_conv(st(x), sd, "inc.conv", training, taps, store)
     skips.append(h)
     for k in (1, 2, 3, 4):
         h = F.max_pool3d(h, 2)
-        h = _double_conv(h, sd, f"down{k}.maxpool_conv.1.conv", training, taps)
+        h = _double_conv(h, sd, f"down{k}.maxpool_conv.1.conv", training, taps, store)
         if k < 4:
             skips.append(h)
     for j in (1, 2, 3, 4):
         skip = skips[4 - j]
-        h = F.conv_transpose3d(h, sd[f"up{j}.up.weight"], sd[f"up{j}.up.bias"], stride=2)
+        h = st(F.conv_transpose3d(h, wop(sd[f"up{j}.up.weight"]), sd[f"up{j}.up.bias"], stride=2))
         if taps is not None:
             taps[f"up{j}.up"] = h
         dz, dy, dx = (skip.shape[2] - h.shape[2], skip.shape[3] - h.shape[3], skip.shape[4] - h.shape[4])
         h = F.pad(h, [dx // 2, dx - dx // 2, dy // 2, dy - dy // 2, dz // 2, dz - dz // 2])
         h = torch.cat([skip, h], dim=1)
-        h = _double_conv(h, sd, f"up{j}.conv.conv", training, taps)
+        h = _double_conv(h, sd, f"up{j}.conv.conv", training, taps, store)
     return F.conv3d(h, sd["outc.weight"], sd["outc.bias"])
 
 

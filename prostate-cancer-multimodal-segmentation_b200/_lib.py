@@ -29,6 +29,10 @@ SIGNATURES = {
     "b200_abi_version": (_i32, []),
     "b200_sm_count": (_i32, []),
     "b200_pack_input": (_i32, [_vp, _i64, _i64, _i64, _i64, _i64, _AP, _vp]),
+    "b200_im2col_input": (_i32, [_vp, _i64, _i64, _i64, _i64, _i64, _AP, _vp]),
+    "b200_pack_rows": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp]),
+    "b200_conv1_fprop": (_i32, [_AP, _vp, _vp, _AP, _vp, _i32, _vp, _vp, _vp]),
+    "b200_conv1_wgrad": (_i32, [_AP, _AP, _vp, _i32, _vp]),
     "b200_pack_conv_weight": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "b200_pack_convt_weight": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "b200_conv3d_mtiles": (_i64, [_i64, _i64, _i64, _i64]),

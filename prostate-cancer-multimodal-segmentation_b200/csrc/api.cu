@@ -206,7 +206,7 @@ static void set_out(IgemmParams& p, const b200_act* y) {
 
 // shared by fprop (sign = +1) and dgrad (sign = -1): 27 taps over one activation map
 static int conv3_igemm(const b200_act* in, const void* w_packed, const b200_act* out, int sign, int mode,
-                       const float* v0, const float* v1, float* stats, cudaStream_t s) {
+                       const float* v0, const float* v1, float* stats, cudaStream_t s, int ntaps = 27) {
     int rc = get_encode();
     if (rc) return rc;
     REQUIRE(in->n == out->n && in->d == out->d && in->h == out->h && in->w == out->w, "conv3d: extent mismatch");
@@ -220,14 +220,14 @@ static int conv3_igemm(const b200_act* in, const void* w_packed, const b200_act*
                       in->ld, in->w, in->h, in->d, 1, b.tw, b.th, b.td);
     if (rc) return rc;
     p.block_n = igemm_block_n(out->c);
-    rc = make_weight_map(&p.b_map, w_packed, in->c, out->c, 27, p.block_n);
+    rc = make_weight_map(&p.b_map, w_packed, in->c, out->c, ntaps, p.block_n);
     if (rc) return rc;
-    p.ntaps = 27;
-    for (int t = 0; t < 27; ++t) {
+    p.ntaps = ntaps;
+    for (int t = 0; t < ntaps; ++t) {
         p.a_map_of_tap[t] = 0;
-        p.tap_dd[t] = sign * (t / 9 - 1);
-        p.tap_dh[t] = sign * ((t / 3) % 3 - 1);
-        p.tap_dw[t] = sign * (t % 3 - 1);
+        p.tap_dd[t] = ntaps == 1 ? 0 : sign * (t / 9 - 1);
+        p.tap_dh[t] = ntaps == 1 ? 0 : sign * ((t / 3) % 3 - 1);
+        p.tap_dw[t] = ntaps == 1 ? 0 : sign * (t % 3 - 1);
     }
     p.cin = (int)in->c;
     p.kc_blocks = (int)((in->c + 63) / 64);
@@ -251,9 +251,21 @@ extern "C" int b200_conv3d_stat_rows(int64_t n, int64_t d, int64_t h, int64_t w,
     return (int)(tiles < sms ? tiles : sms);
 }
 
+static int fprop_impl(const b200_act* x, const void* w_fprop, const float* bias, const b200_act* y,
+                      float* stats_partial, int mode, const float* scale, const float* shift, void* stream, int ntaps);
 extern "C" int b200_conv3d_fprop(const b200_act* x, const void* w_fprop, const float* bias, const b200_act* y,
                                  float* stats_partial, int mode, const float* scale, const float* shift,
                                  void* stream) {
+    return fprop_impl(x, w_fprop, bias, y, stats_partial, mode, scale, shift, stream, 27);
+}
+extern "C" int b200_conv1_fprop(const b200_act* x, const void* w_rows, const float* bias, const b200_act* y,
+                                float* stats_partial, int mode, const float* scale, const float* shift,
+                                void* stream) {
+    return fprop_impl(x, w_rows, bias, y, stats_partial, mode, scale, shift, stream, 1);
+}
+static int fprop_impl(const b200_act* x, const void* w_fprop, const float* bias, const b200_act* y,
+                      float* stats_partial, int mode, const float* scale, const float* shift, void* stream,
+                      int ntaps) {
     CHECK_VIEW(x);
     CHECK_VIEW(y);
     REQUIRE(w_fprop != nullptr, "conv3d_fprop: null weights");
@@ -275,7 +287,7 @@ extern "C" int b200_conv3d_fprop(const b200_act* x, const void* w_fprop, const f
             break;
         default: return fail(B200_ERR_BAD_ARG, "conv3d_fprop: unknown mode %d", mode);
     }
-    return conv3_igemm(x, w_fprop, y, +1, mode, v0, v1, stats_partial, (cudaStream_t)stream);
+    return conv3_igemm(x, w_fprop, y, +1, mode, v0, v1, stats_partial, (cudaStream_t)stream, ntaps);
 }
 
 extern "C" int b200_conv3d_dgrad(const b200_act* dy, const void* w_dgrad, const b200_act* dx, void* stream) {
@@ -443,6 +455,36 @@ extern "C" int b200_conv3d_wgrad(const b200_act* x, const b200_act* dy, float* d
     return launch_wgrad(p, (cudaStream_t)stream);
 }
 
+extern "C" int b200_conv1_wgrad(const b200_act* x, const b200_act* dy, float* dw, int k_real, void* stream) {
+    CHECK_VIEW(x);
+    CHECK_VIEW(dy);
+    REQUIRE(dw != nullptr, "conv1_wgrad: null dw");
+    REQUIRE(x->n == dy->n && x->d == dy->d && x->h == dy->h && x->w == dy->w, "conv1_wgrad: extent mismatch");
+    REQUIRE(k_real > 0 && k_real <= x->c, "conv1_wgrad: k_real out of range");
+    int rc = get_encode();
+    if (rc) return rc;
+    WgradParams p;
+    memset(&p, 0, sizeof(p));
+    const Brick b = choose_brick(x->w, x->h, x->d);
+    rc = make_act_map(&p.p_map, reinterpret_cast<const __nv_bfloat16*>(dy->ptr), dy->c, dy->w, dy->h, dy->d, dy->n,
+                      dy->ld, dy->w, dy->h, dy->d, 1, b.tw, b.th, b.td);
+    if (rc) return rc;
+    rc = make_act_map(&p.q_map[0], reinterpret_cast<const __nv_bfloat16*>(x->ptr), x->c, x->w, x->h, x->d, x->n,
+                      x->ld, x->w, x->h, x->d, 1, b.tw, b.th, b.td);
+    if (rc) return rc;
+    p.ntaps = 1;
+    p.p_extent = (int)dy->c;
+    p.q_extent = k_real;
+    p.q_chunks = (k_real + 63) / 64;
+    p.nbw = (int)b.nbw; p.nbh = (int)b.nbh; p.nbd = (int)b.nbd; p.nbatch = (int)x->n;
+    p.tw = b.tw; p.th = b.th; p.td = b.td;
+    p.out = dw;
+    p.st = 0;
+    p.sp = k_real;
+    p.sq = 1;
+    return launch_wgrad(p, (cudaStream_t)stream);
+}
+
 extern "C" int b200_convt2x_wgrad(const b200_act* x, const b200_act* dy, int pad_d, int pad_h, int pad_w, float* dw,
                                   void* stream) {
     CHECK_VIEW(x);
@@ -488,6 +530,21 @@ extern "C" int b200_pack_input(const float* x, int64_t n, int64_t c, int64_t d, 
     REQUIRE(x != nullptr, "pack_input: null input");
     REQUIRE(out->n == n && out->d == d && out->h == h && out->w == w && out->c >= c, "pack_input: extent mismatch");
     CUDA_TRY(launch_pack_input(x, n, c, d, h, w, to_view(out), (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int b200_im2col_input(const float* x, int64_t n, int64_t c, int64_t d, int64_t h, int64_t w,
+                                 const b200_act* out, void* stream) {
+    CHECK_VIEW(out);
+    REQUIRE(x != nullptr, "im2col_input: null input");
+    REQUIRE(out->n == n && out->d == d && out->h == h && out->w == w && out->c >= 27 * c && out->c % 16 == 0,
+            "im2col_input: output view must have the input's extent and >= 27*C channels (multiple of 16)");
+    REQUIRE(out->c <= 512, "im2col_input: 27*C too large for the im2col path");
+    CUDA_TRY(launch_im2col_input(x, n, c, d, h, w, to_view(out), (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int b200_pack_rows(const float* w, int rows, int k, int k_pad, void* out, void* stream) {
+    REQUIRE(w && out && rows > 0 && k > 0 && k_pad >= k, "pack_rows: bad arguments");
+    CUDA_TRY(launch_pack_rows(w, rows, k, k_pad, reinterpret_cast<__nv_bfloat16*>(out), (cudaStream_t)stream));
     return 0;
 }
 extern "C" int b200_pack_conv_weight(const float* w, int cout, int cin, int cin_pad, void* w_fprop, void* w_dgrad,

@@ -81,6 +81,77 @@ cudaError_t launch_pack_input(const float* x, long long n, long long c, long lon
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------ im2col of the input
+// First conv (Cin = n_modalities = 5): K = 27*5 = 135 is too thin for 27 separate 64-channel TMA boxes, so the input
+// is expanded once to rows of kpad = pad16(27*C) bf16, column k = c*27 + tap (tap = kd*9+kh*3+kw): exactly the
+// flattened (C,3,3,3) weight layout, so the layer becomes a plain GEMM (1 tap) for fprop and wgrad.
+constexpr int kI2cVox = 128;
+__global__ void __launch_bounds__(256) im2col_input_kernel(const float* __restrict__ x, int c_in, int D, int H, int W,
+                                                           long long nvox, View out) {
+    extern __shared__ uint32_t i2c_smem[];  // [128][kpad/2 + 1] packed bf16 pairs (row pitch padded: conflict-free)
+    const int kpad = (int)out.c, pitch = kpad / 2 + 1;
+    const long long v0 = (long long)blockIdx.x * kI2cVox;
+    const int vl = threadIdx.x & (kI2cVox - 1), half = threadIdx.x >> 7;  // 2 threads per voxel, alternating pairs
+    const long long v = v0 + vl;
+    const long long plane = (long long)D * H * W;
+    if (v < nvox) {
+        const long long nb = v / plane;
+        long long r = v - nb * plane;
+        const int d = (int)(r / ((long long)H * W));
+        r -= (long long)d * H * W;
+        const int h = (int)(r / W), w = (int)(r - (long long)h * W);
+        const float* xb = x + nb * c_in * plane;
+        for (int kp = half; kp < kpad / 2; kp += 2) {
+            float f[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int k = 2 * kp + e;
+                float val = 0.f;
+                if (k < 27 * c_in) {
+                    const int c = k / 27, t = k - c * 27;
+                    const int dd = d + t / 9 - 1, hh = h + (t / 3) % 3 - 1, ww = w + t % 3 - 1;
+                    if (dd >= 0 && dd < D && hh >= 0 && hh < H && ww >= 0 && ww < W)
+                        val = __ldg(xb + c * plane + ((long long)dd * H + hh) * W + ww);
+                }
+                f[e] = val;
+            }
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(f[0], f[1]);
+            i2c_smem[vl * pitch + kp] = *reinterpret_cast<uint32_t*>(&b2);
+        }
+    }
+    __syncthreads();
+    const int words_per_row = kpad / 2;
+    const long long rows = (nvox - v0) < kI2cVox ? (nvox - v0) : kI2cVox;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(out.p + v0 * out.ld);
+    const int ld_words = (int)(out.ld / 2);
+    for (int i = threadIdx.x; i < rows * words_per_row; i += blockDim.x) {
+        const int row = i / words_per_row, col = i - row * words_per_row;
+        dst[(long long)row * ld_words + col] = i2c_smem[row * pitch + col];
+    }
+}
+cudaError_t launch_im2col_input(const float* x, long long n, long long c, long long d, long long h, long long w,
+                                View out, cudaStream_t s) {
+    const long long nvox = n * d * h * w;
+    const int smem = kI2cVox * ((int)out.c / 2 + 1) * 4;
+    const long long blocks = (nvox + kI2cVox - 1) / kI2cVox;
+    im2col_input_kernel<<<(unsigned)blocks, 256, smem, s>>>(x, (int)c, (int)d, (int)h, (int)w, nvox, out);
+    return cudaGetLastError();
+}
+
+// fp32 [rows][k] -> bf16 [rows][kpad] (zero padded): GEMM-form weights of the im2col'd first conv
+__global__ void pack_rows_kernel(const float* __restrict__ w, int rows, int k, int kpad, __nv_bfloat16* out) {
+    const long long total = (long long)rows * kpad;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / kpad), col = (int)(i - (long long)r * kpad);
+        out[i] = __float2bfloat16_rn(col < k ? __ldg(w + (long long)r * k + col) : 0.f);
+    }
+}
+cudaError_t launch_pack_rows(const float* w, int rows, int k, int kpad, __nv_bfloat16* out, cudaStream_t s) {
+    pack_rows_kernel<<<grid_for((long long)rows * kpad, 256, 148, 8), 256, 0, s>>>(w, rows, k, kpad, out);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------ pack weights
 // one block = 32 output channels x 32 input channels x 27 taps staged through shared memory
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int cout, int cin, int cin_pad,
@@ -161,18 +232,41 @@ cudaError_t launch_pack_convt_weight(const float* w, const float* bias, int cin,
 }
 
 // ------------------------------------------------------------------------------------------------ BN finalize
-__global__ void bn_finalize_kernel(const float* __restrict__ partial, int rows, double inv_count, double unbias,
-                                   int c, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                   float momentum, float* rm, float* rv, float* mean, float* rstd, float* scale,
-                                   float* shift) {
-    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ch >= c) return;
-    double s = 0.0, q = 0.0;
-    for (int r = 0; r < rows; ++r) {
-        const float2 v = __ldg(reinterpret_cast<const float2*>(partial) + (long long)r * c + ch);
-        s += v.x;
-        q += v.y;
+// partial[rows][c][2] -> per-channel (sum0, sum1) in double; block = 32 channels x 8 row slices
+DEV void reduce_partials(const float* __restrict__ partial, int rows, int c, int ch, int slice, double (&red)[8][32][2],
+                         double& s0, double& s1) {
+    double a = 0.0, b = 0.0;
+    if (ch < c) {
+        for (int r = slice; r < rows; r += 8) {
+            const float2 v = __ldg(reinterpret_cast<const float2*>(partial) + (long long)r * c + ch);
+            a += v.x;
+            b += v.y;
+        }
     }
+    red[slice][threadIdx.x & 31][0] = a;
+    red[slice][threadIdx.x & 31][1] = b;
+    __syncthreads();
+    s0 = s1 = 0.0;
+    if (slice == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            s0 += red[k][threadIdx.x & 31][0];
+            s1 += red[k][threadIdx.x & 31][1];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ partial, int rows,
+                                                          double inv_count, double unbias, int c,
+                                                          const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, float eps, float momentum,
+                                                          float* rm, float* rv, float* mean, float* rstd, float* scale,
+                                                          float* shift) {
+    __shared__ double red[8][32][2];
+    const int ch = blockIdx.x * 32 + (threadIdx.x & 31), slice = threadIdx.x >> 5;
+    double s, q;
+    reduce_partials(partial, rows, c, ch, slice, red, s, q);
+    if (slice != 0 || ch >= c) return;
     const double mu = s * inv_count;
     double var = q * inv_count - mu * mu;
     if (var < 0.0) var = 0.0;
@@ -190,8 +284,8 @@ cudaError_t launch_bn_finalize(const float* partial, long long rows, long long c
                                const float* beta, float eps, float momentum, float* rm, float* rv, float* mean,
                                float* rstd, float* scale, float* shift, cudaStream_t s) {
     const double unbias = count > 1 ? (double)count / (double)(count - 1) : 1.0;
-    bn_finalize_kernel<<<(c + 127) / 128, 128, 0, s>>>(partial, (int)rows, 1.0 / (double)count, unbias, c, gamma,
-                                                      beta, eps, momentum, rm, rv, mean, rstd, scale, shift);
+    bn_finalize_kernel<<<(c + 31) / 32, 256, 0, s>>>(partial, (int)rows, 1.0 / (double)count, unbias, c, gamma, beta,
+                                                    eps, momentum, rm, rv, mean, rstd, scale, shift);
     return cudaGetLastError();
 }
 
@@ -316,16 +410,14 @@ cudaError_t launch_bn_bwd_reduce(View dout, View y, const float* scale, const fl
     return cudaGetLastError();
 }
 
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int c, double inv_count,
-                                       float* dgamma, float* dbeta, float* coef) {
-    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ch >= c) return;
-    double s1 = 0.0, s2 = 0.0;
-    for (int b = 0; b < nblk; ++b) {
-        const float2 v = __ldg(reinterpret_cast<const float2*>(partial) + (long long)b * c + ch);
-        s1 += v.x;
-        s2 += v.y;
-    }
+__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int c,
+                                                              double inv_count, float* dgamma, float* dbeta,
+                                                              float* coef) {
+    __shared__ double red[8][32][2];
+    const int ch = blockIdx.x * 32 + (threadIdx.x & 31), slice = threadIdx.x >> 5;
+    double s1, s2;
+    reduce_partials(partial, nblk, c, ch, slice, red, s1, s2);
+    if (slice != 0 || ch >= c) return;
     if (dbeta) dbeta[ch] += (float)s1;
     if (dgamma) dgamma[ch] += (float)s2;
     coef[2 * ch] = (float)(s1 * inv_count);
@@ -333,7 +425,7 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nb
 }
 cudaError_t launch_bn_bwd_finalize(const float* partial, int nblk, int c, long long count, float* dgamma,
                                    float* dbeta, float* coef, cudaStream_t s) {
-    bn_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, s>>>(partial, nblk, c, 1.0 / (double)count, dgamma, dbeta, coef);
+    bn_bwd_finalize_kernel<<<(c + 31) / 32, 256, 0, s>>>(partial, nblk, c, 1.0 / (double)count, dgamma, dbeta, coef);
     return cudaGetLastError();
 }
 

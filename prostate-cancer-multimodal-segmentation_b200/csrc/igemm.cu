@@ -31,7 +31,7 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __g
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform role index
     const int lane = threadIdx.x & 31;
     const uint32_t nst = p.stages;
     const uint32_t b_bytes = p.block_n * 128;
@@ -74,35 +74,46 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __g
 
     const int m_tiles = p.nbw * p.nbh * p.nbd * p.nbatch;
     const int total_tiles = m_tiles * p.n_tiles;
-    const int kblocks = p.ntaps * p.kc_blocks;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 0) {
         // ===================================================================== TMA producer
+        // The whole warp walks the loop (uniform control flow, barrier polls by all lanes); one elected lane issues.
         PipeState ps;
+        const int kc_blocks = p.kc_blocks, ntaps = p.ntaps, n_tiles = p.n_tiles;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            int mt = tile / p.n_tiles;
-            const int n_tile = tile - mt * p.n_tiles;
+            int mt = tile / n_tiles;
+            const int n_tile = tile - mt * n_tiles;
             const int bw = mt % p.nbw; mt /= p.nbw;
             const int bh = mt % p.nbh; mt /= p.nbh;
             const int bd = mt % p.nbd; mt /= p.nbd;
             const int nb = mt;
             const int w0 = bw << p.tw_log2, h0 = bh << p.th_log2, d0 = bd << p.td_log2;
             const int n0 = n_tile * p.block_n;
-            for (int tap = 0; tap < p.ntaps; ++tap) {
+            for (int tap = 0; tap < ntaps; ++tap) {
                 const void* amap = &p.a_map[p.a_map_of_tap[tap]];
                 const int cw = w0 + p.tap_dw[tap], ch = h0 + p.tap_dh[tap], cd = d0 + p.tap_dd[tap];
-                for (int kc = 0; kc < p.kc_blocks; ++kc) {
+                for (int kc = 0; kc < kc_blocks; ++kc) {
                     mbar_wait(empty_bar(ps.stage), ps.phase ^ 1);
-                    mbar_arrive_expect_tx(full_bar(ps.stage), kBoxBytes + b_bytes);
-                    tma_load_5d(smem_a + ps.stage * kBoxBytes, amap, full_bar(ps.stage), kc * 64, cw, ch, cd, nb);
-                    tma_load_3d(smem_b + ps.stage * b_bytes, &p.b_map, full_bar(ps.stage), kc * 64, n0, tap);
+                    if (elect_one()) {
+                        const uint32_t fb = full_bar(ps.stage);
+                        mbar_arrive_expect_tx(fb, kBoxBytes + b_bytes);
+                        tma_load_5d(smem_a + ps.stage * kBoxBytes, amap, fb, kc * 64, cw, ch, cd, nb);
+                        tma_load_3d(smem_b + ps.stage * b_bytes, &p.b_map, fb, kc * 64, n0, tap);
+                    }
+                    __syncwarp();
                     ps.advance(nst);
                 }
             }
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
         // ===================================================================== MMA issuer
+        // Lean loop: descriptors are base + stage offset (low word only), no divisions, one elected lane issues.
         const uint32_t idesc = make_idesc_bf16(128, p.block_n, 0, 0);
+        const uint64_t a_desc0 = make_smem_desc_sw128(smem_a, 0, 1024);
+        const uint64_t b_desc0 = make_smem_desc_sw128(smem_b, 0, 1024);
+        const uint32_t a_step = kBoxBytes >> 4, b_step = b_bytes >> 4;
+        const int kc_blocks = p.kc_blocks, ntaps = p.ntaps;
+        const int nk_last = ((p.cin - (kc_blocks - 1) * 64) + 15) >> 4;  // K steps of the last channel block (1..4)
         PipeState ps;
         int iter = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
@@ -110,22 +121,29 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __g
             mbar_wait(tempty_bar(acc), acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * p.block_n;
-            for (int kb = 0; kb < kblocks; ++kb) {
-                const int kc = kb % p.kc_blocks;
-                const int krem = p.cin - kc * 64;
-                const int nk = krem >= 64 ? 4 : ((krem + 15) >> 4);
-                mbar_wait(full_bar(ps.stage), ps.phase);
-                tc_fence_after();
-                const uint64_t a_desc = make_smem_desc_sw128(smem_a + ps.stage * kBoxBytes, 0, 1024);
-                const uint64_t b_desc = make_smem_desc_sw128(smem_b + ps.stage * b_bytes, 0, 1024);
-                for (int k = 0; k < nk; ++k) {
-                    // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (>>4) address field
-                    umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            uint32_t accum = 0;
+            for (int tap = 0; tap < ntaps; ++tap) {
+                for (int kc = 0; kc < kc_blocks; ++kc) {
+                    const int nk = (kc == kc_blocks - 1) ? nk_last : 4;
+                    mbar_wait(full_bar(ps.stage), ps.phase);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t a_desc = a_desc0 + ps.stage * a_step;
+                        const uint64_t b_desc = b_desc0 + ps.stage * b_step;
+                        // 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (>>4) address field
+                        umma_f16(d_tmem, a_desc, b_desc, idesc, accum);
+                        if (nk > 1) umma_f16(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);
+                        if (nk > 2) umma_f16(d_tmem, a_desc + 4, b_desc + 4, idesc, 1u);
+                        if (nk > 3) umma_f16(d_tmem, a_desc + 6, b_desc + 6, idesc, 1u);
+                        umma_commit(empty_bar(ps.stage));
+                    }
+                    __syncwarp();
+                    accum = 1u;
+                    ps.advance(nst);
                 }
-                umma_commit(empty_bar(ps.stage));
-                ps.advance(nst);
             }
-            umma_commit(tfull_bar(acc));
+            if (elect_one()) umma_commit(tfull_bar(acc));
+            __syncwarp();
         }
     } else if (warp >= 4) {
         // ===================================================================== epilogue
@@ -268,7 +286,7 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __g
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
 
     constexpr uint32_t kPSlot = 2 * kBoxBytes, kQSlot = 4 * kBoxBytes, kNP = 2, kNQ = 2;
@@ -312,8 +330,8 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __g
     const int nsg = (ncb + 3) >> 2;  // slot groups of up to 4 column blocks (UMMA N up to 256)
     const int nbricks = p.nbw * p.nbh * p.nbd * p.nbatch;
 
-    if (warp == 0 && lane == 0) {
-        // ===================================================================== TMA producer
+    if (warp == 0) {
+        // ===================================================================== TMA producer (whole warp, elected issue)
         PipeState pp, qp;
         for (int b = split; b < nbricks; b += p.splits) {
             int mt = b;
@@ -323,52 +341,67 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __g
             const int nb = mt;
             const int w0 = bw * p.tw, h0 = bh * p.th, d0 = bd * p.td;
             mbar_wait(pempty(pp.stage), pp.phase ^ 1);
-            mbar_arrive_expect_tx(pfull(pp.stage), 2 * kBoxBytes);
-            tma_load_5d(smem_p + pp.stage * kPSlot, &p.p_map, pfull(pp.stage), p0, w0, h0, d0, nb);
-            tma_load_5d(smem_p + pp.stage * kPSlot + kBoxBytes, &p.p_map, pfull(pp.stage), p0 + 64, w0, h0, d0, nb);
+            if (elect_one()) {
+                const uint32_t fb = pfull(pp.stage);
+                mbar_arrive_expect_tx(fb, 2 * kBoxBytes);
+                tma_load_5d(smem_p + pp.stage * kPSlot, &p.p_map, fb, p0, w0, h0, d0, nb);
+                tma_load_5d(smem_p + pp.stage * kPSlot + kBoxBytes, &p.p_map, fb, p0 + 64, w0, h0, d0, nb);
+            }
+            __syncwarp();
             pp.advance(kNP);
             for (int sg = 0; sg < nsg; ++sg) {
                 const int nb4 = min(4, ncb - sg * 4);
                 mbar_wait(qempty(qp.stage), qp.phase ^ 1);
-                mbar_arrive_expect_tx(qfull(qp.stage), nb4 * kBoxBytes);
-                for (int i = 0; i < nb4; ++i) {
-                    const int cb = cb0 + sg * 4 + i;
-                    const int tap = cb / p.q_chunks;
-                    const int qc = cb - tap * p.q_chunks;
-                    tma_load_5d(smem_q + qp.stage * kQSlot + i * kBoxBytes, &p.q_map[p.q_map_of_tap[tap]],
-                                qfull(qp.stage), qc * 64, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap],
-                                d0 + p.tap_dd[tap], nb);
+                if (elect_one()) {
+                    const uint32_t fb = qfull(qp.stage);
+                    mbar_arrive_expect_tx(fb, nb4 * kBoxBytes);
+                    for (int i = 0; i < nb4; ++i) {
+                        const int cb = cb0 + sg * 4 + i;
+                        const int tap = cb / p.q_chunks;
+                        const int qc = cb - tap * p.q_chunks;
+                        tma_load_5d(smem_q + qp.stage * kQSlot + i * kBoxBytes, &p.q_map[p.q_map_of_tap[tap]], fb,
+                                    qc * 64, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], d0 + p.tap_dd[tap], nb);
+                    }
                 }
+                __syncwarp();
                 qp.advance(kNQ);
             }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ===================================================================== MMA issuer
+    } else if (warp == 1) {
+        // ===================================================================== MMA issuer (whole warp, elected issue)
         PipeState pp, qp;
-        int it = 0;
-        for (int b = split; b < nbricks; b += p.splits, ++it) {
+        // MN-major SWIZZLE_128B operands: 64-channel atoms (16 KB boxes) LBO apart, 8-voxel groups SBO apart
+        const uint64_t a_desc0 = make_smem_desc_sw128(smem_p, kBoxBytes, 1024);
+        const uint64_t b_desc0 = make_smem_desc_sw128(smem_q, kBoxBytes, 1024);
+        uint32_t accum = 0;
+        for (int b = split; b < nbricks; b += p.splits) {
             mbar_wait(pfull(pp.stage), pp.phase);
             tc_fence_after();
-            // MN-major SWIZZLE_128B operands: 64-channel atoms (16 KB boxes) LBO apart, 8-voxel groups SBO apart
-            const uint64_t a_desc = make_smem_desc_sw128(smem_p + pp.stage * kPSlot, kBoxBytes, 1024);
+            const uint64_t a_desc = a_desc0 + pp.stage * (kPSlot >> 4);
             for (int sg = 0; sg < nsg; ++sg) {
                 const int nb4 = min(4, ncb - sg * 4);
                 const uint32_t idesc = make_idesc_bf16(128, 64 * nb4, 1, 1);
                 mbar_wait(qfull(qp.stage), qp.phase);
                 tc_fence_after();
-                const uint64_t b_desc = make_smem_desc_sw128(smem_q + qp.stage * kQSlot, kBoxBytes, 1024);
-                for (int k = 0; k < 8; ++k) {
+                if (elect_one()) {
+                    const uint64_t b_desc = b_desc0 + qp.stage * (kQSlot >> 4);
+                    const uint32_t d_tmem = tmem_base + sg * 256;
                     // 16 voxels = 16 rows x 128 B = 2048 B along K: +128 in the (>>4) address field
-                    umma_f16(tmem_base + sg * 256, a_desc + 128 * k, b_desc + 128 * k, idesc,
-                             (it > 0 || k > 0) ? 1u : 0u);
+                    umma_f16(d_tmem, a_desc, b_desc, idesc, accum);
+#pragma unroll
+                    for (int k = 1; k < 8; ++k) umma_f16(d_tmem, a_desc + 128 * k, b_desc + 128 * k, idesc, 1u);
+                    umma_commit(qempty(qp.stage));
                 }
-                umma_commit(qempty(qp.stage));
+                __syncwarp();
                 qp.advance(kNQ);
             }
-            umma_commit(pempty(pp.stage));
+            if (elect_one()) umma_commit(pempty(pp.stage));
+            __syncwarp();
+            accum = 1u;
             pp.advance(kNP);
         }
-        umma_commit(tfull);
+        if (elect_one()) umma_commit(tfull);
+        __syncwarp();
     } else if (warp >= 4) {
         // ===================================================================== epilogue
         const int q = warp - 4;

@@ -26,17 +26,53 @@ def _pad16(c: int) -> int:
 
 
 class _ConvPack:
-    """bf16 operand shadows of one Conv3d 3x3x3"""
+    """bf16 operand shadows of one Conv3d 3x3x3.
+
+    Thin inputs (Cin not a multiple of 16, i.e. the 5-modality first layer) use the im2col form: the input is
+    expanded to rows of pad16(27*Cin) columns and the conv runs as a 1-tap GEMM on the flattened weights."""
 
     def __init__(self, conv, device):
         self.conv = conv
         self.cout, self.cin = conv.out_channels, conv.in_channels
-        self.cin_pad = _pad16(self.cin)
-        self.wf = torch.empty(27, self.cout, self.cin_pad, device=device, dtype=torch.bfloat16)
-        self.wd = torch.empty(27, self.cin_pad, self.cout, device=device, dtype=torch.bfloat16)
+        self.im2col = self.cin % 16 != 0 and 27 * self.cin <= 512
+        if self.im2col:
+            self.k_real = 27 * self.cin
+            self.cin_pad = _pad16(self.k_real)  # width of the im2col rows
+            self.wf = torch.empty(self.cout, self.cin_pad, device=device, dtype=torch.bfloat16)
+            self.wd = None
+        else:
+            self.k_real = self.cin
+            self.cin_pad = _pad16(self.cin)
+            self.wf = torch.empty(27, self.cout, self.cin_pad, device=device, dtype=torch.bfloat16)
+            self.wd = torch.empty(27, self.cin_pad, self.cout, device=device, dtype=torch.bfloat16)
 
     def pack(self):
-        ops.pack_conv_weight(self.conv.weight.data, self.cin_pad, self.wf, self.wd)
+        if self.im2col:
+            ops.pack_rows(self.conv.weight.data, self.cin_pad, self.wf)
+        else:
+            ops.pack_conv_weight(self.conv.weight.data, self.cin_pad, self.wf, self.wd)
+
+    def make_input(self, x: torch.Tensor) -> ActView:
+        """fp32 (N,C,D,H,W) -> the bf16 operand this conv reads (channel-padded NDHWC, or im2col rows)"""
+        n, _, d, h, w = x.shape
+        v = ActView(new_act(n, d, h, w, self.cin_pad, x.device))
+        (ops.im2col_input if self.im2col else ops.pack_input)(x, v)
+        return v
+
+    def fprop(self, xin, bias, y, stats, mode, scale=None, shift=None):
+        f = ops.conv1_fprop if self.im2col else ops.conv3d_fprop
+        f(xin, self.wf, bias, y, stats, mode, scale, shift, k_real=self.k_real)
+
+    def wgrad(self, xin, dy, dw):
+        if self.im2col:
+            ops.conv1_wgrad(xin, dy, dw.view(self.cout, -1), self.k_real)
+        else:
+            ops.conv3d_wgrad(xin, dy, dw, self.cin)
+
+    def dgrad(self, dy, dx):
+        if self.im2col:
+            raise B200Error("input gradient of an im2col'd (thin-input) convolution is not available")
+        ops.conv3d_dgrad(dy, self.wd, dx)
 
 
 class _ConvTPack:
@@ -80,7 +116,7 @@ class _DoubleConv:
         y = ActView(new_act(n, d, h, w, cout, dev))
         rows = ops.conv3d_stat_rows(n, d, h, w, cout)
         stats = torch.empty(rows, cout, 2, device=dev, dtype=torch.float32)
-        ops.conv3d_fprop(xin, pack.wf, pack.conv.bias.data, y, stats, ops.EPI_BIAS_STATS, k_real=pack.cin)
+        pack.fprop(xin, pack.conv.bias.data, y, stats, ops.EPI_BIAS_STATS)
         vec = torch.empty(4, cout, device=dev, dtype=torch.float32)  # mean, rstd, scale, shift
         momentum = bn.momentum
         if bn.track_running_stats:
@@ -99,7 +135,7 @@ class _DoubleConv:
         vec = torch.empty(2, pack.cout, device=dev, dtype=torch.float32)
         ops.bn_fold_eval(bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var, pack.conv.bias.data, bn.eps,
                          vec[0], vec[1])
-        ops.conv3d_fprop(xin, pack.wf, None, out, None, ops.EPI_AFFINE_RELU, vec[0], vec[1], k_real=pack.cin)
+        pack.fprop(xin, None, out, None, ops.EPI_AFFINE_RELU, vec[0], vec[1])
 
     def forward(self, xin: ActView, out: ActView, training: bool):
         n, d, h, w, _ = xin.shape
@@ -125,17 +161,17 @@ class _DoubleConv:
         dy2 = ActView(new_act(n, d, h, w, self.cout, dev))
         ops.bn_bwd(dout, st.y2, st.bn2[2], st.bn2[3], st.bn2[0], st.bn2[1], self.bn2.weight.data, scratch.partial,
                    scratch.coef, g(self.bn2.weight), g(self.bn2.bias), dy2, g(self.conv2.bias))
-        ops.conv3d_wgrad(st.a1, dy2, g(self.conv2.weight), self.p2.cin)
+        self.p2.wgrad(st.a1, dy2, g(self.conv2.weight))
         da1 = ActView(new_act(n, d, h, w, self.cout, dev))
-        ops.conv3d_dgrad(dy2, self.p2.wd, da1)
+        self.p2.dgrad(dy2, da1)
         st.y2 = None
         # first conv (dy1 reuses dy2's buffer)
         dy1 = dy2
         ops.bn_bwd(da1, st.y1, st.bn1[2], st.bn1[3], st.bn1[0], st.bn1[1], self.bn1.weight.data, scratch.partial,
                    scratch.coef, g(self.bn1.weight), g(self.bn1.bias), dy1, g(self.conv1.bias))
-        ops.conv3d_wgrad(st.xin, dy1, g(self.conv1.weight), self.p1.cin)
+        self.p1.wgrad(st.xin, dy1, g(self.conv1.weight))
         if dxin is not None:
-            ops.conv3d_dgrad(dy1, self.p1.wd, dxin)
+            self.p1.dgrad(dy1, dxin)
 
 
 class _Scratch:
@@ -268,8 +304,7 @@ class Engine:
 
         tape = _Tape()
         tape.dims, tape.x_shape = dims, tuple(x.shape)
-        x0 = ActView(new_act(n, D, H, W, self.inc.p1.cin_pad, dev))
-        ops.pack_input(x, x0)
+        x0 = self.inc.p1.make_input(x)
         # encoder: skip of level k lives in the lower half of cats[k]
         cats = [new_act(n, *dims[k], 2 * ch[k], dev) for k in range(4)]
         dcs = {}

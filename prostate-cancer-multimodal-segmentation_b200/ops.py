@@ -90,6 +90,35 @@ def pack_input(x: torch.Tensor, out: ActView):
     check(_lib.load().b200_pack_input(ptr(x), n, c, d, h, w, out.ref, stream_ptr()), "pack_input")
 
 
+def im2col_input(x: torch.Tensor, out: ActView):
+    _launched(1)
+    n, c, d, h, w = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    check(_lib.load().b200_im2col_input(ptr(x), n, c, d, h, w, out.ref, stream_ptr()), "im2col_input")
+
+
+def pack_rows(w: torch.Tensor, k_pad: int, out):
+    _launched(1)
+    rows = w.shape[0]
+    k = w.numel() // rows
+    assert w.dtype == torch.float32 and w.is_contiguous()
+    check(_lib.load().b200_pack_rows(ptr(w), rows, k, k_pad, ptr(out), stream_ptr()), "pack_rows")
+
+
+def conv1_fprop(x: ActView, w_rows, bias, y: ActView, stats=None, mode=EPI_BIAS_STATS, scale=None, shift=None,
+                k_real=None):
+    lib = _lib.load()
+    _gemm("igemm_kernel", "conv1_fprop", 2.0 * x.voxels * y.c * (k_real or x.c),
+          lambda: check(lib.b200_conv1_fprop(x.ref, ptr(w_rows), ptr(bias), y.ref, ptr(stats), mode, ptr(scale),
+                                             ptr(shift), stream_ptr()), "conv1_fprop"))
+
+
+def conv1_wgrad(x: ActView, dy: ActView, dw: torch.Tensor, k_real: int):
+    lib = _lib.load()
+    _gemm("wgrad_kernel", "conv1_wgrad", 2.0 * x.voxels * dy.c * k_real,
+          lambda: check(lib.b200_conv1_wgrad(x.ref, dy.ref, ptr(dw), k_real, stream_ptr()), "conv1_wgrad"))
+
+
 def pack_conv_weight(w: torch.Tensor, cin_pad: int, w_fprop, w_dgrad):
     _launched(1)
     cout, cin = w.shape[0], w.shape[1]

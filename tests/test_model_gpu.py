@@ -31,7 +31,7 @@ def synth(shape, seed, device):
     return x.to(device), y.to(device)
 
 
-def oracle_grads(sd, x, y, autocast_bf16=False):
+def oracle_grads(sd, x, y, autocast_bf16=False, store=None):
     """loss and parameter gradients of the oracle; with autocast_bf16 the same graph under torch's stock bf16 autocast
     (what the reference's AMP loop, train_bph_optimized.py:269, does with fp16) — the yardstick for end-to-end error"""
     names = oracle.param_names(sd)
@@ -39,7 +39,7 @@ def oracle_grads(sd, x, y, autocast_bf16=False):
     work = {k: v.clone() for k, v in sd.items()}
     work.update(leaves)
     with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast_bf16):
-        logits = oracle.unet3d_forward(x, work, training=True)
+        logits = oracle.unet3d_forward(x, work, training=True, store=store)
     loss = oracle.bce_dice_loss(logits.float(), y)
     return loss.detach(), dict(zip(names, torch.autograd.grad(loss, [leaves[k] for k in names]))), logits.detach()
 
@@ -100,13 +100,18 @@ def test_training_step_vs_reference_golden_and_oracle(pkg, cuda_dev):
     assert rel_l2(logits.detach(), o_logits) < TOL_LAYER
     assert abs(loss.item() - o_loss.item()) < 1e-3
     report, bad = check_grads_against_yardstick(model, o_grads, y_grads)
+    # the same oracle in bf16-storage mode: what the engine computes up to accumulation order
+    _, s_grads, s_logits = oracle_grads(sd0, x, y, store=oracle.store_bf16)
+    s_report = {n: rel_l2(p.grad, s_grads[n]) for n, p in model.named_parameters() if not is_dead_bias(n)}
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "grad_parity_32cube.txt"), "w") as f:
         f.write(f"logits rel-L2: ours {rel_l2(logits.detach(), o_logits):.3e}  torch-bf16-autocast "
                 f"{rel_l2(y_logits.float(), o_logits):.3e}\n# parameter  ours  torch_bf16_autocast (rel-L2 vs fp32 oracle)\n")
         for k, (a, b) in report.items():
-            f.write(f"{k} {a:.4e} {b:.4e}\n")
+            f.write(f"{k} {a:.4e} {b:.4e} vs_bf16_storage_oracle {s_report[k]:.4e}\n")
+        f.write(f"logits vs bf16-storage oracle {rel_l2(logits.detach(), s_logits):.3e}\n")
     assert not bad, f"gradient rel-L2 (ours, stock bf16 autocast) beyond max(2e-2, 2x stock): {bad}"
+    assert rel_l2(logits.detach(), s_logits) < 1e-2
     # optimizer step: parameters after Adam
     opt.step()
     torch.cuda.synchronize()
