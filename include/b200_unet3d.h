@@ -48,7 +48,7 @@ int b200_sm_count(void);
 int b200_pack_input(const float* x_ncdhw, int64_t n, int64_t c, int64_t d, int64_t h, int64_t w,
                     const b200_act* out, void* stream);
 /* Conv3d weight (Cout,Cin,3,3,3) fp32 -> w_fprop bf16 [27][Cout][cin_pad], w_dgrad bf16 [27][cin_pad][Cout]
- * (either may be NULL).  models/unet3d.py:29,35 */
+ * (either may be NULL); packed tap index t = kd*9 + kw*3 + kh (kh fastest).  models/unet3d.py:29,35 */
 int b200_pack_conv_weight(const float* w, int cout, int cin, int cin_pad, void* w_fprop, void* w_dgrad, void* stream);
 /* ConvTranspose3d weight (Cin,Cout,2,2,2) fp32 -> w_fwd bf16 [8*Cout][Cin], w_dgrad bf16 [8][Cin][Cout],
  * bias (Cout) -> bias8 fp32 [8*Cout].  models/unet3d.py:120 */
@@ -70,8 +70,9 @@ int b200_conv1_wgrad(const b200_act* x, const b200_act* dy, float* dw, int k_rea
 /* ---- 3x3x3 convolution, padding 1 (nn.Conv3d, models/unet3d.py:29,35), tcgen05 implicit GEMM ------------ */
 /* number of 128-voxel output bricks of a volume */
 int64_t b200_conv3d_mtiles(int64_t n, int64_t d, int64_t h, int64_t w);
-/* rows of stats_partial that fprop(BIAS_STATS) writes for this problem (one per persistent CTA), <0 on error */
-int b200_conv3d_stat_rows(int64_t n, int64_t d, int64_t h, int64_t w, int64_t cout);
+/* rows of stats_partial that fprop(BIAS_STATS) writes for this problem (one per persistent CTA), <0 on error;
+ * ntaps = 27 for b200_conv3d_fprop, 1 for b200_conv1_fprop */
+int b200_conv3d_stat_rows(int64_t n, int64_t d, int64_t h, int64_t w, int64_t cout, int ntaps);
 /* mode BIAS_STATS : y = bf16(conv + bias); stats_partial[row][Cout][2] = (sum, sum of squares) of stored y
  * mode AFFINE_RELU: y = relu(conv * scale + shift)   (eval-mode BatchNorm + bias folded)
  * mode BIAS / PLAIN likewise without statistics. */

@@ -114,10 +114,10 @@ static int make_act_map(CUtensorMap* map, const __nv_bfloat16* base, long long c
 }
 // 3-D map over packed weights [taps][rows][k] (k contiguous): box = (64, box_rows, 1)
 static int make_weight_map(CUtensorMap* map, const void* base, long long k, long long rows, long long taps,
-                           int box_rows) {
+                           int box_rows, int box_taps = 1) {
     cuuint64_t dims[3] = {(cuuint64_t)k, (cuuint64_t)rows, (cuuint64_t)taps};
     cuuint64_t strides[2] = {(cuuint64_t)(k * 2), (cuuint64_t)(rows * k * 2)};
-    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, (cuuint32_t)box_taps};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -154,23 +154,40 @@ static Brick choose_brick(long long w, long long h, long long d) {
 }
 
 static int igemm_block_n(long long ncols) { return ncols >= 256 ? 256 : (int)((ncols + 15) / 16 * 16); }
-static int igemm_stages(int block_n) {
-    const int per_stage = kBoxBytes + block_n * 128;
-    int st = (200 * 1024) / per_stage;
+static int igemm_stages(int a_bytes, int b_bytes) {
+    const int per_stage = a_bytes + b_bytes;
+    int st = (204 * 1024) / per_stage;
     if (st > 8) st = 8;
     if (st < 2) st = 2;
     return st;
 }
-static size_t igemm_smem(int stages, int block_n) {
-    return 1024 + (size_t)stages * (kBoxBytes + block_n * 128) + 8 * (2 * stages + 4) + 32 + 4 * 256 * 2 * 4 +
+static size_t igemm_smem(int stages, int a_bytes, int b_bytes) {
+    return 1024 + (size_t)stages * (a_bytes + b_bytes) + 8 * (2 * stages + 4) + 32 + 4 * 256 * 2 * 4 +
            (size_t)kMaxStatCols * 2 * 4;
+}
+// brick geometry of a conv3d / conv1 implicit GEMM; shared by the launcher and b200_conv3d_stat_rows
+static bool conv_geometry(long long w, long long h, long long d, long long cout, int ntaps, Brick* b) {
+    const bool halo = ntaps == 27 && igemm_block_n(cout) <= 128 && w >= 8 && h >= 16;
+    if (halo) {
+        b->tw = 8; b->th = 16; b->td = 1; b->lw = 3; b->lh = 4; b->ld = 0;
+        b->nbw = (w + 7) / 8; b->nbh = (h + 15) / 16; b->nbd = d;
+    } else {
+        *b = choose_brick(w, h, d);
+    }
+    return halo;
+}
+static void set_plain_stage(IgemmParams& p) {
+    p.group = 1;
+    p.a_stage_bytes = kBoxBytes;
+    p.a_goff[0] = p.a_goff[1] = p.a_goff[2] = 0;
+    p.stages = igemm_stages(kBoxBytes, p.block_n * 128);
 }
 
 static int launch_igemm(IgemmParams& p, cudaStream_t s, int* grid_out) {
     const int sms = sm_count();
     if (sms <= 0) return fail(B200_ERR_CUDA, "no CUDA device");
     static size_t attr_smem = 0;
-    const size_t smem = igemm_smem(p.stages, p.block_n);
+    const size_t smem = igemm_smem(p.stages, p.a_stage_bytes, p.block_n * 128 * p.group);
     {
         std::lock_guard<std::mutex> lk(g_mu);
         if (smem > attr_smem) {
@@ -215,26 +232,42 @@ static int conv3_igemm(const b200_act* in, const void* w_packed, const b200_act*
     REQUIRE(in->n * in->d * in->h * in->w < (1LL << 31), "conv3d: too many voxels");
     IgemmParams p;
     memset(&p, 0, sizeof(p));
-    const Brick b = choose_brick(in->w, in->h, in->d);
-    rc = make_act_map(&p.a_map[0], reinterpret_cast<const __nv_bfloat16*>(in->ptr), in->c, in->w, in->h, in->d, in->n,
-                      in->ld, in->w, in->h, in->d, 1, b.tw, b.th, b.td);
-    if (rc) return rc;
     p.block_n = igemm_block_n(out->c);
-    rc = make_weight_map(&p.b_map, w_packed, in->c, out->c, ntaps, p.block_n);
+    // h-halo mode: worth it when the MMA per tap is short (narrow N) and the volume holds 8 x 16 bricks
+    Brick b;
+    const bool halo = conv_geometry(in->w, in->h, in->d, out->c, ntaps, &b);
+    rc = make_act_map(&p.a_map[0], reinterpret_cast<const __nv_bfloat16*>(in->ptr), in->c, in->w, in->h, in->d, in->n,
+                      in->ld, in->w, in->h, in->d, 1, b.tw, halo ? b.th + 2 : b.th, b.td);
+    if (rc) return rc;
+    rc = make_weight_map(&p.b_map, w_packed, in->c, out->c, ntaps, p.block_n, halo ? 3 : 1);
     if (rc) return rc;
     p.ntaps = ntaps;
-    for (int t = 0; t < ntaps; ++t) {
-        p.a_map_of_tap[t] = 0;
-        p.tap_dd[t] = ntaps == 1 ? 0 : sign * (t / 9 - 1);
-        p.tap_dh[t] = ntaps == 1 ? 0 : sign * ((t / 3) % 3 - 1);
-        p.tap_dw[t] = ntaps == 1 ? 0 : sign * (t % 3 - 1);
+    if (halo) {
+        // pipeline stage tg = kd*3 + kw covers packed taps 3*tg .. 3*tg+2 (kh = 0,1,2); box origin h0 - 1
+        for (int tg = 0; tg < 9; ++tg) {
+            p.a_map_of_tap[tg] = 0;
+            p.tap_dd[tg] = sign * (tg / 3 - 1);
+            p.tap_dw[tg] = sign * (tg % 3 - 1);
+            p.tap_dh[tg] = -1;
+        }
+        p.group = 3;
+        p.a_stage_bytes = (b.th + 2) * b.tw * 128;
+        for (int g = 0; g < 3; ++g) p.a_goff[g] = ((sign > 0 ? g : 2 - g) * b.tw * 128) >> 4;
+        p.stages = igemm_stages(p.a_stage_bytes, p.block_n * 128 * 3);
+    } else {
+        for (int t = 0; t < ntaps; ++t) {  // packed tap order: t = kd*9 + kw*3 + kh
+            p.a_map_of_tap[t] = 0;
+            p.tap_dd[t] = ntaps == 1 ? 0 : sign * (t / 9 - 1);
+            p.tap_dw[t] = ntaps == 1 ? 0 : sign * ((t / 3) % 3 - 1);
+            p.tap_dh[t] = ntaps == 1 ? 0 : sign * (t % 3 - 1);
+        }
+        set_plain_stage(p);
     }
     p.cin = (int)in->c;
     p.kc_blocks = (int)((in->c + 63) / 64);
     p.ncols = (int)out->c;
     p.n_tiles = (p.ncols + p.block_n - 1) / p.block_n;
     set_m_grid(p, b, in->n, in->w, in->h, in->d);
-    p.stages = igemm_stages(p.block_n);
     p.mode = mode;
     p.vec0 = v0; p.vec1 = v1; p.stats = stats;
     set_out(p, out);
@@ -243,11 +276,13 @@ static int conv3_igemm(const b200_act* in, const void* w_packed, const b200_act*
     return launch_igemm(p, s, nullptr);
 }
 
-extern "C" int b200_conv3d_stat_rows(int64_t n, int64_t d, int64_t h, int64_t w, int64_t cout) {
+extern "C" int b200_conv3d_stat_rows(int64_t n, int64_t d, int64_t h, int64_t w, int64_t cout, int ntaps) {
     const int sms = sm_count();
     if (sms <= 0) return -1;
     const int bn = igemm_block_n(cout);
-    const long long tiles = b200_conv3d_mtiles(n, d, h, w) * ((cout + bn - 1) / bn);
+    Brick b;
+    conv_geometry(w, h, d, cout, ntaps, &b);
+    const long long tiles = n * b.nbw * b.nbh * b.nbd * ((cout + bn - 1) / bn);
     return (int)(tiles < sms ? tiles : sms);
 }
 
@@ -336,7 +371,7 @@ extern "C" int b200_convt2x_fwd(const b200_act* x, const void* w_fwd, const floa
     p.ncols = (int)ncols;
     p.n_tiles = (int)((ncols + p.block_n - 1) / p.block_n);
     set_m_grid(p, b, x->n, x->w, x->h, x->d);
-    p.stages = igemm_stages(p.block_n);
+    set_plain_stage(p);
     p.mode = EPI_BIAS;
     p.vec0 = bias8;
     set_out(p, y);
@@ -381,7 +416,7 @@ extern "C" int b200_convt2x_dgrad(const b200_act* dy, int pad_d, int pad_h, int 
     p.ncols = (int)dx->c;
     p.n_tiles = (p.ncols + p.block_n - 1) / p.block_n;
     set_m_grid(p, b, dx->n, dx->w, dx->h, dx->d);
-    p.stages = igemm_stages(p.block_n);
+    set_plain_stage(p);
     p.mode = EPI_PLAIN;
     set_out(p, dx);
     p.out_mul = 1;
@@ -429,29 +464,37 @@ extern "C" int b200_conv3d_wgrad(const b200_act* x, const b200_act* dy, float* d
     WgradParams p;
     memset(&p, 0, sizeof(p));
     const Brick b = choose_brick(x->w, x->h, x->d);
-    // dw[co, ci, t] = sum_v dy[v, co] * x[v + off(t), ci]   (P = dy unshifted, Q_t = x shifted by off(t))
-    rc = make_act_map(&p.p_map, reinterpret_cast<const __nv_bfloat16*>(dy->ptr), dy->c, dy->w, dy->h, dy->d, dy->n,
-                      dy->ld, dy->w, dy->h, dy->d, 1, b.tw, b.th, b.td);
+    // dw[co, ci, t] = sum_v dy[v, co] * x[v + off(t), ci].  The M side of the MMA is 128 channels of the un-shifted
+    // operand P; the other operand Q is read once per tap.  Put the wider tensor on M when the narrower one would
+    // leave half of the 128 rows empty:
+    //   normal : P = dy,  Q_t = x shifted by +off(t)      out[p = co][q = ci]
+    //   swapped: P = x,   Q_t = dy shifted by -off(t)     out[p = ci][q = co]   (same sum, u = v + off(t))
+    const bool swapped = dy->c <= 64 && cin_real >= 128 && cin_real == x->c;
+    const b200_act* P = swapped ? x : dy;
+    const b200_act* Q = swapped ? dy : x;
+    rc = make_act_map(&p.p_map, reinterpret_cast<const __nv_bfloat16*>(P->ptr), P->c, P->w, P->h, P->d, P->n, P->ld,
+                      P->w, P->h, P->d, 1, b.tw, b.th, b.td);
     if (rc) return rc;
-    rc = make_act_map(&p.q_map[0], reinterpret_cast<const __nv_bfloat16*>(x->ptr), x->c, x->w, x->h, x->d, x->n,
-                      x->ld, x->w, x->h, x->d, 1, b.tw, b.th, b.td);
+    rc = make_act_map(&p.q_map[0], reinterpret_cast<const __nv_bfloat16*>(Q->ptr), Q->c, Q->w, Q->h, Q->d, Q->n,
+                      Q->ld, Q->w, Q->h, Q->d, 1, b.tw, b.th, b.td);
     if (rc) return rc;
     p.ntaps = 27;
+    const int sgn = swapped ? -1 : 1;
     for (int t = 0; t < 27; ++t) {
         p.q_map_of_tap[t] = 0;
-        p.tap_dd[t] = t / 9 - 1;
-        p.tap_dh[t] = (t / 3) % 3 - 1;
-        p.tap_dw[t] = t % 3 - 1;
+        p.tap_dd[t] = sgn * (t / 9 - 1);
+        p.tap_dh[t] = sgn * ((t / 3) % 3 - 1);
+        p.tap_dw[t] = sgn * (t % 3 - 1);
     }
-    p.p_extent = (int)dy->c;
-    p.q_extent = cin_real;
-    p.q_chunks = (cin_real + 63) / 64;
+    p.p_extent = swapped ? cin_real : (int)dy->c;
+    p.q_extent = swapped ? (int)dy->c : cin_real;
+    p.q_chunks = (p.q_extent + 63) / 64;
     p.nbw = (int)b.nbw; p.nbh = (int)b.nbh; p.nbd = (int)b.nbd; p.nbatch = (int)x->n;
     p.tw = b.tw; p.th = b.th; p.td = b.td;
     p.out = dw;
     p.st = 1;
-    p.sp = (long long)cin_real * 27;
-    p.sq = 27;
+    p.sp = swapped ? 27 : (long long)cin_real * 27;
+    p.sq = swapped ? (long long)cin_real * 27 : 27;
     return launch_wgrad(p, (cudaStream_t)stream);
 }
 

@@ -170,20 +170,24 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int cout, i
     }
     __syncthreads();
     const int lane = tid & 31, wrp = tid >> 5, nw = blockDim.x >> 5;
+    // packed tap order t = kd*9 + kw*3 + kh (kh fastest: the three kh taps of a (kd,kw) group are one TMA box);
+    // native (torch) tap index tn = kd*9 + kh*3 + kw
     if (wf) {  // [27][cout][cin_pad], ci contiguous
         for (int job = wrp; job < 27 * 32; job += nw) {
             const int t = job / 32, r = job - t * 32;
+            const int tn = (t / 9) * 9 + (t % 3) * 3 + (t / 3) % 3;
             const int co = co0 + r, ci = ci0 + lane;
             if (co < cout && ci < cin_pad)
-                wf[((long long)t * cout + co) * cin_pad + ci] = __float2bfloat16_rn(tile[r * 864 + lane * 27 + t]);
+                wf[((long long)t * cout + co) * cin_pad + ci] = __float2bfloat16_rn(tile[r * 864 + lane * 27 + tn]);
         }
     }
     if (wd) {  // [27][cin_pad][cout], co contiguous
         for (int job = wrp; job < 27 * 32; job += nw) {
             const int t = job / 32, r = job - t * 32;
+            const int tn = (t / 9) * 9 + (t % 3) * 3 + (t / 3) % 3;
             const int ci = ci0 + r, co = co0 + lane;
             if (co < cout && ci < cin_pad)
-                wd[((long long)t * cin_pad + ci) * cout + co] = __float2bfloat16_rn(tile[lane * 864 + r * 27 + t]);
+                wd[((long long)t * cin_pad + ci) * cout + co] = __float2bfloat16_rn(tile[lane * 864 + r * 27 + tn]);
         }
     }
 }

@@ -34,9 +34,11 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __g
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform role index
     const int lane = threadIdx.x & 31;
     const uint32_t nst = p.stages;
-    const uint32_t b_bytes = p.block_n * 128;
+    const uint32_t a_bytes = p.a_stage_bytes;
+    const uint32_t bt_bytes = p.block_n * 128;          // one tap of B
+    const uint32_t b_bytes = bt_bytes * p.group;        // B bytes per stage
     const uint32_t smem_a = smem_base;
-    const uint32_t smem_b = smem_a + nst * kBoxBytes;
+    const uint32_t smem_b = smem_a + nst * a_bytes;
     const uint32_t bar_base = smem_b + nst * b_bytes;  // 8-byte aligned (multiple of 1024)
     // barrier layout: full[nst], empty[nst], tmem_full[2], tmem_empty[2]
     auto full_bar = [&](uint32_t s) { return bar_base + 8 * s; };
@@ -79,7 +81,7 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __g
         // ===================================================================== TMA producer
         // The whole warp walks the loop (uniform control flow, barrier polls by all lanes); one elected lane issues.
         PipeState ps;
-        const int kc_blocks = p.kc_blocks, ntaps = p.ntaps, n_tiles = p.n_tiles;
+        const int kc_blocks = p.kc_blocks, ntaps = p.ntaps / p.group, n_tiles = p.n_tiles, group = p.group;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             int mt = tile / n_tiles;
             const int n_tile = tile - mt * n_tiles;
@@ -96,9 +98,9 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __g
                     mbar_wait(empty_bar(ps.stage), ps.phase ^ 1);
                     if (elect_one()) {
                         const uint32_t fb = full_bar(ps.stage);
-                        mbar_arrive_expect_tx(fb, kBoxBytes + b_bytes);
-                        tma_load_5d(smem_a + ps.stage * kBoxBytes, amap, fb, kc * 64, cw, ch, cd, nb);
-                        tma_load_3d(smem_b + ps.stage * b_bytes, &p.b_map, fb, kc * 64, n0, tap);
+                        mbar_arrive_expect_tx(fb, a_bytes + b_bytes);
+                        tma_load_5d(smem_a + ps.stage * a_bytes, amap, fb, kc * 64, cw, ch, cd, nb);
+                        tma_load_3d(smem_b + ps.stage * b_bytes, &p.b_map, fb, kc * 64, n0, tap * group);
                     }
                     __syncwarp();
                     ps.advance(nst);
@@ -111,8 +113,9 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __g
         const uint32_t idesc = make_idesc_bf16(128, p.block_n, 0, 0);
         const uint64_t a_desc0 = make_smem_desc_sw128(smem_a, 0, 1024);
         const uint64_t b_desc0 = make_smem_desc_sw128(smem_b, 0, 1024);
-        const uint32_t a_step = kBoxBytes >> 4, b_step = b_bytes >> 4;
-        const int kc_blocks = p.kc_blocks, ntaps = p.ntaps;
+        const uint32_t a_step = a_bytes >> 4, b_step = b_bytes >> 4, bt_step = bt_bytes >> 4;
+        const int kc_blocks = p.kc_blocks, ntaps = p.ntaps / p.group, group = p.group;
+        const uint32_t goff1 = p.a_goff[1], goff2 = p.a_goff[2], goff0 = p.a_goff[0];
         const int nk_last = ((p.cin - (kc_blocks - 1) * 64) + 15) >> 4;  // K steps of the last channel block (1..4)
         PipeState ps;
         int iter = 0;
@@ -128,13 +131,17 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __g
                     mbar_wait(full_bar(ps.stage), ps.phase);
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint64_t a_desc = a_desc0 + ps.stage * a_step;
-                        const uint64_t b_desc = b_desc0 + ps.stage * b_step;
-                        // 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (>>4) address field
-                        umma_f16(d_tmem, a_desc, b_desc, idesc, accum);
-                        if (nk > 1) umma_f16(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);
-                        if (nk > 2) umma_f16(d_tmem, a_desc + 4, b_desc + 4, idesc, 1u);
-                        if (nk > 3) umma_f16(d_tmem, a_desc + 6, b_desc + 6, idesc, 1u);
+                        const uint64_t a_st = a_desc0 + ps.stage * a_step;
+                        const uint64_t b_st = b_desc0 + ps.stage * b_step;
+                        for (int g = 0; g < group; ++g) {
+                            const uint64_t a_desc = a_st + (g == 0 ? goff0 : (g == 1 ? goff1 : goff2));
+                            const uint64_t b_desc = b_st + g * bt_step;
+                            // 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (>>4) address field
+                            umma_f16(d_tmem, a_desc, b_desc, idesc, g == 0 ? accum : 1u);
+                            if (nk > 1) umma_f16(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);
+                            if (nk > 2) umma_f16(d_tmem, a_desc + 4, b_desc + 4, idesc, 1u);
+                            if (nk > 3) umma_f16(d_tmem, a_desc + 6, b_desc + 6, idesc, 1u);
+                        }
                         umma_commit(empty_bar(ps.stage));
                     }
                     __syncwarp();

@@ -25,6 +25,9 @@ enum EpilogueMode : int {
 // A_tap is read by TMA from an NDHWC bf16 tensor through a_map[a_map_of_tap[tap]] at the brick origin
 // shifted by (tap_dw, tap_dh, tap_dd); out-of-range coordinates are zero-filled by the TMA unit, which is
 // the convolution's zero padding.  B is the packed weight [taps][n][c] (c contiguous).
+// h-halo mode (group == 3): bricks are tw x th x 1 (w fastest), the A box holds rows h0-1 .. h0+th of the brick, and
+// the three kh taps of a (kd, kw) group are the same box read at row offsets 0, tw, 2*tw (multiples of the 8-row
+// swizzle atom, so the plain SWIZZLE_128B descriptor stays valid): A traffic per tap drops ~2.7x.
 struct alignas(64) IgemmParams {
     CUtensorMap a_map[kMaxMaps];
     CUtensorMap b_map;
@@ -40,6 +43,9 @@ struct alignas(64) IgemmParams {
     int tw_log2, th_log2, td_log2;
     int W, H, D;    // extent of the M grid
     int stages;
+    int group;          // taps per pipeline stage: 1, or 3 (h-halo mode: one A box of th+2 rows serves kh = 0,1,2)
+    int a_stage_bytes;  // bytes of one A box (16 KB, or (th+2)*tw*128 B in h-halo mode)
+    int a_goff[3];      // start offset (bytes >> 4) of tap g of a group inside the A box
     int mode;
     const float* vec0;  // bias (modes 1,3) or scale (mode 2)
     const float* vec1;  // shift (mode 2)

@@ -114,7 +114,7 @@ class _DoubleConv:
             raise ValueError(f"Expected more than 1 value per channel when training, got input size "
                              f"{(n, cout, d, h, w)}")
         y = ActView(new_act(n, d, h, w, cout, dev))
-        rows = ops.conv3d_stat_rows(n, d, h, w, cout)
+        rows = ops.conv3d_stat_rows(n, d, h, w, cout, 1 if pack.im2col else 27)
         stats = torch.empty(rows, cout, 2, device=dev, dtype=torch.float32)
         pack.fprop(xin, pack.conv.bias.data, y, stats, ops.EPI_BIAS_STATS)
         vec = torch.empty(4, cout, device=dev, dtype=torch.float32)  # mean, rstd, scale, shift

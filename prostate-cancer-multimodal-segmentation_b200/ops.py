@@ -135,8 +135,8 @@ def pack_convt_weight(w: torch.Tensor, bias: torch.Tensor, w_fwd, w_dgrad, bias8
                                              stream_ptr()), "pack_convt_weight")
 
 
-def conv3d_stat_rows(n, d, h, w, cout) -> int:
-    r = _lib.load().b200_conv3d_stat_rows(n, d, h, w, cout)
+def conv3d_stat_rows(n, d, h, w, cout, ntaps=27) -> int:
+    r = _lib.load().b200_conv3d_stat_rows(n, d, h, w, cout, ntaps)
     if r <= 0:
         raise _lib.B200Error("b200_conv3d_stat_rows failed (no CUDA device?)")
     return r

