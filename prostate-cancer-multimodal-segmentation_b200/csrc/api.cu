@@ -154,16 +154,19 @@ static Brick choose_brick(long long w, long long h, long long d) {
 }
 
 static int igemm_block_n(long long ncols) { return ncols >= 256 ? 256 : (int)((ncols + 15) / 16 * 16); }
-static int igemm_stages(int a_bytes, int b_bytes) {
+// dynamic shared memory of igemm_kernel: 1 KB alignment slack + stages + epilogue-v2 staging + barriers, TMEM pointer,
+// statistics scratch [4][256][2], per-CTA column sums [kMaxStatCols][2], per-tile column vectors [2][256]
+constexpr int kIgemmFixedSmem = 1024 + 8 * (2 * 8 + 4) + 64 + 4 * 256 * 2 * 4 + kMaxStatCols * 2 * 4 + 2 * 256 * 4;
+constexpr int kSmemLimit = 227 * 1024;
+static int epi_staging_bytes(const IgemmParams& p) { return p.epi_v2 ? ((p.block_n + 63) / 64) * kBoxBytes : 0; }
+static int igemm_stages(int a_bytes, int b_bytes, int c_bytes) {
     const int per_stage = a_bytes + b_bytes;
-    int st = (204 * 1024) / per_stage;
+    int st = (kSmemLimit - kIgemmFixedSmem - c_bytes) / per_stage;
     if (st > 8) st = 8;
-    if (st < 2) st = 2;
     return st;
 }
-static size_t igemm_smem(int stages, int a_bytes, int b_bytes) {
-    return 1024 + (size_t)stages * (a_bytes + b_bytes) + 8 * (2 * stages + 4) + 32 + 4 * 256 * 2 * 4 +
-           (size_t)kMaxStatCols * 2 * 4;
+static size_t igemm_smem(int stages, int a_bytes, int b_bytes, int c_bytes) {
+    return (size_t)kIgemmFixedSmem + (size_t)stages * (a_bytes + b_bytes) + c_bytes;
 }
 // brick geometry of a conv3d / conv1 implicit GEMM; shared by the launcher and b200_conv3d_stat_rows
 static bool conv_geometry(long long w, long long h, long long d, long long cout, int ntaps, Brick* b) {
@@ -180,14 +183,15 @@ static void set_plain_stage(IgemmParams& p) {
     p.group = 1;
     p.a_stage_bytes = kBoxBytes;
     p.a_goff[0] = p.a_goff[1] = p.a_goff[2] = 0;
-    p.stages = igemm_stages(kBoxBytes, p.block_n * 128);
+    p.stages = igemm_stages(kBoxBytes, p.block_n * 128, epi_staging_bytes(p));
 }
 
 static int launch_igemm(IgemmParams& p, cudaStream_t s, int* grid_out) {
     const int sms = sm_count();
     if (sms <= 0) return fail(B200_ERR_CUDA, "no CUDA device");
     static size_t attr_smem = 0;
-    const size_t smem = igemm_smem(p.stages, p.a_stage_bytes, p.block_n * 128 * p.group);
+    if (p.stages < 2) return fail(B200_ERR_UNSUPPORTED_SHAPE, "igemm: tile does not fit shared memory");
+    const size_t smem = igemm_smem(p.stages, p.a_stage_bytes, p.block_n * 128 * p.group, epi_staging_bytes(p));
     {
         std::lock_guard<std::mutex> lk(g_mu);
         if (smem > attr_smem) {
@@ -242,6 +246,13 @@ static int conv3_igemm(const b200_act* in, const void* w_packed, const b200_act*
     rc = make_weight_map(&p.b_map, w_packed, in->c, out->c, ntaps, p.block_n, halo ? 3 : 1);
     if (rc) return rc;
     p.ntaps = ntaps;
+    // epilogue v2 (staged tile + TMA store): pays off when the MMA time per tile is short, i.e. narrow N
+    p.epi_v2 = (p.block_n <= 64 && p.block_n % 32 == 0) ? 1 : 0;
+    if (p.epi_v2) {
+        rc = make_act_map(&p.c_map[0], reinterpret_cast<const __nv_bfloat16*>(out->ptr), out->c, out->w, out->h,
+                          out->d, out->n, out->ld, out->w, out->h, out->d, 1, b.tw, b.th, b.td);
+        if (rc) return rc;
+    }
     if (halo) {
         // pipeline stage tg = kd*3 + kw covers packed taps 3*tg .. 3*tg+2 (kh = 0,1,2); box origin h0 - 1
         for (int tg = 0; tg < 9; ++tg) {
@@ -253,7 +264,7 @@ static int conv3_igemm(const b200_act* in, const void* w_packed, const b200_act*
         p.group = 3;
         p.a_stage_bytes = (b.th + 2) * b.tw * 128;
         for (int g = 0; g < 3; ++g) p.a_goff[g] = ((sign > 0 ? g : 2 - g) * b.tw * 128) >> 4;
-        p.stages = igemm_stages(p.a_stage_bytes, p.block_n * 128 * 3);
+        p.stages = igemm_stages(p.a_stage_bytes, p.block_n * 128 * 3, epi_staging_bytes(p));
     } else {
         for (int t = 0; t < ntaps; ++t) {  // packed tap order: t = kd*9 + kw*3 + kh
             p.a_map_of_tap[t] = 0;
@@ -371,17 +382,26 @@ extern "C" int b200_convt2x_fwd(const b200_act* x, const void* w_fwd, const floa
     p.ncols = (int)ncols;
     p.n_tiles = (int)((ncols + p.block_n - 1) / p.block_n);
     set_m_grid(p, b, x->n, x->w, x->h, x->d);
-    set_plain_stage(p);
     p.mode = EPI_BIAS;
     p.vec0 = bias8;
     set_out(p, y);
     p.out_mul = 2;
     p.cols_per_group = (int)y->c;
+    // the tile is K-short (K = Cin), so the epilogue dominates: stage + TMA store through 8 strided (parity) maps
+    p.epi_v2 = (y->c % 64 == 0 && p.block_n % 64 == 0) ? 1 : 0;
     for (int t = 0; t < 8; ++t) {
         p.out_od[t] = pad_d + ((t >> 2) & 1);
         p.out_oh[t] = pad_h + ((t >> 1) & 1);
         p.out_ow[t] = pad_w + (t & 1);
+        if (p.epi_v2) {
+            const __nv_bfloat16* bt = reinterpret_cast<const __nv_bfloat16*>(y->ptr) +
+                                      (((long long)p.out_od[t] * y->h + p.out_oh[t]) * y->w + p.out_ow[t]) * y->ld;
+            rc = make_act_map(&p.c_map[t], bt, y->c, x->w, x->h, x->d, x->n, y->ld, y->w, y->h, y->d, 2, b.tw, b.th,
+                              b.td);
+            if (rc) return rc;
+        }
     }
+    set_plain_stage(p);
     return launch_igemm(p, (cudaStream_t)stream, nullptr);
 }
 

@@ -39,7 +39,9 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __g
     const uint32_t b_bytes = bt_bytes * p.group;        // B bytes per stage
     const uint32_t smem_a = smem_base;
     const uint32_t smem_b = smem_a + nst * a_bytes;
-    const uint32_t bar_base = smem_b + nst * b_bytes;  // 8-byte aligned (multiple of 1024)
+    const uint32_t smem_c = smem_b + nst * b_bytes;    // epilogue v2 staging: (block_n / 64) boxes of 128 rows x 128 B
+    const uint32_t c_bytes = p.epi_v2 ? ((p.block_n + 63) >> 6) * kBoxBytes : 0;
+    const uint32_t bar_base = smem_c + c_bytes;        // 8-byte aligned (multiple of 1024)
     // barrier layout: full[nst], empty[nst], tmem_full[2], tmem_empty[2]
     auto full_bar = [&](uint32_t s) { return bar_base + 8 * s; };
     auto empty_bar = [&](uint32_t s) { return bar_base + 8 * (nst + s); };
@@ -49,6 +51,7 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __g
     const uint32_t scratch_off = (tmem_ptr_smem + 16 - smem_base + 15u) & ~15u;
     float* scratch = reinterpret_cast<float*>(smem_gen + scratch_off);  // [4 warps][256 cols][2]
     float* colacc = scratch + 4 * 256 * 2;                              // [ncols <= kMaxStatCols][2], per-CTA running sums
+    float* colvec = colacc + 2 * kMaxStatCols;                          // epilogue v2: [2][256] per-tile bias | scale, shift
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&p.b_map);
@@ -165,6 +168,112 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __g
             named_bar_sync(1, 128);
         }
         int iter = 0;
+        if (p.epi_v2) {
+            // ------------------------------------------------------------- epilogue v2
+            // TMEM -> registers (32 columns per load) -> bias / affine+ReLU -> bf16 -> swizzled shared-memory tile ->
+            // one TMA store per 64-channel box (clips rows/columns outside the tensor); BatchNorm partial sums are
+            // read back from the staged tile (conflict-free word reads) instead of 30 shuffles per 16 columns.
+            const int nbox = (p.block_n + 63) >> 6, nslab = p.block_n >> 5;
+            const int mode = p.mode;
+            const uint32_t row_smem = smem_c + row * 128;
+            const uint32_t sw = row & 7;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+                const uint32_t acc = iter & 1, acc_phase = (iter >> 1) & 1;
+                const int m_tile = tile / p.n_tiles;
+                const int n_tile = tile - m_tile * p.n_tiles;
+                int mt = m_tile;
+                const int bw = mt % p.nbw; mt /= p.nbw;
+                const int bh = mt % p.nbh; mt /= p.nbh;
+                const int bd = mt % p.nbd; mt /= p.nbd;
+                const int nb = mt;
+                const int w0 = bw << p.tw_log2, h0 = bh << p.th_log2, d0 = bd << p.td_log2;
+                const bool row_ok = (w0 + rw) < p.W && (h0 + rh) < p.H && (d0 + rd) < p.D;
+                const int n0 = n_tile * p.block_n;
+                if (mode != EPI_PLAIN) {
+                    for (int c = et; c < p.block_n; c += 128) {
+                        const bool ok = n0 + c < p.ncols;
+                        colvec[c] = ok ? __ldg(p.vec0 + n0 + c) : 0.f;
+                        if (mode == EPI_AFFINE_RELU) colvec[256 + c] = ok ? __ldg(p.vec1 + n0 + c) : 0.f;
+                    }
+                }
+                if (et == 0) bulk_wait_read0();  // the previous tile's TMA store has finished reading the staging tile
+                named_bar_sync(1, 128);
+                mbar_wait(tfull_bar(acc), acc_phase);
+                tc_fence_after();
+                const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.block_n;
+                for (int j = 0; j < nslab; ++j) {
+                    uint32_t v[32];
+                    tmem_ld32(t_addr + j * 32, v);
+                    tmem_ld_wait();
+                    const float* cv = colvec + j * 32;
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float a = __uint_as_float(v[2 * i]), b = __uint_as_float(v[2 * i + 1]);
+                        if (mode == EPI_AFFINE_RELU) {
+                            a = fmaxf(fmaf(a, cv[2 * i], cv[256 + 2 * i]), 0.f);
+                            b = fmaxf(fmaf(b, cv[2 * i + 1], cv[256 + 2 * i + 1]), 0.f);
+                        } else if (mode != EPI_PLAIN) {
+                            a += cv[2 * i];
+                            b += cv[2 * i + 1];
+                        }
+                        pk[i] = row_ok ? pack_bf16x2(a, b) : 0u;
+                    }
+                    const uint32_t box_addr = row_smem + (j >> 1) * kBoxBytes;
+                    const uint32_t c0 = (j & 1) * 4;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        st_shared_v4(box_addr + (((c0 + c) ^ sw) << 4), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2],
+                                     pk[4 * c + 3]);
+                }
+                tc_fence_before();
+                mbar_arrive(tempty_bar(acc));  // TMEM stage drained
+                fence_proxy_async_smem();      // generic-proxy writes -> visible to the TMA engine
+                named_bar_sync(1, 128);
+                if (et == 0) {
+                    for (int b = 0; b < nbox; ++b) {
+                        const int col0 = n0 + b * 64;
+                        if (col0 < p.ncols) {
+                            const int g = col0 / p.cols_per_group;
+                            tma_store_5d(&p.c_map[g], smem_c + b * kBoxBytes, col0 - g * p.cols_per_group, w0, h0, d0,
+                                         nb);
+                        }
+                    }
+                    bulk_commit();
+                }
+                if (mode == EPI_BIAS_STATS) {
+                    // warp q sums rows 32q..32q+31 of column pair `lane` of every box
+                    for (int b = 0; b < nbox; ++b) {
+                        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+                        const uint32_t base = smem_c + b * kBoxBytes + (q * 32) * 128 + (lane & 3) * 4;
+#pragma unroll 8
+                        for (int r = 0; r < 32; ++r) {
+                            const uint32_t wv = ld_shared_b32(base + r * 128 + ((((uint32_t)lane >> 2) ^ (r & 7)) << 4));
+                            const float lo = __uint_as_float(wv << 16), hi = __uint_as_float(wv & 0xffff0000u);
+                            s0 += lo; q0 = fmaf(lo, lo, q0);
+                            s1 += hi; q1 = fmaf(hi, hi, q1);
+                        }
+                        float4* dst = reinterpret_cast<float4*>(scratch + ((q * 256 + b * 64 + 2 * lane) * 2));
+                        *dst = make_float4(s0, q0, s1, q1);
+                    }
+                    named_bar_sync(1, 128);
+                    for (int cl = et; cl < p.block_n; cl += 128) {
+                        const int col = n0 + cl;
+                        if (col < p.ncols) {
+                            float a = 0.f, b2 = 0.f;
+#pragma unroll
+                            for (int w4 = 0; w4 < 4; ++w4) {
+                                a += scratch[(w4 * 256 + cl) * 2 + 0];
+                                b2 += scratch[(w4 * 256 + cl) * 2 + 1];
+                            }
+                            colacc[2 * col] += a;
+                            colacc[2 * col + 1] += b2;
+                        }
+                    }
+                }
+            }
+            if (et == 0) bulk_wait0();  // all output tiles are in global memory before the CTA exits
+        } else
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
             const uint32_t acc = iter & 1, acc_phase = (iter >> 1) & 1;
             const int m_tile = tile / p.n_tiles;
