@@ -217,7 +217,10 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        time.sleep(0.3)
+        t_wait = time.time()
+        while not sampler.rows and time.time() - t_wait < 5.0:  # first nvidia-smi sample can take a second
+            time.sleep(0.05)
+        sampler.rows.clear()
     barrier()
     l0 = ops.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

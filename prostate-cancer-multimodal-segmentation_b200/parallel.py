@@ -121,7 +121,7 @@ def window_schedule(shape, window, stride):
 
 @torch.no_grad()
 def sliding_window_logits(model, x, window=(128, 128, 64), stride=(64, 64, 64), rank=0, world=1, group=None,
-                          windows_per_launch=1):
+                          windows_per_launch=1, reduce=True):
     """Average of window logits over a batch of volumes; with world > 1 every rank evaluates windows
     rank, rank+world, ... and the partial sums are all-reduced.  x: (N, C, D, H, W) on this rank's GPU (every rank
     holds the volumes; they are small next to the activations)."""
@@ -139,6 +139,8 @@ def sliding_window_logits(model, x, window=(128, 128, 64), stride=(64, 64, 64), 
             acc[v, :, d0:d0 + wd, h0:h0 + wh, w0:w0 + ww] += lg[j]
     for (v, d0, h0, w0) in sched:  # the count map is deterministic: every rank builds the full one locally
         cnt[v, :, d0:d0 + wd, h0:h0 + wh, w0:w0 + ww] += 1
+    if world > 1 and not reduce:
+        return acc, cnt  # this rank's partial logit sums (caller reduces) and the full count map
     if world > 1:
         dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
     return acc / cnt

@@ -102,7 +102,10 @@ def test_sliding_window_inference_vs_oracle(pkg, cuda_dev):
     assert got.shape == ref.shape == (2, 1, 48, 40, 32)
     assert rel_l2(got, ref) < 2e-2
     # sharding the window list over ranks changes nothing but the order of additions
-    parts = [pkg.parallel.sliding_window_logits(model, x, window, stride, rank=r, world=3) for r in range(3)]
+    parts = [pkg.parallel.sliding_window_logits(model, x, window, stride, rank=r, world=3, reduce=False)
+             for r in range(3)]
+    merged = sum(p[0] for p in parts) / parts[0][1]
+    assert torch.allclose(merged, got, rtol=1e-5, atol=1e-5)
     sched, _ = pkg.parallel.window_schedule(x.shape, window, stride)
     assert len(sched) == 2 * 3 * 2 * 1
     probs, mask = pkg.parallel.sliding_window_predict(model, x, window, stride)
