@@ -47,9 +47,10 @@ int b200_sm_count(void);
 /* (N,C,D,H,W) fp32 -> NDHWC bf16 view, channels c..out->c-1 zero (input of UNet3D.forward, models/unet3d.py:247) */
 int b200_pack_input(const float* x_ncdhw, int64_t n, int64_t c, int64_t d, int64_t h, int64_t w,
                     const b200_act* out, void* stream);
-/* Conv3d weight (Cout,Cin,3,3,3) fp32 -> w_fprop bf16 [27][Cout][cin_pad], w_dgrad bf16 [27][cin_pad][Cout]
- * (either may be NULL); packed tap index t = kd*9 + kw*3 + kh (kh fastest).  models/unet3d.py:29,35 */
-int b200_pack_conv_weight(const float* w, int cout, int cin, int cin_pad, void* w_fprop, void* w_dgrad, void* stream);
+/* Conv3d weight (Cout,Cin,3,3,3) fp32 -> w_packed bf16 [27][Cout][cin_pad]; packed tap index t = kd*9 + kw*3 + kh
+ * (kh fastest).  The one layout serves fprop (K-major B operand) and dgrad (MN-major B operand).
+ * models/unet3d.py:29,35 */
+int b200_pack_conv_weight(const float* w, int cout, int cin, int cin_pad, void* w_packed, void* stream);
 /* ConvTranspose3d weight (Cin,Cout,2,2,2) fp32 -> w_fwd bf16 [8*Cout][Cin], w_dgrad bf16 [8][Cin][Cout],
  * bias (Cout) -> bias8 fp32 [8*Cout].  models/unet3d.py:120 */
 int b200_pack_convt_weight(const float* w, const float* bias, int cin, int cout, void* w_fwd, void* w_dgrad,
@@ -76,9 +77,9 @@ int b200_conv3d_stat_rows(int64_t n, int64_t d, int64_t h, int64_t w, int64_t co
 /* mode BIAS_STATS : y = bf16(conv + bias); stats_partial[row][Cout][2] = (sum, sum of squares) of stored y
  * mode AFFINE_RELU: y = relu(conv * scale + shift)   (eval-mode BatchNorm + bias folded)
  * mode BIAS / PLAIN likewise without statistics. */
-int b200_conv3d_fprop(const b200_act* x, const void* w_fprop, const float* bias, const b200_act* y,
+int b200_conv3d_fprop(const b200_act* x, const void* w_packed, const float* bias, const b200_act* y,
                       float* stats_partial, int mode, const float* scale, const float* shift, void* stream);
-int b200_conv3d_dgrad(const b200_act* dy, const void* w_dgrad, const b200_act* dx, void* stream);
+int b200_conv3d_dgrad(const b200_act* dy, const void* w_packed, const b200_act* dx, void* stream);
 /* dw fp32 (Cout, cin_real, 3,3,3) += ; x->c may exceed cin_real (zero padded channels) */
 int b200_conv3d_wgrad(const b200_act* x, const b200_act* dy, float* dw, int cin_real, void* stream);
 

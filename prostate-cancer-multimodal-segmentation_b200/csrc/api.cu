@@ -158,6 +158,9 @@ static int igemm_block_n(long long ncols) { return ncols >= 256 ? 256 : (int)((n
 // statistics scratch [4][256][2], per-CTA column sums [kMaxStatCols][2], per-tile column vectors [2][256]
 constexpr int kIgemmFixedSmem = 1024 + 8 * (2 * 8 + 4) + 64 + 4 * 256 * 2 * 4 + kMaxStatCols * 2 * 4 + 2 * 256 * 4;
 constexpr int kSmemLimit = 227 * 1024;
+static int b_stage_bytes(const IgemmParams& p) {
+    return p.b_mn ? ((p.block_n + 63) / 64) * 8192 * p.group : p.block_n * 128 * p.group;
+}
 static int epi_staging_bytes(const IgemmParams& p) { return p.epi_v2 ? ((p.block_n + 63) / 64) * kBoxBytes : 0; }
 static int igemm_stages(int a_bytes, int b_bytes, int c_bytes) {
     const int per_stage = a_bytes + b_bytes;
@@ -183,7 +186,7 @@ static void set_plain_stage(IgemmParams& p) {
     p.group = 1;
     p.a_stage_bytes = kBoxBytes;
     p.a_goff[0] = p.a_goff[1] = p.a_goff[2] = 0;
-    p.stages = igemm_stages(kBoxBytes, p.block_n * 128, epi_staging_bytes(p));
+    p.stages = igemm_stages(kBoxBytes, b_stage_bytes(p), epi_staging_bytes(p));
 }
 
 static int launch_igemm(IgemmParams& p, cudaStream_t s, int* grid_out) {
@@ -191,7 +194,7 @@ static int launch_igemm(IgemmParams& p, cudaStream_t s, int* grid_out) {
     if (sms <= 0) return fail(B200_ERR_CUDA, "no CUDA device");
     static size_t attr_smem = 0;
     if (p.stages < 2) return fail(B200_ERR_UNSUPPORTED_SHAPE, "igemm: tile does not fit shared memory");
-    const size_t smem = igemm_smem(p.stages, p.a_stage_bytes, p.block_n * 128 * p.group, epi_staging_bytes(p));
+    const size_t smem = igemm_smem(p.stages, p.a_stage_bytes, b_stage_bytes(p), epi_staging_bytes(p));
     {
         std::lock_guard<std::mutex> lk(g_mu);
         if (smem > attr_smem) {
@@ -243,7 +246,13 @@ static int conv3_igemm(const b200_act* in, const void* w_packed, const b200_act*
     rc = make_act_map(&p.a_map[0], reinterpret_cast<const __nv_bfloat16*>(in->ptr), in->c, in->w, in->h, in->d, in->n,
                       in->ld, in->w, in->h, in->d, 1, b.tw, halo ? b.th + 2 : b.th, b.td);
     if (rc) return rc;
-    rc = make_weight_map(&p.b_map, w_packed, in->c, out->c, ntaps, p.block_n, halo ? 3 : 1);
+    // fprop: K-major B from [tap][Cout rows][Cin].  dgrad (sign < 0) reads the SAME packed weights MN-major:
+    // K = Cout rows (in->c), N = Cin contiguous (out->c), 64 x 64 boxes.
+    p.b_mn = sign < 0 ? 1 : 0;
+    if (p.b_mn)
+        rc = make_weight_map(&p.b_map, w_packed, out->c, in->c, ntaps, 64, halo ? 3 : 1);
+    else
+        rc = make_weight_map(&p.b_map, w_packed, in->c, out->c, ntaps, p.block_n, halo ? 3 : 1);
     if (rc) return rc;
     p.ntaps = ntaps;
     // epilogue v2 (staged tile + TMA store): pays off when the MMA time per tile is short, i.e. narrow N
@@ -264,7 +273,7 @@ static int conv3_igemm(const b200_act* in, const void* w_packed, const b200_act*
         p.group = 3;
         p.a_stage_bytes = (b.th + 2) * b.tw * 128;
         for (int g = 0; g < 3; ++g) p.a_goff[g] = ((sign > 0 ? g : 2 - g) * b.tw * 128) >> 4;
-        p.stages = igemm_stages(p.a_stage_bytes, p.block_n * 128 * 3, epi_staging_bytes(p));
+        p.stages = igemm_stages(p.a_stage_bytes, b_stage_bytes(p), epi_staging_bytes(p));
     } else {
         for (int t = 0; t < ntaps; ++t) {  // packed tap order: t = kd*9 + kw*3 + kh
             p.a_map_of_tap[t] = 0;
@@ -336,12 +345,12 @@ static int fprop_impl(const b200_act* x, const void* w_fprop, const float* bias,
     return conv3_igemm(x, w_fprop, y, +1, mode, v0, v1, stats_partial, (cudaStream_t)stream, ntaps);
 }
 
-extern "C" int b200_conv3d_dgrad(const b200_act* dy, const void* w_dgrad, const b200_act* dx, void* stream) {
+extern "C" int b200_conv3d_dgrad(const b200_act* dy, const void* w_packed, const b200_act* dx, void* stream) {
     CHECK_VIEW(dy);
     CHECK_VIEW(dx);
-    REQUIRE(w_dgrad != nullptr, "conv3d_dgrad: null weights");
-    // dx[v, ci] = sum_t sum_co dy[v - off(t), co] * w[co, ci, t]
-    return conv3_igemm(dy, w_dgrad, dx, -1, B200_EPI_PLAIN, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+    REQUIRE(w_packed != nullptr, "conv3d_dgrad: null weights");
+    // dx[v, ci] = sum_t sum_co dy[v - off(t), co] * w[co, ci, t]; w_packed is the fprop layout [27][Cout][Cin]
+    return conv3_igemm(dy, w_packed, dx, -1, B200_EPI_PLAIN, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------ transposed conv
@@ -610,11 +619,10 @@ extern "C" int b200_pack_rows(const float* w, int rows, int k, int k_pad, void* 
     CUDA_TRY(launch_pack_rows(w, rows, k, k_pad, reinterpret_cast<__nv_bfloat16*>(out), (cudaStream_t)stream));
     return 0;
 }
-extern "C" int b200_pack_conv_weight(const float* w, int cout, int cin, int cin_pad, void* w_fprop, void* w_dgrad,
-                                     void* stream) {
-    REQUIRE(w && cout > 0 && cin > 0 && cin_pad >= cin, "pack_conv_weight: bad arguments");
-    CUDA_TRY(launch_pack_conv_weight(w, cout, cin, cin_pad, reinterpret_cast<__nv_bfloat16*>(w_fprop),
-                                     reinterpret_cast<__nv_bfloat16*>(w_dgrad), (cudaStream_t)stream));
+extern "C" int b200_pack_conv_weight(const float* w, int cout, int cin, int cin_pad, void* w_packed, void* stream) {
+    REQUIRE(w && w_packed && cout > 0 && cin > 0 && cin_pad >= cin, "pack_conv_weight: bad arguments");
+    CUDA_TRY(launch_pack_conv_weight(w, cout, cin, cin_pad, reinterpret_cast<__nv_bfloat16*>(w_packed),
+                                     (cudaStream_t)stream));
     return 0;
 }
 extern "C" int b200_pack_convt_weight(const float* w, const float* bias, int cin, int cout, void* w_fwd,

@@ -86,12 +86,16 @@ cudaError_t launch_pack_input(const float* x, long long n, long long c, long lon
 // is expanded once to rows of kpad = pad16(27*C) bf16, column k = c*27 + tap (tap = kd*9+kh*3+kw): exactly the
 // flattened (C,3,3,3) weight layout, so the layer becomes a plain GEMM (1 tap) for fprop and wgrad.
 constexpr int kI2cVox = 128;
+// 256 threads = 128 voxels x 2 channel groups; each thread gathers whole channels (27 taps unrolled, coalesced along w
+// across the warp, L1 reuse 27x) into a bf16 tile [128][kpad + 2] in shared memory; the block then streams the tile
+// out as contiguous 4-byte words (rows are contiguous in global memory when ld == kpad).
 __global__ void __launch_bounds__(256) im2col_input_kernel(const float* __restrict__ x, int c_in, int D, int H, int W,
                                                            long long nvox, View out) {
-    extern __shared__ uint32_t i2c_smem[];  // [128][kpad/2 + 1] packed bf16 pairs (row pitch padded: conflict-free)
-    const int kpad = (int)out.c, pitch = kpad / 2 + 1;
+    extern __shared__ uint32_t i2c_smem[];  // [128][kpad/2 + 1] words
+    __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(i2c_smem);
+    const int kpad = (int)out.c, pitch = kpad / 2 + 1, pitch16 = 2 * pitch;
     const long long v0 = (long long)blockIdx.x * kI2cVox;
-    const int vl = threadIdx.x & (kI2cVox - 1), half = threadIdx.x >> 7;  // 2 threads per voxel, alternating pairs
+    const int vl = threadIdx.x & (kI2cVox - 1), half = threadIdx.x >> 7;
     const long long v = v0 + vl;
     const long long plane = (long long)D * H * W;
     if (v < nvox) {
@@ -100,24 +104,27 @@ __global__ void __launch_bounds__(256) im2col_input_kernel(const float* __restri
         const int d = (int)(r / ((long long)H * W));
         r -= (long long)d * H * W;
         const int h = (int)(r / W), w = (int)(r - (long long)h * W);
-        const float* xb = x + nb * c_in * plane;
-        for (int kp = half; kp < kpad / 2; kp += 2) {
-            float f[2];
+        const float* xb = x + nb * c_in * plane + ((long long)d * H + h) * W + w;
+        bool okd[3], okh[3], okw[3];
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int k = 2 * kp + e;
-                float val = 0.f;
-                if (k < 27 * c_in) {
-                    const int c = k / 27, t = k - c * 27;
-                    const int dd = d + t / 9 - 1, hh = h + (t / 3) % 3 - 1, ww = w + t % 3 - 1;
-                    if (dd >= 0 && dd < D && hh >= 0 && hh < H && ww >= 0 && ww < W)
-                        val = __ldg(xb + c * plane + ((long long)dd * H + hh) * W + ww);
-                }
-                f[e] = val;
-            }
-            __nv_bfloat162 b2 = __floats2bfloat162_rn(f[0], f[1]);
-            i2c_smem[vl * pitch + kp] = *reinterpret_cast<uint32_t*>(&b2);
+        for (int i = 0; i < 3; ++i) {
+            okd[i] = (unsigned)(d + i - 1) < (unsigned)D;
+            okh[i] = (unsigned)(h + i - 1) < (unsigned)H;
+            okw[i] = (unsigned)(w + i - 1) < (unsigned)W;
         }
+        __nv_bfloat16* row = tile + vl * pitch16;
+        for (int c = half; c < c_in; c += 2) {
+            const float* xc = xb + c * plane;
+#pragma unroll
+            for (int t = 0; t < 27; ++t) {
+                const int kd = t / 9, kh = (t / 3) % 3, kw = t % 3;
+                float val = 0.f;
+                if (okd[kd] && okh[kh] && okw[kw])
+                    val = __ldg(xc + ((long long)(kd - 1) * H + (kh - 1)) * W + (kw - 1));
+                row[c * 27 + t] = __float2bfloat16_rn(val);
+            }
+        }
+        for (int k = 27 * c_in + half; k < kpad; k += 2) row[k] = __float2bfloat16_rn(0.f);
     }
     __syncthreads();
     const int words_per_row = kpad / 2;
@@ -153,47 +160,56 @@ cudaError_t launch_pack_rows(const float* w, int rows, int k, int kpad, __nv_bfl
 }
 
 // ------------------------------------------------------------------------------------------------ pack weights
-// one block = 32 output channels x 32 input channels x 27 taps staged through shared memory
-__global__ void pack_conv_weight_kernel(const float* __restrict__ w, int cout, int cin, int cin_pad,
-                                        __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd) {
-    extern __shared__ float tile[];  // [32 co][32 ci][27]
+// one block = 32 output channels x 32 input channels x 27 taps; the tile is converted to bf16 on the way into
+// shared memory ([27][32 co][32 ci], row pitch 34 to spread banks), then written out as [27][Cout][Cin] with 64-byte rows
+// (the one packed layout serves fprop as a K-major and dgrad as an MN-major B operand).  55 KB of shared memory -> 4 blocks per SM.
+constexpr int kPackPitch = 34;
+__global__ void __launch_bounds__(256) pack_conv_weight_kernel(const float* __restrict__ w, int cout, int cin,
+                                                               int cin_pad, __nv_bfloat16* __restrict__ wf) {
+    extern __shared__ __nv_bfloat16 ptile[];  // [27][32][kPackPitch]
     const int co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
     const int tid = threadIdx.x;
-    for (int r = 0; r < 32; ++r) {
-        const int co = co0 + r;
-        for (int i = tid; i < 32 * 27; i += blockDim.x) {
-            const int ci = ci0 + i / 27;
+    const int nci = min(32, cin - ci0);        // valid input channels of this tile (may be <= 0 in the padded tail)
+    const int nco = min(32, cout - co0);
+    const int row_len = max(nci, 0) * 27;      // contiguous floats per output channel
+    const bool vec = (nci == 32) && ((((long long)cin * 27) & 3) == 0);
+    if (vec) {
+        for (int i = tid; i < 32 * 216; i += 256) {
+            const int r = i / 216, c4 = i - r * 216;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < nco) v = __ldg(reinterpret_cast<const float4*>(w + ((long long)(co0 + r) * cin + ci0) * 27) + c4);
+            const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int k = c4 * 4 + e, ci = k / 27, t = k - ci * 27;
+                ptile[(t * 32 + r) * kPackPitch + ci] = __float2bfloat16_rn(f[e]);
+            }
+        }
+    } else {
+        for (int i = tid; i < 32 * 864; i += 256) {
+            const int r = i / 864, k = i - r * 864;
+            const int ci = k / 27, t = k - ci * 27;
             float v = 0.f;
-            if (co < cout && ci < cin) v = __ldg(w + ((long long)co * cin + ci0) * 27 + i);
-            tile[r * 864 + i] = v;
+            if (r < nco && k < row_len) v = __ldg(w + ((long long)(co0 + r) * cin + ci0) * 27 + k);
+            ptile[(t * 32 + r) * kPackPitch + ci] = __float2bfloat16_rn(v);
         }
     }
     __syncthreads();
-    const int lane = tid & 31, wrp = tid >> 5, nw = blockDim.x >> 5;
+    const int lane = tid & 31, wrp = tid >> 5;
     // packed tap order t = kd*9 + kw*3 + kh (kh fastest: the three kh taps of a (kd,kw) group are one TMA box);
     // native (torch) tap index tn = kd*9 + kh*3 + kw
-    if (wf) {  // [27][cout][cin_pad], ci contiguous
-        for (int job = wrp; job < 27 * 32; job += nw) {
-            const int t = job / 32, r = job - t * 32;
-            const int tn = (t / 9) * 9 + (t % 3) * 3 + (t / 3) % 3;
+    for (int job = wrp; job < 27 * 32; job += 8) {
+        const int t = job >> 5, r = job & 31;
+        const int tn = (t / 9) * 9 + (t % 3) * 3 + (t / 3) % 3;
+        {  // [27][cout][cin_pad], ci contiguous: row r = output channel, lane = input channel
             const int co = co0 + r, ci = ci0 + lane;
-            if (co < cout && ci < cin_pad)
-                wf[((long long)t * cout + co) * cin_pad + ci] = __float2bfloat16_rn(tile[r * 864 + lane * 27 + tn]);
-        }
-    }
-    if (wd) {  // [27][cin_pad][cout], co contiguous
-        for (int job = wrp; job < 27 * 32; job += nw) {
-            const int t = job / 32, r = job - t * 32;
-            const int tn = (t / 9) * 9 + (t % 3) * 3 + (t / 3) % 3;
-            const int ci = ci0 + r, co = co0 + lane;
-            if (co < cout && ci < cin_pad)
-                wd[((long long)t * cin_pad + ci) * cout + co] = __float2bfloat16_rn(tile[lane * 864 + r * 27 + tn]);
+            if (co < cout && ci < cin_pad) wf[((long long)t * cout + co) * cin_pad + ci] = ptile[(tn * 32 + r) * kPackPitch + lane];
         }
     }
 }
 cudaError_t launch_pack_conv_weight(const float* w, int cout, int cin, int cin_pad, __nv_bfloat16* wf,
-                                    __nv_bfloat16* wd, cudaStream_t s) {
-    const int smem = 32 * 32 * 27 * 4;
+                                    cudaStream_t s) {
+    const int smem = 27 * 32 * kPackPitch * 2;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e =
@@ -202,7 +218,7 @@ cudaError_t launch_pack_conv_weight(const float* w, int cout, int cin, int cin_p
         attr_set = true;
     }
     dim3 grid((cin_pad + 31) / 32, (cout + 31) / 32);
-    pack_conv_weight_kernel<<<grid, 256, smem, s>>>(w, cout, cin, cin_pad, wf, wd);
+    pack_conv_weight_kernel<<<grid, 256, smem, s>>>(w, cout, cin, cin_pad, wf);
     return cudaGetLastError();
 }
 

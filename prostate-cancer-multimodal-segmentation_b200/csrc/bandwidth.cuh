@@ -37,7 +37,7 @@ cudaError_t launch_im2col_input(const float* x, long long n, long long c, long l
                                 View out, cudaStream_t s);
 cudaError_t launch_pack_rows(const float* w, int rows, int k, int kpad, __nv_bfloat16* out, cudaStream_t s);
 cudaError_t launch_pack_conv_weight(const float* w, int cout, int cin, int cin_pad, __nv_bfloat16* wf,
-                                    __nv_bfloat16* wd, cudaStream_t s);
+                                    cudaStream_t s);
 cudaError_t launch_pack_convt_weight(const float* w, const float* bias, int cin, int cout, __nv_bfloat16* wf,
                                      __nv_bfloat16* wd, float* bias8, cudaStream_t s);
 cudaError_t launch_bn_finalize(const float* partial, long long m_tiles, long long count, int c, const float* gamma,

@@ -35,8 +35,10 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __g
     const int lane = threadIdx.x & 31;
     const uint32_t nst = p.stages;
     const uint32_t a_bytes = p.a_stage_bytes;
-    const uint32_t bt_bytes = p.block_n * 128;          // one tap of B
-    const uint32_t b_bytes = bt_bytes * p.group;        // B bytes per stage
+    const uint32_t b_atoms = (p.block_n + 63) >> 6;     // MN-major B: 64-column atoms per stage
+    const uint32_t bt_bytes = p.b_mn ? 8192u : p.block_n * 128;   // one tap of B (MN-major: of one atom)
+    const uint32_t b_atom_bytes = 8192u * p.group;
+    const uint32_t b_bytes = p.b_mn ? b_atoms * b_atom_bytes : bt_bytes * p.group;  // B bytes per stage
     const uint32_t smem_a = smem_base;
     const uint32_t smem_b = smem_a + nst * a_bytes;
     const uint32_t smem_c = smem_b + nst * b_bytes;    // epilogue v2 staging: (block_n / 64) boxes of 128 rows x 128 B
@@ -103,7 +105,13 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __g
                         const uint32_t fb = full_bar(ps.stage);
                         mbar_arrive_expect_tx(fb, a_bytes + b_bytes);
                         tma_load_5d(smem_a + ps.stage * a_bytes, amap, fb, kc * 64, cw, ch, cd, nb);
-                        tma_load_3d(smem_b + ps.stage * b_bytes, &p.b_map, fb, kc * 64, n0, tap * group);
+                        if (p.b_mn) {
+                            for (uint32_t a = 0; a < b_atoms; ++a)
+                                tma_load_3d(smem_b + ps.stage * b_bytes + a * b_atom_bytes, &p.b_map, fb, n0 + a * 64,
+                                            kc * 64, tap * group);
+                        } else {
+                            tma_load_3d(smem_b + ps.stage * b_bytes, &p.b_map, fb, kc * 64, n0, tap * group);
+                        }
                     }
                     __syncwarp();
                     ps.advance(nst);
@@ -113,9 +121,11 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __g
     } else if (warp == 1) {
         // ===================================================================== MMA issuer
         // Lean loop: descriptors are base + stage offset (low word only), no divisions, one elected lane issues.
-        const uint32_t idesc = make_idesc_bf16(128, p.block_n, 0, 0);
+        const uint32_t idesc = make_idesc_bf16(128, p.block_n, 0, p.b_mn ? 1u : 0u);
         const uint64_t a_desc0 = make_smem_desc_sw128(smem_a, 0, 1024);
-        const uint64_t b_desc0 = make_smem_desc_sw128(smem_b, 0, 1024);
+        // K-major B: rows = N, 128 B = 64 K.  MN-major B: rows = K, 128 B = 64 N, atoms of 64 N are LBO apart.
+        const uint64_t b_desc0 = make_smem_desc_sw128(smem_b, p.b_mn ? b_atom_bytes : 0, 1024);
+        const uint32_t kinc = p.b_mn ? 128u : 2u;  // one K step (16): 16 rows x 128 B, or 32 B inside the swizzle row
         const uint32_t a_step = a_bytes >> 4, b_step = b_bytes >> 4, bt_step = bt_bytes >> 4;
         const int kc_blocks = p.kc_blocks, ntaps = p.ntaps / p.group, group = p.group;
         const uint32_t goff1 = p.a_goff[1], goff2 = p.a_goff[2], goff0 = p.a_goff[0];
@@ -141,9 +151,9 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __g
                             const uint64_t b_desc = b_st + g * bt_step;
                             // 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (>>4) address field
                             umma_f16(d_tmem, a_desc, b_desc, idesc, g == 0 ? accum : 1u);
-                            if (nk > 1) umma_f16(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);
-                            if (nk > 2) umma_f16(d_tmem, a_desc + 4, b_desc + 4, idesc, 1u);
-                            if (nk > 3) umma_f16(d_tmem, a_desc + 6, b_desc + 6, idesc, 1u);
+                            if (nk > 1) umma_f16(d_tmem, a_desc + 2, b_desc + kinc, idesc, 1u);
+                            if (nk > 2) umma_f16(d_tmem, a_desc + 4, b_desc + 2 * kinc, idesc, 1u);
+                            if (nk > 3) umma_f16(d_tmem, a_desc + 6, b_desc + 3 * kinc, idesc, 1u);
                         }
                         umma_commit(empty_bar(ps.stage));
                     }

@@ -48,6 +48,8 @@ struct alignas(64) IgemmParams {
     int group;          // taps per pipeline stage: 1, or 3 (h-halo mode: one A box of th+2 rows serves kh = 0,1,2)
     int a_stage_bytes;  // bytes of one A box (16 KB, or (th+2)*tw*128 B in h-halo mode)
     int a_goff[3];      // start offset (bytes >> 4) of tap g of a group inside the A box
+    int b_mn;           // 1: B is read MN-major from the fprop-packed weights [tap][K rows][N contiguous] (dgrad):
+                        //    per stage ceil(block_n/64) atoms of [group taps][64 K rows][64 N] (8 KB per tap)
     int mode;
     const float* vec0;  // bias (modes 1,3) or scale (mode 2)
     const float* vec1;  // shift (mode 2)

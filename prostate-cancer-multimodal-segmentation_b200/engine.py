@@ -39,18 +39,16 @@ class _ConvPack:
             self.k_real = 27 * self.cin
             self.cin_pad = _pad16(self.k_real)  # width of the im2col rows
             self.wf = torch.empty(self.cout, self.cin_pad, device=device, dtype=torch.bfloat16)
-            self.wd = None
         else:
             self.k_real = self.cin
             self.cin_pad = _pad16(self.cin)
             self.wf = torch.empty(27, self.cout, self.cin_pad, device=device, dtype=torch.bfloat16)
-            self.wd = torch.empty(27, self.cin_pad, self.cout, device=device, dtype=torch.bfloat16)
 
     def pack(self):
         if self.im2col:
             ops.pack_rows(self.conv.weight.data, self.cin_pad, self.wf)
         else:
-            ops.pack_conv_weight(self.conv.weight.data, self.cin_pad, self.wf, self.wd)
+            ops.pack_conv_weight(self.conv.weight.data, self.cin_pad, self.wf)
 
     def make_input(self, x: torch.Tensor) -> ActView:
         """fp32 (N,C,D,H,W) -> the bf16 operand this conv reads (channel-padded NDHWC, or im2col rows)"""
@@ -72,7 +70,7 @@ class _ConvPack:
     def dgrad(self, dy, dx):
         if self.im2col:
             raise B200Error("input gradient of an im2col'd (thin-input) convolution is not available")
-        ops.conv3d_dgrad(dy, self.wd, dx)
+        ops.conv3d_dgrad(dy, self.wf, dx)
 
 
 class _ConvTPack:

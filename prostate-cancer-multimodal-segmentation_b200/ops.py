@@ -119,11 +119,11 @@ def conv1_wgrad(x: ActView, dy: ActView, dw: torch.Tensor, k_real: int):
           lambda: check(lib.b200_conv1_wgrad(x.ref, dy.ref, ptr(dw), k_real, stream_ptr()), "conv1_wgrad"))
 
 
-def pack_conv_weight(w: torch.Tensor, cin_pad: int, w_fprop, w_dgrad):
+def pack_conv_weight(w: torch.Tensor, cin_pad: int, w_packed):
     _launched(1)
     cout, cin = w.shape[0], w.shape[1]
     assert w.dtype == torch.float32 and w.is_contiguous()
-    check(_lib.load().b200_pack_conv_weight(ptr(w), cout, cin, cin_pad, ptr(w_fprop), ptr(w_dgrad), stream_ptr()),
+    check(_lib.load().b200_pack_conv_weight(ptr(w), cout, cin, cin_pad, ptr(w_packed), stream_ptr()),
           "pack_conv_weight")
 
 
@@ -150,10 +150,10 @@ def conv3d_fprop(x: ActView, w_fprop, bias, y: ActView, stats=None, mode=EPI_BIA
                                               ptr(shift), stream_ptr()), "conv3d_fprop"))
 
 
-def conv3d_dgrad(dy: ActView, w_dgrad, dx: ActView):
+def conv3d_dgrad(dy: ActView, w_packed, dx: ActView):
     lib = _lib.load()
     _gemm("igemm_kernel", "conv3d_dgrad", 2.0 * dy.voxels * dy.c * dx.c * 27,
-          lambda: check(lib.b200_conv3d_dgrad(dy.ref, ptr(w_dgrad), dx.ref, stream_ptr()), "conv3d_dgrad"))
+          lambda: check(lib.b200_conv3d_dgrad(dy.ref, ptr(w_packed), dx.ref, stream_ptr()), "conv3d_dgrad"))
 
 
 def conv3d_wgrad(x: ActView, dy: ActView, dw: torch.Tensor, cin_real: int):

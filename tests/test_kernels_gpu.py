@@ -45,15 +45,13 @@ def test_conv3d_fprop_bias_stats(ops, cuda_dev, case):
     n, cin, cin_real, cout, d, h, w = case
     x, wt, b = _conv_inputs(cuda_dev, n, cin, cout, d, h, w, cin_real=cin_real)
     wf = torch.empty(27, cout, cin, device=cuda_dev, dtype=torch.bfloat16)
-    wd = torch.empty(27, cin, cout, device=cuda_dev, dtype=torch.bfloat16)
-    ops.pack_conv_weight(wt.contiguous(), cin, wf, wd)
+    ops.pack_conv_weight(wt.contiguous(), cin, wf)
     # packing is exact
     ref_wf = torch.zeros(27, cout, cin, device=cuda_dev)
     # packed tap order t = kd*9 + kw*3 + kh; torch's native order is kd*9 + kh*3 + kw
     native = [(t // 9) * 9 + (t % 3) * 3 + (t // 3) % 3 for t in range(27)]
     ref_wf[:, :, :cin_real] = wt.reshape(cout, cin_real, 27).permute(2, 0, 1)[native]
     assert torch.equal(wf.float(), ref_wf)
-    assert torch.equal(wd.float(), ref_wf.permute(0, 2, 1))
 
     xv = to_act(ops, x)
     yv = empty_act(ops, n, cout, d, h, w, cuda_dev)
@@ -77,7 +75,7 @@ def test_conv3d_fprop_affine_relu_and_views(ops, cuda_dev):
     n, cin, cout, d, h, w = 1, 64, 64, 8, 8, 8
     x, wt, _ = _conv_inputs(cuda_dev, n, cin, cout, d, h, w, seed=3)
     wf = torch.empty(27, cout, cin, device=cuda_dev, dtype=torch.bfloat16)
-    ops.pack_conv_weight(wt.contiguous(), cin, wf, None)
+    ops.pack_conv_weight(wt.contiguous(), cin, wf)
     scale = torch.rand(cout, device=cuda_dev) + 0.5
     shift = torch.randn(cout, device=cuda_dev) * 0.2
     xv = to_act(ops, x, ld=128, c_off=64)
@@ -97,11 +95,11 @@ def test_conv3d_dgrad(ops, cuda_dev, case):
     _, wt, _ = _conv_inputs(cuda_dev, n, cin, cout, d, h, w, seed=1)
     g = torch.Generator(device="cpu").manual_seed(5)
     dy = bf16_round(torch.randn(n, cout, d, h, w, generator=g)).to(cuda_dev)
-    wd = torch.empty(27, cin, cout, device=cuda_dev, dtype=torch.bfloat16)
-    ops.pack_conv_weight(wt.contiguous(), cin, None, wd)
+    wf = torch.empty(27, cout, cin, device=cuda_dev, dtype=torch.bfloat16)
+    ops.pack_conv_weight(wt.contiguous(), cin, wf)   # dgrad reads the fprop-packed weights as an MN-major operand
     dyv = to_act(ops, dy)
     dxv = empty_act(ops, n, cin, d, h, w, cuda_dev)
-    ops.conv3d_dgrad(dyv, wd, dxv)
+    ops.conv3d_dgrad(dyv, wf, dxv)
     torch.cuda.synchronize()
     ref = torch.nn.grad.conv3d_input((n, cin, d, h, w), wt, dy, padding=1)
     err = rel_l2(from_act(dxv), ref)
