@@ -76,8 +76,11 @@ def load():
     if _lib is not None:
         return _lib
     path = _build.LIB_PATH
-    if not os.path.exists(path):
-        path = _build.build()
+    try:
+        path = _build.build()  # no-op unless the library is missing or older than its sources
+    except Exception:
+        if not os.path.exists(path):
+            raise  # no library and no way to build it: fail loudly, there is no fallback
     lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing: fail loudly
