@@ -41,6 +41,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile-pass", action="store_true")
     ap.add_argument("--dump-kernels", default=None, help="write the per-launch GEMM timing table of the profile pass")
+    ap.add_argument("--workload", default="train", choices=["train", "infer"],
+                    help="train: BASELINE configs[1]/[2] (default, the headline); infer: configs[3] sliding-window "
+                         "inference on 5x256x256x64 volumes, one volume per GPU, windows 128x128x64 stride 64")
     return ap.parse_args()
 
 
@@ -149,6 +152,73 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": max(pw)}
 
 
+# ------------------------------------------------------------------------------------------------ inference workload
+def run_infer(args, pkg, par, dev, world, rank):
+    """BASELINE configs[3]: sliding-window inference, `world` volumes of 5x256x256x64, the 9*world windows dealt
+    round-robin to the ranks, one all-reduce of the logit volumes, sigmoid + threshold.  voxels/s = output voxels."""
+    import torch
+    import torch.distributed as dist
+    torch.manual_seed(0)
+    model = pkg.UNet3D(5, 1, init_features=args.base).to(dev).eval()
+    g = torch.Generator().manual_seed(99)
+    x_host = torch.rand(world, 5, 256, 256, 64, generator=g).pin_memory()
+    x = x_host.to(dev)
+    window, stride = (128, 128, 64), (64, 64, 64)
+
+    def step():
+        return par.sliding_window_predict(model, x, window, stride, rank=rank, world=world)
+
+    for _ in range(args.warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = pkg.ops.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        probs, mask = step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    launches = pkg.ops.launch_count - l0
+    # end to end: host volume in, host mask out
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        x.copy_(x_host, non_blocking=True)
+        probs, mask = step()
+        m_host = mask.to(torch.uint8).cpu()
+    e3.record()
+    torch.cuda.synchronize()
+    ms2 = e2.elapsed_time(e3)
+    if world > 1:
+        t = torch.tensor([ms2], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms2 = t.item()
+    vox = world * 256 * 256 * 64
+    if rank == 0:
+        fwd, _ = importlib.import_module(PKG + ".engine").total_flops_per_voxel(args.base, 5, 1)
+        win_vox = 9 * 128 * 128 * 64 * world
+        print(json.dumps({
+            "metric": "infer_voxels_per_s", "value": vox / (ms / args.steps * 1e-3), "unit": "voxels/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "UNet3D sliding-window inference, 5x256x256x64 volumes (BASELINE configs[3]), "
+                                   "window 128x128x64 stride 64 (9 windows/volume), one volume per GPU",
+                       "volumes": world, "parallelism": f"windows sharded over {world} rank(s)"},
+            "e2e": {"value": vox / (ms2 / args.steps * 1e-3), "unit": "voxels/s",
+                    "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": int(m_host.numel())},
+            "gpu_launches": launches,
+            "model_tflops": round(win_vox * fwd / (ms / args.steps * 1e-3) / 1e12, 1)}), flush=True)
+
+
 # ------------------------------------------------------------------------------------------------ main arm
 def main():
     args = parse()
@@ -173,6 +243,12 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     pkg.load_library()
 
+    if args.workload == "infer":
+        run_infer(args, pkg, par, dev, world, rank)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     D, H, W = args.size
     B = args.batch
     torch.manual_seed(0)

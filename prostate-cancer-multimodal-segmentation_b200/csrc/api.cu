@@ -153,7 +153,15 @@ static Brick choose_brick(long long w, long long h, long long d) {
     return best;
 }
 
-static int igemm_block_n(long long ncols) { return ncols >= 256 ? 256 : (int)((ncols + 15) / 16 * 16); }
+// UMMA N of a tile.  256 where possible; 128 when 256-wide tiles would leave more than half of the SMs idle (the deep
+// 8^3 / 4^3 levels: few voxel bricks, wide Cout).
+static int sm_count();
+static int igemm_block_n(long long ncols, long long m_tiles) {
+    if (ncols < 256) return (int)((ncols + 15) / 16 * 16);
+    const int sms = sm_count();
+    if (sms > 0 && ncols % 128 == 0 && m_tiles * ((ncols + 255) / 256) * 2 <= sms) return 128;
+    return 256;
+}
 // dynamic shared memory of igemm_kernel: 1 KB alignment slack + stages + epilogue-v2 staging + barriers, TMEM pointer,
 // statistics scratch [4][256][2], per-CTA column sums [kMaxStatCols][2], per-tile column vectors [2][256]
 constexpr int kIgemmFixedSmem = 1024 + 8 * (2 * 8 + 4) + 64 + 4 * 256 * 2 * 4 + kMaxStatCols * 2 * 4 + 2 * 256 * 4;
@@ -172,13 +180,16 @@ static size_t igemm_smem(int stages, int a_bytes, int b_bytes, int c_bytes) {
     return (size_t)kIgemmFixedSmem + (size_t)stages * (a_bytes + b_bytes) + c_bytes;
 }
 // brick geometry of a conv3d / conv1 implicit GEMM; shared by the launcher and b200_conv3d_stat_rows
-static bool conv_geometry(long long w, long long h, long long d, long long cout, int ntaps, Brick* b) {
-    const bool halo = ntaps == 27 && igemm_block_n(cout) <= 128 && w >= 8 && h >= 16;
+static bool conv_geometry(long long n, long long w, long long h, long long d, long long cout, int ntaps, Brick* b,
+                          int* block_n) {
+    const Brick plain = choose_brick(w, h, d);
+    *block_n = igemm_block_n(cout, n * plain.nbw * plain.nbh * plain.nbd);
+    const bool halo = ntaps == 27 && *block_n <= 128 && w >= 8 && h >= 16;
     if (halo) {
         b->tw = 8; b->th = 16; b->td = 1; b->lw = 3; b->lh = 4; b->ld = 0;
         b->nbw = (w + 7) / 8; b->nbh = (h + 15) / 16; b->nbd = d;
     } else {
-        *b = choose_brick(w, h, d);
+        *b = plain;
     }
     return halo;
 }
@@ -239,10 +250,9 @@ static int conv3_igemm(const b200_act* in, const void* w_packed, const b200_act*
     REQUIRE(in->n * in->d * in->h * in->w < (1LL << 31), "conv3d: too many voxels");
     IgemmParams p;
     memset(&p, 0, sizeof(p));
-    p.block_n = igemm_block_n(out->c);
     // h-halo mode: worth it when the MMA per tap is short (narrow N) and the volume holds 8 x 16 bricks
     Brick b;
-    const bool halo = conv_geometry(in->w, in->h, in->d, out->c, ntaps, &b);
+    const bool halo = conv_geometry(in->n, in->w, in->h, in->d, out->c, ntaps, &b, &p.block_n);
     rc = make_act_map(&p.a_map[0], reinterpret_cast<const __nv_bfloat16*>(in->ptr), in->c, in->w, in->h, in->d, in->n,
                       in->ld, in->w, in->h, in->d, 1, b.tw, halo ? b.th + 2 : b.th, b.td);
     if (rc) return rc;
@@ -299,9 +309,9 @@ static int conv3_igemm(const b200_act* in, const void* w_packed, const b200_act*
 extern "C" int b200_conv3d_stat_rows(int64_t n, int64_t d, int64_t h, int64_t w, int64_t cout, int ntaps) {
     const int sms = sm_count();
     if (sms <= 0) return -1;
-    const int bn = igemm_block_n(cout);
+    int bn = 0;
     Brick b;
-    conv_geometry(w, h, d, cout, ntaps, &b);
+    conv_geometry(n, w, h, d, cout, ntaps, &b, &bn);
     const long long tiles = n * b.nbw * b.nbh * b.nbd * ((cout + bn - 1) / bn);
     return (int)(tiles < sms ? tiles : sms);
 }
@@ -380,7 +390,7 @@ extern "C" int b200_convt2x_fwd(const b200_act* x, const void* w_fwd, const floa
                       x->ld, x->w, x->h, x->d, 1, b.tw, b.th, b.td);
     if (rc) return rc;
     const long long ncols = 8 * y->c;
-    p.block_n = igemm_block_n(ncols);
+    p.block_n = igemm_block_n(ncols, x->n * b.nbw * b.nbh * b.nbd);
     // a 256-column tile must not straddle a tap group unless the group size divides it
     REQUIRE(p.block_n % 16 == 0 && (y->c % 16 == 0), "convt2x_fwd: bad column tiling");
     rc = make_weight_map(&p.b_map, w_fwd, x->c, ncols, 1, p.block_n);
@@ -436,7 +446,7 @@ extern "C" int b200_convt2x_dgrad(const b200_act* dy, int pad_d, int pad_h, int 
         if (rc) return rc;
         p.a_map_of_tap[t] = t;
     }
-    p.block_n = igemm_block_n(dx->c);
+    p.block_n = igemm_block_n(dx->c, dx->n * b.nbw * b.nbh * b.nbd);
     rc = make_weight_map(&p.b_map, w_dgrad, dy->c, dx->c, 8, p.block_n);
     if (rc) return rc;
     p.ntaps = 8;

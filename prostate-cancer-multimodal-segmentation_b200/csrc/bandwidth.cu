@@ -576,7 +576,10 @@ cudaError_t launch_maxpool_fwd(View x, View y, int sms, cudaStream_t s) {
     return cudaGetLastError();
 }
 
-// one thread = one 2x2x2 cell of the input grid (cells cover ceil(dim/2)) x 8 channels
+// one thread = one 2x2x2 cell of the input grid (cells cover ceil(dim/2)) x 8 channels; all selection logic stays in
+// packed bf16x2 (compare masks), so the eight input vectors cost 32 registers instead of 64
+DEV uint32_t bits(const __nv_bfloat162& v) { return *reinterpret_cast<const uint32_t*>(&v); }
+DEV __nv_bfloat162 from_bits(uint32_t u) { return *reinterpret_cast<__nv_bfloat162*>(&u); }
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(View x, View dy, View dskip, int has_skip, View dx,
                                                           FastDiv c8d, FastDiv cwd, FastDiv chd, FastDiv cdd,
                                                           uint32_t total) {
@@ -591,47 +594,48 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(View x, View dy, View 
         const uint32_t cd = r - q * cdd.div;
         const uint32_t nb = q;
         const bool full = (2 * cd + 1 < x.d) && (2 * ch + 1 < x.h) && (2 * cw + 1 < x.w);
-        float xin[8][8];
-        float g[8];
+        const long long v000 = (((long long)nb * x.d + 2 * cd) * x.h + 2 * ch) * x.w + 2 * cw;
+        Bf8 xin[8], g, mx;
         if (full) {
             const long long ov = (((long long)nb * dy.d + cd) * dy.h + ch) * dy.w + cw;
-            unpack8(ld8_stream(dy.p + ov * dy.ld + c0), g);
-        }
-        float mx[8];
+            g = ld8_stream(dy.p + ov * dy.ld + c0);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int kd = (k >> 2) & 1, kh = (k >> 1) & 1, kw = k & 1;
-            if (full) {
-                const long long v = (((long long)nb * x.d + 2 * cd + kd) * x.h + 2 * ch + kh) * x.w + 2 * cw + kw;
-                unpack8(ld8_stream(x.p + v * x.ld + c0), xin[k]);
+            for (int k = 0; k < 8; ++k) {
+                const long long v = v000 + ((k >> 2) & 1) * x.h * x.w + ((k >> 1) & 1) * x.w + (k & 1);
+                xin[k] = ld8_stream(x.p + v * x.ld + c0);
+            }
 #pragma unroll
-                for (int j = 0; j < 8; ++j) mx[j] = (k == 0) ? xin[0][j] : fmaxf(mx[j], xin[k][j]);
+            for (int j = 0; j < 4; ++j) {
+                __nv_bfloat162 m = xin[0].v[j];
+#pragma unroll
+                for (int k = 1; k < 8; ++k) m = __hmax2(m, xin[k].v[j]);
+                mx.v[j] = m;
             }
         }
-        bool taken[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) taken[j] = false;
+        uint32_t taken[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const int kd = (k >> 2) & 1, kh = (k >> 1) & 1, kw = k & 1;
             const uint32_t d = 2 * cd + kd, h = 2 * ch + kh, w = 2 * cw + kw;
             if (d < x.d && h < x.h && w < x.w) {
-                const long long v = (((long long)nb * x.d + d) * x.h + h) * x.w + w;
-                float o[8];
-                if (has_skip)
-                    unpack8(ld8_stream(dskip.p + v * dskip.ld + c0), o);
-                else {
+                const long long v = v000 + (long long)kd * x.h * x.w + kh * x.w + kw;
+                Bf8 o;
+                if (has_skip) {
+                    o = ld8_stream(dskip.p + v * dskip.ld + c0);
+                } else {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) o[j] = 0.f;
+                    for (int j = 0; j < 4; ++j) o.v[j] = from_bits(0u);
                 }
                 if (full) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const bool hit = !taken[j] && xin[k][j] == mx[j];
-                        if (hit) { o[j] += g[j]; taken[j] = true; }
+                    for (int j = 0; j < 4; ++j) {
+                        // first position (d, h, w scan order) equal to the window maximum takes the gradient
+                        const uint32_t hit = __heq2_mask(xin[k].v[j], mx.v[j]) & ~taken[j];
+                        taken[j] |= hit;
+                        o.v[j] = __hadd2(o.v[j], from_bits(bits(g.v[j]) & hit));
                     }
                 }
-                st8(dx.p + v * dx.ld + c0, pack8(o));
+                st8(dx.p + v * dx.ld + c0, o);
             }
         }
     }

@@ -223,3 +223,29 @@ def test_grad_scaler_and_autocast_api(pkg, cuda_dev):
         losses.append(loss.item())
     assert all(torch.isfinite(torch.tensor(losses)))
     assert losses[-1] < losses[0]
+
+
+def test_baseline_config_shapes_smoke(pkg, cuda_dev):
+    """BASELINE configs[4]: zero_fill inputs at 5x160^3 with base 32 (one full training step) and configs[3]'s window
+    shape 128x128x64 in eval mode at base 64; sanity only (finite, right shapes) — parity is covered at small sizes."""
+    torch.manual_seed(0)
+    m32 = pkg.UNet3D(5, 1, init_features=32).to(cuda_dev).train()
+    ds = pkg.data.SyntheticProstateDataset(2, (160, 160, 160), "zero_fill", missing_prob=0.5, seed=3)
+    batch = ds[1]
+    x = batch["image"].unsqueeze(0).to(cuda_dev)
+    y = batch["label"].unsqueeze(0).to(cuda_dev)
+    opt = pkg.FusedAdam(m32, lr=1e-4, weight_decay=1e-5)
+    losses = []
+    for _ in range(2):
+        opt.zero_grad()
+        loss = pkg.DiceLoss()(m32(x), y)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert all(0.0 < l < 1.0 for l in losses)
+    del m32, opt
+    torch.cuda.empty_cache()
+    m64 = pkg.UNet3D(5, 1).to(cuda_dev)
+    probs = m64.predict(torch.rand(1, 5, 128, 128, 64, device=cuda_dev))
+    assert probs.shape == (1, 1, 128, 128, 64) and torch.isfinite(probs).all()
+    assert 0.0 <= probs.min().item() and probs.max().item() <= 1.0
