@@ -360,22 +360,44 @@ static LaneMap lane_map(long long c) {
     return m;
 }
 
+// dynamic shared memory of the final per-block reduction (floats): small on purpose — these kernels are meant to
+// co-reside with a persistent GEMM CTA that leaves < 30 KB of the SM's shared memory
+static size_t reduce_smem_bytes(const LaneMap& m, int nacc) {
+    const bool warp_pre = m.c8 <= 32 && (m.c8 & (m.c8 - 1)) == 0;
+    const int slabs = warp_pre ? 8 : m.rows;
+    return (size_t)slabs * m.c8 * nacc * 8 * sizeof(float);
+}
+
 template <int NACC>
 DEV void block_reduce_store(float (&acc)[NACC][8], int c8, int rows, int row, int cv, bool active, float* smem,
                             float* dst /* [c][NACC] or atomics */, int c, bool atomic) {
-    // smem [rows][c8][NACC*8]
+    const bool warp_pre = c8 <= 32 && (c8 & (c8 - 1)) == 0;
+    int slabs = rows, slab = row;
+    if (warp_pre) {
+        // rows that share a warp are folded with shuffles first (lane = row_in_warp * c8 + cv)
+        for (int off = c8; off < 32; off <<= 1) {
+#pragma unroll
+            for (int a = 0; a < NACC; ++a)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[a][j] += __shfl_xor_sync(0xffffffffu, acc[a][j], off);
+        }
+        slabs = 8;
+        slab = threadIdx.x >> 5;
+        active = (threadIdx.x & 31) < c8;  // one lane per channel group holds the warp's total
+    }
+    // smem [slabs][c8][NACC*8]
     if (active) {
 #pragma unroll
         for (int a = 0; a < NACC; ++a)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) smem[((row * c8 + cv) * NACC + a) * 8 + j] = acc[a][j];
+            for (int j = 0; j < 8; ++j) smem[((slab * c8 + cv) * NACC + a) * 8 + j] = acc[a][j];
     }
     __syncthreads();
     for (int t = threadIdx.x; t < c * NACC; t += blockDim.x) {
         const int ch = t / NACC, a = t - ch * NACC;
         const int cvv = ch >> 3, j = ch & 7;
         float s = 0.f;
-        for (int r = 0; r < rows; ++r) s += smem[((r * c8 + cvv) * NACC + a) * 8 + j];
+        for (int r = 0; r < slabs; ++r) s += smem[((r * c8 + cvv) * NACC + a) * 8 + j];
         if (atomic)
             atomicAdd(dst + ch * NACC + a, s);
         else
@@ -424,7 +446,7 @@ cudaError_t launch_bn_bwd_reduce(View dout, View y, const float* scale, const fl
     if (blocks > kBwdMaxBlocks) blocks = kBwdMaxBlocks;
     if (blocks < 1) blocks = 1;
     *nblk = (int)blocks;
-    const size_t smem = (size_t)m.rows * m.c8 * 16 * sizeof(float);
+    const size_t smem = reduce_smem_bytes(m, 2);
     bn_bwd_reduce_kernel<<<(int)blocks, 256, smem, s>>>(dout, y, scale, shift, mean, rstd, partial, m.c8, m.rows,
                                                        nvox);
     return cudaGetLastError();
@@ -501,7 +523,7 @@ cudaError_t launch_bn_bwd_apply(View dout, View y, const float* scale, const flo
     long long blocks = (nvox + m.rows * 8LL - 1) / (m.rows * 8LL);
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
-    const size_t smem = (size_t)m.rows * m.c8 * 8 * sizeof(float);
+    const size_t smem = reduce_smem_bytes(m, 1);
     bn_bwd_apply_kernel<<<(int)blocks, 256, smem, s>>>(dout, y, scale, shift, mean, rstd, coef, dy, dbias, m.c8, m.rows,
                                                       nvox);
     return cudaGetLastError();
@@ -531,7 +553,7 @@ cudaError_t launch_channel_sum(View v, float* out, cudaStream_t s) {
     long long blocks = (nvox + m.rows * 8LL - 1) / (m.rows * 8LL);
     if (blocks > 148 * 4) blocks = 148 * 4;
     if (blocks < 1) blocks = 1;
-    const size_t smem = (size_t)m.rows * m.c8 * 8 * sizeof(float);
+    const size_t smem = reduce_smem_bytes(m, 1);
     channel_sum_kernel<<<(int)blocks, 256, smem, s>>>(v, out, m.c8, m.rows, nvox);
     return cudaGetLastError();
 }

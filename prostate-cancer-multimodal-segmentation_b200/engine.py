@@ -150,8 +150,9 @@ class _DoubleConv:
         return st
 
     # ---- backward
-    def backward(self, st: _DCState, dout: ActView, dxin, grads, scratch):
-        """dout: gradient w.r.t. the block output; dxin: view to receive the input gradient (None: not needed)"""
+    def backward(self, st: _DCState, dout: ActView, dxin, grads, scratch, side):
+        """dout: gradient w.r.t. the block output; dxin: view to receive the input gradient (None: not needed).
+        Weight gradients are launched through `side` (runs them on the side stream, see Engine._Side)."""
         n, d, h, w, _ = dout.shape
         dev = dout.t.device
         g = grads
@@ -159,17 +160,53 @@ class _DoubleConv:
         dy2 = ActView(new_act(n, d, h, w, self.cout, dev))
         ops.bn_bwd(dout, st.y2, st.bn2[2], st.bn2[3], st.bn2[0], st.bn2[1], self.bn2.weight.data, scratch.partial,
                    scratch.coef, g(self.bn2.weight), g(self.bn2.bias), dy2, g(self.conv2.bias))
-        self.p2.wgrad(st.a1, dy2, g(self.conv2.weight))
+        side.run(lambda: self.p2.wgrad(st.a1, dy2, g(self.conv2.weight)), keep=(st.a1, dy2))
         da1 = ActView(new_act(n, d, h, w, self.cout, dev))
         self.p2.dgrad(dy2, da1)
         st.y2 = None
-        # first conv (dy1 reuses dy2's buffer)
-        dy1 = dy2
+        # first conv
+        dy1 = ActView(new_act(n, d, h, w, self.cout, dev))
         ops.bn_bwd(da1, st.y1, st.bn1[2], st.bn1[3], st.bn1[0], st.bn1[1], self.bn1.weight.data, scratch.partial,
                    scratch.coef, g(self.bn1.weight), g(self.bn1.bias), dy1, g(self.conv1.bias))
-        self.p1.wgrad(st.xin, dy1, g(self.conv1.weight))
+        side.run(lambda: self.p1.wgrad(st.xin, dy1, g(self.conv1.weight)), keep=(st.xin, dy1))
         if dxin is not None:
             self.p1.dgrad(dy1, dxin)
+
+
+class _Side:
+    """Weight-gradient GEMMs run on a second stream: they hang off the backward chain (nothing downstream reads them
+    before the optimizer), so they overlap with the HBM-bound BatchNorm-backward / pool-backward kernels of the next
+    layer, which fit beside a persistent GEMM CTA on every SM.  Buffers they read are kept alive until join()."""
+
+    def __init__(self, enabled=True):
+        self.enabled = enabled
+        self.stream = torch.cuda.Stream() if enabled else None
+        self.keep = []
+
+    def run(self, fn, keep=()):
+        if not self.enabled:
+            fn()
+            return
+        main = torch.cuda.current_stream()
+        self.stream.wait_event(main.record_event())
+        with torch.cuda.stream(self.stream):
+            fn()
+        self.keep.extend(keep)
+
+    def sync_point(self, fn):
+        """run fn (data-parallel bucket launch) where every gradient produced so far on either stream is visible"""
+        if not self.enabled:
+            fn()
+            return
+        main = torch.cuda.current_stream()
+        self.stream.wait_event(main.record_event())
+        with torch.cuda.stream(self.stream):
+            fn()
+
+    def join(self):
+        if self.enabled:
+            torch.cuda.current_stream().wait_stream(self.stream)
+        self.keep = []
 
 
 class _Scratch:
@@ -189,7 +226,8 @@ class Engine:
         self.device = None
         self._pack_key = None
         self.external_epoch = 0  # bumped by anything that writes parameter memory behind torch's back (FusedAdam)
-        self.grad_sync = None    # optional data-parallel hook: object with .ready(lo, hi) and .finish()
+        self.grad_sync = None    # optional data-parallel hook: object with .ready(hi) and .finish()
+        self.overlap_wgrad = True  # weight gradients on a side stream (see _Side)
         self.flat_param = None
         self.flat_grad = None
         self._slots = None       # id(param) -> (offset, numel)
@@ -379,13 +417,14 @@ class Engine:
         ch = [f, 2 * f, 4 * f, 8 * f, 16 * f]
         g, foreign = self._begin_grads()
         sync = self.grad_sync
+        side = _Side(self.overlap_wgrad)
         if dlogits.dtype != torch.float32 or not dlogits.is_contiguous():
             dlogits = dlogits.float().contiguous()
 
         def mark(p):
             if sync is not None:
                 o, cnt = self._slots[id(p)]
-                sync.ready(o + cnt)
+                side.sync_point(lambda: sync.ready(o + cnt))
 
         dcur = ActView(new_act(n, *dims[0], ch[0], dev))
         ops.head_bwd(tape.last, m.outc.weight.data.view(m.n_classes, -1), dlogits, dcur,
@@ -398,7 +437,7 @@ class Engine:
             tp, dc = self.ups[j - 1]
             dcat = new_act(n, *dims[k], 2 * ch[k], dev)
             dcats[k] = dcat
-            dc.backward(tape.dcs[f"up{j}"], dcur, ActView(dcat), g, self.scratch)
+            dc.backward(tape.dcs[f"up{j}"], dcur, ActView(dcat), g, self.scratch, side)
             tape.dcs[f"up{j}"] = None
             mark(dc.conv1.bias)
             dupper = ActView(dcat, ch[k], ch[k])
@@ -410,7 +449,9 @@ class Engine:
             else:  # F.pad border carries no bias gradient: reduce the un-padded core only
                 core = dupper.as_torch()[:, pad[0]:pad[0] + 2 * d1, pad[1]:pad[1] + 2 * h1, pad[2]:pad[2] + 2 * w1]
                 g(tp.up.bias).add_(core.float().sum((0, 1, 2, 3)))
-            ops.convt2x_wgrad(x_in, dupper, pad, g(tp.up.weight))
+            side.run(lambda x_in=x_in, dupper=dupper, pad=pad, tp=tp: ops.convt2x_wgrad(x_in, dupper, pad,
+                                                                                      g(tp.up.weight)),
+                     keep=(x_in, dupper, dcat))
             dprev = ActView(new_act(*x_in.shape, dev))
             ops.convt2x_dgrad(dupper, pad, tp.wd, dprev)
             mark(tp.up.bias)
@@ -419,20 +460,21 @@ class Engine:
         for k in (4, 3, 2, 1):
             dcobj = self.downs[k - 1]
             dpool = ActView(new_act(n, *dims[k], ch[k - 1], dev))
-            dcobj.backward(tape.dcs[f"down{k}"], dcur, dpool, g, self.scratch)
+            dcobj.backward(tape.dcs[f"down{k}"], dcur, dpool, g, self.scratch, side)
             tape.dcs[f"down{k}"] = None
             mark(dcobj.conv1.bias)
             skip_act = ActView(tape.cats[k - 1], 0, ch[k - 1])
             dskip = ActView(dcats[k - 1], 0, ch[k - 1])
             ops.maxpool3d_bwd(skip_act, dpool, dskip, dskip)  # in place: dskip += scatter(dpool)
             dcur = dskip
-        self.inc.backward(tape.dcs["inc"], dcur, None, g, self.scratch)
+        self.inc.backward(tape.dcs["inc"], dcur, None, g, self.scratch, side)
         mark(self.inc.conv1.bias)
         tape.dcs = tape.cats = tape.pooled = None
+        if sync is not None:
+            side.sync_point(sync.finish)
+        side.join()
         for p, tmp in foreign:
             p.grad.add_(tmp.to(p.grad.dtype))
-        if sync is not None:
-            sync.finish()
 
 
 def total_flops_per_voxel(init_features: int = 64, n_modalities: int = 5, n_classes: int = 1):

@@ -61,7 +61,9 @@ def test_double_conv_block(pkg, ops, cuda_dev, cin, cout, shape):
     dxin = empty_act(ops, n, cpad, d, h, w, cuda_dev) if cin % 16 == 0 else None
     grads = _Grads()
     scratch = eng._Scratch(cuda_dev, cout)
-    dc.backward(st, to_act(ops, dout), dxin, grads, scratch)
+    side = eng._Side(enabled=True)
+    dc.backward(st, to_act(ops, dout), dxin, grads, scratch, side)
+    side.join()
     torch.cuda.synchronize()
 
     leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items() if "running" not in k and "num_batches" not in k}
