@@ -334,8 +334,10 @@ def main():
     if not args.no_profile_pass:
         recs = []
         ops.profile_hook = lambda k, tag, fl, a, b: recs.append((k, tag, fl, a, b))
+        model.engine.overlap_wgrad = False   # per-kernel durations: no concurrent side-stream kernels in this pass
         step(x, y)
         torch.cuda.synchronize()
+        model.engine.overlap_wgrad = True
         ops.profile_hook = None
         if args.dump_kernels and rank == 0:
             with open(args.dump_kernels, "w") as f:

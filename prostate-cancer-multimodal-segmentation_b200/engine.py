@@ -160,17 +160,19 @@ class _DoubleConv:
         dy2 = ActView(new_act(n, d, h, w, self.cout, dev))
         ops.bn_bwd(dout, st.y2, st.bn2[2], st.bn2[3], st.bn2[0], st.bn2[1], self.bn2.weight.data, scratch.partial,
                    scratch.coef, g(self.bn2.weight), g(self.bn2.bias), dy2, g(self.conv2.bias))
-        side.run(lambda: self.p2.wgrad(st.a1, dy2, g(self.conv2.weight)), keep=(st.a1, dy2))
+        # dgrad first: it is on the critical chain (the next BatchNorm backward needs da1) and must win the SMs; the
+        # weight gradient then runs beside that BatchNorm backward
         da1 = ActView(new_act(n, d, h, w, self.cout, dev))
         self.p2.dgrad(dy2, da1)
+        side.run(lambda: self.p2.wgrad(st.a1, dy2, g(self.conv2.weight)), keep=(st.a1, dy2))
         st.y2 = None
         # first conv
         dy1 = ActView(new_act(n, d, h, w, self.cout, dev))
         ops.bn_bwd(da1, st.y1, st.bn1[2], st.bn1[3], st.bn1[0], st.bn1[1], self.bn1.weight.data, scratch.partial,
                    scratch.coef, g(self.bn1.weight), g(self.bn1.bias), dy1, g(self.conv1.bias))
-        side.run(lambda: self.p1.wgrad(st.xin, dy1, g(self.conv1.weight)), keep=(st.xin, dy1))
         if dxin is not None:
             self.p1.dgrad(dy1, dxin)
+        side.run(lambda: self.p1.wgrad(st.xin, dy1, g(self.conv1.weight)), keep=(st.xin, dy1))
 
 
 class _Side:
@@ -449,11 +451,11 @@ class Engine:
             else:  # F.pad border carries no bias gradient: reduce the un-padded core only
                 core = dupper.as_torch()[:, pad[0]:pad[0] + 2 * d1, pad[1]:pad[1] + 2 * h1, pad[2]:pad[2] + 2 * w1]
                 g(tp.up.bias).add_(core.float().sum((0, 1, 2, 3)))
+            dprev = ActView(new_act(*x_in.shape, dev))
+            ops.convt2x_dgrad(dupper, pad, tp.wd, dprev)
             side.run(lambda x_in=x_in, dupper=dupper, pad=pad, tp=tp: ops.convt2x_wgrad(x_in, dupper, pad,
                                                                                       g(tp.up.weight)),
                      keep=(x_in, dupper, dcat))
-            dprev = ActView(new_act(*x_in.shape, dev))
-            ops.convt2x_dgrad(dupper, pad, tp.wd, dprev)
             mark(tp.up.bias)
             dcur = dprev
         tape.dec_in = None
