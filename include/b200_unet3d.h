@@ -80,8 +80,11 @@ int b200_conv3d_stat_rows(int64_t n, int64_t d, int64_t h, int64_t w, int64_t co
 int b200_conv3d_fprop(const b200_act* x, const void* w_packed, const float* bias, const b200_act* y,
                       float* stats_partial, int mode, const float* scale, const float* shift, void* stream);
 int b200_conv3d_dgrad(const b200_act* dy, const void* w_packed, const b200_act* dx, void* stream);
-/* dw fp32 (Cout, cin_real, 3,3,3) += ; x->c may exceed cin_real (zero padded channels) */
-int b200_conv3d_wgrad(const b200_act* x, const b200_act* dy, float* dw, int cin_real, void* stream);
+/* dw += weight gradient; x->c may exceed cin_real (zero padded channels).
+ * packed_layout = 0: dw is torch's (Cout, cin_real, 3,3,3);  1: dw is [27][Cout][cin_real] in the packed tap order
+ * of b200_pack_conv_weight (the engine's physical parameter layout: contiguous, coalesced accumulation). */
+int b200_conv3d_wgrad(const b200_act* x, const b200_act* dy, float* dw, int cin_real, int packed_layout,
+                      void* stream);
 
 /* ---- ConvTranspose3d k=2 s=2 (models/unet3d.py:120,134) + F.pad + cat written in place (:143-156) -------- */
 /* y: view (upper channel half of the concat buffer) with the skip's extents; output voxel (2d+i+pad_d, ...) */
@@ -143,11 +146,14 @@ int b200_loss_bwd(const float* logits, const float* target, int64_t n, float bce
 
 /* ---- optimizer (torch.optim.Adam, utils/trainer.py:113-117,192) ---------------------------------------- */
 /* fused over a flat fp32 buffer: g = grad*grad_scale + wd*p ; Adam moments ; bias-corrected update.
- * step is the 1-based step count.  If found_inf != NULL and *found_inf != 0 the update is skipped. */
+ * step is the 1-based step count.  If found_inf != NULL and *found_inf != 0 the update is skipped.
+ * bf16_shadow (nullable): bf16 copy of the updated parameters written in the same pass. */
 int b200_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                    double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step,
                    double grad_scale,
-                   const float* found_inf, void* stream);
+                   const float* found_inf, void* bf16_shadow, void* stream);
+/* out[i] = bf16(x[i]) — operand shadow of the flat parameter buffer when a foreign optimizer updated it */
+int b200_cast_bf16(const float* x, int64_t n, void* out, void* stream);
 /* sum of squares of a flat fp32 buffer -> out[0] (+=) ; nonfinite flag -> out[1] (clip_grad_norm_/GradScaler) */
 int b200_sumsq(const float* x, int64_t n, float* out, void* stream);
 

@@ -468,7 +468,8 @@ static int launch_wgrad(WgradParams& p, cudaStream_t s) {
     const int sms = sm_count();
     if (sms <= 0) return fail(B200_ERR_CUDA, "no CUDA device");
     static bool attr = false;
-    const size_t smem = 1024 + 2 * 2 * kBoxBytes + 2 * 4 * kBoxBytes + 128;
+    // alignment slack + 2 P slots + 2 Q slots + barriers/TMEM pointer + 4 transpose tiles of 32 x 33 floats
+    const size_t smem = 1024 + 2 * 2 * kBoxBytes + 2 * 4 * kBoxBytes + 128 + 4 * 32 * 33 * 4;
     {
         std::lock_guard<std::mutex> lk(g_mu);
         if (!attr) {
@@ -492,7 +493,8 @@ static int launch_wgrad(WgradParams& p, cudaStream_t s) {
     return 0;
 }
 
-extern "C" int b200_conv3d_wgrad(const b200_act* x, const b200_act* dy, float* dw, int cin_real, void* stream) {
+extern "C" int b200_conv3d_wgrad(const b200_act* x, const b200_act* dy, float* dw, int cin_real, int packed_layout,
+                                 void* stream) {
     CHECK_VIEW(x);
     CHECK_VIEW(dy);
     REQUIRE(dw != nullptr, "conv3d_wgrad: null dw");
@@ -531,9 +533,20 @@ extern "C" int b200_conv3d_wgrad(const b200_act* x, const b200_act* dy, float* d
     p.nbw = (int)b.nbw; p.nbh = (int)b.nbh; p.nbd = (int)b.nbd; p.nbatch = (int)x->n;
     p.tw = b.tw; p.th = b.th; p.td = b.td;
     p.out = dw;
-    p.st = 1;
-    p.sp = swapped ? 27 : (long long)cin_real * 27;
-    p.sq = swapped ? (long long)cin_real * 27 : 27;
+    const long long cout = dy->c;
+    if (packed_layout) {
+        // dw is [27][Cout][Cin] with the packed tap order (kd, kw, kh): Cin contiguous -> coalesced accumulation
+        for (int t = 0; t < 27; ++t) p.tap_out[t] = (t / 9) * 9 + (t % 3) * 3 + (t / 3) % 3;
+        p.st = cout * cin_real;
+        p.sp = swapped ? 1 : cin_real;
+        p.sq = swapped ? cin_real : 1;
+    } else {
+        // dw is torch's (Cout, Cin, 3, 3, 3)
+        for (int t = 0; t < 27; ++t) p.tap_out[t] = t;
+        p.st = 1;
+        p.sp = swapped ? 27 : (long long)cin_real * 27;
+        p.sq = swapped ? (long long)cin_real * 27 : 27;
+    }
     return launch_wgrad(p, (cudaStream_t)stream);
 }
 
@@ -555,6 +568,7 @@ extern "C" int b200_conv1_wgrad(const b200_act* x, const b200_act* dy, float* dw
                       x->ld, x->w, x->h, x->d, 1, b.tw, b.th, b.td);
     if (rc) return rc;
     p.ntaps = 1;
+    p.tap_out[0] = 0;
     p.p_extent = (int)dy->c;
     p.q_extent = k_real;
     p.q_chunks = (k_real + 63) / 64;
@@ -591,6 +605,7 @@ extern "C" int b200_convt2x_wgrad(const b200_act* x, const b200_act* dy, int pad
                           b.td);
         if (rc) return rc;
         p.q_map_of_tap[t] = t;
+        p.tap_out[t] = t;
     }
     p.ntaps = 8;
     p.p_extent = (int)x->c;
@@ -767,13 +782,18 @@ extern "C" int b200_loss_bwd(const float* logits, const float* target, int64_t n
 }
 extern "C" int b200_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                    double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step,
-                   double grad_scale, const float* found_inf, void* stream) {
+                   double grad_scale, const float* found_inf, void* bf16_shadow, void* stream) {
     REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, "adam_step: bad arguments");
     REQUIRE(((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) |
               reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) == 0,
             "adam_step: buffers must be 16-byte aligned");
     CUDA_TRY(launch_adam(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale,
-                         found_inf, sm_count(), (cudaStream_t)stream));
+                         found_inf, reinterpret_cast<__nv_bfloat16*>(bf16_shadow), sm_count(), (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int b200_cast_bf16(const float* x, int64_t n, void* out, void* stream) {
+    REQUIRE(x && out && n > 0, "cast_bf16: bad arguments");
+    CUDA_TRY(launch_cast_bf16(x, n, reinterpret_cast<__nv_bfloat16*>(out), sm_count(), (cudaStream_t)stream));
     return 0;
 }
 extern "C" int b200_sumsq(const float* x, int64_t n, float* out, void* stream) {

@@ -909,11 +909,35 @@ cudaError_t launch_loss_bwd(const float* z, const float* t, long long n, float b
     return cudaGetLastError();
 }
 
+DEV uint32_t pack2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ x, long long n,
+                                                        __nv_bfloat16* __restrict__ out) {
+    const long long n8 = n >> 3;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
+         i += (long long)gridDim.x * blockDim.x) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(x) + 2 * i);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(x) + 2 * i + 1);
+        uint4 o;
+        o.x = pack2(a.x, a.y); o.y = pack2(a.z, a.w); o.z = pack2(b.x, b.y); o.w = pack2(b.z, b.w);
+        reinterpret_cast<uint4*>(out)[i] = o;
+    }
+    if (blockIdx.x == 0)
+        for (long long i = (n8 << 3) + threadIdx.x; i < n; i += blockDim.x) out[i] = __float2bfloat16_rn(x[i]);
+}
+cudaError_t launch_cast_bf16(const float* x, long long n, __nv_bfloat16* out, int sms, cudaStream_t s) {
+    cast_bf16_kernel<<<grid_for(n / 8 + 1, 256, sms, 8), 256, 0, s>>>(x, n, out);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------ Adam
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, long long n,
                                                    float step_size, float b2, float w1, float w2, float eps,
-                                                   float wd, float bc2_sqrt, float gscale, const float* found_inf) {
+                                                   float wd, float bc2_sqrt, float gscale, const float* found_inf,
+                                                   __nv_bfloat16* __restrict__ shadow) {
     // torch.optim.Adam arithmetic: m.lerp_(g, 1-b1); v.mul_(b2).addcmul_(g, g, 1-b2); p.addcdiv_(m, sqrt(v)/bc2+eps)
     if (found_inf && *found_inf != 0.f) return;
     const long long n4 = n >> 2;
@@ -938,6 +962,12 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
         reinterpret_cast<float4*>(p)[i] = pp;
         reinterpret_cast<float4*>(m)[i] = mm;
         reinterpret_cast<float4*>(v)[i] = vv;
+        if (shadow) {  // bf16 operand shadow of the weights, same flat index
+            uint2 sv;
+            sv.x = pack2(pa[0], pa[1]);
+            sv.y = pack2(pa[2], pa[3]);
+            reinterpret_cast<uint2*>(shadow)[i] = sv;
+        }
     }
     if (blockIdx.x == 0) {
         for (long long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
@@ -946,17 +976,18 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
             v[i] = fmaf(w2 * gr, gr, b2 * v[i]);
             const float denom = sqrtf(v[i]) / bc2_sqrt + eps;
             p[i] -= step_size * (m[i] / denom);
+            if (shadow) shadow[i] = __float2bfloat16_rn(p[i]);
         }
     }
 }
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, long long n, double lr, double b1, double b2,
-                        double eps, double wd, long long step, double gscale, const float* found_inf, int sms,
-                        cudaStream_t s) {
+                        double eps, double wd, long long step, double gscale, const float* found_inf,
+                        __nv_bfloat16* shadow, int sms, cudaStream_t s) {
     const double bc1 = 1.0 - pow(b1, (double)step);
     const double bc2 = 1.0 - pow(b2, (double)step);
     adam_kernel<<<grid_for(n / 4 + 1, 256, sms, 8), 256, 0, s>>>(p, g, m, v, n, (float)(lr / bc1), (float)b2,
                                                                 (float)(1.0 - b1), (float)(1.0 - b2), (float)eps,
-                                                                (float)wd, (float)sqrt(bc2), (float)gscale, found_inf);
+                                                                (float)wd, (float)sqrt(bc2), (float)gscale, found_inf, shadow);
     return cudaGetLastError();
 }
 

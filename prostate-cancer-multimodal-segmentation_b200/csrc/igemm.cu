@@ -536,20 +536,47 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __g
         mbar_wait(tfull, 0);
         tc_fence_after();
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        for (int i = 0; i < ncb; ++i) {
-            const int cb = cb0 + i;
-            const int tap = cb / p.q_chunks;
-            const int qc = cb - tap * p.q_chunks;
-            for (int c = 0; c < 4; ++c) {
-                uint32_t v[16];
-                tmem_ld16(t_addr + i * 64 + c * 16, v);
-                tmem_ld_wait();
-                if (pidx < p.p_extent) {
-                    float* dst = p.out + tap * p.st + (long long)pidx * p.sp;
+        if (p.sq == 1) {
+            // q is the contiguous output axis: transpose each 32 x 32 block through shared memory so that one RED
+            // instruction covers 128 contiguous bytes of one output row (1 request instead of 32 scattered sectors)
+            float* tile = reinterpret_cast<float*>(smem_gen + (tmem_ptr_smem + 16 - smem_base)) + q * (32 * 33);
+            for (int i = 0; i < ncb; ++i) {
+                const int cb = cb0 + i;
+                const int tap = cb / p.q_chunks;
+                const int qc = cb - tap * p.q_chunks;
+                float* obase = p.out + (long long)p.tap_out[tap] * p.st + (long long)(p0 + q * 32) * p.sp + qc * 64;
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t v[32];
+                    tmem_ld32(t_addr + i * 64 + half * 32, v);
+                    tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int qi = qc * 64 + c * 16 + j;
-                        if (qi < p.q_extent) atomicAdd(dst + (long long)qi * p.sq, __uint_as_float(v[j]));
+                    for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = __uint_as_float(v[j]);
+                    __syncwarp();
+                    const int qi = qc * 64 + half * 32 + lane;
+                    if (qi < p.q_extent) {
+                        const int nrows = min(32, p.p_extent - (p0 + q * 32));
+                        for (int rr = 0; rr < nrows; ++rr)
+                            atomicAdd(obase + (long long)rr * p.sp + half * 32 + lane, tile[rr * 33 + lane]);
+                    }
+                    __syncwarp();
+                }
+            }
+        } else {
+            for (int i = 0; i < ncb; ++i) {
+                const int cb = cb0 + i;
+                const int tap = cb / p.q_chunks;
+                const int qc = cb - tap * p.q_chunks;
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t v[16];
+                    tmem_ld16(t_addr + i * 64 + c * 16, v);
+                    tmem_ld_wait();
+                    if (pidx < p.p_extent) {
+                        float* dst = p.out + (long long)p.tap_out[tap] * p.st + (long long)pidx * p.sp;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int qi = qc * 64 + c * 16 + j;
+                            if (qi < p.q_extent) atomicAdd(dst + (long long)qi * p.sq, __uint_as_float(v[j]));
+                        }
                     }
                 }
             }

@@ -69,6 +69,7 @@ struct alignas(64) WgradParams {
     int ntaps;
     int q_map_of_tap[kMaxTaps];
     int tap_dw[kMaxTaps], tap_dh[kMaxTaps], tap_dd[kMaxTaps];
+    int tap_out[kMaxTaps];  // index of tap t along the output's tap axis (native or packed tap order)
     int p_extent, q_extent;
     int q_chunks;      // ceil(q_extent / 64)
     int n_colblocks;   // ntaps * q_chunks

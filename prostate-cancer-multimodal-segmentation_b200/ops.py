@@ -277,3 +277,31 @@ def fill_zero(v: ActView):
 def channel_sum(v: ActView, out):
     _launched(1)
     check(_lib.load().b200_channel_sum(v.ref, ptr(out), stream_ptr()), "channel_sum")
+
+
+# ---- optional timeline (dev tool): CUDA events around every op on whatever stream it runs, to inspect cross-stream
+# overlap without an external profiler.  `timeline = []` switches it on; entries are (name, stream, start, end).
+timeline = None
+
+
+def _traced(fn):
+    def wrapper(*a, **k):
+        if timeline is None:
+            return fn(*a, **k)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn(*a, **k)
+        e1.record()
+        timeline.append((fn.__name__, torch.cuda.current_stream().cuda_stream, e0, e1))
+        return r
+    wrapper.__name__ = fn.__name__
+    wrapper.__doc__ = fn.__doc__
+    return wrapper
+
+
+for _n in ("pack_input", "im2col_input", "pack_rows", "pack_conv_weight", "pack_convt_weight", "conv3d_fprop",
+           "conv1_fprop", "conv3d_dgrad", "conv3d_wgrad", "conv1_wgrad", "convt2x_fwd", "convt2x_dgrad",
+           "convt2x_wgrad", "bn_finalize", "bn_fold_eval", "bn_apply_relu", "bn_bwd", "maxpool3d_fwd",
+           "maxpool3d_bwd", "head_fwd", "head_bwd", "loss_fwd", "loss_bwd", "adam_step", "sumsq", "fill_zero",
+           "channel_sum"):
+    globals()[_n] = _traced(globals()[_n])
