@@ -39,7 +39,7 @@ SIGNATURES = {
     "b200_conv3d_stat_rows": (_i32, [_i64, _i64, _i64, _i64, _i64, _i32]),
     "b200_conv3d_fprop": (_i32, [_AP, _vp, _vp, _AP, _vp, _i32, _vp, _vp, _vp]),
     "b200_conv3d_dgrad": (_i32, [_AP, _vp, _AP, _vp]),
-    "b200_conv3d_wgrad": (_i32, [_AP, _AP, _vp, _i32, _vp]),
+    "b200_conv3d_wgrad": (_i32, [_AP, _AP, _vp, _i32, _i32, _vp]),
     "b200_convt2x_fwd": (_i32, [_AP, _vp, _vp, _AP, _i32, _i32, _i32, _vp]),
     "b200_convt2x_dgrad": (_i32, [_AP, _i32, _i32, _i32, _vp, _AP, _vp]),
     "b200_convt2x_wgrad": (_i32, [_AP, _AP, _i32, _i32, _i32, _vp, _vp]),
@@ -56,7 +56,8 @@ SIGNATURES = {
     "b200_head_bwd": (_i32, [_AP, _vp, _i32, _vp, _AP, _vp, _vp, _vp]),
     "b200_loss_fwd": (_i32, [_vp, _vp, _i64, _f32, _f32, _f32, _vp, _vp, _vp, _vp]),
     "b200_loss_bwd": (_i32, [_vp, _vp, _i64, _f32, _f32, _f32, _vp, _vp, _vp, _vp]),
-    "b200_adam_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _f64, _f64, _f64, _f64, _f64, _i64, _f64, _vp, _vp]),
+    "b200_adam_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _f64, _f64, _f64, _f64, _f64, _i64, _f64, _vp, _vp, _vp]),
+    "b200_cast_bf16": (_i32, [_vp, _i64, _vp, _vp]),
     "b200_sumsq": (_i32, [_vp, _i64, _vp, _vp]),
     "b200_fill_zero": (_i32, [_AP, _vp]),
     "b200_channel_sum": (_i32, [_AP, _vp, _vp]),

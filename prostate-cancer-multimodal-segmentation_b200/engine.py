@@ -25,30 +25,66 @@ def _pad16(c: int) -> int:
     return (c + 15) // 16 * 16
 
 
-class _ConvPack:
-    """bf16 operand shadows of one Conv3d 3x3x3.
+def _is_conv3(p) -> bool:
+    """3x3x3 conv weight that the engine stores physically as [27][Cout][Cin] (packed tap order kd, kw, kh)"""
+    return p.dim() == 5 and tuple(p.shape[2:]) == (3, 3, 3) and p.shape[1] % 16 == 0
 
-    Thin inputs (Cin not a multiple of 16, i.e. the 5-modality first layer) use the im2col form: the input is
-    expanded to rows of pad16(27*Cin) columns and the conv runs as a 1-tap GEMM on the flattened weights."""
+
+def _phys_strides(cout: int, cin: int):
+    cc = cout * cin
+    return (cin, 1, 9 * cc, cc, 3 * cc)  # logical (cout, cin, kd, kh, kw) over physical (kd, kw, kh, cout, cin)
+
+
+def _slot_view(flat: torch.Tensor, off: int, p) -> torch.Tensor:
+    """logical-shape view of flat[off : off + numel] for parameter p (permuted for physically packed conv weights)"""
+    n = p.numel()
+    if _is_conv3(p):
+        cout, cin = p.shape[0], p.shape[1]
+        return flat[off:off + n].view(3, 3, 3, cout, cin).permute(3, 4, 0, 2, 1)
+    return flat[off:off + n].view(p.shape)
+
+
+class _ConvPack:
+    """bf16 operand of one Conv3d 3x3x3.
+
+    * Engine-managed weights live physically as fp32 [27][Cout][Cin]; their bf16 operand is a slice of the engine's
+      bf16 shadow of the flat parameter buffer (written by the fused Adam, or by one cast kernel) — no packing kernel,
+      and the weight gradient accumulates into the same contiguous layout (coalesced).
+    * Stand-alone (torch-layout) weights are packed by b200_pack_conv_weight into a private buffer.
+    * Thin inputs (Cin not a multiple of 16, i.e. the 5-modality first layer) use the im2col form: the input is
+      expanded to rows of pad16(27*Cin) columns and the conv runs as a 1-tap GEMM on the flattened weights."""
 
     def __init__(self, conv, device):
         self.conv = conv
+        self.device = device
         self.cout, self.cin = conv.out_channels, conv.in_channels
         self.im2col = self.cin % 16 != 0 and 27 * self.cin <= 512
+        self.shadow = None   # set by the engine: bf16 [27][Cout][Cin] view of its parameter shadow
+        self._own = None
         if self.im2col:
             self.k_real = 27 * self.cin
             self.cin_pad = _pad16(self.k_real)  # width of the im2col rows
-            self.wf = torch.empty(self.cout, self.cin_pad, device=device, dtype=torch.bfloat16)
+            self._own = torch.empty(self.cout, self.cin_pad, device=device, dtype=torch.bfloat16)
         else:
             self.k_real = self.cin
             self.cin_pad = _pad16(self.cin)
-            self.wf = torch.empty(27, self.cout, self.cin_pad, device=device, dtype=torch.bfloat16)
+
+    def _phys(self, t) -> bool:
+        return (not self.im2col) and self.shadow is not None and t.stride() == _phys_strides(self.cout, self.cin)
+
+    @property
+    def wf(self):
+        if self._phys(self.conv.weight.data):
+            return self.shadow
+        if self._own is None:
+            self._own = torch.empty(27, self.cout, self.cin_pad, device=self.device, dtype=torch.bfloat16)
+        return self._own
 
     def pack(self):
         if self.im2col:
-            ops.pack_rows(self.conv.weight.data, self.cin_pad, self.wf)
-        else:
-            ops.pack_conv_weight(self.conv.weight.data, self.cin_pad, self.wf)
+            ops.pack_rows(self.conv.weight.data, self.cin_pad, self._own)
+        elif not self._phys(self.conv.weight.data):
+            ops.pack_conv_weight(self.conv.weight.data.contiguous(), self.cin_pad, self.wf)
 
     def make_input(self, x: torch.Tensor) -> ActView:
         """fp32 (N,C,D,H,W) -> the bf16 operand this conv reads (channel-padded NDHWC, or im2col rows)"""
@@ -64,8 +100,12 @@ class _ConvPack:
     def wgrad(self, xin, dy, dw):
         if self.im2col:
             ops.conv1_wgrad(xin, dy, dw.view(self.cout, -1), self.k_real)
+        elif dw.stride() == _phys_strides(self.cout, self.cin):
+            ops.conv3d_wgrad(xin, dy, dw, self.cin, packed=True)
+        elif dw.is_contiguous():
+            ops.conv3d_wgrad(xin, dy, dw, self.cin, packed=False)
         else:
-            ops.conv3d_wgrad(xin, dy, dw, self.cin)
+            raise B200Error("conv weight gradient buffer has an unsupported memory layout")
 
     def dgrad(self, dy, dx):
         if self.im2col:
@@ -232,6 +272,8 @@ class Engine:
         self.overlap_wgrad = True  # weight gradients on a side stream (see _Side)
         self.flat_param = None
         self.flat_grad = None
+        self.flat_bf16 = None    # bf16 shadow of flat_param: the conv kernels' weight operand
+        self._shadow_key = None
         self._slots = None       # id(param) -> (offset, numel)
 
     # ------------------------------------------------------------------ parameters
@@ -261,32 +303,47 @@ class Engine:
         base = self.flat_param.data_ptr()
         for _, p in self.ordered_params():
             off, n = self._slots[id(p)]
-            if p.data.data_ptr() != base + 4 * off or p.data.numel() != n or p.data.dtype != torch.float32:
+            d = p.data
+            if d.data_ptr() != base + 4 * off or d.numel() != n or d.dtype != torch.float32:
+                return False
+            if _is_conv3(p) and d.stride() != _phys_strides(p.shape[0], p.shape[1]):
                 return False
         return True
 
     def flatten(self, device):
-        """re-home every parameter into one flat fp32 buffer (values preserved) and allocate the flat gradient"""
+        """Re-home every parameter into one flat fp32 buffer (values preserved), allocate the flat gradient and the
+        bf16 operand shadow.  3x3x3 conv weights are stored physically as [27][Cout][Cin]; `Parameter.data` is the
+        permuted (Cout, Cin, 3, 3, 3) view, so state_dict / load_state_dict / any optimizer see torch's shape."""
         params = self.ordered_params()
         slots, off = {}, 0
         for _, p in params:
             slots[id(p)] = (off, p.numel())
-            off += (p.numel() + 3) // 4 * 4
+            off += (p.numel() + 7) // 8 * 8
         flat = torch.zeros(off, device=device, dtype=torch.float32)
         for _, p in params:
-            o, n = slots[id(p)]
-            view = flat[o:o + n].view(p.shape)
+            o, _n = slots[id(p)]
+            view = _slot_view(flat, o, p)
             view.copy_(p.data)
             p.data = view
             p.grad = None
         self._slots = slots
         self.flat_param = flat
         self.flat_grad = torch.zeros(off, device=device, dtype=torch.float32)
+        self.flat_bf16 = torch.empty(off, device=device, dtype=torch.bfloat16)
         self._pack_key = None
+        self._shadow_key = None
+        for dc in [self.inc] + self.downs + [d for _, d in self.ups]:
+            for pk in (dc.p1, dc.p2):
+                if not pk.im2col:
+                    o, n = slots[id(pk.conv.weight)]
+                    pk.shadow = self.flat_bf16[o:o + n].view(27, pk.cout, pk.cin)
 
     def grad_view(self, p):
-        o, n = self._slots[id(p)]
-        return self.flat_grad[o:o + n].view(p.shape)
+        o, _n = self._slots[id(p)]
+        return _slot_view(self.flat_grad, o, p)
+
+    def current_key(self):
+        return (self.external_epoch, self.flat_param.data_ptr(), tuple(p._version for _, p in self.ordered_params()))
 
     def _build(self, device):
         m = self.model
@@ -307,9 +364,11 @@ class Engine:
             self._build(device)
         if not self._is_flat():
             self.flatten(device)
-        key = (self.external_epoch, self.flat_param.data_ptr(),
-               tuple(p._version for _, p in self.ordered_params()))
+        key = self.current_key()
         if key != self._pack_key:
+            if key != self._shadow_key:  # the fused Adam refreshes the shadow itself
+                ops.cast_bf16(self.flat_param, self.flat_bf16)
+                self._shadow_key = key
             self.inc.pack()
             for d in self.downs:
                 d.pack()

@@ -156,10 +156,12 @@ def conv3d_dgrad(dy: ActView, w_packed, dx: ActView):
           lambda: check(lib.b200_conv3d_dgrad(dy.ref, ptr(w_packed), dx.ref, stream_ptr()), "conv3d_dgrad"))
 
 
-def conv3d_wgrad(x: ActView, dy: ActView, dw: torch.Tensor, cin_real: int):
+def conv3d_wgrad(x: ActView, dy: ActView, dw: torch.Tensor, cin_real: int, packed: bool = False):
+    """dw (+=): torch's (Cout, Cin, 3, 3, 3), or with packed=True the engine's physical [27][Cout][Cin] buffer"""
     lib = _lib.load()
     _gemm("wgrad_kernel", "conv3d_wgrad", 2.0 * x.voxels * dy.c * cin_real * 27,
-          lambda: check(lib.b200_conv3d_wgrad(x.ref, dy.ref, ptr(dw), cin_real, stream_ptr()), "conv3d_wgrad"))
+          lambda: check(lib.b200_conv3d_wgrad(x.ref, dy.ref, ptr(dw), cin_real, 1 if packed else 0, stream_ptr()),
+                        "conv3d_wgrad"))
 
 
 def convt2x_fwd(x: ActView, w_fwd, bias8, y: ActView, pads=(0, 0, 0)):
@@ -257,11 +259,16 @@ def loss_bwd(logits, target, bce_w, dice_w, smooth, sums, gout, dlogits):
 
 
 def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0,
-              found_inf=None):
+              found_inf=None, bf16_shadow=None):
     _launched(1)
     check(_lib.load().b200_adam_step(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), lr, beta1,
-                                     beta2, eps, weight_decay, step, grad_scale, ptr(found_inf), stream_ptr()),
-          "adam_step")
+                                     beta2, eps, weight_decay, step, grad_scale, ptr(found_inf), ptr(bf16_shadow),
+                                     stream_ptr()), "adam_step")
+
+
+def cast_bf16(x, out):
+    _launched(1)
+    check(_lib.load().b200_cast_bf16(ptr(x), x.numel(), ptr(out), stream_ptr()), "cast_bf16")
 
 
 def sumsq(x, out):
@@ -302,6 +309,6 @@ def _traced(fn):
 for _n in ("pack_input", "im2col_input", "pack_rows", "pack_conv_weight", "pack_convt_weight", "conv3d_fprop",
            "conv1_fprop", "conv3d_dgrad", "conv3d_wgrad", "conv1_wgrad", "convt2x_fwd", "convt2x_dgrad",
            "convt2x_wgrad", "bn_finalize", "bn_fold_eval", "bn_apply_relu", "bn_bwd", "maxpool3d_fwd",
-           "maxpool3d_bwd", "head_fwd", "head_bwd", "loss_fwd", "loss_bwd", "adam_step", "sumsq", "fill_zero",
-           "channel_sum"):
+           "maxpool3d_bwd", "head_fwd", "head_bwd", "loss_fwd", "loss_bwd", "adam_step", "cast_bf16", "sumsq",
+           "fill_zero", "channel_sum"):
     globals()[_n] = _traced(globals()[_n])

@@ -45,8 +45,10 @@ class FusedAdam(torch.optim.Optimizer):
         g = self.param_groups[0]
         self._step += 1
         ops.adam_step(eng.flat_param, eng.flat_grad, self.exp_avg, self.exp_avg_sq, g["lr"], g["betas"][0],
-                      g["betas"][1], g["eps"], g["weight_decay"], self._step, self.grad_scale, self.found_inf)
+                      g["betas"][1], g["eps"], g["weight_decay"], self._step, self.grad_scale, self.found_inf,
+                      bf16_shadow=eng.flat_bf16)
         eng.external_epoch += 1
+        eng._shadow_key = eng.current_key()  # the bf16 operand shadow was rewritten in the same pass
         return loss
 
     def zero_grad(self, set_to_none: bool = True):

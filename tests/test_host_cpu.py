@@ -134,3 +134,31 @@ def test_oracle_dp_semantics_small():
         assert torch.allclose(g1[k], g2[k], rtol=1e-4, atol=1e-7), k
     for k in sd_a:
         assert torch.allclose(sd_a[k].float(), sd_b[k].float(), rtol=1e-4, atol=1e-6), k
+
+
+def test_physical_weight_layout_views(pkg):
+    """conv weights live as [27][Cout][Cin] (packed tap order kd, kw, kh); Parameter.data is the permuted torch-shaped
+    view, so state_dict / load_state_dict / optimizers are unaffected"""
+    import importlib
+    eng = importlib.import_module(pkg.__name__ + ".engine")
+    w = torch.randn(32, 16, 3, 3, 3)
+    p = torch.nn.Parameter(w.clone())
+    flat = torch.zeros(8 + w.numel())
+    view = eng._slot_view(flat, 8, p)
+    assert view.shape == w.shape and view.stride() == eng._phys_strides(32, 16)
+    view.copy_(w)
+    phys = flat[8:].view(27, 32, 16)
+    native = [(t // 9) * 9 + (t % 3) * 3 + (t // 3) % 3 for t in range(27)]
+    assert torch.equal(phys, w.reshape(32, 16, 27).permute(2, 0, 1)[native])
+    assert torch.equal(view, w) and torch.equal(view.contiguous(), w)
+    # non-conv3 parameters keep their natural layout; the 5-modality first conv is not a packed conv
+    b = torch.nn.Parameter(torch.randn(7))
+    assert eng._slot_view(flat, 0, b).is_contiguous()
+    assert not eng._is_conv3(torch.nn.Parameter(torch.randn(64, 5, 3, 3, 3)))
+    assert not eng._is_conv3(torch.nn.Parameter(torch.randn(1, 64, 1, 1, 1)))
+    # a state_dict made of such views round-trips through torch.save / load_state_dict
+    import io
+    buf = io.BytesIO()
+    torch.save({"w": view}, buf)
+    buf.seek(0)
+    assert torch.equal(torch.load(buf)["w"], w)

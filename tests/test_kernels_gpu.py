@@ -122,6 +122,13 @@ def test_conv3d_wgrad(ops, cuda_dev, case):
     ops.conv3d_wgrad(to_act(ops, x), to_act(ops, dy), dw, cin_real)
     torch.cuda.synchronize()
     assert rel_l2(dw, 2 * ref) < 2e-3
+    if cin == cin_real:
+        # the engine's physical layout: [27][Cout][Cin] in packed tap order, accumulated with coalesced REDs
+        dwp = torch.zeros(27, cout, cin, device=cuda_dev)
+        ops.conv3d_wgrad(to_act(ops, x), to_act(ops, dy), dwp, cin_real, packed=True)
+        torch.cuda.synchronize()
+        native = [(t // 9) * 9 + (t % 3) * 3 + (t // 3) % 3 for t in range(27)]
+        assert rel_l2(dwp, ref.reshape(cout, cin, 27).permute(2, 0, 1)[native]) < 2e-3
 
 
 CONVT_CASES = [
