@@ -318,7 +318,7 @@ class Engine:
         slots, off = {}, 0
         for _, p in params:
             slots[id(p)] = (off, p.numel())
-            off += (p.numel() + 7) // 8 * 8
+            off += (p.numel() + 63) // 64 * 64   # 128-byte aligned bf16 shadow slices (TMA rows must not straddle lines)
         flat = torch.zeros(off, device=device, dtype=torch.float32)
         for _, p in params:
             o, _n = slots[id(p)]

@@ -75,7 +75,7 @@ def test_bucket_plan_and_batch_sharding(pkg):
     slots, off = {}, 0
     for _, p in eng.ordered_params():
         slots[id(p)] = (off, p.numel())
-        off += (p.numel() + 3) // 4 * 4
+        off += (p.numel() + 63) // 64 * 64
     plan = par.plan_buckets(off, sorted({o + n for o, n in slots.values()}), int(25 * 2 ** 20 / 4))
     assert 8 <= len(plan) <= 16 and plan[-1][1] == off
 
