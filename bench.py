@@ -362,8 +362,14 @@ def main():
                     "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1)} for k, v in agg.items()}
         a = agg[top]
         achieved = a["flops"] / (a["ms"] * 1e-3) / 1e12
+        # DRAM bytes of one captured launch of the dominant kernel (committed ncu --set full summary), if present
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(top)
+        except Exception:
+            pass
         roofline = {"bound": "tensor", "kernel": top, "achieved": round(achieved, 2), "peak": peak,
-                    "unit": "TFLOP/s", "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                    "unit": "TFLOP/s", "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                     "avg_launch_ms": round(a["ms"] / a["launches"], 4),
                     "algorithmic_flops_per_launch": a["flops"] / a["launches"],
                     "gemm_share_of_step": round(sum(v["ms"] for v in agg.values()) / ms_step, 3),

@@ -423,7 +423,31 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(View dout, View y, c
         ldf8(shift + cv * 8, sh);
         ldf8(mean + cv * 8, mu);
         ldf8(rstd + cv * 8, rs);
-        for (long long v = (long long)blockIdx.x * rows + row; v < nvox; v += (long long)gridDim.x * rows) {
+        const long long step = (long long)gridDim.x * rows;
+        long long v = (long long)blockIdx.x * rows + row;
+        // two voxels per iteration: four 16-byte loads in flight per thread (these kernels often share the SM with a
+        // persistent GEMM CTA and then run at low occupancy)
+        for (; v + step < nvox; v += 2 * step) {
+            const Bf8 g0 = ld8_stream(dout.p + v * dout.ld + cv * 8), x0 = ld8_stream(y.p + v * y.ld + cv * 8);
+            const Bf8 g1 = ld8_stream(dout.p + (v + step) * dout.ld + cv * 8);
+            const Bf8 x1 = ld8_stream(y.p + (v + step) * y.ld + cv * 8);
+            float g[8], x[8];
+            unpack8(g0, g); unpack8(x0, x);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float gm = fmaf(x[j], sc[j], sh[j]) > 0.f ? g[j] : 0.f;
+                acc[0][j] += gm;
+                acc[1][j] += gm * ((x[j] - mu[j]) * rs[j]);
+            }
+            unpack8(g1, g); unpack8(x1, x);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float gm = fmaf(x[j], sc[j], sh[j]) > 0.f ? g[j] : 0.f;
+                acc[0][j] += gm;
+                acc[1][j] += gm * ((x[j] - mu[j]) * rs[j]);
+            }
+        }
+        for (; v < nvox; v += step) {
             float g[8], x[8];
             unpack8(ld8_stream(dout.p + v * dout.ld + cv * 8), g);
             unpack8(ld8_stream(y.p + v * y.ld + cv * 8), x);
@@ -496,10 +520,11 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(View dout, View y, co
             k0[0] = t[0]; k1[0] = t[1]; k0[1] = t[2]; k1[1] = t[3]; k0[2] = t[4]; k1[2] = t[5]; k0[3] = t[6]; k1[3] = t[7];
             k0[4] = u[0]; k1[4] = u[1]; k0[5] = u[2]; k1[5] = u[3]; k0[6] = u[4]; k1[6] = u[5]; k0[7] = u[6]; k1[7] = u[7];
         }
-        for (long long v = (long long)blockIdx.x * rows + row; v < nvox; v += (long long)gridDim.x * rows) {
+        const long long step = (long long)gridDim.x * rows;
+        auto one = [&](long long v, const Bf8& gb, const Bf8& xb) {
             float g[8], x[8], o[8];
-            unpack8(ld8_stream(dout.p + v * dout.ld + cv * 8), g);
-            unpack8(ld8_stream(y.p + v * y.ld + cv * 8), x);
+            unpack8(gb, g);
+            unpack8(xb, x);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const float gm = fmaf(x[j], sc[j], sh[j]) > 0.f ? g[j] : 0.f;
@@ -512,7 +537,17 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(View dout, View y, co
             unpack8(ob, r);
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[0][j] += r[j];
+        };
+        long long v = (long long)blockIdx.x * rows + row;
+        for (; v + step < nvox; v += 2 * step) {  // two voxels per iteration: four loads in flight
+            const Bf8 g0 = ld8_stream(dout.p + v * dout.ld + cv * 8), x0 = ld8_stream(y.p + v * y.ld + cv * 8);
+            const Bf8 g1 = ld8_stream(dout.p + (v + step) * dout.ld + cv * 8);
+            const Bf8 x1 = ld8_stream(y.p + (v + step) * y.ld + cv * 8);
+            one(v, g0, x0);
+            one(v + step, g1, x1);
         }
+        for (; v < nvox; v += step)
+            one(v, ld8_stream(dout.p + v * dout.ld + cv * 8), ld8_stream(y.p + v * y.ld + cv * 8));
     }
     if (dbias) block_reduce_store<1>(acc, c8, rows, row, cv, active, smem, dbias, (int)y.c, true);
 }
