@@ -164,6 +164,10 @@ int b200_channel_sum(const b200_act* v, float* out, void* stream);
 /* NDHWC bf16 view -> (N,C,D,H,W) fp32 (debug / per-layer parity taps) */
 int b200_unpack_act(const b200_act* v, float* out_ncdhw, void* stream);
 
+/* dev probe (not on the hot path): cycles for `iters` x 4 tcgen05.mma (M=128, N=n, K=16, SS mode) per CTA, operands
+ * cycling through `stages` shared-memory slots; out_cycles[blocks] (int64) */
+int b200_probe_mma(int n, int iters, int stages, long long* out_cycles, int blocks, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -62,6 +62,7 @@ SIGNATURES = {
     "b200_fill_zero": (_i32, [_AP, _vp]),
     "b200_channel_sum": (_i32, [_AP, _vp, _vp]),
     "b200_unpack_act": (_i32, [_AP, _vp, _vp]),
+    "b200_probe_mma": (_i32, [_i32, _i32, _i32, _vp, _i32, _vp]),
 }
 
 _lib = None
