@@ -16,6 +16,7 @@
 namespace b200 {
 extern "C" __global__ void igemm_kernel(const __grid_constant__ IgemmParams p);
 extern "C" __global__ void wgrad_kernel(const __grid_constant__ WgradParams p);
+extern "C" __global__ void dmarch_kernel(const __grid_constant__ DmarchParams p);
 }  // namespace b200
 
 using namespace b200;
@@ -193,6 +194,34 @@ static bool conv_geometry(long long n, long long w, long long h, long long d, lo
     }
     return halo;
 }
+// depth-marching path (dmarch.cu): 3x3x3 conv with exactly 64 output columns on 8 x 16 bricks
+struct DmPlan {
+    bool use;
+    int nbw, nbh, seg_len, nseg, grid;
+};
+static DmPlan dmarch_plan(long long n, long long w, long long h, long long d, long long ncols, int ntaps) {
+    DmPlan pl{};
+    const int sms = sm_count();
+    pl.use = ntaps == 27 && ncols == 64 && w >= 8 && h >= 16 && sms > 0;
+    if (!pl.use) return pl;
+    pl.nbw = (int)((w + 7) / 8);
+    pl.nbh = (int)((h + 15) / 16);
+    const long long columns = n * pl.nbw * pl.nbh;
+    long long nseg = (4LL * sms + columns - 1) / columns;       // about four waves of work units
+    const long long max_seg = d >= 8 ? d / 4 : 1;               // segments of at least 4 slices
+    if (nseg > max_seg) nseg = max_seg;
+    if (nseg < 1) nseg = 1;
+    pl.seg_len = (int)((d + nseg - 1) / nseg);
+    pl.nseg = (int)((d + pl.seg_len - 1) / pl.seg_len);
+    const long long units = columns * pl.nseg;
+    pl.grid = (int)(units < sms ? units : sms);
+    return pl;
+}
+constexpr int kDmSmem = 1024 + kDmAStages * kDmABytes + kDmBStages * kDmBBytes + kBoxBytes +
+                        8 * (2 * kDmAStages + 2 * kDmBStages + 2 * kDmSlots) + 64 + (4 * 64 * 2 + 128 + 128) * 4;
+static int launch_dmarch(const b200_act* in, const void* w_packed, const b200_act* out, int sign, int mode,
+                         const float* v0, const float* v1, float* stats, const DmPlan& pl, cudaStream_t s);
+
 static void set_plain_stage(IgemmParams& p) {
     p.group = 1;
     p.a_stage_bytes = kBoxBytes;
@@ -248,6 +277,10 @@ static int conv3_igemm(const b200_act* in, const void* w_packed, const b200_act*
     REQUIRE(out->c % 16 == 0, "conv3d: output channels (%lld) must be a multiple of 16", (long long)out->c);
     REQUIRE(in->c % 16 == 0, "conv3d: input channels (%lld) must be a multiple of 16", (long long)in->c);
     REQUIRE(in->n * in->d * in->h * in->w < (1LL << 31), "conv3d: too many voxels");
+    {
+        const DmPlan pl = dmarch_plan(in->n, in->w, in->h, in->d, out->c, ntaps);
+        if (pl.use) return launch_dmarch(in, w_packed, out, sign, mode, v0, v1, stats, pl, s);
+    }
     IgemmParams p;
     memset(&p, 0, sizeof(p));
     // h-halo mode: worth it when the MMA per tap is short (narrow N) and the volume holds 8 x 16 bricks
@@ -306,9 +339,49 @@ static int conv3_igemm(const b200_act* in, const void* w_packed, const b200_act*
     return launch_igemm(p, s, nullptr);
 }
 
+static int launch_dmarch(const b200_act* in, const void* w_packed, const b200_act* out, int sign, int mode,
+                         const float* v0, const float* v1, float* stats, const DmPlan& pl, cudaStream_t s) {
+    DmarchParams p;
+    memset(&p, 0, sizeof(p));
+    int rc = make_act_map(&p.a_map, reinterpret_cast<const __nv_bfloat16*>(in->ptr), in->c, in->w, in->h, in->d,
+                          in->n, in->ld, in->w, in->h, in->d, 1, 8, 18, 1);
+    if (rc) return rc;
+    p.b_mn = sign < 0 ? 1 : 0;
+    if (p.b_mn)  // [tap][Cout rows = K][Cin = N contiguous]: 64 x 64 boxes
+        rc = make_weight_map(&p.b_map, w_packed, out->c, in->c, 27, 64, 1);
+    else         // [tap][Cout rows = N][Cin = K contiguous]
+        rc = make_weight_map(&p.b_map, w_packed, in->c, out->c, 27, 64, 1);
+    if (rc) return rc;
+    rc = make_act_map(&p.c_map, reinterpret_cast<const __nv_bfloat16*>(out->ptr), out->c, out->w, out->h, out->d,
+                      out->n, out->ld, out->w, out->h, out->d, 1, 8, 16, 1);
+    if (rc) return rc;
+    p.sign = sign;
+    p.cin = (int)in->c;
+    p.kc_blocks = (int)((in->c + 63) / 64);
+    p.W = (int)in->w; p.H = (int)in->h; p.D = (int)in->d; p.nbatch = (int)in->n;
+    p.nbw = pl.nbw; p.nbh = pl.nbh; p.seg_len = pl.seg_len; p.nseg = pl.nseg;
+    p.mode = mode;
+    p.vec0 = v0; p.vec1 = v1; p.stats = stats;
+    static bool attr = false;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (!attr) {
+            CUDA_TRY(cudaFuncSetAttribute(dmarch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDmSmem));
+            attr = true;
+        }
+    }
+    dmarch_kernel<<<pl.grid, kThreads, kDmSmem, s>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int b200_conv3d_stat_rows(int64_t n, int64_t d, int64_t h, int64_t w, int64_t cout, int ntaps) {
     const int sms = sm_count();
     if (sms <= 0) return -1;
+    {
+        const DmPlan pl = dmarch_plan(n, w, h, d, cout, ntaps);
+        if (pl.use) return pl.grid;
+    }
     int bn = 0;
     Brick b;
     conv_geometry(n, w, h, d, cout, ntaps, &b, &bn);

@@ -61,6 +61,34 @@ struct alignas(64) IgemmParams {
     int out_od[kMaxMaps], out_oh[kMaxMaps], out_ow[kMaxMaps];
 };
 
+// Depth-marching implicit GEMM for 3x3x3 convolutions with 64 output columns (fprop with Cout = 64, dgrad with Cin = 64).
+// A tcgen05.mma in SS mode costs max(N/2, ~42 + 0.18 N) cycles (tools/probe_mma.py): N = 64 cannot exceed 60 % of the
+// tensor pipe, N = 192 reaches 99.9 %.  So the three kd taps are concatenated along N: for input slice dz the MMA
+// D[128 voxels x 192] = A(dz, kh, kw) . [W(kd=a) | W(kd=b) | W(kd=c)] adds into the accumulators of the three output
+// slices dz-1, dz, dz+1, which live side by side in a ring of eight 64-column TMEM slots.  A CTA owns a (w,h) brick
+// column and marches along d; an output slice is complete one input slice later and is drained by the epilogue warps
+// while the MMAs go on.
+constexpr int kDmSlots = 8;      // TMEM ring: 8 x 64 columns
+constexpr int kDmAStages = 3;    // A ring: h-halo boxes of 18 KB
+constexpr int kDmBStages = 6;    // B ring: [3 slabs][64 rows][128 B] = 24 KB
+constexpr int kDmABytes = 18 * 8 * 128;
+constexpr int kDmBBytes = 3 * 8192;
+struct alignas(64) DmarchParams {
+    CUtensorMap a_map;   // box (64 ch, 8 w, 18 h, 1, 1)
+    CUtensorMap b_map;   // K-major: (k, rows, taps) box (64, 64, 1);  MN-major: (n, k rows, taps) box (64, 64, 1)
+    CUtensorMap c_map;   // output store, box (64 ch, 8 w, 16 h, 1, 1)
+    int b_mn;            // 1: dgrad (B read MN-major from the fprop-packed weights)
+    int sign;            // +1 fprop, -1 dgrad (tap shifts negated)
+    int cin;             // K extent per tap
+    int kc_blocks;
+    int W, H, D, nbatch, nbw, nbh;
+    int seg_len, nseg;   // output slices per work unit, segments per column
+    int mode;
+    const float* vec0;
+    const float* vec1;
+    float* stats;        // [gridDim.x][64][2]
+};
+
 // Weight-gradient GEMM  G[tap][p][q] += sum_{voxel} P[voxel][p] * Q_tap[voxel][q]
 // Both operands are voxel-major in memory (channel contiguous), i.e. MN-major UMMA operands.
 struct alignas(64) WgradParams {

@@ -37,6 +37,10 @@ CONV_CASES = [
     (1, 64, 64, 64, 3, 20, 12),      # h-halo mode (w >= 8, h >= 16) with partial bricks in w and h
     (2, 128, 128, 128, 2, 32, 16),   # h-halo mode, N = 128, two K blocks
     (1, 256, 256, 32, 3, 6, 5),      # wgrad with swapped roles (Cout <= 64 < Cin)
+    (2, 64, 64, 64, 21, 16, 8),      # depth-marching kernel: several depth segments, TMEM ring wraps
+    (1, 128, 128, 64, 9, 36, 20),    # depth-marching, two K blocks, partial bricks
+    (1, 64, 64, 128, 7, 16, 16),     # dgrad through the depth-marching kernel (dx has 64 channels, K = 128)
+    (1, 96, 96, 64, 1, 16, 8),       # depth-marching with a single slice and a K tail
 ]
 
 
@@ -72,7 +76,7 @@ def test_conv3d_fprop_bias_stats(ops, cuda_dev, case):
 
 def test_conv3d_fprop_affine_relu_and_views(ops, cuda_dev):
     """eval-mode epilogue; input and output are channel halves of wider (concat) buffers."""
-    n, cin, cout, d, h, w = 1, 64, 64, 8, 8, 8
+    n, cin, cout, d, h, w = 1, 64, 64, 6, 16, 8   # 64 output channels on 8x16 bricks: depth-marching kernel
     x, wt, _ = _conv_inputs(cuda_dev, n, cin, cout, d, h, w, seed=3)
     wf = torch.empty(27, cout, cin, device=cuda_dev, dtype=torch.bfloat16)
     ops.pack_conv_weight(wt.contiguous(), cin, wf)
