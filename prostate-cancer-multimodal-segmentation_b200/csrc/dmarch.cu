@@ -124,13 +124,18 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) dmarch_kernel(const __
         }
     } else if (warp == 1) {
         // ===================================================================== MMA issuer
+        // The issuing lane must stay lean (a dependent chain of uniform-datapath instructions per MMA is what bounds a
+        // short-N pipeline): descriptors are 32-bit low words + a constant high word, the per-slice plan (which TMEM
+        // columns, which B slabs, which instruction descriptor) is computed once per input slice.
         Ring ra, rb;
         const uint64_t a_desc0 = make_smem_desc_sw128(smem_a, 0, 1024);
         const uint64_t b_desc0 = make_smem_desc_sw128(smem_b, p.b_mn ? 8192 : 0, 1024);
+        const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), b_hi = (uint32_t)(b_desc0 >> 32);
+        const uint32_t a_lo0 = (uint32_t)a_desc0, b_lo0 = (uint32_t)b_desc0;
         const uint32_t kinc_b = p.b_mn ? 128u : 2u;
-        const uint32_t idesc64 = make_idesc_bf16(128, 64, 0, p.b_mn ? 1u : 0u);
-        const uint32_t idesc128 = make_idesc_bf16(128, 128, 0, p.b_mn ? 1u : 0u);
-        const uint32_t idesc192 = make_idesc_bf16(128, 192, 0, p.b_mn ? 1u : 0u);
+        const uint32_t bmaj = p.b_mn ? 1u : 0u;
+        const uint32_t idesc0 = make_idesc_bf16(128, 0, 0, bmaj);   // N field added per run: (64 * slabs) >> 3 at bit 17
+        const uint32_t idesc64 = idesc0 | (8u << 17);
         const int nk_last = ((p.cin - (kc_blocks - 1) * 64) + 15) >> 4;
         uint32_t ubase = 0;  // TMEM-slot use index of output slice ds of the current unit
         for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
@@ -141,26 +146,31 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) dmarch_kernel(const __
             for (int dz = z0; dz <= z1; ++dz) {
                 // slabs j (output slice d = dz - 1 + j) that belong to this unit
                 const int jlo = max(0, ds - (dz - 1)), jhi = min(2, (de - 1) - (dz - 1));
-                uint32_t slot[3];
-                bool fresh[3];
+                uint32_t tm[3], acc0[3];
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
                     const int d = dz - 1 + j;
                     const uint32_t u = ubase + (uint32_t)(d - ds);
-                    slot[j] = u % kDmSlots;
-                    fresh[j] = (j >= jlo && j <= jhi) && (dz == max(d - 1, 0));
-                    if (fresh[j]) {  // first write of this use: the epilogue must have drained the previous one
-                        mbar_wait(tempty(slot[j]), ((u / kDmSlots) & 1) ^ 1);
-                    }
+                    const uint32_t sl = u % kDmSlots;
+                    tm[j] = tmem_base + sl * 64;
+                    const bool fresh = (j >= jlo && j <= jhi) && (dz == max(d - 1, 0));
+                    acc0[j] = fresh ? 0u : 1u;
+                    if (fresh) mbar_wait(tempty(sl), ((u / kDmSlots) & 1) ^ 1);  // previous use drained
                 }
                 tc_fence_after();
-                // contiguous runs of slabs for the regular k-steps (the ring may wrap inside the window)
-                int run_j[2] = {jlo, 0}, run_n[2] = {jhi - jlo + 1, 0};
-                for (int j = jlo; j < jhi; ++j) {
-                    if (slot[j + 1] != slot[j] + 1) {
-                        run_n[0] = j + 1 - jlo;
-                        run_j[1] = j + 1;
-                        run_n[1] = jhi - j;
+                // regular k-steps: one MMA over all slabs, or two when the ring wraps inside the window
+                const uint32_t tm_lo = jlo == 0 ? tm[0] : (jlo == 1 ? tm[1] : tm[2]);
+                uint32_t r_tm0 = tm_lo, r_bo0 = jlo * (8192u >> 4), r_id0 = idesc0 | ((uint32_t)(jhi - jlo + 1) << 20);
+                uint32_t r_tm1 = 0, r_bo1 = 0, r_id1 = 0;
+                bool two = false;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    if (j >= jlo && j < jhi && tm[j + 1] != tm[j] + 64) {
+                        two = true;
+                        r_id0 = idesc0 | ((uint32_t)(j + 1 - jlo) << 20);
+                        r_tm1 = tm[j + 1];
+                        r_bo1 = (j + 1) * (8192u >> 4);
+                        r_id1 = idesc0 | ((uint32_t)(jhi - j) << 20);
                     }
                 }
                 bool first = true;
@@ -168,36 +178,44 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) dmarch_kernel(const __
                     for (int kc = 0; kc < kc_blocks; ++kc) {
                         const int nk = (kc == kc_blocks - 1) ? nk_last : 4;
                         mbar_wait(afull(ra.stage), ra.phase);
-                        const uint64_t a_st = a_desc0 + ra.stage * (kDmABytes >> 4);
+                        const uint32_t a_st = a_lo0 + ra.stage * (kDmABytes >> 4);
                         for (int kh = 0; kh < 3; ++kh) {
                             mbar_wait(bfull(rb.stage), rb.phase);
                             tc_fence_after();
                             if (elect_one()) {
                                 // tap kh reads the halo box at row offset kh (fprop) or 2 - kh (dgrad): 8 rows = 1 KB
-                                const uint64_t a_desc = a_st + (uint32_t)((sign > 0 ? kh : 2 - kh) * (1024 >> 4));
-                                const uint64_t b_st = b_desc0 + rb.stage * (kDmBBytes >> 4);
-                                for (int k = 0; k < nk; ++k) {
-                                    if (first) {
-                                        // per-slab MMAs: slabs differ in their accumulate flag on their first write
-                                        for (int j = jlo; j <= jhi; ++j)
-                                            umma_f16(tmem_base + slot[j] * 64, a_desc + 2 * k,
-                                                     b_st + j * (8192 >> 4) + k * kinc_b, idesc64, fresh[j] ? 0u : 1u);
-                                        first = false;
-                                    } else {
+                                const uint32_t a_lo = a_st + (uint32_t)((sign > 0 ? kh : 2 - kh) * (1024 >> 4));
+                                const uint32_t b_lo = b_lo0 + rb.stage * (kDmBBytes >> 4);
+                                int k0 = 0;
+                                if (first) {
+                                    // first k-step of the slice: per-slab MMAs (a fresh slab must not accumulate)
 #pragma unroll
-                                        for (int r = 0; r < 2; ++r) {
-                                            if (run_n[r] > 0) {
-                                                const uint32_t idesc =
-                                                    run_n[r] == 3 ? idesc192 : (run_n[r] == 2 ? idesc128 : idesc64);
-                                                umma_f16(tmem_base + slot[run_j[r]] * 64, a_desc + 2 * k,
-                                                         b_st + run_j[r] * (8192 >> 4) + k * kinc_b, idesc, 1u);
-                                            }
+                                    for (int j = 0; j < 3; ++j)
+                                        if (j >= jlo && j <= jhi)
+                                            umma_f16_lohi(tm[j], a_lo, a_hi, b_lo + j * (8192u >> 4), b_hi, idesc64,
+                                                          acc0[j]);
+                                    k0 = 1;
+                                }
+                                if (!two) {
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k)
+                                        if (k >= k0 && k < nk)
+                                            umma_f16_lohi(r_tm0, a_lo + 2 * k, a_hi, b_lo + r_bo0 + k * kinc_b, b_hi,
+                                                          r_id0, 1u);
+                                } else {
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k)
+                                        if (k >= k0 && k < nk) {
+                                            umma_f16_lohi(r_tm0, a_lo + 2 * k, a_hi, b_lo + r_bo0 + k * kinc_b, b_hi,
+                                                          r_id0, 1u);
+                                            umma_f16_lohi(r_tm1, a_lo + 2 * k, a_hi, b_lo + r_bo1 + k * kinc_b, b_hi,
+                                                          r_id1, 1u);
                                         }
-                                    }
                                 }
                                 umma_commit(bempty(rb.stage));
                             }
                             __syncwarp();
+                            first = false;
                             rb.advance(kDmBStages);
                         }
                         if (elect_one()) umma_commit(aempty(ra.stage));
@@ -207,9 +225,13 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) dmarch_kernel(const __
                 }
                 // output slices whose last contribution was this input slice are complete
                 if (elect_one()) {
-                    for (int j = jlo; j <= jhi; ++j) {
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
                         const int d = dz - 1 + j;
-                        if (dz == min(d + 1, p.D - 1)) umma_commit(tfull(slot[j]));
+                        if (j >= jlo && j <= jhi && dz == min(d + 1, p.D - 1)) {
+                            const uint32_t u = ubase + (uint32_t)(d - ds);
+                            umma_commit(tfull(u % kDmSlots));
+                        }
                     }
                 }
                 __syncwarp();
