@@ -207,11 +207,18 @@ static DmPlan dmarch_plan(long long n, long long w, long long h, long long d, lo
     pl.nbw = (int)((w + 7) / 8);
     pl.nbh = (int)((h + 15) / 16);
     const long long columns = n * pl.nbw * pl.nbh;
-    long long nseg = (4LL * sms + columns - 1) / columns;       // about four waves of work units
+    // depth segments per column: minimise waves x (segment length + the two boundary slices, which cost ~1/3 each)
     const long long max_seg = d >= 8 ? d / 4 : 1;               // segments of at least 4 slices
-    if (nseg > max_seg) nseg = max_seg;
-    if (nseg < 1) nseg = 1;
-    pl.seg_len = (int)((d + nseg - 1) / nseg);
+    long long best_nseg = 1;
+    double best_cost = 1e30;
+    for (long long nseg = 1; nseg <= max_seg; ++nseg) {
+        const long long seg_len = (d + nseg - 1) / nseg;
+        const long long real_nseg = (d + seg_len - 1) / seg_len;
+        const long long waves = (columns * real_nseg + sms - 1) / sms;
+        const double cost = (double)waves * ((double)seg_len + 0.67);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best_nseg = nseg; }
+    }
+    pl.seg_len = (int)((d + best_nseg - 1) / best_nseg);
     pl.nseg = (int)((d + pl.seg_len - 1) / pl.seg_len);
     const long long units = columns * pl.nseg;
     pl.grid = (int)(units < sms ? units : sms);
