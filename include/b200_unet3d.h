@@ -167,6 +167,9 @@ int b200_unpack_act(const b200_act* v, float* out_ncdhw, void* stream);
 /* dev probe (not on the hot path): cycles for `iters` x 4 tcgen05.mma (M=128, N=n, K=16, SS mode) per CTA, operands
  * cycling through `stages` shared-memory slots; out_cycles[blocks] (int64) */
 int b200_probe_mma(int n, int iters, int stages, long long* out_cycles, int blocks, void* stream);
+/* same with UMMA M (64 or 128) and operand majorness (0: both K-major, 1: both MN-major) selectable */
+int b200_probe_mma2(int m, int n, int mn_major, int iters, int stages, long long* out_cycles, int blocks,
+                    void* stream);
 
 #ifdef __cplusplus
 }

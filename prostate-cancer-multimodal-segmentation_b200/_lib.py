@@ -63,6 +63,7 @@ SIGNATURES = {
     "b200_channel_sum": (_i32, [_AP, _vp, _vp]),
     "b200_unpack_act": (_i32, [_AP, _vp, _vp]),
     "b200_probe_mma": (_i32, [_i32, _i32, _i32, _vp, _i32, _vp]),
+    "b200_probe_mma2": (_i32, [_i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
 }
 
 _lib = None

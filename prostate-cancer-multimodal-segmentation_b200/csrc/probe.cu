@@ -7,7 +7,8 @@
 
 namespace b200 {
 
-__global__ void __launch_bounds__(128, 1) mma_probe_kernel(int n, int iters, int stages, long long* out) {
+__global__ void __launch_bounds__(128, 1) mma_probe_kernel(int n, int iters, int stages, long long* out, int m,
+                                                          int mn_major) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -29,8 +30,10 @@ __global__ void __launch_bounds__(128, 1) mma_probe_kernel(int n, int iters, int
     tc_fence_after();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen + (tptr - base));
     if (warp == 1) {
-        const uint32_t idesc = make_idesc_bf16(128, n, 0, 0);
-        const uint64_t a0 = make_smem_desc_sw128(smem_a, 0, 1024), b0 = make_smem_desc_sw128(smem_b, 0, 1024);
+        const uint32_t idesc = make_idesc_bf16(m, n, mn_major, mn_major);
+        const uint64_t a0 = make_smem_desc_sw128(smem_a, mn_major ? 8192 : 0, 1024);
+        const uint64_t b0 = make_smem_desc_sw128(smem_b, mn_major ? 8192 : 0, 1024);
+        const uint32_t kinc = mn_major ? 128u : 2u;
         long long t0 = 0, t1 = 0;
         if (elect_one()) {
             t0 = clock64();
@@ -38,9 +41,9 @@ __global__ void __launch_bounds__(128, 1) mma_probe_kernel(int n, int iters, int
                 const int st = it % stages;
                 const uint64_t a = a0 + st * (16384 >> 4), b = b0 + st * ((n * 128) >> 4);
                 umma_f16(tmem, a, b, idesc, it > 0);
-                umma_f16(tmem, a + 2, b + 2, idesc, 1u);
-                umma_f16(tmem, a + 4, b + 4, idesc, 1u);
-                umma_f16(tmem, a + 6, b + 6, idesc, 1u);
+                umma_f16(tmem, a + kinc, b + kinc, idesc, 1u);
+                umma_f16(tmem, a + 2 * kinc, b + 2 * kinc, idesc, 1u);
+                umma_f16(tmem, a + 3 * kinc, b + 3 * kinc, idesc, 1u);
             }
             umma_commit(bar);
         }
@@ -62,12 +65,18 @@ __global__ void __launch_bounds__(128, 1) mma_probe_kernel(int n, int iters, int
 
 }  // namespace b200
 
+extern "C" int b200_probe_mma2(int m, int n, int mn_major, int iters, int stages, long long* out_cycles, int blocks,
+                               void* stream);
 extern "C" int b200_probe_mma(int n, int iters, int stages, long long* out_cycles, int blocks, void* stream) {
+    return b200_probe_mma2(128, n, 0, iters, stages, out_cycles, blocks, stream);
+}
+extern "C" int b200_probe_mma2(int m, int n, int mn_major, int iters, int stages, long long* out_cycles, int blocks,
+                               void* stream) {
     using namespace b200;
     const size_t smem = 1024 + (size_t)stages * (16384 + n * 128) + 64;
     if (smem > 227 * 1024 || n % 16 || n < 16 || n > 256) return 1;
     if (cudaFuncSetAttribute(mma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return 3;
-    mma_probe_kernel<<<blocks, 128, smem, (cudaStream_t)stream>>>(n, iters, stages, out_cycles);
+    mma_probe_kernel<<<blocks, 128, smem, (cudaStream_t)stream>>>(n, iters, stages, out_cycles, m, mn_major);
     return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }
