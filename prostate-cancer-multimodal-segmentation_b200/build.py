@@ -5,7 +5,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_NAME = "libb200unet3d.so"
 LIB_PATH = os.path.join(_HERE, LIB_NAME)
-SOURCES = ["api.cu", "igemm.cu", "dmarch.cu", "bandwidth.cu", "probe.cu"]
+SOURCES = ["api.cu", "igemm.cu", "dmarch.cu", "wgrad_halo.cu", "bandwidth.cu", "probe.cu"]
 HEADERS = ["igemm.cuh", "ptx.cuh", "bandwidth.cuh", "../../include/b200_unet3d.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

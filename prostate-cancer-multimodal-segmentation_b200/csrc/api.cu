@@ -17,6 +17,7 @@ namespace b200 {
 extern "C" __global__ void igemm_kernel(const __grid_constant__ IgemmParams p);
 extern "C" __global__ void wgrad_kernel(const __grid_constant__ WgradParams p);
 extern "C" __global__ void dmarch_kernel(const __grid_constant__ DmarchParams p);
+extern "C" __global__ void wgrad_halo_kernel(const __grid_constant__ WgradHaloParams p);
 }  // namespace b200
 
 using namespace b200;
@@ -593,6 +594,61 @@ extern "C" int b200_conv3d_wgrad(const b200_act* x, const b200_act* dy, float* d
     const bool swapped = dy->c <= 64 && cin_real >= 128 && cin_real == x->c;
     const b200_act* P = swapped ? x : dy;
     const b200_act* Q = swapped ? dy : x;
+    if (x->w >= 8 && x->h >= 16) {
+        // h-halo kernel: 8 x 16 x 1 bricks, one 18-row Q box per (kd, kw, chunk), three kh taps per N = 192 MMA
+        const int sms = sm_count();
+        if (sms <= 0) return fail(B200_ERR_CUDA, "no CUDA device");
+        WgradHaloParams hp;
+        memset(&hp, 0, sizeof(hp));
+        rc = make_act_map(&hp.p_map, reinterpret_cast<const __nv_bfloat16*>(P->ptr), P->c, P->w, P->h, P->d, P->n,
+                          P->ld, P->w, P->h, P->d, 1, 8, 16, 1);
+        if (rc) return rc;
+        rc = make_act_map(&hp.q_map, reinterpret_cast<const __nv_bfloat16*>(Q->ptr), Q->c, Q->w, Q->h, Q->d, Q->n,
+                          Q->ld, Q->w, Q->h, Q->d, 1, 8, 18, 1);
+        if (rc) return rc;
+        hp.sgn = swapped ? -1 : 1;
+        hp.p_extent = swapped ? cin_real : (int)dy->c;
+        hp.q_extent = swapped ? (int)dy->c : cin_real;
+        hp.q_chunks = (hp.q_extent + 63) / 64;
+        hp.n_units = 9 * hp.q_chunks;
+        hp.units_per_group = 2;
+        hp.n_groups = (hp.n_units + 1) / 2;
+        hp.p_tiles = (hp.p_extent + 127) / 128;
+        hp.nbw = (int)((x->w + 7) / 8); hp.nbh = (int)((x->h + 15) / 16); hp.nbd = (int)x->d; hp.nbatch = (int)x->n;
+        const long long base_ctas = (long long)hp.n_groups * hp.p_tiles;
+        const long long nbricks = (long long)hp.nbw * hp.nbh * hp.nbd * hp.nbatch;
+        long long splits = (2LL * sms + base_ctas - 1) / base_ctas;
+        if (splits > nbricks) splits = nbricks;
+        if (splits < 1) splits = 1;
+        hp.splits = (int)splits;
+        hp.out = dw;
+        const long long cout_ = dy->c;
+        if (packed_layout) {
+            for (int t = 0; t < 27; ++t) hp.tap_out[t] = (t / 9) * 9 + (t % 3) * 3 + (t / 3) % 3;
+            hp.st = cout_ * cin_real;
+            hp.sp = swapped ? 1 : cin_real;
+            hp.sq = swapped ? cin_real : 1;
+        } else {
+            for (int t = 0; t < 27; ++t) hp.tap_out[t] = t;
+            hp.st = 1;
+            hp.sp = swapped ? 27 : (long long)cin_real * 27;
+            hp.sq = swapped ? (long long)cin_real * 27 : 27;
+        }
+        static bool attr_h = false;
+        const size_t smem_h = 1024 + 2 * 2 * kBoxBytes + kWhQStages * kWhQBytes + 8 * (4 + 2 * kWhQStages + 1) + 64 +
+                              4 * 32 * 33 * 4;
+        {
+            std::lock_guard<std::mutex> lk(g_mu);
+            if (!attr_h) {
+                CUDA_TRY(cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)smem_h));
+                attr_h = true;
+            }
+        }
+        wgrad_halo_kernel<<<(int)(base_ctas * splits), kThreads, smem_h, (cudaStream_t)stream>>>(hp);
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
     rc = make_act_map(&p.p_map, reinterpret_cast<const __nv_bfloat16*>(P->ptr), P->c, P->w, P->h, P->d, P->n, P->ld,
                       P->w, P->h, P->d, 1, b.tw, b.th, b.td);
     if (rc) return rc;

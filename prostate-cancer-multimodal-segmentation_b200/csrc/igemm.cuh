@@ -109,4 +109,23 @@ struct alignas(64) WgradParams {
     long long st, sp, sq;  // element strides of G for (tap, p, q)
 };
 
+// h-halo variant of the weight-gradient GEMM (wgrad_halo.cu): bricks are 8 w x 16 h x 1 d; the shifted operand Q is
+// loaded as one 18-row halo box per (kd, kw, 64-channel chunk) and its three kh taps are three N-atoms of ONE MN-major
+// descriptor (LBO = 1 KB = one h line), i.e. one N = 192 MMA per k-step instead of three boxes / 64 columns each.
+constexpr int kWhQStages = 6;
+constexpr int kWhQBytes = 18 * 8 * 128;
+struct alignas(64) WgradHaloParams {
+    CUtensorMap p_map;   // box (64, 8, 16, 1, 1)
+    CUtensorMap q_map;   // box (64, 8, 18, 1, 1)
+    int sgn;             // +1: Q taps shifted by +off(t); -1: swapped roles, shifted by -off(t)
+    int tap_out[kMaxTaps];
+    int p_extent, q_extent, q_chunks;
+    int n_units;         // 9 * q_chunks column units of 192 TMEM columns: unit = (kd*3 + kw) * q_chunks + chunk
+    int units_per_group; // <= 2 (384 of 512 TMEM columns)
+    int n_groups, p_tiles, splits;
+    int nbw, nbh, nbd, nbatch;
+    float* out;
+    long long st, sp, sq;
+};
+
 }  // namespace b200
