@@ -615,12 +615,19 @@ extern "C" int b200_conv3d_wgrad(const b200_act* x, const b200_act* dy, float* d
         hp.n_groups = (hp.n_units + 1) / 2;
         hp.p_tiles = (hp.p_extent + 127) / 128;
         hp.nbw = (int)((x->w + 7) / 8); hp.nbh = (int)((x->h + 15) / 16); hp.nbd = (int)x->d; hp.nbatch = (int)x->n;
-        const long long base_ctas = (long long)hp.n_groups * hp.p_tiles;
+        // one wave of equally loaded CTAs: every extra voxel split multiplies the atomics on the (small) gradient
         const long long nbricks = (long long)hp.nbw * hp.nbh * hp.nbd * hp.nbatch;
-        long long splits = (2LL * sms + base_ctas - 1) / base_ctas;
+        const bool short_last = (hp.n_units & 1) != 0 && hp.n_groups > 1;   // last group holds one unit of two
+        const double weight = (double)hp.p_tiles * ((double)(hp.n_groups - 1) + (short_last ? 0.5 : 1.0));
+        long long splits = (long long)((double)sms / weight);
         if (splits > nbricks) splits = nbricks;
         if (splits < 1) splits = 1;
+        long long last_splits = short_last ? (splits + 1) / 2 : splits;
+        if (hp.n_groups == 1) last_splits = splits;
         hp.splits = (int)splits;
+        hp.last_splits = (int)last_splits;
+        const long long base_ctas = 0;  // (grid computed below)
+        const long long grid_h = (long long)hp.p_tiles * ((long long)(hp.n_groups - 1) * splits + last_splits);
         hp.out = dw;
         const long long cout_ = dy->c;
         if (packed_layout) {
@@ -645,7 +652,8 @@ extern "C" int b200_conv3d_wgrad(const b200_act* x, const b200_act* dy, float* d
                 attr_h = true;
             }
         }
-        wgrad_halo_kernel<<<(int)(base_ctas * splits), kThreads, smem_h, (cudaStream_t)stream>>>(hp);
+        (void)base_ctas;
+        wgrad_halo_kernel<<<(int)grid_h, kThreads, smem_h, (cudaStream_t)stream>>>(hp);
         CUDA_TRY(cudaGetLastError());
         return 0;
     }

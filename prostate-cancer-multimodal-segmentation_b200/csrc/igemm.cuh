@@ -123,6 +123,7 @@ struct alignas(64) WgradHaloParams {
     int n_units;         // 9 * q_chunks column units of 192 TMEM columns: unit = (kd*3 + kw) * q_chunks + chunk
     int units_per_group; // <= 2 (384 of 512 TMEM columns)
     int n_groups, p_tiles, splits;
+    int last_splits;     // voxel splits of the last group (fewer when it holds a single unit: equal work per CTA)
     int nbw, nbh, nbd, nbatch;
     float* out;
     long long st, sp, sq;

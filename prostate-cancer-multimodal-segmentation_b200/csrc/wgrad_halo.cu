@@ -50,11 +50,21 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) wgrad_halo_kernel(cons
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_smem - smem_base));
 
-    // work decode: blockIdx = (split * n_groups + group) * p_tiles + ptile
+    // work decode: CTAs [0, (n_groups-1)*splits*p_tiles) cover the full groups, the rest the last group, which may be
+    // split fewer times (it holds one unit when n_units is odd) so that every CTA carries the same MMA work
     int bid = blockIdx.x;
     const int ptile = bid % p.p_tiles; bid /= p.p_tiles;
-    const int group = bid % p.n_groups; bid /= p.n_groups;
-    const int split = bid;
+    const int full = (p.n_groups - 1) * p.splits;
+    int group, split, nsplit;
+    if (bid < full) {
+        group = bid % (p.n_groups - 1);
+        split = bid / (p.n_groups - 1);
+        nsplit = p.splits;
+    } else {
+        group = p.n_groups - 1;
+        split = bid - full;
+        nsplit = p.last_splits;
+    }
     const int p0 = ptile * 128;
     const int u0 = group * p.units_per_group;
     const int nun = min(p.units_per_group, p.n_units - u0);
@@ -76,7 +86,7 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) wgrad_halo_kernel(cons
     if (warp == 0) {
         // ===================================================================== TMA producer
         RingW pp, qp;
-        for (int b = split; b < nbricks; b += p.splits) {
+        for (int b = split; b < nbricks; b += nsplit) {
             int mt = b;
             const int bw = mt % p.nbw; mt /= p.nbw;
             const int bh = mt % p.nbh; mt /= p.nbh;
@@ -117,7 +127,7 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) wgrad_halo_kernel(cons
         const uint32_t a_lo0 = (uint32_t)a_desc0, b_lo0 = (uint32_t)b_desc0;
         const uint32_t idesc = make_idesc_bf16(128, 192, 1, 1);
         uint32_t accum = 0;
-        for (int b = split; b < nbricks; b += p.splits) {
+        for (int b = split; b < nbricks; b += nsplit) {
             mbar_wait(pfull(pp.stage), pp.phase);
             tc_fence_after();
             const uint32_t a_lo = a_lo0 + pp.stage * (kPSlot >> 4);
