@@ -317,17 +317,20 @@ def main():
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_host0 = time.perf_counter()
     e2.record()
-    for _ in range(args.steps):
-        x.copy_(x_host, non_blocking=True)
-        y.copy_(y_host, non_blocking=True)
-        loss = step(x, y)
-        _ = loss.item()  # device -> host read of the step's result, as utils/trainer.py:188
+    # the trainer's own input path (trainer.py:train_epoch): every step's image+label go pinned host -> device through
+    # data.DevicePrefetcher, which issues the copy of step i+1 on a copy stream under the kernels of step i
+    host_batches = [{"image": x_host, "label": y_host}] * args.steps
+    losses = pkg.data.AsyncScalarReader()  # every step's loss comes back to the host, read one step late
+    for batch in pkg.data.DevicePrefetcher(host_batches, dev):
+        losses.push(step(batch["image"], batch["label"]))
+    e2e_losses = losses.finish()
     e3.record()
     barrier()
     ms_e2e = max_over_ranks(max(e2.elapsed_time(e3), (time.perf_counter() - t_host0) * 1e3 if world == 1 else 0.0))
     e2e_value = vox_step / (ms_e2e / args.steps * 1e-3)
     h2d = (x_host.numel() + y_host.numel()) * 4 * world
     d2h = 4 * world
+    assert len(e2e_losses) == args.steps
 
     # ---- per-kernel pass: CUDA events around every GEMM launch of one more step (dominant-kernel roofline)
     roofline = None

@@ -564,7 +564,9 @@ static int launch_wgrad(WgradParams& p, cudaStream_t s) {
     p.p_tiles = (p.p_extent + 127) / 128;
     const long long base_ctas = (long long)p.n_groups * p.p_tiles;
     const long long nbricks = (long long)p.nbw * p.nbh * p.nbd * p.nbatch;
-    long long splits = (2LL * sms + base_ctas - 1) / base_ctas;  // about two waves of CTAs
+    // one wave of CTAs: every voxel split adds its whole accumulator to the gradient with REDs, and for the small
+    // GEMMs routed here (deep levels, transposed convs, first layer) those REDs, not the MMAs, are the cost
+    long long splits = sms / base_ctas;
     if (splits > nbricks) splits = nbricks;
     if (splits < 1) splits = 1;
     p.splits = (int)splits;
@@ -610,11 +612,15 @@ extern "C" int b200_conv3d_wgrad(const b200_act* x, const b200_act* dy, float* d
         hp.p_extent = swapped ? cin_real : (int)dy->c;
         hp.q_extent = swapped ? (int)dy->c : cin_real;
         hp.q_chunks = (hp.q_extent + 63) / 64;
-        hp.n_units = 9 * hp.q_chunks;
+        // a P tile of <= 64 channels fills only half of the 128 MMA rows: stack the brick one slice deeper under it
+        // (depth-pair mode, WgradHaloParams::pair) so that one MMA yields two kd taps: 6 units per chunk instead of 9
+        hp.pair = (!swapped && hp.p_extent <= 64) ? 1 : 0;
+        hp.n_units = (hp.pair ? 6 : 9) * hp.q_chunks;
         hp.units_per_group = 2;
         hp.n_groups = (hp.n_units + 1) / 2;
         hp.p_tiles = (hp.p_extent + 127) / 128;
-        hp.nbw = (int)((x->w + 7) / 8); hp.nbh = (int)((x->h + 15) / 16); hp.nbd = (int)x->d; hp.nbatch = (int)x->n;
+        hp.nbw = (int)((x->w + 7) / 8); hp.nbh = (int)((x->h + 15) / 16); hp.nbatch = (int)x->n;
+        hp.nbd = (int)x->d + (hp.pair ? 1 : 0);
         // one wave of equally loaded CTAs: every extra voxel split multiplies the atomics on the (small) gradient
         const long long nbricks = (long long)hp.nbw * hp.nbh * hp.nbd * hp.nbatch;
         const bool short_last = (hp.n_units & 1) != 0 && hp.n_groups > 1;   // last group holds one unit of two
@@ -642,8 +648,8 @@ extern "C" int b200_conv3d_wgrad(const b200_act* x, const b200_act* dy, float* d
             hp.sq = swapped ? (long long)cin_real * 27 : 27;
         }
         static bool attr_h = false;
-        const size_t smem_h = 1024 + 2 * 2 * kBoxBytes + kWhQStages * kWhQBytes + 8 * (4 + 2 * kWhQStages + 1) + 64 +
-                              4 * 32 * 33 * 4;
+        const size_t smem_h = 1024 + kWhPBoxes * kBoxBytes + kWhQStages * kWhQBytes +
+                              8 * (2 * (kWhPBoxes - 1) + 2 * kWhQStages + 1) + 64 + 4 * 32 * 33 * 4;
         {
             std::lock_guard<std::mutex> lk(g_mu);
             if (!attr_h) {
@@ -752,6 +758,7 @@ extern "C" int b200_convt2x_wgrad(const b200_act* x, const b200_act* dy, int pad
         p.tap_out[t] = t;
     }
     p.ntaps = 8;
+    p.tap_minor = 1;
     p.p_extent = (int)x->c;
     p.q_extent = (int)dy->c;
     p.q_chunks = (int)((dy->c + 63) / 64);

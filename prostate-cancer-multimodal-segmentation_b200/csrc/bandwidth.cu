@@ -50,6 +50,11 @@ DEV void ldf8(const float* p, float (&f)[8]) {
     f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
 
+DEV uint32_t pack_bf16x2_(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
 static int grid_for(long long work_items, int threads, int sms, int waves) {
     long long blocks = (work_items + threads - 1) / threads;
     const long long cap = (long long)sms * waves;
@@ -136,11 +141,70 @@ __global__ void __launch_bounds__(256) im2col_input_kernel(const float* __restri
         dst[(long long)row * ld_words + col] = i2c_smem[row * pitch + col];
     }
 }
+// Specialisation for a compile-time channel count (the 5-modality input): the kernel above is issue-bound (two
+// instructions per 2-byte element plus a divide per copied word).  Here thread (voxel, half) builds words
+// [36*half, 36*half + 36) of its row: every (channel, tap) of a word is a compile-time constant, two taps are converted
+// and stored as one 32-bit word, and the copy-out walks whole rows per warp without divisions.
+template <int CIN>
+__global__ void __launch_bounds__(256) im2col_input_fixed_kernel(const float* __restrict__ x, int D, int H, int W,
+                                                                 long long nvox, View out) {
+    constexpr int K = 27 * CIN, KPAD = (K + 15) / 16 * 16, WORDS = KPAD / 2, PITCH = WORDS | 1, HW = WORDS / 2;
+    extern __shared__ uint32_t i2c_smem[];  // [128][PITCH] words
+    const long long v0 = (long long)blockIdx.x * kI2cVox;
+    const int vl = threadIdx.x & (kI2cVox - 1), half = threadIdx.x >> 7;   // half is warp-uniform
+    const long long v = v0 + vl;
+    const int plane = D * H * W, hw = H * W;
+    if (v < nvox) {
+        const int nb = (int)(v / plane);
+        int r = (int)(v - (long long)nb * plane);
+        const int d = r / hw;
+        r -= d * hw;
+        const int h = r / W, w = r - h * W;
+        const float* xb = x + (long long)nb * CIN * plane + (d * hw + h * W + w);
+        bool okdh[9], okw[3];
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+            okdh[i] = (unsigned)(d + i / 3 - 1) < (unsigned)D && (unsigned)(h + i % 3 - 1) < (unsigned)H;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) okw[i] = (unsigned)(w + i - 1) < (unsigned)W;
+        uint32_t* row = i2c_smem + vl * PITCH;
+        auto tap = [&](int k) -> float {
+            if (k >= K) return 0.f;
+            const int c = k / 27, t = k % 27, kd = t / 9, kh = (t / 3) % 3, kw = t % 3;
+            if (!(okdh[kd * 3 + kh] && okw[kw])) return 0.f;
+            return __ldg(xb + ((long long)c * plane + (kd - 1) * hw + (kh - 1) * W + (kw - 1)));
+        };
+        if (half == 0) {
+#pragma unroll
+            for (int j = 0; j < HW; ++j) row[j] = pack_bf16x2_(tap(2 * j), tap(2 * j + 1));
+        } else {
+#pragma unroll
+            for (int j = HW; j < WORDS; ++j) row[j] = pack_bf16x2_(tap(2 * j), tap(2 * j + 1));
+        }
+    }
+    __syncthreads();
+    const int rows = (int)((nvox - v0) < kI2cVox ? (nvox - v0) : kI2cVox);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(out.p + v0 * out.ld);
+    const int ld_words = (int)(out.ld / 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int rr = warp; rr < rows; rr += 8) {
+        const uint32_t* src = i2c_smem + rr * PITCH;
+        uint32_t* o = dst + (long long)rr * ld_words;
+#pragma unroll
+        for (int c = 0; c < (WORDS + 31) / 32; ++c)
+            if (c * 32 + lane < WORDS) o[c * 32 + lane] = src[c * 32 + lane];
+    }
+}
 cudaError_t launch_im2col_input(const float* x, long long n, long long c, long long d, long long h, long long w,
                                 View out, cudaStream_t s) {
     const long long nvox = n * d * h * w;
-    const int smem = kI2cVox * ((int)out.c / 2 + 1) * 4;
     const long long blocks = (nvox + kI2cVox - 1) / kI2cVox;
+    if (c == 5 && out.c == 144 && d * h * w < (1LL << 31)) {
+        const int smem = kI2cVox * 73 * 4;
+        im2col_input_fixed_kernel<5><<<(unsigned)blocks, 256, smem, s>>>(x, (int)d, (int)h, (int)w, nvox, out);
+        return cudaGetLastError();
+    }
+    const int smem = kI2cVox * ((int)out.c / 2 + 1) * 4;
     im2col_input_kernel<<<(unsigned)blocks, 256, smem, s>>>(x, (int)c, (int)d, (int)h, (int)w, nvox, out);
     return cudaGetLastError();
 }
@@ -252,13 +316,25 @@ cudaError_t launch_pack_convt_weight(const float* w, const float* bias, int cin,
 }
 
 // ------------------------------------------------------------------------------------------------ BN finalize
-// partial[rows][c][2] -> per-channel (sum0, sum1) in double; block = 32 channels x 8 row slices
-DEV void reduce_partials(const float* __restrict__ partial, int rows, int c, int ch, int slice, double (&red)[8][32][2],
-                         double& s0, double& s1) {
+// partial[rows][c][2] -> per-channel (sum0, sum1) in double; block = 32 channels x kRedSlices row slices (1024
+// threads: the kernel is a chain of dependent loads, so the rows are spread wide and loaded four at a time)
+constexpr int kRedSlices = 32;
+DEV void reduce_partials(const float* __restrict__ partial, int rows, int c, int ch, int slice,
+                         double (&red)[kRedSlices][32][2], double& s0, double& s1) {
     double a = 0.0, b = 0.0;
     if (ch < c) {
-        for (int r = slice; r < rows; r += 8) {
-            const float2 v = __ldg(reinterpret_cast<const float2*>(partial) + (long long)r * c + ch);
+        const float2* src = reinterpret_cast<const float2*>(partial) + ch;
+        int r = slice;
+        for (; r + 3 * kRedSlices < rows; r += 4 * kRedSlices) {
+            const float2 v0 = __ldg(src + (long long)r * c);
+            const float2 v1 = __ldg(src + (long long)(r + kRedSlices) * c);
+            const float2 v2 = __ldg(src + (long long)(r + 2 * kRedSlices) * c);
+            const float2 v3 = __ldg(src + (long long)(r + 3 * kRedSlices) * c);
+            a += ((double)v0.x + (double)v1.x) + ((double)v2.x + (double)v3.x);
+            b += ((double)v0.y + (double)v1.y) + ((double)v2.y + (double)v3.y);
+        }
+        for (; r < rows; r += kRedSlices) {
+            const float2 v = __ldg(src + (long long)r * c);
             a += v.x;
             b += v.y;
         }
@@ -269,20 +345,20 @@ DEV void reduce_partials(const float* __restrict__ partial, int rows, int c, int
     s0 = s1 = 0.0;
     if (slice == 0) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < kRedSlices; ++k) {
             s0 += red[k][threadIdx.x & 31][0];
             s1 += red[k][threadIdx.x & 31][1];
         }
     }
 }
 
-__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ partial, int rows,
+__global__ void __launch_bounds__(32 * kRedSlices) bn_finalize_kernel(const float* __restrict__ partial, int rows,
                                                           double inv_count, double unbias, int c,
                                                           const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, float eps, float momentum,
                                                           float* rm, float* rv, float* mean, float* rstd, float* scale,
                                                           float* shift) {
-    __shared__ double red[8][32][2];
+    __shared__ double red[kRedSlices][32][2];
     const int ch = blockIdx.x * 32 + (threadIdx.x & 31), slice = threadIdx.x >> 5;
     double s, q;
     reduce_partials(partial, rows, c, ch, slice, red, s, q);
@@ -304,7 +380,7 @@ cudaError_t launch_bn_finalize(const float* partial, long long rows, long long c
                                const float* beta, float eps, float momentum, float* rm, float* rv, float* mean,
                                float* rstd, float* scale, float* shift, cudaStream_t s) {
     const double unbias = count > 1 ? (double)count / (double)(count - 1) : 1.0;
-    bn_finalize_kernel<<<(c + 31) / 32, 256, 0, s>>>(partial, (int)rows, 1.0 / (double)count, unbias, c, gamma, beta,
+    bn_finalize_kernel<<<(c + 31) / 32, 32 * kRedSlices, 0, s>>>(partial, (int)rows, 1.0 / (double)count, unbias, c, gamma, beta,
                                                     eps, momentum, rm, rv, mean, rstd, scale, shift);
     return cudaGetLastError();
 }
@@ -476,10 +552,10 @@ cudaError_t launch_bn_bwd_reduce(View dout, View y, const float* scale, const fl
     return cudaGetLastError();
 }
 
-__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int c,
+__global__ void __launch_bounds__(32 * kRedSlices) bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int c,
                                                               double inv_count, float* dgamma, float* dbeta,
                                                               float* coef) {
-    __shared__ double red[8][32][2];
+    __shared__ double red[kRedSlices][32][2];
     const int ch = blockIdx.x * 32 + (threadIdx.x & 31), slice = threadIdx.x >> 5;
     double s1, s2;
     reduce_partials(partial, nblk, c, ch, slice, red, s1, s2);
@@ -491,7 +567,7 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __res
 }
 cudaError_t launch_bn_bwd_finalize(const float* partial, int nblk, int c, long long count, float* dgamma,
                                    float* dbeta, float* coef, cudaStream_t s) {
-    bn_bwd_finalize_kernel<<<(c + 31) / 32, 256, 0, s>>>(partial, nblk, c, 1.0 / (double)count, dgamma, dbeta, coef);
+    bn_bwd_finalize_kernel<<<(c + 31) / 32, 32 * kRedSlices, 0, s>>>(partial, nblk, c, 1.0 / (double)count, dgamma, dbeta, coef);
     return cudaGetLastError();
 }
 

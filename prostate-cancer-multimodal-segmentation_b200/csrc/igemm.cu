@@ -483,8 +483,8 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __g
                     mbar_arrive_expect_tx(fb, nb4 * kBoxBytes);
                     for (int i = 0; i < nb4; ++i) {
                         const int cb = cb0 + sg * 4 + i;
-                        const int tap = cb / p.q_chunks;
-                        const int qc = cb - tap * p.q_chunks;
+                        const int tap = p.tap_minor ? cb % p.ntaps : cb / p.q_chunks;
+                        const int qc = p.tap_minor ? cb / p.ntaps : cb - tap * p.q_chunks;
                         tma_load_5d(smem_q + qp.stage * kQSlot + i * kBoxBytes, &p.q_map[p.q_map_of_tap[tap]], fb,
                                     qc * 64, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], d0 + p.tap_dd[tap], nb);
                     }
@@ -542,8 +542,8 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __g
             float* tile = reinterpret_cast<float*>(smem_gen + (tmem_ptr_smem + 16 - smem_base)) + q * (32 * 33);
             for (int i = 0; i < ncb; ++i) {
                 const int cb = cb0 + i;
-                const int tap = cb / p.q_chunks;
-                const int qc = cb - tap * p.q_chunks;
+                const int tap = p.tap_minor ? cb % p.ntaps : cb / p.q_chunks;
+                const int qc = p.tap_minor ? cb / p.ntaps : cb - tap * p.q_chunks;
                 float* obase = p.out + (long long)p.tap_out[tap] * p.st + (long long)(p0 + q * 32) * p.sp + qc * 64;
                 for (int half = 0; half < 2; ++half) {
                     uint32_t v[32];
@@ -561,11 +561,37 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __g
                     __syncwarp();
                 }
             }
+        } else if (p.tap_minor && ncb == 8 && p.ntaps == 8 && p.sq == 8 && p.st == 1 &&
+                   (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && (p.sp & 3) == 0) {
+            // transposed conv, G[p][q][8 taps]: this CTA holds all 8 taps of one 64-channel chunk, so the taps of one
+            // (p, q) are 32 contiguous bytes: two 16-byte vector REDs instead of eight scattered 4-byte ones (the
+            // scattered form made every convT weight gradient cost ~0.17 ms whatever its size: ~19 M REDs per launch)
+            const int qc = cb0 >> 3;
+            for (int c8 = 0; c8 < 8; ++c8) {
+                uint32_t v[8][8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) tmem_ld8(t_addr + t * 64 + c8 * 8, v[t]);
+                tmem_ld_wait();
+                if (pidx < p.p_extent) {
+                    float* dst = p.out + (long long)pidx * p.sp + (long long)(qc * 64 + c8 * 8) * 8;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (qc * 64 + c8 * 8 + j < p.q_extent) {
+                            atomicAdd(reinterpret_cast<float4*>(dst + j * 8),
+                                      make_float4(__uint_as_float(v[0][j]), __uint_as_float(v[1][j]),
+                                                  __uint_as_float(v[2][j]), __uint_as_float(v[3][j])));
+                            atomicAdd(reinterpret_cast<float4*>(dst + j * 8 + 4),
+                                      make_float4(__uint_as_float(v[4][j]), __uint_as_float(v[5][j]),
+                                                  __uint_as_float(v[6][j]), __uint_as_float(v[7][j])));
+                        }
+                    }
+                }
+            }
         } else {
             for (int i = 0; i < ncb; ++i) {
                 const int cb = cb0 + i;
-                const int tap = cb / p.q_chunks;
-                const int qc = cb - tap * p.q_chunks;
+                const int tap = p.tap_minor ? cb % p.ntaps : cb / p.q_chunks;
+                const int qc = p.tap_minor ? cb / p.ntaps : cb - tap * p.q_chunks;
                 for (int c = 0; c < 4; ++c) {
                     uint32_t v[16];
                     tmem_ld16(t_addr + i * 64 + c * 16, v);

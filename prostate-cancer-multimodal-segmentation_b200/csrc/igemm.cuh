@@ -101,6 +101,8 @@ struct alignas(64) WgradParams {
     int p_extent, q_extent;
     int q_chunks;      // ceil(q_extent / 64)
     int n_colblocks;   // ntaps * q_chunks
+    int tap_minor;     // column block = chunk * ntaps + tap (else tap * q_chunks + chunk): with 8 taps a CTA then owns
+                       // every tap of one 64-channel chunk, which the transposed-conv epilogue stores as 32-byte runs
     int cb_per_group;  // column blocks (64 wide) accumulated by one CTA (<= 8 -> 512 TMEM columns)
     int n_groups, p_tiles, splits;
     int nbw, nbh, nbd, nbatch;
@@ -112,7 +114,8 @@ struct alignas(64) WgradParams {
 // h-halo variant of the weight-gradient GEMM (wgrad_halo.cu): bricks are 8 w x 16 h x 1 d; the shifted operand Q is
 // loaded as one 18-row halo box per (kd, kw, 64-channel chunk) and its three kh taps are three N-atoms of ONE MN-major
 // descriptor (LBO = 1 KB = one h line), i.e. one N = 192 MMA per k-step instead of three boxes / 64 columns each.
-constexpr int kWhQStages = 6;
+constexpr int kWhQStages = 5;
+constexpr int kWhPBoxes = 6;     // P ring capacity in 16 KB boxes (wgrad_halo.cu)
 constexpr int kWhQBytes = 18 * 8 * 128;
 struct alignas(64) WgradHaloParams {
     CUtensorMap p_map;   // box (64, 8, 16, 1, 1)
@@ -121,6 +124,10 @@ struct alignas(64) WgradHaloParams {
     int tap_out[kMaxTaps];
     int p_extent, q_extent, q_chunks;
     int n_units;         // 9 * q_chunks column units of 192 TMEM columns: unit = (kd*3 + kw) * q_chunks + chunk
+    int pair;            // depth-pair mode for P tiles of <= 64 channels: the M side is [P(brick); P(brick + 1 slice)],
+                         // so one MMA yields two kd taps.  6 * q_chunks units: unit = ((kw * q_chunks + chunk) * 2 + kind,
+                         // kind 0: Q one slice ahead (rows 0-63 -> kd 2, rows 64-127 -> kd 1); kind 1: Q one slice
+                         // behind (rows 0-63 -> kd 0, upper rows unused).  Bricks then start at depth -1 (nbd = D + 1).
     int units_per_group; // <= 2 (384 of 512 TMEM columns)
     int n_groups, p_tiles, splits;
     int last_splits;     // voxel splits of the last group (fewer when it holds a single unit: equal work per CTA)

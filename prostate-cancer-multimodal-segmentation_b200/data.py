@@ -50,6 +50,108 @@ class SyntheticProstateDataset(Dataset):
         return {"image": img, "label": lab, "case_id": f"case_{c:04d}"}
 
 
+class DevicePrefetcher:
+    """Iterates a loader of batch dicts and hands out the same dicts with their tensors on `device`.
+
+    The host->device copy of batch i+1 is issued on a copy stream as soon as batch i is handed out, so it runs under
+    the kernels of step i (the reference's loop, utils/trainer.py:177-181, copies synchronously in front of every
+    step).  Host tensors that are not pinned are staged through a pinned buffer first (a pageable source would make
+    the copy synchronous).  Two device slots per key rotate; a slot is only overwritten after the compute stream has
+    passed the event recorded when its successor was handed out, so no allocator traffic and no host sync."""
+
+    def __init__(self, loader, device, keys=("image", "label")):
+        self.loader, self.device, self.keys = loader, torch.device(device), tuple(keys)
+        if self.device.type != "cuda":
+            raise ValueError("DevicePrefetcher stages batches into CUDA memory; got device " + str(device))
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self._slots = [{}, {}]
+        self._pinned = [{}, {}]
+        self._free = [None, None]   # event on the compute stream after which slot i may be overwritten
+        self._ready = [None, None]  # event on the copy stream after which slot i's pinned staging buffer is free
+
+    def __len__(self):
+        return len(self.loader)
+
+    def _stage(self, batch, i):
+        out = dict(batch)
+        slot, pinned = self._slots[i], self._pinned[i]
+        if self._free[i] is not None:
+            self.copy_stream.wait_event(self._free[i])
+        with torch.cuda.stream(self.copy_stream):
+            for k in self.keys:
+                src = batch[k]
+                if not src.is_pinned():
+                    buf = pinned.get(k)
+                    if buf is None or buf.shape != src.shape or buf.dtype != src.dtype:
+                        buf = pinned[k] = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+                    if self._ready[i] is not None:
+                        self._ready[i].synchronize()
+                    buf.copy_(src)
+                    src = buf
+                dst = slot.get(k)
+                if dst is None or dst.shape != src.shape or dst.dtype != src.dtype:
+                    dst = slot[k] = torch.empty(src.shape, dtype=src.dtype, device=self.device)
+                dst.copy_(src, non_blocking=True)
+                out[k] = dst
+            ready = self._ready[i] = self.copy_stream.record_event()
+        return out, ready
+
+    def __iter__(self):
+        it = iter(self.loader)
+        i = 0
+        try:
+            nxt = self._stage(next(it), i)
+        except StopIteration:
+            return
+        while nxt is not None:
+            cur, ready = nxt
+            main = torch.cuda.current_stream(self.device)
+            main.wait_event(ready)
+            # the other slot was handed out one iteration ago: everything queued on the compute stream so far is what
+            # read it, so it may be overwritten once the compute stream gets here
+            self._free[1 - i] = main.record_event()
+            try:
+                nxt = self._stage(next(it), 1 - i)
+            except StopIteration:
+                nxt = None
+            yield cur
+            i = 1 - i
+
+
+class AsyncScalarReader:
+    """Device->host read of one scalar per step without stalling the launch queue: every pushed 0-dim CUDA tensor is
+    copied into a pinned slot on the compute stream and collected `depth` pushes later, when its copy has long
+    finished (the reference's `loss.item()` per step, utils/trainer.py:188, drains the GPU every step).
+    `values` holds every scalar, in order, once `finish()` has returned."""
+
+    def __init__(self, depth=2):
+        self.depth = depth
+        self.buf = torch.empty(depth, dtype=torch.float32, pin_memory=True)
+        self.events = [None] * depth
+        self.values = []
+        self._n = 0
+
+    def _collect(self, i):
+        self.events[i].synchronize()
+        self.values.append(float(self.buf[i]))
+        self.events[i] = None
+
+    def push(self, scalar):
+        i = self._n % self.depth
+        if self.events[i] is not None:
+            self._collect(i)
+        self.buf[i:i + 1].copy_(scalar.detach().reshape(1), non_blocking=True)
+        self.events[i] = torch.cuda.current_stream(scalar.device).record_event()
+        self._n += 1
+
+    def finish(self):
+        for k in range(self.depth):
+            i = (self._n + k) % self.depth
+            if self.events[i] is not None:
+                self._collect(i)
+        return self.values
+
+
 def get_dataloader(data_dir=None, batch_size=2, shuffle=True, modalities=None, missing_strategy="zero_fill",
                    target_size=(128, 128, 128), num_workers=0, is_training=True, data_type="BPH", indices=None,
                    n_cases=8, seed=1234):

@@ -87,11 +87,11 @@ class BaseTrainer:
     def train_epoch(self):
         self.model.train()
         total, n = 0.0, 0
-        for batch in self.train_loader:
-            images = batch["image"].to(self.device, non_blocking=True)
-            labels = batch["label"].to(self.device, non_blocking=True)
-            total += self._step(images, labels).item()
+        losses = _data.AsyncScalarReader()  # per-step loss read back one step late: no GPU drain between steps
+        for batch in _data.DevicePrefetcher(self.train_loader, self.device):  # next batch's H2D under this step
+            losses.push(self._step(batch["image"], batch["label"]))
             n += 1
+        total = sum(losses.finish())
         return total / max(n, 1)
 
     def validate_epoch(self):
@@ -100,10 +100,8 @@ class BaseTrainer:
         self.model.eval()
         total, n = 0.0, 0
         with torch.no_grad():
-            for batch in self.val_loader:
-                images = batch["image"].to(self.device, non_blocking=True)
-                labels = batch["label"].to(self.device, non_blocking=True)
-                total += self.criterion(self.model(images), labels).item()
+            for batch in _data.DevicePrefetcher(self.val_loader, self.device):
+                total += self.criterion(self.model(batch["image"]), batch["label"]).item()
                 n += 1
         return total / max(n, 1)
 
@@ -210,8 +208,8 @@ class CrossValidationTrainer:
         for epoch in range(self.config["num_epochs"]):
             model.train()
             tl, n = 0.0, 0
-            for batch in train_loader:
-                images, labels = batch["image"].to(self.device), batch["label"].to(self.device)
+            for batch in _data.DevicePrefetcher(train_loader, self.device):
+                images, labels = batch["image"], batch["label"]
                 opt.zero_grad()
                 with torch.autocast("cuda", dtype=torch.bfloat16):
                     outputs = model(images)
@@ -223,8 +221,8 @@ class CrossValidationTrainer:
             model.eval()
             vl, m = 0.0, 0
             with torch.no_grad():
-                for batch in val_loader:
-                    images, labels = batch["image"].to(self.device), batch["label"].to(self.device)
+                for batch in _data.DevicePrefetcher(val_loader, self.device):
+                    images, labels = batch["image"], batch["label"]
                     outputs = model(images)
                     vl += crit(outputs, self._fix_labels(outputs, labels)).item(); m += 1
             tl, vl = tl / max(n, 1), vl / max(m, 1)

@@ -41,6 +41,7 @@ CONV_CASES = [
     (1, 128, 128, 64, 9, 36, 20),    # depth-marching, two K blocks, partial bricks
     (1, 64, 64, 128, 7, 16, 16),     # dgrad through the depth-marching kernel (dx has 64 channels, K = 128)
     (1, 96, 96, 64, 1, 16, 8),       # depth-marching with a single slice and a K tail
+    (1, 64, 64, 32, 5, 16, 16),      # wgrad depth-pair mode with a half-filled P tile (Cout = 32)
 ]
 
 
