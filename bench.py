@@ -189,12 +189,22 @@ def run_infer(args, pkg, par, dev, world, rank):
         ms = t.item()
     launches = pkg.ops.launch_count - l0
     # end to end: host volume in, host mask out
+    # every rank uploads only the volumes its windows read and downloads the masks of those volumes
+    vols = par.rank_volumes(tuple(x.shape), window, stride, rank, world)
+    m_host = torch.empty(world, 1, 256, 256, 64, dtype=torch.uint8).pin_memory()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
     e2.record()
     for _ in range(args.steps):
-        x.copy_(x_host, non_blocking=True)
+        for v in vols:
+            x[v].copy_(x_host[v], non_blocking=True)
         probs, mask = step()
-        m_host = mask.to(torch.uint8).cpu()
+        m8 = mask.to(torch.uint8)
+        for v in vols:
+            m_host[v].copy_(m8[v], non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the host holds this step's masks before the next one starts
     e3.record()
     torch.cuda.synchronize()
     ms2 = e2.elapsed_time(e3)
@@ -214,7 +224,8 @@ def run_infer(args, pkg, par, dev, world, rank):
                                    "window 128x128x64 stride 64 (9 windows/volume), one volume per GPU",
                        "volumes": world, "parallelism": f"windows sharded over {world} rank(s)"},
             "e2e": {"value": vox / (ms2 / args.steps * 1e-3), "unit": "voxels/s",
-                    "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": int(m_host.numel())},
+                    "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": int(m_host.numel()),
+                    "note": "per step every rank uploads the volumes its windows read and downloads their masks"},
             "gpu_launches": launches,
             "model_tflops": round(win_vox * fwd / (ms / args.steps * 1e-3) / 1e12, 1)}), flush=True)
 
@@ -240,6 +251,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL's version banner / debug lines go to stderr: stdout carries the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     pkg.load_library()
 

@@ -164,6 +164,21 @@ int b200_channel_sum(const b200_act* v, float* out, void* stream);
 /* NDHWC bf16 view -> (N,C,D,H,W) fp32 (debug / per-layer parity taps) */
 int b200_unpack_act(const b200_act* v, float* out_ncdhw, void* stream);
 
+/* ---- "next" rows: input pipeline and validation metrics on the device -------------------------- */
+/* nvol contiguous fp32 volumes (d_in,h_in,w_in) -> (d_out,h_out,w_out) with the semantics of the reference's
+ * sitk.ResampleImageFilter call (script/data_loader.py:240-283 image: linear; :395-409 label: nearest then > 0):
+ * output index i reads the continuous input index i*in/out per axis, the upper neighbour is clamped to the last index,
+ * points at or beyond size-0.5 get the default value 0.  nearest != 0: floor(index+0.5).  binarize != 0: out = out > 0. */
+int b200_resample3d(const float* in, int64_t nvol, int64_t d_in, int64_t h_in, int64_t w_in, float* out,
+                    int64_t d_out, int64_t h_out, int64_t w_out, int nearest, int binarize, void* stream);
+/* in place, per volume: (x - min) / (max - min), a constant volume becomes zeros (script/predict.py:69-75).
+ * workspace: >= 8 * nvol bytes */
+int b200_minmax_normalize(float* x, int64_t nvol, int64_t voxels_per_volume, void* workspace, void* stream);
+/* counts[s][3] (int64, +=) = (|P & T|, |P|, |T|) with P = score > threshold, T = label > 0.5, per sample: the integer
+ * sums behind calculate_dice_score / calculate_iou (script/validate_model.py:24-95) */
+int b200_seg_counts(const float* score, const float* label, int64_t nsamples, int64_t voxels_per_sample,
+                    float threshold, int64_t* counts, void* stream);
+
 /* dev probe (not on the hot path): cycles for `iters` x 4 tcgen05.mma (M=128, N=n, K=16, SS mode) per CTA, operands
  * cycling through `stages` shared-memory slots; out_cycles[blocks] (int64) */
 int b200_probe_mma(int n, int iters, int stages, long long* out_cycles, int blocks, void* stream);

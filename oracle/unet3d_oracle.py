@@ -230,3 +230,74 @@ def sliding_window_logits(x, sd, window, stride):
                     out[:, :, d0:d0 + wd, h0:h0 + wh, w0:w0 + ww] += lg
                     cnt[:, :, d0:d0 + wd, h0:h0 + wh, w0:w0 + ww] += 1
     return out / cnt
+
+
+# ------------------------------------------------------------------------------------------------ "next" rows (8f)
+def resample3d_itk(x, size, nearest=False, binarize=False):
+    """numpy restatement of the reference's resample-to-target (script/data_loader.py:257-279 image, :389-406 label):
+    sitk.ResampleImageFilter with identity transform, the input's origin/direction and output spacing
+    in_size * spacing / out_size.  PARITY UNPINNED: SimpleITK (an un-vendored dependency, requirements.txt) is not
+    installable offline, so this follows ITK's published algorithm — ResampleImageFilter maps output index i to the
+    continuous input index i * in/out; IsInsideBuffer is index < size - 0.5 (else DefaultPixelValue 0);
+    LinearInterpolateImageFunction takes floor + fraction and clamps the upper neighbour to the last index;
+    NearestNeighborInterpolateImageFunction rounds half up.  x: (..., D, H, W) float array."""
+    import numpy as np
+    x = np.asarray(x, dtype=np.float32)
+    di, hi, wi = x.shape[-3:]
+    do, ho, wo = size
+    out = np.zeros(x.shape[:-3] + (do, ho, wo), dtype=np.float32)
+
+    def axis(n_in, n_out):
+        c = np.arange(n_out, dtype=np.float64) * (n_in / n_out)
+        inside = c < n_in - 0.5
+        if nearest:
+            i0 = np.minimum(np.floor(c + 0.5).astype(np.int64), n_in - 1)
+            return inside, i0, i0, np.zeros(n_out, dtype=np.float32)
+        i0 = np.floor(c).astype(np.int64)
+        return inside, np.minimum(i0, n_in - 1), np.minimum(i0 + 1, n_in - 1), (c - i0).astype(np.float32)
+
+    ind, d0, d1, fd = axis(di, do)
+    inh, h0, h1, fh = axis(hi, ho)
+    inw, w0, w1, fw = axis(wi, wo)
+    fd, fh, fw = fd[:, None, None], fh[None, :, None], fw[None, None, :]
+
+    def g(a, b, c):
+        return x[..., a[:, None, None], b[None, :, None], c[None, None, :]]
+
+    if nearest:
+        v = g(d0, h0, w0)
+    else:
+        c00 = g(d0, h0, w0) + fw * (g(d0, h0, w1) - g(d0, h0, w0))
+        c01 = g(d0, h1, w0) + fw * (g(d0, h1, w1) - g(d0, h1, w0))
+        c10 = g(d1, h0, w0) + fw * (g(d1, h0, w1) - g(d1, h0, w0))
+        c11 = g(d1, h1, w0) + fw * (g(d1, h1, w1) - g(d1, h1, w0))
+        c0 = c00 + fh * (c01 - c00)
+        c1 = c10 + fh * (c11 - c10)
+        v = c0 + fd * (c1 - c0)
+    inside = ind[:, None, None] & inh[None, :, None] & inw[None, None, :]
+    out[...] = np.where(inside, v, 0.0)
+    if binarize:
+        out = (out > 0).astype(np.float32)
+    return out
+
+
+def minmax_normalize(image):
+    """per-modality (x - min) / (max - min), constant volume -> zeros (script/predict.py:69-75)"""
+    import numpy as np
+    out = np.zeros_like(image, dtype=np.float32)
+    for m in range(image.shape[0]):
+        lo, hi = np.float32(image[m].min()), np.float32(image[m].max())
+        if hi > lo:
+            out[m] = (image[m].astype(np.float32) - lo) / (hi - lo)
+    return out
+
+
+def hard_dice_iou(pred_mask, target_mask, eps=1e-8):
+    """script/validate_model.py:24-95 on float 0/1 masks, in double"""
+    import numpy as np
+    p = np.asarray(pred_mask, dtype=np.float64).reshape(-1)
+    t = np.asarray(target_mask, dtype=np.float64).reshape(-1)
+    inter = float((p * t).sum())
+    dice = (2 * inter + eps) / (p.sum() + t.sum() + eps)
+    iou = (inter + eps) / (p.sum() + t.sum() - inter + eps)
+    return float(dice), float(iou)

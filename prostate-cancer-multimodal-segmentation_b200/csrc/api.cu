@@ -969,3 +969,36 @@ extern "C" int b200_unpack_act(const b200_act* v, float* out, void* stream) {
     CUDA_TRY(launch_unpack_act(to_view(v), out, (cudaStream_t)stream));
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------ input pipeline / metrics
+extern "C" int b200_resample3d(const float* in, int64_t nvol, int64_t d_in, int64_t h_in, int64_t w_in, float* out,
+                               int64_t d_out, int64_t h_out, int64_t w_out, int nearest, int binarize, void* stream) {
+    REQUIRE(in && out, "resample3d: null pointer");
+    REQUIRE(nvol >= 0 && d_in > 0 && h_in > 0 && w_in > 0 && d_out > 0 && h_out > 0 && w_out > 0,
+            "resample3d: extents must be positive");
+    REQUIRE(d_in * h_in * w_in < (1LL << 31) && d_out * h_out * w_out < (1LL << 31), "resample3d: volume too large");
+    const int sms = sm_count();
+    if (sms <= 0) return fail(B200_ERR_CUDA, "no CUDA device");
+    CUDA_TRY(launch_resample3d(in, nvol, (int)d_in, (int)h_in, (int)w_in, out, (int)d_out, (int)h_out, (int)w_out,
+                               nearest, binarize, sms, (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int b200_minmax_normalize(float* x, int64_t nvol, int64_t voxels_per_volume, void* workspace, void* stream) {
+    REQUIRE(x && workspace, "minmax_normalize: null pointer");
+    REQUIRE(nvol >= 0 && nvol < 65536 && voxels_per_volume >= 0, "minmax_normalize: bad extents");
+    const int sms = sm_count();
+    if (sms <= 0) return fail(B200_ERR_CUDA, "no CUDA device");
+    CUDA_TRY(launch_minmax_normalize(x, nvol, voxels_per_volume, reinterpret_cast<uint32_t*>(workspace), sms,
+                                     (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int b200_seg_counts(const float* score, const float* label, int64_t nsamples, int64_t voxels_per_sample,
+                               float threshold, int64_t* counts, void* stream) {
+    REQUIRE(score && label && counts, "seg_counts: null pointer");
+    REQUIRE(nsamples >= 0 && nsamples < 65536 && voxels_per_sample >= 0, "seg_counts: bad extents");
+    const int sms = sm_count();
+    if (sms <= 0) return fail(B200_ERR_CUDA, "no CUDA device");
+    CUDA_TRY(launch_seg_counts(score, label, nsamples, voxels_per_sample, threshold,
+                               reinterpret_cast<unsigned long long*>(counts), sms, (cudaStream_t)stream));
+    return 0;
+}

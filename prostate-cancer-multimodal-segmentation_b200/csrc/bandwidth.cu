@@ -1161,4 +1161,144 @@ cudaError_t launch_unpack_act(View v, float* out, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+
+// ================================================================================================ "next" rows (8f)
+// Input pipeline and validation metrics on the device.  Reference call sites: resample-to-target of every modality
+// (script/data_loader.py:240-283, sitk.ResampleImageFilter, linear) and of the label (:395-409, nearest, then > 0),
+// per-modality min-max normalisation (script/predict.py:69-75), hard Dice / IoU of thresholded predictions
+// (script/validate_model.py:24-95).
+
+// ITK semantics of that resample (identity direction, same origin, output spacing = in_size*spacing/out_size): output
+// index i maps to the continuous input index i * (in/out) per axis (pixel centres at integer indices).  A point is
+// inside the buffer iff index < size - 0.5 on every axis, else the default pixel value 0 is written.  Linear: base =
+// floor, the upper neighbour is clamped to the last index.  Nearest: floor(index + 0.5).
+__global__ void __launch_bounds__(256) resample3d_kernel(const float* __restrict__ in, int di, int hi, int wi,
+                                                         float* __restrict__ out, int dout, int ho, int wo,
+                                                         long long nvol, int nearest, int binarize) {
+    const double sd = (double)di / dout, sh = (double)hi / ho, sw = (double)wi / wo;
+    const long long per = (long long)dout * ho * wo, total = nvol * per;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long vol = i / per;
+        long long r = i - vol * per;
+        const int od = (int)(r / ((long long)ho * wo));
+        r -= (long long)od * ho * wo;
+        const int oh = (int)(r / wo), ow = (int)(r - (long long)oh * wo);
+        const double cd = od * sd, ch = oh * sh, cw = ow * sw;
+        const float* src = in + vol * (long long)di * hi * wi;
+        float v = 0.f;
+        if (cd < di - 0.5 && ch < hi - 0.5 && cw < wi - 0.5) {
+            if (nearest) {
+                const int zd = min((int)floor(cd + 0.5), di - 1), zh = min((int)floor(ch + 0.5), hi - 1),
+                          zw = min((int)floor(cw + 0.5), wi - 1);
+                v = __ldg(src + ((long long)zd * hi + zh) * wi + zw);
+            } else {
+                const int d0 = (int)floor(cd), h0 = (int)floor(ch), w0 = (int)floor(cw);
+                const int d1 = min(d0 + 1, di - 1), h1 = min(h0 + 1, hi - 1), w1 = min(w0 + 1, wi - 1);
+                const float fd = (float)(cd - d0), fh = (float)(ch - h0), fw = (float)(cw - w0);
+                auto at = [&](int z, int y, int x) { return __ldg(src + ((long long)z * hi + y) * wi + x); };
+                const float c00 = at(d0, h0, w0) + fw * (at(d0, h0, w1) - at(d0, h0, w0));
+                const float c01 = at(d0, h1, w0) + fw * (at(d0, h1, w1) - at(d0, h1, w0));
+                const float c10 = at(d1, h0, w0) + fw * (at(d1, h0, w1) - at(d1, h0, w0));
+                const float c11 = at(d1, h1, w0) + fw * (at(d1, h1, w1) - at(d1, h1, w0));
+                const float c0 = c00 + fh * (c01 - c00), c1 = c10 + fh * (c11 - c10);
+                v = c0 + fd * (c1 - c0);
+            }
+        }
+        out[i] = binarize ? (v > 0.f ? 1.f : 0.f) : v;
+    }
+}
+cudaError_t launch_resample3d(const float* in, long long nvol, int di, int hi, int wi, float* out, int dout, int ho,
+                              int wo, int nearest, int binarize, int sms, cudaStream_t s) {
+    const long long total = nvol * dout * ho * wo;
+    if (total == 0) return cudaSuccess;
+    resample3d_kernel<<<grid_for(total, 256, sms, 16), 256, 0, s>>>(in, di, hi, wi, out, dout, ho, wo, nvol, nearest,
+                                                                   binarize);
+    return cudaGetLastError();
+}
+
+// per-volume min / max (order-preserving unsigned keys so that one atomicMin / atomicMax per block suffices)
+DEV uint32_t f2key(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+DEV float key2f(uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
+__global__ void minmax_init_kernel(uint32_t* keys, int nvol) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nvol) { keys[2 * i] = 0xffffffffu; keys[2 * i + 1] = 0u; }
+}
+__global__ void __launch_bounds__(256) minmax_reduce_kernel(const float* __restrict__ x, long long per, uint32_t* keys) {
+    const int vol = blockIdx.y;
+    const float* src = x + vol * per;
+    float lo = INFINITY, hi = -INFINITY;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per; i += (long long)gridDim.x * blockDim.x) {
+        const float v = __ldg(src + i);
+        lo = fminf(lo, v);
+        hi = fmaxf(hi, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(keys + 2 * vol, f2key(lo));
+        atomicMax(keys + 2 * vol + 1, f2key(hi));
+    }
+}
+__global__ void __launch_bounds__(256) minmax_apply_kernel(float* __restrict__ x, long long per,
+                                                           const uint32_t* __restrict__ keys) {
+    const int vol = blockIdx.y;
+    const float lo = key2f(keys[2 * vol]), hi = key2f(keys[2 * vol + 1]);
+    const bool flat = !(hi > lo);          // constant volume -> zeros (predict.py's division guard)
+    const float range = hi - lo;
+    float* dst = x + vol * per;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = flat ? 0.f : (dst[i] - lo) / range;
+}
+cudaError_t launch_minmax_normalize(float* x, long long nvol, long long per, uint32_t* keys, int sms, cudaStream_t s) {
+    if (nvol == 0 || per == 0) return cudaSuccess;
+    minmax_init_kernel<<<(int)((nvol + 127) / 128), 128, 0, s>>>(keys, (int)nvol);
+    int bx = grid_for(per, 256, sms, 8);
+    if (bx * nvol > (long long)sms * 16) bx = (int)((sms * 16 + nvol - 1) / nvol);
+    dim3 grid(bx, (unsigned)nvol);
+    minmax_reduce_kernel<<<grid, 256, 0, s>>>(x, per, keys);
+    minmax_apply_kernel<<<grid, 256, 0, s>>>(x, per, keys);
+    return cudaGetLastError();
+}
+
+// counts[sample][3] += (|pred & target|, |pred|, |target|) with pred = score > threshold, target = label > 0.5:
+// exact integer arithmetic (the reference sums 0/1 floats, which is exact up to 2^24 only)
+__global__ void __launch_bounds__(256) seg_counts_kernel(const float* __restrict__ score,
+                                                         const float* __restrict__ label, long long per,
+                                                         float threshold, unsigned long long* counts) {
+    const int smp = blockIdx.y;
+    const float* sc = score + smp * per;
+    const float* lb = label + smp * per;
+    unsigned int inter = 0, np = 0, nt = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per; i += (long long)gridDim.x * blockDim.x) {
+        const bool p = __ldg(sc + i) > threshold, t = __ldg(lb + i) > 0.5f;
+        inter += p && t;
+        np += p;
+        nt += t;
+    }
+    inter = __reduce_add_sync(0xffffffffu, inter);
+    np = __reduce_add_sync(0xffffffffu, np);
+    nt = __reduce_add_sync(0xffffffffu, nt);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(counts + 3 * smp, (unsigned long long)inter);
+        atomicAdd(counts + 3 * smp + 1, (unsigned long long)np);
+        atomicAdd(counts + 3 * smp + 2, (unsigned long long)nt);
+    }
+}
+cudaError_t launch_seg_counts(const float* score, const float* label, long long nsmp, long long per, float threshold,
+                              unsigned long long* counts, int sms, cudaStream_t s) {
+    if (nsmp == 0 || per == 0) return cudaSuccess;
+    int bx = grid_for(per, 256, sms, 8);
+    if (bx * nsmp > (long long)sms * 16) bx = (int)((sms * 16 + nsmp - 1) / nsmp);
+    if (bx < 1) bx = 1;
+    seg_counts_kernel<<<dim3(bx, (unsigned)nsmp), 256, 0, s>>>(score, label, per, threshold, counts);
+    return cudaGetLastError();
+}
+
 }  // namespace b200

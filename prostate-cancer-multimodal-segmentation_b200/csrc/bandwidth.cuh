@@ -70,5 +70,10 @@ cudaError_t launch_sumsq(const float* x, long long n, float* out, int sms, cudaS
 cudaError_t launch_fill_zero(View v, int sms, cudaStream_t s);
 cudaError_t launch_channel_sum(View v, float* out, cudaStream_t s);
 cudaError_t launch_unpack_act(View v, float* out, cudaStream_t s);
+cudaError_t launch_resample3d(const float* in, long long nvol, int di, int hi, int wi, float* out, int dout, int ho,
+                              int wo, int nearest, int binarize, int sms, cudaStream_t s);
+cudaError_t launch_minmax_normalize(float* x, long long nvol, long long per, uint32_t* keys, int sms, cudaStream_t s);
+cudaError_t launch_seg_counts(const float* score, const float* label, long long nsmp, long long per, float threshold,
+                              unsigned long long* counts, int sms, cudaStream_t s);
 
 }  // namespace b200

@@ -50,6 +50,23 @@ class SyntheticProstateDataset(Dataset):
         return {"image": img, "label": lab, "case_id": f"case_{c:04d}"}
 
 
+def resample_case(image, label, target_size):
+    """Device half of MultimodalDataset.__getitem__ (script/data_loader.py:294-419) for one case that is already in
+    CUDA memory: every modality is resampled to `target_size` (linear), the label with nearest-neighbour and then
+    binarised (> 0).  image (5, D, H, W) fp32, label (1, D', H', W') fp32 -> the reference's tensors at target_size.
+    Axis order is (D, H, W) throughout (the reference hands its (D,H,W) tuple to ITK's (x,y,z) SetSize, which only
+    agrees for cubic targets)."""
+    from . import ops
+    target_size = tuple(int(v) for v in target_size)
+    if tuple(image.shape[-3:]) != target_size:
+        image = ops.resample3d(image.float().contiguous(), target_size)
+    if tuple(label.shape[-3:]) != target_size:
+        label = ops.resample3d(label.float().contiguous(), target_size, nearest=True, binarize=True)
+    else:
+        label = (label > 0).float()
+    return image, label
+
+
 class DevicePrefetcher:
     """Iterates a loader of batch dicts and hands out the same dicts with their tensors on `device`.
 

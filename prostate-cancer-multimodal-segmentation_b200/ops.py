@@ -286,6 +286,53 @@ def channel_sum(v: ActView, out):
     check(_lib.load().b200_channel_sum(v.ref, ptr(out), stream_ptr()), "channel_sum")
 
 
+def _cuda_f32(t, what):
+    if not t.is_cuda:
+        raise _lib.B200Error(f"{what}: b200 kernels need CUDA tensors: there is no CPU path")
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise ValueError(f"{what}: expected a contiguous float32 tensor")
+
+
+def resample3d(x: torch.Tensor, size, nearest: bool = False, binarize: bool = False) -> torch.Tensor:
+    """(..., D, H, W) fp32 -> (..., *size): the reference loader's resample-to-target (script/data_loader.py:240-283
+    linear for images, :395-409 nearest + `> 0` for labels) with ITK's index mapping (see include/b200_unet3d.h)."""
+    _cuda_f32(x, "resample3d")
+    if x.dim() < 3:
+        raise ValueError(f"resample3d: expected at least 3 dimensions, got shape {tuple(x.shape)}")
+    d, h, w = x.shape[-3:]
+    nvol = x.numel() // max(1, d * h * w)
+    out = torch.empty(tuple(x.shape[:-3]) + tuple(int(v) for v in size), device=x.device, dtype=torch.float32)
+    _launched(1)
+    check(_lib.load().b200_resample3d(ptr(x), nvol, d, h, w, ptr(out), int(size[0]), int(size[1]), int(size[2]),
+                                      int(nearest), int(binarize), stream_ptr()), "resample3d")
+    return out
+
+
+def minmax_normalize_(x: torch.Tensor) -> torch.Tensor:
+    """in place, per leading index: (x - min) / (max - min) over the last three axes (script/predict.py:69-75)"""
+    _cuda_f32(x, "minmax_normalize_")
+    per = x.shape[-1] * x.shape[-2] * x.shape[-3]
+    nvol = x.numel() // max(1, per)
+    ws = torch.empty(2 * max(nvol, 1), device=x.device, dtype=torch.int32)
+    _launched(3)
+    check(_lib.load().b200_minmax_normalize(ptr(x), nvol, per, ptr(ws), stream_ptr()), "minmax_normalize")
+    return x
+
+
+def seg_counts(score: torch.Tensor, label: torch.Tensor, threshold: float = 0.5) -> torch.Tensor:
+    """(N, ...) scores and labels -> int64 (N, 3): |P & T|, |P|, |T| with P = score > threshold, T = label > 0.5"""
+    _cuda_f32(score, "seg_counts")
+    _cuda_f32(label, "seg_counts")
+    if score.shape != label.shape:
+        raise ValueError(f"seg_counts: score shape {tuple(score.shape)} != label shape {tuple(label.shape)}")
+    n = score.shape[0]
+    counts = torch.zeros(n, 3, device=score.device, dtype=torch.int64)
+    _launched(1)
+    check(_lib.load().b200_seg_counts(ptr(score), ptr(label), n, score.numel() // max(n, 1), float(threshold),
+                                      ptr(counts), stream_ptr()), "seg_counts")
+    return counts
+
+
 # ---- optional timeline (dev tool): CUDA events around every op on whatever stream it runs, to inspect cross-stream
 # overlap without an external profiler.  `timeline = []` switches it on; entries are (name, stream, start, end).
 timeline = None

@@ -119,18 +119,30 @@ def window_schedule(shape, window, stride):
     return sched, (wd, wh, ww)
 
 
+def rank_windows(sched, rank, world):
+    """this rank's share of the window schedule: a contiguous block, so that a rank touches as few volumes as possible
+    (one volume per rank when the volume count equals the world size: only that volume has to be uploaded there)"""
+    return sched[shard_batch(len(sched), rank, world)]
+
+
+def rank_volumes(shape, window, stride, rank, world):
+    """indices of the volumes this rank reads in sliding_window_logits"""
+    sched, _ = window_schedule(shape, window, stride)
+    return sorted({w[0] for w in rank_windows(sched, rank, world)})
+
+
 @torch.no_grad()
 def sliding_window_logits(model, x, window=(128, 128, 64), stride=(64, 64, 64), rank=0, world=1, group=None,
                           windows_per_launch=1, reduce=True):
-    """Average of window logits over a batch of volumes; with world > 1 every rank evaluates windows
-    rank, rank+world, ... and the partial sums are all-reduced.  x: (N, C, D, H, W) on this rank's GPU (every rank
-    holds the volumes; they are small next to the activations)."""
+    """Average of window logits over a batch of volumes; with world > 1 every rank evaluates its contiguous block of
+    the window schedule (rank_windows) and the partial sums are all-reduced.  x: (N, C, D, H, W) on this rank's GPU;
+    only the volumes named by rank_volumes() are read on this rank."""
     model.eval()
     n, _, D, H, W = x.shape
     sched, (wd, wh, ww) = window_schedule(x.shape, window, stride)
     acc = torch.zeros(n, model.n_classes, D, H, W, device=x.device, dtype=torch.float32)
     cnt = torch.zeros(n, 1, D, H, W, device=x.device, dtype=torch.float32)
-    mine = sched[rank::world]
+    mine = rank_windows(sched, rank, world)
     for i in range(0, len(mine), windows_per_launch):
         chunk = mine[i:i + windows_per_launch]
         xb = torch.stack([x[v, :, d0:d0 + wd, h0:h0 + wh, w0:w0 + ww] for (v, d0, h0, w0) in chunk])

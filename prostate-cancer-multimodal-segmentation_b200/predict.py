@@ -25,6 +25,12 @@ def normalize_modalities(image):
     return out
 
 
+def normalize_modalities_(image):
+    """same, in place on a CUDA tensor (M, D, H, W): one min/max reduction + one apply kernel for all modalities"""
+    from . import ops
+    return ops.minmax_normalize_(image)
+
+
 class ModelPredictor:
     def __init__(self, model_path, device="cuda", init_features=64):
         self.device = torch.device(device)

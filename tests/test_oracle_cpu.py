@@ -177,3 +177,32 @@ def test_flops_accounting(pkg):
     assert abs(fwd / 1e6 - 1.8245) < 2e-3 and abs(fb / 1e6 - 5.4563) < 5e-3
     fwd32, fb32 = eng.total_flops_per_voxel(32, 5, 1)
     assert abs(fwd32 / 1e6 - 0.4605) < 2e-3 and abs(fb32 / 1e6 - 1.3728) < 5e-3
+
+
+def test_resample_restatement_known_answers():
+    """hand-computed values of the ITK index mapping (i * in/out, clamp, outside -> 0) on a ramp"""
+    import numpy as np
+    x = np.arange(4, dtype=np.float32).reshape(1, 1, 4) * 10.0         # W axis ramp 0,10,20,30
+    up = oracle.resample3d_itk(x, (1, 1, 8))                            # continuous index 0,.5,...,3.5
+    assert np.allclose(up[0, 0], [0, 5, 10, 15, 20, 25, 30, 0])         # 3.5 >= 4 - 0.5 -> outside -> 0
+    down = oracle.resample3d_itk(x, (1, 1, 2))                          # index 0, 2
+    assert np.allclose(down[0, 0], [0, 20])
+    near = oracle.resample3d_itk(x, (1, 1, 8), nearest=True)            # round half up: 0,1,1,2,2,3,3,outside
+    assert np.allclose(near[0, 0], [0, 10, 10, 20, 20, 30, 30, 0])
+    third = oracle.resample3d_itk(x, (1, 1, 3))                         # index 0, 4/3, 8/3
+    assert np.allclose(third[0, 0], [0, 40 / 3, 80 / 3], atol=1e-5)
+    assert np.array_equal(oracle.resample3d_itk(x, (1, 1, 4)), x)
+    assert np.array_equal(oracle.resample3d_itk(x, (1, 1, 2), nearest=True, binarize=True)[0, 0], [0, 1])
+
+
+def test_metric_and_normalise_restatements():
+    import numpy as np
+    p = np.array([1, 1, 0, 0, 1], dtype=np.float32)
+    t = np.array([1, 0, 0, 1, 1], dtype=np.float32)
+    d, j = oracle.hard_dice_iou(p, t)
+    assert abs(d - (4 + 1e-8) / (6 + 1e-8)) < 1e-12 and abs(j - (2 + 1e-8) / (4 + 1e-8)) < 1e-12
+    d0, j0 = oracle.hard_dice_iou(np.zeros(4), np.zeros(4))             # both empty -> eps/eps = 1
+    assert d0 == 1.0 and j0 == 1.0
+    img = np.stack([np.array([[[2.0, 4.0, 6.0]]]), np.full((1, 1, 3), 7.0)]).astype(np.float32)
+    out = oracle.minmax_normalize(img)
+    assert np.allclose(out[0], [[[0, 0.5, 1]]]) and np.array_equal(out[1], np.zeros((1, 1, 3)))
