@@ -225,7 +225,7 @@ static DmPlan dmarch_plan(long long n, long long w, long long h, long long d, lo
     pl.grid = (int)(units < sms ? units : sms);
     return pl;
 }
-constexpr int kDmSmem = 1024 + kDmAStages * kDmABytes + kDmBStages * kDmBBytes + kBoxBytes +
+constexpr int kDmSmem = 1024 + kDmAStages * kDmAStageBytes + kDmBStages * kDmBBytes + kBoxBytes +
                         8 * (2 * kDmAStages + 2 * kDmBStages + 2 * kDmSlots) + 64 + (4 * 64 * 2 + 128 + 128) * 4;
 static int launch_dmarch(const b200_act* in, const void* w_packed, const b200_act* out, int sign, int mode,
                          const float* v0, const float* v1, float* stats, const DmPlan& pl, cudaStream_t s);

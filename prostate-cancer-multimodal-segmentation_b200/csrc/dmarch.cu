@@ -25,7 +25,7 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) dmarch_kernel(const __
     const int lane = threadIdx.x & 31;
 
     const uint32_t smem_a = smem_base;
-    const uint32_t smem_b = smem_a + kDmAStages * kDmABytes;
+    const uint32_t smem_b = smem_a + kDmAStages * kDmAStageBytes;
     const uint32_t smem_c = smem_b + kDmBStages * kDmBBytes;   // 16 KB output staging tile
     const uint32_t bar_base = smem_c + kBoxBytes;
     auto afull = [&](uint32_t s) { return bar_base + 8 * s; };
@@ -86,15 +86,17 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) dmarch_kernel(const __
             decode(unit, nb, w0, h0, ds, de);
             if (ds >= de) continue;
             const int z0 = max(ds - 1, 0), z1 = min(de, p.D - 1);
-            for (int dz = z0; dz <= z1; ++dz) {
+            for (int dz = z0; dz <= z1; dz += kDmG) {
+                const int nin = min(kDmG, z1 - dz + 1);   // input slices that share this pass over the weights
                 for (int kw = 0; kw < 3; ++kw) {
                     for (int kc = 0; kc < kc_blocks; ++kc) {
                         mbar_wait(aempty(ra.stage), ra.phase ^ 1);
                         if (elect_one()) {
                             const uint32_t fb = afull(ra.stage);
-                            mbar_arrive_expect_tx(fb, kDmABytes);
-                            tma_load_5d(smem_a + ra.stage * kDmABytes, &p.a_map, fb, kc * 64, w0 + sign * (kw - 1),
-                                        h0 - 1, dz, nb);
+                            mbar_arrive_expect_tx(fb, nin * kDmABytes);
+                            for (int si = 0; si < nin; ++si)
+                                tma_load_5d(smem_a + ra.stage * kDmAStageBytes + si * kDmABytes, &p.a_map, fb, kc * 64,
+                                            w0 + sign * (kw - 1), h0 - 1, dz + si, nb);
                         }
                         __syncwarp();
                         ra.advance(kDmAStages);
@@ -143,74 +145,92 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) dmarch_kernel(const __
             decode(unit, nb, w0, h0, ds, de);
             if (ds >= de) continue;
             const int z0 = max(ds - 1, 0), z1 = min(de, p.D - 1);
-            for (int dz = z0; dz <= z1; ++dz) {
-                // slabs j (output slice d = dz - 1 + j) that belong to this unit
-                const int jlo = max(0, ds - (dz - 1)), jhi = min(2, (de - 1) - (dz - 1));
-                uint32_t tm[3], acc0[3];
+            for (int dz0 = z0; dz0 <= z1; dz0 += kDmG) {
+                // kDmG consecutive input slices share one pass over the 27 tap weights (the B stream, 216 KB per
+                // pass and channel block, is the larger half of the shared-memory fill traffic of this kernel)
+                const int nin = min(kDmG, z1 - dz0 + 1);
+                uint32_t tm[kDmG][3], acc0[kDmG][3];
+                int jlo[kDmG], jhi[kDmG];
+                uint32_t r_tm0[kDmG], r_bo0[kDmG], r_id0[kDmG], r_tm1[kDmG], r_bo1[kDmG], r_id1[kDmG];
+                bool two[kDmG];
 #pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    const int d = dz - 1 + j;
-                    const uint32_t u = ubase + (uint32_t)(d - ds);
-                    const uint32_t sl = u % kDmSlots;
-                    tm[j] = tmem_base + sl * 64;
-                    const bool fresh = (j >= jlo && j <= jhi) && (dz == max(d - 1, 0));
-                    acc0[j] = fresh ? 0u : 1u;
-                    if (fresh) mbar_wait(tempty(sl), ((u / kDmSlots) & 1) ^ 1);  // previous use drained
-                }
-                tc_fence_after();
-                // regular k-steps: one MMA over all slabs, or two when the ring wraps inside the window
-                const uint32_t tm_lo = jlo == 0 ? tm[0] : (jlo == 1 ? tm[1] : tm[2]);
-                uint32_t r_tm0 = tm_lo, r_bo0 = jlo * (8192u >> 4), r_id0 = idesc0 | ((uint32_t)(jhi - jlo + 1) << 20);
-                uint32_t r_tm1 = 0, r_bo1 = 0, r_id1 = 0;
-                bool two = false;
+                for (int si = 0; si < kDmG; ++si) {
+                    const int dz = dz0 + si;
+                    // slabs j (output slice d = dz - 1 + j) that belong to this unit
+                    jlo[si] = max(0, ds - (dz - 1));
+                    jhi[si] = min(2, (de - 1) - (dz - 1));
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    if (j >= jlo && j < jhi && tm[j + 1] != tm[j] + 64) {
-                        two = true;
-                        r_id0 = idesc0 | ((uint32_t)(j + 1 - jlo) << 20);
-                        r_tm1 = tm[j + 1];
-                        r_bo1 = (j + 1) * (8192u >> 4);
-                        r_id1 = idesc0 | ((uint32_t)(jhi - j) << 20);
+                    for (int j = 0; j < 3; ++j) {
+                        const int d = dz - 1 + j;
+                        const uint32_t u = ubase + (uint32_t)(d - ds);
+                        const uint32_t sl = u % kDmSlots;
+                        tm[si][j] = tmem_base + sl * 64;
+                        const bool fresh = si < nin && (j >= jlo[si] && j <= jhi[si]) && (dz == max(d - 1, 0));
+                        acc0[si][j] = fresh ? 0u : 1u;
+                        if (fresh) mbar_wait(tempty(sl), ((u / kDmSlots) & 1) ^ 1);  // previous use drained
+                    }
+                    // regular k-steps: one MMA over all slabs, or two when the ring wraps inside the window
+                    const int lo = jlo[si], hi = jhi[si];
+                    const uint32_t tm_lo = lo == 0 ? tm[si][0] : (lo == 1 ? tm[si][1] : tm[si][2]);
+                    r_tm0[si] = tm_lo; r_bo0[si] = lo * (8192u >> 4); r_id0[si] = idesc0 | ((uint32_t)(hi - lo + 1) << 20);
+                    r_tm1[si] = 0; r_bo1[si] = 0; r_id1[si] = 0;
+                    two[si] = false;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        if (j >= lo && j < hi && tm[si][j + 1] != tm[si][j] + 64) {
+                            two[si] = true;
+                            r_id0[si] = idesc0 | ((uint32_t)(j + 1 - lo) << 20);
+                            r_tm1[si] = tm[si][j + 1];
+                            r_bo1[si] = (j + 1) * (8192u >> 4);
+                            r_id1[si] = idesc0 | ((uint32_t)(hi - j) << 20);
+                        }
                     }
                 }
+                tc_fence_after();
                 bool first = true;
                 for (int kw = 0; kw < 3; ++kw) {
                     for (int kc = 0; kc < kc_blocks; ++kc) {
                         const int nk = (kc == kc_blocks - 1) ? nk_last : 4;
                         mbar_wait(afull(ra.stage), ra.phase);
-                        const uint32_t a_st = a_lo0 + ra.stage * (kDmABytes >> 4);
+                        const uint32_t a_st = a_lo0 + ra.stage * (kDmAStageBytes >> 4);
                         for (int kh = 0; kh < 3; ++kh) {
                             mbar_wait(bfull(rb.stage), rb.phase);
                             tc_fence_after();
                             if (elect_one()) {
-                                // tap kh reads the halo box at row offset kh (fprop) or 2 - kh (dgrad): 8 rows = 1 KB
-                                const uint32_t a_lo = a_st + (uint32_t)((sign > 0 ? kh : 2 - kh) * (1024 >> 4));
                                 const uint32_t b_lo = b_lo0 + rb.stage * (kDmBBytes >> 4);
-                                int k0 = 0;
-                                if (first) {
-                                    // first k-step of the slice: per-slab MMAs (a fresh slab must not accumulate)
 #pragma unroll
-                                    for (int j = 0; j < 3; ++j)
-                                        if (j >= jlo && j <= jhi)
-                                            umma_f16_lohi(tm[j], a_lo, a_hi, b_lo + j * (8192u >> 4), b_hi, idesc64,
-                                                          acc0[j]);
-                                    k0 = 1;
-                                }
-                                if (!two) {
+                                for (int si = 0; si < kDmG; ++si) {
+                                    if (si < nin && jlo[si] <= jhi[si]) {
+                                        // tap kh reads the halo box at row offset kh (fprop) or 2 - kh (dgrad): 8 rows = 1 KB
+                                        const uint32_t a_lo = a_st + si * (kDmABytes >> 4) +
+                                                              (uint32_t)((sign > 0 ? kh : 2 - kh) * (1024 >> 4));
+                                        int k0 = 0;
+                                        if (first) {
+                                            // first k-step of the slice: per-slab MMAs (a fresh slab must not accumulate)
 #pragma unroll
-                                    for (int k = 0; k < 4; ++k)
-                                        if (k >= k0 && k < nk)
-                                            umma_f16_lohi(r_tm0, a_lo + 2 * k, a_hi, b_lo + r_bo0 + k * kinc_b, b_hi,
-                                                          r_id0, 1u);
-                                } else {
-#pragma unroll
-                                    for (int k = 0; k < 4; ++k)
-                                        if (k >= k0 && k < nk) {
-                                            umma_f16_lohi(r_tm0, a_lo + 2 * k, a_hi, b_lo + r_bo0 + k * kinc_b, b_hi,
-                                                          r_id0, 1u);
-                                            umma_f16_lohi(r_tm1, a_lo + 2 * k, a_hi, b_lo + r_bo1 + k * kinc_b, b_hi,
-                                                          r_id1, 1u);
+                                            for (int j = 0; j < 3; ++j)
+                                                if (j >= jlo[si] && j <= jhi[si])
+                                                    umma_f16_lohi(tm[si][j], a_lo, a_hi, b_lo + j * (8192u >> 4), b_hi,
+                                                                  idesc64, acc0[si][j]);
+                                            k0 = 1;
                                         }
+                                        if (!two[si]) {
+#pragma unroll
+                                            for (int k = 0; k < 4; ++k)
+                                                if (k >= k0 && k < nk)
+                                                    umma_f16_lohi(r_tm0[si], a_lo + 2 * k, a_hi,
+                                                                  b_lo + r_bo0[si] + k * kinc_b, b_hi, r_id0[si], 1u);
+                                        } else {
+#pragma unroll
+                                            for (int k = 0; k < 4; ++k)
+                                                if (k >= k0 && k < nk) {
+                                                    umma_f16_lohi(r_tm0[si], a_lo + 2 * k, a_hi,
+                                                                  b_lo + r_bo0[si] + k * kinc_b, b_hi, r_id0[si], 1u);
+                                                    umma_f16_lohi(r_tm1[si], a_lo + 2 * k, a_hi,
+                                                                  b_lo + r_bo1[si] + k * kinc_b, b_hi, r_id1[si], 1u);
+                                                }
+                                        }
+                                    }
                                 }
                                 umma_commit(bempty(rb.stage));
                             }
@@ -223,12 +243,12 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) dmarch_kernel(const __
                         ra.advance(kDmAStages);
                     }
                 }
-                // output slices whose last contribution was this input slice are complete
+                // output slices whose last contribution came from one of these input slices are complete
                 if (elect_one()) {
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) {
-                        const int d = dz - 1 + j;
-                        if (j >= jlo && j <= jhi && dz == min(d + 1, p.D - 1)) {
+                    const int dlo = max(ds, dz0 - 1), dhi = min(de - 1, dz0 + nin);
+                    for (int d = dlo; d <= dhi; ++d) {
+                        const int last = min(d + 1, p.D - 1);
+                        if (last >= dz0 && last < dz0 + nin) {
                             const uint32_t u = ubase + (uint32_t)(d - ds);
                             umma_commit(tfull(u % kDmSlots));
                         }
