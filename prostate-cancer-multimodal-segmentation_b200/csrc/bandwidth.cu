@@ -826,8 +826,79 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(View x, const float* __re
         }
     }
 }
+// Coalesced form for power-of-two channel counts (c/8 lanes per voxel, 16 bytes per lane: a warp reads whole 128-byte
+// lines; the one-thread-per-voxel kernel above touches 32 lines per load instruction and ran at ~1.1 TB/s in the step).
+// Four voxels per thread are in flight; the class dot products are reduced across the c/8 lanes with shuffles.
+template <int NCLS>
+__global__ void __launch_bounds__(256) head_fwd_vec_kernel(View x, const float* __restrict__ w,
+                                                           const float* __restrict__ b, float* logits, float* probs,
+                                                           int c8, long long nvox, long long nvox_per_n) {
+    constexpr int U = 4;
+    const int rows = 256 / c8, g = threadIdx.x / c8, cv = threadIdx.x - g * c8;
+    const int c = (int)x.c;
+    float wk[NCLS][8], bk[NCLS];
+#pragma unroll
+    for (int k = 0; k < NCLS; ++k) {
+        ldf8(w + k * c + cv * 8, wk[k]);
+        bk[k] = __ldg(b + k);
+    }
+    const long long step = (long long)gridDim.x * rows * U;
+    for (long long v0 = (long long)blockIdx.x * rows * U; v0 < nvox; v0 += step) {
+        Bf8 a[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long v = v0 + u * rows + g;
+            ok[u] = v < nvox;
+            if (ok[u]) a[u] = ld8_stream(x.p + v * x.ld + cv * 8);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            float f[8];
+            if (ok[u]) unpack8(a[u], f);
+            float acc[NCLS];
+#pragma unroll
+            for (int k = 0; k < NCLS; ++k) {
+                acc[k] = 0.f;
+                if (ok[u]) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[k] = fmaf(f[j], wk[k][j], acc[k]);
+                }
+                for (int o = c8 >> 1; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+            }
+            if (ok[u] && cv == 0) {
+                const long long v = v0 + u * rows + g;
+                const long long nb = v / nvox_per_n, sp = v - nb * nvox_per_n;
+#pragma unroll
+                for (int k = 0; k < NCLS; ++k) {
+                    const float z = acc[k] + bk[k];
+                    const long long o = (nb * NCLS + k) * nvox_per_n + sp;
+                    logits[o] = z;
+                    if (probs) probs[o] = 1.f / (1.f + __expf(-z));
+                }
+            }
+        }
+    }
+}
+template <int NCLS>
+static cudaError_t head_fwd_vec_launch(View x, const float* w, const float* b, float* logits, float* probs,
+                                       cudaStream_t s) {
+    const int c8 = (int)(x.c / 8);
+    const long long nvox = x.voxels();
+    long long blocks = (nvox + (256 / c8) * 4 - 1) / ((256 / c8) * 4);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    head_fwd_vec_kernel<NCLS><<<(int)blocks, 256, 0, s>>>(x, w, b, logits, probs, c8, nvox, x.d * x.h * x.w);
+    return cudaGetLastError();
+}
 cudaError_t launch_head_fwd(View x, const float* w, const float* b, int ncls, float* logits, float* probs,
                             cudaStream_t s) {
+    const long long c8 = x.c / 8;
+    if (x.c % 8 == 0 && c8 >= 1 && c8 <= 32 && (c8 & (c8 - 1)) == 0 && ncls <= 2) {
+        // summation order differs from the scalar kernel only in the grouping of the fp32 partial dot products
+        return ncls == 1 ? head_fwd_vec_launch<1>(x, w, b, logits, probs, s)
+                         : head_fwd_vec_launch<2>(x, w, b, logits, probs, s);
+    }
     head_fwd_kernel<<<grid_for(x.voxels(), 256, 148, 16), 256, 0, s>>>(x, w, b, ncls, logits, probs,
                                                                       x.d * x.h * x.w);
     return cudaGetLastError();
