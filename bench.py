@@ -326,6 +326,10 @@ def main():
     final_loss = loss.item()
 
     # ---- end to end through the public API with host buffers (`e2e`)
+    # warm the staging path (device slots of the prefetcher, copy stream) like the compute path: untimed steps
+    prefetcher = pkg.data.DevicePrefetcher([], dev)
+    for batch in prefetcher.over([{"image": x_host, "label": y_host}] * max(2, min(args.warmup, 3))):
+        step(batch["image"], batch["label"])
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_host0 = time.perf_counter()
@@ -334,7 +338,7 @@ def main():
     # data.DevicePrefetcher, which issues the copy of step i+1 on a copy stream under the kernels of step i
     host_batches = [{"image": x_host, "label": y_host}] * args.steps
     losses = pkg.data.AsyncScalarReader()  # every step's loss comes back to the host, read one step late
-    for batch in pkg.data.DevicePrefetcher(host_batches, dev):
+    for batch in prefetcher.over(host_batches):
         losses.push(step(batch["image"], batch["label"]))
     e2e_losses = losses.finish()
     e3.record()

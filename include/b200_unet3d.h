@@ -98,10 +98,12 @@ int b200_convt2x_wgrad(const b200_act* x, const b200_act* dy, int pad_d, int pad
 
 /* ---- BatchNorm3d + ReLU (models/unet3d.py:31-33,37-39) -------------------------------------------------- */
 /* reduce conv-epilogue partials; train-mode batch statistics, running-stat update (momentum, unbiased var),
- * scale = gamma*rstd, shift = beta - mean*scale.  running_* may be NULL. */
+ * scale = gamma*rstd, shift = beta - mean*scale.  running_* may be NULL.  num_batches_tracked (int64, nullable) is
+ * incremented by one in the same launch (nn.BatchNorm3d's counter). */
 int b200_bn_finalize(const float* stats_partial, int64_t rows, int64_t count, int c, const float* gamma,
                      const float* beta, float eps, float momentum, float* running_mean, float* running_var,
-                     float* mean, float* rstd, float* scale, float* shift, void* stream);
+                     int64_t* num_batches_tracked, float* mean, float* rstd, float* scale, float* shift,
+                     void* stream);
 /* eval mode: scale = gamma/sqrt(rv+eps), shift = beta + (conv_bias - rm)*scale */
 int b200_bn_fold_eval(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                       const float* conv_bias, float eps, int c, float* scale, float* shift, void* stream);

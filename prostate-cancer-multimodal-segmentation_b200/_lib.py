@@ -43,7 +43,7 @@ SIGNATURES = {
     "b200_convt2x_fwd": (_i32, [_AP, _vp, _vp, _AP, _i32, _i32, _i32, _vp]),
     "b200_convt2x_dgrad": (_i32, [_AP, _i32, _i32, _i32, _vp, _AP, _vp]),
     "b200_convt2x_wgrad": (_i32, [_AP, _AP, _i32, _i32, _i32, _vp, _vp]),
-    "b200_bn_finalize": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200_bn_finalize": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200_bn_fold_eval": (_i32, [_vp, _vp, _vp, _vp, _vp, _f32, _i32, _vp, _vp, _vp]),
     "b200_bn_apply_relu": (_i32, [_AP, _vp, _vp, _AP, _vp]),
     "b200_bn_bwd_max_blocks": (_i32, []),

@@ -810,12 +810,13 @@ extern "C" int b200_pack_convt_weight(const float* w, const float* bias, int cin
 }
 extern "C" int b200_bn_finalize(const float* stats_partial, int64_t rows, int64_t count, int c, const float* gamma,
                                 const float* beta, float eps, float momentum, float* running_mean,
-                                float* running_var, float* mean, float* rstd, float* scale, float* shift,
-                                void* stream) {
+                                float* running_var, int64_t* num_batches_tracked, float* mean, float* rstd,
+                                float* scale, float* shift, void* stream) {
     REQUIRE(stats_partial && gamma && beta && mean && rstd && scale && shift && rows > 0 && count > 0 && c > 0,
             "bn_finalize: bad arguments");
     CUDA_TRY(launch_bn_finalize(stats_partial, rows, count, c, gamma, beta, eps, momentum, running_mean, running_var,
-                                mean, rstd, scale, shift, (cudaStream_t)stream));
+                                reinterpret_cast<long long*>(num_batches_tracked), mean, rstd, scale, shift,
+                                (cudaStream_t)stream));
     return 0;
 }
 extern "C" int b200_bn_fold_eval(const float* gamma, const float* beta, const float* running_mean,

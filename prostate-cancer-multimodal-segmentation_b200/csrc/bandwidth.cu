@@ -356,9 +356,10 @@ __global__ void __launch_bounds__(32 * kRedSlices) bn_finalize_kernel(const floa
                                                           double inv_count, double unbias, int c,
                                                           const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, float eps, float momentum,
-                                                          float* rm, float* rv, float* mean, float* rstd, float* scale,
-                                                          float* shift) {
+                                                          float* rm, float* rv, long long* nbt, float* mean,
+                                                          float* rstd, float* scale, float* shift) {
     __shared__ double red[kRedSlices][32][2];
+    if (nbt && blockIdx.x == 0 && threadIdx.x == 0) nbt[0] += 1;   // num_batches_tracked
     const int ch = blockIdx.x * 32 + (threadIdx.x & 31), slice = threadIdx.x >> 5;
     double s, q;
     reduce_partials(partial, rows, c, ch, slice, red, s, q);
@@ -377,11 +378,11 @@ __global__ void __launch_bounds__(32 * kRedSlices) bn_finalize_kernel(const floa
     if (rv) rv[ch] = (1.f - momentum) * rv[ch] + momentum * (float)(var * unbias);
 }
 cudaError_t launch_bn_finalize(const float* partial, long long rows, long long count, int c, const float* gamma,
-                               const float* beta, float eps, float momentum, float* rm, float* rv, float* mean,
-                               float* rstd, float* scale, float* shift, cudaStream_t s) {
+                               const float* beta, float eps, float momentum, float* rm, float* rv, long long* nbt,
+                               float* mean, float* rstd, float* scale, float* shift, cudaStream_t s) {
     const double unbias = count > 1 ? (double)count / (double)(count - 1) : 1.0;
     bn_finalize_kernel<<<(c + 31) / 32, 32 * kRedSlices, 0, s>>>(partial, (int)rows, 1.0 / (double)count, unbias, c, gamma, beta,
-                                                    eps, momentum, rm, rv, mean, rstd, scale, shift);
+                                                    eps, momentum, rm, rv, nbt, mean, rstd, scale, shift);
     return cudaGetLastError();
 }
 

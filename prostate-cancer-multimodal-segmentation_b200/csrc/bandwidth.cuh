@@ -41,8 +41,8 @@ cudaError_t launch_pack_conv_weight(const float* w, int cout, int cin, int cin_p
 cudaError_t launch_pack_convt_weight(const float* w, const float* bias, int cin, int cout, __nv_bfloat16* wf,
                                      __nv_bfloat16* wd, float* bias8, cudaStream_t s);
 cudaError_t launch_bn_finalize(const float* partial, long long m_tiles, long long count, int c, const float* gamma,
-                               const float* beta, float eps, float momentum, float* rm, float* rv, float* mean,
-                               float* rstd, float* scale, float* shift, cudaStream_t s);
+                               const float* beta, float eps, float momentum, float* rm, float* rv, long long* nbt,
+                               float* mean, float* rstd, float* scale, float* shift, cudaStream_t s);
 cudaError_t launch_bn_fold_eval(const float* gamma, const float* beta, const float* rm, const float* rv,
                                 const float* cbias, float eps, int c, float* scale, float* shift, cudaStream_t s);
 cudaError_t launch_bn_apply_relu(View y, const float* scale, const float* shift, View out, int sms, cudaStream_t s);

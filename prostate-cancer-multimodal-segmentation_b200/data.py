@@ -89,6 +89,12 @@ class DevicePrefetcher:
     def __len__(self):
         return len(self.loader)
 
+    def over(self, loader):
+        """iterate another loader through the same staging buffers and copy stream (e.g. one object per trainer,
+        re-used for every epoch's loader)"""
+        self.loader = loader
+        return self
+
     def _stage(self, batch, i):
         out = dict(batch)
         slot, pinned = self._slots[i], self._pinned[i]

@@ -157,14 +157,18 @@ class _DoubleConv:
         pack.fprop(xin, pack.conv.bias.data, y, stats, ops.EPI_BIAS_STATS)
         vec = torch.empty(4, cout, device=dev, dtype=torch.float32)  # mean, rstd, scale, shift
         momentum = bn.momentum
+        nbt = None
         if bn.track_running_stats:
-            bn.num_batches_tracked.add_(1)
-            if momentum is None:  # cumulative moving average, as torch
+            if momentum is None:  # cumulative moving average, as torch: needs the count on the host
+                bn.num_batches_tracked.add_(1)
                 momentum = 1.0 / float(bn.num_batches_tracked.item())
+            else:
+                nbt = bn.num_batches_tracked  # incremented inside the finalize launch
         ops.bn_finalize(stats, rows, n * d * h * w, cout, bn.weight.data, bn.bias.data, bn.eps,
                         momentum if momentum is not None else 0.0,
                         bn.running_mean if bn.track_running_stats else None,
-                        bn.running_var if bn.track_running_stats else None, vec[0], vec[1], vec[2], vec[3])
+                        bn.running_var if bn.track_running_stats else None, vec[0], vec[1], vec[2], vec[3],
+                        num_batches_tracked=nbt)
         ops.bn_apply_relu(y, vec[2], vec[3], out)
         return y, vec
 

@@ -186,11 +186,13 @@ def convt2x_wgrad(x: ActView, dy: ActView, pads, dw: torch.Tensor):
 
 
 def bn_finalize(stats, rows, count, c, gamma, beta, eps, momentum, running_mean, running_var, mean, rstd, scale,
-                shift):
+                shift, num_batches_tracked=None):
     _launched(1)
+    if num_batches_tracked is not None:
+        assert num_batches_tracked.dtype == torch.int64 and num_batches_tracked.is_cuda
     check(_lib.load().b200_bn_finalize(ptr(stats), rows, count, c, ptr(gamma), ptr(beta), eps, momentum,
-                                       ptr(running_mean), ptr(running_var), ptr(mean), ptr(rstd), ptr(scale),
-                                       ptr(shift), stream_ptr()), "bn_finalize")
+                                       ptr(running_mean), ptr(running_var), ptr(num_batches_tracked), ptr(mean),
+                                       ptr(rstd), ptr(scale), ptr(shift), stream_ptr()), "bn_finalize")
 
 
 def bn_fold_eval(gamma, beta, running_mean, running_var, conv_bias, eps, scale, shift):

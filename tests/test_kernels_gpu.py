@@ -214,7 +214,10 @@ def test_batchnorm_relu_fwd_bwd(ops, cuda_dev, shape):
         torch.stack([half.sum((0, 2, 3, 4)), (half * half).sum((0, 2, 3, 4))], -1),
         torch.stack([rest.sum((0, 2, 3, 4)), (rest * rest).sum((0, 2, 3, 4))], -1)]).float().contiguous()
     mean, rstd, scale, shift = (torch.empty(c, device=cuda_dev) for _ in range(4))
-    ops.bn_finalize(stats, 2, count, c, gamma, beta, 1e-5, 0.1, rm, rv, mean, rstd, scale, shift)
+    nbt = torch.tensor(41, device=cuda_dev, dtype=torch.int64)
+    ops.bn_finalize(stats, 2, count, c, gamma, beta, 1e-5, 0.1, rm, rv, mean, rstd, scale, shift,
+                    num_batches_tracked=nbt)
+    assert nbt.item() == 42          # nn.BatchNorm3d's counter, incremented inside the launch
     yv = to_act(ops, y)
     av = empty_act(ops, n, c, d, h, w, cuda_dev)
     ops.bn_apply_relu(yv, scale, shift, av)
