@@ -181,6 +181,11 @@ int b200_minmax_normalize(float* x, int64_t nvol, int64_t voxels_per_volume, voi
 int b200_seg_counts(const float* score, const float* label, int64_t nsamples, int64_t voxels_per_sample,
                     float threshold, int64_t* counts, void* stream);
 
+/* routing queries (instrumentation): 3x3x3 conv fprop / dgrad -> 0 igemm_kernel, 1 dmarch_kernel (64 output columns on
+ * 8 x 16 bricks); weight gradient -> 0 wgrad_kernel, 1 wgrad_halo_kernel (w >= 8 and h >= 16) */
+int b200_conv3d_kernel_id(int64_t n, int64_t d, int64_t h, int64_t w, int64_t out_cols);
+int b200_conv3d_wgrad_kernel_id(int64_t h, int64_t w);
+
 /* dev probe (not on the hot path): cycles for `iters` x 4 tcgen05.mma (M=128, N=n, K=16, SS mode) per CTA, operands
  * cycling through `stages` shared-memory slots; out_cycles[blocks] (int64) */
 int b200_probe_mma(int n, int iters, int stages, long long* out_cycles, int blocks, void* stream);

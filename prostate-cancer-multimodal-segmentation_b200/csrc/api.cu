@@ -1003,3 +1003,11 @@ extern "C" int b200_seg_counts(const float* score, const float* label, int64_t n
                                reinterpret_cast<unsigned long long*>(counts), sms, (cudaStream_t)stream));
     return 0;
 }
+
+// which kernel a 3x3x3 conv call is routed to (bench.py labels its per-launch timings with the kernel that ran)
+extern "C" int b200_conv3d_kernel_id(int64_t n, int64_t d, int64_t h, int64_t w, int64_t out_cols) {
+    return dmarch_plan(n, w, h, d, out_cols, 27).use ? 1 : 0;   // 0: igemm_kernel, 1: dmarch_kernel
+}
+extern "C" int b200_conv3d_wgrad_kernel_id(int64_t h, int64_t w) {
+    return (w >= 8 && h >= 16) ? 1 : 0;                           // 0: wgrad_kernel, 1: wgrad_halo_kernel
+}

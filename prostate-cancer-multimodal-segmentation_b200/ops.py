@@ -142,24 +142,33 @@ def conv3d_stat_rows(n, d, h, w, cout, ntaps=27) -> int:
     return r
 
 
+def _conv_kernel(lib, v: ActView, out_cols: int) -> str:
+    """name of the kernel a 3x3x3 conv over view v is routed to (only asked for when a profile hook is installed)"""
+    if profile_hook is None:
+        return "igemm_kernel"
+    n, d, h, w, _ = v.shape
+    return "dmarch_kernel" if lib.b200_conv3d_kernel_id(n, d, h, w, out_cols) else "igemm_kernel"
+
+
 def conv3d_fprop(x: ActView, w_fprop, bias, y: ActView, stats=None, mode=EPI_BIAS_STATS, scale=None, shift=None,
                  k_real=None):
     lib = _lib.load()
-    _gemm("igemm_kernel", "conv3d_fprop", 2.0 * x.voxels * y.c * (k_real or x.c) * 27,
+    _gemm(_conv_kernel(lib, x, y.c), "conv3d_fprop", 2.0 * x.voxels * y.c * (k_real or x.c) * 27,
           lambda: check(lib.b200_conv3d_fprop(x.ref, ptr(w_fprop), ptr(bias), y.ref, ptr(stats), mode, ptr(scale),
                                               ptr(shift), stream_ptr()), "conv3d_fprop"))
 
 
 def conv3d_dgrad(dy: ActView, w_packed, dx: ActView):
     lib = _lib.load()
-    _gemm("igemm_kernel", "conv3d_dgrad", 2.0 * dy.voxels * dy.c * dx.c * 27,
+    _gemm(_conv_kernel(lib, dy, dx.c), "conv3d_dgrad", 2.0 * dy.voxels * dy.c * dx.c * 27,
           lambda: check(lib.b200_conv3d_dgrad(dy.ref, ptr(w_packed), dx.ref, stream_ptr()), "conv3d_dgrad"))
 
 
 def conv3d_wgrad(x: ActView, dy: ActView, dw: torch.Tensor, cin_real: int, packed: bool = False):
     """dw (+=): torch's (Cout, Cin, 3, 3, 3), or with packed=True the engine's physical [27][Cout][Cin] buffer"""
     lib = _lib.load()
-    _gemm("wgrad_kernel", "conv3d_wgrad", 2.0 * x.voxels * dy.c * cin_real * 27,
+    kern = "wgrad_halo_kernel" if profile_hook and lib.b200_conv3d_wgrad_kernel_id(x.shape[2], x.shape[3]) else "wgrad_kernel"
+    _gemm(kern, "conv3d_wgrad", 2.0 * x.voxels * dy.c * cin_real * 27,
           lambda: check(lib.b200_conv3d_wgrad(x.ref, dy.ref, ptr(dw), cin_real, 1 if packed else 0, stream_ptr()),
                         "conv3d_wgrad"))
 

@@ -1,0 +1,21 @@
+#!/bin/bash
+# Runs ON THE GPU BOX (gpurun -- 'bash tools/collect_profiles.sh TAG'): bench lines, ncu launch list, one ncu --set full
+# capture per GEMM kernel, CUDA-event timeline.  Everything lands in gpurun_out/; tools/summarize_profiles.py (run in
+# the build container) turns it into the tracked summaries under profiles/.
+TAG=${1:-r1}
+O=gpurun_out
+mkdir -p $O
+python bench.py --dump-kernels $O/${TAG}_gemm_launches.txt > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err
+python bench.py --impl reference --steps 3 --warmup 1 > $O/${TAG}_bench_reference_arm.json 2> $O/${TAG}_bench_reference_arm.err
+python bench.py --workload infer --steps 5 > $O/${TAG}_bench_infer.json 2> $O/${TAG}_bench_infer.err
+python tools/timeline_step.py $O/${TAG}_timeline_events.txt > $O/${TAG}_timeline.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $O/${TAG}_launches.csv \
+    python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-profile-pass > $O/${TAG}_ncu_list.log 2>&1
+# one full capture per GEMM kernel; launch indices pick the big full-resolution layers of the second step
+for spec in "igemm_kernel:45:igemm" "dmarch_kernel:6:dmarch" "wgrad_halo_kernel:15:wgrad_halo"; do
+    IFS=: read -r kern skip name <<< "$spec"
+    ncu --set full --clock-control none --import-source on --kernel-name $kern --launch-skip $skip --launch-count 2 \
+        -f -o $O/${TAG}_prof_${name} python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-profile-pass \
+        > $O/${TAG}_ncu_${name}.log 2>&1
+done
+ls -la $O | tail -20
