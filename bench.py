@@ -389,7 +389,9 @@ def main():
         except Exception:
             pass
         roofline = {"bound": "tensor", "kernel": top, "achieved": round(achieved, 2), "peak": peak,
-                    "unit": "TFLOP/s", "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                    "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
+                    "traffic": traffic.get("dram_bytes") if isinstance(traffic, dict) else None,
+                    "traffic_detail": traffic, "peak_source": peak_src,
                     "avg_launch_ms": round(a["ms"] / a["launches"], 4),
                     "algorithmic_flops_per_launch": a["flops"] / a["launches"],
                     "gemm_share_of_step": round(sum(v["ms"] for v in agg.values()) / ms_step, 3),

@@ -12,9 +12,11 @@ python tools/timeline_step.py $O/${TAG}_timeline_events.txt > $O/${TAG}_timeline
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $O/${TAG}_launches.csv \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-profile-pass > $O/${TAG}_ncu_list.log 2>&1
 # one full capture per GEMM kernel; launch indices pick the big full-resolution layers of the second step
-for spec in "igemm_kernel:45:igemm" "dmarch_kernel:6:dmarch" "wgrad_halo_kernel:15:wgrad_halo"; do
-    IFS=: read -r kern skip name <<< "$spec"
-    ncu --set full --clock-control none --import-source on --kernel-name $kern --launch-skip $skip --launch-count 2 \
+# igemm: 37 launches per step; #17-#20 of the second step = up3.conv1 fprop (928 GF, N = 128), up3.conv2 fprop, up4
+# transposed conv, up4.conv1 dgrad (1855 GF, 64 -> 128 at 128^3).  dmarch: 6 per step, wgrad_halo: 15 per step.
+for spec in "igemm_kernel:53:4:igemm" "dmarch_kernel:6:2:dmarch" "wgrad_halo_kernel:15:2:wgrad_halo"; do
+    IFS=: read -r kern skip cnt name <<< "$spec"
+    ncu --set full --clock-control none --import-source on --kernel-name $kern --launch-skip $skip --launch-count $cnt \
         -f -o $O/${TAG}_prof_${name} python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-profile-pass \
         > $O/${TAG}_ncu_${name}.log 2>&1
 done
