@@ -193,6 +193,11 @@ int b200_probe_mma(int n, int iters, int stages, long long* out_cycles, int bloc
 int b200_probe_mma2(int m, int n, int mn_major, int iters, int stages, long long* out_cycles, int blocks,
                     void* stream);
 
+/* dev probe of the CTA-pair (cta_group::2) primitives: d_out[pairs][256][n] fp32 = A[256][k] * B[n][k]^T (bf16, k
+ * contiguous) computed by `pairs` clusters of two CTAs, the MMA chain repeated `iters` times; cycles[pairs] (int64) */
+int b200_probe_pair(const void* a, const void* b, int n, int k, int iters, float* d_out, long long* cycles, int pairs,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

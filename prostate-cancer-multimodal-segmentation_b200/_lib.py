@@ -67,6 +67,7 @@ SIGNATURES = {
     "b200_seg_counts": (_i32, [_vp, _vp, _i64, _i64, _f32, _vp, _vp]),
     "b200_conv3d_kernel_id": (_i32, [_i64, _i64, _i64, _i64, _i64]),
     "b200_conv3d_wgrad_kernel_id": (_i32, [_i64, _i64]),
+    "b200_probe_pair": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp]),
     "b200_probe_mma": (_i32, [_i32, _i32, _i32, _vp, _i32, _vp]),
     "b200_probe_mma2": (_i32, [_i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
 }

@@ -1011,3 +1011,25 @@ extern "C" int b200_conv3d_kernel_id(int64_t n, int64_t d, int64_t h, int64_t w,
 extern "C" int b200_conv3d_wgrad_kernel_id(int64_t h, int64_t w) {
     return (w >= 8 && h >= 16) ? 1 : 0;                           // 0: wgrad_kernel, 1: wgrad_halo_kernel
 }
+
+// dev probe of the CTA-pair (cta_group::2) primitives: d_out[pairs][256][n] = A[256][k] B[n][k]^T (bf16 in, fp32 out),
+// the MMA chain repeated `iters` times (iters > 1 accumulates iters copies); cycles[pairs] = leader-side duration
+namespace b200 {
+cudaError_t launch_pair_probe(const CUtensorMap& a_map, const CUtensorMap& b_map, int n, int kblocks, int iters,
+                              float* d_out, long long* cycles, int pairs, cudaStream_t s);
+}
+extern "C" int b200_probe_pair(const void* a, const void* b, int n, int k, int iters, float* d_out, long long* cycles,
+                               int pairs, void* stream) {
+    REQUIRE(a && b && d_out && cycles, "probe_pair: null pointer");
+    REQUIRE(n >= 32 && n <= 256 && n % 32 == 0 && k >= 64 && k % 64 == 0 && k <= 256 && iters >= 1 && pairs >= 1,
+            "probe_pair: n in [32,256] step 32, k in {64,128,192,256}");
+    int rc = get_encode();
+    if (rc) return rc;
+    CUtensorMap am, bm;
+    rc = make_weight_map(&am, a, k, 256, 1, 128);
+    if (rc) return rc;
+    rc = make_weight_map(&bm, b, k, n, 1, n / 2);
+    if (rc) return rc;
+    CUDA_TRY(launch_pair_probe(am, bm, n, k / 64, iters, d_out, cycles, pairs, (cudaStream_t)stream));
+    return 0;
+}
