@@ -182,7 +182,7 @@ int b200_seg_counts(const float* score, const float* label, int64_t nsamples, in
                     float threshold, int64_t* counts, void* stream);
 
 /* routing queries (instrumentation): 3x3x3 conv fprop / dgrad -> 0 igemm_kernel, 1 dmarch_kernel (64 output columns on
- * 8 x 16 bricks); weight gradient -> 0 wgrad_kernel, 1 wgrad_halo_kernel (w >= 8 and h >= 16) */
+ * 8 x 16 bricks), 2 igemm_pair_kernel (tiles of >= 128 columns: CTA pairs, cta_group::2); weight gradient -> 0 wgrad_kernel, 1 wgrad_halo_kernel (w >= 8 and h >= 16) */
 int b200_conv3d_kernel_id(int64_t n, int64_t d, int64_t h, int64_t w, int64_t out_cols);
 int b200_conv3d_wgrad_kernel_id(int64_t h, int64_t w);
 

@@ -16,6 +16,7 @@
 namespace b200 {
 extern "C" __global__ void igemm_kernel(const __grid_constant__ IgemmParams p);
 extern "C" __global__ void wgrad_kernel(const __grid_constant__ WgradParams p);
+extern "C" __global__ void igemm_pair_kernel(const __grid_constant__ IgemmParams p);
 extern "C" __global__ void dmarch_kernel(const __grid_constant__ DmarchParams p);
 extern "C" __global__ void wgrad_halo_kernel(const __grid_constant__ WgradHaloParams p);
 }  // namespace b200
@@ -169,8 +170,16 @@ static int igemm_block_n(long long ncols, long long m_tiles) {
 constexpr int kIgemmFixedSmem = 1024 + 8 * (2 * 8 + 4) + 64 + 4 * 256 * 2 * 4 + kMaxStatCols * 2 * 4 + 2 * 256 * 4;
 constexpr int kSmemLimit = 227 * 1024;
 static int b_stage_bytes(const IgemmParams& p) {
-    return p.b_mn ? ((p.block_n + 63) / 64) * 8192 * p.group : p.block_n * 128 * p.group;
+    const int bn = p.pair ? p.block_n / 2 : p.block_n;   // pair mode: each CTA stages half of the B tile
+    return p.b_mn ? ((bn + 63) / 64) * 8192 * p.group : bn * 128 * p.group;
 }
+// CTA-pair mode of igemm_kernel (clusters of 2, tcgen05.mma.cta_group::2): wide-N 3x3x3 tiles, where halving the B
+// operand traffic per SM lifts the shared-memory bound; MN-major B needs whole 64-column atoms per CTA
+static bool igemm_pair_ok(int block_n, int ntaps, bool b_mn) {
+    if (ntaps != 27 || block_n < 128 || block_n % 32 != 0) return false;
+    return b_mn ? block_n % 128 == 0 : true;
+}
+static int igemm_max_clusters();
 static int epi_staging_bytes(const IgemmParams& p) { return p.epi_v2 ? ((p.block_n + 63) / 64) * kBoxBytes : 0; }
 static int igemm_stages(int a_bytes, int b_bytes, int c_bytes) {
     const int per_stage = a_bytes + b_bytes;
@@ -250,12 +259,51 @@ static int launch_igemm(IgemmParams& p, cudaStream_t s, int* grid_out) {
             attr_smem = 227 * 1024;
         }
     }
-    const long long tiles = (long long)p.nbw * p.nbh * p.nbd * p.nbatch * p.n_tiles;
+    const long long m_tiles = (long long)p.nbw * p.nbh * p.nbd * p.nbatch;
+    if (p.pair) {
+        const int ncl = igemm_max_clusters();
+        if (ncl <= 0) return fail(B200_ERR_CUDA, "igemm: no co-resident CTA pair fits on this device");
+        const long long units = ((m_tiles + 1) / 2) * p.n_tiles;
+        const int grid = 2 * (int)(units < ncl ? units : ncl);
+        if (grid_out) *grid_out = grid;
+        igemm_pair_kernel<<<grid, kThreads, smem, s>>>(p);   // compiled with __cluster_dims__(2, 1, 1)
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
+    const long long tiles = m_tiles * p.n_tiles;
     const int grid = (int)(tiles < sms ? tiles : sms);
     if (grid_out) *grid_out = grid;
     igemm_kernel<<<grid, kThreads, smem, s>>>(p);
     CUDA_TRY(cudaGetLastError());
     return 0;
+}
+// clusters of two igemm CTAs (227 KB of shared memory each) that can be resident at once: one per TPC with both SMs
+static int igemm_max_clusters() {
+    static int cached[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (cached[dev] != 0) return cached[dev];
+    if (cudaFuncSetAttribute(igemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
+        cudaSuccess)
+        return -1;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * 148);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = 227 * 1024;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, igemm_pair_kernel, &cfg) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        n = -1;
+    }
+    cached[dev] = n;
+    return n;
 }
 
 extern "C" int64_t b200_conv3d_mtiles(int64_t n, int64_t d, int64_t h, int64_t w) {
@@ -300,10 +348,12 @@ static int conv3_igemm(const b200_act* in, const void* w_packed, const b200_act*
     // fprop: K-major B from [tap][Cout rows][Cin].  dgrad (sign < 0) reads the SAME packed weights MN-major:
     // K = Cout rows (in->c), N = Cin contiguous (out->c), 64 x 64 boxes.
     p.b_mn = sign < 0 ? 1 : 0;
+    p.pair = (igemm_pair_ok(p.block_n, ntaps, p.b_mn != 0) && igemm_max_clusters() > 0) ? 1 : 0;
     if (p.b_mn)
         rc = make_weight_map(&p.b_map, w_packed, out->c, in->c, ntaps, 64, halo ? 3 : 1);
-    else
-        rc = make_weight_map(&p.b_map, w_packed, in->c, out->c, ntaps, p.block_n, halo ? 3 : 1);
+    else  // box rows = the B columns one CTA stages (half a tile in pair mode)
+        rc = make_weight_map(&p.b_map, w_packed, in->c, out->c, ntaps, p.pair ? p.block_n / 2 : p.block_n,
+                             halo ? 3 : 1);
     if (rc) return rc;
     p.ntaps = ntaps;
     // epilogue v2 (staged tile + TMA store): pays off when the MMA time per tile is short, i.e. narrow N
@@ -393,7 +443,13 @@ extern "C" int b200_conv3d_stat_rows(int64_t n, int64_t d, int64_t h, int64_t w,
     int bn = 0;
     Brick b;
     conv_geometry(n, w, h, d, cout, ntaps, &b, &bn);
-    const long long tiles = n * b.nbw * b.nbh * b.nbd * ((cout + bn - 1) / bn);
+    const long long m_tiles = n * b.nbw * b.nbh * b.nbd, n_tiles = (cout + bn - 1) / bn;
+    if (igemm_pair_ok(bn, ntaps, false) && igemm_max_clusters() > 0) {   // same decision as conv3_igemm (fprop)
+        const long long units = ((m_tiles + 1) / 2) * n_tiles;
+        const int ncl = igemm_max_clusters();
+        return 2 * (int)(units < ncl ? units : ncl);
+    }
+    const long long tiles = m_tiles * n_tiles;
     return (int)(tiles < sms ? tiles : sms);
 }
 
@@ -1006,7 +1062,11 @@ extern "C" int b200_seg_counts(const float* score, const float* label, int64_t n
 
 // which kernel a 3x3x3 conv call is routed to (bench.py labels its per-launch timings with the kernel that ran)
 extern "C" int b200_conv3d_kernel_id(int64_t n, int64_t d, int64_t h, int64_t w, int64_t out_cols) {
-    return dmarch_plan(n, w, h, d, out_cols, 27).use ? 1 : 0;   // 0: igemm_kernel, 1: dmarch_kernel
+    if (dmarch_plan(n, w, h, d, out_cols, 27).use) return 1;      // 0: igemm_kernel, 1: dmarch_kernel,
+    int bn = 0;                                                   // 2: igemm_pair_kernel
+    Brick b;
+    conv_geometry(n, w, h, d, out_cols, 27, &b, &bn);
+    return (igemm_pair_ok(bn, 27, true) && igemm_max_clusters() > 0) ? 2 : 0;
 }
 extern "C" int b200_conv3d_wgrad_kernel_id(int64_t h, int64_t w) {
     return (w >= 8 && h >= 16) ? 1 : 0;                           // 0: wgrad_kernel, 1: wgrad_halo_kernel

@@ -26,7 +26,8 @@ struct PipeState {
 // igemm_kernel
 // ------------------------------------------------------------------------------------------------
 // smem: [stages x A box 16 KB][stages x B tile block_n x 128 B][barriers][tmem ptr][stats scratch][column sums]
-extern "C" __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
+template <bool kPair>
+DEV void igemm_body(const IgemmParams& p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -35,8 +36,15 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __g
     const int lane = threadIdx.x & 31;
     const uint32_t nst = p.stages;
     const uint32_t a_bytes = p.a_stage_bytes;
-    const uint32_t b_atoms = (p.block_n + 63) >> 6;     // MN-major B: 64-column atoms per stage
-    const uint32_t bt_bytes = p.b_mn ? 8192u : p.block_n * 128;   // one tap of B (MN-major: of one atom)
+    // CTA-pair mode (kPair, launched as clusters of 2): the pair computes two adjacent M tiles against one N tile with
+    // tcgen05.mma.cta_group::2 (M = 256).  Each CTA stages its own A box and HALF of the B tile (columns
+    // [rank * block_n / 2, +block_n / 2)), which halves the B fill and the B operand reads per SM; the even CTA
+    // issues every MMA and commit, both run their own producer and epilogue.
+    const uint32_t mmul = kPair ? 2u : 1u;
+    const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+    const uint32_t bn_cta = p.block_n / mmul;          // B columns staged by this CTA
+    const uint32_t b_atoms = (bn_cta + 63) >> 6;       // MN-major B: 64-column atoms per stage
+    const uint32_t bt_bytes = p.b_mn ? 8192u : bn_cta * 128;      // one tap of B (MN-major: of one atom)
     const uint32_t b_atom_bytes = 8192u * p.group;
     const uint32_t b_bytes = p.b_mn ? b_atoms * b_atom_bytes : bt_bytes * p.group;  // B bytes per stage
     const uint32_t smem_a = smem_base;
@@ -66,30 +74,40 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __g
         }
         for (uint32_t s = 0; s < 2; ++s) {
             mbar_init(tfull_bar(s), 1);
-            mbar_init(tempty_bar(s), 128);
+            mbar_init(tempty_bar(s), 128 * mmul);   // pair: the epilogue threads of both CTAs arrive on the leader's
         }
         fence_mbar_init();
     }
     if (warp == 2) {
-        tmem_alloc(tmem_ptr_smem, 512);
-        tmem_relinquish();
+        if (kPair) {
+            tmem_alloc_pair(tmem_ptr_smem, 512);
+            tmem_relinquish_pair();
+        } else {
+            tmem_alloc(tmem_ptr_smem, 512);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (kPair) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_smem - smem_base));
 
+    // work units: (M tile, N tile), or in pair mode (pair of adjacent M tiles, N tile); a pair walks the same units,
+    // CTA `rank` owning M tile 2 * m_unit + rank (past the last tile: all-out-of-range coordinates, nothing stored)
     const int m_tiles = p.nbw * p.nbh * p.nbd * p.nbatch;
-    const int total_tiles = m_tiles * p.n_tiles;
+    const int m_units = (m_tiles + (int)mmul - 1) / (int)mmul;
+    const int total_tiles = m_units * p.n_tiles;
+    const int unit0 = blockIdx.x / mmul, unit_stride = gridDim.x / mmul;
 
     if (warp == 0) {
         // ===================================================================== TMA producer
         // The whole warp walks the loop (uniform control flow, barrier polls by all lanes); one elected lane issues.
         PipeState ps;
         const int kc_blocks = p.kc_blocks, ntaps = p.ntaps / p.group, n_tiles = p.n_tiles, group = p.group;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int tile = unit0; tile < total_tiles; tile += unit_stride) {
             int mt = tile / n_tiles;
             const int n_tile = tile - mt * n_tiles;
+            mt = mt * (int)mmul + (int)rank;
             const int bw = mt % p.nbw; mt /= p.nbw;
             const int bh = mt % p.nbh; mt /= p.nbh;
             const int bd = mt % p.nbd; mt /= p.nbd;
@@ -103,14 +121,28 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __g
                     mbar_wait(empty_bar(ps.stage), ps.phase ^ 1);
                     if (elect_one()) {
                         const uint32_t fb = full_bar(ps.stage);
-                        mbar_arrive_expect_tx(fb, a_bytes + b_bytes);
-                        tma_load_5d(smem_a + ps.stage * a_bytes, amap, fb, kc * 64, cw, ch, cd, nb);
-                        if (p.b_mn) {
-                            for (uint32_t a = 0; a < b_atoms; ++a)
-                                tma_load_3d(smem_b + ps.stage * b_bytes + a * b_atom_bytes, &p.b_map, fb, n0 + a * 64,
-                                            kc * 64, tap * group);
+                        if (!kPair) {
+                            mbar_arrive_expect_tx(fb, a_bytes + b_bytes);
+                            tma_load_5d(smem_a + ps.stage * a_bytes, amap, fb, kc * 64, cw, ch, cd, nb);
+                            if (p.b_mn) {
+                                for (uint32_t a = 0; a < b_atoms; ++a)
+                                    tma_load_3d(smem_b + ps.stage * b_bytes + a * b_atom_bytes, &p.b_map, fb,
+                                                n0 + a * 64, kc * 64, tap * group);
+                            } else {
+                                tma_load_3d(smem_b + ps.stage * b_bytes, &p.b_map, fb, kc * 64, n0, tap * group);
+                            }
                         } else {
-                            tma_load_3d(smem_b + ps.stage * b_bytes, &p.b_map, fb, kc * 64, n0, tap * group);
+                            // both CTAs' bytes are counted on the leader's barrier (the pair form of the TMA load)
+                            if (rank == 0) mbar_arrive_expect_tx(fb, 2 * (a_bytes + b_bytes));
+                            tma_load_5d_pair(smem_a + ps.stage * a_bytes, amap, fb, kc * 64, cw, ch, cd, nb);
+                            const int nc = n0 + (int)(rank * bn_cta);
+                            if (p.b_mn) {
+                                for (uint32_t a = 0; a < b_atoms; ++a)
+                                    tma_load_3d_pair(smem_b + ps.stage * b_bytes + a * b_atom_bytes, &p.b_map, fb,
+                                                     nc + a * 64, kc * 64, tap * group);
+                            } else {
+                                tma_load_3d_pair(smem_b + ps.stage * b_bytes, &p.b_map, fb, kc * 64, nc, tap * group);
+                            }
                         }
                     }
                     __syncwarp();
@@ -118,10 +150,11 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __g
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===================================================================== MMA issuer
+    } else if (warp == 1 && rank == 0) {
+        // ===================================================================== MMA issuer (pair mode: leader CTA only)
         // Lean loop: descriptors are base + stage offset (low word only), no divisions, one elected lane issues.
-        const uint32_t idesc = make_idesc_bf16(128, p.block_n, 0, p.b_mn ? 1u : 0u);
+        const uint32_t idesc = make_idesc_bf16(128 * mmul, p.block_n, 0, p.b_mn ? 1u : 0u);
+        const bool pair = kPair;
         const uint64_t a_desc0 = make_smem_desc_sw128(smem_a, 0, 1024);
         // K-major B: rows = N, 128 B = 64 K.  MN-major B: rows = K, 128 B = 64 N, atoms of 64 N are LBO apart.
         const uint64_t b_desc0 = make_smem_desc_sw128(smem_b, p.b_mn ? b_atom_bytes : 0, 1024);
@@ -132,7 +165,7 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __g
         const int nk_last = ((p.cin - (kc_blocks - 1) * 64) + 15) >> 4;  // K steps of the last channel block (1..4)
         PipeState ps;
         int iter = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+        for (int tile = unit0; tile < total_tiles; tile += unit_stride, ++iter) {
             const uint32_t acc = iter & 1, acc_phase = (iter >> 1) & 1;
             mbar_wait(tempty_bar(acc), acc_phase ^ 1);
             tc_fence_after();
@@ -150,19 +183,30 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __g
                             const uint64_t a_desc = a_st + (g == 0 ? goff0 : (g == 1 ? goff1 : goff2));
                             const uint64_t b_desc = b_st + g * bt_step;
                             // 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (>>4) address field
-                            umma_f16(d_tmem, a_desc, b_desc, idesc, g == 0 ? accum : 1u);
-                            if (nk > 1) umma_f16(d_tmem, a_desc + 2, b_desc + kinc, idesc, 1u);
-                            if (nk > 2) umma_f16(d_tmem, a_desc + 4, b_desc + 2 * kinc, idesc, 1u);
-                            if (nk > 3) umma_f16(d_tmem, a_desc + 6, b_desc + 3 * kinc, idesc, 1u);
+                            if (!pair) {
+                                umma_f16(d_tmem, a_desc, b_desc, idesc, g == 0 ? accum : 1u);
+                                if (nk > 1) umma_f16(d_tmem, a_desc + 2, b_desc + kinc, idesc, 1u);
+                                if (nk > 2) umma_f16(d_tmem, a_desc + 4, b_desc + 2 * kinc, idesc, 1u);
+                                if (nk > 3) umma_f16(d_tmem, a_desc + 6, b_desc + 3 * kinc, idesc, 1u);
+                            } else {
+                                umma_f16_pair(d_tmem, a_desc, b_desc, idesc, g == 0 ? accum : 1u);
+                                if (nk > 1) umma_f16_pair(d_tmem, a_desc + 2, b_desc + kinc, idesc, 1u);
+                                if (nk > 2) umma_f16_pair(d_tmem, a_desc + 4, b_desc + 2 * kinc, idesc, 1u);
+                                if (nk > 3) umma_f16_pair(d_tmem, a_desc + 6, b_desc + 3 * kinc, idesc, 1u);
+                            }
                         }
-                        umma_commit(empty_bar(ps.stage));
+                        if (pair) umma_commit_pair(empty_bar(ps.stage), 3u);   // frees the slot in both CTAs
+                        else umma_commit(empty_bar(ps.stage));
                     }
                     __syncwarp();
                     accum = 1u;
                     ps.advance(nst);
                 }
             }
-            if (elect_one()) umma_commit(tfull_bar(acc));
+            if (elect_one()) {
+                if (pair) umma_commit_pair(tfull_bar(acc), 3u);
+                else umma_commit(tfull_bar(acc));
+            }
             __syncwarp();
         }
     } else if (warp >= 4) {
@@ -187,17 +231,17 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __g
             const int mode = p.mode;
             const uint32_t row_smem = smem_c + row * 128;
             const uint32_t sw = row & 7;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+            for (int tile = unit0; tile < total_tiles; tile += unit_stride, ++iter) {
                 const uint32_t acc = iter & 1, acc_phase = (iter >> 1) & 1;
-                const int m_tile = tile / p.n_tiles;
-                const int n_tile = tile - m_tile * p.n_tiles;
-                int mt = m_tile;
+                const int m_unit = tile / p.n_tiles;
+                const int n_tile = tile - m_unit * p.n_tiles;
+                int mt = m_unit * (int)mmul + (int)rank;
                 const int bw = mt % p.nbw; mt /= p.nbw;
                 const int bh = mt % p.nbh; mt /= p.nbh;
                 const int bd = mt % p.nbd; mt /= p.nbd;
                 const int nb = mt;
                 const int w0 = bw << p.tw_log2, h0 = bh << p.th_log2, d0 = bd << p.td_log2;
-                const bool row_ok = (w0 + rw) < p.W && (h0 + rh) < p.H && (d0 + rd) < p.D;
+                const bool row_ok = (w0 + rw) < p.W && (h0 + rh) < p.H && (d0 + rd) < p.D && nb < p.nbatch;
                 const int n0 = n_tile * p.block_n;
                 if (mode != EPI_PLAIN) {
                     for (int c = et; c < p.block_n; c += 128) {
@@ -237,7 +281,8 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __g
                                      pk[4 * c + 3]);
                 }
                 tc_fence_before();
-                mbar_arrive(tempty_bar(acc));  // TMEM stage drained
+                if (kPair) mbar_arrive_leader(tempty_bar(acc));
+                else mbar_arrive(tempty_bar(acc));  // TMEM stage drained
                 fence_proxy_async_smem();      // generic-proxy writes -> visible to the TMA engine
                 named_bar_sync(1, 128);
                 if (et == 0) {
@@ -284,17 +329,17 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __g
             }
             if (et == 0) bulk_wait0();  // all output tiles are in global memory before the CTA exits
         } else
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+        for (int tile = unit0; tile < total_tiles; tile += unit_stride, ++iter) {
             const uint32_t acc = iter & 1, acc_phase = (iter >> 1) & 1;
-            const int m_tile = tile / p.n_tiles;
-            const int n_tile = tile - m_tile * p.n_tiles;
-            int mt = m_tile;
+            const int m_unit = tile / p.n_tiles;
+            const int n_tile = tile - m_unit * p.n_tiles;
+            int mt = m_unit * (int)mmul + (int)rank;
             const int bw = mt % p.nbw; mt /= p.nbw;
             const int bh = mt % p.nbh; mt /= p.nbh;
             const int bd = mt % p.nbd; mt /= p.nbd;
             const int nb = mt;
             const int gw = (bw << p.tw_log2) + rw, gh = (bh << p.th_log2) + rh, gd = (bd << p.td_log2) + rd;
-            const bool row_ok = gw < p.W && gh < p.H && gd < p.D;
+            const bool row_ok = gw < p.W && gh < p.H && gd < p.D && nb < p.nbatch;
             const int n0 = n_tile * p.block_n;
 
             mbar_wait(tfull_bar(acc), acc_phase);
@@ -364,9 +409,10 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __g
                     scratch[(q * 256 + cl) * 2 + (lane & 1)] = (lane & 1) ? ss[0] : s[0];
                 }
             }
-            // TMEM stage drained: hand it back to the MMA warp
+            // TMEM stage drained: hand it back to the MMA warp (pair mode: of the leader CTA)
             tc_fence_before();
-            mbar_arrive(tempty_bar(acc));
+            if (kPair) mbar_arrive_leader(tempty_bar(acc));
+            else mbar_arrive(tempty_bar(acc));
 
             if (p.mode == EPI_BIAS_STATS) {
                 named_bar_sync(1, 128);
@@ -395,11 +441,22 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __g
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (kPair) cluster_sync_all(); else __syncthreads();   // no CTA of a pair leaves while its peer may still signal it
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        if (kPair) tmem_dealloc_pair(tmem_base, 512);
+        else tmem_dealloc(tmem_base, 512);
     }
+}
+
+// The single-CTA form contains no cluster instruction at all (a kernel that does cannot be launched without a
+// cluster configuration); the pair form is compiled for clusters of two.
+extern "C" __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
+    igemm_body<false>(p);
+}
+extern "C" __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+    igemm_pair_kernel(const __grid_constant__ IgemmParams p) {
+    igemm_body<true>(p);
 }
 
 // ------------------------------------------------------------------------------------------------
