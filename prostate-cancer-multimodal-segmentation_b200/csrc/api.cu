@@ -18,6 +18,7 @@ extern "C" __global__ void igemm_kernel(const __grid_constant__ IgemmParams p);
 extern "C" __global__ void wgrad_kernel(const __grid_constant__ WgradParams p);
 extern "C" __global__ void igemm_pair_kernel(const __grid_constant__ IgemmParams p);
 extern "C" __global__ void dmarch_kernel(const __grid_constant__ DmarchParams p);
+extern "C" __global__ void dmarch_pair_kernel(const __grid_constant__ DmarchParams p);
 extern "C" __global__ void wgrad_halo_kernel(const __grid_constant__ WgradHaloParams p);
 }  // namespace b200
 
@@ -190,12 +191,17 @@ static int igemm_stages(int a_bytes, int b_bytes, int c_bytes) {
 static size_t igemm_smem(int stages, int a_bytes, int b_bytes, int c_bytes) {
     return (size_t)kIgemmFixedSmem + (size_t)stages * (a_bytes + b_bytes) + c_bytes;
 }
+static bool igemm_pair_ok(int block_n, int ntaps, bool b_mn);
+static int igemm_max_clusters();
 // brick geometry of a conv3d / conv1 implicit GEMM; shared by the launcher and b200_conv3d_stat_rows
 static bool conv_geometry(long long n, long long w, long long h, long long d, long long cout, int ntaps, Brick* b,
                           int* block_n) {
     const Brick plain = choose_brick(w, h, d);
     *block_n = igemm_block_n(cout, n * plain.nbw * plain.nbh * plain.nbd);
-    const bool halo = ntaps == 27 && *block_n <= 128 && w >= 8 && h >= 16;
+    // h-halo mode needs the three kh taps of B in one stage: 3 x block_n x 128 B.  That fits next to the A box for
+    // block_n <= 128, and for 256-column tiles in CTA-pair mode (each CTA stages half of B: 48 KB)
+    const bool wide_pair = *block_n == 256 && igemm_pair_ok(256, ntaps, true) && igemm_max_clusters() > 0;
+    const bool halo = ntaps == 27 && (*block_n <= 128 || wide_pair) && w >= 8 && h >= 16;
     if (halo) {
         b->tw = 8; b->th = 16; b->td = 1; b->lw = 3; b->lh = 4; b->ld = 0;
         b->nbw = (w + 7) / 8; b->nbh = (h + 15) / 16; b->nbd = d;
@@ -206,17 +212,26 @@ static bool conv_geometry(long long n, long long w, long long h, long long d, lo
 }
 // depth-marching path (dmarch.cu): 3x3x3 conv with exactly 64 output columns on 8 x 16 bricks
 struct DmPlan {
-    bool use;
+    bool use, pair;
     int nbw, nbh, seg_len, nseg, grid;
 };
+static int dmarch_max_clusters();
 static DmPlan dmarch_plan(long long n, long long w, long long h, long long d, long long ncols, int ntaps) {
     DmPlan pl{};
-    const int sms = sm_count();
+    int sms = sm_count();
     pl.use = ntaps == 27 && ncols == 64 && w >= 8 && h >= 16 && sms > 0;
     if (!pl.use) return pl;
     pl.nbw = (int)((w + 7) / 8);
     pl.nbh = (int)((h + 15) / 16);
-    const long long columns = n * pl.nbw * pl.nbh;
+    long long columns = n * pl.nbw * pl.nbh;
+    // pair mode (dmarch_pair_kernel): clusters of two CTAs march two adjacent columns in lockstep and share the weight
+    // stream through TMA multicast; the planner then balances column pairs over resident clusters
+    const int ncl = dmarch_max_clusters();
+    pl.pair = ncl > 0 && columns >= 2;
+    if (pl.pair) {
+        columns = (columns + 1) / 2;
+        sms = ncl;
+    }
     // depth segments per column: minimise waves x (segment length + the two boundary slices, which cost ~1/3 each)
     const long long max_seg = d >= 8 ? d / 4 : 1;               // segments of at least 4 slices
     long long best_nseg = 1;
@@ -231,7 +246,7 @@ static DmPlan dmarch_plan(long long n, long long w, long long h, long long d, lo
     pl.seg_len = (int)((d + best_nseg - 1) / best_nseg);
     pl.nseg = (int)((d + pl.seg_len - 1) / pl.seg_len);
     const long long units = columns * pl.nseg;
-    pl.grid = (int)(units < sms ? units : sms);
+    pl.grid = (int)(units < sms ? units : sms) * (pl.pair ? 2 : 1);
     return pl;
 }
 constexpr int kDmSmem = 1024 + kDmAStages * kDmAStageBytes + kDmBStages * kDmBBytes + kBoxBytes +
@@ -428,9 +443,36 @@ static int launch_dmarch(const b200_act* in, const void* w_packed, const b200_ac
             attr = true;
         }
     }
-    dmarch_kernel<<<pl.grid, kThreads, kDmSmem, s>>>(p);
+    if (pl.pair) dmarch_pair_kernel<<<pl.grid, kThreads, kDmSmem, s>>>(p);   // __cluster_dims__(2, 1, 1)
+    else dmarch_kernel<<<pl.grid, kThreads, kDmSmem, s>>>(p);
     CUDA_TRY(cudaGetLastError());
     return 0;
+}
+static int dmarch_max_clusters() {
+    static int cached[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (cached[dev] != 0) return cached[dev];
+    int n = -1;
+    if (cudaFuncSetAttribute(dmarch_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDmSmem) == cudaSuccess) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(2 * 148);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = kDmSmem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        if (cudaOccupancyMaxActiveClusters(&n, dmarch_pair_kernel, &cfg) != cudaSuccess || n <= 0) {
+            cudaGetLastError();
+            n = -1;
+        }
+    }
+    cached[dev] = n;
+    return n;
 }
 
 extern "C" int b200_conv3d_stat_rows(int64_t n, int64_t d, int64_t h, int64_t w, int64_t cout, int ntaps) {
@@ -1062,8 +1104,11 @@ extern "C" int b200_seg_counts(const float* score, const float* label, int64_t n
 
 // which kernel a 3x3x3 conv call is routed to (bench.py labels its per-launch timings with the kernel that ran)
 extern "C" int b200_conv3d_kernel_id(int64_t n, int64_t d, int64_t h, int64_t w, int64_t out_cols) {
-    if (dmarch_plan(n, w, h, d, out_cols, 27).use) return 1;      // 0: igemm_kernel, 1: dmarch_kernel,
-    int bn = 0;                                                   // 2: igemm_pair_kernel
+    {
+        const DmPlan pl = dmarch_plan(n, w, h, d, out_cols, 27);  // 0: igemm_kernel, 1: dmarch_kernel,
+        if (pl.use) return pl.pair ? 3 : 1;                       // 2: igemm_pair_kernel, 3: dmarch_pair_kernel
+    }
+    int bn = 0;
     Brick b;
     conv_geometry(n, w, h, d, out_cols, 27, &b, &bn);
     return (igemm_pair_ok(bn, 27, true) && igemm_max_clusters() > 0) ? 2 : 0;

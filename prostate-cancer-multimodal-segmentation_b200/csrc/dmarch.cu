@@ -17,7 +17,12 @@ struct Ring {
     }
 };
 
-extern "C" __global__ void __launch_bounds__(kThreads, 1) dmarch_kernel(const __grid_constant__ DmarchParams p) {
+// kPair: launched as clusters of two CTAs that march two adjacent brick columns through the same depth segment in
+// lockstep and SHARE the weight stream: every B stage is fetched once, by the CTA whose rank equals the parity of the
+// stage count, and multicast into both CTAs' shared memory.  Every large GEMM here runs against the L2 -> SM fabric
+// (~10-11 TB/s measured in all ncu captures); the weights are 2/3 of this kernel's fabric bytes.
+template <bool kPair>
+DEV void dmarch_body(const DmarchParams& p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -47,7 +52,8 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) dmarch_kernel(const __
     }
     if (warp == 1 && lane == 0) {
         for (uint32_t s = 0; s < kDmAStages; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
-        for (uint32_t s = 0; s < kDmBStages; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
+        // a B stage is rewritten in both CTAs of a pair at once: both MMA issuers release it
+        for (uint32_t s = 0; s < kDmBStages; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), kPair ? 2 : 1); }
         for (uint32_t s = 0; s < kDmSlots; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), 128); }
         fence_mbar_init();
     }
@@ -56,18 +62,24 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) dmarch_kernel(const __
         tmem_relinquish();
     }
     tc_fence_before();
-    __syncthreads();
+    if (kPair) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_smem - smem_base));
 
     const int columns = p.nbatch * p.nbw * p.nbh;
-    const int units = columns * p.nseg;
+    const int cmul = kPair ? 2 : 1;
+    const int rank = kPair ? (int)cluster_ctarank() : 0;
+    // pair mode: a unit is (pair of adjacent columns, depth segment); CTA `rank` owns column 2 * cpair + rank (a
+    // column past the last one has every coordinate out of range: zero-filled loads, clipped stores)
+    const int units = ((columns + cmul - 1) / cmul) * p.nseg;
+    const int unit0 = blockIdx.x / cmul, unit_stride = gridDim.x / cmul;
     const int kc_blocks = p.kc_blocks;
     const int sign = p.sign;
 
     // unit -> (batch, brick column, depth segment); segments of one column are consecutive units
     auto decode = [&](int unit, int& nb, int& w0, int& h0, int& ds, int& de) {
-        const int col = unit / p.nseg, seg = unit - col * p.nseg;
+        const int cu = unit / p.nseg, seg = unit - cu * p.nseg;
+        const int col = cu * cmul + rank;
         int c = col;
         const int bw = c % p.nbw; c /= p.nbw;
         const int bh = c % p.nbh; c /= p.nbh;
@@ -81,7 +93,8 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) dmarch_kernel(const __
     if (warp == 0) {
         // ===================================================================== TMA producer
         Ring ra, rb;
-        for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+        uint32_t bcount = 0;   // B stages so far: in pair mode the CTA of that parity fetches the stage for both
+        for (int unit = unit0; unit < units; unit += unit_stride) {
             int nb, w0, h0, ds, de;
             decode(unit, nb, w0, h0, ds, de);
             if (ds >= de) continue;
@@ -105,19 +118,21 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) dmarch_kernel(const __
                             if (elect_one()) {
                                 const uint32_t fb = bfull(rb.stage);
                                 mbar_arrive_expect_tx(fb, kDmBBytes);
+                                if (!kPair || (int)(bcount & 1u) == rank) {
 #pragma unroll
-                                for (int j = 0; j < 3; ++j) {
-                                    // slab j feeds output slice dz - 1 + j
-                                    const int kd = sign > 0 ? 2 - j : j;
-                                    const int tap = kd * 9 + kw * 3 + kh;  // packed tap order
-                                    const uint32_t dst = smem_b + rb.stage * kDmBBytes + j * 8192;
-                                    if (p.b_mn)
-                                        tma_load_3d(dst, &p.b_map, fb, 0, kc * 64, tap);
-                                    else
-                                        tma_load_3d(dst, &p.b_map, fb, kc * 64, 0, tap);
+                                    for (int j = 0; j < 3; ++j) {
+                                        // slab j feeds output slice dz - 1 + j
+                                        const int kd = sign > 0 ? 2 - j : j;
+                                        const int tap = kd * 9 + kw * 3 + kh;  // packed tap order
+                                        const uint32_t dst = smem_b + rb.stage * kDmBBytes + j * 8192;
+                                        const int c0 = p.b_mn ? 0 : kc * 64, c1 = p.b_mn ? kc * 64 : 0;
+                                        if (kPair) tma_load_3d_mc(dst, &p.b_map, fb, c0, c1, tap, 3u);
+                                        else tma_load_3d(dst, &p.b_map, fb, c0, c1, tap);
+                                    }
                                 }
                             }
                             __syncwarp();
+                            ++bcount;
                             rb.advance(kDmBStages);
                         }
                     }
@@ -140,7 +155,7 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) dmarch_kernel(const __
         const uint32_t idesc64 = idesc0 | (8u << 17);
         const int nk_last = ((p.cin - (kc_blocks - 1) * 64) + 15) >> 4;
         uint32_t ubase = 0;  // TMEM-slot use index of output slice ds of the current unit
-        for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+        for (int unit = unit0; unit < units; unit += unit_stride) {
             int nb, w0, h0, ds, de;
             decode(unit, nb, w0, h0, ds, de);
             if (ds >= de) continue;
@@ -232,7 +247,8 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) dmarch_kernel(const __
                                         }
                                     }
                                 }
-                                umma_commit(bempty(rb.stage));
+                                if (kPair) umma_commit_mc(bempty(rb.stage), 3u);   // both CTAs' producers
+                                else umma_commit(bempty(rb.stage));
                             }
                             __syncwarp();
                             first = false;
@@ -278,10 +294,10 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) dmarch_kernel(const __
         }
         named_bar_sync(1, 128);
         uint32_t u = 0;
-        for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+        for (int unit = unit0; unit < units; unit += unit_stride) {
             int nb, w0, h0, ds, de;
             decode(unit, nb, w0, h0, ds, de);
-            const bool row_ok = (w0 + rw) < p.W && (h0 + rh) < p.H;
+            const bool row_ok = (w0 + rw) < p.W && (h0 + rh) < p.H && nb < p.nbatch;
             for (int d = ds; d < de; ++d, ++u) {
                 const uint32_t slot = u % kDmSlots, par = (u / kDmSlots) & 1;
                 if (et == 0) bulk_wait_read0();  // previous TMA store finished reading the staging tile
@@ -355,11 +371,19 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) dmarch_kernel(const __
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (kPair) cluster_sync_all(); else __syncthreads();   // a peer may still signal this CTA's barriers until here
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
+}
+
+extern "C" __global__ void __launch_bounds__(kThreads, 1) dmarch_kernel(const __grid_constant__ DmarchParams p) {
+    dmarch_body<false>(p);
+}
+extern "C" __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+    dmarch_pair_kernel(const __grid_constant__ DmarchParams p) {
+    dmarch_body<true>(p);
 }
 
 }  // namespace b200

@@ -231,6 +231,26 @@ DEV void tma_load_5d_pair(uint32_t smem_dst, const void* desc, uint32_t bar, int
         "r"(c3), "r"(c4)
         : "memory");
 }
+// TMA load delivered to the same shared-memory offset (and counted on the barrier at the same offset) in every CTA
+// of `cta_mask`: one L2 read feeds several SMs
+DEV void tma_load_3d_mc(uint32_t smem_dst, const void* desc, uint32_t bar, int c0, int c1, int c2, uint32_t cta_mask) {
+    asm volatile(
+        "{\n\t.reg .b16 m;\n\t"
+        "cvt.u16.u32 m, %6;\n\t"
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4, %5}], [%2], m;\n\t}"
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(cta_mask)
+        : "memory");
+}
+// single-CTA MMA completion signalled on the barrier at the same offset in every CTA of `cta_mask`
+DEV void umma_commit_mc(uint32_t bar, uint32_t cta_mask) {
+    asm volatile(
+        "{\n\t.reg .b16 m;\n\t"
+        "cvt.u16.u32 m, %1;\n\t"
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}"
+        ::"r"(bar), "r"(cta_mask)
+        : "memory");
+}
 // arrive on the leader CTA's copy of a barrier (from either CTA of the pair)
 DEV void mbar_arrive_leader(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");

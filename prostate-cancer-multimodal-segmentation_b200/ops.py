@@ -147,7 +147,8 @@ def _conv_kernel(lib, v: ActView, out_cols: int) -> str:
     if profile_hook is None:
         return "igemm_kernel"
     n, d, h, w, _ = v.shape
-    return ("igemm_kernel", "dmarch_kernel", "igemm_pair_kernel")[lib.b200_conv3d_kernel_id(n, d, h, w, out_cols)]
+    return ("igemm_kernel", "dmarch_kernel", "igemm_pair_kernel",
+            "dmarch_pair_kernel")[lib.b200_conv3d_kernel_id(n, d, h, w, out_cols)]
 
 
 def conv3d_fprop(x: ActView, w_fprop, bias, y: ActView, stats=None, mode=EPI_BIAS_STATS, scale=None, shift=None,
