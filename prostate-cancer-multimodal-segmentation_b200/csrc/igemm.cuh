@@ -71,8 +71,8 @@ struct alignas(64) IgemmParams {
 // while the MMAs go on.
 constexpr int kDmSlots = 8;      // TMEM ring: 8 x 64 columns
 constexpr int kDmG = 2;          // input slices that share one pass over the tap weights (B stream / kDmG)
-constexpr int kDmAStages = 2;    // A ring: kDmG h-halo boxes of 18 KB per stage
-constexpr int kDmBStages = 5;    // B ring: [3 slabs][64 rows][128 B] = 24 KB
+constexpr int kDmAStages = 3;    // A ring: kDmG h-halo boxes of 18 KB per stage
+constexpr int kDmBStages = 4;    // B ring: [3 slabs][64 rows][128 B] = 24 KB
 constexpr int kDmABytes = 18 * 8 * 128;
 constexpr int kDmAStageBytes = kDmG * kDmABytes;
 constexpr int kDmBBytes = 3 * 8192;

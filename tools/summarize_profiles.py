@@ -60,7 +60,7 @@ WANT = ["gpu__time_duration.sum", "launch__grid_size", "sm__cycles_elapsed.max",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread",
         "launch__shared_mem_per_block_dynamic", "smsp__inst_executed.sum"]
 traffic = {}
-for name in ("igemm", "dmarch", "wgrad_halo"):
+for name in ("igemm_pair", "dmarch_pair", "wgrad_halo", "igemm", "dmarch"):
     rep = os.path.join(G, f"{tag}_prof_{name}.ncu-rep")
     if not os.path.exists(rep):
         continue
@@ -86,7 +86,7 @@ for name in ("igemm", "dmarch", "wgrad_halo"):
                 v = float(v.replace(",", ""))
                 return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}.get(u, 1.0)
             if li == 0 and "dram__bytes_read.sum" in vals:
-                kname = {"igemm": "igemm_kernel", "dmarch": "dmarch_kernel", "wgrad_halo": "wgrad_halo_kernel"}[name]
+                kname = name + "_kernel"
                 traffic[kname] = {"dram_bytes": int(num("dram__bytes_read.sum") + num("dram__bytes_write.sum")),
                                   "duration_ms_under_ncu": float(vals["gpu__time_duration.sum"][0]) *
                                   {"ms": 1.0, "us": 1e-3, "ns": 1e-6}[vals["gpu__time_duration.sum"][1]],
