@@ -176,8 +176,9 @@ static int b_stage_bytes(const IgemmParams& p) {
 }
 // CTA-pair mode of igemm_kernel (clusters of 2, tcgen05.mma.cta_group::2): wide-N 3x3x3 tiles, where halving the B
 // operand traffic per SM lifts the shared-memory bound; MN-major B needs whole 64-column atoms per CTA
-static bool igemm_pair_ok(int block_n, int ntaps, bool b_mn) {
+static bool igemm_pair_ok(int block_n, int ntaps, bool b_mn, long long m_tiles) {
     if (ntaps != 27 || block_n < 128 || block_n % 32 != 0) return false;
+    if (m_tiles < 32) return false;   // the 8^3 level: a handful of tiles, the cluster hand-shakes cost more than B saves
     return b_mn ? block_n % 128 == 0 : true;
 }
 static int igemm_max_clusters();
@@ -191,8 +192,6 @@ static int igemm_stages(int a_bytes, int b_bytes, int c_bytes) {
 static size_t igemm_smem(int stages, int a_bytes, int b_bytes, int c_bytes) {
     return (size_t)kIgemmFixedSmem + (size_t)stages * (a_bytes + b_bytes) + c_bytes;
 }
-static bool igemm_pair_ok(int block_n, int ntaps, bool b_mn);
-static int igemm_max_clusters();
 // brick geometry of a conv3d / conv1 implicit GEMM; shared by the launcher and b200_conv3d_stat_rows
 static bool conv_geometry(long long n, long long w, long long h, long long d, long long cout, int ntaps, Brick* b,
                           int* block_n) {
@@ -200,7 +199,9 @@ static bool conv_geometry(long long n, long long w, long long h, long long d, lo
     *block_n = igemm_block_n(cout, n * plain.nbw * plain.nbh * plain.nbd);
     // h-halo mode needs the three kh taps of B in one stage: 3 x block_n x 128 B.  That fits next to the A box for
     // block_n <= 128, and for 256-column tiles in CTA-pair mode (each CTA stages half of B: 48 KB)
-    const bool wide_pair = *block_n == 256 && igemm_pair_ok(256, ntaps, true) && igemm_max_clusters() > 0;
+    const bool wide_pair = *block_n == 256 && w >= 8 && h >= 16 &&
+                           igemm_pair_ok(256, ntaps, true, n * ((w + 7) / 8) * ((h + 15) / 16) * d) &&
+                           igemm_max_clusters() > 0;
     const bool halo = ntaps == 27 && (*block_n <= 128 || wide_pair) && w >= 8 && h >= 16;
     if (halo) {
         b->tw = 8; b->th = 16; b->td = 1; b->lw = 3; b->lh = 4; b->ld = 0;
@@ -363,7 +364,8 @@ static int conv3_igemm(const b200_act* in, const void* w_packed, const b200_act*
     // fprop: K-major B from [tap][Cout rows][Cin].  dgrad (sign < 0) reads the SAME packed weights MN-major:
     // K = Cout rows (in->c), N = Cin contiguous (out->c), 64 x 64 boxes.
     p.b_mn = sign < 0 ? 1 : 0;
-    p.pair = (igemm_pair_ok(p.block_n, ntaps, p.b_mn != 0) && igemm_max_clusters() > 0) ? 1 : 0;
+    p.pair = (igemm_pair_ok(p.block_n, ntaps, p.b_mn != 0, in->n * b.nbw * b.nbh * b.nbd) &&
+              igemm_max_clusters() > 0) ? 1 : 0;
     if (p.b_mn)
         rc = make_weight_map(&p.b_map, w_packed, out->c, in->c, ntaps, 64, halo ? 3 : 1);
     else  // box rows = the B columns one CTA stages (half a tile in pair mode)
@@ -486,7 +488,7 @@ extern "C" int b200_conv3d_stat_rows(int64_t n, int64_t d, int64_t h, int64_t w,
     Brick b;
     conv_geometry(n, w, h, d, cout, ntaps, &b, &bn);
     const long long m_tiles = n * b.nbw * b.nbh * b.nbd, n_tiles = (cout + bn - 1) / bn;
-    if (igemm_pair_ok(bn, ntaps, false) && igemm_max_clusters() > 0) {   // same decision as conv3_igemm (fprop)
+    if (igemm_pair_ok(bn, ntaps, false, m_tiles) && igemm_max_clusters() > 0) {   // same decision as conv3_igemm (fprop)
         const long long units = ((m_tiles + 1) / 2) * n_tiles;
         const int ncl = igemm_max_clusters();
         return 2 * (int)(units < ncl ? units : ncl);
@@ -1111,7 +1113,7 @@ extern "C" int b200_conv3d_kernel_id(int64_t n, int64_t d, int64_t h, int64_t w,
     int bn = 0;
     Brick b;
     conv_geometry(n, w, h, d, out_cols, 27, &b, &bn);
-    return (igemm_pair_ok(bn, 27, true) && igemm_max_clusters() > 0) ? 2 : 0;
+    return (igemm_pair_ok(bn, 27, true, n * b.nbw * b.nbh * b.nbd) && igemm_max_clusters() > 0) ? 2 : 0;
 }
 extern "C" int b200_conv3d_wgrad_kernel_id(int64_t h, int64_t w) {
     return (w >= 8 && h >= 16) ? 1 : 0;                           // 0: wgrad_kernel, 1: wgrad_halo_kernel

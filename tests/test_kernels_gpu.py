@@ -42,8 +42,9 @@ CONV_CASES = [
     (1, 64, 64, 128, 7, 16, 16),     # dgrad through the depth-marching kernel (dx has 64 channels, K = 128)
     (1, 96, 96, 64, 1, 16, 8),       # depth-marching with a single slice and a K tail
     (1, 64, 64, 32, 5, 16, 16),      # wgrad depth-pair mode with a half-filled P tile (Cout = 32)
-    (1, 64, 64, 128, 3, 16, 24),     # CTA-pair igemm (N = 128, h-halo) with an odd number of M tiles: 9 -> dummy peer
-    (1, 128, 128, 256, 2, 16, 8),    # CTA-pair igemm, 256-column tile in h-halo mode (half a B tile per CTA)
+    (1, 64, 64, 128, 11, 16, 24),    # CTA-pair igemm (N = 128, h-halo) with an odd number of M tiles: 33 -> dummy peer
+    (1, 128, 128, 256, 33, 16, 8),   # CTA-pair igemm, 256-column tile in h-halo mode (half a B tile per CTA), odd tiles
+    (2, 128, 128, 256, 2, 4, 8),     # 256-column tiles, plain bricks, too few tiles for pair mode
 ]
 
 
