@@ -133,10 +133,12 @@ def rank_volumes(shape, window, stride, rank, world):
 
 @torch.no_grad()
 def sliding_window_logits(model, x, window=(128, 128, 64), stride=(64, 64, 64), rank=0, world=1, group=None,
-                          windows_per_launch=1, reduce=True):
+                          windows_per_launch=9, reduce=True):
     """Average of window logits over a batch of volumes; with world > 1 every rank evaluates its contiguous block of
     the window schedule (rank_windows) and the partial sums are all-reduced.  x: (N, C, D, H, W) on this rank's GPU;
-    only the volumes named by rank_volumes() are read on this rank."""
+    only the volumes named by rank_volumes() are read on this rank.  Windows are evaluated `windows_per_launch` at a
+    time as one batch (measured at 5x256x256x64 on one B200: 222 / 264 / 279 M voxels/s for 1 / 3 / 9 windows per
+    launch — fuller waves on the deep levels); the accumulation order is the schedule order either way."""
     model.eval()
     n, _, D, H, W = x.shape
     sched, (wd, wh, ww) = window_schedule(x.shape, window, stride)
