@@ -55,19 +55,52 @@ class FusedAdam(torch.optim.Optimizer):
         # gradients live in the flat buffer; dropping the views lets the next backward zero it with one memset
         super().zero_grad(set_to_none=set_to_none)
 
+    # ---- checkpoint format: exactly torch.optim.Adam's (utils/trainer.py:262 stores optimizer.state_dict()), so that a
+    # checkpoint written here resumes under torch.optim.Adam and a reference checkpoint resumes here
+    def _param_views(self, flat):
+        from .engine import _slot_view
+        eng = self.model.engine
+        return [_slot_view(flat, eng._slots[id(p)][0], p) for p in self.param_groups[0]["params"]]
+
     def state_dict(self):
-        sd = super().state_dict()
-        sd["b200"] = {"step": self._step,
-                      "exp_avg": None if self.exp_avg is None else self.exp_avg.clone(),
-                      "exp_avg_sq": None if self.exp_avg_sq is None else self.exp_avg_sq.clone()}
-        return sd
+        group = {k: v for k, v in self.param_groups[0].items() if k != "params"}
+        n = len(self.param_groups[0]["params"])
+        group["params"] = list(range(n))
+        state = {}
+        if self.exp_avg is not None and self._step > 0:
+            m, v = self._param_views(self.exp_avg), self._param_views(self.exp_avg_sq)
+            for i in range(n):
+                state[i] = {"step": torch.tensor(float(self._step)), "exp_avg": m[i].clone().contiguous(),
+                            "exp_avg_sq": v[i].clone().contiguous()}
+        return {"state": state, "param_groups": [group]}
 
     def load_state_dict(self, sd):
-        extra = sd.get("b200")
-        super().load_state_dict({k: v for k, v in sd.items() if k != "b200"})
-        if extra is not None:
-            self._step = extra["step"]
-            self._ensure_state()
-            if extra["exp_avg"] is not None:
-                self.exp_avg.copy_(extra["exp_avg"])
-                self.exp_avg_sq.copy_(extra["exp_avg_sq"])
+        groups = sd["param_groups"]
+        if len(groups) != 1 or len(groups[0]["params"]) != len(self.param_groups[0]["params"]):
+            raise ValueError("loaded state dict has a different number of parameter groups / parameters")
+        for k, v in groups[0].items():
+            if k != "params":
+                self.param_groups[0][k] = v
+        state = sd.get("state", {})
+        legacy = sd.get("b200")   # flat-buffer format of earlier builds of this package
+        self._ensure_state()
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        self._step = 0
+        if legacy is not None:
+            self._step = int(legacy["step"])
+            if legacy["exp_avg"] is not None:
+                self.exp_avg.copy_(legacy["exp_avg"])
+                self.exp_avg_sq.copy_(legacy["exp_avg_sq"])
+            return
+        if state:
+            m, v = self._param_views(self.exp_avg), self._param_views(self.exp_avg_sq)
+            steps = set()
+            for i, st in state.items():
+                i = int(i)
+                m[i].copy_(st["exp_avg"].to(m[i].device))
+                v[i].copy_(st["exp_avg_sq"].to(v[i].device))
+                steps.add(int(float(st["step"])))
+            if len(steps) != 1:
+                raise ValueError(f"per-parameter step counts differ ({sorted(steps)}): FusedAdam keeps one step count")
+            self._step = steps.pop()

@@ -306,3 +306,52 @@ def test_full_size_properties_cfg2(pkg, cuda_dev):
         assert torch.equal(mask, (one > 0).float())
         probs = model.predict(x[1:2].contiguous())
         assert torch.equal(probs > 0.5, one > 0)
+
+
+def test_optimizer_checkpoint_interchange_with_torch_adam(pkg, cuda_dev):
+    """FusedAdam.state_dict() is torch.optim.Adam's format (what utils/trainer.py:262 stores): a run checkpointed under
+    one optimizer continues identically under the other, in both directions."""
+    x, y = synth((2, 5, 16, 16, 16), 11, cuda_dev)
+
+    def make():
+        model, _ = build(pkg, 5, 1, cuda_dev, init_features=16)
+        return model.train()
+
+    def run(model, opt, n):
+        for _ in range(n):
+            opt.zero_grad()
+            pkg.BCEDiceLoss()(model(x), y).backward()
+            opt.step()
+
+    # (a) two fused steps -> checkpoint -> one torch.optim.Adam step  ==  three fused steps
+    m_ref = make()
+    o_ref = pkg.FusedAdam(m_ref, lr=1e-3, weight_decay=1e-5)
+    run(m_ref, o_ref, 2)
+    ck_model = {k: v.clone() for k, v in m_ref.state_dict().items()}
+    ck_opt = o_ref.state_dict()
+    assert set(ck_opt) == {"state", "param_groups"} and len(ck_opt["state"]) == 82
+    for i, p in enumerate(o_ref.param_groups[0]["params"]):
+        assert ck_opt["state"][i]["exp_avg"].shape == p.shape and ck_opt["state"][i]["exp_avg"].is_contiguous()
+    run(m_ref, o_ref, 1)
+
+    m_t = make()
+    m_t.load_state_dict(ck_model)
+    o_t = torch.optim.Adam(m_t.parameters(), lr=1e-3, weight_decay=1e-5)
+    o_t.load_state_dict(ck_opt)
+    run(m_t, o_t, 1)
+    for (n1, p1), (_, p2) in zip(m_ref.named_parameters(), m_t.named_parameters()):
+        assert torch.allclose(p1, p2, rtol=1e-4, atol=1e-6), n1
+
+    # (b) two torch.optim.Adam steps -> checkpoint -> third step fused  ==  third step under torch.optim.Adam
+    m_a = make()
+    o_a = torch.optim.Adam(m_a.parameters(), lr=1e-3, weight_decay=1e-5)
+    run(m_a, o_a, 2)
+    m_f = make()
+    m_f.load_state_dict({k: v.clone() for k, v in m_a.state_dict().items()})
+    o_f = pkg.FusedAdam(m_f, lr=5e-2, weight_decay=0.0)          # hyper-parameters come from the checkpoint
+    o_f.load_state_dict(o_a.state_dict())
+    assert o_f.param_groups[0]["lr"] == 1e-3 and o_f.param_groups[0]["weight_decay"] == 1e-5 and o_f._step == 2
+    run(m_f, o_f, 1)
+    run(m_a, o_a, 1)
+    for (n1, p1), (_, p2) in zip(m_a.named_parameters(), m_f.named_parameters()):
+        assert torch.allclose(p1, p2, rtol=1e-4, atol=1e-6), n1
