@@ -246,11 +246,27 @@ class CrossValidationTrainer:
                     "config": {k: v for k, v in self.config.items() if not k.endswith("_loader")}},
                    os.path.join(self.config["save_dir"], f"best_model_fold_{fold_idx}.pth"))
 
-    def train(self):
+    def train(self, rank=None, world=None):
+        """Folds are independent models (train_bph_optimized.py:428-429 runs them one after another).  With
+        `config['fold_parallel']` and an initialised process group (or explicit rank / world) every rank trains folds
+        rank, rank + world, ... on its own GPU — replicas only, no data-path collective — and the per-fold results are
+        gathered on every rank before `cv_results.json` is written by rank 0."""
+        import torch.distributed as dist
+        parallel = bool(self.config.get("fold_parallel", False))
+        if parallel and rank is None and dist.is_available() and dist.is_initialized():
+            rank, world = dist.get_rank(), dist.get_world_size()
+        if not parallel or rank is None:
+            rank, world = 0, 1
         for fold_idx, (tr, va) in enumerate(self.splits):
-            self.train_fold(fold_idx, tr, va)
-        self.save_results()
-        self.print_summary()
+            if fold_idx % world == rank:
+                self.train_fold(fold_idx, tr, va)
+        if world > 1 and dist.is_available() and dist.is_initialized():
+            parts = [None] * world
+            dist.all_gather_object(parts, self.fold_results)
+            self.fold_results = sorted((r for part in parts for r in part), key=lambda r: r["fold"])
+        if rank == 0:
+            self.save_results()
+            self.print_summary()
         return self.fold_results
 
     def save_results(self):

@@ -76,6 +76,20 @@ def test_cross_validation_trainer(pkg, cuda_dev, tmp_path):
     assert cv._fix_labels(x, torch.zeros(1, 1, 8, 8, 8)).shape == x.shape
 
 
+def test_cross_validation_fold_parallel_schedule(pkg, cuda_dev, tmp_path):
+    """fold-parallel mode: rank r of `world` trains folds r, r + world, ... (replicas only); emulated rank by rank"""
+    done = {}
+    for rank in range(2):
+        cv = pkg.CrossValidationTrainer(_cfg(tmp_path, n_splits=3, num_epochs=1, n_cases=6, fold_parallel=True))
+        res = cv.train(rank=rank, world=2)
+        done[rank] = sorted(r["fold"] for r in res)
+    assert done == {0: [0, 2], 1: [1]}
+    assert all(os.path.exists(os.path.join(tmp_path, f"best_model_fold_{k}.pth")) for k in range(3))
+    # without the flag the explicit rank is ignored: every fold runs, as in the reference
+    cv = pkg.CrossValidationTrainer(_cfg(tmp_path, n_splits=2, num_epochs=1, n_cases=4))
+    assert sorted(r["fold"] for r in cv.train(rank=1, world=2)) == [0, 1]
+
+
 def test_validation_metrics(pkg, cuda_dev):
     val = pkg.validate
     a = torch.zeros(4, 4, 4); a[:2] = 1
