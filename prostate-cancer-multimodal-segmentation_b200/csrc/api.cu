@@ -732,7 +732,6 @@ extern "C" int b200_conv3d_wgrad(const b200_act* x, const b200_act* dy, float* d
         if (hp.n_groups == 1) last_splits = splits;
         hp.splits = (int)splits;
         hp.last_splits = (int)last_splits;
-        const long long base_ctas = 0;  // (grid computed below)
         const long long grid_h = (long long)hp.p_tiles * ((long long)(hp.n_groups - 1) * splits + last_splits);
         hp.out = dw;
         const long long cout_ = dy->c;
@@ -758,7 +757,6 @@ extern "C" int b200_conv3d_wgrad(const b200_act* x, const b200_act* dy, float* d
                 attr_h = true;
             }
         }
-        (void)base_ctas;
         wgrad_halo_kernel<<<(int)grid_h, kThreads, smem_h, (cudaStream_t)stream>>>(hp);
         CUDA_TRY(cudaGetLastError());
         return 0;
