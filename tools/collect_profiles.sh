@@ -12,10 +12,10 @@ python tools/timeline_step.py $O/${TAG}_timeline_events.txt > $O/${TAG}_timeline
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $O/${TAG}_launches.csv \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-profile-pass > $O/${TAG}_ncu_list.log 2>&1
 # one full capture per GEMM kernel; launch indices pick the big full-resolution layers of the second step
-# igemm_pair_kernel: 28 launches per step; #13-#15 of the second step = up3.conv1 fprop (928 GF, 256 -> 128 at 64^3),
+# igemm_pair_kernel: 24 launches per step; #11-#13 of the second step = up3.conv1 fprop (928 GF, 256 -> 128 at 64^3),
 # up3.conv2 fprop (464 GF), up4.conv1 dgrad (1855 GF, 64 -> 128 at 128^3).  dmarch_pair_kernel: 6 per step (#1 inc.conv2
 # fprop 928 GF, #2 up4.conv1 fprop 1855 GF), wgrad_halo_kernel: 15 per step (#1 up4.conv2 64 -> 64, #2 up4.conv1).
-for spec in "igemm_pair_kernel:40:3:igemm_pair" "dmarch_pair_kernel:6:2:dmarch_pair" "wgrad_halo_kernel:15:2:wgrad_halo"; do
+for spec in "igemm_pair_kernel:34:3:igemm_pair" "dmarch_pair_kernel:6:2:dmarch_pair" "wgrad_halo_kernel:15:2:wgrad_halo"; do
     IFS=: read -r kern skip cnt name <<< "$spec"
     ncu --set full --clock-control none --import-source on --kernel-name $kern --launch-skip $skip --launch-count $cnt \
         -f -o $O/${TAG}_prof_${name} python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-profile-pass \
