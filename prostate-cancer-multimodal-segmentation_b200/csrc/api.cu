@@ -437,6 +437,10 @@ static int launch_dmarch(const b200_act* in, const void* w_packed, const b200_ac
     p.nbw = pl.nbw; p.nbh = pl.nbh; p.seg_len = pl.seg_len; p.nseg = pl.nseg;
     p.mode = mode;
     p.vec0 = v0; p.vec1 = v1; p.stats = stats;
+    {
+        const char* ab = getenv("B200_DMARCH_ABLATE");   // dev only, see DmarchParams::ablate
+        p.ablate = ab ? atoi(ab) : 0;
+    }
     static bool attr = false;
     {
         std::lock_guard<std::mutex> lk(g_mu);

@@ -90,6 +90,8 @@ struct alignas(64) DmarchParams {
     const float* vec0;
     const float* vec1;
     float* stats;        // [gridDim.x][64][2]
+    int ablate;          // dev only (env B200_DMARCH_ABLATE): 1 = no TMA loads after arming the barriers (MMAs on stale
+                         // shared memory), 2 = no MMAs (loads + epilogue only); results are garbage, timings are not
 };
 
 // Weight-gradient GEMM  G[tap][p][q] += sum_{voxel} P[voxel][p] * Q_tap[voxel][q]
