@@ -168,7 +168,7 @@ static int igemm_block_n(long long ncols, long long m_tiles) {
 }
 // dynamic shared memory of igemm_kernel: 1 KB alignment slack + stages + epilogue-v2 staging + barriers, TMEM pointer,
 // statistics scratch [4][256][2], per-CTA column sums [kMaxStatCols][2], per-tile column vectors [2][256]
-constexpr int kIgemmFixedSmem = 1024 + 8 * (2 * 8 + 4) + 64 + 4 * 256 * 2 * 4 + kMaxStatCols * 2 * 4 + 2 * 256 * 4;
+constexpr int kIgemmFixedSmem = 1024 + 8 * (2 * 8 + 4) + 64 + 64 + 4 * 256 * 2 * 4 + kMaxStatCols * 2 * 4 + 2 * 256 * 4;
 constexpr int kSmemLimit = 227 * 1024;
 static int b_stage_bytes(const IgemmParams& p) {
     const int bn = p.pair ? p.block_n / 2 : p.block_n;   // pair mode: each CTA stages half of the B tile
@@ -177,6 +177,8 @@ static int b_stage_bytes(const IgemmParams& p) {
 // CTA-pair mode of igemm_kernel (clusters of 2, tcgen05.mma.cta_group::2): wide-N 3x3x3 tiles, where halving the B
 // operand traffic per SM lifts the shared-memory bound; MN-major B needs whole 64-column atoms per CTA
 static bool igemm_pair_ok(int block_n, int ntaps, bool b_mn, long long m_tiles) {
+    static const bool disabled = getenv("B200_IGEMM_NOPAIR") != nullptr;   // dev only: single-CTA kernel everywhere
+    if (disabled) return false;
     if (ntaps != 27 || block_n < 128 || block_n % 32 != 0) return false;
     if (m_tiles < 32) return false;   // the 8^3 level: a handful of tiles, the cluster hand-shakes cost more than B saves
     return b_mn ? block_n % 128 == 0 : true;
@@ -187,6 +189,8 @@ static int igemm_stages(int a_bytes, int b_bytes, int c_bytes) {
     const int per_stage = a_bytes + b_bytes;
     int st = (kSmemLimit - kIgemmFixedSmem - c_bytes) / per_stage;
     if (st > 8) st = 8;
+    static const char* cap = getenv("B200_IGEMM_STAGES");   // dev only: ring-depth sensitivity experiments
+    if (cap && atoi(cap) >= 2 && atoi(cap) < st) st = atoi(cap);
     return st;
 }
 static size_t igemm_smem(int stages, int a_bytes, int b_bytes, int c_bytes) {
@@ -276,6 +280,10 @@ static int launch_igemm(IgemmParams& p, cudaStream_t s, int* grid_out) {
         }
     }
     const long long m_tiles = (long long)p.nbw * p.nbh * p.nbd * p.nbatch;
+    {
+        const char* ab = getenv("B200_IGEMM_ABLATE");   // dev only, see IgemmParams::ablate
+        p.ablate = ab ? atoi(ab) : 0;
+    }
     if (p.pair) {
         const int ncl = igemm_max_clusters();
         if (ncl <= 0) return fail(B200_ERR_CUDA, "igemm: no co-resident CTA pair fits on this device");

@@ -58,7 +58,8 @@ DEV void igemm_body(const IgemmParams& p) {
     auto tfull_bar = [&](uint32_t s) { return bar_base + 8 * (2 * nst + s); };
     auto tempty_bar = [&](uint32_t s) { return bar_base + 8 * (2 * nst + 2 + s); };
     const uint32_t tmem_ptr_smem = bar_base + 8 * (2 * nst + 4);
-    const uint32_t scratch_off = (tmem_ptr_smem + 16 - smem_base + 15u) & ~15u;
+    auto sink_bar = [&](uint32_t s) { return tmem_ptr_smem + 16 + 8 * s; };   // dev ablation 3 only
+    const uint32_t scratch_off = (tmem_ptr_smem + 16 + 64 - smem_base + 15u) & ~15u;
     float* scratch = reinterpret_cast<float*>(smem_gen + scratch_off);  // [4 warps][256 cols][2]
     float* colacc = scratch + 4 * 256 * 2;                              // [ncols <= kMaxStatCols][2], per-CTA running sums
     float* colvec = colacc + 2 * kMaxStatCols;                          // epilogue v2: [2][256] per-tile bias | scale, shift
@@ -76,6 +77,7 @@ DEV void igemm_body(const IgemmParams& p) {
             mbar_init(tfull_bar(s), 1);
             mbar_init(tempty_bar(s), 128 * mmul);   // pair: the epilogue threads of both CTAs arrive on the leader's
         }
+        for (uint32_t s = 0; s < nst; ++s) mbar_init(sink_bar(s), 1);   // dev ablation 3: loads the MMAs do not wait for
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -103,6 +105,7 @@ DEV void igemm_body(const IgemmParams& p) {
         // ===================================================================== TMA producer
         // The whole warp walks the loop (uniform control flow, barrier polls by all lanes); one elected lane issues.
         PipeState ps;
+        uint32_t sink_uses = 0;   // dev ablation 3: stages issued so far
         const int kc_blocks = p.kc_blocks, ntaps = p.ntaps / p.group, n_tiles = p.n_tiles, group = p.group;
         for (int tile = unit0; tile < total_tiles; tile += unit_stride) {
             int mt = tile / n_tiles;
@@ -120,8 +123,16 @@ DEV void igemm_body(const IgemmParams& p) {
                 for (int kc = 0; kc < kc_blocks; ++kc) {
                     mbar_wait(empty_bar(ps.stage), ps.phase ^ 1);
                     if (elect_one()) {
-                        const uint32_t fb = full_bar(ps.stage);
-                        if (!kPair) {
+                        uint32_t fb = full_bar(ps.stage);
+                        if (p.ablate == 3) {   // loads issued, the MMAs do not wait for them: contention without latency
+                            if (rank == 0) mbar_arrive(fb);
+                            fb = sink_bar(ps.stage);
+                            if (rank == 0 && sink_uses >= nst)   // this slot's previous loads have landed
+                                while (!mbar_try_wait(fb, ((sink_uses / nst) - 1) & 1)) {}
+                        }
+                        if (p.ablate == 1) {
+                            if (rank == 0) mbar_arrive(fb);
+                        } else if (!kPair) {
                             mbar_arrive_expect_tx(fb, a_bytes + b_bytes);
                             tma_load_5d(smem_a + ps.stage * a_bytes, amap, fb, kc * 64, cw, ch, cd, nb);
                             if (p.b_mn) {
@@ -146,10 +157,18 @@ DEV void igemm_body(const IgemmParams& p) {
                         }
                     }
                     __syncwarp();
+                    ++sink_uses;
                     ps.advance(nst);
                 }
             }
         }
+        if (p.ablate == 3 && rank == 0 && elect_one()) {   // no load may be in flight when the CTAs exit
+            for (uint32_t s = 0; s < nst; ++s) {
+                const uint32_t uses = sink_uses / nst + (s < sink_uses % nst ? 1u : 0u);
+                if (uses > 0) while (!mbar_try_wait(sink_bar(s), (uses - 1) & 1)) {}
+            }
+        }
+        __syncwarp();
     } else if (warp == 1 && rank == 0) {
         // ===================================================================== MMA issuer (pair mode: leader CTA only)
         // Lean loop: descriptors are base + stage offset (low word only), no divisions, one elected lane issues.
@@ -179,7 +198,7 @@ DEV void igemm_body(const IgemmParams& p) {
                     if (elect_one()) {
                         const uint64_t a_st = a_desc0 + ps.stage * a_step;
                         const uint64_t b_st = b_desc0 + ps.stage * b_step;
-                        for (int g = 0; g < group; ++g) {
+                        for (int g = 0; g < group && p.ablate != 2; ++g) {
                             const uint64_t a_desc = a_st + (g == 0 ? goff0 : (g == 1 ? goff1 : goff2));
                             const uint64_t b_desc = b_st + g * bt_step;
                             // 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (>>4) address field

@@ -34,6 +34,7 @@ struct alignas(64) IgemmParams {
     CUtensorMap c_map[kMaxMaps];  // epilogue v2: TMA store maps of the output (one per output offset group)
     int epi_v2;         // 1: stage the bf16 tile in shared memory, TMA store, statistics from the staged tile
     int pair;           // 1: launched as clusters of two CTAs; M = 256 tcgen05.mma.cta_group::2, B tile split between them
+    int ablate;         // dev only (env B200_IGEMM_ABLATE): 1 = barriers armed without TMA loads, 2 = no MMAs issued
     int ntaps;
     int a_map_of_tap[kMaxTaps];
     int tap_dw[kMaxTaps], tap_dh[kMaxTaps], tap_dd[kMaxTaps];
