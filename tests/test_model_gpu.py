@@ -355,3 +355,30 @@ def test_optimizer_checkpoint_interchange_with_torch_adam(pkg, cuda_dev):
     run(m_a, o_a, 1)
     for (n1, p1), (_, p2) in zip(m_a.named_parameters(), m_f.named_parameters()):
         assert torch.allclose(p1, p2, rtol=1e-4, atol=1e-6), n1
+
+
+@pytest.mark.parametrize("base,shape,ncls", [(48, (2, 5, 32, 32, 32), 1), (16, (1, 5, 16, 48, 24), 3)])
+def test_other_widths_and_class_counts_vs_oracle(pkg, cuda_dev, base, shape, ncls):
+    """channel counts that are not powers of two (48 ... 768: partial N tiles, K tails, the scalar head kernel) and a
+    3-class head on a non-cubic volume: loss within 1e-3 and logits within 2e-2 of the fp32 oracle"""
+    model, sd = build(pkg, 0, ncls, cuda_dev, init_features=base)
+    model.train()
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(*shape, generator=g).to(cuda_dev)
+    y = (torch.rand(shape[0], ncls, *shape[2:], generator=g) < 0.1).float().to(cuda_dev)
+    logits = model(x)
+    loss = pkg.BCEDiceLoss()(logits, y)
+    loss.backward()
+    with torch.no_grad():
+        o_logits = oracle.unet3d_forward(x, {k: v.clone() for k, v in sd.items()}, training=True)
+        o_loss = oracle.bce_dice_loss(o_logits.float(), y)
+    assert abs(loss.item() - o_loss.item()) < 1e-3
+    assert rel_l2(logits, o_logits) < TOL_LAYER
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
+
+
+def test_training_width_limit_is_reported(pkg, cuda_dev):
+    """the BatchNorm partial sums of one CTA hold 1024 columns: base 80 (1280 channels at the bottom) is refused"""
+    model = pkg.UNet3D(5, 1, init_features=80).to(cuda_dev).train()
+    with pytest.raises(pkg.B200Error, match="1024 output channels"):
+        model(torch.randn(1, 5, 32, 32, 32, device=cuda_dev))
