@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--base", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile-pass", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="issue every launch eagerly (no CUDA-graph replay)")
     ap.add_argument("--dump-kernels", default=None, help="write the per-launch GEMM timing table of the profile pass")
     ap.add_argument("--workload", default="train", choices=["train", "infer"],
                     help="train: BASELINE configs[1]/[2] (default, the headline); infer: configs[3] sliding-window "
@@ -289,13 +290,18 @@ def main():
     y = y_host.to(dev)
     vox_step = B * D * H * W * world
 
-    def step(xx, yy):
+    def eager_step(xx, yy):
         opt.zero_grad()
         out = model(xx)
         loss = crit(out, yy)
         loss.backward()
         opt.step()
         return loss
+
+    # what BaseTrainer._step runs: on one process the step is replayed from a CUDA graph after two eager steps
+    # (graph.GraphedTrainStep; same kernels, same arithmetic); data-parallel ranks issue it eagerly
+    graphed = pkg.GraphedTrainStep(model, crit, opt) if (world == 1 and not args.no_graph) else None
+    step = graphed if graphed is not None else eager_step
 
     def barrier():
         if world > 1:
@@ -366,7 +372,7 @@ def main():
         recs = []
         ops.profile_hook = lambda k, tag, fl, a, b: recs.append((k, tag, fl, a, b))
         model.engine.overlap_wgrad = False   # per-kernel durations: no concurrent side-stream kernels in this pass
-        step(x, y)
+        eager_step(x, y)
         torch.cuda.synchronize()
         model.engine.overlap_wgrad = True
         ops.profile_hook = None
@@ -424,7 +430,11 @@ def main():
             "config": {"workload": f"UNet3D(5->1, base {args.base}) training step fwd+BCEDice+bwd+Adam, "
                                    f"batch {B}/GPU, 5x{D}x{H}x{W} (BASELINE configs[1]; N=8 -> configs[2])",
                        "global_batch": B * world, "per_gpu_batch": B, "volume": [D, H, W],
-                       "parallelism": f"dp{world}", "l2": "per-step working set (GBs of activations) exceeds the "
+                       "parallelism": f"dp{world}",
+                       "launch": ("CUDA-graph replay of the step" if graphed is not None and graphed.replays > 0
+                                  else "eager launches" + (f" ({graphed.disabled})" if graphed is not None and
+                                                           graphed.disabled else "")),
+                       "l2": "per-step working set (GBs of activations) exceeds the "
                                                            "126 MB L2; no explicit flush",
                        "loss": final_loss},
             "clocks": clocks,

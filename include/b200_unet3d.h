@@ -149,11 +149,13 @@ int b200_loss_bwd(const float* logits, const float* target, int64_t n, float bce
 /* ---- optimizer (torch.optim.Adam, utils/trainer.py:113-117,192) ---------------------------------------- */
 /* fused over a flat fp32 buffer: g = grad*grad_scale + wd*p ; Adam moments ; bias-corrected update.
  * step is the 1-based step count.  If found_inf != NULL and *found_inf != 0 the update is skipped.
- * bf16_shadow (nullable): bf16 copy of the updated parameters written in the same pass. */
+ * bf16_shadow (nullable): bf16 copy of the updated parameters written in the same pass.
+ * dyn_scalars (nullable): device float[3] = (lr / (1 - beta1^step), sqrt(1 - beta2^step), grad_scale) read by the kernel
+ * instead of the values derived from lr / step / grad_scale, so that one captured launch (CUDA graph) serves every step. */
 int b200_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                    double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step,
                    double grad_scale,
-                   const float* found_inf, void* bf16_shadow, void* stream);
+                   const float* found_inf, void* bf16_shadow, const float* dyn_scalars, void* stream);
 /* out[i] = bf16(x[i]) — operand shadow of the flat parameter buffer when a foreign optimizer updated it */
 int b200_cast_bf16(const float* x, int64_t n, void* out, void* stream);
 /* sum of squares of a flat fp32 buffer -> out[0] (+=) ; nonfinite flag -> out[1] (clip_grad_norm_/GradScaler) */

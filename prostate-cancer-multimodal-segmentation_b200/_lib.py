@@ -56,7 +56,7 @@ SIGNATURES = {
     "b200_head_bwd": (_i32, [_AP, _vp, _i32, _vp, _AP, _vp, _vp, _vp]),
     "b200_loss_fwd": (_i32, [_vp, _vp, _i64, _f32, _f32, _f32, _vp, _vp, _vp, _vp]),
     "b200_loss_bwd": (_i32, [_vp, _vp, _i64, _f32, _f32, _f32, _vp, _vp, _vp, _vp]),
-    "b200_adam_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _f64, _f64, _f64, _f64, _f64, _i64, _f64, _vp, _vp, _vp]),
+    "b200_adam_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _f64, _f64, _f64, _f64, _f64, _i64, _f64, _vp, _vp, _vp, _vp]),
     "b200_cast_bf16": (_i32, [_vp, _i64, _vp, _vp]),
     "b200_sumsq": (_i32, [_vp, _i64, _vp, _vp]),
     "b200_fill_zero": (_i32, [_AP, _vp]),

@@ -1044,13 +1044,15 @@ extern "C" int b200_loss_bwd(const float* logits, const float* target, int64_t n
 }
 extern "C" int b200_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                    double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step,
-                   double grad_scale, const float* found_inf, void* bf16_shadow, void* stream) {
+                   double grad_scale, const float* found_inf, void* bf16_shadow, const float* dyn_scalars,
+                   void* stream) {
     REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, "adam_step: bad arguments");
     REQUIRE(((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) |
               reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) == 0,
             "adam_step: buffers must be 16-byte aligned");
     CUDA_TRY(launch_adam(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale,
-                         found_inf, reinterpret_cast<__nv_bfloat16*>(bf16_shadow), sm_count(), (cudaStream_t)stream));
+                         found_inf, reinterpret_cast<__nv_bfloat16*>(bf16_shadow), dyn_scalars, sm_count(),
+                         (cudaStream_t)stream));
     return 0;
 }
 extern "C" int b200_cast_bf16(const float* x, int64_t n, void* out, void* stream) {

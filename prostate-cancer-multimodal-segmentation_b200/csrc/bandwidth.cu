@@ -1120,9 +1120,14 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
                                                    float* __restrict__ m, float* __restrict__ v, long long n,
                                                    float step_size, float b2, float w1, float w2, float eps,
                                                    float wd, float bc2_sqrt, float gscale, const float* found_inf,
-                                                   __nv_bfloat16* __restrict__ shadow) {
+                                                   __nv_bfloat16* __restrict__ shadow, const float* __restrict__ dyn) {
     // torch.optim.Adam arithmetic: m.lerp_(g, 1-b1); v.mul_(b2).addcmul_(g, g, 1-b2); p.addcdiv_(m, sqrt(v)/bc2+eps)
     if (found_inf && *found_inf != 0.f) return;
+    if (dyn) {   // step-dependent scalars from device memory: the launch can be replayed from a CUDA graph
+        step_size = __ldg(dyn);
+        bc2_sqrt = __ldg(dyn + 1);
+        gscale = __ldg(dyn + 2);
+    }
     const long long n4 = n >> 2;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
          i += (long long)gridDim.x * blockDim.x) {
@@ -1165,12 +1170,12 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 }
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, long long n, double lr, double b1, double b2,
                         double eps, double wd, long long step, double gscale, const float* found_inf,
-                        __nv_bfloat16* shadow, int sms, cudaStream_t s) {
+                        __nv_bfloat16* shadow, const float* dyn, int sms, cudaStream_t s) {
     const double bc1 = 1.0 - pow(b1, (double)step);
     const double bc2 = 1.0 - pow(b2, (double)step);
     adam_kernel<<<grid_for(n / 4 + 1, 256, sms, 8), 256, 0, s>>>(p, g, m, v, n, (float)(lr / bc1), (float)b2,
                                                                 (float)(1.0 - b1), (float)(1.0 - b2), (float)eps,
-                                                                (float)wd, (float)sqrt(bc2), (float)gscale, found_inf, shadow);
+                                                                (float)wd, (float)sqrt(bc2), (float)gscale, found_inf, shadow, dyn);
     return cudaGetLastError();
 }
 

@@ -64,7 +64,7 @@ cudaError_t launch_loss_bwd(const float* z, const float* t, long long n, float b
                             const float* sums, const float* gout, float* dz, int sms, cudaStream_t s);
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, long long n, double lr, double b1, double b2,
                         double eps, double wd, long long step, double gscale, const float* found_inf,
-                        __nv_bfloat16* shadow, int sms, cudaStream_t s);
+                        __nv_bfloat16* shadow, const float* dyn, int sms, cudaStream_t s);
 cudaError_t launch_cast_bf16(const float* x, long long n, __nv_bfloat16* out, int sms, cudaStream_t s);
 cudaError_t launch_sumsq(const float* x, long long n, float* out, int sms, cudaStream_t s);
 cudaError_t launch_fill_zero(View v, int sms, cudaStream_t s);

@@ -271,11 +271,11 @@ def loss_bwd(logits, target, bce_w, dice_w, smooth, sums, gout, dlogits):
 
 
 def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0,
-              found_inf=None, bf16_shadow=None):
+              found_inf=None, bf16_shadow=None, dyn_scalars=None):
     _launched(1)
     check(_lib.load().b200_adam_step(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), lr, beta1,
                                      beta2, eps, weight_decay, step, grad_scale, ptr(found_inf), ptr(bf16_shadow),
-                                     stream_ptr()), "adam_step")
+                                     ptr(dyn_scalars), stream_ptr()), "adam_step")
 
 
 def cast_bf16(x, out):

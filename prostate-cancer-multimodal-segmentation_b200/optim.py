@@ -25,6 +25,8 @@ class FusedAdam(torch.optim.Optimizer):
         self.exp_avg_sq = None
         self.grad_scale = 1.0     # multiply gradients on the fly (1/world for DP sums, 1/loss_scale, clip coefficient)
         self.found_inf = None     # optional device flag: skip the update when non-zero
+        self._dyn = None          # device float[3] read by a captured launch (see graph.GraphedTrainStep)
+        self._dyn_host = None
 
     def _ensure_state(self):
         eng = self.model.engine
@@ -43,6 +45,15 @@ class FusedAdam(torch.optim.Optimizer):
                 loss = closure()
         eng = self._ensure_state()
         g = self.param_groups[0]
+        if torch.cuda.is_current_stream_capturing():
+            # the launch being recorded reads its step-dependent scalars from device memory; the step counter is
+            # advanced by whoever replays the graph (refresh_dynamic_scalars)
+            if self._dyn is None:
+                raise RuntimeError("FusedAdam.step() under CUDA-graph capture needs refresh_dynamic_scalars() first")
+            ops.adam_step(eng.flat_param, eng.flat_grad, self.exp_avg, self.exp_avg_sq, g["lr"], g["betas"][0],
+                          g["betas"][1], g["eps"], g["weight_decay"], max(self._step, 1), self.grad_scale,
+                          self.found_inf, bf16_shadow=eng.flat_bf16, dyn_scalars=self._dyn)
+            return loss
         self._step += 1
         ops.adam_step(eng.flat_param, eng.flat_grad, self.exp_avg, self.exp_avg_sq, g["lr"], g["betas"][0],
                       g["betas"][1], g["eps"], g["weight_decay"], self._step, self.grad_scale, self.found_inf,
@@ -50,6 +61,25 @@ class FusedAdam(torch.optim.Optimizer):
         eng.external_epoch += 1
         eng._shadow_key = eng.current_key()  # the bf16 operand shadow was rewritten in the same pass
         return loss
+
+    def refresh_dynamic_scalars(self, advance: bool = True):
+        """For replays of a captured step: advance the step count and upload (lr / (1 - b1^t), sqrt(1 - b2^t),
+        grad_scale) — computed in double exactly as the eager launch does — to the device scalars the captured
+        launch reads.  The upload is an asynchronous copy from pinned memory on the current stream."""
+        self._ensure_state()
+        g = self.param_groups[0]
+        if advance:
+            self._step += 1
+        t = max(self._step, 1)
+        if self._dyn is None:
+            self._dyn = torch.zeros(3, device=self.exp_avg.device, dtype=torch.float32)
+            self._dyn_host = torch.zeros(3, dtype=torch.float32).pin_memory()
+        bc1 = 1.0 - g["betas"][0] ** t
+        bc2 = 1.0 - g["betas"][1] ** t
+        self._dyn_host[0] = g["lr"] / bc1
+        self._dyn_host[1] = bc2 ** 0.5
+        self._dyn_host[2] = self.grad_scale
+        self._dyn.copy_(self._dyn_host, non_blocking=True)
 
     def zero_grad(self, set_to_none: bool = True):
         # gradients live in the flat buffer; dropping the views lets the next backward zero it with one memset

@@ -68,6 +68,13 @@ class BaseTrainer:
 
     # ---- one step / epoch
     def _step(self, images, labels):
+        clip = self.config.get("clip_grad_norm")
+        if isinstance(self.optimizer, FusedAdam) and not clip and self.config.get("cuda_graph", True):
+            # the whole step replayed from a CUDA graph after two eager steps (graph.py); same arithmetic
+            if getattr(self, "_graphed", None) is None:
+                from .graph import GraphedTrainStep
+                self._graphed = GraphedTrainStep(self.model, self.criterion, self.optimizer)
+            return self._graphed(images, labels)
         self.optimizer.zero_grad()
         outputs = self.model(images)
         loss = self.criterion(outputs, labels)

@@ -382,3 +382,46 @@ def test_training_width_limit_is_reported(pkg, cuda_dev):
     model = pkg.UNet3D(5, 1, init_features=80).to(cuda_dev).train()
     with pytest.raises(pkg.B200Error, match="1024 output channels"):
         model(torch.randn(1, 5, 32, 32, 32, device=cuda_dev))
+
+
+def test_graphed_train_step_matches_eager(pkg, cuda_dev):
+    """GraphedTrainStep: two eager steps, then every call replays the captured step.  Each replayed step is compared
+    with an eager step taken from the same model / optimizer state (whole trajectories cannot be compared tightly:
+    Adam's sign-like early updates amplify the RED-order noise of near-zero gradients)."""
+    batches = [synth((2, 5, 16, 16, 16), 5 + i, cuda_dev) for i in range(2)]
+    crit = pkg.BCEDiceLoss()
+    model, _ = build(pkg, 2, 1, cuda_dev, init_features=16)
+    model.train()
+    opt = pkg.FusedAdam(model, lr=1e-3, weight_decay=1e-5)
+    stepper = pkg.GraphedTrainStep(model, crit, opt)
+    ref, _ = build(pkg, 2, 1, cuda_dev, init_features=16)
+    ref.train()
+    ref_opt = pkg.FusedAdam(ref, lr=1e-3, weight_decay=1e-5)
+    for i in range(6):
+        xb, yb = batches[i % 2]
+        if i == 4:
+            opt.param_groups[0]["lr"] = 2.5e-4          # a scheduler changes the LR between replays
+        # the reference model takes the same step eagerly from the same state
+        ref.load_state_dict({k: v.clone() for k, v in model.state_dict().items()})
+        ref_opt.load_state_dict(opt.state_dict())
+        before = {n: p.detach().clone() for n, p in model.named_parameters()}
+        loss = stepper(xb, yb).item()
+        ref_opt.zero_grad()
+        ref_loss = crit(ref(xb), yb)
+        ref_loss.backward()
+        ref_opt.step()
+        assert abs(loss - ref_loss.item()) < 1e-4, (i, loss, ref_loss.item())
+        for (n, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
+            if not is_dead_bias(n):
+                assert rel_l2(p.detach() - before[n], q.detach() - before[n]) < 2e-2, (i, n)
+        assert opt._step == ref_opt._step == i + 1
+        assert model.inc.conv[1].num_batches_tracked.item() == i + 1
+    assert stepper.disabled is None and stepper.replays == 4
+    # an eager forward after replays sees the updated weights (operand packs are refreshed)
+    model.eval()
+    with torch.no_grad():
+        a = model(batches[0][0])
+        b = model(batches[0][0])
+    assert torch.equal(a, b) and torch.isfinite(a).all()
+    with pytest.raises(TypeError):
+        pkg.GraphedTrainStep(model, pkg.BCEDiceLoss(), torch.optim.Adam(model.parameters()))
