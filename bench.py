@@ -300,7 +300,9 @@ def main():
 
     # what BaseTrainer._step runs: on one process the step is replayed from a CUDA graph after two eager steps
     # (graph.GraphedTrainStep; same kernels, same arithmetic); data-parallel ranks issue it eagerly
-    graphed = pkg.GraphedTrainStep(model, crit, opt) if (world == 1 and not args.no_graph) else None
+    graph_dp = os.environ.get("B200_GRAPH_DP") == "1"   # experiment: record the NCCL all-reduces too
+    graphed = (pkg.GraphedTrainStep(model, crit, opt, capture_collectives=graph_dp)
+               if ((world == 1 or graph_dp) and not args.no_graph) else None)
     step = graphed if graphed is not None else eager_step
 
     def barrier():

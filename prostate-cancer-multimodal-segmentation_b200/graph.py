@@ -16,11 +16,13 @@ from .optim import FusedAdam
 
 
 class GraphedTrainStep:
-    def __init__(self, model, criterion, optimizer, eager_steps: int = 2, max_graphs: int = 2):
+    def __init__(self, model, criterion, optimizer, eager_steps: int = 2, max_graphs: int = 2,
+                 capture_collectives: bool = False):
         if not isinstance(optimizer, FusedAdam):
             raise TypeError("GraphedTrainStep needs the FusedAdam optimizer (its step reads device-side scalars)")
         self.model, self.criterion, self.optimizer = model, criterion, optimizer
         self.eager_steps, self.max_graphs = eager_steps, max_graphs
+        self.capture_collectives = capture_collectives   # record the NCCL bucket all-reduces too (data-parallel ranks)
         self._seen = {}      # shape key -> eager steps taken
         self._graphs = {}    # shape key -> (graph, static_x, static_y, static_loss, launches)
         self.disabled = None  # reason, once capture has failed or is not applicable
@@ -45,7 +47,8 @@ class GraphedTrainStep:
 
     def __call__(self, x, y):
         eng = self.model.engine
-        if self.disabled is None and (eng.grad_sync is not None or not self.model.training):
+        if self.disabled is None and ((eng.grad_sync is not None and not self.capture_collectives) or
+                                      not self.model.training):
             self.disabled = "data-parallel gradient sync installed" if eng.grad_sync is not None else "model in eval mode"
         if self.disabled is not None or not x.is_cuda:
             return self._eager(x, y)
