@@ -450,6 +450,11 @@ def main():
             line["config"]["allreduce_buckets_per_step"] = sync.launched // max(1, args.steps * 2 + args.warmup + 1)
         print(json.dumps(line), flush=True)
     if world > 1:
+        # recorded NCCL kernels (B200_GRAPH_DP=1) keep the communicator busy until the graph object is gone
+        graphed = step = None  # noqa: F841
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
         dist.barrier()
         dist.destroy_process_group()
 

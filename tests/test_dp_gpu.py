@@ -79,3 +79,52 @@ def test_two_rank_dp_matches_emulation():
         assert ok, f"rank {r}: replicas diverged or too few buckets"
         assert rel < 1e-3, f"rank {r}: all-reduced gradient vs emulation rel-L2 {rel}"
         assert relw < 5e-2, f"rank {r}: Adam update vs emulation rel-L2 {relw}"
+
+
+def _worker_graph(rank, world, port, out):
+    """data-parallel ranks replaying the step from a CUDA graph that also holds the NCCL bucket all-reduces"""
+    import gc
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    pkg = load_pkg()
+    par = pkg.parallel
+    torch.manual_seed(100 + rank)
+    model = pkg.UNet3D(5, 1, init_features=16).to(dev).train()
+    opt = pkg.FusedAdam(model, lr=1e-3, weight_decay=1e-5)
+    par.make_data_parallel(model, opt, bucket_mb=0.25)
+    stepper = pkg.GraphedTrainStep(model, pkg.BCEDiceLoss(), opt, capture_collectives=True)
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(2 * world, 5, 32, 32, 32, generator=g)
+    y = (torch.rand(2 * world, 1, 32, 32, 32, generator=g) > 0.85).float()
+    sl = par.shard_batch(x.shape[0], rank, world)        # every rank trains on its own shard
+    xs, ys = x[sl].to(dev), y[sl].to(dev)
+    ok, losses = True, []
+    for i in range(5):
+        losses.append(stepper(xs, ys).item())
+        torch.cuda.synchronize()
+        for t in (model.engine.flat_param, model.engine.flat_grad):   # identical on every rank only if the recorded
+            ref = t.clone()                                            # all-reduces really ran in the replay
+            dist.broadcast(ref, 0)
+            ok = ok and torch.equal(ref, t)
+    out[rank] = (bool(ok), stepper.replays, stepper.disabled, losses)
+    del stepper
+    gc.collect()
+    torch.cuda.synchronize()
+    dist.destroy_process_group()
+
+
+def test_two_rank_dp_graph_replay_keeps_replicas_identical():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_graph, args=(world, 29634, out), nprocs=world, join=True)
+    for r in range(world):
+        ok, replays, disabled, losses = out[r]
+        assert disabled is None and replays == 3, (replays, disabled)
+        assert ok, f"rank {r}: replicas or all-reduced gradients differ between ranks after a replayed step"
+        assert losses[-1] < losses[0]
