@@ -353,6 +353,15 @@ def test_adam_matches_torch(ops, cuda_dev):
     st = opt.state[pr]
     assert torch.allclose(m, st["exp_avg"], rtol=1e-5, atol=1e-7)
     assert torch.allclose(v, st["exp_avg_sq"], rtol=1e-5, atol=1e-9)
+    # device-side scalars (the form a CUDA-graph replay uses): same result bit for bit, whatever the host scalars say
+    grad = torch.randn(n, generator=g).to(cuda_dev)
+    pa, ma, va = p.clone(), m.clone(), v.clone()
+    pb, mb, vb = p.clone(), m.clone(), v.clone()
+    ops.adam_step(pa, grad, ma, va, 1e-3, 0.9, 0.999, 1e-8, 1e-5, 4, grad_scale=0.5)
+    dyn = torch.tensor([1e-3 / (1 - 0.9 ** 4), (1 - 0.999 ** 4) ** 0.5, 0.5], device=cuda_dev, dtype=torch.float32)
+    ops.adam_step(pb, grad, mb, vb, 123.0, 0.9, 0.999, 1e-8, 1e-5, 99, grad_scale=7.0, dyn_scalars=dyn)
+    torch.cuda.synchronize()
+    assert torch.equal(pa, pb) and torch.equal(ma, mb) and torch.equal(va, vb)
 
 
 def test_pack_input_and_unpack(ops, cuda_dev):
