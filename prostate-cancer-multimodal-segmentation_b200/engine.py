@@ -279,6 +279,8 @@ class Engine:
         self.flat_bf16 = None    # bf16 shadow of flat_param: the conv kernels' weight operand
         self._shadow_key = None
         self._slots = None       # id(param) -> (offset, numel)
+        self.keep_tape = False   # parity tooling: keep the last forward's tape in .last_tape (see layer_outputs)
+        self.last_tape = None
 
     # ------------------------------------------------------------------ parameters
     def ordered_params(self):
@@ -444,7 +446,40 @@ class Engine:
         probs = torch.empty_like(logits) if want_probs else None
         ops.head_fwd(cur, m.outc.weight.data.view(m.n_classes, -1), m.outc.bias.data, logits, probs)
         tape.cats, tape.dcs, tape.pooled, tape.dec_in, tape.pads, tape.last = cats, dcs, pooled, dec_in, pads, cur
+        if self.keep_tape:
+            self.last_tape = tape
         return logits, probs, tape
+
+    def layer_outputs(self, tape: _Tape):
+        """(reference module path, ActView) of every tensor a training-mode forward keeps: raw conv outputs at
+        '<block>.0' / '<block>.3', post-ReLU activations at '<block>.2' / '<block>.5', transposed-conv outputs at
+        'upJ.up' — the keys the oracle's `taps` use (parity tests compare layer by layer).  Call before backward
+        (backward releases the tape as it goes)."""
+        f = self.model.init_features
+        ch = [f, 2 * f, 4 * f, 8 * f, 16 * f]
+        outs = {"inc": ActView(tape.cats[0], 0, ch[0])}
+        for k in (1, 2, 3):
+            outs[f"down{k}"] = ActView(tape.cats[k], 0, ch[k])
+        outs["down4"] = tape.dec_in[0]
+        for j in (1, 2, 3):
+            outs[f"up{j}"] = tape.dec_in[j]
+        outs["up4"] = tape.last
+        prefix = {"inc": "inc.conv"}
+        for k in (1, 2, 3, 4):
+            prefix[f"down{k}"] = f"down{k}.maxpool_conv.1.conv"
+        for j in (1, 2, 3, 4):
+            prefix[f"up{j}"] = f"up{j}.conv.conv"
+        for name in ["inc", "down1", "down2", "down3", "down4", "up1", "up2", "up3", "up4"]:
+            st = tape.dcs[name]
+            if name.startswith("up"):
+                k = 4 - int(name[2])
+                yield f"{name}.up", ActView(tape.cats[k], ch[k], ch[k])
+            if st is None:
+                continue
+            yield f"{prefix[name]}.0", st.y1
+            yield f"{prefix[name]}.2", st.a1
+            yield f"{prefix[name]}.3", st.y2
+            yield f"{prefix[name]}.5", outs[name]
 
     # ------------------------------------------------------------------ backward
     def _begin_grads(self):
