@@ -188,17 +188,8 @@ int b200_seg_counts(const float* score, const float* label, int64_t nsamples, in
 int b200_conv3d_kernel_id(int64_t n, int64_t d, int64_t h, int64_t w, int64_t out_cols);
 int b200_conv3d_wgrad_kernel_id(int64_t h, int64_t w);
 
-/* dev probe (not on the hot path): cycles for `iters` x 4 tcgen05.mma (M=128, N=n, K=16, SS mode) per CTA, operands
- * cycling through `stages` shared-memory slots; out_cycles[blocks] (int64) */
-int b200_probe_mma(int n, int iters, int stages, long long* out_cycles, int blocks, void* stream);
-/* same with UMMA M (64 or 128) and operand majorness (0: both K-major, 1: both MN-major) selectable */
-int b200_probe_mma2(int m, int n, int mn_major, int iters, int stages, long long* out_cycles, int blocks,
-                    void* stream);
-
-/* dev probe of the CTA-pair (cta_group::2) primitives: d_out[pairs][256][n] fp32 = A[256][k] * B[n][k]^T (bf16, k
- * contiguous) computed by `pairs` clusters of two CTAs, the MMA chain repeated `iters` times; cycles[pairs] (int64) */
-int b200_probe_pair(const void* a, const void* b, int n, int k, int iters, float* d_out, long long* cycles, int pairs,
-                    void* stream);
+/* The tcgen05 micro-probes and kernel ablation switches used during development are NOT part of this ABI: they are
+ * compiled only into the development library (libb200unet3d_dev.so, -DB200_DEV) and declared in csrc/dev_api.h. */
 
 #ifdef __cplusplus
 }

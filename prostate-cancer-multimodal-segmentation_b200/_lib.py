@@ -67,10 +67,17 @@ SIGNATURES = {
     "b200_seg_counts": (_i32, [_vp, _vp, _i64, _i64, _f32, _vp, _vp]),
     "b200_conv3d_kernel_id": (_i32, [_i64, _i64, _i64, _i64, _i64]),
     "b200_conv3d_wgrad_kernel_id": (_i32, [_i64, _i64]),
+}
+
+# development library only (build.build(dev=True), -DB200_DEV): tcgen05 micro-probes and kernel ablation switches
+DEV_SIGNATURES = {
     "b200_probe_pair": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp]),
     "b200_probe_mma": (_i32, [_i32, _i32, _i32, _vp, _i32, _vp]),
     "b200_probe_mma2": (_i32, [_i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
+    "b200_dev_set_ablation": (_i32, [_i32, _i32, _i32, _i32]),
 }
+
+ABI_VERSION = 2   # must equal b200_abi_version() of the loaded library
 
 _lib = None
 
@@ -79,22 +86,41 @@ def lib_path() -> str:
     return _build.LIB_PATH
 
 
-def load():
-    """dlopen the C-ABI library (building it first if nvcc is present and it is missing)."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    path = _build.LIB_PATH
-    try:
-        path = _build.build()  # no-op unless the library is missing or older than its sources
-    except Exception:
-        if not os.path.exists(path):
-            raise  # no library and no way to build it: fail loudly, there is no fallback
-    lib = C.CDLL(path)
-    for name, (res, args) in SIGNATURES.items():
+def _bind(lib, table):
+    for name, (res, args) in table.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing: fail loudly
         fn.restype = res
         fn.argtypes = args
+
+
+def load():
+    """dlopen the C-ABI library, (re)building it first when it is missing or its sources changed.
+
+    No fallback: a failed rebuild of a stale library raises (an old binary with other kernels or another ABI is never
+    loaded silently), and so does an ABI version mismatch.  Only when no compiler exists at all (a deployment box
+    without nvcc) is an existing library loaded as it is — with a warning if its recorded source hash differs.
+    B200_DEV=1 selects the development variant (ablation switches, probes)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    dev = os.environ.get("B200_DEV") == "1"
+    path = _build.DEV_LIB_PATH if dev else _build.LIB_PATH
+    try:
+        path = _build.build(dev=dev)  # no-op unless the library is missing or its sources changed
+    except FileNotFoundError as e:    # nvcc itself is absent
+        if not os.path.exists(path):
+            raise B200Error(f"{path} is missing and cannot be built here ({e}); there is no fallback") from e
+        if _build.is_stale(dev):
+            import warnings
+            warnings.warn(f"{path}: sources differ from the ones it was built from and no nvcc is available to "
+                          "rebuild it; loading the existing binary", RuntimeWarning)
+    lib = C.CDLL(path)
+    _bind(lib, SIGNATURES)
+    if dev:
+        _bind(lib, DEV_SIGNATURES)
+    got = lib.b200_abi_version()
+    if got != ABI_VERSION:
+        raise B200Error(f"{path}: ABI version {got}, this package needs {ABI_VERSION} (stale library?)")
     _lib = lib
     return lib
 
@@ -105,8 +131,9 @@ def check(rc: int, what: str = "") -> None:
         raise B200Error(f"{what or 'b200 call'} failed (status {rc}): {msg}")
 
 
-def stream_ptr() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def stream_ptr(device=None) -> int:
+    """raw cudaStream_t of torch's current stream on `device` (default: the current device)"""
+    return torch.cuda.current_stream(device).cuda_stream
 
 
 def ptr(t) -> int:

@@ -44,7 +44,20 @@ static int fail(int code, const char* fmt, ...) {
     } while (0)
 
 extern "C" const char* b200_last_error(void) { return g_err; }
-extern "C" int b200_abi_version(void) { return 1; }
+extern "C" int b200_abi_version(void) { return 2; }
+
+// Development switches: compiled only into the development library (-DB200_DEV).  The product library has no
+// environment lookups and no ablation branches on its launch path.
+#ifdef B200_DEV
+static int g_dev_igemm_ablate = 0, g_dev_dmarch_ablate = 0, g_dev_nopair = 0, g_dev_stage_cap = 0;
+extern "C" int b200_dev_set_ablation(int igemm_ablate, int dmarch_ablate, int nopair, int stage_cap) {
+    g_dev_igemm_ablate = igemm_ablate; g_dev_dmarch_ablate = dmarch_ablate;
+    g_dev_nopair = nopair; g_dev_stage_cap = stage_cap;
+    return 0;
+}
+#else
+constexpr int g_dev_igemm_ablate = 0, g_dev_dmarch_ablate = 0, g_dev_nopair = 0, g_dev_stage_cap = 0;
+#endif
 
 // ------------------------------------------------------------------------------------------------ device info
 static int g_sms[64];
@@ -72,6 +85,24 @@ static int get_encode() {
         return fail(B200_ERR_DRIVER, "cuTensorMapEncodeTiled not available from the driver (%s)",
                     cudaGetErrorString(e));
     g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    return 0;
+}
+
+// cudaFuncSetAttribute applies to the CURRENT device's copy of a kernel: the opt-in for > 48 KB of dynamic shared memory
+// is recorded per device (a process that drives several GPUs launches on each of them)
+struct SmemOptIn {
+    int bytes[64];
+};
+template <typename K>
+static int ensure_smem(K kernel, int bytes, SmemOptIn& st) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(B200_ERR_CUDA, "device ordinal %d out of range", dev);
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (st.bytes[dev] < bytes) {
+        CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        st.bytes[dev] = bytes;
+    }
     return 0;
 }
 
@@ -177,8 +208,7 @@ static int b_stage_bytes(const IgemmParams& p) {
 // CTA-pair mode of igemm_kernel (clusters of 2, tcgen05.mma.cta_group::2): wide-N 3x3x3 tiles, where halving the B
 // operand traffic per SM lifts the shared-memory bound; MN-major B needs whole 64-column atoms per CTA
 static bool igemm_pair_ok(int block_n, int ntaps, bool b_mn, long long m_tiles) {
-    static const bool disabled = getenv("B200_IGEMM_NOPAIR") != nullptr;   // dev only: single-CTA kernel everywhere
-    if (disabled) return false;
+    if (g_dev_nopair) return false;   // development library only: single-CTA kernel everywhere
     if (ntaps != 27 || block_n < 128 || block_n % 32 != 0) return false;
     if (m_tiles < 32) return false;   // the 8^3 level: a handful of tiles, the cluster hand-shakes cost more than B saves
     return b_mn ? block_n % 128 == 0 : true;
@@ -189,8 +219,7 @@ static int igemm_stages(int a_bytes, int b_bytes, int c_bytes) {
     const int per_stage = a_bytes + b_bytes;
     int st = (kSmemLimit - kIgemmFixedSmem - c_bytes) / per_stage;
     if (st > 8) st = 8;
-    static const char* cap = getenv("B200_IGEMM_STAGES");   // dev only: ring-depth sensitivity experiments
-    if (cap && atoi(cap) >= 2 && atoi(cap) < st) st = atoi(cap);
+    if (g_dev_stage_cap >= 2 && g_dev_stage_cap < st) st = g_dev_stage_cap;   // development library only
     return st;
 }
 static size_t igemm_smem(int stages, int a_bytes, int b_bytes, int c_bytes) {
@@ -269,21 +298,15 @@ static void set_plain_stage(IgemmParams& p) {
 static int launch_igemm(IgemmParams& p, cudaStream_t s, int* grid_out) {
     const int sms = sm_count();
     if (sms <= 0) return fail(B200_ERR_CUDA, "no CUDA device");
-    static size_t attr_smem = 0;
+    static SmemOptIn optin;
     if (p.stages < 2) return fail(B200_ERR_UNSUPPORTED_SHAPE, "igemm: tile does not fit shared memory");
     const size_t smem = igemm_smem(p.stages, p.a_stage_bytes, b_stage_bytes(p), epi_staging_bytes(p));
-    {
-        std::lock_guard<std::mutex> lk(g_mu);
-        if (smem > attr_smem) {
-            CUDA_TRY(cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            attr_smem = 227 * 1024;
-        }
+    if (!p.pair) {   // the pair kernel is opted in by igemm_max_clusters() (per device)
+        const int rc_attr = ensure_smem(igemm_kernel, 227 * 1024, optin);
+        if (rc_attr) return rc_attr;
     }
     const long long m_tiles = (long long)p.nbw * p.nbh * p.nbd * p.nbatch;
-    {
-        const char* ab = getenv("B200_IGEMM_ABLATE");   // dev only, see IgemmParams::ablate
-        p.ablate = ab ? atoi(ab) : 0;
-    }
+    p.ablate = g_dev_igemm_ablate;
     if (p.pair) {
         const int ncl = igemm_max_clusters();
         if (ncl <= 0) return fail(B200_ERR_CUDA, "igemm: no co-resident CTA pair fits on this device");
@@ -445,17 +468,11 @@ static int launch_dmarch(const b200_act* in, const void* w_packed, const b200_ac
     p.nbw = pl.nbw; p.nbh = pl.nbh; p.seg_len = pl.seg_len; p.nseg = pl.nseg;
     p.mode = mode;
     p.vec0 = v0; p.vec1 = v1; p.stats = stats;
-    {
-        const char* ab = getenv("B200_DMARCH_ABLATE");   // dev only, see DmarchParams::ablate
-        p.ablate = ab ? atoi(ab) : 0;
-    }
-    static bool attr = false;
-    {
-        std::lock_guard<std::mutex> lk(g_mu);
-        if (!attr) {
-            CUDA_TRY(cudaFuncSetAttribute(dmarch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDmSmem));
-            attr = true;
-        }
+    p.ablate = g_dev_dmarch_ablate;
+    if (!pl.pair) {   // the pair kernel is opted in by dmarch_max_clusters() (per device)
+        static SmemOptIn optin;
+        const int rc_attr = ensure_smem(dmarch_kernel, kDmSmem, optin);
+        if (rc_attr) return rc_attr;
     }
     if (pl.pair) dmarch_pair_kernel<<<pl.grid, kThreads, kDmSmem, s>>>(p);   // __cluster_dims__(2, 1, 1)
     else dmarch_kernel<<<pl.grid, kThreads, kDmSmem, s>>>(p);
@@ -660,15 +677,12 @@ extern "C" int b200_convt2x_dgrad(const b200_act* dy, int pad_d, int pad_h, int 
 static int launch_wgrad(WgradParams& p, cudaStream_t s) {
     const int sms = sm_count();
     if (sms <= 0) return fail(B200_ERR_CUDA, "no CUDA device");
-    static bool attr = false;
+    static SmemOptIn optin;
     // alignment slack + 2 P slots + 2 Q slots + barriers/TMEM pointer + 4 transpose tiles of 32 x 33 floats
     const size_t smem = 1024 + 2 * 2 * kBoxBytes + 2 * 4 * kBoxBytes + 128 + 4 * 32 * 33 * 4;
     {
-        std::lock_guard<std::mutex> lk(g_mu);
-        if (!attr) {
-            CUDA_TRY(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr = true;
-        }
+        const int rc_attr = ensure_smem(wgrad_kernel, (int)smem, optin);
+        if (rc_attr) return rc_attr;
     }
     p.n_colblocks = p.ntaps * p.q_chunks;
     p.cb_per_group = p.n_colblocks < 8 ? p.n_colblocks : 8;
@@ -758,16 +772,12 @@ extern "C" int b200_conv3d_wgrad(const b200_act* x, const b200_act* dy, float* d
             hp.sp = swapped ? 27 : (long long)cin_real * 27;
             hp.sq = swapped ? (long long)cin_real * 27 : 27;
         }
-        static bool attr_h = false;
+        static SmemOptIn optin_h;
         const size_t smem_h = 1024 + kWhPBoxes * kBoxBytes + kWhQStages * kWhQBytes +
                               8 * (2 * (kWhPBoxes - 1) + 2 * kWhQStages + 1) + 64 + 4 * 32 * 33 * 4;
         {
-            std::lock_guard<std::mutex> lk(g_mu);
-            if (!attr_h) {
-                CUDA_TRY(cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)smem_h));
-                attr_h = true;
-            }
+            const int rc_attr = ensure_smem(wgrad_halo_kernel, (int)smem_h, optin_h);
+            if (rc_attr) return rc_attr;
         }
         wgrad_halo_kernel<<<(int)grid_h, kThreads, smem_h, (cudaStream_t)stream>>>(hp);
         CUDA_TRY(cudaGetLastError());
@@ -1131,6 +1141,7 @@ extern "C" int b200_conv3d_wgrad_kernel_id(int64_t h, int64_t w) {
     return (w >= 8 && h >= 16) ? 1 : 0;                           // 0: wgrad_kernel, 1: wgrad_halo_kernel
 }
 
+#ifdef B200_DEV
 // dev probe of the CTA-pair (cta_group::2) primitives: d_out[pairs][256][n] = A[256][k] B[n][k]^T (bf16 in, fp32 out),
 // the MMA chain repeated `iters` times (iters > 1 accumulates iters copies); cycles[pairs] = leader-side duration
 namespace b200 {
@@ -1152,3 +1163,4 @@ extern "C" int b200_probe_pair(const void* a, const void* b, int n, int k, int i
     CUDA_TRY(launch_pair_probe(am, bm, n, k / 64, iters, d_out, cycles, pairs, (cudaStream_t)stream));
     return 0;
 }
+#endif  // B200_DEV

@@ -274,12 +274,10 @@ __global__ void __launch_bounds__(256) pack_conv_weight_kernel(const float* __re
 cudaError_t launch_pack_conv_weight(const float* w, int cout, int cin, int cin_pad, __nv_bfloat16* wf,
                                     cudaStream_t s) {
     const int smem = 27 * 32 * kPackPitch * 2;
-    static bool attr_set = false;
-    if (!attr_set) {
+    {   // the > 48 KB opt-in is per device; setting it again is cheap and this launch is off the hot path
         cudaError_t e =
             cudaFuncSetAttribute(pack_conv_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     dim3 grid((cin_pad + 31) / 32, (cout + 31) / 32);
     pack_conv_weight_kernel<<<grid, 256, smem, s>>>(w, cout, cin, cin_pad, wf);

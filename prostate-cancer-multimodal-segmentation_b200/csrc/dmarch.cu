@@ -106,9 +106,9 @@ DEV void dmarch_body(const DmarchParams& p) {
                         mbar_wait(aempty(ra.stage), ra.phase ^ 1);
                         if (elect_one()) {
                             const uint32_t fb = afull(ra.stage);
-                            if (p.ablate == 1) { mbar_arrive(fb); }
+                            if (B200_ABLATE(p) == 1) { mbar_arrive(fb); }
                             else mbar_arrive_expect_tx(fb, nin * kDmABytes);
-                            for (int si = 0; si < nin && p.ablate != 1; ++si)
+                            for (int si = 0; si < nin && B200_ABLATE(p) != 1; ++si)
                                 tma_load_5d(smem_a + ra.stage * kDmAStageBytes + si * kDmABytes, &p.a_map, fb, kc * 64,
                                             w0 + sign * (kw - 1), h0 - 1, dz + si, nb);
                         }
@@ -118,9 +118,9 @@ DEV void dmarch_body(const DmarchParams& p) {
                             mbar_wait(bempty(rb.stage), rb.phase ^ 1);
                             if (elect_one()) {
                                 const uint32_t fb = bfull(rb.stage);
-                                if (p.ablate == 1) { mbar_arrive(fb); }
+                                if (B200_ABLATE(p) == 1) { mbar_arrive(fb); }
                                 else mbar_arrive_expect_tx(fb, kDmBBytes);
-                                if (p.ablate != 1 && (!kPair || (int)(bcount & 1u) == rank)) {
+                                if (B200_ABLATE(p) != 1 && (!kPair || (int)(bcount & 1u) == rank)) {
 #pragma unroll
                                     for (int j = 0; j < 3; ++j) {
                                         // slab j feeds output slice dz - 1 + j
@@ -217,7 +217,7 @@ DEV void dmarch_body(const DmarchParams& p) {
                                 const uint32_t b_lo = b_lo0 + rb.stage * (kDmBBytes >> 4);
 #pragma unroll
                                 for (int si = 0; si < kDmG; ++si) {
-                                    if (si < nin && jlo[si] <= jhi[si] && p.ablate != 2) {
+                                    if (si < nin && jlo[si] <= jhi[si] && B200_ABLATE(p) != 2) {
                                         // tap kh reads the halo box at row offset kh (fprop) or 2 - kh (dgrad): 8 rows = 1 KB
                                         const uint32_t a_lo = a_st + si * (kDmABytes >> 4) +
                                                               (uint32_t)((sign > 0 ? kh : 2 - kh) * (1024 >> 4));

@@ -124,13 +124,13 @@ DEV void igemm_body(const IgemmParams& p) {
                     mbar_wait(empty_bar(ps.stage), ps.phase ^ 1);
                     if (elect_one()) {
                         uint32_t fb = full_bar(ps.stage);
-                        if (p.ablate == 3) {   // loads issued, the MMAs do not wait for them: contention without latency
+                        if (B200_ABLATE(p) == 3) {   // loads issued, the MMAs do not wait for them: contention without latency
                             if (rank == 0) mbar_arrive(fb);
                             fb = sink_bar(ps.stage);
                             if (rank == 0 && sink_uses >= nst)   // this slot's previous loads have landed
                                 while (!mbar_try_wait(fb, ((sink_uses / nst) - 1) & 1)) {}
                         }
-                        if (p.ablate == 1) {
+                        if (B200_ABLATE(p) == 1) {
                             if (rank == 0) mbar_arrive(fb);
                         } else if (!kPair) {
                             mbar_arrive_expect_tx(fb, a_bytes + b_bytes);
@@ -162,7 +162,7 @@ DEV void igemm_body(const IgemmParams& p) {
                 }
             }
         }
-        if (p.ablate == 3 && rank == 0 && elect_one()) {   // no load may be in flight when the CTAs exit
+        if (B200_ABLATE(p) == 3 && rank == 0 && elect_one()) {   // no load may be in flight when the CTAs exit
             for (uint32_t s = 0; s < nst; ++s) {
                 const uint32_t uses = sink_uses / nst + (s < sink_uses % nst ? 1u : 0u);
                 if (uses > 0) while (!mbar_try_wait(sink_bar(s), (uses - 1) & 1)) {}
@@ -198,7 +198,7 @@ DEV void igemm_body(const IgemmParams& p) {
                     if (elect_one()) {
                         const uint64_t a_st = a_desc0 + ps.stage * a_step;
                         const uint64_t b_st = b_desc0 + ps.stage * b_step;
-                        for (int g = 0; g < group && p.ablate != 2; ++g) {
+                        for (int g = 0; g < group && B200_ABLATE(p) != 2; ++g) {
                             const uint64_t a_desc = a_st + (g == 0 ? goff0 : (g == 1 ? goff1 : goff2));
                             const uint64_t b_desc = b_st + g * bt_step;
                             // 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (>>4) address field

@@ -13,6 +13,15 @@ constexpr int kBoxBytes = 128 * 128;     // one TMA box: 128 rows x 64 bf16
 constexpr int kMaxStatCols = 1024;       // widest Cout whose BatchNorm partial sums fit the CTA's smem
 constexpr int kThreads = 256;            // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 4..7 epilogue
 
+// Ablation switches (loads without MMAs, MMAs without loads, ...) exist only in the development library
+// (-DB200_DEV, build.py dev=True): in the product library B200_ABLATE(p) is the constant 0 and every branch on it
+// is removed by the compiler.
+#ifdef B200_DEV
+#define B200_ABLATE(p) ((p).ablate)
+#else
+#define B200_ABLATE(p) 0
+#endif
+
 enum EpilogueMode : int {
     EPI_PLAIN = 0,       // out = acc                         (dgrad)
     EPI_BIAS_STATS = 1,  // out = bf16(acc + bias); per-tile sum / sum-of-squares of out (train fprop)
@@ -34,7 +43,7 @@ struct alignas(64) IgemmParams {
     CUtensorMap c_map[kMaxMaps];  // epilogue v2: TMA store maps of the output (one per output offset group)
     int epi_v2;         // 1: stage the bf16 tile in shared memory, TMA store, statistics from the staged tile
     int pair;           // 1: launched as clusters of two CTAs; M = 256 tcgen05.mma.cta_group::2, B tile split between them
-    int ablate;         // dev only (env B200_IGEMM_ABLATE): 1 = barriers armed without TMA loads, 2 = no MMAs issued
+    int ablate;         // development library only (B200_ABLATE): 1 = barriers armed without TMA loads, 2 = no MMAs issued
     int ntaps;
     int a_map_of_tap[kMaxTaps];
     int tap_dw[kMaxTaps], tap_dh[kMaxTaps], tap_dd[kMaxTaps];
@@ -91,7 +100,7 @@ struct alignas(64) DmarchParams {
     const float* vec0;
     const float* vec1;
     float* stats;        // [gridDim.x][64][2]
-    int ablate;          // dev only (env B200_DMARCH_ABLATE): 1 = no TMA loads after arming the barriers (MMAs on stale
+    int ablate;          // development library only (B200_ABLATE): 1 = no TMA loads after arming the barriers (MMAs on stale
                          // shared memory), 2 = no MMAs (loads + epilogue only); results are garbage, timings are not
 };
 

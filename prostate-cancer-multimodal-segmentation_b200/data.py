@@ -81,6 +81,7 @@ class DevicePrefetcher:
         if self.device.type != "cuda":
             raise ValueError("DevicePrefetcher stages batches into CUDA memory; got device " + str(device))
         self.copy_stream = torch.cuda.Stream(self.device)
+        self._consumer = torch.cuda.current_stream(self.device)
         self._slots = [{}, {}]
         self._pinned = [{}, {}]
         self._free = [None, None]   # event on the compute stream after which slot i may be overwritten
@@ -88,6 +89,10 @@ class DevicePrefetcher:
 
     def __len__(self):
         return len(self.loader)
+
+    def _main_stream(self):
+        # the consumer's stream: torch's current stream outside the `with torch.cuda.stream(copy_stream)` block
+        return self._consumer
 
     def over(self, loader):
         """iterate another loader through the same staging buffers and copy stream (e.g. one object per trainer,
@@ -103,6 +108,9 @@ class DevicePrefetcher:
         with torch.cuda.stream(self.copy_stream):
             for k in self.keys:
                 src = batch[k]
+                if src.is_cuda and src.device == self.device:
+                    out[k] = src   # already resident: nothing to stage
+                    continue
                 if not src.is_pinned():
                     buf = pinned.get(k)
                     if buf is None or buf.shape != src.shape or buf.dtype != src.dtype:
@@ -114,6 +122,9 @@ class DevicePrefetcher:
                 dst = slot.get(k)
                 if dst is None or dst.shape != src.shape or dst.dtype != src.dtype:
                     dst = slot[k] = torch.empty(src.shape, dtype=src.dtype, device=self.device)
+                    # the slot is allocated under the copy stream but read by the compute stream: tell the caching
+                    # allocator, so the block is not handed out again while a step still reads it
+                    dst.record_stream(self._main_stream())
                 dst.copy_(src, non_blocking=True)
                 out[k] = dst
             ready = self._ready[i] = self.copy_stream.record_event()
@@ -128,7 +139,7 @@ class DevicePrefetcher:
             return
         while nxt is not None:
             cur, ready = nxt
-            main = torch.cuda.current_stream(self.device)
+            main = self._consumer = torch.cuda.current_stream(self.device)
             main.wait_event(ready)
             # the other slot was handed out one iteration ago: everything queued on the compute stream so far is what
             # read it, so it may be overwritten once the compute stream gets here

@@ -224,9 +224,9 @@ class _Side:
     before the optimizer), so they overlap with the HBM-bound BatchNorm-backward / pool-backward kernels of the next
     layer, which fit beside a persistent GEMM CTA on every SM.  Buffers they read are kept alive until join()."""
 
-    def __init__(self, enabled=True):
+    def __init__(self, enabled=True, device=None):
         self.enabled = enabled
-        self.stream = torch.cuda.Stream() if enabled else None
+        self.stream = torch.cuda.Stream(device) if enabled else None
         self.keep = []
 
     def run(self, fn, keep=()):
@@ -366,6 +366,10 @@ class Engine:
         if device.type != "cuda":
             raise B200Error("UNet3D (B200) runs on CUDA tensors only: there is no CPU path. "
                             "Move the model and its input to a cuda device.")
+        with torch.cuda.device(device):
+            self._prepare(device)
+
+    def _prepare(self, device):
         if self.device != device:
             self._build(device)
         if not self._is_flat():
@@ -385,6 +389,13 @@ class Engine:
 
     # ------------------------------------------------------------------ forward
     def forward(self, x: torch.Tensor, training: bool, want_probs: bool = False):
+        """logits (+ probabilities) and the tape of one forward; runs on x's device whatever the current device is"""
+        if x.is_cuda:
+            with torch.cuda.device(x.device):
+                return self._forward(x, training, want_probs)
+        return self._forward(x, training, want_probs)
+
+    def _forward(self, x: torch.Tensor, training: bool, want_probs: bool = False):
         m = self.model
         if x.dim() != 5:
             raise ValueError(f"expected a 5-D input (N, C, D, H, W), got shape {tuple(x.shape)}")
@@ -509,6 +520,10 @@ class Engine:
         return (lambda p: ours[id(p)]), foreign
 
     def backward(self, tape: _Tape, dlogits: torch.Tensor):
+        with torch.cuda.device(dlogits.device):
+            return self._backward(tape, dlogits)
+
+    def _backward(self, tape: _Tape, dlogits: torch.Tensor):
         m = self.model
         dev = dlogits.device
         n = tape.x_shape[0]
@@ -517,7 +532,7 @@ class Engine:
         ch = [f, 2 * f, 4 * f, 8 * f, 16 * f]
         g, foreign = self._begin_grads()
         sync = self.grad_sync
-        side = _Side(self.overlap_wgrad)
+        side = _Side(self.overlap_wgrad, dev)
         if dlogits.dtype != torch.float32 or not dlogits.is_contiguous():
             dlogits = dlogits.float().contiguous()
 

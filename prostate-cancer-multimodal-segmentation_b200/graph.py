@@ -76,4 +76,4 @@ class GraphedTrainStep:
         eng._pack_key = None             # an eager forward after replays must repack its weight operands
         ops.launch_count += launches
         self.replays += 1
-        return static_loss
+        return static_loss.clone()   # a fresh tensor per step, as the eager path returns (4-byte copy on this stream)

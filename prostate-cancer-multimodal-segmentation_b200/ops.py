@@ -70,7 +70,8 @@ class ActView:
     def to_ncdhw(self) -> torch.Tensor:
         n, d, h, w, c = self.shape
         out = torch.empty((n, c, d, h, w), device=self.t.device, dtype=torch.float32)
-        check(_lib.load().b200_unpack_act(self.ref, ptr(out), stream_ptr()), "unpack_act")
+        with torch.cuda.device(self.t.device):
+            check(_lib.load().b200_unpack_act(self.ref, ptr(out), stream_ptr()), "unpack_act")
         return out
 
 
@@ -345,21 +346,42 @@ def seg_counts(score: torch.Tensor, label: torch.Tensor, threshold: float = 0.5)
     return counts
 
 
-# ---- optional timeline (dev tool): CUDA events around every op on whatever stream it runs, to inspect cross-stream
-# overlap without an external profiler.  `timeline = []` switches it on; entries are (name, stream, start, end).
+# ---- every op runs on the device that owns its tensors -------------------------------------------------------------
+# The C ABI launches on the CURRENT device with the stream it is handed; a tensor on cuda:1 while cuda:0 is current
+# would otherwise get device 0's stream and device 0's kernel attributes.  The wrapper switches the current device to
+# the first CUDA argument's device for the duration of the call (a no-op in the usual one-process-per-GPU setting).
+# Optional timeline (dev tool): `timeline = []` records CUDA events around every op on whatever stream it runs, to
+# inspect cross-stream overlap without an external profiler; entries are (name, stream, start, end).
 timeline = None
 
 
-def _traced(fn):
+def _device_of(args):
+    for a in args:
+        if isinstance(a, ActView):
+            return a.t.device
+        if isinstance(a, torch.Tensor) and a.is_cuda:
+            return a.device
+    return None
+
+
+def _run(fn, a, k):
+    if timeline is None:
+        return fn(*a, **k)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r = fn(*a, **k)
+    e1.record()
+    timeline.append((fn.__name__, torch.cuda.current_stream().cuda_stream, e0, e1))
+    return r
+
+
+def _op(fn):
     def wrapper(*a, **k):
-        if timeline is None:
-            return fn(*a, **k)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        r = fn(*a, **k)
-        e1.record()
-        timeline.append((fn.__name__, torch.cuda.current_stream().cuda_stream, e0, e1))
-        return r
+        dev = _device_of(a)
+        if dev is not None and dev.index is not None and dev.index != torch.cuda.current_device():
+            with torch.cuda.device(dev):
+                return _run(fn, a, k)
+        return _run(fn, a, k)
     wrapper.__name__ = fn.__name__
     wrapper.__doc__ = fn.__doc__
     return wrapper
@@ -369,5 +391,5 @@ for _n in ("pack_input", "im2col_input", "pack_rows", "pack_conv_weight", "pack_
            "conv1_fprop", "conv3d_dgrad", "conv3d_wgrad", "conv1_wgrad", "convt2x_fwd", "convt2x_dgrad",
            "convt2x_wgrad", "bn_finalize", "bn_fold_eval", "bn_apply_relu", "bn_bwd", "maxpool3d_fwd",
            "maxpool3d_bwd", "head_fwd", "head_bwd", "loss_fwd", "loss_bwd", "adam_step", "cast_bf16", "sumsq",
-           "fill_zero", "channel_sum"):
-    globals()[_n] = _traced(globals()[_n])
+           "fill_zero", "channel_sum", "resample3d", "minmax_normalize_", "seg_counts"):
+    globals()[_n] = _op(globals()[_n])

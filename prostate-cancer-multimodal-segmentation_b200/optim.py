@@ -19,6 +19,12 @@ class FusedAdam(torch.optim.Optimizer):
         super().__init__(params, defaults)
         if len(self.param_groups) != 1:
             raise ValueError("FusedAdam supports a single param group (the whole model)")
+        given = self.param_groups[0]["params"]
+        if {id(p) for p in given} != {id(p) for p in model.parameters()} or not all(p.requires_grad for p in given):
+            # one launch updates the whole flat buffer (weight decay included): a subset or frozen layers would be
+            # modified behind the caller's back
+            raise ValueError("FusedAdam updates every parameter of the UNet3D in one launch: pass exactly "
+                             "model.parameters(), all with requires_grad=True (use torch.optim.Adam for subsets)")
         self.model = model
         self._step = 0
         self.exp_avg = None

@@ -10,6 +10,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from ._lib import B200Error
 from .engine import Engine
 
 
@@ -64,6 +65,7 @@ class _UNetFunction(torch.autograd.Function):
         logits, _, tape = model._engine.forward(x, training=model.training)
         ctx.model = model
         ctx.tape = tape
+        ctx.saved_nothing = any(st is None for st in tape.dcs.values())   # eval-mode forward: BatchNorm folded
         return logits
 
     @staticmethod
@@ -71,6 +73,10 @@ class _UNetFunction(torch.autograd.Function):
         tape, ctx.tape = ctx.tape, None
         if tape is None:
             raise RuntimeError("UNet3D (B200): backward called twice on the same forward; activations were freed")
+        if ctx.saved_nothing:
+            raise B200Error("UNet3D (B200): backward through an eval-mode forward is not supported (BatchNorm is folded "
+                            "into the convolution epilogue and nothing is saved); call model.train() first, or run "
+                            "the forward under torch.no_grad()")
         ctx.model._engine.backward(tape, dlogits)
         # parameter gradients were accumulated straight into Parameter.grad (views of the flat gradient buffer);
         # the input gets no gradient (the reference never asks for one: images do not require grad)
@@ -123,6 +129,11 @@ class UNet3D(nn.Module):
         """logits (N, n_classes, D, H, W) fp32 for x (N, n_modalities, D, H, W)"""
         eng = self._engine
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            if not all(p.requires_grad for p in self.parameters()):
+                # the engine's backward produces every parameter gradient in one schedule; a silently updated
+                # "frozen" layer would be worse than refusing
+                raise B200Error("UNet3D (B200): freezing a subset of the parameters (requires_grad=False) is not "
+                                "supported; train all parameters or run under torch.no_grad()")
             eng.prepare(x.device)  # parameters must be in their final (flat) storage before autograd sees them
             return _UNetFunction.apply(self, x, *[p for _, p in eng.ordered_params()])
         logits, _, _ = eng.forward(x, training=self.training)

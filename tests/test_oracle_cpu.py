@@ -167,7 +167,10 @@ def test_c_abi_exports_every_declared_symbol(pkg):
     from importlib import import_module
     sigs = import_module(pkg.__name__ + "._lib").SIGNATURES
     assert declared == set(sigs), declared ^ set(sigs)
-    assert lib.b200_abi_version() == 1
+    assert lib.b200_abi_version() == import_module(pkg.__name__ + "._lib").ABI_VERSION
+    # development-only entry points (micro-probes, ablation switches) are not in the product header or library
+    assert not any("probe" in n or "_dev_" in n for n in declared)
+    assert not hasattr(lib, "b200_probe_mma") and not hasattr(lib, "b200_dev_set_ablation")
 
 
 def test_flops_accounting(pkg):

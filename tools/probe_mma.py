@@ -1,5 +1,6 @@
 """Dev tool: tcgen05.mma cycles vs N (SS mode, operands in shared memory).  python tools/probe_mma.py"""
 import importlib, os, sys
+os.environ["B200_DEV"] = "1"   # the probes live in the development library only (build.build(dev=True))
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

@@ -1,5 +1,6 @@
 """Dev tool: functional check and cycle count of the CTA-pair (cta_group::2) MMA primitives.  python tools/probe_pair.py"""
 import importlib, os, sys
+os.environ["B200_DEV"] = "1"   # the probes live in the development library only (build.build(dev=True))
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
