@@ -183,6 +183,23 @@ int b200_minmax_normalize(float* x, int64_t nvol, int64_t voxels_per_volume, voi
 int b200_seg_counts(const float* score, const float* label, int64_t nsamples, int64_t voxels_per_sample,
                     float threshold, int64_t* counts, void* stream);
 
+/* per-channel sum over the box [d0,d0+bd) x [h0,h0+bh) x [w0,w0+bw) of every sample, added to out[c] (fp32): the
+ * ConvTranspose3d bias gradient when F.pad (models/unet3d.py:149-151) put a zero border around the upsampled map */
+int b200_channel_sum_box(const b200_act* v, int d0, int h0, int w0, int bd, int bh, int bw, float* out, void* stream);
+
+/* ---- sliding-window inference (BASELINE configs[3]; script/predict.py:152-172 predicts whole volumes) ------------ */
+/* origins: device int32 [nwin][4] = (volume, d0, h0, w0).  gather: x (n,c,d,h,w) fp32 -> out (nwin,c,wd,wh,ww) fp32.
+ * accumulate: acc (n,k,d,h,w) += window logits (nwin,k,wd,wh,ww), windows added in list order per voxel (no atomics),
+ * for volumes [v_lo, v_lo+v_cnt).  finalize: acc[(nk),d,h,w] /= cover[d]*cover[D+h]*cover[D+H+w] (device int32, the
+ * per-axis number of covering windows), then probs = sigmoid, mask = probs > threshold (either may be null). */
+int b200_window_gather(const float* x, int64_t n, int64_t c, int64_t d, int64_t h, int64_t w, const int32_t* origins,
+                       int nwin, int64_t wd, int64_t wh, int64_t ww, float* out, void* stream);
+int b200_window_accumulate(const float* logits, const int32_t* origins, int nwin, int64_t k, int64_t wd, int64_t wh,
+                           int64_t ww, float* acc, int64_t n, int64_t d, int64_t h, int64_t w, int v_lo, int v_cnt,
+                           void* stream);
+int b200_window_finalize(float* acc, const int32_t* cover, int64_t nk, int64_t d, int64_t h, int64_t w, float threshold,
+                         float* probs, float* mask, void* stream);
+
 /* routing queries (instrumentation): 3x3x3 conv fprop / dgrad -> 0 igemm_kernel, 1 dmarch_kernel (64 output columns on
  * 8 x 16 bricks), 2 igemm_pair_kernel (tiles of >= 128 columns: CTA pairs, cta_group::2); weight gradient -> 0 wgrad_kernel, 1 wgrad_halo_kernel (w >= 8 and h >= 16) */
 int b200_conv3d_kernel_id(int64_t n, int64_t d, int64_t h, int64_t w, int64_t out_cols);

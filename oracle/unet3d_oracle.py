@@ -177,7 +177,7 @@ def apply_adam(sd, opt_state, grads, lr=1e-4, weight_decay=1e-5):
             adam_update(sd[k], g, m, v, opt_state["step"], lr, weight_decay=weight_decay)
 
 
-def dp_train_step(sd, opt_state, x_shards, y_shards, lr=1e-4, weight_decay=1e-5, loss="bce_dice"):
+def dp_train_step(sd, opt_state, x_shards, y_shards, lr=1e-4, weight_decay=1e-5, loss="bce_dice", store=None):
     """Data-parallel semantics: every rank runs forward/backward on its shard from the same weights
     with rank-local BatchNorm statistics and rank-local loss; parameter gradients are averaged; one Adam step.
     Running statistics follow rank 0 (DDP broadcast_buffers behaviour).  Returns (mean loss, averaged grads)."""
@@ -188,7 +188,7 @@ def dp_train_step(sd, opt_state, x_shards, y_shards, lr=1e-4, weight_decay=1e-5,
         work = {k: (v.clone() if not k in names else v) for k, v in sd.items()}
         leaves = {k: sd[k].detach().clone().requires_grad_(True) for k in names}
         work.update(leaves)
-        logits = unet3d_forward(xs, work, training=True)
+        logits = unet3d_forward(xs, work, training=True, store=store)
         lval = bce_dice_loss(logits, ys) if loss == "bce_dice" else dice_loss(logits, ys)
         gr = torch.autograd.grad(lval, [leaves[k] for k in names])
         total = list(gr) if total is None else [a + b for a, b in zip(total, gr)]

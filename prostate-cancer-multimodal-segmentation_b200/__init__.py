@@ -12,8 +12,8 @@ from .optim import FusedAdam  # noqa: F401
 from .graph import GraphedTrainStep  # noqa: F401
 from . import data, parallel, predict, trainer, validate  # noqa: F401
 from .trainer import BaseTrainer, BPHTrainer, CrossValidationTrainer, Trainer  # noqa: F401
-from .predict import ModelPredictor, preprocess_image  # noqa: F401
+from .predict import ModelPredictor, load_multimodal_images, preprocess_image  # noqa: F401
 
 __all__ = ["B200Error", "load_library", "lib_path", "ops", "UNet3D", "DoubleConv3D", "Down3D", "Up3D", "DiceLoss",
            "BCEDiceLoss", "FusedAdam", "GraphedTrainStep", "BaseTrainer", "BPHTrainer", "CrossValidationTrainer", "Trainer",
-           "ModelPredictor", "preprocess_image", "data", "parallel", "predict", "trainer", "validate"]
+           "ModelPredictor", "load_multimodal_images", "preprocess_image", "data", "parallel", "predict", "trainer", "validate"]

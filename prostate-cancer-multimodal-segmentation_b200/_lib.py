@@ -61,6 +61,11 @@ SIGNATURES = {
     "b200_sumsq": (_i32, [_vp, _i64, _vp, _vp]),
     "b200_fill_zero": (_i32, [_AP, _vp]),
     "b200_channel_sum": (_i32, [_AP, _vp, _vp]),
+    "b200_channel_sum_box": (_i32, [_AP, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "b200_window_gather": (_i32, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _i32, _i64, _i64, _i64, _vp, _vp]),
+    "b200_window_accumulate": (_i32, [_vp, _vp, _i32, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _i64, _i32,
+                                      _i32, _vp]),
+    "b200_window_finalize": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _f32, _vp, _vp, _vp]),
     "b200_unpack_act": (_i32, [_AP, _vp, _vp]),
     "b200_resample3d": (_i32, [_vp, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _i32, _i32, _vp]),
     "b200_minmax_normalize": (_i32, [_vp, _i64, _i64, _vp, _vp]),

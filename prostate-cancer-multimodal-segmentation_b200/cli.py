@@ -31,6 +31,11 @@ def build_parser():
     t.add_argument("--optimized", action="store_true")
     t.add_argument("--cross_validation", action="store_true")
     t.add_argument("--save_dir", default="checkpoints")
+    t.add_argument("--seed", type=int, default=None, help="seed of the weight initialisation")
+    t.add_argument("--loss", choices=["dice", "bce_dice"], default="dice")
+    t.add_argument("--fold_parallel", action="store_true",
+                   help="multi-GPU cross-validation: deal the folds to the ranks instead of training every fold "
+                        "data-parallel over all ranks")
     v = sub.add_parser("validate")
     _add_common(v)
     v.add_argument("--model_path", required=True)
@@ -38,7 +43,9 @@ def build_parser():
     p = sub.add_parser("predict")
     _add_common(p)
     p.add_argument("--model_path", required=True)
-    p.add_argument("--input_dir", default=None, help=".npy file of shape (5,D,H,W); synthetic volume if omitted")
+    p.add_argument("--input_dir", default=None,
+                   help="case directory with one <modality>.npy per modality (ADC, DWI, T2 fs, T2 not fs, gaoqing-T2), "
+                        "or one .npy file of shape (5,D,H,W); a synthetic volume if omitted")
     p.add_argument("--output_dir", default="predictions")
     p.add_argument("--window", type=int, nargs=3, default=None, help="sliding-window extent (D H W)")
     p.add_argument("--stride", type=int, nargs=3, default=None)
@@ -67,15 +74,37 @@ def _config(args):
             "learning_rate": args.learning_rate, "device": args.device, "save_dir": args.save_dir,
             "data_type": args.data_type, "handle_missing_modalities": args.missing_strategy, "validation": True,
             "init_features": args.init_features, "target_size": tuple(args.size), "n_cases": args.n_cases,
-            "n_splits": 5}
+            "n_splits": 5, "seed": getattr(args, "seed", None), "loss": getattr(args, "loss", "dice")}
+
+
+def _distributed():
+    """(rank, world, device-or-None): under `python -m torch.distributed.run` (WORLD_SIZE > 1) this process is one
+    data-parallel rank bound to GPU LOCAL_RANK; otherwise a plain single-process run"""
+    if int(os.environ.get("WORLD_SIZE", "1")) <= 1:
+        return 0, 1, None
+    from . import parallel
+    return parallel.init_distributed()
 
 
 def cmd_train(args):
+    from . import parallel
     from .trainer import BaseTrainer, BPHTrainer, CrossValidationTrainer
+    rank, world, dev = _distributed()
     cfg = _config(args)
-    if args.cross_validation:
-        return CrossValidationTrainer(cfg).train()
-    return (BPHTrainer if args.optimized else BaseTrainer)(cfg).train()
+    if dev is not None:
+        cfg["device"] = str(dev)
+        cfg["fold_parallel"] = bool(getattr(args, "fold_parallel", False))
+    trainer = None
+    try:
+        if args.cross_validation:
+            return CrossValidationTrainer(cfg).train()
+        trainer = (BPHTrainer if args.optimized else BaseTrainer)(cfg)
+        return trainer.train()
+    finally:
+        if trainer is not None:
+            trainer.close()
+        if world > 1:
+            parallel.shutdown_distributed()
 
 
 def cmd_validate(args):
@@ -95,21 +124,31 @@ def cmd_validate(args):
 
 
 def cmd_predict(args):
-    from . import data
-    from .predict import ModelPredictor, normalize_modalities, preprocess_image
-    pred = ModelPredictor(args.model_path, args.device, args.init_features)
-    if args.input_dir:
-        image = np.load(args.input_dir)
-    else:
-        image = data.SyntheticProstateDataset(1, tuple(args.size))[0]["image"].numpy()
-    x = preprocess_image(normalize_modalities(image))
-    out = pred.predict(x, window=tuple(args.window) if args.window else None,
-                       stride=tuple(args.stride) if args.stride else None)
-    os.makedirs(args.output_dir, exist_ok=True)
-    path = os.path.join(args.output_dir, "prediction.npy")
-    mask = pred.save_prediction(out, path)
-    print(f"prediction {out.shape} saved to {path}; foreground voxels {int(mask.sum())}")
-    return out
+    from . import data, parallel
+    from .predict import ModelPredictor, load_multimodal_images, normalize_modalities, preprocess_image
+    rank, world, dev = _distributed()
+    try:
+        pred = ModelPredictor(args.model_path, str(dev) if dev is not None else args.device, args.init_features)
+        if args.input_dir and os.path.isdir(args.input_dir):
+            # a case directory with one .npy volume per modality (script/predict.py:8-82 reads .nii.gz there)
+            image, _ = load_multimodal_images(args.input_dir, handle_missing=args.missing_strategy)
+        elif args.input_dir:
+            image = normalize_modalities(np.load(args.input_dir))
+        else:
+            image = normalize_modalities(data.SyntheticProstateDataset(1, tuple(args.size))[0]["image"].numpy())
+        x = preprocess_image(image)
+        # sliding windows are sharded over the ranks; whole-volume prediction is computed by every rank
+        out = pred.predict(x, window=tuple(args.window) if args.window else None,
+                           stride=tuple(args.stride) if args.stride else None, rank=rank, world=world)
+        if rank == 0:
+            os.makedirs(args.output_dir, exist_ok=True)
+            path = os.path.join(args.output_dir, "prediction.npy")
+            mask = pred.save_prediction(out, path)
+            print(f"prediction {out.shape} saved to {path}; foreground voxels {int(mask.sum())}")
+        return out
+    finally:
+        if world > 1:
+            parallel.shutdown_distributed()
 
 
 def main(argv=None):

@@ -1083,7 +1083,17 @@ extern "C" int b200_fill_zero(const b200_act* v, void* stream) {
 extern "C" int b200_channel_sum(const b200_act* v, float* out, void* stream) {
     CHECK_VIEW(v);
     REQUIRE(out, "channel_sum: null output");
-    CUDA_TRY(launch_channel_sum(to_view(v), out, (cudaStream_t)stream));
+    CUDA_TRY(launch_channel_sum(to_view(v), out, nullptr, (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int b200_channel_sum_box(const b200_act* v, int d0, int h0, int w0, int bd, int bh, int bw, float* out,
+                                    void* stream) {
+    CHECK_VIEW(v);
+    REQUIRE(out, "channel_sum_box: null output");
+    REQUIRE(d0 >= 0 && h0 >= 0 && w0 >= 0 && bd > 0 && bh > 0 && bw > 0 && d0 + bd <= v->d && h0 + bh <= v->h &&
+                w0 + bw <= v->w, "channel_sum_box: box (%d,%d,%d)+(%d,%d,%d) outside the volume", d0, h0, w0, bd, bh, bw);
+    const int box[6] = {d0, h0, w0, bd, bh, bw};
+    CUDA_TRY(launch_channel_sum(to_view(v), out, box, (cudaStream_t)stream));
     return 0;
 }
 extern "C" int b200_unpack_act(const b200_act* v, float* out, void* stream) {
@@ -1123,6 +1133,47 @@ extern "C" int b200_seg_counts(const float* score, const float* label, int64_t n
     if (sms <= 0) return fail(B200_ERR_CUDA, "no CUDA device");
     CUDA_TRY(launch_seg_counts(score, label, nsamples, voxels_per_sample, threshold,
                                reinterpret_cast<unsigned long long*>(counts), sms, (cudaStream_t)stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ sliding windows
+static int check_windows(int nwin, int64_t wd, int64_t wh, int64_t ww, int64_t d, int64_t h, int64_t w,
+                         const char* who) {
+    REQUIRE(nwin > 0 && nwin <= 1024, "%s: 1..1024 windows per call", who);
+    REQUIRE(wd > 0 && wh > 0 && ww > 0 && wd <= d && wh <= h && ww <= w, "%s: window larger than the volume", who);
+    return 0;
+}
+extern "C" int b200_window_gather(const float* x, int64_t n, int64_t c, int64_t d, int64_t h, int64_t w,
+                                  const int32_t* origins, int nwin, int64_t wd, int64_t wh, int64_t ww, float* out,
+                                  void* stream) {
+    REQUIRE(x && origins && out && n > 0 && c > 0, "window_gather: bad arguments");
+    int rc = check_windows(nwin, wd, wh, ww, d, h, w, "window_gather");
+    if (rc) return rc;
+    const int sms = sm_count();
+    if (sms <= 0) return fail(B200_ERR_CUDA, "no CUDA device");
+    CUDA_TRY(launch_window_gather(x, c, d, h, w, origins, nwin, (int)wd, (int)wh, (int)ww, out, sms,
+                                  (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int b200_window_accumulate(const float* logits, const int32_t* origins, int nwin, int64_t k, int64_t wd,
+                                      int64_t wh, int64_t ww, float* acc, int64_t n, int64_t d, int64_t h, int64_t w,
+                                      int v_lo, int v_cnt, void* stream) {
+    REQUIRE(logits && origins && acc && k > 0, "window_accumulate: bad arguments");
+    REQUIRE(v_lo >= 0 && v_cnt > 0 && v_lo + v_cnt <= n, "window_accumulate: volume range outside the batch");
+    int rc = check_windows(nwin, wd, wh, ww, d, h, w, "window_accumulate");
+    if (rc) return rc;
+    const int sms = sm_count();
+    if (sms <= 0) return fail(B200_ERR_CUDA, "no CUDA device");
+    CUDA_TRY(launch_window_accumulate(logits, origins, nwin, k, (int)wd, (int)wh, (int)ww, acc, d, h, w, v_lo, v_cnt,
+                                      sms, (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int b200_window_finalize(float* acc, const int32_t* cover, int64_t nk, int64_t d, int64_t h, int64_t w,
+                                    float threshold, float* probs, float* mask, void* stream) {
+    REQUIRE(acc && cover && nk > 0 && d > 0 && h > 0 && w > 0, "window_finalize: bad arguments");
+    const int sms = sm_count();
+    if (sms <= 0) return fail(B200_ERR_CUDA, "no CUDA device");
+    CUDA_TRY(launch_window_finalize(acc, cover, nk, d, h, w, threshold, probs, mask, sms, (cudaStream_t)stream));
     return 0;
 }
 

@@ -640,7 +640,12 @@ cudaError_t launch_bn_bwd_apply(View dout, View y, const float* scale, const flo
 }
 
 // ------------------------------------------------------------------------------------------------ channel sum
-__global__ void __launch_bounds__(256) channel_sum_kernel(View v, float* out, int c8, int rows, long long nvox) {
+// per-channel sum over a box [d0, d0+bd) x [h0, h0+bh) x [w0, w0+bw) of every sample (the whole volume by default):
+// the bias gradient of a transposed convolution is the sum of the output gradient over the un-padded core of the
+// concat half (the F.pad border, models/unet3d.py:149-151, carries no bias)
+__global__ void __launch_bounds__(256) channel_sum_kernel(View v, float* out, int c8, int rows, long long nvox,
+                                                          int d0, int h0, int w0, FastDiv bwd, FastDiv bhd,
+                                                          FastDiv bdd, int boxed) {
     extern __shared__ float smem[];
     const int row = threadIdx.x / c8, cv = threadIdx.x - row * c8;
     const bool active = row < rows;
@@ -649,22 +654,41 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(View v, float* out, in
     for (int j = 0; j < 8; ++j) acc[0][j] = 0.f;
     if (active) {
         for (long long i = (long long)blockIdx.x * rows + row; i < nvox; i += (long long)gridDim.x * rows) {
+            long long vox = i;
+            if (boxed) {
+                uint32_t r = (uint32_t)i, q = bwd.quot(r);
+                const uint32_t w = r - q * bwd.div;
+                r = q; q = bhd.quot(r);
+                const uint32_t h = r - q * bhd.div;
+                r = q; q = bdd.quot(r);
+                const uint32_t d = r - q * bdd.div;
+                vox = (((long long)q * v.d + d0 + d) * v.h + h0 + h) * v.w + w0 + w;
+            }
             float x[8];
-            unpack8(ld8_stream(v.p + i * v.ld + cv * 8), x);
+            unpack8(ld8_stream(v.p + vox * v.ld + cv * 8), x);
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[0][j] += x[j];
         }
     }
     block_reduce_store<1>(acc, c8, rows, row, cv, active, smem, out, (int)v.c, true);
 }
-cudaError_t launch_channel_sum(View v, float* out, cudaStream_t s) {
+cudaError_t launch_channel_sum(View v, float* out, const int* box, cudaStream_t s) {
     const LaneMap m = lane_map(v.c);
-    const long long nvox = v.voxels();
+    long long nvox = v.voxels();
+    int boxed = 0, d0 = 0, h0 = 0, w0 = 0;
+    FastDiv bw, bh, bd;
+    if (box) {
+        boxed = 1;
+        d0 = box[0]; h0 = box[1]; w0 = box[2];
+        nvox = v.n * (long long)box[3] * box[4] * box[5];
+        if (nvox >= (1LL << 31)) return cudaErrorInvalidValue;
+        bd = FastDiv((uint32_t)box[3]); bh = FastDiv((uint32_t)box[4]); bw = FastDiv((uint32_t)box[5]);
+    }
     long long blocks = (nvox + m.rows * 8LL - 1) / (m.rows * 8LL);
     if (blocks > 148 * 4) blocks = 148 * 4;
     if (blocks < 1) blocks = 1;
     const size_t smem = reduce_smem_bytes(m, 1);
-    channel_sum_kernel<<<(int)blocks, 256, smem, s>>>(v, out, m.c8, m.rows, nvox);
+    channel_sum_kernel<<<(int)blocks, 256, smem, s>>>(v, out, m.c8, m.rows, nvox, d0, h0, w0, bw, bh, bd, boxed);
     return cudaGetLastError();
 }
 
@@ -1373,6 +1397,102 @@ cudaError_t launch_seg_counts(const float* score, const float* label, long long 
     if (bx * nsmp > (long long)sms * 16) bx = (int)((sms * 16 + nsmp - 1) / nsmp);
     if (bx < 1) bx = 1;
     seg_counts_kernel<<<dim3(bx, (unsigned)nsmp), 256, 0, s>>>(score, label, per, threshold, counts);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ sliding windows
+// Sliding-window inference (BASELINE configs[3]; the reference's script/predict.py:152-172 predicts whole volumes, a
+// window schedule is the new capability): windows (volume, d0, h0, w0) of a batch of fp32 volumes are gathered into
+// one contiguous batch, their logits are summed back into the volume in schedule order, and the sums are divided by
+// the number of covering windows (a product of per-axis counts), squashed and thresholded in one pass.
+__global__ void __launch_bounds__(256) window_gather_kernel(const float* __restrict__ x, long long C, long long D,
+                                                            long long H, long long W, const int* __restrict__ org,
+                                                            int wd, int wh, int ww, float* __restrict__ out,
+                                                            long long per_win) {
+    const int win = blockIdx.y;
+    const int v = org[4 * win], d0 = org[4 * win + 1], h0 = org[4 * win + 2], w0 = org[4 * win + 3];
+    const float* src = x + (long long)v * C * D * H * W;
+    float* dst = out + (long long)win * per_win;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_win;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long r = i;
+        const int l = (int)(r % ww); r /= ww;
+        const int j = (int)(r % wh); r /= wh;
+        const int k = (int)(r % wd); r /= wd;   // r = channel
+        dst[i] = __ldg(src + ((r * D + d0 + k) * H + h0 + j) * W + w0 + l);
+    }
+}
+cudaError_t launch_window_gather(const float* x, long long c, long long d, long long h, long long w, const int* org,
+                                 int nwin, int wd, int wh, int ww, float* out, int sms, cudaStream_t s) {
+    const long long per = c * wd * wh * ww;
+    dim3 grid((unsigned)grid_for(per, 256, sms, 8), (unsigned)nwin);
+    window_gather_kernel<<<grid, 256, 0, s>>>(x, c, d, h, w, org, wd, wh, ww, out, per);
+    return cudaGetLastError();
+}
+// one thread per voxel of the volumes [v_lo, v_lo + v_cnt): the windows of the launch that cover it are added in
+// schedule order (deterministic: no atomics although windows overlap)
+__global__ void __launch_bounds__(256) window_accumulate_kernel(const float* __restrict__ lg, const int* __restrict__ org,
+                                                                int nwin, long long K, int wd, int wh, int ww,
+                                                                float* __restrict__ acc, long long D, long long H,
+                                                                long long W, int v_lo, long long total) {
+    extern __shared__ int s_org[];
+    for (int i = threadIdx.x; i < 4 * nwin; i += blockDim.x) s_org[i] = org[i];
+    __syncthreads();
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long r = i;
+        const int w = (int)(r % W); r /= W;
+        const int h = (int)(r % H); r /= H;
+        const int d = (int)(r % D); r /= D;
+        const int k = (int)(r % K); r /= K;
+        const int v = v_lo + (int)r;
+        float a = 0.f;
+        bool hit = false;
+        for (int q = 0; q < nwin; ++q) {
+            const int dd = d - s_org[4 * q + 1], hh = h - s_org[4 * q + 2], wl = w - s_org[4 * q + 3];
+            if (s_org[4 * q] == v && (unsigned)dd < (unsigned)wd && (unsigned)hh < (unsigned)wh &&
+                (unsigned)wl < (unsigned)ww) {
+                a += __ldg(lg + ((((long long)q * K + k) * wd + dd) * wh + hh) * ww + wl);
+                hit = true;
+            }
+        }
+        if (hit) {
+            float* dst = acc + ((((long long)v * K + k) * D + d) * H + h) * W + w;
+            *dst += a;
+        }
+    }
+}
+cudaError_t launch_window_accumulate(const float* lg, const int* org, int nwin, long long k, int wd, int wh, int ww,
+                                     float* acc, long long d, long long h, long long w, int v_lo, int v_cnt, int sms,
+                                     cudaStream_t s) {
+    const long long total = (long long)v_cnt * k * d * h * w;
+    window_accumulate_kernel<<<grid_for(total, 256, sms, 16), 256, 4 * nwin * sizeof(int), s>>>(
+        lg, org, nwin, k, wd, wh, ww, acc, d, h, w, v_lo, total);
+    return cudaGetLastError();
+}
+__global__ void __launch_bounds__(256) window_finalize_kernel(float* __restrict__ acc, const int* __restrict__ cover,
+                                                              long long D, long long H, long long W, float threshold,
+                                                              float* __restrict__ probs, float* __restrict__ mask,
+                                                              long long total) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long r = i;
+        const int w = (int)(r % W); r /= W;
+        const int h = (int)(r % H); r /= H;
+        const int d = (int)(r % D);
+        const float cnt = (float)(cover[d] * cover[D + h] * cover[D + H + w]);
+        const float z = acc[i] / cnt;
+        acc[i] = z;
+        const float pr = 1.f / (1.f + __expf(-z));
+        if (probs) probs[i] = pr;
+        if (mask) mask[i] = pr > threshold ? 1.f : 0.f;
+    }
+}
+cudaError_t launch_window_finalize(float* acc, const int* cover, long long nk, long long d, long long h, long long w,
+                                   float threshold, float* probs, float* mask, int sms, cudaStream_t s) {
+    const long long total = nk * d * h * w;
+    window_finalize_kernel<<<grid_for(total, 256, sms, 16), 256, 0, s>>>(acc, cover, d, h, w, threshold, probs, mask,
+                                                                        total);
     return cudaGetLastError();
 }
 

@@ -68,12 +68,20 @@ cudaError_t launch_adam(float* p, const float* g, float* m, float* v, long long 
 cudaError_t launch_cast_bf16(const float* x, long long n, __nv_bfloat16* out, int sms, cudaStream_t s);
 cudaError_t launch_sumsq(const float* x, long long n, float* out, int sms, cudaStream_t s);
 cudaError_t launch_fill_zero(View v, int sms, cudaStream_t s);
-cudaError_t launch_channel_sum(View v, float* out, cudaStream_t s);
+cudaError_t launch_channel_sum(View v, float* out, const int* box /* d0,h0,w0,bd,bh,bw or null */, cudaStream_t s);
 cudaError_t launch_unpack_act(View v, float* out, cudaStream_t s);
 cudaError_t launch_resample3d(const float* in, long long nvol, int di, int hi, int wi, float* out, int dout, int ho,
                               int wo, int nearest, int binarize, int sms, cudaStream_t s);
 cudaError_t launch_minmax_normalize(float* x, long long nvol, long long per, uint32_t* keys, int sms, cudaStream_t s);
 cudaError_t launch_seg_counts(const float* score, const float* label, long long nsmp, long long per, float threshold,
                               unsigned long long* counts, int sms, cudaStream_t s);
+
+cudaError_t launch_window_gather(const float* x, long long c, long long d, long long h, long long w, const int* org,
+                                 int nwin, int wd, int wh, int ww, float* out, int sms, cudaStream_t s);
+cudaError_t launch_window_accumulate(const float* lg, const int* org, int nwin, long long k, int wd, int wh, int ww,
+                                     float* acc, long long d, long long h, long long w, int v_lo, int v_cnt, int sms,
+                                     cudaStream_t s);
+cudaError_t launch_window_finalize(float* acc, const int* cover, long long nk, long long d, long long h, long long w,
+                                   float threshold, float* probs, float* mask, int sms, cudaStream_t s);
 
 }  // namespace b200

@@ -192,8 +192,10 @@ def get_dataloader(data_dir=None, batch_size=2, shuffle=True, modalities=None, m
     """same signature as script/data_loader.py:421-423 (+ n_cases/seed); data_dir is ignored (synthetic volumes)"""
     ds = SyntheticProstateDataset(n_cases=n_cases, size=target_size, missing_strategy=missing_strategy, seed=seed,
                                   indices=indices)
+    # the shuffle order comes from a seeded generator: data-parallel ranks iterate identical global batches and each
+    # takes its share (parallel.ShardedLoader)
     return DataLoader(ds, batch_size=batch_size, shuffle=shuffle and is_training, num_workers=num_workers,
-                      pin_memory=True, drop_last=False)
+                      pin_memory=True, drop_last=False, generator=torch.Generator().manual_seed(seed + 17))
 
 
 def get_kfold_splits(n_cases, n_splits=5, seed=42):

@@ -194,9 +194,10 @@ class _DoubleConv:
         return st
 
     # ---- backward
-    def backward(self, st: _DCState, dout: ActView, dxin, grads, scratch, side):
+    def backward(self, st: _DCState, dout: ActView, dxin, grads, scratch, side, taps=None, name=""):
         """dout: gradient w.r.t. the block output; dxin: view to receive the input gradient (None: not needed).
-        Weight gradients are launched through `side` (runs them on the side stream, see Engine._Side)."""
+        Weight gradients are launched through `side` (runs them on the side stream, see Engine._Side).
+        taps (parity tooling): dict that receives every intermediate gradient view of the block."""
         n, d, h, w, _ = dout.shape
         dev = dout.t.device
         g = grads
@@ -217,6 +218,8 @@ class _DoubleConv:
         if dxin is not None:
             self.p1.dgrad(dy1, dxin)
         side.run(lambda: self.p1.wgrad(st.xin, dy1, g(self.conv1.weight)), keep=(st.xin, dy1))
+        if taps is not None:
+            taps[name] = {"dout": dout, "dy2": dy2, "da1": da1, "dy1": dy1, "dx": dxin}
 
 
 class _Side:
@@ -281,6 +284,7 @@ class Engine:
         self._slots = None       # id(param) -> (offset, numel)
         self.keep_tape = False   # parity tooling: keep the last forward's tape in .last_tape (see layer_outputs)
         self.last_tape = None
+        self.grad_taps = None    # parity tooling: dict that receives every intermediate gradient of the next backward
 
     # ------------------------------------------------------------------ parameters
     def ordered_params(self):
@@ -487,6 +491,8 @@ class Engine:
                 yield f"{name}.up", ActView(tape.cats[k], ch[k], ch[k])
             if st is None:
                 continue
+            if name != "inc":   # (the first block reads im2col rows of the network input)
+                yield f"{prefix[name]}.in", st.xin
             yield f"{prefix[name]}.0", st.y1
             yield f"{prefix[name]}.2", st.a1
             yield f"{prefix[name]}.3", st.y2
@@ -532,6 +538,7 @@ class Engine:
         ch = [f, 2 * f, 4 * f, 8 * f, 16 * f]
         g, foreign = self._begin_grads()
         sync = self.grad_sync
+        gt = self.grad_taps
         side = _Side(self.overlap_wgrad, dev)
         if dlogits.dtype != torch.float32 or not dlogits.is_contiguous():
             dlogits = dlogits.float().contiguous()
@@ -546,13 +553,15 @@ class Engine:
                      g(m.outc.weight).view(m.n_classes, -1), g(m.outc.bias))
         tape.last = None
         mark(m.outc.bias)
+        if gt is not None:
+            gt["head"] = {"dx": dcur}
         dcats = [None] * 4
         for j in (4, 3, 2, 1):
             k = 4 - j
             tp, dc = self.ups[j - 1]
             dcat = new_act(n, *dims[k], 2 * ch[k], dev)
             dcats[k] = dcat
-            dc.backward(tape.dcs[f"up{j}"], dcur, ActView(dcat), g, self.scratch, side)
+            dc.backward(tape.dcs[f"up{j}"], dcur, ActView(dcat), g, self.scratch, side, gt, f"up{j}")
             tape.dcs[f"up{j}"] = None
             mark(dc.conv1.bias)
             dupper = ActView(dcat, ch[k], ch[k])
@@ -562,27 +571,30 @@ class Engine:
             if (2 * d1, 2 * h1, 2 * w1) == dims[k]:
                 ops.channel_sum(dupper, g(tp.up.bias))
             else:  # F.pad border carries no bias gradient: reduce the un-padded core only
-                core = dupper.as_torch()[:, pad[0]:pad[0] + 2 * d1, pad[1]:pad[1] + 2 * h1, pad[2]:pad[2] + 2 * w1]
-                g(tp.up.bias).add_(core.float().sum((0, 1, 2, 3)))
+                ops.channel_sum_box(dupper, pad, (2 * d1, 2 * h1, 2 * w1), g(tp.up.bias))
             dprev = ActView(new_act(*x_in.shape, dev))
             ops.convt2x_dgrad(dupper, pad, tp.wd, dprev)
             side.run(lambda x_in=x_in, dupper=dupper, pad=pad, tp=tp: ops.convt2x_wgrad(x_in, dupper, pad,
                                                                                       g(tp.up.weight)),
                      keep=(x_in, dupper, dcat))
             mark(tp.up.bias)
+            if gt is not None:
+                gt[f"up{j}.up"] = {"dout": dupper, "dx": dprev, "x": x_in, "pad": pad}
             dcur = dprev
         tape.dec_in = None
         for k in (4, 3, 2, 1):
             dcobj = self.downs[k - 1]
             dpool = ActView(new_act(n, *dims[k], ch[k - 1], dev))
-            dcobj.backward(tape.dcs[f"down{k}"], dcur, dpool, g, self.scratch, side)
+            dcobj.backward(tape.dcs[f"down{k}"], dcur, dpool, g, self.scratch, side, gt, f"down{k}")
             tape.dcs[f"down{k}"] = None
             mark(dcobj.conv1.bias)
             skip_act = ActView(tape.cats[k - 1], 0, ch[k - 1])
             dskip = ActView(dcats[k - 1], 0, ch[k - 1])
+            if gt is not None:
+                gt[f"pool{k}"] = {"x": skip_act, "dy": dpool, "dskip_before": dskip.to_ncdhw(), "dx": dskip}
             ops.maxpool3d_bwd(skip_act, dpool, dskip, dskip)  # in place: dskip += scatter(dpool)
             dcur = dskip
-        self.inc.backward(tape.dcs["inc"], dcur, None, g, self.scratch, side)
+        self.inc.backward(tape.dcs["inc"], dcur, None, g, self.scratch, side, gt, "inc")
         mark(self.inc.conv1.bias)
         tape.dcs = tape.cats = tape.pooled = None
         if sync is not None:

@@ -299,6 +299,46 @@ def channel_sum(v: ActView, out):
     check(_lib.load().b200_channel_sum(v.ref, ptr(out), stream_ptr()), "channel_sum")
 
 
+def channel_sum_box(v: ActView, origin, extent, out):
+    """out[c] += sum over the box origin + [0, extent) of every sample"""
+    _launched(1)
+    check(_lib.load().b200_channel_sum_box(v.ref, int(origin[0]), int(origin[1]), int(origin[2]), int(extent[0]),
+                                           int(extent[1]), int(extent[2]), ptr(out), stream_ptr()), "channel_sum_box")
+
+
+def window_gather(x: torch.Tensor, origins: torch.Tensor, window) -> torch.Tensor:
+    """x (N,C,D,H,W) fp32, origins int32 (nwin,4) on the device = (volume, d0, h0, w0) -> (nwin,C,*window) fp32"""
+    _cuda_f32(x, "window_gather")
+    n, c, d, h, w = x.shape
+    nwin = origins.shape[0]
+    out = torch.empty((nwin, c) + tuple(window), device=x.device, dtype=torch.float32)
+    _launched(1)
+    check(_lib.load().b200_window_gather(ptr(x), n, c, d, h, w, ptr(origins), nwin, window[0], window[1], window[2],
+                                         ptr(out), stream_ptr()), "window_gather")
+    return out
+
+
+def window_accumulate(logits: torch.Tensor, origins: torch.Tensor, acc: torch.Tensor, v_lo: int, v_cnt: int):
+    """acc (N,K,D,H,W) += logits (nwin,K,wd,wh,ww) at their origins, in list order, for volumes [v_lo, v_lo+v_cnt)"""
+    _cuda_f32(logits, "window_accumulate")
+    _cuda_f32(acc, "window_accumulate")
+    nwin, k, wd, wh, ww = logits.shape
+    n, _, d, h, w = acc.shape
+    _launched(1)
+    check(_lib.load().b200_window_accumulate(ptr(logits), ptr(origins), nwin, k, wd, wh, ww, ptr(acc), n, d, h, w,
+                                             int(v_lo), int(v_cnt), stream_ptr()), "window_accumulate")
+
+
+def window_finalize(acc: torch.Tensor, cover: torch.Tensor, threshold=0.5, probs=None, mask=None):
+    """in place: acc (N,K,D,H,W) /= per-voxel window count (cover: int32 [D+H+W] per-axis counts); optional sigmoid
+    probabilities and thresholded mask"""
+    _cuda_f32(acc, "window_finalize")
+    n, k, d, h, w = acc.shape
+    _launched(1)
+    check(_lib.load().b200_window_finalize(ptr(acc), ptr(cover), n * k, d, h, w, float(threshold), ptr(probs),
+                                           ptr(mask), stream_ptr()), "window_finalize")
+
+
 def _cuda_f32(t, what):
     if not t.is_cuda:
         raise _lib.B200Error(f"{what}: b200 kernels need CUDA tensors: there is no CPU path")
@@ -391,5 +431,6 @@ for _n in ("pack_input", "im2col_input", "pack_rows", "pack_conv_weight", "pack_
            "conv1_fprop", "conv3d_dgrad", "conv3d_wgrad", "conv1_wgrad", "convt2x_fwd", "convt2x_dgrad",
            "convt2x_wgrad", "bn_finalize", "bn_fold_eval", "bn_apply_relu", "bn_bwd", "maxpool3d_fwd",
            "maxpool3d_bwd", "head_fwd", "head_bwd", "loss_fwd", "loss_bwd", "adam_step", "cast_bf16", "sumsq",
-           "fill_zero", "channel_sum", "resample3d", "minmax_normalize_", "seg_counts"):
+           "fill_zero", "channel_sum", "channel_sum_box", "window_gather", "window_accumulate", "window_finalize",
+           "resample3d", "minmax_normalize_", "seg_counts"):
     globals()[_n] = _op(globals()[_n])

@@ -8,8 +8,107 @@
   * sliding-window inference: windows of a volume are independent -> dealt round-robin to ranks, per-rank accumulation
     of logits, one all-reduce(sum) of the logit volume, uniform averaging, sigmoid, threshold.
 """
+import os
+
 import torch
 import torch.distributed as dist
+
+from . import ops
+
+
+# ------------------------------------------------------------------------------------------------ process group
+def dist_info(group=None):
+    """(rank, world) of the initialised process group, (0, 1) without one"""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def init_distributed(backend=None):
+    """One process per GPU, as launched by `python -m torch.distributed.run ...` (RANK / LOCAL_RANK / WORLD_SIZE /
+    MASTER_* in the environment).  Binds this process to its GPU and creates the process group (NCCL over
+    NVLink/NVSwitch; B200_DIST_BACKEND=gloo for the one-GPU test rig, where several ranks share a device).
+    Returns (rank, world, device); a plain single-process run returns (0, 1, current cuda device)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    ndev = torch.cuda.device_count()
+    dev = torch.device("cuda", local % max(ndev, 1))
+    torch.cuda.set_device(dev)
+    if world > 1 and not dist.is_initialized():
+        backend = backend or os.environ.get("B200_DIST_BACKEND", "nccl")
+        if backend == "nccl":
+            dist.init_process_group("nccl", device_id=dev)
+        else:
+            dist.init_process_group(backend)
+    rank, world = dist_info()
+    return rank, world, dev
+
+
+def backend_is_nccl(group=None) -> bool:
+    return dist.is_initialized() and dist.get_backend(group) == "nccl"
+
+
+def shutdown_distributed():
+    if dist.is_available() and dist.is_initialized():
+        torch.cuda.synchronize()
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def all_mean(value: float, device, group=None) -> float:
+    """mean over ranks of a host scalar (epoch losses: every rank must see the same number, it drives the LR
+    scheduler and early stopping)"""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return float(value)
+    t = torch.tensor([float(value)], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return float(t.item()) / dist.get_world_size(group)
+
+
+def sync_buffers(model, group=None):
+    """BatchNorm running statistics are rank-local during training; before validation and before a checkpoint every
+    rank takes rank 0's (DistributedDataParallel's broadcast_buffers behaviour)"""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        for b in model.buffers():
+            dist.broadcast(b, src=0, group=group)
+
+
+def shard_dict_batch(batch, rank, world, keys=("image", "label")):
+    """this rank's contiguous share of a global batch dict (tensors under `keys`, lists alongside); None when the
+    batch holds fewer samples than ranks (skipped on every rank alike: a rank without samples could not take part
+    in the gradient exchange)"""
+    n = batch[keys[0]].shape[0]
+    if world == 1:
+        return batch
+    if n < world:
+        return None
+    sl = shard_batch(n, rank, world)
+    out = {}
+    for k, v in batch.items():
+        if torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == n:
+            out[k] = v[sl]
+        elif isinstance(v, (list, tuple)) and len(v) == n:
+            out[k] = list(v[sl])
+        else:
+            out[k] = v
+    return out
+
+
+class ShardedLoader:
+    """iterates a loader of GLOBAL batches and yields this rank's share of each (every rank must iterate the same
+    batches in the same order: data.get_dataloader shuffles with a seeded generator for that reason)"""
+
+    def __init__(self, loader, rank, world):
+        self.loader, self.rank, self.world = loader, rank, world
+
+    def __len__(self):
+        return len(self.loader)
+
+    def __iter__(self):
+        for batch in self.loader:
+            part = shard_dict_batch(batch, self.rank, self.world)
+            if part is not None:
+                yield part
 
 
 def plan_buckets(total: int, boundaries, bucket_elems: int):
@@ -119,6 +218,21 @@ def window_schedule(shape, window, stride):
     return sched, (wd, wh, ww)
 
 
+def window_cover(shape, window, stride):
+    """per-axis number of windows covering each coordinate, concatenated [D + H + W] (int32): the windows of a volume
+    are the product of the per-axis origin lists, so a voxel is covered by cover[d] * cover[D+h] * cover[D+H+w]"""
+    _, _, D, H, W = shape
+    out = []
+    for extent, win, st in ((D, window[0], stride[0]), (H, window[1], stride[1]), (W, window[2], stride[2])):
+        win = min(win, extent)
+        c = [0] * extent
+        for o in window_origins(extent, win, st):
+            for i in range(o, o + win):
+                c[i] += 1
+        out += c
+    return torch.tensor(out, dtype=torch.int32)
+
+
 def rank_windows(sched, rank, world):
     """this rank's share of the window schedule: a contiguous block, so that a rank touches as few volumes as possible
     (one volume per rank when the volume count equals the world size: only that volume has to be uploaded there)"""
@@ -131,37 +245,74 @@ def rank_volumes(shape, window, stride, rank, world):
     return sorted({w[0] for w in rank_windows(sched, rank, world)})
 
 
+def volume_owners(shape, window, stride, world):
+    """{volume: (owner rank, [ranks that evaluate some of its windows])}; the owner is the lowest such rank and is
+    the one that ends up with the volume's result"""
+    sched, _ = window_schedule(shape, window, stride)
+    touch = {}
+    for r in range(world):
+        for w in rank_windows(sched, r, world):
+            touch.setdefault(w[0], []).append(r)
+    return {v: (min(rs), sorted(set(rs))) for v, rs in touch.items()}
+
+
+def owned_volumes(shape, window, stride, rank, world):
+    return sorted(v for v, (o, _) in volume_owners(shape, window, stride, world).items() if o == rank)
+
+
 @torch.no_grad()
 def sliding_window_logits(model, x, window=(128, 128, 64), stride=(64, 64, 64), rank=0, world=1, group=None,
-                          windows_per_launch=9, reduce=True):
-    """Average of window logits over a batch of volumes; with world > 1 every rank evaluates its contiguous block of
-    the window schedule (rank_windows) and the partial sums are all-reduced.  x: (N, C, D, H, W) on this rank's GPU;
-    only the volumes named by rank_volumes() are read on this rank.  Windows are evaluated `windows_per_launch` at a
-    time as one batch (measured at 5x256x256x64 on one B200: 222 / 264 / 279 M voxels/s for 1 / 3 / 9 windows per
-    launch — fuller waves on the deep levels); the accumulation order is the schedule order either way."""
+                          windows_per_launch=9, reduce=True, exchange="owner", threshold=0.5, want=("logits",)):
+    """Uniform average of window logits over a batch of volumes x (N, C, D, H, W) fp32 on this rank's GPU.
+
+    With world > 1 every rank evaluates a contiguous block of the window schedule (rank_windows; only the volumes
+    named by rank_volumes() are read here).  A volume whose windows all sit on one rank never leaves that rank; a
+    volume split over several ranks has its partial logit sums reduced to its owner (`exchange="owner"`, the lowest
+    rank that evaluates one of its windows) — the only exchange of the path.  `exchange="all"` all-reduces every
+    volume instead, so that every rank holds the full result.  The returned tensors are valid for owned_volumes()
+    (all volumes with world == 1 or exchange="all"), zeros elsewhere.
+
+    Windows are evaluated `windows_per_launch` at a time as one batch (fuller waves on the deep levels); gather,
+    accumulation (schedule order, no atomics), averaging, sigmoid and threshold are three small kernels
+    (ops.window_gather / window_accumulate / window_finalize).  want: any of "logits", "probs", "mask"; returns them
+    in that order (a single tensor when one is asked for).  reduce=False returns this rank's partial sums and the
+    cover table instead (caller reduces)."""
     model.eval()
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        x = x.float().contiguous()
     n, _, D, H, W = x.shape
-    sched, (wd, wh, ww) = window_schedule(x.shape, window, stride)
+    sched, win = window_schedule(x.shape, window, stride)
     acc = torch.zeros(n, model.n_classes, D, H, W, device=x.device, dtype=torch.float32)
-    cnt = torch.zeros(n, 1, D, H, W, device=x.device, dtype=torch.float32)
     mine = rank_windows(sched, rank, world)
-    for i in range(0, len(mine), windows_per_launch):
-        chunk = mine[i:i + windows_per_launch]
-        xb = torch.stack([x[v, :, d0:d0 + wd, h0:h0 + wh, w0:w0 + ww] for (v, d0, h0, w0) in chunk])
-        lg = model(xb.contiguous())
-        for j, (v, d0, h0, w0) in enumerate(chunk):
-            acc[v, :, d0:d0 + wd, h0:h0 + wh, w0:w0 + ww] += lg[j]
-    for (v, d0, h0, w0) in sched:  # the count map is deterministic: every rank builds the full one locally
-        cnt[v, :, d0:d0 + wd, h0:h0 + wh, w0:w0 + ww] += 1
+    if mine:
+        org = torch.tensor(mine, dtype=torch.int32).pin_memory().to(x.device, non_blocking=True)
+        for i in range(0, len(mine), windows_per_launch):
+            chunk = mine[i:i + windows_per_launch]
+            o = org[i:i + len(chunk)]
+            lg = model(ops.window_gather(x, o, win))
+            v_lo, v_hi = chunk[0][0], chunk[-1][0]
+            ops.window_accumulate(lg, o, acc, v_lo, v_hi - v_lo + 1)
+    cover = window_cover(x.shape, win, stride).to(x.device)
     if world > 1 and not reduce:
-        return acc, cnt  # this rank's partial logit sums (caller reduces) and the full count map
+        return acc, cover
     if world > 1:
-        dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
-    return acc / cnt
+        if exchange == "all":
+            dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
+        else:
+            for v, (owner, ranks) in sorted(volume_owners(x.shape, window, stride, world).items()):
+                # every rank runs the same sequence of collectives: one reduce per split volume
+                if len(ranks) > 1:
+                    dist.reduce(acc[v], dst=owner, op=dist.ReduceOp.SUM, group=group)
+                    if rank != owner:
+                        acc[v].zero_()
+    probs = torch.empty_like(acc) if "probs" in want else None
+    mask = torch.empty_like(acc) if "mask" in want else None
+    ops.window_finalize(acc, cover, threshold, probs, mask)
+    res = tuple({"logits": acc, "probs": probs, "mask": mask}[k] for k in want)
+    return res[0] if len(res) == 1 else res
 
 
 @torch.no_grad()
 def sliding_window_predict(model, x, window=(128, 128, 64), stride=(64, 64, 64), threshold=0.5, **kw):
-    logits = sliding_window_logits(model, x, window, stride, **kw)
-    probs = torch.sigmoid(logits)
-    return probs, (probs > threshold).float()
+    """(probabilities, 0/1 float mask) of the window-averaged logits; see sliding_window_logits"""
+    return sliding_window_logits(model, x, window, stride, threshold=threshold, want=("probs", "mask"), **kw)

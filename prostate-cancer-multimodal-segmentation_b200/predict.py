@@ -11,6 +11,57 @@ from . import parallel
 from .unet3d import UNet3D
 
 
+PREDICT_MODALITIES = ["ADC", "DWI", "gaoqing-T2", "T2 fs", "T2 not fs"]   # channel order of script/predict.py:24
+
+
+def _read_volume(path):
+    if path.endswith(".npy"):
+        return np.load(path)
+    import SimpleITK as sitk  # noqa: N813  (NIfTI needs SimpleITK, which is not part of this build)
+    return sitk.GetArrayFromImage(sitk.ReadImage(path))
+
+
+def load_multimodal_images(case_dir, handle_missing="zero_fill"):
+    """(image (5, D, H, W) float32 in [0, 1], modality names) of one case directory — script/predict.py:8-82 with the
+    same layout, order, missing-modality rules and per-modality min-max normalisation.  Each modality is a
+    sub-directory `case_dir/<modality>/` holding one volume file; `.npy` volumes are read natively (`.nii` only when
+    SimpleITK is importable: NIfTI IO is outside this build).  A missing sub-directory raises FileNotFoundError; an
+    empty one is zero-filled (shape of the first modality found, or 64^3 before any), duplicated from the first
+    modality found (`duplicate`), or an error (`skip`), exactly as the reference does."""
+    try:
+        import SimpleITK  # noqa: F401, N813
+        exts = (".npy", ".nii")
+    except ImportError:
+        exts = (".npy",)
+    images, reference = [], None
+    for modality in PREDICT_MODALITIES:
+        mdir = os.path.join(case_dir, modality)
+        if not os.path.exists(mdir):
+            raise FileNotFoundError(f"模态目录不存在: {mdir}")
+        files = sorted(f for f in os.listdir(mdir) if f.endswith(exts))
+        if not files:
+            if handle_missing == "zero_fill":
+                img = np.zeros_like(reference, dtype=np.float32) if reference is not None else \
+                    np.zeros((64, 64, 64), dtype=np.float32)
+                print(f"警告: 模态 {modality} 缺失，使用零填充")
+            elif handle_missing == "duplicate" and reference is not None:
+                img = reference.copy()
+                print(f"警告: 模态 {modality} 缺失，使用参考模态填充")
+            else:
+                raise FileNotFoundError(f"在 {mdir} 中未找到.nii文件")
+        else:
+            if len(files) > 1:
+                print(f"警告: 在 {mdir} 中找到多个.nii文件，将使用第一个文件")
+            img = _read_volume(os.path.join(mdir, files[0]))
+            if reference is None:
+                reference = img
+        img = img.astype(np.float32)
+        lo, hi = img.min(), img.max()
+        img = (img - lo) / (hi - lo) if hi - lo != 0 else np.zeros_like(img, dtype=np.float32)
+        images.append(img)
+    return np.stack(images, axis=0), list(PREDICT_MODALITIES)
+
+
 def preprocess_image(image):
     """(5, D, H, W) numpy -> (1, 5, D, H, W) float tensor (script/predict.py:84-101)"""
     return torch.from_numpy(np.ascontiguousarray(image)).float().unsqueeze(0)

@@ -8,7 +8,13 @@ Differences from the reference, all on purpose:
   * data comes from `config['train_loader']` / `config['val_loader']` when given, else from the synthetic source in
     data.py (NIfTI IO is out of scope);
   * the optimizer is the fused Adam (same update rule); `config['optimizer'] = 'torch'` selects torch.optim.Adam;
-  * optional `config['clip_grad_norm']` (train_bph.py:166) is folded into the fused optimizer's gradient scale.
+  * optional `config['clip_grad_norm']` (train_bph.py:166) is folded into the fused optimizer's gradient scale;
+  * under `python -m torch.distributed.run` (one process per GPU) the trainers are data-parallel: identical replicas
+    (rank 0's weights and BatchNorm buffers are broadcast), every global batch of `config['batch_size']` samples is
+    split contiguously over the ranks, BatchNorm statistics and the loss stay rank-local, the flat gradient is
+    all-reduced in buckets while backward still runs (parallel.GradSync) and 1/world is folded into the fused Adam.
+    Epoch losses are averaged over ranks (so scheduler and early stopping agree everywhere); rank 0 alone writes
+    checkpoints, after every rank has taken rank 0's BatchNorm buffers.
 """
 import json
 import os
@@ -18,6 +24,7 @@ from torch import optim
 
 from . import data as _data
 from . import ops
+from . import parallel as _par
 from .losses import BCEDiceLoss, DiceLoss
 from .optim import FusedAdam
 from .unet3d import UNet3D
@@ -28,18 +35,41 @@ class BaseTrainer:
 
     def __init__(self, config):
         self.config = config
-        self.device = torch.device(config.get("device", "cuda"))
+        self.rank, self.world = _par.dist_info()
+        if self.world > 1 and "device" not in config:
+            self.device = torch.device("cuda", torch.cuda.current_device())   # set by parallel.init_distributed
+        else:
+            self.device = torch.device(config.get("device", "cuda"))
         self.model = self._create_model()
         self.criterion = self._create_criterion()
         self.optimizer = self._create_optimizer()
         self.scheduler = self._create_scheduler()
+        self.grad_sync = None
+        if self.world > 1:
+            if not isinstance(self.optimizer, FusedAdam):
+                raise ValueError("data-parallel training needs the fused optimizer (config['optimizer'] = 'fused'): "
+                                 "the 1/world gradient scale is folded into its update")
+            self.grad_sync = _par.make_data_parallel(self.model, self.optimizer,
+                                                     bucket_mb=config.get("bucket_mb", 25.0))
         self.train_loader = self._create_dataloader("train")
         self.val_loader = self._create_dataloader("test") if config.get("validation", False) else None
-        os.makedirs(config["save_dir"], exist_ok=True)
+        if self.rank == 0:
+            os.makedirs(config["save_dir"], exist_ok=True)
         self.history = []
+        self._graphed = None
+
+    def close(self):
+        """drop the recorded step (it holds NCCL kernels: must go before the process group does)"""
+        self._graphed = None
+        import gc
+        gc.collect()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
 
     # ---- factories (names as in the reference)
     def _create_model(self):
+        if self.config.get("seed") is not None:   # reproducible initialisation (the reference never seeds)
+            torch.manual_seed(int(self.config["seed"]))
         return UNet3D(n_modalities=5, n_classes=1,
                       init_features=self.config.get("init_features", 64)).to(self.device)
 
@@ -58,7 +88,13 @@ class BaseTrainer:
     def _create_dataloader(self, mode):
         key = "train_loader" if mode == "train" else "val_loader"
         if self.config.get(key) is not None:
-            return self.config[key]
+            loader = self.config[key]
+        else:
+            loader = self._synthetic_loader(mode)
+        # data-parallel: the loader yields GLOBAL batches, every rank takes its contiguous share
+        return _par.ShardedLoader(loader, self.rank, self.world) if self.world > 1 else loader
+
+    def _synthetic_loader(self, mode):
         return _data.get_dataloader(
             self.config.get("data_dir"), batch_size=self.config["batch_size"],
             missing_strategy=self.config.get("handle_missing_modalities", "zero_fill"),
@@ -73,7 +109,10 @@ class BaseTrainer:
             # the whole step replayed from a CUDA graph after two eager steps (graph.py); same arithmetic
             if getattr(self, "_graphed", None) is None:
                 from .graph import GraphedTrainStep
-                self._graphed = GraphedTrainStep(self.model, self.criterion, self.optimizer)
+                # data-parallel ranks record the NCCL bucket all-reduces into the graph as well (gloo cannot be
+                # captured: those ranks launch eagerly)
+                self._graphed = GraphedTrainStep(self.model, self.criterion, self.optimizer,
+                                                 capture_collectives=self.world > 1 and _par.backend_is_nccl())
             return self._graphed(images, labels)
         self.optimizer.zero_grad()
         outputs = self.model(images)
@@ -99,21 +138,26 @@ class BaseTrainer:
             losses.push(self._step(batch["image"], batch["label"]))
             n += 1
         total = sum(losses.finish())
-        return total / max(n, 1)
+        return _par.all_mean(total / max(n, 1), self.device)
 
     def validate_epoch(self):
         if self.val_loader is None:
             return None
+        _par.sync_buffers(self.model)   # every rank evaluates with rank 0's running statistics
         self.model.eval()
         total, n = 0.0, 0
         with torch.no_grad():
             for batch in _data.DevicePrefetcher(self.val_loader, self.device):
                 total += self.criterion(self.model(batch["image"]), batch["label"]).item()
                 n += 1
-        return total / max(n, 1)
+        return _par.all_mean(total / max(n, 1), self.device)
 
     def save_checkpoint(self, epoch, loss, is_best=False):
-        """latest_checkpoint.pth (dict) and best_model_epoch_{E}.pth (raw state_dict): utils/trainer.py:255-278"""
+        """latest_checkpoint.pth (dict) and best_model_epoch_{E}.pth (raw state_dict): utils/trainer.py:255-278.
+        Data-parallel: every rank calls this (the buffer broadcast is a collective), rank 0 writes."""
+        _par.sync_buffers(self.model)
+        if self.rank != 0:
+            return
         sd = {k: v.detach().clone().cpu() for k, v in self.model.state_dict().items()}
         ckpt = {"epoch": epoch, "model_state_dict": sd, "optimizer_state_dict": self.optimizer.state_dict(),
                 "scheduler_state_dict": self.scheduler.state_dict(), "loss": loss,
@@ -136,15 +180,16 @@ class BaseTrainer:
 
     def train(self):
         cfg = self.config
-        print(f"training {cfg.get('data_type', 'BPH')}: epochs {cfg['num_epochs']}, batch {cfg['batch_size']}, "
-              f"lr {cfg['learning_rate']}, device {cfg.get('device', 'cuda')}, save_dir {cfg['save_dir']}")
+        say = print if self.rank == 0 else (lambda *a, **k: None)
+        say(f"training {cfg.get('data_type', 'BPH')}: epochs {cfg['num_epochs']}, batch {cfg['batch_size']}, "
+            f"lr {cfg['learning_rate']}, device {self.device}, ranks {self.world}, save_dir {cfg['save_dir']}")
         best, patience = float("inf"), 0
         for epoch in range(cfg["num_epochs"]):
             train_loss = self.train_epoch()
             val_loss = self.validate_epoch()
             monitored = val_loss if val_loss is not None else train_loss
-            print(f"epoch {epoch + 1}/{cfg['num_epochs']}: train {train_loss:.4f}"
-                  + (f", val {val_loss:.4f}" if val_loss is not None else ""))
+            say(f"epoch {epoch + 1}/{cfg['num_epochs']}: train {train_loss:.4f}"
+                + (f", val {val_loss:.4f}" if val_loss is not None else ""))
             self.history.append({"epoch": epoch + 1, "train_loss": train_loss, "val_loss": val_loss})
             self.scheduler.step(monitored)
             if monitored < best:
@@ -153,9 +198,9 @@ class BaseTrainer:
             else:
                 patience += 1
             if patience >= self.max_patience:
-                print(f"early stop: {self.max_patience} epochs without improvement")
+                say(f"early stop: {self.max_patience} epochs without improvement")
                 break
-        print(f"done, best loss {best:.4f}")
+        say(f"done, best loss {best:.4f}")
         return best
 
 
@@ -178,7 +223,14 @@ class CrossValidationTrainer:
 
     def __init__(self, config):
         self.config = config
-        self.device = torch.device(config.get("device", "cuda"))
+        self.rank, self.world = _par.dist_info()
+        # config['fold_parallel']: folds are dealt to the ranks (replicas only, no gradient exchange); otherwise
+        # every fold is trained data-parallel over all ranks, folds one after another (train_bph_optimized.py:428-429)
+        self.dp = self.world > 1 and not config.get("fold_parallel", False)
+        if self.world > 1 and "device" not in config:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        else:
+            self.device = torch.device(config.get("device", "cuda"))
         self.n_splits = config.get("n_splits", 5)
         self.n_cases = config.get("n_cases", 10)
         self.splits = _data.get_kfold_splits(self.n_cases, self.n_splits)
@@ -189,11 +241,12 @@ class CrossValidationTrainer:
         return UNet3D(5, 1, init_features=self.config.get("init_features", 64)).to(self.device)
 
     def _loader(self, indices, training):
-        return _data.get_dataloader(self.config.get("data_dir"), batch_size=self.config["batch_size"],
-                                    missing_strategy=self.config.get("handle_missing_modalities", "zero_fill"),
-                                    target_size=tuple(self.config.get("target_size", (128, 128, 128))),
-                                    is_training=training, data_type=self.config.get("data_type", "BPH"),
-                                    indices=indices, n_cases=self.n_cases)
+        loader = _data.get_dataloader(self.config.get("data_dir"), batch_size=self.config["batch_size"],
+                                      missing_strategy=self.config.get("handle_missing_modalities", "zero_fill"),
+                                      target_size=tuple(self.config.get("target_size", (128, 128, 128))),
+                                      is_training=training, data_type=self.config.get("data_type", "BPH"),
+                                      indices=indices, n_cases=self.n_cases)
+        return _par.ShardedLoader(loader, self.rank, self.world) if self.dp else loader
 
     @staticmethod
     def _fix_labels(outputs, labels):
@@ -207,6 +260,8 @@ class CrossValidationTrainer:
     def train_fold(self, fold_idx, train_idx, val_idx):
         model = self._create_model()
         opt = FusedAdam(model, lr=self.config["learning_rate"], weight_decay=1e-5)
+        if self.dp:
+            _par.make_data_parallel(model, opt, bucket_mb=self.config.get("bucket_mb", 25.0))
         sched = optim.lr_scheduler.ReduceLROnPlateau(opt, mode="min", patience=10, factor=0.5)
         crit = DiceLoss()
         train_loader, val_loader = self._loader(train_idx, True), self._loader(val_idx, False)
@@ -225,6 +280,8 @@ class CrossValidationTrainer:
                 scaler.step(opt)
                 scaler.update()
                 tl += loss.item(); n += 1
+            if self.dp:
+                _par.sync_buffers(model)
             model.eval()
             vl, m = 0.0, 0
             with torch.no_grad():
@@ -233,6 +290,8 @@ class CrossValidationTrainer:
                     outputs = model(images)
                     vl += crit(outputs, self._fix_labels(outputs, labels)).item(); m += 1
             tl, vl = tl / max(n, 1), vl / max(m, 1)
+            if self.dp:
+                tl, vl = _par.all_mean(tl, self.device), _par.all_mean(vl, self.device)
             hist.append({"epoch": epoch + 1, "train_loss": tl, "val_loss": vl})
             sched.step(vl)
             if vl < best:
@@ -248,6 +307,10 @@ class CrossValidationTrainer:
         return result
 
     def save_best_model(self, model, fold_idx, epoch, loss):
+        if self.dp:
+            _par.sync_buffers(model)
+            if self.rank != 0:
+                return
         sd = {k: v.detach().clone().cpu() for k, v in model.state_dict().items()}
         torch.save({"epoch": epoch, "model_state_dict": sd, "fold_idx": fold_idx, "loss": loss,
                     "config": {k: v for k, v in self.config.items() if not k.endswith("_loader")}},
@@ -267,7 +330,9 @@ class CrossValidationTrainer:
         for fold_idx, (tr, va) in enumerate(self.splits):
             if fold_idx % world == rank:
                 self.train_fold(fold_idx, tr, va)
-        if world > 1 and dist.is_available() and dist.is_initialized():
+        if self.dp:   # every rank trained every fold together and holds the same (rank-averaged) results
+            rank = self.rank
+        elif world > 1 and dist.is_available() and dist.is_initialized():
             parts = [None] * world
             dist.all_gather_object(parts, self.fold_results)
             self.fold_results = sorted((r for part in parts for r in part), key=lambda r: r["fold"])

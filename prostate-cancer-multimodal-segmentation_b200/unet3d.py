@@ -3,8 +3,9 @@ and buffer names (136 state_dict entries at base 64), same initialisation RNG or
 B200 engine (tcgen05 implicit-GEMM convolutions, fused BatchNorm/ReLU, in-place skip concat) instead of torch.nn ops.
 
 The torch.nn layer objects below are *parameter containers*: they give identical ``state_dict`` keys, identical
-default/Kaiming initialisation (models/unet3d.py:227-245) and keep ``isinstance`` checks in user code working. Their
-own ``forward`` is never called on the hot path.
+default/Kaiming initialisation (models/unet3d.py:227-245) and keep ``isinstance`` checks in user code working.  Inside a
+``UNet3D`` the engine schedules the whole network; called on their own, ``DoubleConv3D`` / ``Down3D`` / ``Up3D`` run the
+same kernels block by block (blocks.py).
 """
 import torch
 import torch.nn as nn
@@ -29,9 +30,9 @@ class DoubleConv3D(nn.Module):
         )
 
     def forward(self, x):
-        raise NotImplementedError(
-            "DoubleConv3D is executed by the UNet3D engine on B200; standalone block execution is not part of the "
-            "hot path (there is no torch fallback)")
+        """stand-alone call (inside a UNet3D the network engine schedules the block): same B200 kernels"""
+        from .blocks import run_block
+        return run_block(self, "double", x)
 
 
 class Down3D(nn.Module):
@@ -42,7 +43,8 @@ class Down3D(nn.Module):
         self.maxpool_conv = nn.Sequential(nn.MaxPool3d(2), DoubleConv3D(in_channels, out_channels))
 
     def forward(self, x):
-        raise NotImplementedError("Down3D is executed by the UNet3D engine on B200 (no torch fallback)")
+        from .blocks import run_block
+        return run_block(self, "down", x)
 
 
 class Up3D(nn.Module):
@@ -54,7 +56,9 @@ class Up3D(nn.Module):
         self.conv = DoubleConv3D(in_channels, out_channels)
 
     def forward(self, x1, x2):
-        raise NotImplementedError("Up3D is executed by the UNet3D engine on B200 (no torch fallback)")
+        """x1: the coarser feature map (upsampled 2x), x2: the skip connection (models/unet3d.py:134-158)"""
+        from .blocks import run_block
+        return run_block(self, "up", x1, x2)
 
 
 class _UNetFunction(torch.autograd.Function):

@@ -118,8 +118,11 @@ def test_sliding_window_inference_vs_oracle(pkg, cuda_dev):
     # sharding the window list over ranks changes nothing but the order of additions
     parts = [pkg.parallel.sliding_window_logits(model, x, window, stride, rank=r, world=3, reduce=False)
              for r in range(3)]
-    merged = sum(p[0] for p in parts) / parts[0][1]
+    merged = sum(p[0] for p in parts)
+    pkg.ops.window_finalize(merged, parts[0][1])   # divide by the per-voxel window count
     assert torch.allclose(merged, got, rtol=1e-5, atol=1e-5)
+    # contiguous blocks of the schedule: volume 0 is shared by ranks 0 and 1 and owned by rank 0
+    assert pkg.parallel.volume_owners(tuple(x.shape), window, stride, 3) == {0: (0, [0, 1]), 1: (1, [1, 2])}
     sched, _ = pkg.parallel.window_schedule(x.shape, window, stride)
     assert len(sched) == 2 * 2 * 2 * 1   # origins (0,16) x (0,8) x (0,) per volume
     probs, mask = pkg.parallel.sliding_window_predict(model, x, window, stride)
@@ -146,6 +149,6 @@ def test_cli_train_validate_predict(pkg, cuda_dev, tmp_path):
     out = cli.main(["predict", "--model_path", model_path, "--output_dir", str(tmp_path / "pred")] + common)
     assert out.shape == (16, 16, 16)
     rep = cli.main(["check"])
-    assert rep["abi_version"] == 1 and rep["sm_count"] > 0
+    assert rep["abi_version"] == 2 and rep["sm_count"] > 0
     # failures are reported, not raised (run.py:339-344)
     assert cli.main(["predict", "--model_path", "/nonexistent.pth"] + common) is None

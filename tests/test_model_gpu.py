@@ -154,20 +154,19 @@ def test_pad_path_two_classes_vs_reference_golden(pkg, cuda_dev):
     assert logits.shape == (1, 2, 20, 36, 18)
     err = rel_l2(logits.cpu(), gold["logits_train"])
     assert err < TOL_LAYER, f"pad path rel-L2 {err}"
-    # gradients through the pad path vs the oracle (odd extents: pool remainder voxels, padded concat halves)
-    y2 = (torch.rand(1, 2, 20, 36, 18, device=cuda_dev) > 0.8).float()
-    model.zero_grad()
-    out = model(x)
-    pkg.BCEDiceLoss()(out, y2).backward()
-    # (the bottom level holds 2 values per channel here: BatchNorm over 2 samples amplifies any rounding, so the
-    #  end-to-end bound is the stock-bf16 yardstick with a wider slack)
-    _, og, _ = oracle_grads(sd, x, y2)
-    _, yg, _ = oracle_grads(sd, x, y2, autocast_bf16=True)
-    report, bad = check_grads_against_yardstick(model, og, yg, floor=5e-2, slack=3.0)
-    with open(os.path.join(ROOT, "gpurun_out", "grad_parity_pad.txt"), "w") as f:
-        for k, (a, b) in report.items():
-            f.write(f"{k} {a:.4e} {b:.4e}\n")
-    assert not bad, f"pad path gradient rel-L2 (ours, stock bf16 autocast): {bad}"
+    # gradients through the pad path (odd extents: pool remainder voxels, padded concat halves).  The bottom level
+    # holds 2 values per channel here, so BatchNorm amplifies any rounding end to end; the bound is the bf16-storage
+    # oracle's own sensitivity to a one-fp32-rounding perturbation (tests/parity_util.py), floor 2e-2 — every single
+    # op of this shape is checked at 4e-3 on identical inputs in tests/test_fullsize_gpu.py (case odd_2class)
+    import parity_util as pu
+    res = pu.train_step_parity(pkg, cuda_dev, batch=1, size=(20, 36, 18), base=64, n_classes=2, seed=gold["seed"],
+                               x_seed=gold["x_seed"])
+    pu.write_report(res, os.path.join(ROOT, "gpurun_out", "parity_pad_2class.txt"))
+    assert abs(res["loss"]["ours"] - res["loss"]["fp32"]) < 1e-3
+    bad = {n: row for n, row in res["grads"].items()
+           if row["ours_vs_storage"] > max(TOL_LAYER, 1.25 * row["storage~_vs_storage"])
+           or row["ours_vs_fp32"] > max(TOL_LAYER, 1.25 * row["storage_vs_fp32"])}
+    assert not bad, f"pad path gradients beyond the bf16-storage yardstick: {bad}"
 
 
 def test_state_dict_roundtrip_and_foreign_optimizer(pkg, cuda_dev):

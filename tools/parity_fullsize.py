@@ -36,3 +36,10 @@ if __name__ == "__main__":
         torch.cuda.empty_cache()
     with open(os.path.join(out, f"{tag}_parity_summary.json"), "w") as f:
         json.dump(summary, f, indent=1)
+    # layer-by-layer check with identical inputs at the same shapes
+    for name in cases:
+        rows = pu.layerwise_check(pkg, dev, **CASES[name])
+        pu.write_layerwise(rows, os.path.join(out, f"{tag}_layerwise_{name}.txt"), header=f"{name}: {CASES[name]}")
+        worst = max((r for r in rows if not r[1].endswith("mismatches") and r[0] != "loss"), key=lambda r: r[2])
+        print(name, "layerwise worst", worst, flush=True)
+        torch.cuda.empty_cache()
