@@ -320,9 +320,13 @@ def layerwise_check(pkg, device, batch, size, base=64, n_classes=1, zero_fill=Fa
             add(f"{pre}.{bi}", "fwd", f32(fw[f"{pre}.{ak}"]), aref.detach())
             dout = f32(g["dout"] if ci == 3 else g["da1"])
             gy, gg, gbb = torch.autograd.grad(aref, [yv, gam, bet], dout)
-            add(f"{pre}.{bi}", "dx", dy, gy)
-            add(f"{pre}.{bi}", "dgamma", pg[f"{pre}.{bi}.weight"], gg)
-            add(f"{pre}.{bi}", "dbeta", pg[f"{pre}.{bi}.bias"], gbb)
+            per_channel = yv.numel() // yv.shape[1]
+            # BatchNorm over a handful of samples is degenerate (2 samples: x-hat = +-1, the input gradient cancels to
+            # rounding noise, a zero variance puts every output ON the ReLU threshold): reported, not comparable
+            tag = "" if per_channel >= 16 else f"(degenerate:{per_channel}_samples_per_channel)"
+            add(f"{pre}.{bi}", "dx" + tag, dy, gy)
+            add(f"{pre}.{bi}", "dgamma" + tag, pg[f"{pre}.{bi}.weight"], gg)
+            add(f"{pre}.{bi}", "dbeta" + tag, pg[f"{pre}.{bi}.bias"], gbb)
             del yv, aref, dout, gy, dy
         del xin
         torch.cuda.empty_cache()

@@ -6,8 +6,8 @@ GPUs are present.
 
 Oracle: oracle.dp_train_step — every rank's shard forward/backward from the same weights with rank-local
 BatchNorm statistics and loss, mean of the parameter gradients, one Adam step, BatchNorm buffers of rank 0.  Bounds as
-in tests/test_fullsize_gpu.py: per parameter max(2e-2, 1.25 x the bf16-storage oracle's own sensitivity to a one-fp32-
-rounding perturbation)."""
+in tests/test_fullsize_gpu.py: per parameter max(2e-2, 1.5 x the bf16-storage oracle's own sensitivity to a one-fp32-
+rounding perturbation — the larger of two draws)."""
 import importlib
 import os
 import sys
@@ -91,14 +91,15 @@ def _dp_worker(rank, world, port, out):
         l32, g32, sd32 = run(sd0, None)
         ls, gs, sds = run(sd0, oracle.store_bf16)
         _, gp, _ = run(sd0, oracle.store_bf16, perturb=5)
+        _, gp2, _ = run(sd0, oracle.store_bf16, perturb=6)
         res["loss_err"] = abs(mean_loss - l32.item())
         bad = {}
         for n, gg in grads.items():
             if pu.is_dead_bias(n):
                 continue
-            sens = _rel(gp[n], gs[n])
+            sens = max(_rel(gp[n], gs[n]), _rel(gp2[n], gs[n]))
             e_s, e_f = _rel(gg, gs[n]), _rel(gg, g32[n])
-            if e_s > max(2e-2, 1.25 * sens) or e_f > max(2e-2, 1.25 * _rel(gs[n], g32[n])):
+            if e_s > max(2e-2, 1.5 * sens) or e_f > max(2e-2, 1.5 * _rel(gs[n], g32[n])):
                 bad[n] = (e_s, sens, e_f)
         res["bad_grads"] = bad
         res["near_loss"] = {n: _rel(grads[n], g32[n]) for n in ("outc.weight", "outc.bias", "up4.conv.conv.4.weight")}

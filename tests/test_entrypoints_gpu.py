@@ -21,7 +21,8 @@ pytestmark = pytest.mark.gpu
 def _cfg(tmp_path, **kw):
     cfg = {"data_dir": None, "num_epochs": 3, "batch_size": 2, "learning_rate": 1e-3, "device": "cuda:0",
            "save_dir": str(tmp_path), "data_type": "BPH", "handle_missing_modalities": "zero_fill",
-           "validation": True, "init_features": 16, "target_size": (16, 16, 16), "n_cases": 6, "loss": "bce_dice"}
+           "validation": True, "init_features": 16, "target_size": (16, 16, 16), "n_cases": 6, "loss": "bce_dice",
+           "seed": 0}
     cfg.update(kw)
     return cfg
 
@@ -32,7 +33,8 @@ def test_base_trainer_trains_and_checkpoints(pkg, cuda_dev, tmp_path):
         assert hasattr(tr, attr)
     first = tr.train_epoch()
     best = tr.train()
-    assert best < first
+    # the training loss falls over the three further epochs (`best` is the monitored validation loss)
+    assert tr.history[-1]["train_loss"] < first and best == min(h["val_loss"] for h in tr.history)
     files = os.listdir(tmp_path)
     assert "latest_checkpoint.pth" in files and any(f.startswith("best_model_epoch_") for f in files)
     ckpt = torch.load(os.path.join(tmp_path, "latest_checkpoint.pth"), weights_only=False)

@@ -21,6 +21,7 @@ import unet3d_oracle as oracle  # noqa: E402
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(ROOT, "tests", "golden")
 TOL_LAYER = 2e-2
+SLACK = 1.5   # on the bf16-storage yardsticks of tests/parity_util.py (each is a single random draw)
 
 
 def synth(shape, seed, device):
@@ -164,8 +165,8 @@ def test_pad_path_two_classes_vs_reference_golden(pkg, cuda_dev):
     pu.write_report(res, os.path.join(ROOT, "gpurun_out", "parity_pad_2class.txt"))
     assert abs(res["loss"]["ours"] - res["loss"]["fp32"]) < 1e-3
     bad = {n: row for n, row in res["grads"].items()
-           if row["ours_vs_storage"] > max(TOL_LAYER, 1.25 * row["storage~_vs_storage"])
-           or row["ours_vs_fp32"] > max(TOL_LAYER, 1.25 * row["storage_vs_fp32"])}
+           if row["ours_vs_storage"] > max(TOL_LAYER, SLACK * row["storage~_vs_storage"])
+           or row["ours_vs_fp32"] > max(TOL_LAYER, SLACK * row["storage_vs_fp32"])}
     assert not bad, f"pad path gradients beyond the bf16-storage yardstick: {bad}"
 
 
