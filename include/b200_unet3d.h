@@ -183,6 +183,18 @@ int b200_minmax_normalize(float* x, int64_t nvol, int64_t voxels_per_volume, voi
 int b200_seg_counts(const float* score, const float* label, int64_t nsamples, int64_t voxels_per_sample,
                     float threshold, int64_t* counts, void* stream);
 
+/* First conv of the 5-modality network straight from the fp32 (N,5,D,H,W) input: the im2col rows are built in shared
+ * memory inside the GEMM kernels (never in HBM).  w_rows = b200_pack_rows of the (Cout,5,3,3,3) weight, k_pad = 144;
+ * modes as b200_conv3d_fprop; dw is fp32 [Cout][135] (+=).  models/unet3d.py:194 (inc = DoubleConv3D(5, 64)), :29.
+ * b200_conv1_direct_supported(c, cout) != 0 tells whether this form exists for the channel counts (c == 5); other
+ * thin inputs use b200_im2col_input + b200_conv1_fprop / b200_conv1_wgrad. */
+int b200_conv1_direct_supported(int64_t c, int64_t cout);
+int b200_conv1_direct_fprop(const float* x, int64_t n, int64_t c, int64_t d, int64_t h, int64_t w, const void* w_rows,
+                            const float* bias, const b200_act* y, float* stats_partial, int mode, const float* scale,
+                            const float* shift, void* stream);
+int b200_conv1_direct_wgrad(const float* x, int64_t n, int64_t c, int64_t d, int64_t h, int64_t w, const b200_act* dy,
+                            float* dw, void* stream);
+
 /* per-channel sum over the box [d0,d0+bd) x [h0,h0+bh) x [w0,w0+bw) of every sample, added to out[c] (fp32): the
  * ConvTranspose3d bias gradient when F.pad (models/unet3d.py:149-151) put a zero border around the upsampled map */
 int b200_channel_sum_box(const b200_act* v, int d0, int h0, int w0, int bd, int bh, int bw, float* out, void* stream);

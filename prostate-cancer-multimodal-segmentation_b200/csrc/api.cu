@@ -17,6 +17,8 @@ namespace b200 {
 extern "C" __global__ void igemm_kernel(const __grid_constant__ IgemmParams p);
 extern "C" __global__ void wgrad_kernel(const __grid_constant__ WgradParams p);
 extern "C" __global__ void igemm_pair_kernel(const __grid_constant__ IgemmParams p);
+extern "C" __global__ void igemm_im2col5_kernel(const __grid_constant__ IgemmParams p);
+extern "C" __global__ void wgrad_im2col5_kernel(const __grid_constant__ WgradParams p);
 extern "C" __global__ void dmarch_kernel(const __grid_constant__ DmarchParams p);
 extern "C" __global__ void dmarch_pair_kernel(const __grid_constant__ DmarchParams p);
 extern "C" __global__ void wgrad_halo_kernel(const __grid_constant__ WgradHaloParams p);
@@ -298,9 +300,20 @@ static void set_plain_stage(IgemmParams& p) {
 static int launch_igemm(IgemmParams& p, cudaStream_t s, int* grid_out) {
     const int sms = sm_count();
     if (sms <= 0) return fail(B200_ERR_CUDA, "no CUDA device");
-    static SmemOptIn optin;
+    static SmemOptIn optin, optin_i2c;
     if (p.stages < 2) return fail(B200_ERR_UNSUPPORTED_SHAPE, "igemm: tile does not fit shared memory");
     const size_t smem = igemm_smem(p.stages, p.a_stage_bytes, b_stage_bytes(p), epi_staging_bytes(p));
+    if (p.x_src) {   // direct first-layer form: A built in shared memory by warps 8..15 (512 threads)
+        const int rc_attr = ensure_smem(igemm_im2col5_kernel, 227 * 1024, optin_i2c);
+        if (rc_attr) return rc_attr;
+        const long long tiles_ = (long long)p.nbw * p.nbh * p.nbd * p.nbatch * p.n_tiles;
+        const int grid_ = (int)(tiles_ < sms ? tiles_ : sms);
+        if (grid_out) *grid_out = grid_;
+        p.ablate = 0;
+        igemm_im2col5_kernel<<<grid_, kIm2colThreads, smem, s>>>(p);
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
     if (!p.pair) {   // the pair kernel is opted in by igemm_max_clusters() (per device)
         const int rc_attr = ensure_smem(igemm_kernel, 227 * 1024, optin);
         if (rc_attr) return rc_attr;
@@ -697,7 +710,14 @@ static int launch_wgrad(WgradParams& p, cudaStream_t s) {
     if (splits < 1) splits = 1;
     p.splits = (int)splits;
     const long long grid = base_ctas * splits;
-    wgrad_kernel<<<(int)grid, kThreads, smem, s>>>(p);
+    if (p.x_src) {
+        static SmemOptIn optin_i2c;
+        const int rc_attr = ensure_smem(wgrad_im2col5_kernel, (int)smem, optin_i2c);
+        if (rc_attr) return rc_attr;
+        wgrad_im2col5_kernel<<<(int)grid, kIm2colThreads, smem, s>>>(p);
+    } else {
+        wgrad_kernel<<<(int)grid, kThreads, smem, s>>>(p);
+    }
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -848,6 +868,105 @@ extern "C" int b200_conv1_wgrad(const b200_act* x, const b200_act* dy, float* dw
     p.st = 0;
     p.sp = k_real;
     p.sq = 1;
+    return launch_wgrad(p, (cudaStream_t)stream);
+}
+
+// ---- first layer straight from the fp32 network input (no im2col buffer in HBM)
+static int log2_exact(int v) {
+    int l = 0;
+    while ((1 << l) < v) ++l;
+    return l;
+}
+extern "C" int b200_conv1_direct_supported(int64_t c, int64_t cout) {
+    return (c == 5 && cout % 16 == 0 && cout >= 16 && cout <= 256) ? 1 : 0;   // the 5-modality input of the reference
+}
+extern "C" int b200_conv1_direct_fprop(const float* x, int64_t n, int64_t c, int64_t d, int64_t h, int64_t w,
+                                       const void* w_rows, const float* bias, const b200_act* y,
+                                       float* stats_partial, int mode, const float* scale, const float* shift,
+                                       void* stream) {
+    CHECK_VIEW(y);
+    REQUIRE(x && w_rows, "conv1_direct_fprop: null input / weights");
+    REQUIRE(b200_conv1_direct_supported(c, y->c), "conv1_direct_fprop: needs 5 input channels and 16..256 outputs");
+    REQUIRE(y->n == n && y->d == d && y->h == h && y->w == w, "conv1_direct_fprop: extent mismatch");
+    REQUIRE(n * d * h * w < (1LL << 31), "conv1_direct_fprop: too many voxels");
+    const float *v0 = nullptr, *v1 = nullptr;
+    switch (mode) {
+        case B200_EPI_BIAS_STATS:
+            REQUIRE(bias && stats_partial, "conv1_direct_fprop: BIAS_STATS needs bias and stats_partial");
+            v0 = bias;
+            break;
+        case B200_EPI_AFFINE_RELU:
+            REQUIRE(scale && shift, "conv1_direct_fprop: AFFINE_RELU needs scale and shift");
+            v0 = scale; v1 = shift;
+            break;
+        case B200_EPI_BIAS:
+            REQUIRE(bias, "conv1_direct_fprop: BIAS needs bias");
+            v0 = bias;
+            break;
+        case B200_EPI_PLAIN: break;
+        default: return fail(B200_ERR_BAD_ARG, "conv1_direct_fprop: unknown mode %d", mode);
+    }
+    int rc = get_encode();
+    if (rc) return rc;
+    IgemmParams p;
+    memset(&p, 0, sizeof(p));
+    const int kpad = (int)((27 * c + 15) / 16 * 16);
+    Brick b;
+    conv_geometry(n, w, h, d, y->c, 1, &b, &p.block_n);   // same tiling as b200_conv3d_stat_rows(..., ntaps = 1)
+    rc = make_weight_map(&p.b_map, w_rows, kpad, y->c, 1, p.block_n);
+    if (rc) return rc;
+    p.a_map[0] = p.b_map;   // never loaded through (the A operand is built in shared memory); a valid map to prefetch
+    p.ntaps = 1;
+    p.epi_v2 = (p.block_n <= 64 && p.block_n % 32 == 0) ? 1 : 0;
+    if (p.epi_v2) {
+        rc = make_act_map(&p.c_map[0], reinterpret_cast<const __nv_bfloat16*>(y->ptr), y->c, y->w, y->h, y->d, y->n,
+                          y->ld, y->w, y->h, y->d, 1, b.tw, b.th, b.td);
+        if (rc) return rc;
+    }
+    set_plain_stage(p);
+    p.cin = kpad;
+    p.kc_blocks = (kpad + 63) / 64;
+    p.ncols = (int)y->c;
+    p.n_tiles = (p.ncols + p.block_n - 1) / p.block_n;
+    set_m_grid(p, b, n, w, h, d);
+    p.mode = mode;
+    p.vec0 = v0; p.vec1 = v1; p.stats = stats_partial;
+    set_out(p, y);
+    p.out_mul = 1;
+    p.cols_per_group = p.ncols;
+    p.x_src = x;
+    return launch_igemm(p, (cudaStream_t)stream, nullptr);
+}
+extern "C" int b200_conv1_direct_wgrad(const float* x, int64_t n, int64_t c, int64_t d, int64_t h, int64_t w,
+                                       const b200_act* dy, float* dw, void* stream) {
+    CHECK_VIEW(dy);
+    REQUIRE(x && dw, "conv1_direct_wgrad: null input / dw");
+    REQUIRE(b200_conv1_direct_supported(c, dy->c), "conv1_direct_wgrad: needs 5 input channels and 16..256 outputs");
+    REQUIRE(dy->n == n && dy->d == d && dy->h == h && dy->w == w, "conv1_direct_wgrad: extent mismatch");
+    int rc = get_encode();
+    if (rc) return rc;
+    WgradParams p;
+    memset(&p, 0, sizeof(p));
+    const Brick b = choose_brick(w, h, d);
+    rc = make_act_map(&p.p_map, reinterpret_cast<const __nv_bfloat16*>(dy->ptr), dy->c, dy->w, dy->h, dy->d, dy->n,
+                      dy->ld, dy->w, dy->h, dy->d, 1, b.tw, b.th, b.td);
+    if (rc) return rc;
+    p.q_map[0] = p.p_map;   // never loaded through: Q is built in shared memory
+    const int k_real = (int)(27 * c);
+    p.ntaps = 1;
+    p.tap_out[0] = 0;
+    p.p_extent = (int)dy->c;
+    p.q_extent = k_real;
+    p.q_chunks = (k_real + 63) / 64;
+    p.nbw = (int)b.nbw; p.nbh = (int)b.nbh; p.nbd = (int)b.nbd; p.nbatch = (int)n;
+    p.tw = b.tw; p.th = b.th; p.td = b.td;
+    p.tw_log2 = log2_exact(b.tw); p.th_log2 = log2_exact(b.th);
+    p.W = (int)w; p.H = (int)h; p.D = (int)d;
+    p.out = dw;
+    p.st = 0;
+    p.sp = k_real;
+    p.sq = 1;
+    p.x_src = x;
     return launch_wgrad(p, (cudaStream_t)stream);
 }
 

@@ -22,11 +22,75 @@ struct PipeState {
     }
 };
 
+
+// ------------------------------------------------------------------------------------------------
+// im2col rows built in shared memory (first layer, CIN modalities): 64 columns [64*KC, 64*KC+64) of the 128 rows of one
+// brick, written as the SWIZZLE_128B K-major box a TMA load of the (never materialised) im2col matrix would have
+// produced: row r at r*128 B, its 16-byte chunk j at ((j ^ (r & 7)) << 4).  256 producer threads: thread pt builds
+// columns 32*(pt >> 7) .. +32 of row pt & 127; every (channel, tap) of a column is a compile-time constant.
+// ------------------------------------------------------------------------------------------------
+template <int CIN, int KC, int HALF>
+DEV void im2col_cols(const float* __restrict__ xb, long long plane, int hw, int W, const bool (&okdh)[9],
+                     const bool (&okw)[3], uint32_t row_addr, uint32_t sw) {
+    constexpr int K = 27 * CIN;
+    constexpr int COL0 = 64 * KC + 32 * HALF;
+    if (COL0 >= ((K + 15) / 16) * 16) return;   // beyond the padded row: the MMAs never read these columns
+    auto tap = [&](int k) -> float {
+        if (k >= K) return 0.f;
+        const int c = k / 27, t = k % 27, kd = t / 9, kh = (t / 3) % 3, kw = t % 3;
+        if (!(okdh[kd * 3 + kh] && okw[kw])) return 0.f;
+        return __ldg(xb + ((long long)c * plane + (kd - 1) * hw + (kh - 1) * W + (kw - 1)));
+    };
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int k0 = COL0 + 8 * q;
+        if (k0 < ((K + 15) / 16) * 16) {
+            const uint32_t a = pack_bf16x2(tap(k0), tap(k0 + 1)), b = pack_bf16x2(tap(k0 + 2), tap(k0 + 3));
+            const uint32_t c = pack_bf16x2(tap(k0 + 4), tap(k0 + 5)), d = pack_bf16x2(tap(k0 + 6), tap(k0 + 7));
+            st_shared_v4(row_addr + ((((uint32_t)(HALF * 4 + q)) ^ sw) << 4), a, b, c, d);
+        }
+    }
+}
+struct BrickGeom {
+    int tw_log2, th_log2, W, H, D, nbatch;
+};
+template <int CIN>
+DEV void im2col_stage(const float* __restrict__ x, uint32_t box, int kc, int pt, int w0, int h0, int d0, int nb,
+                      const BrickGeom& g) {
+    const int row = pt & 127, half = pt >> 7;   // half is warp-uniform
+    const int rw = row & ((1 << g.tw_log2) - 1);
+    const int rh = (row >> g.tw_log2) & ((1 << g.th_log2) - 1);
+    const int rd = row >> (g.tw_log2 + g.th_log2);
+    const int w = w0 + rw, h = h0 + rh, d = d0 + rd;
+    const bool vox_ok = w < g.W && h < g.H && d < g.D && nb < g.nbatch;
+    const int hw = g.H * g.W;
+    const long long plane = (long long)g.D * hw;
+    const float* xb = x + ((long long)nb * CIN * plane + ((long long)d * hw + h * g.W + w));
+    bool okdh[9], okw[3];
+#pragma unroll
+    for (int i = 0; i < 9; ++i)
+        okdh[i] = vox_ok && (unsigned)(d + i / 3 - 1) < (unsigned)g.D && (unsigned)(h + i % 3 - 1) < (unsigned)g.H;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) okw[i] = (unsigned)(w + i - 1) < (unsigned)g.W;
+    const uint32_t row_addr = box + row * 128, sw = row & 7;
+    if (half == 0) {
+        if (kc == 0) im2col_cols<CIN, 0, 0>(xb, plane, hw, g.W, okdh, okw, row_addr, sw);
+        else if (kc == 1) im2col_cols<CIN, 1, 0>(xb, plane, hw, g.W, okdh, okw, row_addr, sw);
+        else im2col_cols<CIN, 2, 0>(xb, plane, hw, g.W, okdh, okw, row_addr, sw);
+    } else {
+        if (kc == 0) im2col_cols<CIN, 0, 1>(xb, plane, hw, g.W, okdh, okw, row_addr, sw);
+        else if (kc == 1) im2col_cols<CIN, 1, 1>(xb, plane, hw, g.W, okdh, okw, row_addr, sw);
+        else im2col_cols<CIN, 2, 1>(xb, plane, hw, g.W, okdh, okw, row_addr, sw);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // igemm_kernel
 // ------------------------------------------------------------------------------------------------
 // smem: [stages x A box 16 KB][stages x B tile block_n x 128 B][barriers][tmem ptr][stats scratch][column sums]
-template <bool kPair>
+// kIm2colC > 0: direct first-layer form — launched with kIm2colThreads threads; warps 8..15 build the A boxes from the
+// fp32 network input (kIm2colC modalities), the TMA producer only fetches B (see IgemmParams::x_src)
+template <bool kPair, int kIm2colC = 0>
 DEV void igemm_body(const IgemmParams& p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -70,7 +134,7 @@ DEV void igemm_body(const IgemmParams& p) {
     }
     if (warp == 1 && lane == 0) {
         for (uint32_t s = 0; s < nst; ++s) {
-            mbar_init(full_bar(s), 1);
+            mbar_init(full_bar(s), kIm2colC ? 1 + 8 : 1);   // + one arrival per A-building warp
             mbar_init(empty_bar(s), 1);
         }
         for (uint32_t s = 0; s < 2; ++s) {
@@ -133,8 +197,8 @@ DEV void igemm_body(const IgemmParams& p) {
                         if (B200_ABLATE(p) == 1) {
                             if (rank == 0) mbar_arrive(fb);
                         } else if (!kPair) {
-                            mbar_arrive_expect_tx(fb, a_bytes + b_bytes);
-                            tma_load_5d(smem_a + ps.stage * a_bytes, amap, fb, kc * 64, cw, ch, cd, nb);
+                            mbar_arrive_expect_tx(fb, kIm2colC ? b_bytes : a_bytes + b_bytes);
+                            if (!kIm2colC) tma_load_5d(smem_a + ps.stage * a_bytes, amap, fb, kc * 64, cw, ch, cd, nb);
                             if (p.b_mn) {
                                 for (uint32_t a = 0; a < b_atoms; ++a)
                                     tma_load_3d(smem_b + ps.stage * b_bytes + a * b_atom_bytes, &p.b_map, fb,
@@ -228,7 +292,31 @@ DEV void igemm_body(const IgemmParams& p) {
             }
             __syncwarp();
         }
-    } else if (warp >= 4) {
+    } else if (kIm2colC > 0 && warp >= 8) {
+        // ===================================================================== A builders (direct first-layer form)
+        // same stage walk as the TMA producer: tile -> kc; every warp arrives once per stage after its rows are
+        // visible to the tensor core's (async-proxy) reads
+        PipeState ps;
+        const int pt = threadIdx.x - 256;
+        const int kc_blocks = p.kc_blocks, n_tiles = p.n_tiles;
+        const BrickGeom geom{p.tw_log2, p.th_log2, p.W, p.H, p.D, p.nbatch};
+        for (int tile = unit0; tile < total_tiles; tile += unit_stride) {
+            int mt = tile / n_tiles;
+            const int bw = mt % p.nbw; mt /= p.nbw;
+            const int bh = mt % p.nbh; mt /= p.nbh;
+            const int bd = mt % p.nbd; mt /= p.nbd;
+            const int nb = mt;
+            const int w0 = bw << p.tw_log2, h0 = bh << p.th_log2, d0 = bd << p.td_log2;
+            for (int kc = 0; kc < kc_blocks; ++kc) {
+                mbar_wait(empty_bar(ps.stage), ps.phase ^ 1);
+                im2col_stage<kIm2colC ? kIm2colC : 1>(p.x_src, smem_a + ps.stage * a_bytes, kc, pt, w0, h0, d0, nb, geom);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full_bar(ps.stage));
+                ps.advance(nst);
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
         // ===================================================================== epilogue
         const int q = warp - 4;  // == warp % 4: TMEM lane quarter
         const int row = q * 32 + lane;
@@ -477,6 +565,11 @@ extern "C" __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads,
     igemm_pair_kernel(const __grid_constant__ IgemmParams p) {
     igemm_body<true>(p);
 }
+// first layer of the 5-modality network (models/unet3d.py:194 inc = DoubleConv3D(5, 64)), fp32 input read directly
+extern "C" __global__ void __launch_bounds__(kIm2colThreads, 1)
+    igemm_im2col5_kernel(const __grid_constant__ IgemmParams p) {
+    igemm_body<false, 5>(p);
+}
 
 // ------------------------------------------------------------------------------------------------
 // wgrad_kernel
@@ -484,7 +577,10 @@ extern "C" __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads,
 // smem: [2 x P slot 32 KB (two 64-channel boxes)][2 x Q slot 64 KB (up to four boxes)][barriers][tmem ptr]
 // One CTA = (p tile of 128 channels, group of <= 8 column blocks, voxel split); accumulators for the whole
 // group stay in TMEM (<= 512 columns) across all bricks of the split, then are added atomically to G.
-extern "C" __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
+// kIm2colC > 0: first-layer form — the Q operand (im2col rows of the fp32 network input, kIm2colC modalities) is built
+// in shared memory by warps 8..15 instead of being loaded by TMA (kernel launched with kIm2colThreads threads)
+template <int kIm2colC>
+DEV void wgrad_body(const WgradParams& p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -508,7 +604,7 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __g
     }
     if (warp == 1 && lane == 0) {
         for (uint32_t s = 0; s < kNP; ++s) { mbar_init(pfull(s), 1); mbar_init(pempty(s), 1); }
-        for (uint32_t s = 0; s < kNQ; ++s) { mbar_init(qfull(s), 1); mbar_init(qempty(s), 1); }
+        for (uint32_t s = 0; s < kNQ; ++s) { mbar_init(qfull(s), kIm2colC ? 8 : 1); mbar_init(qempty(s), 1); }
         mbar_init(tfull, 1);
         fence_mbar_init();
     }
@@ -551,7 +647,7 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __g
             }
             __syncwarp();
             pp.advance(kNP);
-            for (int sg = 0; sg < nsg; ++sg) {
+            for (int sg = 0; sg < nsg && kIm2colC == 0; ++sg) {
                 const int nb4 = min(4, ncb - sg * 4);
                 mbar_wait(qempty(qp.stage), qp.phase ^ 1);
                 if (elect_one()) {
@@ -604,7 +700,30 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __g
         }
         if (elect_one()) umma_commit(tfull);
         __syncwarp();
-    } else if (warp >= 4) {
+    } else if (kIm2colC > 0 && warp >= 8) {
+        // ===================================================================== Q builders (first-layer form)
+        PipeState qp;
+        const int pt = threadIdx.x - 256;
+        const BrickGeom geom{p.tw_log2, p.th_log2, p.W, p.H, p.D, p.nbatch};
+        for (int b = split; b < nbricks; b += p.splits) {
+            int mt = b;
+            const int bw = mt % p.nbw; mt /= p.nbw;
+            const int bh = mt % p.nbh; mt /= p.nbh;
+            const int bd = mt % p.nbd; mt /= p.nbd;
+            const int nb = mt;
+            for (int sg = 0; sg < nsg; ++sg) {   // one slot group for the first layer (3 column blocks)
+                const int nb4 = min(4, ncb - sg * 4);
+                mbar_wait(qempty(qp.stage), qp.phase ^ 1);
+                for (int i = 0; i < nb4; ++i)
+                    im2col_stage<kIm2colC ? kIm2colC : 1>(p.x_src, smem_q + qp.stage * kQSlot + i * kBoxBytes,
+                                                          cb0 + sg * 4 + i, pt, bw * p.tw, bh * p.th, bd * p.td, nb, geom);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(qfull(qp.stage));
+                qp.advance(kNQ);
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
         // ===================================================================== epilogue
         const int q = warp - 4;
         const int row = q * 32 + lane;
@@ -691,6 +810,14 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __g
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
+}
+
+extern "C" __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
+    wgrad_body<0>(p);
+}
+extern "C" __global__ void __launch_bounds__(kIm2colThreads, 1)
+    wgrad_im2col5_kernel(const __grid_constant__ WgradParams p) {
+    wgrad_body<5>(p);
 }
 
 }  // namespace b200

@@ -70,7 +70,13 @@ struct alignas(64) IgemmParams {
     int out_mul;        // output coordinate = m coordinate * out_mul + offset[group]
     int cols_per_group; // columns sharing one output offset (transposed conv: Cout per tap)
     int out_od[kMaxMaps], out_oh[kMaxMaps], out_ow[kMaxMaps];
+    // direct first-layer form (igemm_im2col_kernel): the A operand is not loaded by TMA but built in shared memory by
+    // eight producer warps straight from the fp32 (N, C, D, H, W) network input — column k = c*27 + kd*9 + kh*3 + kw of
+    // row m is x[n, c, d+kd-1, h+kh-1, w+kw-1] (zero outside the volume), i.e. the rows of the im2col matrix, which
+    // therefore never exists in HBM (it cost 288 B per voxel to write and again to read, against 20 B of input)
+    const float* x_src;
 };
+constexpr int kIm2colThreads = 512;     // igemm_im2col_kernel: the 256 threads above + warps 8..15 building A
 
 // Depth-marching implicit GEMM for 3x3x3 convolutions with 64 output columns (fprop with Cout = 64, dgrad with Cin = 64).
 // A tcgen05.mma in SS mode costs max(N/2, ~42 + 0.18 N) cycles (tools/probe_mma.py): N = 64 cannot exceed 60 % of the
@@ -124,6 +130,9 @@ struct alignas(64) WgradParams {
     int tw, th, td;
     float* out;
     long long st, sp, sq;  // element strides of G for (tap, p, q)
+    // first-layer form (wgrad_im2col5_kernel): Q = im2col rows built in shared memory from the fp32 network input
+    const float* x_src;
+    int tw_log2, th_log2, W, H, D;
 };
 
 // h-halo variant of the weight-gradient GEMM (wgrad_halo.cu): bricks are 8 w x 16 h x 1 d; the shifted operand Q is

@@ -59,6 +59,9 @@ class _ConvPack:
         self.device = device
         self.cout, self.cin = conv.out_channels, conv.in_channels
         self.im2col = self.cin % 16 != 0 and 27 * self.cin <= 512
+        # the 5-modality first layer reads the fp32 network input directly: its im2col rows are built in shared
+        # memory inside the GEMM kernels (ops.conv1_direct_*), never in HBM
+        self.direct = self.im2col and ops.conv1_direct_supported(self.cin, self.cout)
         self.shadow = None   # set by the engine: bf16 [27][Cout][Cin] view of its parameter shadow
         self._own = None
         if self.im2col:
@@ -86,19 +89,27 @@ class _ConvPack:
         elif not self._phys(self.conv.weight.data):
             ops.pack_conv_weight(self.conv.weight.data.contiguous(), self.cin_pad, self.wf)
 
-    def make_input(self, x: torch.Tensor) -> ActView:
-        """fp32 (N,C,D,H,W) -> the bf16 operand this conv reads (channel-padded NDHWC, or im2col rows)"""
+    def make_input(self, x: torch.Tensor):
+        """fp32 (N,C,D,H,W) -> the operand this conv reads: channel-padded NDHWC bf16, im2col rows, or (direct first
+        layer) the fp32 tensor itself"""
+        if self.direct:
+            return RawInput(x)
         n, _, d, h, w = x.shape
         v = ActView(new_act(n, d, h, w, self.cin_pad, x.device))
         (ops.im2col_input if self.im2col else ops.pack_input)(x, v)
         return v
 
     def fprop(self, xin, bias, y, stats, mode, scale=None, shift=None):
+        if self.direct:
+            ops.conv1_direct_fprop(xin.t, self.wf, bias, y, stats, mode, scale, shift)
+            return
         f = ops.conv1_fprop if self.im2col else ops.conv3d_fprop
         f(xin, self.wf, bias, y, stats, mode, scale, shift, k_real=self.k_real)
 
     def wgrad(self, xin, dy, dw):
-        if self.im2col:
+        if self.direct:
+            ops.conv1_direct_wgrad(xin.t, dy, dw.view(self.cout, -1))
+        elif self.im2col:
             ops.conv1_wgrad(xin, dy, dw.view(self.cout, -1), self.k_real)
         elif dw.stride() == _phys_strides(self.cout, self.cin):
             ops.conv3d_wgrad(xin, dy, dw, self.cin, packed=True)
@@ -111,6 +122,19 @@ class _ConvPack:
         if self.im2col:
             raise B200Error("input gradient of an im2col'd (thin-input) convolution is not available")
         ops.conv3d_dgrad(dy, self.wf, dx)
+
+
+class RawInput:
+    """the fp32 (N, C, D, H, W) network input standing where an ActView would (direct first layer)"""
+    __slots__ = ("t",)
+
+    def __init__(self, t: torch.Tensor):
+        self.t = t
+
+    @property
+    def shape(self):
+        n, c, d, h, w = self.t.shape
+        return (n, d, h, w, c)
 
 
 class _ConvTPack:

@@ -120,6 +120,30 @@ def conv1_wgrad(x: ActView, dy: ActView, dw: torch.Tensor, k_real: int):
           lambda: check(lib.b200_conv1_wgrad(x.ref, dy.ref, ptr(dw), k_real, stream_ptr()), "conv1_wgrad"))
 
 
+def conv1_direct_supported(cin: int, cout: int) -> bool:
+    return bool(_lib.load().b200_conv1_direct_supported(cin, cout))
+
+
+def conv1_direct_fprop(x: torch.Tensor, w_rows, bias, y: ActView, stats=None, mode=EPI_BIAS_STATS, scale=None,
+                       shift=None):
+    """first conv straight from the fp32 (N, C, D, H, W) input: im2col rows exist only in shared memory"""
+    lib = _lib.load()
+    n, c, d, h, w = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    _gemm("igemm_im2col5_kernel", "conv1_fprop", 2.0 * y.voxels * y.c * 27 * c,
+          lambda: check(lib.b200_conv1_direct_fprop(ptr(x), n, c, d, h, w, ptr(w_rows), ptr(bias), y.ref, ptr(stats),
+                                                    mode, ptr(scale), ptr(shift), stream_ptr()), "conv1_direct_fprop"))
+
+
+def conv1_direct_wgrad(x: torch.Tensor, dy: ActView, dw: torch.Tensor):
+    lib = _lib.load()
+    n, c, d, h, w = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    _gemm("wgrad_im2col5_kernel", "conv1_wgrad", 2.0 * dy.voxels * dy.c * 27 * c,
+          lambda: check(lib.b200_conv1_direct_wgrad(ptr(x), n, c, d, h, w, dy.ref, ptr(dw), stream_ptr()),
+                        "conv1_direct_wgrad"))
+
+
 def pack_conv_weight(w: torch.Tensor, cin_pad: int, w_packed):
     _launched(1)
     cout, cin = w.shape[0], w.shape[1]
@@ -428,7 +452,7 @@ def _op(fn):
 
 
 for _n in ("pack_input", "im2col_input", "pack_rows", "pack_conv_weight", "pack_convt_weight", "conv3d_fprop",
-           "conv1_fprop", "conv3d_dgrad", "conv3d_wgrad", "conv1_wgrad", "convt2x_fwd", "convt2x_dgrad",
+           "conv1_fprop", "conv3d_dgrad", "conv3d_wgrad", "conv1_wgrad", "conv1_direct_fprop", "conv1_direct_wgrad", "convt2x_fwd", "convt2x_dgrad",
            "convt2x_wgrad", "bn_finalize", "bn_fold_eval", "bn_apply_relu", "bn_bwd", "maxpool3d_fwd",
            "maxpool3d_bwd", "head_fwd", "head_bwd", "loss_fwd", "loss_bwd", "adam_step", "cast_bf16", "sumsq",
            "fill_zero", "channel_sum", "channel_sum_box", "window_gather", "window_accumulate", "window_finalize",

@@ -383,3 +383,63 @@ def test_bad_arguments_raise(ops, pkg, cuda_dev):
     wf = torch.empty(27, 32, 24, device=cuda_dev, dtype=torch.bfloat16)
     with pytest.raises(pkg.B200Error, match="multiple of 16"):
         ops.conv3d_fprop(x, wf, None, y, None, ops.EPI_PLAIN)
+
+
+# ------------------------------------------------------------------------------------------------ first layer, direct
+# (N, D, H, W) with full and partial bricks in every axis, a volume smaller than a brick, two samples
+FIRST_LAYER_CASES = [(1, 16, 16, 16), (2, 5, 9, 140), (1, 3, 7, 6), (2, 20, 36, 18), (1, 2, 2, 128)]
+
+
+@pytest.mark.parametrize("shape", FIRST_LAYER_CASES)
+@pytest.mark.parametrize("cout", [64, 32])
+def test_first_layer_direct_fprop_and_wgrad(ops, cuda_dev, shape, cout):
+    """models/unet3d.py:194/29: Conv3d(5 -> C, 3x3x3, pad 1) computed straight from the fp32 input — the im2col rows are
+    built in shared memory inside the GEMM kernels — against F.conv3d / torch's weight gradient on the bf16-rounded
+    operands, and bit-for-bit against the materialised-im2col path it replaces (same MMAs, same operand bytes)."""
+    n, d, h, w = shape
+    assert ops.conv1_direct_supported(5, cout) and not ops.conv1_direct_supported(4, cout)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(n, 5, d, h, w, generator=g).to(cuda_dev)
+    wt = bf16_round(torch.randn(cout, 5, 3, 3, 3, generator=g) * (2.0 / 135) ** 0.5).to(cuda_dev)
+    b = (torch.randn(cout, generator=g) * 0.1).to(cuda_dev)
+    w_rows = torch.empty(cout, 144, device=cuda_dev, dtype=torch.bfloat16)
+    ops.pack_rows(wt.contiguous(), 144, w_rows)
+    yv = empty_act(ops, n, cout, d, h, w, cuda_dev)
+    rows = ops.conv3d_stat_rows(n, d, h, w, cout, 1)
+    stats = torch.full((rows, cout, 2), float("nan"), device=cuda_dev)
+    ops.conv1_direct_fprop(x, w_rows, b, yv, stats, ops.EPI_BIAS_STATS)
+    torch.cuda.synchronize()
+    got = from_act(yv)
+    ref = F.conv3d(bf16_round(x), wt, b, padding=1)
+    assert torch.isfinite(got).all()
+    assert rel_l2(got, ref) < TOL
+    s = stats.double().sum(0)
+    assert torch.allclose(s[:, 0], got.double().sum((0, 2, 3, 4)), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(s[:, 1], (got.double() ** 2).sum((0, 2, 3, 4)), rtol=1e-4, atol=1e-2)
+    # the path it replaces: im2col rows in HBM + the plain GEMM
+    rows_v = empty_act(ops, n, 144, d, h, w, cuda_dev, poison=False)
+    ops.im2col_input(x, rows_v)
+    y2 = empty_act(ops, n, cout, d, h, w, cuda_dev)
+    stats2 = torch.empty_like(stats)
+    ops.conv1_fprop(rows_v, w_rows, b, y2, stats2, ops.EPI_BIAS_STATS, k_real=135)
+    torch.cuda.synchronize()
+    assert torch.equal(from_act(y2), got)
+    # eval-mode epilogue
+    scale, shift = torch.rand(cout, device=cuda_dev) + 0.5, torch.randn(cout, device=cuda_dev) * 0.2
+    ye = empty_act(ops, n, cout, d, h, w, cuda_dev)
+    ops.conv1_direct_fprop(x, w_rows, None, ye, None, ops.EPI_AFFINE_RELU, scale, shift)
+    refe = torch.relu(F.conv3d(bf16_round(x), wt, None, padding=1) * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1))
+    assert rel_l2(from_act(ye), refe) < TOL
+    # weight gradient
+    dy = bf16_round(torch.randn(n, cout, d, h, w, generator=g)).to(cuda_dev)
+    dw = torch.zeros(cout, 135, device=cuda_dev)
+    ops.conv1_direct_wgrad(x, to_act(ops, dy), dw)
+    dw2 = torch.zeros(cout, 135, device=cuda_dev)
+    ops.conv1_wgrad(rows_v, to_act(ops, dy), dw2, 135)
+    torch.cuda.synchronize()
+    ref_dw = torch.nn.grad.conv3d_weight(bf16_round(x), wt.shape, dy, padding=1).reshape(cout, 135)
+    assert rel_l2(dw, ref_dw) < 2e-3
+    assert rel_l2(dw, dw2) < 1e-5   # same products, the split over CTAs only changes the order of the fp32 adds
+    ops.conv1_direct_wgrad(x, to_act(ops, dy), dw)   # accumulates
+    torch.cuda.synchronize()
+    assert rel_l2(dw, 2 * ref_dw) < 2e-3
