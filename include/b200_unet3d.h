@@ -186,9 +186,11 @@ int b200_seg_counts(const float* score, const float* label, int64_t nsamples, in
 /* First conv of the 5-modality network straight from the fp32 (N,5,D,H,W) input: the im2col rows are built in shared
  * memory inside the GEMM kernels (never in HBM).  w_rows = b200_pack_rows of the (Cout,5,3,3,3) weight, k_pad = 144;
  * modes as b200_conv3d_fprop; dw is fp32 [Cout][135] (+=).  models/unet3d.py:194 (inc = DoubleConv3D(5, 64)), :29.
- * b200_conv1_direct_supported(c, cout) != 0 tells whether this form exists for the channel counts (c == 5); other
- * thin inputs use b200_im2col_input + b200_conv1_fprop / b200_conv1_wgrad. */
-int b200_conv1_direct_supported(int64_t c, int64_t cout);
+ * b200_conv1_direct_supported(c, cout, w) != 0 tells whether this form exists for the channel counts (c == 5) and row
+ * length w; other thin inputs use b200_im2col_input + b200_conv1_fprop / b200_conv1_wgrad.  BIAS_STATS needs
+ * b200_conv1_direct_stat_rows(...) rows of stats_partial. */
+int b200_conv1_direct_supported(int64_t c, int64_t cout, int64_t w);
+int b200_conv1_direct_stat_rows(int64_t n, int64_t d, int64_t h, int64_t w, int64_t cout);
 int b200_conv1_direct_fprop(const float* x, int64_t n, int64_t c, int64_t d, int64_t h, int64_t w, const void* w_rows,
                             const float* bias, const b200_act* y, float* stats_partial, int mode, const float* scale,
                             const float* shift, void* stream);

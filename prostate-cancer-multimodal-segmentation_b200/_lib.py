@@ -33,7 +33,8 @@ SIGNATURES = {
     "b200_pack_rows": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "b200_conv1_fprop": (_i32, [_AP, _vp, _vp, _AP, _vp, _i32, _vp, _vp, _vp]),
     "b200_conv1_wgrad": (_i32, [_AP, _AP, _vp, _i32, _vp]),
-    "b200_conv1_direct_supported": (_i32, [_i64, _i64]),
+    "b200_conv1_direct_supported": (_i32, [_i64, _i64, _i64]),
+    "b200_conv1_direct_stat_rows": (_i32, [_i64, _i64, _i64, _i64, _i64]),
     "b200_conv1_direct_fprop": (_i32, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _AP, _vp, _i32, _vp, _vp, _vp]),
     "b200_conv1_direct_wgrad": (_i32, [_vp, _i64, _i64, _i64, _i64, _i64, _AP, _vp, _vp]),
     "b200_pack_conv_weight": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp]),

@@ -24,7 +24,7 @@ HEADERS = ["igemm.cuh", "ptx.cuh", "bandwidth.cuh", "../../include/b200_unet3d.h
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
-]
+] + os.environ.get("B200_EXTRA_NVCC_FLAGS", "").split()   # development aid (e.g. -DSOME_DEBUG_SWITCH); part of the hash
 
 
 def _paths(dev):

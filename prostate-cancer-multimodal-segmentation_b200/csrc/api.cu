@@ -201,7 +201,7 @@ static int igemm_block_n(long long ncols, long long m_tiles) {
 }
 // dynamic shared memory of igemm_kernel: 1 KB alignment slack + stages + epilogue-v2 staging + barriers, TMEM pointer,
 // statistics scratch [4][256][2], per-CTA column sums [kMaxStatCols][2], per-tile column vectors [2][256]
-constexpr int kIgemmFixedSmem = 1024 + 8 * (2 * 8 + 4) + 64 + 64 + 4 * 256 * 2 * 4 + kMaxStatCols * 2 * 4 + 2 * 256 * 4;
+constexpr int kIgemmFixedSmem = 1024 + 8 * (2 * 8 + 4) + 64 + 64 + 32 + 4 * 256 * 2 * 4 + kMaxStatCols * 2 * 4 + 2 * 256 * 4;
 constexpr int kSmemLimit = 227 * 1024;
 static int b_stage_bytes(const IgemmParams& p) {
     const int bn = p.pair ? p.block_n / 2 : p.block_n;   // pair mode: each CTA stages half of the B tile
@@ -216,7 +216,9 @@ static bool igemm_pair_ok(int block_n, int ntaps, bool b_mn, long long m_tiles) 
     return b_mn ? block_n % 128 == 0 : true;
 }
 static int igemm_max_clusters();
-static int epi_staging_bytes(const IgemmParams& p) { return p.epi_v2 ? ((p.block_n + 63) / 64) * kBoxBytes : 0; }
+static int epi_staging_bytes(const IgemmParams& p) {
+    return p.epi_v2 ? ((p.block_n + 63) / 64) * kBoxBytes * (p.c_bufs > 1 ? 2 : 1) : 0;
+}
 static int igemm_stages(int a_bytes, int b_bytes, int c_bytes) {
     const int per_stage = a_bytes + b_bytes;
     int st = (kSmemLimit - kIgemmFixedSmem - c_bytes) / per_stage;
@@ -302,9 +304,11 @@ static int launch_igemm(IgemmParams& p, cudaStream_t s, int* grid_out) {
     if (sms <= 0) return fail(B200_ERR_CUDA, "no CUDA device");
     static SmemOptIn optin, optin_i2c;
     if (p.stages < 2) return fail(B200_ERR_UNSUPPORTED_SHAPE, "igemm: tile does not fit shared memory");
+    // direct first-layer form: a short ring (one tile + one block ahead) is enough, the builders pace the kernel
+    if (p.x_src && p.stages > 4) p.stages = 4;
     const size_t smem = igemm_smem(p.stages, p.a_stage_bytes, b_stage_bytes(p), epi_staging_bytes(p));
-    if (p.x_src) {   // direct first-layer form: A built in shared memory by warps 8..15 (512 threads)
-        const int rc_attr = ensure_smem(igemm_im2col5_kernel, 227 * 1024, optin_i2c);
+    if (p.x_src) {   // A built in shared memory by warps 8..15 (512 threads)
+        const int rc_attr = ensure_smem(igemm_im2col5_kernel, (int)smem, optin_i2c);
         if (rc_attr) return rc_attr;
         const long long tiles_ = (long long)p.nbw * p.nbh * p.nbd * p.nbatch * p.n_tiles;
         const int grid_ = (int)(tiles_ < sms ? tiles_ : sms);
@@ -419,6 +423,7 @@ static int conv3_igemm(const b200_act* in, const void* w_packed, const b200_act*
     p.ntaps = ntaps;
     // epilogue v2 (staged tile + TMA store): pays off when the MMA time per tile is short, i.e. narrow N
     p.epi_v2 = (p.block_n <= 64 && p.block_n % 32 == 0) ? 1 : 0;
+    p.c_bufs = p.epi_v2 ? 2 : 1;   // one-box tiles: a second staging tile takes the store's read latency off the epilogue
     if (p.epi_v2) {
         rc = make_act_map(&p.c_map[0], reinterpret_cast<const __nv_bfloat16*>(out->ptr), out->c, out->w, out->h,
                           out->d, out->n, out->ld, out->w, out->h, out->d, 1, b.tw, b.th, b.td);
@@ -631,6 +636,7 @@ extern "C" int b200_convt2x_fwd(const b200_act* x, const void* w_fwd, const floa
     p.cols_per_group = (int)y->c;
     // the tile is K-short (K = Cin), so the epilogue dominates: stage + TMA store through 8 strided (parity) maps
     p.epi_v2 = (y->c % 64 == 0 && p.block_n % 64 == 0) ? 1 : 0;
+    p.c_bufs = (p.epi_v2 && p.block_n <= 64) ? 2 : 1;
     for (int t = 0; t < 8; ++t) {
         p.out_od[t] = pad_d + ((t >> 2) & 1);
         p.out_oh[t] = pad_h + ((t >> 1) & 1);
@@ -692,8 +698,8 @@ static int launch_wgrad(WgradParams& p, cudaStream_t s) {
     if (sms <= 0) return fail(B200_ERR_CUDA, "no CUDA device");
     static SmemOptIn optin;
     // alignment slack + 2 P slots + 2 Q slots + barriers/TMEM pointer + 4 transpose tiles of 32 x 33 floats
-    const size_t smem = 1024 + 2 * 2 * kBoxBytes + 2 * 4 * kBoxBytes + 128 + 4 * 32 * 33 * 4;
-    {
+    const size_t smem = 1024 + 2 * 2 * kBoxBytes + 2 * (p.x_src ? 3 : 4) * kBoxBytes + 128 + 4 * 32 * 33 * 4;
+    if (!p.x_src) {
         const int rc_attr = ensure_smem(wgrad_kernel, (int)smem, optin);
         if (rc_attr) return rc_attr;
     }
@@ -877,8 +883,19 @@ static int log2_exact(int v) {
     while ((1 << l) < v) ++l;
     return l;
 }
-extern "C" int b200_conv1_direct_supported(int64_t c, int64_t cout) {
+// bricks of the direct first-layer kernels: as everywhere else (128 voxels, fewest bricks)
+static Brick choose_brick_direct(long long w, long long h, long long d) { return choose_brick(w, h, d); }
+extern "C" int b200_conv1_direct_supported(int64_t c, int64_t cout, int64_t w) {
+    (void)w;   // (any row length: the builder warps read the fp32 input with plain loads)
     return (c == 5 && cout % 16 == 0 && cout >= 16 && cout <= 256) ? 1 : 0;   // the 5-modality input of the reference
+}
+extern "C" int b200_conv1_direct_stat_rows(int64_t n, int64_t d, int64_t h, int64_t w, int64_t cout) {
+    const int sms = sm_count();
+    if (sms <= 0) return -1;
+    const Brick b = choose_brick_direct(w, h, d);
+    const int bn = igemm_block_n(cout, n * b.nbw * b.nbh * b.nbd);
+    const long long tiles = n * b.nbw * b.nbh * b.nbd * ((cout + bn - 1) / bn);
+    return (int)(tiles < sms ? tiles : sms);
 }
 extern "C" int b200_conv1_direct_fprop(const float* x, int64_t n, int64_t c, int64_t d, int64_t h, int64_t w,
                                        const void* w_rows, const float* bias, const b200_act* y,
@@ -886,7 +903,7 @@ extern "C" int b200_conv1_direct_fprop(const float* x, int64_t n, int64_t c, int
                                        void* stream) {
     CHECK_VIEW(y);
     REQUIRE(x && w_rows, "conv1_direct_fprop: null input / weights");
-    REQUIRE(b200_conv1_direct_supported(c, y->c), "conv1_direct_fprop: needs 5 input channels and 16..256 outputs");
+    REQUIRE(b200_conv1_direct_supported(c, y->c, w), "conv1_direct_fprop: needs 5 input channels and 16..256 outputs");
     REQUIRE(y->n == n && y->d == d && y->h == h && y->w == w, "conv1_direct_fprop: extent mismatch");
     REQUIRE(n * d * h * w < (1LL << 31), "conv1_direct_fprop: too many voxels");
     const float *v0 = nullptr, *v1 = nullptr;
@@ -911,13 +928,14 @@ extern "C" int b200_conv1_direct_fprop(const float* x, int64_t n, int64_t c, int
     IgemmParams p;
     memset(&p, 0, sizeof(p));
     const int kpad = (int)((27 * c + 15) / 16 * 16);
-    Brick b;
-    conv_geometry(n, w, h, d, y->c, 1, &b, &p.block_n);   // same tiling as b200_conv3d_stat_rows(..., ntaps = 1)
+    const Brick b = choose_brick_direct(w, h, d);          // same tiling as b200_conv1_direct_stat_rows
+    p.block_n = igemm_block_n(y->c, n * b.nbw * b.nbh * b.nbd);
     rc = make_weight_map(&p.b_map, w_rows, kpad, y->c, 1, p.block_n);
     if (rc) return rc;
     p.a_map[0] = p.b_map;   // never loaded through (the A operand is built in shared memory); a valid map to prefetch
     p.ntaps = 1;
     p.epi_v2 = (p.block_n <= 64 && p.block_n % 32 == 0) ? 1 : 0;
+    p.c_bufs = p.epi_v2 ? 2 : 1;
     if (p.epi_v2) {
         rc = make_act_map(&p.c_map[0], reinterpret_cast<const __nv_bfloat16*>(y->ptr), y->c, y->w, y->h, y->d, y->n,
                           y->ld, y->w, y->h, y->d, 1, b.tw, b.th, b.td);
@@ -941,13 +959,13 @@ extern "C" int b200_conv1_direct_wgrad(const float* x, int64_t n, int64_t c, int
                                        const b200_act* dy, float* dw, void* stream) {
     CHECK_VIEW(dy);
     REQUIRE(x && dw, "conv1_direct_wgrad: null input / dw");
-    REQUIRE(b200_conv1_direct_supported(c, dy->c), "conv1_direct_wgrad: needs 5 input channels and 16..256 outputs");
+    REQUIRE(b200_conv1_direct_supported(c, dy->c, w), "conv1_direct_wgrad: needs 5 input channels and 16..256 outputs");
     REQUIRE(dy->n == n && dy->d == d && dy->h == h && dy->w == w, "conv1_direct_wgrad: extent mismatch");
     int rc = get_encode();
     if (rc) return rc;
     WgradParams p;
     memset(&p, 0, sizeof(p));
-    const Brick b = choose_brick(w, h, d);
+    const Brick b = choose_brick_direct(w, h, d);
     rc = make_act_map(&p.p_map, reinterpret_cast<const __nv_bfloat16*>(dy->ptr), dy->c, dy->w, dy->h, dy->d, dy->n,
                       dy->ld, dy->w, dy->h, dy->d, 1, b.tw, b.th, b.td);
     if (rc) return rc;

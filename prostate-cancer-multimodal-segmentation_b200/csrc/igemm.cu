@@ -29,60 +29,76 @@ struct PipeState {
 // produced: row r at r*128 B, its 16-byte chunk j at ((j ^ (r & 7)) << 4).  256 producer threads: thread pt builds
 // columns 32*(pt >> 7) .. +32 of row pt & 127; every (channel, tap) of a column is a compile-time constant.
 // ------------------------------------------------------------------------------------------------
-template <int CIN, int KC, int HALF>
-DEV void im2col_cols(const float* __restrict__ xb, long long plane, int hw, int W, const bool (&okdh)[9],
-                     const bool (&okw)[3], uint32_t row_addr, uint32_t sw) {
-    constexpr int K = 27 * CIN;
-    constexpr int COL0 = 64 * KC + 32 * HALF;
-    if (COL0 >= ((K + 15) / 16) * 16) return;   // beyond the padded row: the MMAs never read these columns
-    auto tap = [&](int k) -> float {
-        if (k >= K) return 0.f;
-        const int c = k / 27, t = k % 27, kd = t / 9, kh = (t / 3) % 3, kw = t % 3;
-        if (!(okdh[kd * 3 + kh] && okw[kw])) return 0.f;
-        return __ldg(xb + ((long long)c * plane + (kd - 1) * hw + (kh - 1) * W + (kw - 1)));
-    };
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int k0 = COL0 + 8 * q;
-        if (k0 < ((K + 15) / 16) * 16) {
-            const uint32_t a = pack_bf16x2(tap(k0), tap(k0 + 1)), b = pack_bf16x2(tap(k0 + 2), tap(k0 + 3));
-            const uint32_t c = pack_bf16x2(tap(k0 + 4), tap(k0 + 5)), d = pack_bf16x2(tap(k0 + 6), tap(k0 + 7));
-            st_shared_v4(row_addr + ((((uint32_t)(HALF * 4 + q)) ^ sw) << 4), a, b, c, d);
-        }
-    }
-}
 struct BrickGeom {
     int tw_log2, th_log2, W, H, D, nbatch;
 };
+// Words (two bf16 columns each) one builder thread holds for its row: thread half h owns columns 32h .. 32h+31 of each
+// 64-column block, clipped to the padded row length KPAD.  All global loads of a tile are issued before the first
+// shared-memory store (the kernel's dynamic shared memory leaves little L1, so first touches are L2 round trips: they
+// must all be in flight together, not eight at a time between stores).  Every (channel, tap) of a column is a
+// compile-time constant; voxels outside the volume read as zero (the convolution's padding).
+// (A TMA-loaded fp32 halo brick feeding these rows from shared memory was tried: the 5-D fp32 tile load raised an
+//  illegal-instruction fault on sm_100a with driver 580 and was dropped; with the loads removed altogether the kernels
+//  run 6 % / 17 % faster, which bounds what any staging scheme could gain — they are epilogue- / latency-bound.)
 template <int CIN>
-DEV void im2col_stage(const float* __restrict__ x, uint32_t box, int kc, int pt, int w0, int h0, int d0, int nb,
-                      const BrickGeom& g) {
-    const int row = pt & 127, half = pt >> 7;   // half is warp-uniform
-    const int rw = row & ((1 << g.tw_log2) - 1);
-    const int rh = (row >> g.tw_log2) & ((1 << g.th_log2) - 1);
-    const int rd = row >> (g.tw_log2 + g.th_log2);
-    const int w = w0 + rw, h = h0 + rh, d = d0 + rd;
-    const bool vox_ok = w < g.W && h < g.H && d < g.D && nb < g.nbatch;
-    const int hw = g.H * g.W;
-    const long long plane = (long long)g.D * hw;
-    const float* xb = x + ((long long)nb * CIN * plane + ((long long)d * hw + h * g.W + w));
-    bool okdh[9], okw[3];
+struct Im2colRow {
+    static constexpr int K = 27 * CIN, KPAD = (K + 15) / 16 * 16, KC = (KPAD + 63) / 64;
+    static constexpr int kMaxWords = 16 * KC;
+    uint32_t wd[kMaxWords];
+    uint32_t row_off, sw;
+
+    template <int HALF>
+    DEV void load_half(const float* __restrict__ xb, long long plane, int hw, int W, const bool (&okdh)[9],
+                       const bool (&okw)[3]) {
+        auto tap = [&](int k) -> float {
+            if (k >= K) return 0.f;
+            const int c = k / 27, t = k % 27, kd = t / 9, kh = (t / 3) % 3, kw = t % 3;
+            if (!(okdh[kd * 3 + kh] && okw[kw])) return 0.f;
+            return __ldg(xb + ((long long)c * plane + (kd - 1) * hw + (kh - 1) * W + (kw - 1)));
+        };
 #pragma unroll
-    for (int i = 0; i < 9; ++i)
-        okdh[i] = vox_ok && (unsigned)(d + i / 3 - 1) < (unsigned)g.D && (unsigned)(h + i % 3 - 1) < (unsigned)g.H;
+        for (int kc = 0; kc < KC; ++kc)
 #pragma unroll
-    for (int i = 0; i < 3; ++i) okw[i] = (unsigned)(w + i - 1) < (unsigned)g.W;
-    const uint32_t row_addr = box + row * 128, sw = row & 7;
-    if (half == 0) {
-        if (kc == 0) im2col_cols<CIN, 0, 0>(xb, plane, hw, g.W, okdh, okw, row_addr, sw);
-        else if (kc == 1) im2col_cols<CIN, 1, 0>(xb, plane, hw, g.W, okdh, okw, row_addr, sw);
-        else im2col_cols<CIN, 2, 0>(xb, plane, hw, g.W, okdh, okw, row_addr, sw);
-    } else {
-        if (kc == 0) im2col_cols<CIN, 0, 1>(xb, plane, hw, g.W, okdh, okw, row_addr, sw);
-        else if (kc == 1) im2col_cols<CIN, 1, 1>(xb, plane, hw, g.W, okdh, okw, row_addr, sw);
-        else im2col_cols<CIN, 2, 1>(xb, plane, hw, g.W, okdh, okw, row_addr, sw);
+            for (int j = 0; j < 16; ++j) {
+                const int k0 = 64 * kc + 32 * HALF + 2 * j;
+                if (k0 < KPAD) wd[kc * 16 + j] = pack_bf16x2(tap(k0), tap(k0 + 1));
+            }
     }
-}
+    // brick row `pt & 127` of the brick at (w0, h0, d0, nb); pt >> 7 (warp-uniform) selects the column half
+    DEV void load(const float* __restrict__ x, int pt, int w0, int h0, int d0, int nb, const BrickGeom& g) {
+        const int row = pt & 127;
+        const int rw = row & ((1 << g.tw_log2) - 1);
+        const int rh = (row >> g.tw_log2) & ((1 << g.th_log2) - 1);
+        const int rd = row >> (g.tw_log2 + g.th_log2);
+        const int w = w0 + rw, h = h0 + rh, d = d0 + rd;
+        const bool vox_ok = w < g.W && h < g.H && d < g.D && nb < g.nbatch;
+        const int hw = g.H * g.W;
+        const long long plane = (long long)g.D * hw;
+        const float* xb = x + ((long long)nb * CIN * plane + ((long long)d * hw + h * g.W + w));
+        bool okdh[9], okw[3];
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+            okdh[i] = vox_ok && (unsigned)(d + i / 3 - 1) < (unsigned)g.D && (unsigned)(h + i % 3 - 1) < (unsigned)g.H;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) okw[i] = (unsigned)(w + i - 1) < (unsigned)g.W;
+        row_off = row * 128;
+        sw = row & 7;
+        if ((pt >> 7) == 0) load_half<0>(xb, plane, hw, g.W, okdh, okw);
+        else load_half<1>(xb, plane, hw, g.W, okdh, okw);
+    }
+    // 64-column block KCI of the row into the SWIZZLE_128B K-major box at `box`
+    template <int KCI>
+    DEV void store(uint32_t box, int pt) const {
+        const uint32_t half = pt >> 7;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const bool in0 = 64 * KCI + 8 * q < KPAD, in1 = 64 * KCI + 32 + 8 * q < KPAD;
+            if (half == 0 ? in0 : in1)
+                st_shared_v4(box + row_off + (((half * 4 + q) ^ sw) << 4), wd[KCI * 16 + 4 * q],
+                             wd[KCI * 16 + 4 * q + 1], wd[KCI * 16 + 4 * q + 2], wd[KCI * 16 + 4 * q + 3]);
+        }
+    }
+};
 
 // ------------------------------------------------------------------------------------------------
 // igemm_kernel
@@ -114,7 +130,8 @@ DEV void igemm_body(const IgemmParams& p) {
     const uint32_t smem_a = smem_base;
     const uint32_t smem_b = smem_a + nst * a_bytes;
     const uint32_t smem_c = smem_b + nst * b_bytes;    // epilogue v2 staging: (block_n / 64) boxes of 128 rows x 128 B
-    const uint32_t c_bytes = p.epi_v2 ? ((p.block_n + 63) >> 6) * kBoxBytes : 0;
+    const uint32_t c_one = p.epi_v2 ? ((p.block_n + 63) >> 6) * kBoxBytes : 0;   // one staging tile
+    const uint32_t c_bytes = c_one * (p.c_bufs > 1 ? 2u : 1u);
     const uint32_t bar_base = smem_c + c_bytes;        // 8-byte aligned (multiple of 1024)
     // barrier layout: full[nst], empty[nst], tmem_full[2], tmem_empty[2]
     auto full_bar = [&](uint32_t s) { return bar_base + 8 * s; };
@@ -298,22 +315,36 @@ DEV void igemm_body(const IgemmParams& p) {
         // visible to the tensor core's (async-proxy) reads
         PipeState ps;
         const int pt = threadIdx.x - 256;
-        const int kc_blocks = p.kc_blocks, n_tiles = p.n_tiles;
+        const int n_tiles = p.n_tiles;
         const BrickGeom geom{p.tw_log2, p.th_log2, p.W, p.H, p.D, p.nbatch};
+        using Row = Im2colRow<kIm2colC ? kIm2colC : 1>;
+        auto publish = [&]() {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_bar(ps.stage));
+            ps.advance(nst);
+        };
         for (int tile = unit0; tile < total_tiles; tile += unit_stride) {
             int mt = tile / n_tiles;
             const int bw = mt % p.nbw; mt /= p.nbw;
             const int bh = mt % p.nbh; mt /= p.nbh;
             const int bd = mt % p.nbd; mt /= p.nbd;
             const int nb = mt;
-            const int w0 = bw << p.tw_log2, h0 = bh << p.th_log2, d0 = bd << p.td_log2;
-            for (int kc = 0; kc < kc_blocks; ++kc) {
+            Row r;
+            r.load(p.x_src, pt, bw << p.tw_log2, bh << p.th_log2, bd << p.td_log2, nb, geom);
+            // one pipeline stage per 64-column block (p.kc_blocks == Row::KC)
+            mbar_wait(empty_bar(ps.stage), ps.phase ^ 1);
+            r.template store<0>(smem_a + ps.stage * a_bytes, pt);
+            publish();
+            if (Row::KC > 1) {
                 mbar_wait(empty_bar(ps.stage), ps.phase ^ 1);
-                im2col_stage<kIm2colC ? kIm2colC : 1>(p.x_src, smem_a + ps.stage * a_bytes, kc, pt, w0, h0, d0, nb, geom);
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(full_bar(ps.stage));
-                ps.advance(nst);
+                r.template store<(Row::KC > 1 ? 1 : 0)>(smem_a + ps.stage * a_bytes, pt);
+                publish();
+            }
+            if (Row::KC > 2) {
+                mbar_wait(empty_bar(ps.stage), ps.phase ^ 1);
+                r.template store<(Row::KC > 2 ? 2 : 0)>(smem_a + ps.stage * a_bytes, pt);
+                publish();
             }
         }
     } else if (warp >= 4 && warp < 8) {
@@ -336,8 +367,8 @@ DEV void igemm_body(const IgemmParams& p) {
             // read back from the staged tile (conflict-free word reads) instead of 30 shuffles per 16 columns.
             const int nbox = (p.block_n + 63) >> 6, nslab = p.block_n >> 5;
             const int mode = p.mode;
-            const uint32_t row_smem = smem_c + row * 128;
             const uint32_t sw = row & 7;
+            const bool two_bufs = p.c_bufs > 1;
             for (int tile = unit0; tile < total_tiles; tile += unit_stride, ++iter) {
                 const uint32_t acc = iter & 1, acc_phase = (iter >> 1) & 1;
                 const int m_unit = tile / p.n_tiles;
@@ -357,7 +388,13 @@ DEV void igemm_body(const IgemmParams& p) {
                         if (mode == EPI_AFFINE_RELU) colvec[256 + c] = ok ? __ldg(p.vec1 + n0 + c) : 0.f;
                     }
                 }
-                if (et == 0) bulk_wait_read0();  // the previous tile's TMA store has finished reading the staging tile
+                // the staging tile about to be written is free: the TMA store that last read it (of the previous tile,
+                // or with two tiles of the one before) has finished reading
+                const uint32_t cbuf = smem_c + ((two_bufs && (iter & 1)) ? c_one : 0u);
+                const uint32_t row_smem = cbuf + row * 128;
+                if (et == 0) {
+                    if (two_bufs) bulk_wait_read1(); else bulk_wait_read0();
+                }
                 named_bar_sync(1, 128);
                 mbar_wait(tfull_bar(acc), acc_phase);
                 tc_fence_after();
@@ -397,7 +434,7 @@ DEV void igemm_body(const IgemmParams& p) {
                         const int col0 = n0 + b * 64;
                         if (col0 < p.ncols) {
                             const int g = col0 / p.cols_per_group;
-                            tma_store_5d(&p.c_map[g], smem_c + b * kBoxBytes, col0 - g * p.cols_per_group, w0, h0, d0,
+                            tma_store_5d(&p.c_map[g], cbuf + b * kBoxBytes, col0 - g * p.cols_per_group, w0, h0, d0,
                                          nb);
                         }
                     }
@@ -407,7 +444,7 @@ DEV void igemm_body(const IgemmParams& p) {
                     // warp q sums rows 32q..32q+31 of column pair `lane` of every box
                     for (int b = 0; b < nbox; ++b) {
                         float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-                        const uint32_t base = smem_c + b * kBoxBytes + (q * 32) * 128 + (lane & 3) * 4;
+                        const uint32_t base = cbuf + b * kBoxBytes + (q * 32) * 128 + (lane & 3) * 4;
 #pragma unroll 8
                         for (int r = 0; r < 32; ++r) {
                             const uint32_t wv = ld_shared_b32(base + r * 128 + ((((uint32_t)lane >> 2) ^ (r & 7)) << 4));
@@ -587,7 +624,9 @@ DEV void wgrad_body(const WgradParams& p) {
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
 
-    constexpr uint32_t kPSlot = 2 * kBoxBytes, kQSlot = 4 * kBoxBytes, kNP = 2, kNQ = 2;
+    // (first-layer form: three column blocks per slot and shallower P slots leave ~70 KB of the SM to L1, which the
+    //  27-fold re-read of the fp32 input by the Q builders lives on)
+    constexpr uint32_t kPSlot = 2 * kBoxBytes, kQSlot = (kIm2colC ? 3 : 4) * kBoxBytes, kNP = 2, kNQ = 2;
     const uint32_t smem_p = smem_base;
     const uint32_t smem_q = smem_p + kNP * kPSlot;
     const uint32_t bar_base = smem_q + kNQ * kQSlot;
@@ -705,23 +744,25 @@ DEV void wgrad_body(const WgradParams& p) {
         PipeState qp;
         const int pt = threadIdx.x - 256;
         const BrickGeom geom{p.tw_log2, p.th_log2, p.W, p.H, p.D, p.nbatch};
+        using Row = Im2colRow<kIm2colC ? kIm2colC : 1>;
         for (int b = split; b < nbricks; b += p.splits) {
             int mt = b;
             const int bw = mt % p.nbw; mt /= p.nbw;
             const int bh = mt % p.nbh; mt /= p.nbh;
             const int bd = mt % p.nbd; mt /= p.nbd;
             const int nb = mt;
-            for (int sg = 0; sg < nsg; ++sg) {   // one slot group for the first layer (3 column blocks)
-                const int nb4 = min(4, ncb - sg * 4);
-                mbar_wait(qempty(qp.stage), qp.phase ^ 1);
-                for (int i = 0; i < nb4; ++i)
-                    im2col_stage<kIm2colC ? kIm2colC : 1>(p.x_src, smem_q + qp.stage * kQSlot + i * kBoxBytes,
-                                                          cb0 + sg * 4 + i, pt, bw * p.tw, bh * p.th, bd * p.td, nb, geom);
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(qfull(qp.stage));
-                qp.advance(kNQ);
-            }
+            Row r;
+            r.load(p.x_src, pt, bw * p.tw, bh * p.th, bd * p.td, nb, geom);
+            // the whole padded row (Row::KC column blocks = the CTA's one slot group) goes into one Q slot
+            mbar_wait(qempty(qp.stage), qp.phase ^ 1);
+            const uint32_t slot = smem_q + qp.stage * kQSlot;
+            r.template store<0>(slot, pt);
+            if (Row::KC > 1) r.template store<(Row::KC > 1 ? 1 : 0)>(slot + kBoxBytes, pt);
+            if (Row::KC > 2) r.template store<(Row::KC > 2 ? 2 : 0)>(slot + 2 * kBoxBytes, pt);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(qfull(qp.stage));
+            qp.advance(kNQ);
         }
     } else if (warp >= 4 && warp < 8) {
         // ===================================================================== epilogue

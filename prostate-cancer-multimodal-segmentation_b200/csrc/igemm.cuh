@@ -42,6 +42,7 @@ struct alignas(64) IgemmParams {
     CUtensorMap b_map;
     CUtensorMap c_map[kMaxMaps];  // epilogue v2: TMA store maps of the output (one per output offset group)
     int epi_v2;         // 1: stage the bf16 tile in shared memory, TMA store, statistics from the staged tile
+    int c_bufs;         // staging tiles (epilogue v2): 2 = tile i+1 is staged while the TMA store of tile i still reads
     int pair;           // 1: launched as clusters of two CTAs; M = 256 tcgen05.mma.cta_group::2, B tile split between them
     int ablate;         // development library only (B200_ABLATE): 1 = barriers armed without TMA loads, 2 = no MMAs issued
     int ntaps;

@@ -92,9 +92,15 @@ DEV void tma_store_5d(const void* desc, uint32_t smem_src, int c0, int c1, int c
 }
 DEV void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 DEV void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+DEV void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 DEV void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 DEV void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+DEV float ld_shared_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
 }
 DEV uint32_t ld_shared_b32(uint32_t addr) {
     uint32_t v;

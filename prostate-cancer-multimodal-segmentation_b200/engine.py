@@ -61,7 +61,7 @@ class _ConvPack:
         self.im2col = self.cin % 16 != 0 and 27 * self.cin <= 512
         # the 5-modality first layer reads the fp32 network input directly: its im2col rows are built in shared
         # memory inside the GEMM kernels (ops.conv1_direct_*), never in HBM
-        self.direct = self.im2col and ops.conv1_direct_supported(self.cin, self.cout)
+        self.direct = self.im2col and ops.conv1_direct_supported(self.cin, self.cout, 4)
         self.shadow = None   # set by the engine: bf16 [27][Cout][Cin] view of its parameter shadow
         self._own = None
         if self.im2col:
@@ -92,7 +92,7 @@ class _ConvPack:
     def make_input(self, x: torch.Tensor):
         """fp32 (N,C,D,H,W) -> the operand this conv reads: channel-padded NDHWC bf16, im2col rows, or (direct first
         layer) the fp32 tensor itself"""
-        if self.direct:
+        if self.direct and ops.conv1_direct_supported(self.cin, self.cout, x.shape[-1]):
             return RawInput(x)
         n, _, d, h, w = x.shape
         v = ActView(new_act(n, d, h, w, self.cin_pad, x.device))
@@ -100,14 +100,14 @@ class _ConvPack:
         return v
 
     def fprop(self, xin, bias, y, stats, mode, scale=None, shift=None):
-        if self.direct:
+        if isinstance(xin, RawInput):
             ops.conv1_direct_fprop(xin.t, self.wf, bias, y, stats, mode, scale, shift)
             return
         f = ops.conv1_fprop if self.im2col else ops.conv3d_fprop
         f(xin, self.wf, bias, y, stats, mode, scale, shift, k_real=self.k_real)
 
     def wgrad(self, xin, dy, dw):
-        if self.direct:
+        if isinstance(xin, RawInput):
             ops.conv1_direct_wgrad(xin.t, dy, dw.view(self.cout, -1))
         elif self.im2col:
             ops.conv1_wgrad(xin, dy, dw.view(self.cout, -1), self.k_real)
@@ -176,7 +176,8 @@ class _DoubleConv:
             raise ValueError(f"Expected more than 1 value per channel when training, got input size "
                              f"{(n, cout, d, h, w)}")
         y = ActView(new_act(n, d, h, w, cout, dev))
-        rows = ops.conv3d_stat_rows(n, d, h, w, cout, 1 if pack.im2col else 27)
+        rows = (ops.conv1_direct_stat_rows(n, d, h, w, cout) if isinstance(xin, RawInput)
+                else ops.conv3d_stat_rows(n, d, h, w, cout, 1 if pack.im2col else 27))
         stats = torch.empty(rows, cout, 2, device=dev, dtype=torch.float32)
         pack.fprop(xin, pack.conv.bias.data, y, stats, ops.EPI_BIAS_STATS)
         vec = torch.empty(4, cout, device=dev, dtype=torch.float32)  # mean, rstd, scale, shift

@@ -120,8 +120,15 @@ def conv1_wgrad(x: ActView, dy: ActView, dw: torch.Tensor, k_real: int):
           lambda: check(lib.b200_conv1_wgrad(x.ref, dy.ref, ptr(dw), k_real, stream_ptr()), "conv1_wgrad"))
 
 
-def conv1_direct_supported(cin: int, cout: int) -> bool:
-    return bool(_lib.load().b200_conv1_direct_supported(cin, cout))
+def conv1_direct_supported(cin: int, cout: int, w: int = 4) -> bool:
+    return bool(_lib.load().b200_conv1_direct_supported(cin, cout, w))
+
+
+def conv1_direct_stat_rows(n, d, h, w, cout) -> int:
+    r = _lib.load().b200_conv1_direct_stat_rows(n, d, h, w, cout)
+    if r <= 0:
+        raise _lib.B200Error("b200_conv1_direct_stat_rows failed (no CUDA device?)")
+    return r
 
 
 def conv1_direct_fprop(x: torch.Tensor, w_rows, bias, y: ActView, stats=None, mode=EPI_BIAS_STATS, scale=None,

@@ -387,7 +387,7 @@ def test_bad_arguments_raise(ops, pkg, cuda_dev):
 
 # ------------------------------------------------------------------------------------------------ first layer, direct
 # (N, D, H, W) with full and partial bricks in every axis, a volume smaller than a brick, two samples
-FIRST_LAYER_CASES = [(1, 16, 16, 16), (2, 5, 9, 140), (1, 3, 7, 6), (2, 20, 36, 18), (1, 2, 2, 128)]
+FIRST_LAYER_CASES = [(1, 16, 16, 16), (2, 5, 9, 140), (1, 3, 7, 6), (2, 20, 36, 18), (1, 2, 2, 128), (1, 33, 2, 4)]
 
 
 @pytest.mark.parametrize("shape", FIRST_LAYER_CASES)
@@ -397,7 +397,7 @@ def test_first_layer_direct_fprop_and_wgrad(ops, cuda_dev, shape, cout):
     built in shared memory inside the GEMM kernels — against F.conv3d / torch's weight gradient on the bf16-rounded
     operands, and bit-for-bit against the materialised-im2col path it replaces (same MMAs, same operand bytes)."""
     n, d, h, w = shape
-    assert ops.conv1_direct_supported(5, cout) and not ops.conv1_direct_supported(4, cout)
+    assert ops.conv1_direct_supported(5, cout, w) and not ops.conv1_direct_supported(4, cout, w)
     g = torch.Generator().manual_seed(11)
     x = torch.randn(n, 5, d, h, w, generator=g).to(cuda_dev)
     wt = bf16_round(torch.randn(cout, 5, 3, 3, 3, generator=g) * (2.0 / 135) ** 0.5).to(cuda_dev)
@@ -405,7 +405,7 @@ def test_first_layer_direct_fprop_and_wgrad(ops, cuda_dev, shape, cout):
     w_rows = torch.empty(cout, 144, device=cuda_dev, dtype=torch.bfloat16)
     ops.pack_rows(wt.contiguous(), 144, w_rows)
     yv = empty_act(ops, n, cout, d, h, w, cuda_dev)
-    rows = ops.conv3d_stat_rows(n, d, h, w, cout, 1)
+    rows = ops.conv1_direct_stat_rows(n, d, h, w, cout)
     stats = torch.full((rows, cout, 2), float("nan"), device=cuda_dev)
     ops.conv1_direct_fprop(x, w_rows, b, yv, stats, ops.EPI_BIAS_STATS)
     torch.cuda.synchronize()
@@ -420,7 +420,7 @@ def test_first_layer_direct_fprop_and_wgrad(ops, cuda_dev, shape, cout):
     rows_v = empty_act(ops, n, 144, d, h, w, cuda_dev, poison=False)
     ops.im2col_input(x, rows_v)
     y2 = empty_act(ops, n, cout, d, h, w, cuda_dev)
-    stats2 = torch.empty_like(stats)
+    stats2 = torch.empty(ops.conv3d_stat_rows(n, d, h, w, cout, 1), cout, 2, device=cuda_dev)
     ops.conv1_fprop(rows_v, w_rows, b, y2, stats2, ops.EPI_BIAS_STATS, k_real=135)
     torch.cuda.synchronize()
     assert torch.equal(from_act(y2), got)
