@@ -14,7 +14,8 @@ EPI_PLAIN, EPI_BIAS_STATS, EPI_AFFINE_RELU, EPI_BIAS = 0, 1, 2, 3
 
 # ---- instrumentation (bench.py): kernel launch counter and an optional per-launch timing hook for the GEMM kernels
 launch_count = 0
-profile_hook = None  # callable(kernel_name, tag, algorithmic_flops, start_event, end_event)
+profile_hook = None  # callable(kernel_name, tag, algorithmic_flops, start_event, end_event, shape)
+#                      shape = (voxels, in channels, out channels) of the GEMM: identifies the layer
 
 
 def _launched(n: int = 1):
@@ -22,7 +23,7 @@ def _launched(n: int = 1):
     launch_count += n
 
 
-def _gemm(kernel, tag, flops, call):
+def _gemm(kernel, tag, flops, call, shape=None):
     _launched(1)
     if profile_hook is None:
         return call()
@@ -30,7 +31,7 @@ def _gemm(kernel, tag, flops, call):
     e0.record()
     call()
     e1.record()
-    profile_hook(kernel, tag, flops, e0, e1)
+    profile_hook(kernel, tag, flops, e0, e1, shape)
 
 
 class ActView:
@@ -111,13 +112,15 @@ def conv1_fprop(x: ActView, w_rows, bias, y: ActView, stats=None, mode=EPI_BIAS_
     lib = _lib.load()
     _gemm("igemm_kernel", "conv1_fprop", 2.0 * x.voxels * y.c * (k_real or x.c),
           lambda: check(lib.b200_conv1_fprop(x.ref, ptr(w_rows), ptr(bias), y.ref, ptr(stats), mode, ptr(scale),
-                                             ptr(shift), stream_ptr()), "conv1_fprop"))
+                                             ptr(shift), stream_ptr()), "conv1_fprop"),
+          shape=(x.voxels, (k_real or x.c) // 27, y.c))
 
 
 def conv1_wgrad(x: ActView, dy: ActView, dw: torch.Tensor, k_real: int):
     lib = _lib.load()
     _gemm("wgrad_kernel", "conv1_wgrad", 2.0 * x.voxels * dy.c * k_real,
-          lambda: check(lib.b200_conv1_wgrad(x.ref, dy.ref, ptr(dw), k_real, stream_ptr()), "conv1_wgrad"))
+          lambda: check(lib.b200_conv1_wgrad(x.ref, dy.ref, ptr(dw), k_real, stream_ptr()), "conv1_wgrad"),
+          shape=(x.voxels, k_real // 27, dy.c))
 
 
 def conv1_direct_supported(cin: int, cout: int, w: int = 4) -> bool:
@@ -139,7 +142,8 @@ def conv1_direct_fprop(x: torch.Tensor, w_rows, bias, y: ActView, stats=None, mo
     assert x.dtype == torch.float32 and x.is_contiguous()
     _gemm("igemm_im2col5_kernel", "conv1_fprop", 2.0 * y.voxels * y.c * 27 * c,
           lambda: check(lib.b200_conv1_direct_fprop(ptr(x), n, c, d, h, w, ptr(w_rows), ptr(bias), y.ref, ptr(stats),
-                                                    mode, ptr(scale), ptr(shift), stream_ptr()), "conv1_direct_fprop"))
+                                                    mode, ptr(scale), ptr(shift), stream_ptr()), "conv1_direct_fprop"),
+          shape=(y.voxels, c, y.c))
 
 
 def conv1_direct_wgrad(x: torch.Tensor, dy: ActView, dw: torch.Tensor):
@@ -148,7 +152,7 @@ def conv1_direct_wgrad(x: torch.Tensor, dy: ActView, dw: torch.Tensor):
     assert x.dtype == torch.float32 and x.is_contiguous()
     _gemm("wgrad_im2col5_kernel", "conv1_wgrad", 2.0 * dy.voxels * dy.c * 27 * c,
           lambda: check(lib.b200_conv1_direct_wgrad(ptr(x), n, c, d, h, w, dy.ref, ptr(dw), stream_ptr()),
-                        "conv1_direct_wgrad"))
+                        "conv1_direct_wgrad"), shape=(dy.voxels, c, dy.c))
 
 
 def pack_conv_weight(w: torch.Tensor, cin_pad: int, w_packed):
@@ -188,13 +192,15 @@ def conv3d_fprop(x: ActView, w_fprop, bias, y: ActView, stats=None, mode=EPI_BIA
     lib = _lib.load()
     _gemm(_conv_kernel(lib, x, y.c), "conv3d_fprop", 2.0 * x.voxels * y.c * (k_real or x.c) * 27,
           lambda: check(lib.b200_conv3d_fprop(x.ref, ptr(w_fprop), ptr(bias), y.ref, ptr(stats), mode, ptr(scale),
-                                              ptr(shift), stream_ptr()), "conv3d_fprop"))
+                                              ptr(shift), stream_ptr()), "conv3d_fprop"),
+          shape=(x.voxels, k_real or x.c, y.c))
 
 
 def conv3d_dgrad(dy: ActView, w_packed, dx: ActView):
     lib = _lib.load()
     _gemm(_conv_kernel(lib, dy, dx.c), "conv3d_dgrad", 2.0 * dy.voxels * dy.c * dx.c * 27,
-          lambda: check(lib.b200_conv3d_dgrad(dy.ref, ptr(w_packed), dx.ref, stream_ptr()), "conv3d_dgrad"))
+          lambda: check(lib.b200_conv3d_dgrad(dy.ref, ptr(w_packed), dx.ref, stream_ptr()), "conv3d_dgrad"),
+          shape=(dy.voxels, dx.c, dy.c))
 
 
 def conv3d_wgrad(x: ActView, dy: ActView, dw: torch.Tensor, cin_real: int, packed: bool = False):
@@ -203,28 +209,28 @@ def conv3d_wgrad(x: ActView, dy: ActView, dw: torch.Tensor, cin_real: int, packe
     kern = "wgrad_halo_kernel" if profile_hook and lib.b200_conv3d_wgrad_kernel_id(x.shape[2], x.shape[3]) else "wgrad_kernel"
     _gemm(kern, "conv3d_wgrad", 2.0 * x.voxels * dy.c * cin_real * 27,
           lambda: check(lib.b200_conv3d_wgrad(x.ref, dy.ref, ptr(dw), cin_real, 1 if packed else 0, stream_ptr()),
-                        "conv3d_wgrad"))
+                        "conv3d_wgrad"), shape=(x.voxels, cin_real, dy.c))
 
 
 def convt2x_fwd(x: ActView, w_fwd, bias8, y: ActView, pads=(0, 0, 0)):
     lib = _lib.load()
     _gemm("igemm_kernel", "convt2x_fwd", 2.0 * x.voxels * x.c * y.c * 8,
           lambda: check(lib.b200_convt2x_fwd(x.ref, ptr(w_fwd), ptr(bias8), y.ref, pads[0], pads[1], pads[2],
-                                             stream_ptr()), "convt2x_fwd"))
+                                             stream_ptr()), "convt2x_fwd"), shape=(x.voxels, x.c, y.c))
 
 
 def convt2x_dgrad(dy: ActView, pads, w_dgrad, dx: ActView):
     lib = _lib.load()
     _gemm("igemm_kernel", "convt2x_dgrad", 2.0 * dx.voxels * dx.c * dy.c * 8,
           lambda: check(lib.b200_convt2x_dgrad(dy.ref, pads[0], pads[1], pads[2], ptr(w_dgrad), dx.ref,
-                                               stream_ptr()), "convt2x_dgrad"))
+                                               stream_ptr()), "convt2x_dgrad"), shape=(dx.voxels, dx.c, dy.c))
 
 
 def convt2x_wgrad(x: ActView, dy: ActView, pads, dw: torch.Tensor):
     lib = _lib.load()
     _gemm("wgrad_kernel", "convt2x_wgrad", 2.0 * x.voxels * x.c * dy.c * 8,
           lambda: check(lib.b200_convt2x_wgrad(x.ref, dy.ref, pads[0], pads[1], pads[2], ptr(dw), stream_ptr()),
-                        "convt2x_wgrad"))
+                        "convt2x_wgrad"), shape=(x.voxels, x.c, dy.c))
 
 
 def bn_finalize(stats, rows, count, c, gamma, beta, eps, momentum, running_mean, running_var, mean, rstd, scale,
