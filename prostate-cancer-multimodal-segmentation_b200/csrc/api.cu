@@ -196,7 +196,14 @@ static int sm_count();
 static int igemm_block_n(long long ncols, long long m_tiles) {
     if (ncols < 256) return (int)((ncols + 15) / 16 * 16);
     const int sms = sm_count();
-    if (sms > 0 && ncols % 128 == 0 && m_tiles * ((ncols + 255) / 256) * 2 <= sms) return 128;
+    // The deep levels (8^3: 8 M tiles) are bound by what ONE SM can pull from L2 (~100 B/clk: every k-block is a 16 KB
+    // A box + a B tile), not by the tensor pipe: more, narrower tiles spread that stream over more SMs.  256 columns
+    // where that still fills the machine, else 128, else 64 (a 64-column MMA runs at 60 % of the pipe, but twice the
+    // SMs pull operands).
+    if (sms > 0 && ncols % 128 == 0 && m_tiles * ((ncols + 255) / 256) * 2 <= sms) {
+        if (ncols % 64 == 0 && m_tiles * (ncols / 128) * 2 <= sms + sms / 4) return 64;
+        return 128;
+    }
     return 256;
 }
 // dynamic shared memory of igemm_kernel: 1 KB alignment slack + stages + epilogue-v2 staging + barriers, TMEM pointer,
