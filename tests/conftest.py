@@ -13,6 +13,7 @@ PKG_NAME = "prostate-cancer-multimodal-segmentation_b200"
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
+    config.addinivalue_line("markers", "multigpu: needs two or more CUDA devices in one process; run with -m multigpu")
 
 
 def load_pkg():

@@ -162,3 +162,71 @@ def test_physical_weight_layout_views(pkg):
     torch.save({"w": view}, buf)
     buf.seek(0)
     assert torch.equal(torch.load(buf)["w"], w)
+
+
+def test_sharded_loader_and_window_ownership(pkg):
+    par = pkg.parallel
+    batch = {"image": torch.arange(5).view(5, 1).float(), "label": torch.zeros(5, 1), "case_id": list("abcde"),
+             "meta": "kept"}
+    parts = [par.shard_dict_batch(batch, r, 2) for r in range(2)]
+    assert parts[0]["case_id"] == ["a", "b", "c"] and parts[1]["case_id"] == ["d", "e"]
+    assert torch.equal(torch.cat([p["image"] for p in parts]), batch["image"]) and parts[0]["meta"] == "kept"
+    assert par.shard_dict_batch(batch, 0, 1) is batch
+    assert par.shard_dict_batch({"image": torch.zeros(1, 1), "label": torch.zeros(1, 1)}, 0, 2) is None  # fewer samples than ranks
+    loader = [batch, {"image": torch.zeros(1, 1), "label": torch.zeros(1, 1), "case_id": ["z"]}]
+    assert [len(b["case_id"]) for b in par.ShardedLoader(loader, 1, 2)] == [2]   # the short batch is skipped on every rank
+    # data-parallel ranks iterate identical global batches: the shuffle order comes from a seeded generator
+    a = [b["case_id"] for b in pkg.data.get_dataloader(batch_size=2, target_size=(8, 8, 8), n_cases=6)]
+    b = [b["case_id"] for b in pkg.data.get_dataloader(batch_size=2, target_size=(8, 8, 8), n_cases=6)]
+    assert a == b
+    # window cover = per-axis counts whose product is the number of windows over a voxel
+    shape, window, stride = (2, 5, 48, 40, 32), (32, 32, 32), (16, 16, 16)
+    cov = par.window_cover(shape, window, stride)
+    sched, win = par.window_schedule(shape, window, stride)
+    cnt = torch.zeros(48, 40, 32)
+    for v, d0, h0, w0 in sched:
+        if v == 0:
+            cnt[d0:d0 + win[0], h0:h0 + win[1], w0:w0 + win[2]] += 1
+    prod = cov[:48].view(-1, 1, 1) * cov[48:88].view(1, -1, 1) * cov[88:].view(1, 1, -1)
+    assert torch.equal(prod.float(), cnt)
+    # BASELINE configs[3]: 8 volumes on 8 ranks -> one whole volume per rank, nothing to exchange
+    own = par.volume_owners((8, 5, 256, 256, 64), (128, 128, 64), (64, 64, 64), 8)
+    assert own == {v: (v, [v]) for v in range(8)}
+    assert par.owned_volumes((8, 5, 256, 256, 64), (128, 128, 64), (64, 64, 64), 3, 8) == [3]
+    # a single volume on 2 ranks is split and owned by rank 0
+    assert par.volume_owners((1, 5, 256, 256, 64), (128, 128, 64), (64, 64, 64), 2) == {0: (0, [0, 1])}
+    assert par.dist_info() == (0, 1) and par.all_mean(2.5, "cpu") == 2.5
+
+
+def test_load_multimodal_images_case_directory(pkg, tmp_path):
+    """script/predict.py:8-82 on a case directory of .npy volumes: order, min-max, zero_fill / duplicate / skip"""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    vols = {}
+    for m in pkg.predict.PREDICT_MODALITIES:
+        os.makedirs(tmp_path / m)
+        if m != "T2 fs":
+            vols[m] = (rng.normal(size=(4, 5, 6)) * 3 + 1).astype(np.float32)
+            np.save(tmp_path / m / "vol.npy", vols[m])
+    img, names = pkg.load_multimodal_images(str(tmp_path))
+    assert names == ["ADC", "DWI", "gaoqing-T2", "T2 fs", "T2 not fs"] and img.shape == (5, 4, 5, 6)
+    assert img.dtype == np.float32 and img[3].max() == 0.0
+    for i, m in enumerate(names):
+        if m in vols:
+            v = vols[m]
+            assert np.allclose(img[i], oracle.minmax_normalize(v[None])[0], atol=1e-6)
+    dup, _ = pkg.load_multimodal_images(str(tmp_path), "duplicate")
+    assert np.array_equal(dup[3], dup[0])
+    with pytest.raises(FileNotFoundError):
+        pkg.load_multimodal_images(str(tmp_path), "skip")
+    os.rmdir(tmp_path / "T2 fs")
+    with pytest.raises(FileNotFoundError):
+        pkg.load_multimodal_images(str(tmp_path))
+
+
+def test_build_is_content_addressed(pkg):
+    from importlib import import_module
+    b = import_module(pkg.__name__ + ".build")
+    assert not b.is_stale() and b.build() == b.LIB_PATH          # built by the fixture's load; a no-op now
+    assert open(b.LIB_PATH + ".hash").read().strip() == b.source_hash()
+    assert b.source_hash() != b.source_hash(dev=True)
