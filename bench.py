@@ -687,13 +687,14 @@ def main():
             arms = {}
             for base in (32, 64):
                 arms[base] = train_arm(args, pkg, par, ctx, B, size, base, "dice", True,
-                                       want_profile=(base == 64 and not args.no_profile_pass), want_library=False)
+                                       want_profile=not args.no_profile_pass, want_library=False)
             r = arms[64]
             workload = (f"UNet3D zero_fill training step (fwd + DiceLoss + bwd + Adam) at 5x{size[0]}x{size[1]}x{size[2]}, "
                         f"batch {B}/GPU, base channels 32 and 64 back to back (BASELINE configs[4]); value = base 64")
             extra = {"cv": {f"base{b}": {"voxels_per_s": a["value"], "ms_per_step": a["ms_step"],
                                          "e2e_voxels_per_s": a["e2e"]["value"],
-                                         "model_tflops": round(a["value"] * eng_mod.total_flops_per_voxel(b, 5, 1)[1] / 1e12, 1)}
+                                         "model_tflops": round(a["value"] * eng_mod.total_flops_per_voxel(b, 5, 1)[1] / 1e12, 1),
+                                         "kernels": (a.get("roofline") or {}).get("kernels")}
                             for b, a in arms.items()}}
             base = 64
         else:

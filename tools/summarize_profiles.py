@@ -14,8 +14,8 @@ tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 os.makedirs(P, exist_ok=True)
 
-for name in ("bench.json", "bench_reference_arm.json", "bench_infer.json", "gemm_launches.txt", "timeline_events.txt",
-             "launches.csv"):
+for name in ("bench.json", "bench_reference_arm.json", "bench_infer.json", "bench_cv.json", "gemm_launches.txt",
+             "timeline_events.txt", "launches.csv"):
     src = os.path.join(G, f"{tag}_{name}")
     if os.path.exists(src):
         shutil.copy(src, os.path.join(P, f"{tag}_{name}"))
@@ -54,13 +54,16 @@ if os.path.exists(src):
 # ---- full captures -> key metrics
 WANT = ["gpu__time_duration.sum", "launch__grid_size", "sm__cycles_elapsed.max", "sm__cycles_active.avg",
         "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
-        "sm__inst_executed_pipe_tensor.sum", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_tensor.sum", "sm__inst_executed_pipe_uniform.sum",
+        "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
         "l1tex__m_xbar2l1tex_read_bytes.sum", "lts__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
         "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread",
         "launch__shared_mem_per_block_dynamic", "smsp__inst_executed.sum"]
 traffic = {}
-for name in ("igemm_pair", "dmarch_pair", "wgrad_halo", "igemm", "dmarch"):
+for name in ("igemm_pair", "dmarch_pair", "wgrad_halo", "igemm", "dmarch", "igemm_im2col5", "wgrad_im2col5"):
     rep = os.path.join(G, f"{tag}_prof_{name}.ncu-rep")
     if not os.path.exists(rep):
         continue
