@@ -289,9 +289,10 @@ DEV void dmarch_body(const DmarchParams& p) {
             for (int i = et; i < 128; i += 128) colacc[i] = 0.f;
         }
         if (mode != EPI_PLAIN) {
-            if (et < 64) {
-                colvec[et] = __ldg(p.vec0 + et);
-                if (mode == EPI_AFFINE_RELU) colvec[64 + et] = __ldg(p.vec1 + et);
+            if (et < 64) {   // columns past ncols (32-column layers run as 64 with zero weights) get neutral values
+                const bool ok = et < p.ncols;
+                colvec[et] = ok ? __ldg(p.vec0 + et) : 0.f;
+                if (mode == EPI_AFFINE_RELU) colvec[64 + et] = ok ? __ldg(p.vec1 + et) : 0.f;
             }
         }
         named_bar_sync(1, 128);
@@ -367,8 +368,8 @@ DEV void dmarch_body(const DmarchParams& p) {
         if (et == 0) bulk_wait0();
         if (mode == EPI_BIAS_STATS) {
             named_bar_sync(1, 128);
-            float* dst = p.stats + (long long)blockIdx.x * 128;
-            for (int i = et; i < 128; i += 128) dst[i] = colacc[i];
+            float* dst = p.stats + (long long)blockIdx.x * 2 * p.ncols;   // [gridDim.x][ncols][2]
+            for (int i = et; i < 2 * p.ncols; i += 128) dst[i] = colacc[i];
         }
     }
 

@@ -101,12 +101,14 @@ struct alignas(64) DmarchParams {
     int sign;            // +1 fprop, -1 dgrad (tap shifts negated)
     int cin;             // K extent per tap
     int kc_blocks;
+    int ncols;           // valid output columns: 64, or 32 (computed as 64: the weight rows / columns past 32 are
+                         // zero-filled by the TMA unit, the store is clipped by the output map)
     int W, H, D, nbatch, nbw, nbh;
     int seg_len, nseg;   // output slices per work unit, segments per column
     int mode;
     const float* vec0;
     const float* vec1;
-    float* stats;        // [gridDim.x][64][2]
+    float* stats;        // [gridDim.x][ncols][2]
     int ablate;          // development library only (B200_ABLATE): 1 = no TMA loads after arming the barriers (MMAs on stale
                          // shared memory), 2 = no MMAs (loads + epilogue only); results are garbage, timings are not
 };

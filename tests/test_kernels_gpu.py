@@ -45,6 +45,8 @@ CONV_CASES = [
     (1, 64, 64, 128, 11, 16, 24),    # CTA-pair igemm (N = 128, h-halo) with an odd number of M tiles: 33 -> dummy peer
     (1, 128, 128, 256, 33, 16, 8),   # CTA-pair igemm, 256-column tile in h-halo mode (half a B tile per CTA), odd tiles
     (2, 128, 128, 256, 2, 4, 8),     # 256-column tiles, plain bricks, too few tiles for pair mode
+    (1, 32, 32, 32, 6, 16, 24),      # base-32 full-resolution layer: 32 columns run as 64 in the depth-marching kernel (fprop and dgrad, K = 32)
+    (2, 32, 32, 64, 5, 36, 8),       # dgrad into 32 channels from 64 (depth-marching, MN-major B narrower than its box)
 ]
 
 
