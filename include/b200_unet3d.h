@@ -71,15 +71,23 @@ int b200_conv1_wgrad(const b200_act* x, const b200_act* dy, float* dw, int k_rea
 /* ---- 3x3x3 convolution, padding 1 (nn.Conv3d, models/unet3d.py:29,35), tcgen05 implicit GEMM ------------ */
 /* number of 128-voxel output bricks of a volume */
 int64_t b200_conv3d_mtiles(int64_t n, int64_t d, int64_t h, int64_t w);
-/* rows of stats_partial that fprop(BIAS_STATS) writes for this problem (one per persistent CTA), <0 on error;
- * ntaps = 27 for b200_conv3d_fprop, 1 for b200_conv1_fprop */
-int b200_conv3d_stat_rows(int64_t n, int64_t d, int64_t h, int64_t w, int64_t cout, int ntaps);
+/* rows of stats_partial that fprop(BIAS_STATS) writes for this problem (one per persistent CTA, or per block of the
+ * split-K finalize pass when a workspace will be passed), <0 on error; ntaps = 27 for b200_conv3d_fprop, 1 for
+ * b200_conv1_fprop */
+int b200_conv3d_stat_rows(int64_t n, int64_t d, int64_t h, int64_t w, int64_t cout, int ntaps, int with_workspace);
+/* Split-K for the deep levels (a handful of 128-voxel bricks, K = 27 * Cin large): bytes of the caller-owned fp32
+ * workspace [splits][voxels][out_cols] that b200_conv3d_fprop / _dgrad use for this problem, 0 when the problem does
+ * not split.  Scratch only: no initial state needed, nothing kept between calls; the partial tiles are added in a fixed
+ * order (results are run-to-run identical).  Without a workspace (NULL) the same problem runs un-split. */
+int64_t b200_conv3d_workspace_bytes(int64_t n, int64_t d, int64_t h, int64_t w, int64_t out_cols);
 /* mode BIAS_STATS : y = bf16(conv + bias); stats_partial[row][Cout][2] = (sum, sum of squares) of stored y
  * mode AFFINE_RELU: y = relu(conv * scale + shift)   (eval-mode BatchNorm + bias folded)
  * mode BIAS / PLAIN likewise without statistics. */
 int b200_conv3d_fprop(const b200_act* x, const void* w_packed, const float* bias, const b200_act* y,
-                      float* stats_partial, int mode, const float* scale, const float* shift, void* stream);
-int b200_conv3d_dgrad(const b200_act* dy, const void* w_packed, const b200_act* dx, void* stream);
+                      float* stats_partial, int mode, const float* scale, const float* shift, void* workspace,
+                      int64_t workspace_bytes, void* stream);
+int b200_conv3d_dgrad(const b200_act* dy, const void* w_packed, const b200_act* dx, void* workspace,
+                      int64_t workspace_bytes, void* stream);
 /* dw += weight gradient; x->c may exceed cin_real (zero padded channels).
  * packed_layout = 0: dw is torch's (Cout, cin_real, 3,3,3);  1: dw is [27][Cout][cin_real] in the packed tap order
  * of b200_pack_conv_weight (the engine's physical parameter layout: contiguous, coalesced accumulation). */

@@ -40,9 +40,10 @@ SIGNATURES = {
     "b200_pack_conv_weight": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "b200_pack_convt_weight": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "b200_conv3d_mtiles": (_i64, [_i64, _i64, _i64, _i64]),
-    "b200_conv3d_stat_rows": (_i32, [_i64, _i64, _i64, _i64, _i64, _i32]),
-    "b200_conv3d_fprop": (_i32, [_AP, _vp, _vp, _AP, _vp, _i32, _vp, _vp, _vp]),
-    "b200_conv3d_dgrad": (_i32, [_AP, _vp, _AP, _vp]),
+    "b200_conv3d_stat_rows": (_i32, [_i64, _i64, _i64, _i64, _i64, _i32, _i32]),
+    "b200_conv3d_workspace_bytes": (_i64, [_i64, _i64, _i64, _i64, _i64]),
+    "b200_conv3d_fprop": (_i32, [_AP, _vp, _vp, _AP, _vp, _i32, _vp, _vp, _vp, _i64, _vp]),
+    "b200_conv3d_dgrad": (_i32, [_AP, _vp, _AP, _vp, _i64, _vp]),
     "b200_conv3d_wgrad": (_i32, [_AP, _AP, _vp, _i32, _i32, _vp]),
     "b200_convt2x_fwd": (_i32, [_AP, _vp, _vp, _AP, _i32, _i32, _i32, _vp]),
     "b200_convt2x_dgrad": (_i32, [_AP, _i32, _i32, _i32, _vp, _AP, _vp]),
@@ -86,7 +87,7 @@ DEV_SIGNATURES = {
     "b200_dev_set_ablation": (_i32, [_i32, _i32, _i32, _i32]),
 }
 
-ABI_VERSION = 2   # must equal b200_abi_version() of the loaded library
+ABI_VERSION = 3   # must equal b200_abi_version() of the loaded library
 
 _lib = None
 

@@ -46,7 +46,7 @@ static int fail(int code, const char* fmt, ...) {
     } while (0)
 
 extern "C" const char* b200_last_error(void) { return g_err; }
-extern "C" int b200_abi_version(void) { return 2; }
+extern "C" int b200_abi_version(void) { return 3; }
 
 // Development switches: compiled only into the development library (-DB200_DEV).  The product library has no
 // environment lookups and no ablation branches on its launch path.
@@ -336,7 +336,7 @@ static int launch_igemm(IgemmParams& p, cudaStream_t s, int* grid_out) {
     if (p.pair) {
         const int ncl = igemm_max_clusters();
         if (ncl <= 0) return fail(B200_ERR_CUDA, "igemm: no co-resident CTA pair fits on this device");
-        const long long units = ((m_tiles + 1) / 2) * p.n_tiles;
+        const long long units = ((m_tiles + 1) / 2) * p.n_tiles * (p.splits > 1 ? p.splits : 1);
         const int grid = 2 * (int)(units < ncl ? units : ncl);
         if (grid_out) *grid_out = grid;
         igemm_pair_kernel<<<grid, kThreads, smem, s>>>(p);   // compiled with __cluster_dims__(2, 1, 1)
@@ -397,9 +397,38 @@ static void set_out(IgemmParams& p, const b200_act* y) {
     p.out_sn = y->d * y->h * y->w * y->ld;
 }
 
+// Split-K plan of a deep-level 3x3x3 GEMM (a handful of M tiles, K = 27 * Cin large): 256 x 256 CTA-pair tiles (half the
+// operand traffic of 128 x 128 tiles), the 27 taps split so that most clusters work, every split storing its fp32
+// partial tile into its own slice of a workspace [splits][voxels][ncols]; splitk_finalize_kernel adds the slices in
+// split order (deterministic: no atomics, and the workspace needs no initial state).  splits == 0: no split.
+struct SplitPlan {
+    int splits;
+    long long ws_bytes;
+};
+static SplitPlan splitk_plan(long long n, long long w, long long h, long long d, long long ncols, int ntaps) {
+    SplitPlan sp{0, 0};
+    if (ntaps != 27 || ncols < 256 || ncols % 256 != 0) return sp;
+    const Brick b = choose_brick(w, h, d);
+    const long long m_tiles = n * b.nbw * b.nbh * b.nbd;
+    if (m_tiles > 16) return sp;                       // the 8^3 level (and smaller): 8 M tiles at batch 2
+    const int ncl = igemm_max_clusters();
+    if (ncl <= 0) return sp;
+    const long long units = ((m_tiles + 1) / 2) * (ncols / 256);
+    long long splits = ncl / units;
+    if (splits > 9) splits = 9;                        // at least three taps per work unit
+    if (splits < 2) return sp;
+    sp.splits = (int)splits;
+    sp.ws_bytes = splits * n * d * h * w * ncols * 4;
+    return sp;
+}
+extern "C" int64_t b200_conv3d_workspace_bytes(int64_t n, int64_t d, int64_t h, int64_t w, int64_t out_cols) {
+    return splitk_plan(n, w, h, d, out_cols, 27).ws_bytes;
+}
+
 // shared by fprop (sign = +1) and dgrad (sign = -1): 27 taps over one activation map
 static int conv3_igemm(const b200_act* in, const void* w_packed, const b200_act* out, int sign, int mode,
-                       const float* v0, const float* v1, float* stats, cudaStream_t s, int ntaps = 27) {
+                       const float* v0, const float* v1, float* stats, cudaStream_t s, int ntaps = 27,
+                       float* ws = nullptr, long long ws_bytes = 0) {
     int rc = get_encode();
     if (rc) return rc;
     REQUIRE(in->n == out->n && in->d == out->d && in->h == out->h && in->w == out->w, "conv3d: extent mismatch");
@@ -412,9 +441,20 @@ static int conv3_igemm(const b200_act* in, const void* w_packed, const b200_act*
     }
     IgemmParams p;
     memset(&p, 0, sizeof(p));
+    const SplitPlan split = ws ? splitk_plan(in->n, in->w, in->h, in->d, out->c, ntaps) : SplitPlan{0, 0};
+    if (split.splits) {
+        REQUIRE(ws_bytes >= split.ws_bytes, "conv3d: workspace of %lld bytes, the split-K plan needs %lld",
+                ws_bytes, split.ws_bytes);
+        REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "conv3d: workspace not 16-byte aligned");
+    }
     // h-halo mode: worth it when the MMA per tap is short (narrow N) and the volume holds 8 x 16 bricks
     Brick b;
-    const bool halo = conv_geometry(in->n, in->w, in->h, in->d, out->c, ntaps, &b, &p.block_n);
+    bool halo = conv_geometry(in->n, in->w, in->h, in->d, out->c, ntaps, &b, &p.block_n);
+    if (split.splits) {   // plain bricks, 256-column CTA-pair tiles
+        halo = false;
+        b = choose_brick(in->w, in->h, in->d);
+        p.block_n = 256;
+    }
     rc = make_act_map(&p.a_map[0], reinterpret_cast<const __nv_bfloat16*>(in->ptr), in->c, in->w, in->h, in->d, in->n,
                       in->ld, in->w, in->h, in->d, 1, b.tw, halo ? b.th + 2 : b.th, b.td);
     if (rc) return rc;
@@ -423,6 +463,7 @@ static int conv3_igemm(const b200_act* in, const void* w_packed, const b200_act*
     p.b_mn = sign < 0 ? 1 : 0;
     p.pair = (igemm_pair_ok(p.block_n, ntaps, p.b_mn != 0, in->n * b.nbw * b.nbh * b.nbd) &&
               igemm_max_clusters() > 0) ? 1 : 0;
+    if (split.splits) p.pair = 1;
     if (p.b_mn)
         rc = make_weight_map(&p.b_map, w_packed, out->c, in->c, ntaps, 64, halo ? 3 : 1);
     else  // box rows = the B columns one CTA stages (half a tile in pair mode)
@@ -431,7 +472,7 @@ static int conv3_igemm(const b200_act* in, const void* w_packed, const b200_act*
     if (rc) return rc;
     p.ntaps = ntaps;
     // epilogue v2 (staged tile + TMA store): pays off when the MMA time per tile is short, i.e. narrow N
-    p.epi_v2 = (p.block_n <= 64 && p.block_n % 32 == 0) ? 1 : 0;
+    p.epi_v2 = (p.block_n <= 64 && p.block_n % 32 == 0 && !split.splits) ? 1 : 0;
     p.c_bufs = p.epi_v2 ? 2 : 1;   // one-box tiles: a second staging tile takes the store's read latency off the epilogue
     if (p.epi_v2) {
         rc = make_act_map(&p.c_map[0], reinterpret_cast<const __nv_bfloat16*>(out->ptr), out->c, out->w, out->h,
@@ -469,6 +510,18 @@ static int conv3_igemm(const b200_act* in, const void* w_packed, const b200_act*
     set_out(p, out);
     p.out_mul = 1;
     p.cols_per_group = p.ncols;
+    if (split.splits) {
+        p.splits = split.splits;
+        p.ws = ws;
+        p.ws_slice_vox = in->n * in->d * in->h * in->w;
+        p.mode = EPI_SPLITK;
+        rc = launch_igemm(p, s, nullptr);
+        if (rc) return rc;
+        const int fmode = mode == B200_EPI_BIAS_STATS ? 1 : (mode == B200_EPI_AFFINE_RELU ? 2 : 0);
+        REQUIRE(mode != B200_EPI_BIAS, "conv3d: split-K has no plain-bias epilogue");
+        CUDA_TRY(launch_splitk_finalize(ws, split.splits, to_view(out), fmode, v0, v1, stats, s));
+        return 0;
+    }
     return launch_igemm(p, s, nullptr);
 }
 
@@ -534,9 +587,12 @@ static int dmarch_max_clusters() {
     return n;
 }
 
-extern "C" int b200_conv3d_stat_rows(int64_t n, int64_t d, int64_t h, int64_t w, int64_t cout, int ntaps) {
+extern "C" int b200_conv3d_stat_rows(int64_t n, int64_t d, int64_t h, int64_t w, int64_t cout, int ntaps,
+                                     int with_workspace) {
     const int sms = sm_count();
     if (sms <= 0) return -1;
+    if (with_workspace && splitk_plan(n, w, h, d, cout, ntaps).splits)
+        return splitk_finalize_blocks(n * d * h * w, cout);   // the finalize pass writes the partial sums
     {
         const DmPlan pl = dmarch_plan(n, w, h, d, cout, ntaps);
         if (pl.use) return pl.grid;
@@ -555,11 +611,12 @@ extern "C" int b200_conv3d_stat_rows(int64_t n, int64_t d, int64_t h, int64_t w,
 }
 
 static int fprop_impl(const b200_act* x, const void* w_fprop, const float* bias, const b200_act* y,
-                      float* stats_partial, int mode, const float* scale, const float* shift, void* stream, int ntaps);
+                      float* stats_partial, int mode, const float* scale, const float* shift, void* stream, int ntaps,
+                      void* workspace = nullptr, int64_t workspace_bytes = 0);
 extern "C" int b200_conv3d_fprop(const b200_act* x, const void* w_fprop, const float* bias, const b200_act* y,
                                  float* stats_partial, int mode, const float* scale, const float* shift,
-                                 void* stream) {
-    return fprop_impl(x, w_fprop, bias, y, stats_partial, mode, scale, shift, stream, 27);
+                                 void* workspace, int64_t workspace_bytes, void* stream) {
+    return fprop_impl(x, w_fprop, bias, y, stats_partial, mode, scale, shift, stream, 27, workspace, workspace_bytes);
 }
 extern "C" int b200_conv1_fprop(const b200_act* x, const void* w_rows, const float* bias, const b200_act* y,
                                 float* stats_partial, int mode, const float* scale, const float* shift,
@@ -568,7 +625,7 @@ extern "C" int b200_conv1_fprop(const b200_act* x, const void* w_rows, const flo
 }
 static int fprop_impl(const b200_act* x, const void* w_fprop, const float* bias, const b200_act* y,
                       float* stats_partial, int mode, const float* scale, const float* shift, void* stream,
-                      int ntaps) {
+                      int ntaps, void* workspace, int64_t workspace_bytes) {
     CHECK_VIEW(x);
     CHECK_VIEW(y);
     REQUIRE(w_fprop != nullptr, "conv3d_fprop: null weights");
@@ -590,15 +647,18 @@ static int fprop_impl(const b200_act* x, const void* w_fprop, const float* bias,
             break;
         default: return fail(B200_ERR_BAD_ARG, "conv3d_fprop: unknown mode %d", mode);
     }
-    return conv3_igemm(x, w_fprop, y, +1, mode, v0, v1, stats_partial, (cudaStream_t)stream, ntaps);
+    return conv3_igemm(x, w_fprop, y, +1, mode, v0, v1, stats_partial, (cudaStream_t)stream, ntaps,
+                       reinterpret_cast<float*>(workspace), workspace_bytes);
 }
 
-extern "C" int b200_conv3d_dgrad(const b200_act* dy, const void* w_packed, const b200_act* dx, void* stream) {
+extern "C" int b200_conv3d_dgrad(const b200_act* dy, const void* w_packed, const b200_act* dx, void* workspace,
+                                 int64_t workspace_bytes, void* stream) {
     CHECK_VIEW(dy);
     CHECK_VIEW(dx);
     REQUIRE(w_packed != nullptr, "conv3d_dgrad: null weights");
     // dx[v, ci] = sum_t sum_co dy[v - off(t), co] * w[co, ci, t]; w_packed is the fprop layout [27][Cout][Cin]
-    return conv3_igemm(dy, w_packed, dx, -1, B200_EPI_PLAIN, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+    return conv3_igemm(dy, w_packed, dx, -1, B200_EPI_PLAIN, nullptr, nullptr, nullptr, (cudaStream_t)stream, 27,
+                       reinterpret_cast<float*>(workspace), workspace_bytes);
 }
 
 // ------------------------------------------------------------------------------------------------ transposed conv

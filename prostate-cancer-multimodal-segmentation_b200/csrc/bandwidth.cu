@@ -1400,6 +1400,74 @@ cudaError_t launch_seg_counts(const float* score, const float* label, long long 
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------ split-K finalize
+// ws[split][voxel][c] holds the fp32 partial tiles of a deep-level convolution computed by `splits` work units per tile
+// (igemm EPI_SPLITK).  One pass adds them in split order (deterministic) and writes the bf16 output — mode 0: plain
+// (dgrad), 1: + bias and per-block BatchNorm partial sums of the ROUNDED values (train fprop; partial[block][c][2], the
+// layout the conv epilogue writes), 2: relu(acc * scale + shift) (eval fprop).  The slices are L2-resident (<= 36 MB).
+__global__ void __launch_bounds__(256) splitk_finalize_kernel(const float* __restrict__ ws, int splits, View y, int mode,
+                                                              const float* __restrict__ v0,
+                                                              const float* __restrict__ v1, float* partial, int c8,
+                                                              int rows, long long nvox) {
+    extern __shared__ float smem[];
+    const int row = threadIdx.x / c8, cv = threadIdx.x - row * c8;
+    const bool active = row < rows;
+    float acc[2][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+    if (active) {
+        float a0[8], a1[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { a0[j] = 0.f; a1[j] = 0.f; }
+        if (mode != 0) ldf8(v0 + cv * 8, a0);
+        if (mode == 2) ldf8(v1 + cv * 8, a1);
+        const long long slice = nvox * y.c;
+        for (long long v = (long long)blockIdx.x * rows + row; v < nvox; v += (long long)gridDim.x * rows) {
+            const float* src = ws + v * y.c + cv * 8;
+            float f[8];
+            ldf8(src, f);
+            for (int sp = 1; sp < splits; ++sp) {
+                float t[8];
+                ldf8(src + sp * slice, t);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] += t[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (mode == 1) f[j] += a0[j];
+                else if (mode == 2) f[j] = fmaxf(fmaf(f[j], a0[j], a1[j]), 0.f);
+            }
+            const Bf8 ob = pack8(f);
+            st8(y.p + v * y.ld + cv * 8, ob);
+            if (mode == 1) {
+                float r[8];
+                unpack8(ob, r);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { acc[0][j] += r[j]; acc[1][j] = fmaf(r[j], r[j], acc[1][j]); }
+            }
+        }
+    }
+    if (mode == 1)
+        block_reduce_store<2>(acc, c8, rows, row, cv, active, smem, partial + (long long)blockIdx.x * y.c * 2, (int)y.c,
+                              false);
+}
+int splitk_finalize_blocks(long long nvox, long long c) {
+    const LaneMap m = lane_map(c);
+    long long blocks = (nvox + m.rows - 1) / m.rows;
+    if (blocks > 148 * 2) blocks = 148 * 2;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+cudaError_t launch_splitk_finalize(const float* ws, int splits, View y, int mode, const float* v0, const float* v1,
+                                   float* partial, cudaStream_t s) {
+    const LaneMap m = lane_map(y.c);
+    const long long nvox = y.voxels();
+    const size_t smem = mode == 1 ? reduce_smem_bytes(m, 2) : 0;
+    splitk_finalize_kernel<<<splitk_finalize_blocks(nvox, y.c), 256, smem, s>>>(ws, splits, y, mode, v0, v1, partial,
+                                                                                m.c8, m.rows, nvox);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------ sliding windows
 // Sliding-window inference (BASELINE configs[3]; the reference's script/predict.py:152-172 predicts whole volumes, a
 // window schedule is the new capability): windows (volume, d0, h0, w0) of a batch of fp32 volumes are gathered into

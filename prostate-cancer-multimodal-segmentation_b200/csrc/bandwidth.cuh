@@ -76,6 +76,9 @@ cudaError_t launch_minmax_normalize(float* x, long long nvol, long long per, uin
 cudaError_t launch_seg_counts(const float* score, const float* label, long long nsmp, long long per, float threshold,
                               unsigned long long* counts, int sms, cudaStream_t s);
 
+int splitk_finalize_blocks(long long nvox, long long c);
+cudaError_t launch_splitk_finalize(const float* ws, int splits, View y, int mode, const float* v0, const float* v1, float* partial,
+                                   cudaStream_t s);
 cudaError_t launch_window_gather(const float* x, long long c, long long d, long long h, long long w, const int* org,
                                  int nwin, int wd, int wh, int ww, float* out, int sms, cudaStream_t s);
 cudaError_t launch_window_accumulate(const float* lg, const int* org, int nwin, long long k, int wd, int wh, int ww,

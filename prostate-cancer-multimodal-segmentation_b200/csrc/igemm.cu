@@ -181,14 +181,20 @@ DEV void igemm_body(const IgemmParams& p) {
     const int m_units = (m_tiles + (int)mmul - 1) / (int)mmul;
     const int total_tiles = m_units * p.n_tiles;
     const int unit0 = blockIdx.x / mmul, unit_stride = gridDim.x / mmul;
+    // split-K: unit = tile * splits + split; split s takes tap groups [s * G / S, (s + 1) * G / S)
+    const int nsplit = p.splits > 1 ? p.splits : 1;
+    const int total_units = total_tiles * nsplit;
+    const int tap_groups = p.ntaps / p.group;
 
     if (warp == 0) {
         // ===================================================================== TMA producer
         // The whole warp walks the loop (uniform control flow, barrier polls by all lanes); one elected lane issues.
         PipeState ps;
         uint32_t sink_uses = 0;   // dev ablation 3: stages issued so far
-        const int kc_blocks = p.kc_blocks, ntaps = p.ntaps / p.group, n_tiles = p.n_tiles, group = p.group;
-        for (int tile = unit0; tile < total_tiles; tile += unit_stride) {
+        const int kc_blocks = p.kc_blocks, n_tiles = p.n_tiles, group = p.group;
+        for (int unit = unit0; unit < total_units; unit += unit_stride) {
+            const int tile = unit / nsplit, sp = unit - tile * nsplit;
+            const int tap_lo = sp * tap_groups / nsplit, tap_hi = (sp + 1) * tap_groups / nsplit;
             int mt = tile / n_tiles;
             const int n_tile = tile - mt * n_tiles;
             mt = mt * (int)mmul + (int)rank;
@@ -198,7 +204,7 @@ DEV void igemm_body(const IgemmParams& p) {
             const int nb = mt;
             const int w0 = bw << p.tw_log2, h0 = bh << p.th_log2, d0 = bd << p.td_log2;
             const int n0 = n_tile * p.block_n;
-            for (int tap = 0; tap < ntaps; ++tap) {
+            for (int tap = tap_lo; tap < tap_hi; ++tap) {
                 const void* amap = &p.a_map[p.a_map_of_tap[tap]];
                 const int cw = w0 + p.tap_dw[tap], ch = h0 + p.tap_dh[tap], cd = d0 + p.tap_dd[tap];
                 for (int kc = 0; kc < kc_blocks; ++kc) {
@@ -260,18 +266,20 @@ DEV void igemm_body(const IgemmParams& p) {
         const uint64_t b_desc0 = make_smem_desc_sw128(smem_b, p.b_mn ? b_atom_bytes : 0, 1024);
         const uint32_t kinc = p.b_mn ? 128u : 2u;  // one K step (16): 16 rows x 128 B, or 32 B inside the swizzle row
         const uint32_t a_step = a_bytes >> 4, b_step = b_bytes >> 4, bt_step = bt_bytes >> 4;
-        const int kc_blocks = p.kc_blocks, ntaps = p.ntaps / p.group, group = p.group;
+        const int kc_blocks = p.kc_blocks, group = p.group;
         const uint32_t goff1 = p.a_goff[1], goff2 = p.a_goff[2], goff0 = p.a_goff[0];
         const int nk_last = ((p.cin - (kc_blocks - 1) * 64) + 15) >> 4;  // K steps of the last channel block (1..4)
         PipeState ps;
         int iter = 0;
-        for (int tile = unit0; tile < total_tiles; tile += unit_stride, ++iter) {
+        for (int unit = unit0; unit < total_units; unit += unit_stride, ++iter) {
+            const int sp = unit % nsplit;
+            const int tap_lo = sp * tap_groups / nsplit, tap_hi = (sp + 1) * tap_groups / nsplit;
             const uint32_t acc = iter & 1, acc_phase = (iter >> 1) & 1;
             mbar_wait(tempty_bar(acc), acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * p.block_n;
             uint32_t accum = 0;
-            for (int tap = 0; tap < ntaps; ++tap) {
+            for (int tap = tap_lo; tap < tap_hi; ++tap) {
                 for (int kc = 0; kc < kc_blocks; ++kc) {
                     const int nk = (kc == kc_blocks - 1) ? nk_last : 4;
                     mbar_wait(full_bar(ps.stage), ps.phase);
@@ -369,7 +377,7 @@ DEV void igemm_body(const IgemmParams& p) {
             const int mode = p.mode;
             const uint32_t sw = row & 7;
             const bool two_bufs = p.c_bufs > 1;
-            for (int tile = unit0; tile < total_tiles; tile += unit_stride, ++iter) {
+            for (int tile = unit0; tile < total_tiles; tile += unit_stride, ++iter) {   // (never split: host)
                 const uint32_t acc = iter & 1, acc_phase = (iter >> 1) & 1;
                 const int m_unit = tile / p.n_tiles;
                 const int n_tile = tile - m_unit * p.n_tiles;
@@ -473,7 +481,8 @@ DEV void igemm_body(const IgemmParams& p) {
             }
             if (et == 0) bulk_wait0();  // all output tiles are in global memory before the CTA exits
         } else
-        for (int tile = unit0; tile < total_tiles; tile += unit_stride, ++iter) {
+        for (int unit = unit0; unit < total_units; unit += unit_stride, ++iter) {
+            const int tile = unit / nsplit;
             const uint32_t acc = iter & 1, acc_phase = (iter >> 1) & 1;
             const int m_unit = tile / p.n_tiles;
             const int n_tile = tile - m_unit * p.n_tiles;
@@ -490,6 +499,28 @@ DEV void igemm_body(const IgemmParams& p) {
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.block_n;
             const int nchunks = p.block_n >> 4;
+            if (p.mode == EPI_SPLITK) {
+                // fp32 partial tile -> this split's slice of the workspace, row of this voxel (plain 16-byte stores)
+                const long long vox = (((long long)nb * p.D + gd) * p.H + gh) * p.W + gw;
+                float* wrow = p.ws + ((long long)(unit - tile * nsplit) * p.ws_slice_vox + vox) * p.ncols;
+                for (int c = 0; c < nchunks; ++c) {
+                    uint32_t v[16];
+                    tmem_ld16(t_addr + c * 16, v);
+                    tmem_ld_wait();
+                    const int col0 = n0 + c * 16;
+                    if (row_ok && col0 < p.ncols) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            *reinterpret_cast<float4*>(wrow + col0 + 4 * j) =
+                                make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                            __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                    }
+                }
+                tc_fence_before();
+                if (kPair) mbar_arrive_leader(tempty_bar(acc));
+                else mbar_arrive(tempty_bar(acc));
+                continue;
+            }
             for (int c = 0; c < nchunks; ++c) {
                 uint32_t v[16];
                 tmem_ld16(t_addr + c * 16, v);

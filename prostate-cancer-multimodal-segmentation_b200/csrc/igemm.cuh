@@ -27,6 +27,7 @@ enum EpilogueMode : int {
     EPI_BIAS_STATS = 1,  // out = bf16(acc + bias); per-tile sum / sum-of-squares of out (train fprop)
     EPI_AFFINE_RELU = 2, // out = relu(acc * scale + shift)   (eval fprop, BatchNorm folded)
     EPI_BIAS = 3,        // out = acc + bias                  (transposed conv forward)
+    EPI_SPLITK = 4,      // split-K partial: fp32 acc stored to this split's workspace slice; finalised by a second pass
 };
 
 // Implicit GEMM  D[m, n] = sum_{tap, c} A_tap[m, c] * B[tap][n][c]
@@ -71,6 +72,13 @@ struct alignas(64) IgemmParams {
     int out_mul;        // output coordinate = m coordinate * out_mul + offset[group]
     int cols_per_group; // columns sharing one output offset (transposed conv: Cout per tap)
     int out_od[kMaxMaps], out_oh[kMaxMaps], out_ow[kMaxMaps];
+    // split-K over the taps (deep levels: a handful of M tiles, K = 27 * Cin up to 27648): every (M, N) tile is computed
+    // by `splits` work units that each take a contiguous range of the tap groups and store their fp32 partial tile to
+    // ws[split][voxel][ncols]; splitk_finalize_kernel adds the slices in split order and writes the bf16 output (+ bias,
+    // BatchNorm partial sums)
+    int splits;
+    long long ws_slice_vox;   // voxels per slice
+    float* ws;
     // direct first-layer form (igemm_im2col_kernel): the A operand is not loaded by TMA but built in shared memory by
     // eight producer warps straight from the fp32 (N, C, D, H, W) network input — column k = c*27 + kd*9 + kh*3 + kw of
     // row m is x[n, c, d+kd-1, h+kh-1, w+kw-1] (zero outside the volume), i.e. the rows of the im2col matrix, which

@@ -44,6 +44,21 @@ def _slot_view(flat: torch.Tensor, off: int, p) -> torch.Tensor:
     return flat[off:off + n].view(p.shape)
 
 
+_SPLITK_WS = {}
+
+
+def _splitk_workspace(device, n, d, h, w, out_cols):
+    """The fp32 scratch of the split-K form of a deep-level conv / dgrad (None when the shape does not split).  One buffer
+    per device, grown on demand; all split-K launches run on the compute stream, so consecutive layers share it."""
+    nbytes = ops.conv3d_workspace_bytes(n, d, h, w, out_cols)
+    if nbytes == 0:
+        return None
+    t = _SPLITK_WS.get(device)
+    if t is None or t.numel() * 4 < nbytes:
+        t = _SPLITK_WS[device] = torch.empty((nbytes + 3) // 4, device=device, dtype=torch.float32)
+    return t
+
+
 class _ConvPack:
     """bf16 operand of one Conv3d 3x3x3.
 
@@ -99,12 +114,14 @@ class _ConvPack:
         (ops.im2col_input if self.im2col else ops.pack_input)(x, v)
         return v
 
-    def fprop(self, xin, bias, y, stats, mode, scale=None, shift=None):
+    def fprop(self, xin, bias, y, stats, mode, scale=None, shift=None, workspace=None):
         if isinstance(xin, RawInput):
             ops.conv1_direct_fprop(xin.t, self.wf, bias, y, stats, mode, scale, shift)
-            return
-        f = ops.conv1_fprop if self.im2col else ops.conv3d_fprop
-        f(xin, self.wf, bias, y, stats, mode, scale, shift, k_real=self.k_real)
+        elif self.im2col:
+            ops.conv1_fprop(xin, self.wf, bias, y, stats, mode, scale, shift, k_real=self.k_real)
+        else:
+            ops.conv3d_fprop(xin, self.wf, bias, y, stats, mode, scale, shift, k_real=self.k_real,
+                             workspace=workspace)
 
     def wgrad(self, xin, dy, dw):
         if isinstance(xin, RawInput):
@@ -118,10 +135,10 @@ class _ConvPack:
         else:
             raise B200Error("conv weight gradient buffer has an unsupported memory layout")
 
-    def dgrad(self, dy, dx):
+    def dgrad(self, dy, dx, workspace=None):
         if self.im2col:
             raise B200Error("input gradient of an im2col'd (thin-input) convolution is not available")
-        ops.conv3d_dgrad(dy, self.wf, dx)
+        ops.conv3d_dgrad(dy, self.wf, dx, workspace=workspace)
 
 
 class RawInput:
@@ -176,10 +193,11 @@ class _DoubleConv:
             raise ValueError(f"Expected more than 1 value per channel when training, got input size "
                              f"{(n, cout, d, h, w)}")
         y = ActView(new_act(n, d, h, w, cout, dev))
+        ws = None if pack.im2col else _splitk_workspace(dev, n, d, h, w, cout)
         rows = (ops.conv1_direct_stat_rows(n, d, h, w, cout) if isinstance(xin, RawInput)
-                else ops.conv3d_stat_rows(n, d, h, w, cout, 1 if pack.im2col else 27))
+                else ops.conv3d_stat_rows(n, d, h, w, cout, 1 if pack.im2col else 27, with_workspace=ws is not None))
         stats = torch.empty(rows, cout, 2, device=dev, dtype=torch.float32)
-        pack.fprop(xin, pack.conv.bias.data, y, stats, ops.EPI_BIAS_STATS)
+        pack.fprop(xin, pack.conv.bias.data, y, stats, ops.EPI_BIAS_STATS, workspace=ws)
         vec = torch.empty(4, cout, device=dev, dtype=torch.float32)  # mean, rstd, scale, shift
         momentum = bn.momentum
         nbt = None
@@ -202,7 +220,9 @@ class _DoubleConv:
         vec = torch.empty(2, pack.cout, device=dev, dtype=torch.float32)
         ops.bn_fold_eval(bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var, pack.conv.bias.data, bn.eps,
                          vec[0], vec[1])
-        pack.fprop(xin, None, out, None, ops.EPI_AFFINE_RELU, vec[0], vec[1])
+        n, d, h, w, _ = out.shape
+        ws = None if pack.im2col else _splitk_workspace(dev, n, d, h, w, pack.cout)
+        pack.fprop(xin, None, out, None, ops.EPI_AFFINE_RELU, vec[0], vec[1], workspace=ws)
 
     def forward(self, xin: ActView, out: ActView, training: bool):
         n, d, h, w, _ = xin.shape
@@ -233,7 +253,7 @@ class _DoubleConv:
         # dgrad first: it is on the critical chain (the next BatchNorm backward needs da1) and must win the SMs; the
         # weight gradient then runs beside that BatchNorm backward
         da1 = ActView(new_act(n, d, h, w, self.cout, dev))
-        self.p2.dgrad(dy2, da1)
+        self.p2.dgrad(dy2, da1, workspace=_splitk_workspace(dev, n, d, h, w, da1.c))
         side.run(lambda: self.p2.wgrad(st.a1, dy2, g(self.conv2.weight)), keep=(st.a1, dy2))
         st.y2 = None
         # first conv
@@ -241,7 +261,7 @@ class _DoubleConv:
         ops.bn_bwd(da1, st.y1, st.bn1[2], st.bn1[3], st.bn1[0], st.bn1[1], self.bn1.weight.data, scratch.partial,
                    scratch.coef, g(self.bn1.weight), g(self.bn1.bias), dy1, g(self.conv1.bias))
         if dxin is not None:
-            self.p1.dgrad(dy1, dxin)
+            self.p1.dgrad(dy1, dxin, workspace=_splitk_workspace(dev, n, d, h, w, dxin.c))
         side.run(lambda: self.p1.wgrad(st.xin, dy1, g(self.conv1.weight)), keep=(st.xin, dy1))
         if taps is not None:
             taps[name] = {"dout": dout, "dy2": dy2, "da1": da1, "dy1": dy1, "dx": dxin}

@@ -171,8 +171,13 @@ def pack_convt_weight(w: torch.Tensor, bias: torch.Tensor, w_fwd, w_dgrad, bias8
                                              stream_ptr()), "pack_convt_weight")
 
 
-def conv3d_stat_rows(n, d, h, w, cout, ntaps=27) -> int:
-    r = _lib.load().b200_conv3d_stat_rows(n, d, h, w, cout, ntaps)
+def conv3d_workspace_bytes(n, d, h, w, out_cols) -> int:
+    """bytes of the fp32 split-K scratch a 3x3x3 conv / dgrad of this shape uses (0: it does not split)"""
+    return int(_lib.load().b200_conv3d_workspace_bytes(n, d, h, w, out_cols))
+
+
+def conv3d_stat_rows(n, d, h, w, cout, ntaps=27, with_workspace=False) -> int:
+    r = _lib.load().b200_conv3d_stat_rows(n, d, h, w, cout, ntaps, 1 if with_workspace else 0)
     if r <= 0:
         raise _lib.B200Error("b200_conv3d_stat_rows failed (no CUDA device?)")
     return r
@@ -187,19 +192,32 @@ def _conv_kernel(lib, v: ActView, out_cols: int) -> str:
             "dmarch_pair_kernel")[lib.b200_conv3d_kernel_id(n, d, h, w, out_cols)]
 
 
+def _ws(workspace):
+    return (ptr(workspace), 0 if workspace is None else workspace.numel() * workspace.element_size())
+
+
 def conv3d_fprop(x: ActView, w_fprop, bias, y: ActView, stats=None, mode=EPI_BIAS_STATS, scale=None, shift=None,
-                 k_real=None):
+                 k_real=None, workspace=None):
+    """workspace: fp32 scratch of >= conv3d_workspace_bytes(...) for the split-K form of the deep levels"""
     lib = _lib.load()
-    _gemm(_conv_kernel(lib, x, y.c), "conv3d_fprop", 2.0 * x.voxels * y.c * (k_real or x.c) * 27,
+    wp, wb = _ws(workspace)
+    split = workspace is not None and lib.b200_conv3d_workspace_bytes(*x.shape[:4], y.c) > 0
+    _launched(1 if split else 0)   # + the finalize pass
+    _gemm("igemm_pair_kernel" if split else _conv_kernel(lib, x, y.c), "conv3d_fprop",
+          2.0 * x.voxels * y.c * (k_real or x.c) * 27,
           lambda: check(lib.b200_conv3d_fprop(x.ref, ptr(w_fprop), ptr(bias), y.ref, ptr(stats), mode, ptr(scale),
-                                              ptr(shift), stream_ptr()), "conv3d_fprop"),
+                                              ptr(shift), wp, wb, stream_ptr()), "conv3d_fprop"),
           shape=(x.voxels, k_real or x.c, y.c))
 
 
-def conv3d_dgrad(dy: ActView, w_packed, dx: ActView):
+def conv3d_dgrad(dy: ActView, w_packed, dx: ActView, workspace=None):
     lib = _lib.load()
-    _gemm(_conv_kernel(lib, dy, dx.c), "conv3d_dgrad", 2.0 * dy.voxels * dy.c * dx.c * 27,
-          lambda: check(lib.b200_conv3d_dgrad(dy.ref, ptr(w_packed), dx.ref, stream_ptr()), "conv3d_dgrad"),
+    wp, wb = _ws(workspace)
+    split = workspace is not None and lib.b200_conv3d_workspace_bytes(*dy.shape[:4], dx.c) > 0
+    _launched(1 if split else 0)
+    _gemm("igemm_pair_kernel" if split else _conv_kernel(lib, dy, dx.c), "conv3d_dgrad",
+          2.0 * dy.voxels * dy.c * dx.c * 27,
+          lambda: check(lib.b200_conv3d_dgrad(dy.ref, ptr(w_packed), dx.ref, wp, wb, stream_ptr()), "conv3d_dgrad"),
           shape=(dy.voxels, dx.c, dy.c))
 
 

@@ -316,8 +316,16 @@ def layerwise_check(pkg, device, batch, size, base=64, n_classes=1, zero_fill=Fa
             yv = f32(fw[f"{pre}.{yk}"]).requires_grad_(True)
             gam = par[f"{pre}.{bi}.weight"].clone().requires_grad_(True)
             bet = par[f"{pre}.{bi}.bias"].clone().requires_grad_(True)
-            aref = F.relu(F.batch_norm(yv, None, None, gam, bet, True, 0.1, 1e-5))
-            add(f"{pre}.{bi}", "fwd", f32(fw[f"{pre}.{ak}"]), aref.detach())
+            zref = F.batch_norm(yv, None, None, gam, bet, True, 0.1, 1e-5)
+            a_ours = f32(fw[f"{pre}.{ak}"])
+            add(f"{pre}.{bi}", "fwd", a_ours, F.relu(zref).detach())
+            # backward through the ReLU decisions the engine's forward took: a pre-activation within one fp32 rounding of
+            # zero (the batch mean summed in another order) may land on either side — invisible in the forward row,
+            # but one such voxel in a 256-voxel channel of the bottom level moves that channel's dbeta by its whole dout
+            keep = a_ours > 0
+            rows.append((f"{pre}.{bi}", "relu_decisions_differing_from_torch(info)",
+                         float((keep != (zref.detach() > 0)).sum().item())))
+            aref = zref * keep
             dout = f32(g["dout"] if ci == 3 else g["da1"])
             gy, gg, gbb = torch.autograd.grad(aref, [yv, gam, bet], dout)
             per_channel = yv.numel() // yv.shape[1]

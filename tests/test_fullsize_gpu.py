@@ -53,7 +53,7 @@ def test_layerwise_identical_inputs(pkg, cuda_dev, case):
         elif op == "loss":
             if v > 1e-5:
                 bad.append((op, what, v))
-        elif "(degenerate" in what:
+        elif "(degenerate" in what or what.endswith("(info)"):
             continue   # BatchNorm backward over < 16 samples per channel (bottom level of the odd-extent case)
         elif not (v <= TOL_LAYER):
             bad.append((op, what, v))

@@ -116,6 +116,67 @@ def test_conv3d_dgrad(ops, cuda_dev, case):
     assert err < TOL, f"dgrad rel-L2 {err}"
 
 
+SPLITK_CASES = [
+    # n, cin, cout, d, h, w — deep levels: a handful of 128-voxel bricks, K = 27 * Cin large
+    (2, 512, 1024, 8, 8, 8),     # BASELINE configs[1] bottom level, first conv
+    (2, 256, 512, 8, 8, 8),      # base 32
+    (1, 256, 256, 10, 10, 10),   # 160^3 bottom level: partial bricks, odd number of M tiles
+    (1, 128, 256, 4, 4, 4),      # one brick, half filled: dummy peer CTA
+]
+
+
+@pytest.mark.parametrize("case", SPLITK_CASES)
+def test_conv3d_splitk_fprop_dgrad(ops, cuda_dev, case):
+    """Split-K form of the deep levels (fp32 partial tiles in per-split workspace slices + an ordered finalize pass): same
+    results as F.conv3d / conv3d_input, BatchNorm partial sums of the rounded output, bit-identical from run to run
+    whatever the scratch held before."""
+    n, cin, cout, d, h, w = case
+    nbytes = ops.conv3d_workspace_bytes(n, d, h, w, cout)
+    assert nbytes >= 2 * n * d * h * w * cout * 4, "this shape is expected to split"
+    x, wt, b = _conv_inputs(cuda_dev, n, cin, cout, d, h, w, seed=11)
+    wf = torch.empty(27, cout, cin, device=cuda_dev, dtype=torch.bfloat16)
+    ops.pack_conv_weight(wt.contiguous(), cin, wf)
+    ws = torch.full((max(nbytes, ops.conv3d_workspace_bytes(n, d, h, w, cin)) // 4,), float("nan"), device=cuda_dev)
+    xv = to_act(ops, x)
+    ref = F.conv3d(x, wt, b, padding=1)
+    first = None
+    for rep in range(2):   # the second call runs on the scratch the first one left behind
+        yv = empty_act(ops, n, cout, d, h, w, cuda_dev)
+        rows = ops.conv3d_stat_rows(n, d, h, w, cout, with_workspace=True)
+        stats = torch.full((rows, cout, 2), float("nan"), device=cuda_dev)
+        ops.conv3d_fprop(xv, wf, b, yv, stats, ops.EPI_BIAS_STATS, workspace=ws)
+        torch.cuda.synchronize()
+        got = from_act(yv)
+        assert torch.isfinite(got).all()
+        assert rel_l2(got, ref) < TOL
+        assert first is None or torch.equal(first, got), "split-K result differs between runs"
+        first = got
+        s, gd = stats.double().sum(0), got.double()
+        assert torch.allclose(s[:, 0], gd.sum((0, 2, 3, 4)), rtol=1e-4, atol=1e-2)
+        assert torch.allclose(s[:, 1], (gd * gd).sum((0, 2, 3, 4)), rtol=1e-4, atol=1e-2)
+    # eval epilogue
+    scale = torch.rand(cout, device=cuda_dev) + 0.5
+    shift = torch.randn(cout, device=cuda_dev) * 0.2
+    yv = empty_act(ops, n, cout, d, h, w, cuda_dev)
+    ops.conv3d_fprop(xv, wf, None, yv, None, ops.EPI_AFFINE_RELU, scale, shift, workspace=ws)
+    ref2 = torch.relu(F.conv3d(x, wt, None, padding=1) * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1))
+    assert rel_l2(from_act(yv), ref2) < TOL
+    # the un-split form of the same problem (no workspace) agrees
+    yu = empty_act(ops, n, cout, d, h, w, cuda_dev)
+    stats_u = torch.empty(ops.conv3d_stat_rows(n, d, h, w, cout), cout, 2, device=cuda_dev)
+    ops.conv3d_fprop(xv, wf, b, yu, stats_u, ops.EPI_BIAS_STATS)
+    assert rel_l2(from_act(yu), ref) < TOL
+    # dgrad: dx (cin columns) from dy (cout channels)
+    if ops.conv3d_workspace_bytes(n, d, h, w, cin):
+        g = torch.Generator(device="cpu").manual_seed(5)
+        dy = bf16_round(torch.randn(n, cout, d, h, w, generator=g)).to(cuda_dev)
+        dxv = empty_act(ops, n, cin, d, h, w, cuda_dev)
+        ops.conv3d_dgrad(to_act(ops, dy), wf, dxv, workspace=ws)
+        torch.cuda.synchronize()
+        refd = torch.nn.grad.conv3d_input((n, cin, d, h, w), wt, dy, padding=1)
+        assert rel_l2(from_act(dxv), refd) < TOL
+
+
 @pytest.mark.parametrize("case", CONV_CASES)
 def test_conv3d_wgrad(ops, cuda_dev, case):
     n, cin, cin_real, cout, d, h, w = case

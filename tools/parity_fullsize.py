@@ -40,6 +40,6 @@ if __name__ == "__main__":
     for name in cases:
         rows = pu.layerwise_check(pkg, dev, **CASES[name])
         pu.write_layerwise(rows, os.path.join(out, f"{tag}_layerwise_{name}.txt"), header=f"{name}: {CASES[name]}")
-        worst = max((r for r in rows if not r[1].endswith("mismatches") and r[0] != "loss"), key=lambda r: r[2])
+        worst = max((r for r in rows if not r[1].endswith("mismatches") and not r[1].endswith("(info)") and r[0] != "loss"), key=lambda r: r[2])
         print(name, "layerwise worst", worst, flush=True)
         torch.cuda.empty_cache()
