@@ -130,6 +130,21 @@ int b200_bn_bwd_apply(const b200_act* dout, const b200_act* y, const float* scal
                       const float* mean, const float* rstd, const float* gamma, const float* coef,
                       const b200_act* dy, float* dbias, void* stream);
 
+/* ---- fused forms: these passes are HBM-bound, so they are made cheaper by never writing what can be recomputed ---- */
+/* encoder block (models/unet3d.py:37-39 followed by :80): out = relu(y*scale + shift) and pooled = MaxPool3d(2)(out)
+ * in one pass (= b200_bn_apply_relu + b200_maxpool3d_fwd without re-reading out). */
+int b200_bn_apply_relu_pool(const b200_act* y, const float* scale, const float* shift, const b200_act* out,
+                            const b200_act* pooled, void* stream);
+/* BatchNorm backward of the network's last BatchNorm whose incoming gradient is the head's input gradient
+ * dout = dlogits . w: equals b200_head_bwd + b200_bn_bwd_reduce / _apply (3 streams instead of 7); the reduce pass
+ * also accumulates the head's dw (ncls, C) += dlogits^T relu(bn(y)) and db (ncls) += sum dlogits. */
+int b200_bn_bwd_reduce_head(const float* dlogits, const float* w, int ncls, const b200_act* y, const float* scale,
+                            const float* shift, const float* mean, const float* rstd, float* partial, int* nblk,
+                            float* dw, float* db, void* stream);
+int b200_bn_bwd_apply_head(const float* dlogits, const float* w, int ncls, const b200_act* y, const float* scale,
+                           const float* shift, const float* mean, const float* rstd, const float* coef,
+                           const b200_act* dy, float* dbias, void* stream);
+
 /* ---- MaxPool3d(2) (models/unet3d.py:80) ---------------------------------------------------------------- */
 int b200_maxpool3d_fwd(const b200_act* x, const b200_act* y, void* stream);
 /* dx = dskip (may be NULL) + scatter(dy) to the first maximum in d,h,w scan order; voxels not covered by a

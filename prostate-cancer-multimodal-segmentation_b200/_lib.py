@@ -55,6 +55,9 @@ SIGNATURES = {
     "b200_bn_bwd_reduce": (_i32, [_AP, _AP, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i32), _vp]),
     "b200_bn_bwd_finalize": (_i32, [_vp, _i32, _i32, _i64, _vp, _vp, _vp, _vp]),
     "b200_bn_bwd_apply": (_i32, [_AP, _AP, _vp, _vp, _vp, _vp, _vp, _vp, _AP, _vp, _vp]),
+    "b200_bn_apply_relu_pool": (_i32, [_AP, _vp, _vp, _AP, _AP, _vp]),
+    "b200_bn_bwd_reduce_head": (_i32, [_vp, _vp, _i32, _AP, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i32), _vp, _vp, _vp]),
+    "b200_bn_bwd_apply_head": (_i32, [_vp, _vp, _i32, _AP, _vp, _vp, _vp, _vp, _vp, _AP, _vp, _vp]),
     "b200_maxpool3d_fwd": (_i32, [_AP, _AP, _vp]),
     "b200_maxpool3d_bwd": (_i32, [_AP, _AP, _AP, _AP, _AP, _vp]),
     "b200_head_fwd": (_i32, [_AP, _vp, _vp, _i32, _vp, _vp, _vp]),
@@ -85,9 +88,10 @@ DEV_SIGNATURES = {
     "b200_probe_mma": (_i32, [_i32, _i32, _i32, _vp, _i32, _vp]),
     "b200_probe_mma2": (_i32, [_i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "b200_dev_set_ablation": (_i32, [_i32, _i32, _i32, _i32]),
+    "b200_dev_set_variant": (_i32, [_i32, _i32]),
 }
 
-ABI_VERSION = 3   # must equal b200_abi_version() of the loaded library
+ABI_VERSION = 4   # must equal b200_abi_version() of the loaded library
 
 _lib = None
 

@@ -46,7 +46,7 @@ static int fail(int code, const char* fmt, ...) {
     } while (0)
 
 extern "C" const char* b200_last_error(void) { return g_err; }
-extern "C" int b200_abi_version(void) { return 3; }
+extern "C" int b200_abi_version(void) { return 4; }
 
 // Development switches: compiled only into the development library (-DB200_DEV).  The product library has no
 // environment lookups and no ablation branches on its launch path.
@@ -57,8 +57,15 @@ extern "C" int b200_dev_set_ablation(int igemm_ablate, int dmarch_ablate, int no
     g_dev_nopair = nopair; g_dev_stage_cap = stage_cap;
     return 0;
 }
+static int g_dev_var[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // launcher variants under test (tools/bench_variants.py)
+extern "C" int b200_dev_set_variant(int which, int value) {
+    if (which < 0 || which >= 8) return 1;
+    g_dev_var[which] = value;
+    return 0;
+}
 #else
 constexpr int g_dev_igemm_ablate = 0, g_dev_dmarch_ablate = 0, g_dev_nopair = 0, g_dev_stage_cap = 0;
+constexpr int g_dev_var[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
 
 // ------------------------------------------------------------------------------------------------ device info
@@ -689,6 +696,11 @@ extern "C" int b200_convt2x_fwd(const b200_act* x, const void* w_fwd, const floa
     if (rc) return rc;
     const long long ncols = 8 * y->c;
     p.block_n = igemm_block_n(ncols, x->n * b.nbw * b.nbh * b.nbd);
+    // K = Cin is short (1-16 k-blocks per tile), so a tile lives on its loads and stores: 128-column tiles (two staging
+    // tiles fit next to a deeper operand ring) are 3-17 % faster than 256 at all four decoder shapes
+    // (tools/bench_variants.py); 64-column tiles are 40 % slower (the A box is re-read per column tile)
+    if (p.block_n == 256 && ncols % 128 == 0) p.block_n = 128;
+    if (g_dev_var[0] > 0) p.block_n = g_dev_var[0];   // development library only
     // a 256-column tile must not straddle a tap group unless the group size divides it
     REQUIRE(p.block_n % 16 == 0 && (y->c % 16 == 0), "convt2x_fwd: bad column tiling");
     rc = make_weight_map(&p.b_map, w_fwd, x->c, ncols, 1, p.block_n);
@@ -706,7 +718,13 @@ extern "C" int b200_convt2x_fwd(const b200_act* x, const void* w_fwd, const floa
     p.cols_per_group = (int)y->c;
     // the tile is K-short (K = Cin), so the epilogue dominates: stage + TMA store through 8 strided (parity) maps
     p.epi_v2 = (y->c % 64 == 0 && p.block_n % 64 == 0) ? 1 : 0;
-    p.c_bufs = (p.epi_v2 && p.block_n <= 64) ? 2 : 1;
+    // a second staging tile takes the store's read latency off the epilogue once a CTA has many tiles to stream
+    {
+        const long long tiles = x->n * b.nbw * b.nbh * b.nbd * ((ncols + p.block_n - 1) / p.block_n);
+        const int sms = sm_count();
+        p.c_bufs = (p.epi_v2 && (p.block_n <= 64 || (p.block_n <= 128 && sms > 0 && tiles >= 8LL * sms))) ? 2 : 1;
+    }
+    if (g_dev_var[1] > 0 && p.epi_v2) p.c_bufs = g_dev_var[1];   // development library only
     for (int t = 0; t < 8; ++t) {
         p.out_od[t] = pad_d + ((t >> 2) & 1);
         p.out_oh[t] = pad_h + ((t >> 1) & 1);
@@ -1194,6 +1212,48 @@ extern "C" int b200_bn_bwd_apply(const b200_act* dout, const b200_act* y, const 
             "bn_bwd_apply: extent mismatch");
     CUDA_TRY(launch_bn_bwd_apply(to_view(dout), to_view(y), scale, shift, mean, rstd, coef, to_view(dy), dbias,
                                  (cudaStream_t)stream));
+    return 0;
+}
+// ---- fused forms (bandwidth.cu, "fused BatchNorm passes"): the gradient entering the BatchNorm backward is recomputed
+extern "C" int b200_bn_apply_relu_pool(const b200_act* y, const float* scale, const float* shift, const b200_act* out,
+                                       const b200_act* pooled, void* stream) {
+    CHECK_VIEW(y);
+    CHECK_VIEW(out);
+    CHECK_VIEW(pooled);
+    REQUIRE(scale && shift, "bn_apply_relu_pool: null argument");
+    REQUIRE(out->n == y->n && out->c == y->c && out->d == y->d && out->h == y->h && out->w == y->w,
+            "bn_apply_relu_pool: out extent mismatch");
+    REQUIRE(pooled->n == y->n && pooled->c == y->c && pooled->d == y->d / 2 && pooled->h == y->h / 2 &&
+                pooled->w == y->w / 2, "bn_apply_relu_pool: pooled extent must be floor(input / 2)");
+    REQUIRE(y->c % 8 == 0, "bn_apply_relu_pool: channels must be a multiple of 8");
+    CUDA_TRY(launch_bn_apply_relu_pool(to_view(y), scale, shift, to_view(out), to_view(pooled), sm_count(),
+                                       (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int b200_bn_bwd_reduce_head(const float* dlogits, const float* w, int ncls, const b200_act* y,
+                                       const float* scale, const float* shift, const float* mean, const float* rstd,
+                                       float* partial, int* nblk, float* dw, float* db, void* stream) {
+    CHECK_VIEW(y);
+    REQUIRE(dlogits && w && scale && shift && mean && rstd && partial && nblk && dw && db,
+            "bn_bwd_reduce_head: null argument");
+    REQUIRE(ncls >= 1 && ncls <= 4, "bn_bwd_reduce_head: supports 1..4 classes");
+    REQUIRE(y->c % 8 == 0 && y->c <= 2048, "bn_bwd_reduce_head: channels must be a multiple of 8, <= 2048");
+    CUDA_TRY(launch_bn_bwd_head(false, dlogits, w, ncls, to_view(y), scale, shift, mean, rstd, nullptr, partial, nblk,
+                                to_view(y), nullptr, dw, db, (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int b200_bn_bwd_apply_head(const float* dlogits, const float* w, int ncls, const b200_act* y,
+                                      const float* scale, const float* shift, const float* mean, const float* rstd,
+                                      const float* coef, const b200_act* dy, float* dbias, void* stream) {
+    CHECK_VIEW(y);
+    CHECK_VIEW(dy);
+    REQUIRE(dlogits && w && scale && shift && mean && rstd && coef, "bn_bwd_apply_head: null argument");
+    REQUIRE(ncls >= 1 && ncls <= 4, "bn_bwd_apply_head: supports 1..4 classes");
+    REQUIRE(y->c % 8 == 0 && y->c <= 2048, "bn_bwd_apply_head: channels must be a multiple of 8, <= 2048");
+    REQUIRE(dy->n == y->n && dy->c == y->c && dy->d == y->d && dy->h == y->h && dy->w == y->w,
+            "bn_bwd_apply_head: dy extent mismatch");
+    CUDA_TRY(launch_bn_bwd_head(true, dlogits, w, ncls, to_view(y), scale, shift, mean, rstd, coef, nullptr, nullptr,
+                                to_view(dy), dbias, nullptr, nullptr, (cudaStream_t)stream));
     return 0;
 }
 extern "C" int b200_maxpool3d_fwd(const b200_act* x, const b200_act* y, void* stream) {

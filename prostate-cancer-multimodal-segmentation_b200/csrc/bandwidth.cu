@@ -399,19 +399,37 @@ cudaError_t launch_bn_fold_eval(const float* gamma, const float* beta, const flo
 }
 
 // ------------------------------------------------------------------------------------------------ BN apply + ReLU
+// Four 16-byte vectors per thread are in flight before the first is used: with one load per thread the kernel sat at
+// 5.5 TB/s (ncu: 91 % of the warps resident, 31 % issue, 68 % DRAM — bound by the bytes in flight, not by either pipe).
 __global__ void __launch_bounds__(256) bn_apply_relu_kernel(View y, const float* __restrict__ scale,
                                                             const float* __restrict__ shift, View out, FastDiv c8d,
                                                             uint32_t total) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const uint32_t vox = c8d.quot(i);
-        const uint32_t c0 = (i - vox * c8d.div) * 8;
-        float f[8], sc[8], sh[8];
-        unpack8(ld8_stream(y.p + (long long)vox * y.ld + c0), f);
-        ldf8(scale + c0, sc);
-        ldf8(shift + c0, sh);
+    constexpr int U = 4;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += U * stride) {
+        Bf8 in[U];
+        uint32_t vox[U], c0[U];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
-        st8(out.p + (long long)vox * out.ld + c0, pack8(f));
+        for (int u = 0; u < U; ++u) {
+            const uint32_t i = i0 + u * stride;
+            if (i < total) {
+                vox[u] = c8d.quot(i);
+                c0[u] = (i - vox[u] * c8d.div) * 8;
+                in[u] = ld8_stream(y.p + (long long)vox[u] * y.ld + c0[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (i0 + u * stride < total) {
+                float f[8], sc[8], sh[8];
+                unpack8(in[u], f);
+                ldf8(scale + c0[u], sc);
+                ldf8(shift + c0[u], sh);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
+                st8(out.p + (long long)vox[u] * out.ld + c0[u], pack8(f));
+            }
+        }
     }
 }
 cudaError_t launch_bn_apply_relu(View y, const float* scale, const float* shift, View out, int sms, cudaStream_t s) {
@@ -481,11 +499,47 @@ DEV void block_reduce_store(float (&acc)[NACC][8], int c8, int rows, int row, in
 }
 
 // ------------------------------------------------------------------------------------------------ BN backward
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(View dout, View y, const float* __restrict__ scale,
-                                                            const float* __restrict__ shift,
-                                                            const float* __restrict__ mean,
-                                                            const float* __restrict__ rstd, float* partial, int c8,
-                                                            int rows, long long nvox) {
+// Both backward passes are software-pipelined: a thread issues the loads of its next group of kBwdU voxels before it
+// computes on the current one, so every resident warp has loads in flight all the time.  (The straight loops ran at
+// 5.1 TB/s with 24-28 % of the warps resident — registers — and 45-49 % issue: bound by the bytes in flight.)
+constexpr int kBwdU = 4;
+struct BwdGroup {
+    Bf8 g[kBwdU], x[kBwdU];
+};
+DEV void bwd_load(BwdGroup& t, const View& dout, const View& y, long long v0, long long step, long long nvox, int c0) {
+#pragma unroll
+    for (int u = 0; u < kBwdU; ++u) {
+        const long long v = v0 + u * step;
+        if (v < nvox) {
+            t.g[u] = ld8_stream(dout.p + v * dout.ld + c0);
+            t.x[u] = ld8_stream(y.p + v * y.ld + c0);
+        }
+    }
+}
+// walks groups v0, v0 + kBwdU * step, ... with two register sets (ping-pong: no copies)
+template <class Compute>
+DEV void bwd_pipeline(const View& dout, const View& y, long long v0, long long step, long long nvox, int c0,
+                      Compute&& compute) {
+    BwdGroup a, b;
+    const long long big = kBwdU * step;
+    if (v0 < nvox) bwd_load(a, dout, y, v0, step, nvox, c0);
+    while (v0 < nvox) {
+        const long long v1 = v0 + big;
+        if (v1 < nvox) bwd_load(b, dout, y, v1, step, nvox, c0);
+        compute(a, v0);
+        if (v1 >= nvox) break;
+        const long long v2 = v1 + big;
+        if (v2 < nvox) bwd_load(a, dout, y, v2, step, nvox, c0);
+        compute(b, v1);
+        v0 = v2;
+    }
+}
+
+__global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(View dout, View y, const float* __restrict__ scale,
+                                                               const float* __restrict__ shift,
+                                                               const float* __restrict__ mean,
+                                                               const float* __restrict__ rstd, float* partial, int c8,
+                                                               int rows, long long nvox) {
     extern __shared__ float smem[];
     const int row = threadIdx.x / c8, cv = threadIdx.x - row * c8;
     const bool active = row < rows;
@@ -493,46 +547,31 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(View dout, View y, c
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
     if (active) {
-        float sc[8], sh[8], mu[8], rs[8];
+        float sc[8], sh[8], rs[8], nmr[8];   // x-hat = x * rstd - mean * rstd
         ldf8(scale + cv * 8, sc);
         ldf8(shift + cv * 8, sh);
-        ldf8(mean + cv * 8, mu);
         ldf8(rstd + cv * 8, rs);
+        ldf8(mean + cv * 8, nmr);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) nmr[j] = -nmr[j] * rs[j];
         const long long step = (long long)gridDim.x * rows;
-        long long v = (long long)blockIdx.x * rows + row;
-        // two voxels per iteration: four 16-byte loads in flight per thread (these kernels often share the SM with a
-        // persistent GEMM CTA and then run at low occupancy)
-        for (; v + step < nvox; v += 2 * step) {
-            const Bf8 g0 = ld8_stream(dout.p + v * dout.ld + cv * 8), x0 = ld8_stream(y.p + v * y.ld + cv * 8);
-            const Bf8 g1 = ld8_stream(dout.p + (v + step) * dout.ld + cv * 8);
-            const Bf8 x1 = ld8_stream(y.p + (v + step) * y.ld + cv * 8);
-            float g[8], x[8];
-            unpack8(g0, g); unpack8(x0, x);
+        bwd_pipeline(dout, y, (long long)blockIdx.x * rows + row, step, nvox, cv * 8,
+                     [&](const BwdGroup& t, long long v0) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float gm = fmaf(x[j], sc[j], sh[j]) > 0.f ? g[j] : 0.f;
-                acc[0][j] += gm;
-                acc[1][j] += gm * ((x[j] - mu[j]) * rs[j]);
-            }
-            unpack8(g1, g); unpack8(x1, x);
+                         for (int u = 0; u < kBwdU; ++u) {
+                             if (v0 + u * step < nvox) {
+                                 float g[8], x[8];
+                                 unpack8(t.g[u], g);
+                                 unpack8(t.x[u], x);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float gm = fmaf(x[j], sc[j], sh[j]) > 0.f ? g[j] : 0.f;
-                acc[0][j] += gm;
-                acc[1][j] += gm * ((x[j] - mu[j]) * rs[j]);
-            }
-        }
-        for (; v < nvox; v += step) {
-            float g[8], x[8];
-            unpack8(ld8_stream(dout.p + v * dout.ld + cv * 8), g);
-            unpack8(ld8_stream(y.p + v * y.ld + cv * 8), x);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float gm = fmaf(x[j], sc[j], sh[j]) > 0.f ? g[j] : 0.f;
-                acc[0][j] += gm;
-                acc[1][j] += gm * ((x[j] - mu[j]) * rs[j]);
-            }
-        }
+                                 for (int j = 0; j < 8; ++j) {
+                                     const float gm = fmaf(x[j], sc[j], sh[j]) > 0.f ? g[j] : 0.f;
+                                     acc[0][j] += gm;
+                                     acc[1][j] = fmaf(gm, fmaf(x[j], rs[j], nmr[j]), acc[1][j]);
+                                 }
+                             }
+                         }
+                     });
     }
     block_reduce_store<2>(acc, c8, rows, row, cv, active, smem, partial + (long long)blockIdx.x * y.c * 2, (int)y.c,
                           false);
@@ -570,12 +609,30 @@ cudaError_t launch_bn_bwd_finalize(const float* partial, int nblk, int c, long l
     return cudaGetLastError();
 }
 
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(View dout, View y, const float* __restrict__ scale,
-                                                           const float* __restrict__ shift,
-                                                           const float* __restrict__ mean,
-                                                           const float* __restrict__ rstd,
-                                                           const float* __restrict__ coef, View dy, float* dbias,
-                                                           int c8, int rows, long long nvox) {
+// dy = gamma * rstd * (dy_m - coef0 - x-hat * coef1) = scale * dy_m + (P * x + Q) with per-channel
+// P = -scale * coef1 * rstd, Q = scale * (coef1 * mean * rstd - coef0): two FMAs per element
+DEV void bwd_apply_consts(const float* scale, const float* mean, const float* rstd, const float* coef, int cv,
+                          float (&sc)[8], float (&P)[8], float (&Q)[8]) {
+    float mu[8], rs[8], t[8], u[8];
+    ldf8(scale + cv * 8, sc);
+    ldf8(mean + cv * 8, mu);
+    ldf8(rstd + cv * 8, rs);
+    ldf8(coef + cv * 16, t);       // coef[c][2] = (sum dy_m, sum dy_m * x-hat) / count
+    ldf8(coef + cv * 16 + 8, u);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float k0 = j < 4 ? t[2 * j] : u[2 * j - 8], k1 = j < 4 ? t[2 * j + 1] : u[2 * j - 7];
+        P[j] = -sc[j] * k1 * rs[j];
+        Q[j] = sc[j] * (k1 * mu[j] * rs[j] - k0);
+    }
+}
+
+__global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(View dout, View y, const float* __restrict__ scale,
+                                                              const float* __restrict__ shift,
+                                                              const float* __restrict__ mean,
+                                                              const float* __restrict__ rstd,
+                                                              const float* __restrict__ coef, View dy, float* dbias,
+                                                              int c8, int rows, long long nvox) {
     extern __shared__ float smem[];
     const int row = threadIdx.x / c8, cv = threadIdx.x - row * c8;
     const bool active = row < rows;
@@ -583,46 +640,33 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(View dout, View y, co
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[0][j] = 0.f;
     if (active) {
-        float sc[8], sh[8], mu[8], rs[8], k0[8], k1[8];
-        ldf8(scale + cv * 8, sc);
+        float sc[8], sh[8], P[8], Q[8];
         ldf8(shift + cv * 8, sh);
-        ldf8(mean + cv * 8, mu);
-        ldf8(rstd + cv * 8, rs);
-        {
-            float t[8], u[8];
-            ldf8(coef + cv * 16, t);
-            ldf8(coef + cv * 16 + 8, u);
-            k0[0] = t[0]; k1[0] = t[1]; k0[1] = t[2]; k1[1] = t[3]; k0[2] = t[4]; k1[2] = t[5]; k0[3] = t[6]; k1[3] = t[7];
-            k0[4] = u[0]; k1[4] = u[1]; k0[5] = u[2]; k1[5] = u[3]; k0[6] = u[4]; k1[6] = u[5]; k0[7] = u[6]; k1[7] = u[7];
-        }
+        bwd_apply_consts(scale, mean, rstd, coef, cv, sc, P, Q);
         const long long step = (long long)gridDim.x * rows;
-        auto one = [&](long long v, const Bf8& gb, const Bf8& xb) {
-            float g[8], x[8], o[8];
-            unpack8(gb, g);
-            unpack8(xb, x);
+        bwd_pipeline(dout, y, (long long)blockIdx.x * rows + row, step, nvox, cv * 8,
+                     [&](const BwdGroup& t, long long v0) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float gm = fmaf(x[j], sc[j], sh[j]) > 0.f ? g[j] : 0.f;
-                const float xh = (x[j] - mu[j]) * rs[j];
-                o[j] = sc[j] * (gm - k0[j] - xh * k1[j]);
-            }
-            const Bf8 ob = pack8(o);
-            st8(dy.p + v * dy.ld + cv * 8, ob);
-            float r[8];
-            unpack8(ob, r);
+                         for (int u = 0; u < kBwdU; ++u) {
+                             const long long v = v0 + u * step;
+                             if (v < nvox) {
+                                 float g[8], x[8], o[8];
+                                 unpack8(t.g[u], g);
+                                 unpack8(t.x[u], x);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[0][j] += r[j];
-        };
-        long long v = (long long)blockIdx.x * rows + row;
-        for (; v + step < nvox; v += 2 * step) {  // two voxels per iteration: four loads in flight
-            const Bf8 g0 = ld8_stream(dout.p + v * dout.ld + cv * 8), x0 = ld8_stream(y.p + v * y.ld + cv * 8);
-            const Bf8 g1 = ld8_stream(dout.p + (v + step) * dout.ld + cv * 8);
-            const Bf8 x1 = ld8_stream(y.p + (v + step) * y.ld + cv * 8);
-            one(v, g0, x0);
-            one(v + step, g1, x1);
-        }
-        for (; v < nvox; v += step)
-            one(v, ld8_stream(dout.p + v * dout.ld + cv * 8), ld8_stream(y.p + v * y.ld + cv * 8));
+                                 for (int j = 0; j < 8; ++j) {
+                                     const float gm = fmaf(x[j], sc[j], sh[j]) > 0.f ? g[j] : 0.f;
+                                     o[j] = fmaf(sc[j], gm, fmaf(x[j], P[j], Q[j]));
+                                 }
+                                 const Bf8 ob = pack8(o);
+                                 st8(dy.p + v * dy.ld + cv * 8, ob);
+                                 float r[8];
+                                 unpack8(ob, r);
+#pragma unroll
+                                 for (int j = 0; j < 8; ++j) acc[0][j] += r[j];
+                             }
+                         }
+                     });
     }
     if (dbias) block_reduce_store<1>(acc, c8, rows, row, cv, active, smem, dbias, (int)y.c, true);
 }
@@ -751,7 +795,7 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(View x, View dy, View 
         const uint32_t nb = q;
         const bool full = (2 * cd + 1 < x.d) && (2 * ch + 1 < x.h) && (2 * cw + 1 < x.w);
         const long long v000 = (((long long)nb * x.d + 2 * cd) * x.h + 2 * ch) * x.w + 2 * cw;
-        Bf8 xin[8], g, mx;
+        Bf8 xin[8], sk[8], g, mx;
         if (full) {
             const long long ov = (((long long)nb * dy.d + cd) * dy.h + ch) * dy.w + cw;
             g = ld8_stream(dy.p + ov * dy.ld + c0);
@@ -759,6 +803,13 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(View x, View dy, View 
             for (int k = 0; k < 8; ++k) {
                 const long long v = v000 + ((k >> 2) & 1) * x.h * x.w + ((k >> 1) & 1) * x.w + (k & 1);
                 xin[k] = ld8_stream(x.p + v * x.ld + c0);
+            }
+            if (has_skip) {   // the skip gradients are in flight together with the window's inputs
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const long long v = v000 + ((k >> 2) & 1) * x.h * x.w + ((k >> 1) & 1) * x.w + (k & 1);
+                    sk[k] = ld8_stream(dskip.p + v * dskip.ld + c0);
+                }
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -777,7 +828,8 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(View x, View dy, View 
                 const long long v = v000 + (long long)kd * x.h * x.w + kh * x.w + kw;
                 Bf8 o;
                 if (has_skip) {
-                    o = ld8_stream(dskip.p + v * dskip.ld + c0);
+                    if (full) o = sk[k];
+                    else o = ld8_stream(dskip.p + v * dskip.ld + c0);
                 } else {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) o.v[j] = from_bits(0u);
@@ -1016,6 +1068,308 @@ cudaError_t launch_head_bwd(View x, const float* w, int ncls, const float* dlogi
         case 4: return head_bwd_launch<4>(x, w, dlogits, dx, dw, db, s);
         default: return cudaErrorInvalidValue;
     }
+}
+
+// ------------------------------------------------------------------------------------------------ fused BatchNorm passes
+// The BatchNorm passes are bound by HBM, so they get cheaper only by moving fewer bytes:
+//   * forward, encoder blocks: BatchNorm + ReLU + MaxPool3d(2) in one pass (the pooled tensor comes from registers).
+//   * backward, last block (up4): the gradient entering its last BatchNorm is dout = dlogits . w_head, an elementwise
+//     function of a 1/64-size tensor, so it is never written: both backward passes recompute it.  head_bwd + reduce +
+//     apply move 7 tensor-sized streams (a -> dout; dout, y; dout, y -> dy); the fused passes move 3 (y; y -> dy) and
+//     produce the head's dw / db on the way (a = relu(bn(y)) is recomputed with bn_apply_relu_kernel's arithmetic).
+//     Every intermediate is rounded exactly where the unfused kernels round it (dout to bf16, a to bf16).
+//   (The same treatment of the encoder blocks — dout = dskip + MaxPool3d-backward(dpool) recomputed in both passes, 5
+//    streams instead of 8 — was built and measured: 0.93 ms against 0.79 ms for maxpool_bwd + bn_bwd at 2 x 128^3 x 64.
+//    Seventeen 16-byte loads per 2x2x2 cell and thread cost 170 registers, i.e. 8 resident warps per SM, and the
+//    recomputed pooling decisions ~3 instructions per byte: bound by issue at low occupancy, not by HBM.  Dropped.)
+
+DEV void cell_decode(uint32_t cell, const FastDiv& cwd, const FastDiv& chd, const FastDiv& cdd, uint32_t& cw,
+                     uint32_t& ch, uint32_t& cd, uint32_t& nb) {
+    uint32_t q = cwd.quot(cell);
+    cw = cell - q * cwd.div;
+    uint32_t r = q;
+    q = chd.quot(r);
+    ch = r - q * chd.div;
+    r = q;
+    q = cdd.quot(r);
+    cd = r - q * cdd.div;
+    nb = q;
+}
+DEV Bf8 bn_relu8(const Bf8& yb, const float (&sc)[8], const float (&sh)[8]) {
+    float f[8];
+    unpack8(yb, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
+    return pack8(f);
+}
+
+// one thread = one 2x2x2 cell (cells cover ceil(extent / 2)) x 8 channels
+__global__ void __launch_bounds__(256) bn_apply_relu_pool_kernel(View y, const float* __restrict__ scale,
+                                                                 const float* __restrict__ shift, View out,
+                                                                 View pooled, FastDiv c8d, FastDiv cwd, FastDiv chd,
+                                                                 FastDiv cdd, uint32_t total) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t cell = c8d.quot(i);
+        const uint32_t c0 = (i - cell * c8d.div) * 8;
+        uint32_t cw, ch, cd, nb;
+        cell_decode(cell, cwd, chd, cdd, cw, ch, cd, nb);
+        const bool full = (2 * cd + 1 < y.d) && (2 * ch + 1 < y.h) && (2 * cw + 1 < y.w);
+        const long long v000 = (((long long)nb * y.d + 2 * cd) * y.h + 2 * ch) * y.w + 2 * cw;
+        float sc[8], sh[8];
+        ldf8(scale + c0, sc);
+        ldf8(shift + c0, sh);
+        if (full) {
+            Bf8 xin[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const long long v = v000 + ((k >> 2) & 1) * y.h * y.w + ((k >> 1) & 1) * y.w + (k & 1);
+                xin[k] = ld8_stream(y.p + v * y.ld + c0);
+            }
+            Bf8 m;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const long long v = v000 + ((k >> 2) & 1) * y.h * y.w + ((k >> 1) & 1) * y.w + (k & 1);
+                const Bf8 a = bn_relu8(xin[k], sc, sh);
+                st8(out.p + v * out.ld + c0, a);
+                if (k == 0) m = a;
+                else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) m.v[j] = max2_nan(m.v[j], a.v[j]);
+                }
+            }
+            const long long ov = (((long long)nb * pooled.d + cd) * pooled.h + ch) * pooled.w + cw;
+            st8(pooled.p + ov * pooled.ld + c0, m);
+        } else {   // odd extent: the cell sticks out of the volume, its voxels belong to no pooling window
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t kd = (k >> 2) & 1, kh = (k >> 1) & 1, kw = k & 1;
+                if (2 * cd + kd < y.d && 2 * ch + kh < y.h && 2 * cw + kw < y.w) {
+                    const long long v = v000 + (long long)kd * y.h * y.w + kh * y.w + kw;
+                    st8(out.p + v * out.ld + c0, bn_relu8(ld8_stream(y.p + v * y.ld + c0), sc, sh));
+                }
+            }
+        }
+    }
+}
+cudaError_t launch_bn_apply_relu_pool(View y, const float* scale, const float* shift, View out, View pooled, int sms,
+                                      cudaStream_t s) {
+    const long long cw = (y.w + 1) / 2, ch = (y.h + 1) / 2, cd = (y.d + 1) / 2;
+    const long long total = y.n * cd * ch * cw * (y.c / 8);
+    if (total >= (1LL << 31)) return cudaErrorInvalidValue;
+    if (total == 0) return cudaSuccess;
+    bn_apply_relu_pool_kernel<<<grid_for(total, 256, sms, 16), 256, 0, s>>>(
+        y, scale, shift, out, pooled, FastDiv((uint32_t)(y.c / 8)), FastDiv((uint32_t)cw), FastDiv((uint32_t)ch),
+        FastDiv((uint32_t)cd), (uint32_t)total);
+    return cudaGetLastError();
+}
+
+// BatchNorm backward with dout = dlogits . w_head recomputed on the fly (the network's last BatchNorm).  Pass 1 also
+// accumulates the head's weight / bias gradients from a = relu(bn(y)) recomputed the same way.  Software-pipelined like
+// bn_bwd_*_kernel (the group carries the voxels' dlogits too).  Pass 1 reads ONE stream and does ~14 instructions per
+// element, so it is bound by instruction issue, not by HBM (ncu: 71 % issue, 32 % DRAM before the diet below).
+constexpr int kHeadU = 4;
+template <int NCLS>
+struct HeadGroup {
+    Bf8 x[kHeadU];
+    float g[kHeadU][NCLS];
+};
+template <int NCLS>
+DEV void head_load(HeadGroup<NCLS>& t, const float* __restrict__ dl, const View& y, long long v0, long long step,
+                   long long nvox, long long nvox_per_n, int c0) {
+#pragma unroll
+    for (int u = 0; u < kHeadU; ++u) {
+        const long long v = v0 + u * step;
+        if (v < nvox) {
+            t.x[u] = ld8_stream(y.p + v * y.ld + c0);
+            if (NCLS == 1) {
+                t.g[u][0] = __ldg(dl + v);   // (N, 1, D, H, W) is the voxel order itself
+            } else {
+                const long long nb = v / nvox_per_n, sp = v - nb * nvox_per_n;
+#pragma unroll
+                for (int k = 0; k < NCLS; ++k) t.g[u][k] = __ldg(dl + (nb * NCLS + k) * nvox_per_n + sp);
+            }
+        }
+    }
+}
+template <int NCLS, bool APPLY>
+__global__ void __launch_bounds__(256, 2) bn_bwd_head_kernel(const float* __restrict__ dl, const float* __restrict__ w,
+                                                             View y, const float* __restrict__ scale,
+                                                             const float* __restrict__ shift,
+                                                             const float* __restrict__ mean,
+                                                             const float* __restrict__ rstd,
+                                                             const float* __restrict__ coef, float* partial, View dy,
+                                                             float* dbias, float* dw, float* db, int c8, int rows,
+                                                             long long nvox, long long nvox_per_n) {
+    extern __shared__ float smem[];
+    const int row = threadIdx.x / c8, cv = threadIdx.x - row * c8;
+    const bool active = row < rows;
+    const int c = (int)y.c;
+    constexpr int NACC = APPLY ? 1 : 2;
+    constexpr int NW = APPLY ? 1 : NCLS;
+    float acc[NACC][8], wacc[NW][8], dbacc[NW];
+#pragma unroll
+    for (int a = 0; a < NACC; ++a)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[a][j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < NW; ++k) {
+        dbacc[k] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) wacc[k][j] = 0.f;
+    }
+    if (active) {
+        const int c0 = cv * 8;
+        float sc[8], sh[8], A[8], B[8], wk[NCLS][8];   // reduce: A = rstd, B = -mean * rstd; apply: A = P, B = Q
+        ldf8(shift + c0, sh);
+#pragma unroll
+        for (int k = 0; k < NCLS; ++k) ldf8(w + k * c + c0, wk[k]);
+        if (APPLY) {
+            bwd_apply_consts(scale, mean, rstd, coef, cv, sc, A, B);
+        } else {
+            ldf8(scale + c0, sc);
+            ldf8(rstd + c0, A);
+            ldf8(mean + c0, B);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) B[j] = -B[j] * A[j];
+        }
+        const long long step = (long long)gridDim.x * rows;
+        auto compute = [&](const HeadGroup<NCLS>& t, long long v0) {
+#pragma unroll
+            for (int u = 0; u < kHeadU; ++u) {
+                const long long v = v0 + u * step;
+                if (v >= nvox) continue;
+                float x[8], o[8], gq[8], z[8];
+                unpack8(t.x[u], x);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    o[j] = 0.f;
+                    z[j] = fmaf(x[j], sc[j], sh[j]);
+                }
+#pragma unroll
+                for (int k = 0; k < NCLS; ++k)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[j] = fmaf(t.g[u][k], wk[k][j], o[j]);
+                unpack8(pack8(o), gq);   // dout of this voxel, rounded to bf16 as head_bwd_kernel stores it
+                if (APPLY) {
+                    float r[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        r[j] = fmaf(sc[j], z[j] > 0.f ? gq[j] : 0.f, fmaf(x[j], A[j], B[j]));
+                    const Bf8 ob = pack8(r);
+                    st8(dy.p + v * dy.ld + c0, ob);
+                    unpack8(ob, r);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[0][j] += r[j];
+                } else {
+                    float a[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) a[j] = fmaxf(z[j], 0.f);
+                    unpack8(pack8(a), a);   // the head's input as bn_apply_relu_kernel stored it
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float gm = z[j] > 0.f ? gq[j] : 0.f;
+                        acc[0][j] += gm;
+                        acc[NACC - 1][j] = fmaf(gm, fmaf(x[j], A[j], B[j]), acc[NACC - 1][j]);
+                    }
+#pragma unroll
+                    for (int k = 0; k < NW; ++k) {
+                        if (cv == 0) dbacc[k] += t.g[u][k];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) wacc[k][j] = fmaf(t.g[u][k], a[j], wacc[k][j]);
+                    }
+                }
+            }
+        };
+        HeadGroup<NCLS> ga, gb;
+        long long v0 = (long long)blockIdx.x * rows + row;
+        const long long big = kHeadU * step;
+        if (v0 < nvox) head_load<NCLS>(ga, dl, y, v0, step, nvox, nvox_per_n, c0);
+        while (v0 < nvox) {
+            const long long v1 = v0 + big;
+            if (v1 < nvox) head_load<NCLS>(gb, dl, y, v1, step, nvox, nvox_per_n, c0);
+            compute(ga, v0);
+            if (v1 >= nvox) break;
+            const long long v2 = v1 + big;
+            if (v2 < nvox) head_load<NCLS>(ga, dl, y, v2, step, nvox, nvox_per_n, c0);
+            compute(gb, v1);
+            v0 = v2;
+        }
+    }
+    if (APPLY) {
+        if (dbias) block_reduce_store<NACC>(acc, c8, rows, row, cv, active, smem, dbias, (int)y.c, true);
+        return;
+    }
+    block_reduce_store<NACC>(acc, c8, rows, row, cv, active, smem, partial + (long long)blockIdx.x * y.c * NACC,
+                             (int)y.c, false);
+    __syncthreads();
+    // head dw[k][c] / db[k]: smem [rows][c8][NW * 8], as head_bwd_kernel
+    if (active) {
+#pragma unroll
+        for (int k = 0; k < NW; ++k)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) smem[((row * c8 + cv) * NW + k) * 8 + j] = wacc[k][j];
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < c * NW; t += blockDim.x) {
+        const int k = t / c, ch = t - k * c;
+        float sum = 0.f;
+        for (int r = 0; r < rows; ++r) sum += smem[((r * c8 + (ch >> 3)) * NW + k) * 8 + (ch & 7)];
+        atomicAdd(dw + k * c + ch, sum);
+    }
+    __syncthreads();
+    if (active && cv == 0) {
+#pragma unroll
+        for (int k = 0; k < NW; ++k) smem[row * NW + k] = dbacc[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < NW) {
+        float sum = 0.f;
+        for (int r = 0; r < rows; ++r) sum += smem[r * NW + threadIdx.x];
+        atomicAdd(db + threadIdx.x, sum);
+    }
+}
+template <int NCLS>
+static cudaError_t bn_bwd_head_launch(bool apply, const float* dl, const float* w, View y, const float* scale,
+                                      const float* shift, const float* mean, const float* rstd, const float* coef,
+                                      float* partial, int* nblk, View dy, float* dbias, float* dw, float* db,
+                                      cudaStream_t s) {
+    const LaneMap m = lane_map(y.c);
+    const long long nvox = y.voxels();
+    long long blocks = (nvox + m.rows * 8LL - 1) / (m.rows * 8LL);
+    const long long cap = apply ? 148 * 8 : kBwdMaxBlocks;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    if (apply) {
+        bn_bwd_head_kernel<NCLS, true><<<(int)blocks, 256, reduce_smem_bytes(m, 1), s>>>(
+            dl, w, y, scale, shift, mean, rstd, coef, nullptr, dy, dbias, nullptr, nullptr, m.c8, m.rows, nvox,
+            y.d * y.h * y.w);
+    } else {
+        *nblk = (int)blocks;
+        size_t smem = reduce_smem_bytes(m, 2);
+        const size_t head = (size_t)m.rows * m.c8 * NCLS * 8 * sizeof(float);
+        if (head > smem) smem = head;
+        bn_bwd_head_kernel<NCLS, false><<<(int)blocks, 256, smem, s>>>(dl, w, y, scale, shift, mean, rstd, nullptr,
+                                                                      partial, y, nullptr, dw, db, m.c8, m.rows, nvox,
+                                                                      y.d * y.h * y.w);
+    }
+    return cudaGetLastError();
+}
+cudaError_t launch_bn_bwd_head(bool apply, const float* dlogits, const float* w, int ncls, View y, const float* scale,
+                               const float* shift, const float* mean, const float* rstd, const float* coef,
+                               float* partial, int* nblk, View dy, float* dbias, float* dw, float* db,
+                               cudaStream_t s) {
+#define B200_HEAD_CASE(N)                                                                                            \
+    case N:                                                                                                          \
+        return bn_bwd_head_launch<N>(apply, dlogits, w, y, scale, shift, mean, rstd, coef, partial, nblk, dy, dbias, \
+                                     dw, db, s)
+    switch (ncls) {
+        B200_HEAD_CASE(1);
+        B200_HEAD_CASE(2);
+        B200_HEAD_CASE(3);
+        B200_HEAD_CASE(4);
+        default: return cudaErrorInvalidValue;
+    }
+#undef B200_HEAD_CASE
 }
 
 // ------------------------------------------------------------------------------------------------ loss

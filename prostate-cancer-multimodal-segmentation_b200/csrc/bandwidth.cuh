@@ -52,6 +52,11 @@ cudaError_t launch_bn_bwd_finalize(const float* partial, int nblk, int c, long l
                                    float* dbeta, float* coef, cudaStream_t s);
 cudaError_t launch_bn_bwd_apply(View dout, View y, const float* scale, const float* shift, const float* mean,
                                 const float* rstd, const float* coef, View dy, float* dbias, cudaStream_t s);
+cudaError_t launch_bn_apply_relu_pool(View y, const float* scale, const float* shift, View out, View pooled, int sms,
+                                      cudaStream_t s);
+cudaError_t launch_bn_bwd_head(bool apply, const float* dlogits, const float* w, int ncls, View y, const float* scale,
+                               const float* shift, const float* mean, const float* rstd, const float* coef,
+                               float* partial, int* nblk, View dy, float* dbias, float* dw, float* db, cudaStream_t s);
 cudaError_t launch_maxpool_fwd(View x, View y, int sms, cudaStream_t s);
 cudaError_t launch_maxpool_bwd(View x, View dy, const View* dskip, View dx, int sms, cudaStream_t s);
 cudaError_t launch_head_fwd(View x, const float* w, const float* b, int ncls, float* logits, float* probs,

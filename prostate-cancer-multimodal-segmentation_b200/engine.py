@@ -44,6 +44,10 @@ def _slot_view(flat: torch.Tensor, off: int, p) -> torch.Tensor:
     return flat[off:off + n].view(p.shape)
 
 
+# A/B switch for tools/ab_fused.py only: False runs the unfused chains (bn_apply_relu + maxpool3d_fwd, head_bwd +
+# bn_bwd) the fused BatchNorm passes replace; same results, more HBM traffic.
+FUSE_BN_PASSES = True
+
 _SPLITK_WS = {}
 
 
@@ -185,7 +189,7 @@ class _DoubleConv:
         self.p2.pack()
 
     # ---- forward
-    def _conv_bn_relu_train(self, xin: ActView, pack, bn, out: ActView):
+    def _conv_bn_relu_train(self, xin: ActView, pack, bn, out: ActView, pool_out=None):
         n, d, h, w, _ = xin.shape
         dev = xin.t.device
         cout = pack.cout
@@ -212,7 +216,12 @@ class _DoubleConv:
                         bn.running_mean if bn.track_running_stats else None,
                         bn.running_var if bn.track_running_stats else None, vec[0], vec[1], vec[2], vec[3],
                         num_batches_tracked=nbt)
-        ops.bn_apply_relu(y, vec[2], vec[3], out)
+        if pool_out is not None and FUSE_BN_PASSES:   # encoder block: the next level's MaxPool3d(2) in the same pass
+            ops.bn_apply_relu_pool(y, vec[2], vec[3], out, pool_out)
+        else:
+            ops.bn_apply_relu(y, vec[2], vec[3], out)
+            if pool_out is not None:
+                ops.maxpool3d_fwd(out, pool_out)
         return y, vec
 
     def _conv_bn_relu_eval(self, xin: ActView, pack, bn, out: ActView):
@@ -224,18 +233,21 @@ class _DoubleConv:
         ws = None if pack.im2col else _splitk_workspace(dev, n, d, h, w, pack.cout)
         pack.fprop(xin, None, out, None, ops.EPI_AFFINE_RELU, vec[0], vec[1], workspace=ws)
 
-    def forward(self, xin: ActView, out: ActView, training: bool):
+    def forward(self, xin: ActView, out: ActView, training: bool, pool_out=None):
+        """pool_out: view that receives MaxPool3d(2)(out) (models/unet3d.py:80, the next level's input)"""
         n, d, h, w, _ = xin.shape
         dev = xin.t.device
         a1 = ActView(new_act(n, d, h, w, self.cout, dev))
         if not (training or not self.bn1.track_running_stats):
             self._conv_bn_relu_eval(xin, self.p1, self.bn1, a1)
             self._conv_bn_relu_eval(a1, self.p2, self.bn2, out)
+            if pool_out is not None:
+                ops.maxpool3d_fwd(out, pool_out)
             return None
         st = _DCState()
         st.xin, st.a1 = xin, a1
         st.y1, st.bn1 = self._conv_bn_relu_train(xin, self.p1, self.bn1, a1)
-        st.y2, st.bn2 = self._conv_bn_relu_train(a1, self.p2, self.bn2, out)
+        st.y2, st.bn2 = self._conv_bn_relu_train(a1, self.p2, self.bn2, out, pool_out)
         return st
 
     # ---- backward
@@ -243,13 +255,21 @@ class _DoubleConv:
         """dout: gradient w.r.t. the block output; dxin: view to receive the input gradient (None: not needed).
         Weight gradients are launched through `side` (runs them on the side stream, see Engine._Side).
         taps (parity tooling): dict that receives every intermediate gradient view of the block."""
-        n, d, h, w, _ = dout.shape
-        dev = dout.t.device
+        n, d, h, w, _ = st.y2.shape
+        dev = st.y2.t.device
         g = grads
         # second conv
         dy2 = ActView(new_act(n, d, h, w, self.cout, dev))
-        ops.bn_bwd(dout, st.y2, st.bn2[2], st.bn2[3], st.bn2[0], st.bn2[1], self.bn2.weight.data, scratch.partial,
-                   scratch.coef, g(self.bn2.weight), g(self.bn2.bias), dy2, g(self.conv2.bias))
+        bn2 = (st.y2, st.bn2[2], st.bn2[3], st.bn2[0], st.bn2[1], self.bn2.weight.data, scratch.partial, scratch.coef,
+               g(self.bn2.weight), g(self.bn2.bias), dy2, g(self.conv2.bias))
+        if isinstance(dout, HeadGrad) and not FUSE_BN_PASSES:
+            t = ActView(new_act(n, d, h, w, self.cout, dev))
+            ops.head_bwd(dout.act, dout.w, dout.dlogits, t, dout.dw, dout.db)
+            dout = t
+        if isinstance(dout, HeadGrad):   # dout = dlogits . w_head, never written; head dw / db on the way
+            ops.bn_bwd_head(dout.dlogits, dout.w, *bn2, dout.dw, dout.db)
+        else:
+            ops.bn_bwd(dout, *bn2)
         # dgrad first: it is on the critical chain (the next BatchNorm backward needs da1) and must win the SMs; the
         # weight gradient then runs beside that BatchNorm backward
         da1 = ActView(new_act(n, d, h, w, self.cout, dev))
@@ -264,7 +284,17 @@ class _DoubleConv:
             self.p1.dgrad(dy1, dxin, workspace=_splitk_workspace(dev, n, d, h, w, dxin.c))
         side.run(lambda: self.p1.wgrad(st.xin, dy1, g(self.conv1.weight)), keep=(st.xin, dy1))
         if taps is not None:
-            taps[name] = {"dout": dout, "dy2": dy2, "da1": da1, "dy1": dy1, "dx": dxin}
+            taps[name] = {"dout": dout if isinstance(dout, ActView) else dout.materialized, "dy2": dy2, "da1": da1,
+                          "dy1": dy1, "dx": dxin}
+
+
+class HeadGrad:
+    """Gradient w.r.t. the last block's output that is not materialised: dlogits (N, ncls, D, H, W) . w (ncls, C); dw /
+    db are the head's gradient buffers (accumulated by the BatchNorm-backward reduce pass)."""
+    __slots__ = ("dlogits", "w", "dw", "db", "act", "materialized")
+
+    def __init__(self, dlogits, w, dw, db, act=None, materialized=None):
+        self.dlogits, self.w, self.dw, self.db, self.act, self.materialized = dlogits, w, dw, db, act, materialized
 
 
 class _Side:
@@ -471,19 +501,17 @@ class Engine:
         # encoder: skip of level k lives in the lower half of cats[k]
         cats = [new_act(n, *dims[k], 2 * ch[k], dev) for k in range(4)]
         dcs = {}
-        dcs["inc"] = self.inc.forward(x0, ActView(cats[0], 0, ch[0]), training)
-        pooled = []
+        # (the MaxPool3d(2) input of level k + 1 is produced by level k's last BatchNorm + ReLU pass)
+        pooled = [ActView(new_act(n, *dims[k], ch[k - 1], dev)) for k in range(1, 5)]
+        dcs["inc"] = self.inc.forward(x0, ActView(cats[0], 0, ch[0]), training, pool_out=pooled[0])
         bottom = None
         for k in range(1, 5):
-            src = ActView(cats[k - 1], 0, ch[k - 1])
-            pk = ActView(new_act(n, *dims[k], ch[k - 1], dev))
-            ops.maxpool3d_fwd(src, pk)
-            pooled.append(pk)
             if k < 4:
                 out = ActView(cats[k], 0, ch[k])
             else:
                 bottom = out = ActView(new_act(n, *dims[4], ch[4], dev))
-            dcs[f"down{k}"] = self.downs[k - 1].forward(pk, out, training)
+            dcs[f"down{k}"] = self.downs[k - 1].forward(pooled[k - 1], out, training,
+                                                        pool_out=pooled[k] if k < 4 else None)
         # decoder
         cur = bottom
         dec_in, pads = [], []
@@ -593,13 +621,17 @@ class Engine:
                 o, cnt = self._slots[id(p)]
                 side.sync_point(lambda: sync.ready(o + cnt))
 
-        dcur = ActView(new_act(n, *dims[0], ch[0], dev))
-        ops.head_bwd(tape.last, m.outc.weight.data.view(m.n_classes, -1), dlogits, dcur,
-                     g(m.outc.weight).view(m.n_classes, -1), g(m.outc.bias))
+        # the head's input gradient dlogits . w is not written: the last block's BatchNorm backward recomputes it and
+        # accumulates the head's dw / db (ops.bn_bwd_head); their bucket is marked with that block's
+        w_head = m.outc.weight.data.view(m.n_classes, -1)
+        dcur = HeadGrad(dlogits, w_head, g(m.outc.weight).view(m.n_classes, -1), g(m.outc.bias),
+                        act=None if FUSE_BN_PASSES else tape.last)
+        if gt is not None:   # parity tooling: the tensor b200_head_bwd writes for the same inputs
+            dcur.materialized = ActView(new_act(n, *dims[0], ch[0], dev))
+            ops.head_bwd(tape.last, w_head, dlogits, dcur.materialized, torch.zeros_like(w_head),
+                         torch.zeros_like(m.outc.bias.data))
+            gt["head"] = {"dx": dcur.materialized}
         tape.last = None
-        mark(m.outc.bias)
-        if gt is not None:
-            gt["head"] = {"dx": dcur}
         dcats = [None] * 4
         for j in (4, 3, 2, 1):
             k = 4 - j

@@ -291,6 +291,30 @@ def bn_bwd(dout: ActView, y: ActView, scale, shift, mean, rstd, gamma, partial, 
                                 dy.ref, ptr(dbias), s), "bn_bwd_apply")
 
 
+def bn_apply_relu_pool(y: ActView, scale, shift, out: ActView, pooled: ActView):
+    """out = relu(y * scale + shift) and pooled = MaxPool3d(2)(out) in one pass (encoder blocks)"""
+    _launched(1)
+    check(_lib.load().b200_bn_apply_relu_pool(y.ref, ptr(scale), ptr(shift), out.ref, pooled.ref, stream_ptr()),
+          "bn_apply_relu_pool")
+
+
+def bn_bwd_head(dlogits, w, y: ActView, scale, shift, mean, rstd, gamma, partial, coef, dgamma, dbeta, dy: ActView,
+                dbias, dw, db):
+    """BatchNorm3d(train)+ReLU backward of the network's last BatchNorm from the head's dlogits (N, ncls, D, H, W): the
+    head's input gradient is recomputed in both passes, the head's dw / db are accumulated by the first."""
+    _launched(3)
+    lib = _lib.load()
+    nblk = C.c_int(0)
+    s = stream_ptr()
+    ncls = w.shape[0]
+    check(lib.b200_bn_bwd_reduce_head(ptr(dlogits), ptr(w), ncls, y.ref, ptr(scale), ptr(shift), ptr(mean), ptr(rstd),
+                                      ptr(partial), C.byref(nblk), ptr(dw), ptr(db), s), "bn_bwd_reduce_head")
+    check(lib.b200_bn_bwd_finalize(ptr(partial), nblk.value, y.c, y.voxels, ptr(dgamma), ptr(dbeta), ptr(coef), s),
+          "bn_bwd_finalize")
+    check(lib.b200_bn_bwd_apply_head(ptr(dlogits), ptr(w), ncls, y.ref, ptr(scale), ptr(shift), ptr(mean), ptr(rstd),
+                                     ptr(coef), dy.ref, ptr(dbias), s), "bn_bwd_apply_head")
+
+
 def maxpool3d_fwd(x: ActView, y: ActView):
     _launched(1)
     check(_lib.load().b200_maxpool3d_fwd(x.ref, y.ref, stream_ptr()), "maxpool3d_fwd")
@@ -484,7 +508,8 @@ def _op(fn):
 
 for _n in ("pack_input", "im2col_input", "pack_rows", "pack_conv_weight", "pack_convt_weight", "conv3d_fprop",
            "conv1_fprop", "conv3d_dgrad", "conv3d_wgrad", "conv1_wgrad", "conv1_direct_fprop", "conv1_direct_wgrad", "convt2x_fwd", "convt2x_dgrad",
-           "convt2x_wgrad", "bn_finalize", "bn_fold_eval", "bn_apply_relu", "bn_bwd", "maxpool3d_fwd",
+           "convt2x_wgrad", "bn_finalize", "bn_fold_eval", "bn_apply_relu", "bn_bwd", "bn_apply_relu_pool", "bn_bwd_head",
+           "maxpool3d_fwd",
            "maxpool3d_bwd", "head_fwd", "head_bwd", "loss_fwd", "loss_bwd", "adam_step", "cast_bf16", "sumsq",
            "fill_zero", "channel_sum", "channel_sum_box", "window_gather", "window_accumulate", "window_finalize",
            "resample3d", "minmax_normalize_", "seg_counts"):

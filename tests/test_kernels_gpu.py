@@ -316,6 +316,71 @@ def test_batchnorm_relu_fwd_bwd(ops, cuda_dev, shape):
     assert torch.allclose(dbias, from_act(dyv).sum((0, 2, 3, 4)), rtol=1e-3, atol=1e-2)
 
 
+def _bn_setup(ops, dev, n, c, d, h, w, seed):
+    """a conv output y, BatchNorm batch statistics of it (mean, rstd, scale, shift) and the unfused relu(bn(y))"""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    y = bf16_round(torch.randn(n, c, d, h, w, generator=g) * 1.5 + 0.3).to(dev)
+    gamma = (torch.rand(c, generator=g) + 0.5).to(dev)
+    beta = (torch.randn(c, generator=g) * 0.2).to(dev)
+    yd = y.double()
+    stats = torch.stack([yd.sum((0, 2, 3, 4)), (yd * yd).sum((0, 2, 3, 4))], -1).float().reshape(1, c, 2).contiguous()
+    mean, rstd, scale, shift = (torch.empty(c, device=dev) for _ in range(4))
+    ops.bn_finalize(stats, 1, n * d * h * w, c, gamma, beta, 1e-5, 0.1, None, None, mean, rstd, scale, shift)
+    yv = to_act(ops, y)
+    av = empty_act(ops, n, c, d, h, w, dev)
+    ops.bn_apply_relu(yv, scale, shift, av)
+    return g, yv, av, gamma, mean, rstd, scale, shift
+
+
+def _bn_bwd_buffers(ops, dev, n, c, d, h, w):
+    return (torch.empty(ops.bn_bwd_max_blocks(), c, 2, device=dev), torch.empty(c, 2, device=dev),
+            torch.zeros(c, device=dev), torch.zeros(c, device=dev), empty_act(ops, n, c, d, h, w, dev),
+            torch.zeros(c, device=dev))
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 8, 8, 8), (1, 32, 5, 7, 9), (1, 128, 6, 4, 10), (2, 48, 4, 6, 3),
+                                   (1, 512, 2, 4, 2)])
+def test_fused_bn_relu_pool_equals_the_unfused_chain(ops, cuda_dev, shape):
+    """b200_bn_apply_relu_pool == bn_apply_relu + maxpool3d_fwd bit for bit (odd extents: cells sticking out of the
+    volume)"""
+    n, c, d, h, w = shape
+    g, yv, av, gamma, mean, rstd, scale, shift = _bn_setup(ops, cuda_dev, n, c, d, h, w, 23)
+    pv = empty_act(ops, n, c, d // 2, h // 2, w // 2, cuda_dev)
+    ops.maxpool3d_fwd(av, pv)
+    av2 = empty_act(ops, n, c, d, h, w, cuda_dev)
+    pv2 = empty_act(ops, n, c, d // 2, h // 2, w // 2, cuda_dev)
+    ops.bn_apply_relu_pool(yv, scale, shift, av2, pv2)
+    torch.cuda.synchronize()
+    assert torch.equal(from_act(av2), from_act(av))
+    assert torch.equal(from_act(pv2), from_act(pv))
+    assert torch.equal(from_act(pv2), F.max_pool3d(from_act(av), 2))
+
+
+@pytest.mark.parametrize("ncls", [1, 2, 3])
+def test_fused_bn_head_passes_equal_the_unfused_chain(ops, cuda_dev, ncls):
+    """b200_bn_bwd_{reduce,apply}_head == head_bwd + bn_bwd (dy, dgamma, dbeta, conv-bias gradient, head dw / db)"""
+    n, c, d, h, w = 2, 64, 6, 5, 7
+    g, yv, av, gamma, mean, rstd, scale, shift = _bn_setup(ops, cuda_dev, n, c, d, h, w, 29)
+    wt = (torch.randn(ncls, c, generator=g) * 0.2).to(cuda_dev)
+    dl = torch.randn(n, ncls, d, h, w, generator=g).to(cuda_dev)
+    dout = empty_act(ops, n, c, d, h, w, cuda_dev)
+    dw, db = torch.zeros(ncls, c, device=cuda_dev), torch.zeros(ncls, device=cuda_dev)
+    ops.head_bwd(av, wt, dl, dout, dw, db)
+    partial, coef, dgamma, dbeta, dyv, dbias = _bn_bwd_buffers(ops, cuda_dev, n, c, d, h, w)
+    ops.bn_bwd(dout, yv, scale, shift, mean, rstd, gamma, partial, coef, dgamma, dbeta, dyv, dbias)
+    partial2, coef2, dgamma2, dbeta2, dyv2, dbias2 = _bn_bwd_buffers(ops, cuda_dev, n, c, d, h, w)
+    dw2, db2 = torch.zeros(ncls, c, device=cuda_dev), torch.zeros(ncls, device=cuda_dev)
+    ops.bn_bwd_head(dl, wt, yv, scale, shift, mean, rstd, gamma, partial2, coef2, dgamma2, dbeta2, dyv2, dbias2, dw2,
+                    db2)
+    torch.cuda.synchronize()
+    assert torch.allclose(dw2, dw, rtol=1e-4, atol=1e-4) and torch.allclose(db2, db, rtol=1e-4, atol=1e-4)
+    assert torch.allclose(dgamma2, dgamma, rtol=1e-4, atol=1e-4)
+    assert torch.allclose(dbeta2, dbeta, rtol=1e-4, atol=1e-4)
+    a, b = from_act(dyv2), from_act(dyv)
+    assert (a != b).float().mean().item() < 1e-3 and rel_l2(a, b) < 1e-4
+    assert torch.allclose(dbias2, dbias, rtol=1e-3, atol=1e-2)
+
+
 @pytest.mark.parametrize("shape", [(2, 64, 8, 8, 8), (1, 16, 5, 7, 9), (1, 128, 2, 4, 6)])
 def test_maxpool_fwd_bwd_bit_exact(ops, cuda_dev, shape):
     n, c, d, h, w = shape
