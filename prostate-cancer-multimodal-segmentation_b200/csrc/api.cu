@@ -320,8 +320,10 @@ static int launch_igemm(IgemmParams& p, cudaStream_t s, int* grid_out) {
     if (sms <= 0) return fail(B200_ERR_CUDA, "no CUDA device");
     static SmemOptIn optin, optin_i2c;
     if (p.stages < 2) return fail(B200_ERR_UNSUPPORTED_SHAPE, "igemm: tile does not fit shared memory");
-    // direct first-layer form: a short ring (one tile + one block ahead) is enough, the builders pace the kernel
-    if (p.x_src && p.stages > 4) p.stages = 4;
+    // direct first-layer form: a brick takes kc_blocks consecutive ring slots at once; two bricks' worth is enough
+    if (p.x_src && p.stages > 2 * p.kc_blocks) p.stages = 2 * p.kc_blocks;
+    if (p.x_src && p.stages < p.kc_blocks)
+        return fail(B200_ERR_UNSUPPORTED_SHAPE, "igemm (direct first layer): the operand image does not fit shared memory");
     const size_t smem = igemm_smem(p.stages, p.a_stage_bytes, b_stage_bytes(p), epi_staging_bytes(p));
     if (p.x_src) {   // A built in shared memory by warps 8..15 (512 threads)
         const int rc_attr = ensure_smem(igemm_im2col5_kernel, (int)smem, optin_i2c);
@@ -329,7 +331,7 @@ static int launch_igemm(IgemmParams& p, cudaStream_t s, int* grid_out) {
         const long long tiles_ = (long long)p.nbw * p.nbh * p.nbd * p.nbatch * p.n_tiles;
         const int grid_ = (int)(tiles_ < sms ? tiles_ : sms);
         if (grid_out) *grid_out = grid_;
-        p.ablate = 0;
+        p.ablate = g_dev_igemm_ablate;   // development library only
         igemm_im2col5_kernel<<<grid_, kIm2colThreads, smem, s>>>(p);
         CUDA_TRY(cudaGetLastError());
         return 0;
@@ -972,9 +974,27 @@ static int log2_exact(int v) {
     return l;
 }
 // bricks of the direct first-layer kernels: as everywhere else (128 voxels, fewest bricks)
-static Brick choose_brick_direct(long long w, long long h, long long d) { return choose_brick(w, h, d); }
+// bricks of the direct first-layer kernels are at least 8 voxels wide: a 16-byte chunk of the voxel-contiguous operand
+// image (igemm.cu, Im2colImage) is 8 consecutive voxels of one image row
+static Brick choose_brick_direct(long long w, long long h, long long d) {
+    Brick best{};
+    long long best_n = -1;
+    for (int lw = 7; lw >= 3; --lw)
+        for (int lh = 7 - lw; lh >= 0; --lh) {
+            const int ldp = 7 - lw - lh;
+            const long long tw = 1LL << lw, th = 1LL << lh, td = 1LL << ldp;
+            const long long nb = ((w + tw - 1) / tw) * ((h + th - 1) / th) * ((d + td - 1) / td);
+            if (best_n < 0 || nb < best_n) {
+                best_n = nb;
+                best.tw = (int)tw; best.th = (int)th; best.td = (int)td;
+                best.lw = lw; best.lh = lh; best.ld = ldp;
+                best.nbw = (w + tw - 1) / tw; best.nbh = (h + th - 1) / th; best.nbd = (d + td - 1) / td;
+            }
+        }
+    return best;
+}
 extern "C" int b200_conv1_direct_supported(int64_t c, int64_t cout, int64_t w) {
-    (void)w;   // (any row length: the builder warps read the fp32 input with plain loads)
+    (void)w;   // (any row length: rows that are not 16-byte aligned are read with scalar loads)
     return (c == 5 && cout % 16 == 0 && cout >= 16 && cout <= 256) ? 1 : 0;   // the 5-modality input of the reference
 }
 extern "C" int b200_conv1_direct_stat_rows(int64_t n, int64_t d, int64_t h, int64_t w, int64_t cout) {

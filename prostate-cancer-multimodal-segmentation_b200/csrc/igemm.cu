@@ -24,79 +24,102 @@ struct PipeState {
 
 
 // ------------------------------------------------------------------------------------------------
-// im2col rows built in shared memory (first layer, CIN modalities): 64 columns [64*KC, 64*KC+64) of the 128 rows of one
-// brick, written as the SWIZZLE_128B K-major box a TMA load of the (never materialised) im2col matrix would have
-// produced: row r at r*128 B, its 16-byte chunk j at ((j ^ (r & 7)) << 4).  256 producer threads: thread pt builds
-// columns 32*(pt >> 7) .. +32 of row pt & 127; every (channel, tap) of a column is a compile-time constant.
+// First-layer operand built in shared memory (CIN modalities, K = 27 * CIN im2col columns, never materialised).
+// The image is VOXEL-contiguous: one 128-byte row per im2col column k = c*27 + kd*9 + kh*3 + kw holding 64 consecutive
+// voxels of the brick (SWIZZLE_128B: 16-byte chunk j of row r at ((j ^ (r & 7)) << 4)), two such halves for the 128
+// voxels of a brick.  The tensor core reads it as an MN-major A operand in the forward GEMM (M = voxels) and as a
+// K-major B operand in the weight-gradient GEMM (K = voxels) — the same bytes.
+// Why this layout: bricks are at least 8 voxels wide, so a 16-byte chunk is 8 consecutive voxels of one image row and
+// the three kw columns of a (channel, kd, kh) are the same 10 input floats shifted by one — one task loads them once
+// (two aligned 16-byte loads + the two halo floats) and writes three chunks.  45 x 16 tasks per brick, ~50 instructions
+// each, against one thread per voxel gathering 72 predicated scalars (~1000 instructions per thread and brick, which
+// made both first-layer kernels issue-bound: ncu 1.9 IPC, tensor pipe 7 %).
 // ------------------------------------------------------------------------------------------------
 struct BrickGeom {
     int tw_log2, th_log2, W, H, D, nbatch;
 };
-// Words (two bf16 columns each) one builder thread holds for its row: thread half h owns columns 32h .. 32h+31 of each
-// 64-column block, clipped to the padded row length KPAD.  All global loads of a tile are issued before the first
-// shared-memory store (the kernel's dynamic shared memory leaves little L1, so first touches are L2 round trips: they
-// must all be in flight together, not eight at a time between stores).  Every (channel, tap) of a column is a
-// compile-time constant; voxels outside the volume read as zero (the convolution's padding).
-// (A TMA-loaded fp32 halo brick feeding these rows from shared memory was tried: the 5-D fp32 tile load raised an
-//  illegal-instruction fault on sm_100a with driver 580 and was dropped; with the loads removed altogether the kernels
-//  run 6 % / 17 % faster, which bounds what any staging scheme could gain — they are epilogue- / latency-bound.)
 template <int CIN>
-struct Im2colRow {
-    static constexpr int K = 27 * CIN, KPAD = (K + 15) / 16 * 16, KC = (KPAD + 63) / 64;
-    static constexpr int kMaxWords = 16 * KC;
-    uint32_t wd[kMaxWords];
-    uint32_t row_off, sw;
-
-    template <int HALF>
-    DEV void load_half(const float* __restrict__ xb, long long plane, int hw, int W, const bool (&okdh)[9],
-                       const bool (&okw)[3]) {
-        auto tap = [&](int k) -> float {
-            if (k >= K) return 0.f;
-            const int c = k / 27, t = k % 27, kd = t / 9, kh = (t / 3) % 3, kw = t % 3;
-            if (!(okdh[kd * 3 + kh] && okw[kw])) return 0.f;
-            return __ldg(xb + ((long long)c * plane + (kd - 1) * hw + (kh - 1) * W + (kw - 1)));
-        };
-#pragma unroll
-        for (int kc = 0; kc < KC; ++kc)
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int k0 = 64 * kc + 32 * HALF + 2 * j;
-                if (k0 < KPAD) wd[kc * 16 + j] = pack_bf16x2(tap(k0), tap(k0 + 1));
-            }
-    }
-    // brick row `pt & 127` of the brick at (w0, h0, d0, nb); pt >> 7 (warp-uniform) selects the column half
-    DEV void load(const float* __restrict__ x, int pt, int w0, int h0, int d0, int nb, const BrickGeom& g) {
-        const int row = pt & 127;
-        const int rw = row & ((1 << g.tw_log2) - 1);
-        const int rh = (row >> g.tw_log2) & ((1 << g.th_log2) - 1);
-        const int rd = row >> (g.tw_log2 + g.th_log2);
-        const int w = w0 + rw, h = h0 + rh, d = d0 + rd;
-        const bool vox_ok = w < g.W && h < g.H && d < g.D && nb < g.nbatch;
+struct Im2colImage {
+    static constexpr int K = 27 * CIN, KPAD = (K + 15) / 16 * 16, KC = (KPAD + 63) / 64, NTRIPLE = 9 * CIN;
+    static constexpr int kBuilders = 256;                                 // threads that build the image
+    static constexpr int kTasks = (NTRIPLE * 16 + kBuilders - 1) / kBuilders;   // tasks per thread and brick
+    // One task = 8 consecutive voxels (chunk cj) of one (channel, kd, kh): f = x[w - 1 .. w + 8] of the source row, zero
+    // outside the volume (the convolution's padding); nvalid = voxels of the chunk inside the volume (partial bricks
+    // get zero rows: the weight-gradient GEMM sums over voxels).  The loads of a whole brick are issued together and
+    // consumed one brick later (see the builders): a load is an L2 / HBM round trip of ~1 us, as long as a brick takes.
+    struct Regs {
+        float f[kTasks][10];
+        int nvalid[kTasks];
+    };
+    static DEV void load(Regs& r, const float* __restrict__ x, int pt, int w0, int h0, int d0, int nb,
+                         const BrickGeom& g) {
         const int hw = g.H * g.W;
         const long long plane = (long long)g.D * hw;
-        const float* xb = x + ((long long)nb * CIN * plane + ((long long)d * hw + h * g.W + w));
-        bool okdh[9], okw[3];
+        const bool vec_ok = (g.W & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+        const int wmask = (1 << g.tw_log2) - 1, hmask = (1 << g.th_log2) - 1;
 #pragma unroll
-        for (int i = 0; i < 9; ++i)
-            okdh[i] = vox_ok && (unsigned)(d + i / 3 - 1) < (unsigned)g.D && (unsigned)(h + i % 3 - 1) < (unsigned)g.H;
+        for (int i = 0; i < kTasks; ++i) {
+            const int t = pt + i * kBuilders;
+            float (&f)[10] = r.f[i];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) okw[i] = (unsigned)(w + i - 1) < (unsigned)g.W;
-        row_off = row * 128;
-        sw = row & 7;
-        if ((pt >> 7) == 0) load_half<0>(xb, plane, hw, g.W, okdh, okw);
-        else load_half<1>(xb, plane, hw, g.W, okdh, okw);
-    }
-    // 64-column block KCI of the row into the SWIZZLE_128B K-major box at `box`
-    template <int KCI>
-    DEV void store(uint32_t box, int pt) const {
-        const uint32_t half = pt >> 7;
+            for (int e = 0; e < 10; ++e) f[e] = 0.f;
+            r.nvalid[i] = 0;
+            if (t >= NTRIPLE * 16) continue;
+            const int q = t >> 4, cj = t & 15;
+            const int c = q / 9, r9 = q - 9 * c, kd = r9 / 3, kh = r9 - 3 * kd;
+            const int m0 = cj * 8;
+            const int w = w0 + (m0 & wmask), h = h0 + ((m0 >> g.tw_log2) & hmask);
+            const int d = d0 + (m0 >> (g.tw_log2 + g.th_log2));
+            const int hs = h + kh - 1, ds = d + kd - 1;
+            const bool row_ok = nb < g.nbatch && w < g.W && h < g.H && d < g.D && (unsigned)hs < (unsigned)g.H &&
+                                (unsigned)ds < (unsigned)g.D;
+            if (!row_ok) continue;
+            const float* src = x + ((long long)nb * CIN + c) * plane + ((long long)ds * hw + hs * g.W + w);
+            const int nv = min(8, g.W - w);
+            r.nvalid[i] = nv;
+            if (vec_ok && nv == 8) {
+                const float4 lo = __ldg(reinterpret_cast<const float4*>(src));
+                const float4 hi = __ldg(reinterpret_cast<const float4*>(src) + 1);
+                f[1] = lo.x; f[2] = lo.y; f[3] = lo.z; f[4] = lo.w;
+                f[5] = hi.x; f[6] = hi.y; f[7] = hi.z; f[8] = hi.w;
+            } else {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const bool in0 = 64 * KCI + 8 * q < KPAD, in1 = 64 * KCI + 32 + 8 * q < KPAD;
-            if (half == 0 ? in0 : in1)
-                st_shared_v4(box + row_off + (((half * 4 + q) ^ sw) << 4), wd[KCI * 16 + 4 * q],
-                             wd[KCI * 16 + 4 * q + 1], wd[KCI * 16 + 4 * q + 2], wd[KCI * 16 + 4 * q + 3]);
+                for (int e = 0; e < 8; ++e)
+                    if (e < nv) f[1 + e] = __ldg(src + e);
+            }
+            if (w > 0) f[0] = __ldg(src - 1);
+            if (w + 8 < g.W) f[9] = __ldg(src + 8);
         }
+    }
+    // addr(k, cj): shared-memory address of the 16-byte chunk cj (0..15: voxels 8*cj .. 8*cj+7) of column k's row
+    template <class Addr>
+    static DEV void store(const Regs& r, int pt, Addr&& addr) {
+#pragma unroll
+        for (int i = 0; i < kTasks; ++i) {
+            const int t = pt + i * kBuilders;
+            if (t >= NTRIPLE * 16) continue;
+            const int q = t >> 4, cj = t & 15;
+            const float (&f)[10] = r.f[i];
+            const int nvalid = r.nvalid[i];
+            if (nvalid == 8 || nvalid == 0) {   // (nvalid == 0: f is all zero)
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw)
+                    st_shared_v4(addr(3 * q + kw, cj), pack_bf16x2(f[kw], f[kw + 1]), pack_bf16x2(f[kw + 2], f[kw + 3]),
+                                 pack_bf16x2(f[kw + 4], f[kw + 5]), pack_bf16x2(f[kw + 6], f[kw + 7]));
+            } else {
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    uint32_t wd[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        wd[e] = pack_bf16x2(2 * e < nvalid ? f[2 * e + kw] : 0.f,
+                                            2 * e + 1 < nvalid ? f[2 * e + 1 + kw] : 0.f);
+                    st_shared_v4(addr(3 * q + kw, cj), wd[0], wd[1], wd[2], wd[3]);
+                }
+            }
+        }
+        // columns K .. KPAD-1 (zero rows of the packed weights): the MMAs read them, so they must be finite
+        for (int t = pt; t < (KPAD - K) * 16; t += kBuilders) st_shared_v4(addr(K + (t >> 4), t & 15), 0u, 0u, 0u, 0u);
     }
 };
 
@@ -259,9 +282,12 @@ DEV void igemm_body(const IgemmParams& p) {
     } else if (warp == 1 && rank == 0) {
         // ===================================================================== MMA issuer (pair mode: leader CTA only)
         // Lean loop: descriptors are base + stage offset (low word only), no divisions, one elected lane issues.
-        const uint32_t idesc = make_idesc_bf16(128 * mmul, p.block_n, 0, p.b_mn ? 1u : 0u);
+        // (direct first-layer form: A is the voxel-contiguous image above — MN-major, voxel halves 8 KB apart, one K step
+        //  = 16 rows of 128 B)
+        const uint32_t idesc = make_idesc_bf16(128 * mmul, p.block_n, kIm2colC ? 1u : 0u, p.b_mn ? 1u : 0u);
         const bool pair = kPair;
-        const uint64_t a_desc0 = make_smem_desc_sw128(smem_a, 0, 1024);
+        const uint64_t a_desc0 = make_smem_desc_sw128(smem_a, kIm2colC ? 8192u : 0u, 1024);
+        constexpr uint32_t kAk = kIm2colC ? 128u : 2u;
         // K-major B: rows = N, 128 B = 64 K.  MN-major B: rows = K, 128 B = 64 N, atoms of 64 N are LBO apart.
         const uint64_t b_desc0 = make_smem_desc_sw128(smem_b, p.b_mn ? b_atom_bytes : 0, 1024);
         const uint32_t kinc = p.b_mn ? 128u : 2u;  // one K step (16): 16 rows x 128 B, or 32 B inside the swizzle row
@@ -293,9 +319,9 @@ DEV void igemm_body(const IgemmParams& p) {
                             // 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (>>4) address field
                             if (!pair) {
                                 umma_f16(d_tmem, a_desc, b_desc, idesc, g == 0 ? accum : 1u);
-                                if (nk > 1) umma_f16(d_tmem, a_desc + 2, b_desc + kinc, idesc, 1u);
-                                if (nk > 2) umma_f16(d_tmem, a_desc + 4, b_desc + 2 * kinc, idesc, 1u);
-                                if (nk > 3) umma_f16(d_tmem, a_desc + 6, b_desc + 3 * kinc, idesc, 1u);
+                                if (nk > 1) umma_f16(d_tmem, a_desc + kAk, b_desc + kinc, idesc, 1u);
+                                if (nk > 2) umma_f16(d_tmem, a_desc + 2 * kAk, b_desc + 2 * kinc, idesc, 1u);
+                                if (nk > 3) umma_f16(d_tmem, a_desc + 3 * kAk, b_desc + 3 * kinc, idesc, 1u);
                             } else {
                                 umma_f16_pair(d_tmem, a_desc, b_desc, idesc, g == 0 ? accum : 1u);
                                 if (nk > 1) umma_f16_pair(d_tmem, a_desc + 2, b_desc + kinc, idesc, 1u);
@@ -319,41 +345,65 @@ DEV void igemm_body(const IgemmParams& p) {
         }
     } else if (kIm2colC > 0 && warp >= 8) {
         // ===================================================================== A builders (direct first-layer form)
-        // same stage walk as the TMA producer: tile -> kc; every warp arrives once per stage after its rows are
-        // visible to the tensor core's (async-proxy) reads
+        // One brick = Img::KC consecutive ring slots (64 im2col columns each): the builders take all of them, write the
+        // whole image, and every warp arrives once per slot after its rows are visible to the tensor core's
+        // (async-proxy) reads.
         PipeState ps;
         const int pt = threadIdx.x - 256;
         const int n_tiles = p.n_tiles;
         const BrickGeom geom{p.tw_log2, p.th_log2, p.W, p.H, p.D, p.nbatch};
-        using Row = Im2colRow<kIm2colC ? kIm2colC : 1>;
-        auto publish = [&]() {
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(full_bar(ps.stage));
-            ps.advance(nst);
-        };
-        for (int tile = unit0; tile < total_tiles; tile += unit_stride) {
+        using Img = Im2colImage<kIm2colC ? kIm2colC : 1>;
+        auto load_tile = [&](typename Img::Regs& r, int tile) {
+            if (B200_ABLATE(p) == 5) {   // dev: no input loads (zero image)
+#pragma unroll
+                for (int i = 0; i < Img::kTasks; ++i) {
+                    r.nvalid[i] = 0;
+#pragma unroll
+                    for (int e = 0; e < 10; ++e) r.f[i][e] = 0.f;
+                }
+                return;
+            }
             int mt = tile / n_tiles;
             const int bw = mt % p.nbw; mt /= p.nbw;
             const int bh = mt % p.nbh; mt /= p.nbh;
             const int bd = mt % p.nbd; mt /= p.nbd;
-            const int nb = mt;
-            Row r;
-            r.load(p.x_src, pt, bw << p.tw_log2, bh << p.th_log2, bd << p.td_log2, nb, geom);
-            // one pipeline stage per 64-column block (p.kc_blocks == Row::KC)
-            mbar_wait(empty_bar(ps.stage), ps.phase ^ 1);
-            r.template store<0>(smem_a + ps.stage * a_bytes, pt);
-            publish();
-            if (Row::KC > 1) {
+            Img::load(r, p.x_src, pt, bw << p.tw_log2, bh << p.th_log2, bd << p.td_log2, mt, geom);
+        };
+        auto store_tile = [&](const typename Img::Regs& r) {
+            uint32_t slot[Img::KC], bars[Img::KC];
+#pragma unroll
+            for (int i = 0; i < Img::KC; ++i) {
                 mbar_wait(empty_bar(ps.stage), ps.phase ^ 1);
-                r.template store<(Row::KC > 1 ? 1 : 0)>(smem_a + ps.stage * a_bytes, pt);
-                publish();
+                slot[i] = smem_a + ps.stage * a_bytes;
+                bars[i] = full_bar(ps.stage);
+                ps.advance(nst);
             }
-            if (Row::KC > 2) {
-                mbar_wait(empty_bar(ps.stage), ps.phase ^ 1);
-                r.template store<(Row::KC > 2 ? 2 : 0)>(smem_a + ps.stage * a_bytes, pt);
-                publish();
+            Img::store(r, pt, [&](int k, int cj) -> uint32_t {
+                static_assert(Img::KC <= 3, "at most 192 im2col columns");
+                const uint32_t base = k < 64 ? slot[0] : (k < 128 ? slot[Img::KC > 1 ? 1 : 0] : slot[Img::KC > 2 ? 2 : 0]);
+                return base + (uint32_t)(cj >> 3) * 8192u + (uint32_t)(k & 63) * 128u +
+                       ((uint32_t)((cj & 7) ^ (k & 7)) << 4);
+            });
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+#pragma unroll
+                for (int i = 0; i < Img::KC; ++i) mbar_arrive(bars[i]);
             }
+        };
+        // two register sets, ping-pong: the loads of brick i + 1 are in flight while brick i is written
+        typename Img::Regs ra, rb;
+        int tile = unit0;
+        if (tile < total_tiles) load_tile(ra, tile);
+        while (tile < total_tiles) {
+            const int t1 = tile + unit_stride;
+            if (t1 < total_tiles) load_tile(rb, t1);
+            store_tile(ra);
+            if (t1 >= total_tiles) break;
+            const int t2 = t1 + unit_stride;
+            if (t2 < total_tiles) load_tile(ra, t2);
+            store_tile(rb);
+            tile = t2;
         }
     } else if (warp >= 4 && warp < 8) {
         // ===================================================================== epilogue
@@ -406,6 +456,12 @@ DEV void igemm_body(const IgemmParams& p) {
                 named_bar_sync(1, 128);
                 mbar_wait(tfull_bar(acc), acc_phase);
                 tc_fence_after();
+                if (B200_ABLATE(p) == 4) {   // dev: the epilogue only hands the accumulator back
+                    tc_fence_before();
+                    if (kPair) mbar_arrive_leader(tempty_bar(acc));
+                    else mbar_arrive(tempty_bar(acc));
+                    continue;
+                }
                 const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.block_n;
                 for (int j = 0; j < nslab; ++j) {
                     uint32_t v[32];
@@ -658,6 +714,10 @@ DEV void wgrad_body(const WgradParams& p) {
     // (first-layer form: three column blocks per slot and shallower P slots leave ~70 KB of the SM to L1, which the
     //  27-fold re-read of the fp32 input by the Q builders lives on)
     constexpr uint32_t kPSlot = 2 * kBoxBytes, kQSlot = (kIm2colC ? 3 : 4) * kBoxBytes, kNP = 2, kNQ = 2;
+    // first-layer form: the Q slot holds the voxel-contiguous image (Im2colImage): two halves of KPAD rows x 128 B
+    using Img = Im2colImage<kIm2colC ? kIm2colC : 1>;
+    constexpr uint32_t kQHalf = Img::KPAD * 128;
+    static_assert(kIm2colC == 0 || 2 * kQHalf <= kQSlot, "im2col image does not fit the Q slot");
     const uint32_t smem_p = smem_base;
     const uint32_t smem_q = smem_p + kNP * kPSlot;
     const uint32_t bar_base = smem_q + kNQ * kQSlot;
@@ -740,7 +800,8 @@ DEV void wgrad_body(const WgradParams& p) {
         PipeState pp, qp;
         // MN-major SWIZZLE_128B operands: 64-channel atoms (16 KB boxes) LBO apart, 8-voxel groups SBO apart
         const uint64_t a_desc0 = make_smem_desc_sw128(smem_p, kBoxBytes, 1024);
-        const uint64_t b_desc0 = make_smem_desc_sw128(smem_q, kBoxBytes, 1024);
+        // (first-layer form: Q is K-major — rows = im2col columns, 128 B = 64 voxels, the second 64 voxels kQHalf on)
+        const uint64_t b_desc0 = make_smem_desc_sw128(smem_q, kIm2colC ? 0u : (uint32_t)kBoxBytes, 1024);
         uint32_t accum = 0;
         for (int b = split; b < nbricks; b += p.splits) {
             mbar_wait(pfull(pp.stage), pp.phase);
@@ -748,7 +809,7 @@ DEV void wgrad_body(const WgradParams& p) {
             const uint64_t a_desc = a_desc0 + pp.stage * (kPSlot >> 4);
             for (int sg = 0; sg < nsg; ++sg) {
                 const int nb4 = min(4, ncb - sg * 4);
-                const uint32_t idesc = make_idesc_bf16(128, 64 * nb4, 1, 1);
+                const uint32_t idesc = kIm2colC ? make_idesc_bf16(128, Img::KPAD, 1, 0) : make_idesc_bf16(128, 64 * nb4, 1, 1);
                 mbar_wait(qfull(qp.stage), qp.phase);
                 tc_fence_after();
                 if (elect_one()) {
@@ -757,7 +818,9 @@ DEV void wgrad_body(const WgradParams& p) {
                     // 16 voxels = 16 rows x 128 B = 2048 B along K: +128 in the (>>4) address field
                     umma_f16(d_tmem, a_desc, b_desc, idesc, accum);
 #pragma unroll
-                    for (int k = 1; k < 8; ++k) umma_f16(d_tmem, a_desc + 128 * k, b_desc + 128 * k, idesc, 1u);
+                    for (int k = 1; k < 8; ++k)
+                        umma_f16(d_tmem, a_desc + 128 * k,
+                                 kIm2colC ? b_desc + (k >> 2) * (kQHalf >> 4) + (k & 3) * 2 : b_desc + 128 * k, idesc, 1u);
                     umma_commit(qempty(qp.stage));
                 }
                 __syncwarp();
@@ -775,25 +838,37 @@ DEV void wgrad_body(const WgradParams& p) {
         PipeState qp;
         const int pt = threadIdx.x - 256;
         const BrickGeom geom{p.tw_log2, p.th_log2, p.W, p.H, p.D, p.nbatch};
-        using Row = Im2colRow<kIm2colC ? kIm2colC : 1>;
-        for (int b = split; b < nbricks; b += p.splits) {
+        auto load_brick = [&](typename Img::Regs& r, int b) {
             int mt = b;
             const int bw = mt % p.nbw; mt /= p.nbw;
             const int bh = mt % p.nbh; mt /= p.nbh;
             const int bd = mt % p.nbd; mt /= p.nbd;
-            const int nb = mt;
-            Row r;
-            r.load(p.x_src, pt, bw * p.tw, bh * p.th, bd * p.td, nb, geom);
-            // the whole padded row (Row::KC column blocks = the CTA's one slot group) goes into one Q slot
+            Img::load(r, p.x_src, pt, bw * p.tw, bh * p.th, bd * p.td, mt, geom);
+        };
+        auto store_brick = [&](const typename Img::Regs& r) {
             mbar_wait(qempty(qp.stage), qp.phase ^ 1);
             const uint32_t slot = smem_q + qp.stage * kQSlot;
-            r.template store<0>(slot, pt);
-            if (Row::KC > 1) r.template store<(Row::KC > 1 ? 1 : 0)>(slot + kBoxBytes, pt);
-            if (Row::KC > 2) r.template store<(Row::KC > 2 ? 2 : 0)>(slot + 2 * kBoxBytes, pt);
+            Img::store(r, pt, [&](int k, int cj) -> uint32_t {
+                return slot + (uint32_t)(cj >> 3) * kQHalf + (uint32_t)k * 128u + ((uint32_t)((cj & 7) ^ (k & 7)) << 4);
+            });
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(qfull(qp.stage));
             qp.advance(kNQ);
+        };
+        // two register sets, ping-pong: the loads of brick i + 1 are in flight while brick i is written
+        typename Img::Regs ra, rb;
+        int b0 = split;
+        if (b0 < nbricks) load_brick(ra, b0);
+        while (b0 < nbricks) {
+            const int b1 = b0 + p.splits;
+            if (b1 < nbricks) load_brick(rb, b1);
+            store_brick(ra);
+            if (b1 >= nbricks) break;
+            const int b2 = b1 + p.splits;
+            if (b2 < nbricks) load_brick(ra, b2);
+            store_brick(rb);
+            b0 = b2;
         }
     } else if (warp >= 4 && warp < 8) {
         // ===================================================================== epilogue
