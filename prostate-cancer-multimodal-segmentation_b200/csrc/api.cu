@@ -480,9 +480,20 @@ static int conv3_igemm(const b200_act* in, const void* w_packed, const b200_act*
                              halo ? 3 : 1);
     if (rc) return rc;
     p.ntaps = ntaps;
-    // epilogue v2 (staged tile + TMA store): pays off when the MMA time per tile is short, i.e. narrow N
+    // epilogue v2 (staged tile + TMA store, BatchNorm sums read back from the tile): half the instructions of the direct
+    // epilogue per output value, which shows wherever the MMA time per tile is short — narrow N, and 128-column tiles
+    // with few input channels (tools/bench_epi.py: 64 -> 128 @64^3 forward 0.198 -> 0.167 ms, the 128-channel input
+    // gradient at 128^3 1.31 -> 1.24 ms, identical results).  256-column tiles hide either epilogue under their MMAs.
     p.epi_v2 = (p.block_n <= 64 && p.block_n % 32 == 0 && !split.splits) ? 1 : 0;
     p.c_bufs = p.epi_v2 ? 2 : 1;   // one-box tiles: a second staging tile takes the store's read latency off the epilogue
+    if (p.block_n == 128 && out->c % 64 == 0 && !split.splits) {   // two boxes, one staging tile (32 KB)
+        p.epi_v2 = 1;
+        p.c_bufs = 1;
+    }
+    if (g_dev_var[2] > 0 && p.block_n == 128) {   // development library only: 1 = direct epilogue, 2 = two staging tiles
+        p.epi_v2 = g_dev_var[2] == 1 ? 0 : p.epi_v2;
+        p.c_bufs = g_dev_var[2] == 2 && p.epi_v2 ? 2 : p.c_bufs;
+    }
     if (p.epi_v2) {
         rc = make_act_map(&p.c_map[0], reinterpret_cast<const __nv_bfloat16*>(out->ptr), out->c, out->w, out->h,
                           out->d, out->n, out->ld, out->w, out->h, out->d, 1, b.tw, b.th, b.td);
@@ -508,6 +519,10 @@ static int conv3_igemm(const b200_act* in, const void* w_packed, const b200_act*
             p.tap_dh[t] = ntaps == 1 ? 0 : sign * (t % 3 - 1);
         }
         set_plain_stage(p);
+    }
+    if (p.block_n == 128 && p.epi_v2 && p.stages < 3) {   // the staging tile must not starve the operand ring
+        p.epi_v2 = 0;
+        p.stages = igemm_stages(p.a_stage_bytes, b_stage_bytes(p), 0);
     }
     p.cin = (int)in->c;
     p.kc_blocks = (int)((in->c + 63) / 64);

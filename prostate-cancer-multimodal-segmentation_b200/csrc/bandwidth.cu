@@ -697,21 +697,36 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(View v, float* out, in
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[0][j] = 0.f;
     if (active) {
-        for (long long i = (long long)blockIdx.x * rows + row; i < nvox; i += (long long)gridDim.x * rows) {
-            long long vox = i;
-            if (boxed) {
-                uint32_t r = (uint32_t)i, q = bwd.quot(r);
-                const uint32_t w = r - q * bwd.div;
-                r = q; q = bhd.quot(r);
-                const uint32_t h = r - q * bhd.div;
-                r = q; q = bdd.quot(r);
-                const uint32_t d = r - q * bdd.div;
-                vox = (((long long)q * v.d + d0 + d) * v.h + h0 + h) * v.w + w0 + w;
-            }
-            float x[8];
-            unpack8(ld8_stream(v.p + vox * v.ld + cv * 8), x);
+        constexpr int U = 4;   // loads in flight per thread (one per iteration ran at half the copy bandwidth)
+        const long long step = (long long)gridDim.x * rows;
+        for (long long i0 = (long long)blockIdx.x * rows + row; i0 < nvox; i0 += U * step) {
+            Bf8 t[U];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[0][j] += x[j];
+            for (int u = 0; u < U; ++u) {
+                const long long i = i0 + u * step;
+                if (i < nvox) {
+                    long long vox = i;
+                    if (boxed) {
+                        uint32_t r = (uint32_t)i, q = bwd.quot(r);
+                        const uint32_t w = r - q * bwd.div;
+                        r = q; q = bhd.quot(r);
+                        const uint32_t h = r - q * bhd.div;
+                        r = q; q = bdd.quot(r);
+                        const uint32_t d = r - q * bdd.div;
+                        vox = (((long long)q * v.d + d0 + d) * v.h + h0 + h) * v.w + w0 + w;
+                    }
+                    t[u] = ld8_stream(v.p + vox * v.ld + cv * 8);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (i0 + u * step < nvox) {
+                    float x[8];
+                    unpack8(t[u], x);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[0][j] += x[j];
+                }
+            }
         }
     }
     block_reduce_store<1>(acc, c8, rows, row, cv, active, smem, out, (int)v.c, true);

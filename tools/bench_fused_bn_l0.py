@@ -18,8 +18,11 @@ bn = (y, scale, shift, mean, rstd, gamma, partial, coef, dgamma, dbeta, dy, dbia
 w = torch.randn(1, c, device=dev) * 0.1
 dl = torch.randn(n, 1, e, e, e, device=dev)
 dw, db = torch.zeros(1, c, device=dev), torch.zeros(1, device=dev)
-for _ in range(2):
+pooled = act(n, e // 2, e // 2, e // 2, c)
+for _ in range(2):   # 9 launches per round: apply, apply+pool, pool bwd, bn_bwd (3), bn_bwd_head (3)
     ops.bn_apply_relu(y, scale, shift, a)
+    ops.bn_apply_relu_pool(y, scale, shift, a, pooled)
+    ops.maxpool3d_bwd(a, dpool, dskip, dout)
     ops.bn_bwd(dout, *bn)
     ops.bn_bwd_head(dl, w, *bn, dw, db)
 torch.cuda.synchronize()

@@ -15,7 +15,7 @@ G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 os.makedirs(P, exist_ok=True)
 
 for name in ("bench.json", "bench_reference_arm.json", "bench_infer.json", "bench_cv.json", "gemm_launches.txt",
-             "timeline_events.txt", "launches.csv"):
+             "timeline_events.txt", "launches.csv", "bn_passes_timing.txt", "ab_fused.txt"):
     src = os.path.join(G, f"{tag}_{name}")
     if os.path.exists(src):
         shutil.copy(src, os.path.join(P, f"{tag}_{name}"))
@@ -63,7 +63,9 @@ WANT = ["gpu__time_duration.sum", "launch__grid_size", "sm__cycles_elapsed.max",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread",
         "launch__shared_mem_per_block_dynamic", "smsp__inst_executed.sum"]
 traffic = {}
-for name in ("igemm_pair", "dmarch_pair", "wgrad_halo", "igemm", "dmarch", "igemm_im2col5", "wgrad_im2col5"):
+WANT += ["smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]
+for name in ("igemm_pair", "dmarch_pair", "wgrad_halo", "igemm", "dmarch", "igemm_im2col5", "wgrad_im2col5", "bn_passes"):
     rep = os.path.join(G, f"{tag}_prof_{name}.ncu-rep")
     if not os.path.exists(rep):
         continue
@@ -88,7 +90,7 @@ for name in ("igemm_pair", "dmarch_pair", "wgrad_halo", "igemm", "dmarch", "igem
                 v, u = vals[k]
                 v = float(v.replace(",", ""))
                 return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}.get(u, 1.0)
-            if li == 0 and "dram__bytes_read.sum" in vals:
+            if li == 0 and "dram__bytes_read.sum" in vals and name != "bn_passes":
                 kname = name + "_kernel"
                 traffic[kname] = {"dram_bytes": int(num("dram__bytes_read.sum") + num("dram__bytes_write.sum")),
                                   "duration_ms_under_ncu": float(vals["gpu__time_duration.sum"][0]) *
