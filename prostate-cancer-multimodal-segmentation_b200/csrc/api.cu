@@ -248,6 +248,19 @@ static bool conv_geometry(long long n, long long w, long long h, long long d, lo
                           int* block_n) {
     const Brick plain = choose_brick(w, h, d);
     *block_n = igemm_block_n(cout, n * plain.nbw * plain.nbh * plain.nbd);
+    // Wave quantisation of the CTA-pair kernel: 256-column tiles at the 32^3 level are 256 work units on 74 cluster
+    // slots = 3.46 waves, i.e. the fourth wave runs a quarter full; 128-column tiles (512 units, 6.9 waves) finish
+    // earlier although each moves its A box twice (tools/bench_blockn.py: 128 -> 256 @32^3 forward 0.095 -> 0.085 ms,
+    // 512 -> 256 0.298 -> 0.275 ms; with 512 columns the 256-column tiling already fills its waves and stays)
+    if (ntaps == 27 && *block_n == 256 && cout % 128 == 0) {
+        const long long ncl = igemm_max_clusters();
+        const long long pairs = (n * plain.nbw * plain.nbh * plain.nbd + 1) / 2;
+        if (ncl > 0) {
+            const long long w256 = (pairs * ((cout + 255) / 256) + ncl - 1) / ncl;
+            const long long w128 = (pairs * (cout / 128) + ncl - 1) / ncl;
+            if (w256 > 1 && 103 * w128 < 200 * w256) *block_n = 128;   // (a 128-column wave is half as long, + 3 %)
+        }
+    }
     // h-halo mode needs the three kh taps of B in one stage: 3 x block_n x 128 B.  That fits next to the A box for
     // block_n <= 128, and for 256-column tiles in CTA-pair mode (each CTA stages half of B: 48 KB)
     const bool wide_pair = *block_n == 256 && w >= 8 && h >= 16 &&
@@ -459,6 +472,16 @@ static int conv3_igemm(const b200_act* in, const void* w_packed, const b200_act*
     // h-halo mode: worth it when the MMA per tap is short (narrow N) and the volume holds 8 x 16 bricks
     Brick b;
     bool halo = conv_geometry(in->n, in->w, in->h, in->d, out->c, ntaps, &b, &p.block_n);
+    if (g_dev_var[3] > 0 && ntaps == 27 && out->c % g_dev_var[3] == 0) {   // development library only: forced UMMA N
+        p.block_n = g_dev_var[3];
+        halo = p.block_n <= 128 && in->w >= 8 && in->h >= 16;
+        if (halo) {
+            b.tw = 8; b.th = 16; b.td = 1; b.lw = 3; b.lh = 4; b.ld = 0;
+            b.nbw = (in->w + 7) / 8; b.nbh = (in->h + 15) / 16; b.nbd = in->d;
+        } else {
+            b = choose_brick(in->w, in->h, in->d);
+        }
+    }
     if (split.splits) {   // plain bricks, 256-column CTA-pair tiles
         halo = false;
         b = choose_brick(in->w, in->h, in->d);
