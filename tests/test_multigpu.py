@@ -29,8 +29,13 @@ def test_model_on_second_device_while_first_is_current():
         opt.zero_grad()
         loss = pkg.BCEDiceLoss()(m(x.to(d)), y.to(d))
         loss.backward()
+        grad = m.engine.flat_grad.detach().cpu().clone()
         opt.step()
         torch.cuda.synchronize(d)
-        outs.append((loss.item(), m.engine.flat_param.detach().cpu()))
+        assert torch.isfinite(m.engine.flat_param).all()
+        outs.append((loss.item(), grad))
         assert torch.cuda.current_device() == 0
-    assert outs[0][0] == outs[1][0] and torch.equal(outs[0][1], outs[1][1])
+    # the forward is deterministic; weight gradients are accumulated with fp32 atomics whose order differs between two
+    # physical GPUs, so they agree to summation order (and Adam's first step, lr * sign(g), would amplify that noise)
+    assert outs[0][0] == outs[1][0]
+    assert ((outs[0][1] - outs[1][1]).norm() / outs[1][1].norm()).item() < 1e-5
