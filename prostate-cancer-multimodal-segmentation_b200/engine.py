@@ -48,19 +48,23 @@ def _slot_view(flat: torch.Tensor, off: int, p) -> torch.Tensor:
 # bn_bwd) the fused BatchNorm passes replace; same results, more HBM traffic.
 FUSE_BN_PASSES = True
 
-_SPLITK_WS = {}
+_SPLITK_WS = {}   # device -> list of scratch tensors, the last one is the largest
 
 
 def _splitk_workspace(device, n, d, h, w, out_cols):
     """The fp32 scratch of the split-K form of a deep-level conv / dgrad (None when the shape does not split).  One buffer
-    per device, grown on demand; all split-K launches run on the compute stream, so consecutive layers share it."""
+    per device, grown on demand; all split-K launches run on the compute stream, so consecutive layers share it.  A
+    buffer that has been handed out is never freed: a captured CUDA graph (graph.GraphedTrainStep) replays with the
+    pointer it recorded."""
     nbytes = ops.conv3d_workspace_bytes(n, d, h, w, out_cols)
     if nbytes == 0:
         return None
-    t = _SPLITK_WS.get(device)
-    if t is None or t.numel() * 4 < nbytes:
-        t = _SPLITK_WS[device] = torch.empty((nbytes + 3) // 4, device=device, dtype=torch.float32)
-    return t
+    bufs = _SPLITK_WS.setdefault(device, [])
+    if not bufs or bufs[-1].numel() * 4 < nbytes:
+        if torch.cuda.is_current_stream_capturing():
+            raise B200Error("split-K scratch must exist before CUDA-graph capture: run one eager step of this shape first")
+        bufs.append(torch.empty((nbytes + 3) // 4, device=device, dtype=torch.float32))
+    return bufs[-1]
 
 
 class _ConvPack:
