@@ -40,6 +40,11 @@ enum { B200_EPI_PLAIN = 0, B200_EPI_BIAS_STATS = 1, B200_EPI_AFFINE_RELU = 2, B2
 
 const char* b200_last_error(void);
 int b200_abi_version(void);
+/* Programmatic dependent launch for every kernel of the library (default on): a kernel's CTAs may become resident while
+   the previous kernel of the stream drains, and wait (griddepcontrol.wait) for its completion before touching global
+   memory; under stream capture the launches become programmatic graph edges.  on = 1 / 0 sets the process-wide
+   switch, on < 0 only queries; returns the previous setting.  No reference counterpart (torch launches serialise). */
+int b200_set_pdl(int on);
 /* number of SMs of the current device (grid sizing), or <0 on error */
 int b200_sm_count(void);
 
@@ -219,6 +224,18 @@ int b200_conv1_direct_fprop(const float* x, int64_t n, int64_t c, int64_t d, int
                             const float* shift, void* stream);
 int b200_conv1_direct_wgrad(const float* x, int64_t n, int64_t c, int64_t d, int64_t h, int64_t w, const b200_act* dy,
                             float* dw, void* stream);
+
+/* Forward of the same first conv as a depth-marching kernel (csrc/conv1_march.cu; models/unet3d.py:194, :29): a CTA
+ * walks an 8 x 16 brick column along depth and builds ONE 45-row slice image per input slice, which feeds three output
+ * slices; two epilogue warpgroups.  For 5 input channels and Cout <= 64 (b200_conv1_march_supported); w_slices =
+ * b200_pack_conv1_slices of the (Cout,5,3,3,3) weight: bf16 [3 kd][Cout][64], row k = c*9 + kh*3 + kw.  Modes and
+ * arguments as b200_conv1_direct_fprop; BIAS_STATS needs b200_conv1_march_stat_rows(...) rows of stats_partial. */
+int b200_conv1_march_supported(int64_t c, int64_t cout);
+int b200_conv1_march_stat_rows(int64_t n, int64_t d, int64_t h, int64_t w, int64_t cout);
+int b200_pack_conv1_slices(const float* w, int64_t cout, int64_t cin, void* out, void* stream);
+int b200_conv1_march_fprop(const float* x, int64_t n, int64_t c, int64_t d, int64_t h, int64_t w, const void* w_slices,
+                           const float* bias, const b200_act* y, float* stats_partial, int mode, const float* scale,
+                           const float* shift, void* stream);
 
 /* per-channel sum over the box [d0,d0+bd) x [h0,h0+bh) x [w0,w0+bw) of every sample, added to out[c] (fp32): the
  * ConvTranspose3d bias gradient when F.pad (models/unet3d.py:149-151) put a zero border around the upsampled map */

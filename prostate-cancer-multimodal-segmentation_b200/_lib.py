@@ -27,6 +27,7 @@ _AP = C.POINTER(Act)
 SIGNATURES = {
     "b200_last_error": (C.c_char_p, []),
     "b200_abi_version": (_i32, []),
+    "b200_set_pdl": (_i32, [_i32]),
     "b200_sm_count": (_i32, []),
     "b200_pack_input": (_i32, [_vp, _i64, _i64, _i64, _i64, _i64, _AP, _vp]),
     "b200_im2col_input": (_i32, [_vp, _i64, _i64, _i64, _i64, _i64, _AP, _vp]),
@@ -37,6 +38,10 @@ SIGNATURES = {
     "b200_conv1_direct_stat_rows": (_i32, [_i64, _i64, _i64, _i64, _i64]),
     "b200_conv1_direct_fprop": (_i32, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _AP, _vp, _i32, _vp, _vp, _vp]),
     "b200_conv1_direct_wgrad": (_i32, [_vp, _i64, _i64, _i64, _i64, _i64, _AP, _vp, _vp]),
+    "b200_conv1_march_supported": (_i32, [_i64, _i64]),
+    "b200_conv1_march_stat_rows": (_i32, [_i64, _i64, _i64, _i64, _i64]),
+    "b200_pack_conv1_slices": (_i32, [_vp, _i64, _i64, _vp, _vp]),
+    "b200_conv1_march_fprop": (_i32, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _AP, _vp, _i32, _vp, _vp, _vp]),
     "b200_pack_conv_weight": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "b200_pack_convt_weight": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "b200_conv3d_mtiles": (_i64, [_i64, _i64, _i64, _i64]),
@@ -91,7 +96,7 @@ DEV_SIGNATURES = {
     "b200_dev_set_variant": (_i32, [_i32, _i32]),
 }
 
-ABI_VERSION = 4   # must equal b200_abi_version() of the loaded library
+ABI_VERSION = 5   # must equal b200_abi_version() of the loaded library
 
 _lib = None
 

@@ -12,8 +12,10 @@
 #include "../../include/b200_unet3d.h"
 #include "bandwidth.cuh"
 #include "igemm.cuh"
+#include "launch.cuh"
 
 namespace b200 {
+int g_pdl = 1;   // launch.cuh: programmatic dependent launch on every kernel of the library
 extern "C" __global__ void igemm_kernel(const __grid_constant__ IgemmParams p);
 extern "C" __global__ void wgrad_kernel(const __grid_constant__ WgradParams p);
 extern "C" __global__ void igemm_pair_kernel(const __grid_constant__ IgemmParams p);
@@ -22,6 +24,7 @@ extern "C" __global__ void wgrad_im2col5_kernel(const __grid_constant__ WgradPar
 extern "C" __global__ void dmarch_kernel(const __grid_constant__ DmarchParams p);
 extern "C" __global__ void dmarch_pair_kernel(const __grid_constant__ DmarchParams p);
 extern "C" __global__ void wgrad_halo_kernel(const __grid_constant__ WgradHaloParams p);
+extern "C" __global__ void conv1_march_kernel(const __grid_constant__ Conv1MarchParams p);
 }  // namespace b200
 
 using namespace b200;
@@ -46,7 +49,12 @@ static int fail(int code, const char* fmt, ...) {
     } while (0)
 
 extern "C" const char* b200_last_error(void) { return g_err; }
-extern "C" int b200_abi_version(void) { return 4; }
+extern "C" int b200_abi_version(void) { return 5; }
+extern "C" int b200_set_pdl(int on) {
+    const int was = g_pdl;
+    if (on >= 0) g_pdl = on ? 1 : 0;
+    return was;
+}
 
 // Development switches: compiled only into the development library (-DB200_DEV).  The product library has no
 // environment lookups and no ablation branches on its launch path.
@@ -345,7 +353,7 @@ static int launch_igemm(IgemmParams& p, cudaStream_t s, int* grid_out) {
         const int grid_ = (int)(tiles_ < sms ? tiles_ : sms);
         if (grid_out) *grid_out = grid_;
         p.ablate = g_dev_igemm_ablate;   // development library only
-        igemm_im2col5_kernel<<<grid_, kIm2colThreads, smem, s>>>(p);
+        launch_k(igemm_im2col5_kernel, grid_, kIm2colThreads, smem, s, p);
         CUDA_TRY(cudaGetLastError());
         return 0;
     }
@@ -361,14 +369,14 @@ static int launch_igemm(IgemmParams& p, cudaStream_t s, int* grid_out) {
         const long long units = ((m_tiles + 1) / 2) * p.n_tiles * (p.splits > 1 ? p.splits : 1);
         const int grid = 2 * (int)(units < ncl ? units : ncl);
         if (grid_out) *grid_out = grid;
-        igemm_pair_kernel<<<grid, kThreads, smem, s>>>(p);   // compiled with __cluster_dims__(2, 1, 1)
+        launch_k(igemm_pair_kernel, grid, kThreads, smem, s, p);   // compiled with __cluster_dims__(2, 1, 1)
         CUDA_TRY(cudaGetLastError());
         return 0;
     }
     const long long tiles = m_tiles * p.n_tiles;
     const int grid = (int)(tiles < sms ? tiles : sms);
     if (grid_out) *grid_out = grid;
-    igemm_kernel<<<grid, kThreads, smem, s>>>(p);
+    launch_k(igemm_kernel, grid, kThreads, smem, s, p);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -602,8 +610,8 @@ static int launch_dmarch(const b200_act* in, const void* w_packed, const b200_ac
         const int rc_attr = ensure_smem(dmarch_kernel, kDmSmem, optin);
         if (rc_attr) return rc_attr;
     }
-    if (pl.pair) dmarch_pair_kernel<<<pl.grid, kThreads, kDmSmem, s>>>(p);   // __cluster_dims__(2, 1, 1)
-    else dmarch_kernel<<<pl.grid, kThreads, kDmSmem, s>>>(p);
+    if (pl.pair) launch_k(dmarch_pair_kernel, pl.grid, kThreads, kDmSmem, s, p);   // __cluster_dims__(2, 1, 1)
+    else launch_k(dmarch_kernel, pl.grid, kThreads, kDmSmem, s, p);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -848,9 +856,9 @@ static int launch_wgrad(WgradParams& p, cudaStream_t s) {
         static SmemOptIn optin_i2c;
         const int rc_attr = ensure_smem(wgrad_im2col5_kernel, (int)smem, optin_i2c);
         if (rc_attr) return rc_attr;
-        wgrad_im2col5_kernel<<<(int)grid, kIm2colThreads, smem, s>>>(p);
+        launch_k(wgrad_im2col5_kernel, (int)grid, kIm2colThreads, smem, s, p);
     } else {
-        wgrad_kernel<<<(int)grid, kThreads, smem, s>>>(p);
+        launch_k(wgrad_kernel, (int)grid, kThreads, smem, s, p);
     }
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -933,7 +941,7 @@ extern "C" int b200_conv3d_wgrad(const b200_act* x, const b200_act* dy, float* d
             const int rc_attr = ensure_smem(wgrad_halo_kernel, (int)smem_h, optin_h);
             if (rc_attr) return rc_attr;
         }
-        wgrad_halo_kernel<<<(int)grid_h, kThreads, smem_h, (cudaStream_t)stream>>>(hp);
+        launch_k(wgrad_halo_kernel, (int)grid_h, kThreads, smem_h, (cudaStream_t)stream, hp);
         CUDA_TRY(cudaGetLastError());
         return 0;
     }
@@ -1100,6 +1108,98 @@ extern "C" int b200_conv1_direct_fprop(const float* x, int64_t n, int64_t c, int
     p.cols_per_group = p.ncols;
     p.x_src = x;
     return launch_igemm(p, (cudaStream_t)stream, nullptr);
+}
+// ---- depth-marching forward of the first layer (conv1_march.cu)
+struct C1Plan {
+    int nbw, nbh, seg_len, nseg, grid;
+};
+// depth segments per brick column: minimise waves x (segment length + the two extra slice images a segment builds)
+static C1Plan conv1_march_plan(long long n, long long d, long long h, long long w, int sms) {
+    C1Plan pl{};
+    pl.nbw = (int)((w + 7) / 8);
+    pl.nbh = (int)((h + 15) / 16);
+    const long long columns = n * pl.nbw * pl.nbh;
+    const long long max_seg = d >= 8 ? d / 4 : 1;
+    long long best_nseg = 1;
+    double best_cost = 1e30;
+    for (long long nseg = 1; nseg <= max_seg; ++nseg) {
+        const long long seg_len = (d + nseg - 1) / nseg;
+        const long long real_nseg = (d + seg_len - 1) / seg_len;
+        const long long waves = (columns * real_nseg + sms - 1) / sms;
+        const double cost = (double)waves * ((double)seg_len + 1.0);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best_nseg = nseg; }
+    }
+    pl.seg_len = (int)((d + best_nseg - 1) / best_nseg);
+    pl.nseg = (int)((d + pl.seg_len - 1) / pl.seg_len);
+    const long long units = columns * pl.nseg;
+    pl.grid = (int)(units < sms ? units : sms);
+    return pl;
+}
+extern "C" int b200_conv1_march_supported(int64_t c, int64_t cout) {
+    return (c == kC1Cin && cout % 8 == 0 && cout >= 8 && cout <= 64) ? 1 : 0;
+}
+extern "C" int b200_conv1_march_stat_rows(int64_t n, int64_t d, int64_t h, int64_t w, int64_t cout) {
+    (void)cout;
+    const int sms = sm_count();
+    if (sms <= 0) return -1;
+    return conv1_march_plan(n, d, h, w, sms).grid;
+}
+extern "C" int b200_pack_conv1_slices(const float* w, int64_t cout, int64_t cin, void* out, void* stream) {
+    REQUIRE(w && out && cout > 0 && cin > 0 && cin * 9 <= 64, "pack_conv1_slices: bad arguments");
+    CUDA_TRY(launch_pack_conv1_slices(w, (int)cout, (int)cin, reinterpret_cast<__nv_bfloat16*>(out),
+                                      (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int b200_conv1_march_fprop(const float* x, int64_t n, int64_t c, int64_t d, int64_t h, int64_t w,
+                                      const void* w_slices, const float* bias, const b200_act* y,
+                                      float* stats_partial, int mode, const float* scale, const float* shift,
+                                      void* stream) {
+    CHECK_VIEW(y);
+    REQUIRE(x && w_slices, "conv1_march_fprop: null input / weights");
+    REQUIRE(b200_conv1_march_supported(c, y->c), "conv1_march_fprop: needs 5 input channels and 8..64 outputs");
+    REQUIRE(y->n == n && y->d == d && y->h == h && y->w == w, "conv1_march_fprop: extent mismatch");
+    REQUIRE(n * d * h * w < (1LL << 31), "conv1_march_fprop: too many voxels");
+    const float *v0 = nullptr, *v1 = nullptr;
+    switch (mode) {
+        case B200_EPI_BIAS_STATS:
+            REQUIRE(bias && stats_partial, "conv1_march_fprop: BIAS_STATS needs bias and stats_partial");
+            v0 = bias;
+            break;
+        case B200_EPI_AFFINE_RELU:
+            REQUIRE(scale && shift, "conv1_march_fprop: AFFINE_RELU needs scale and shift");
+            v0 = scale; v1 = shift;
+            break;
+        case B200_EPI_BIAS:
+            REQUIRE(bias, "conv1_march_fprop: BIAS needs bias");
+            v0 = bias;
+            break;
+        case B200_EPI_PLAIN: break;
+        default: return fail(B200_ERR_BAD_ARG, "conv1_march_fprop: unknown mode %d", mode);
+    }
+    int rc = get_encode();
+    if (rc) return rc;
+    const int sms = sm_count();
+    if (sms <= 0) return fail(B200_ERR_CUDA, "no CUDA device");
+    Conv1MarchParams p;
+    memset(&p, 0, sizeof(p));
+    rc = make_weight_map(&p.b_map, w_slices, 64, y->c, 3, 64, 1);
+    if (rc) return rc;
+    rc = make_act_map(&p.c_map, reinterpret_cast<const __nv_bfloat16*>(y->ptr), y->c, y->w, y->h, y->d, y->n, y->ld,
+                      y->w, y->h, y->d, 1, 8, 16, 1);
+    if (rc) return rc;
+    const C1Plan pl = conv1_march_plan(n, d, h, w, sms);   // same plan as b200_conv1_march_stat_rows
+    p.x = x;
+    p.vec0 = v0; p.vec1 = v1; p.stats = stats_partial;
+    p.ncols = (int)y->c;
+    p.W = (int)w; p.H = (int)h; p.D = (int)d; p.nbatch = (int)n;
+    p.nbw = pl.nbw; p.nbh = pl.nbh; p.seg_len = pl.seg_len; p.nseg = pl.nseg;
+    p.mode = mode;
+    static SmemOptIn optin;
+    const int rc_attr = ensure_smem(conv1_march_kernel, kC1Smem, optin);
+    if (rc_attr) return rc_attr;
+    launch_k(conv1_march_kernel, pl.grid, kC1Threads, kC1Smem, (cudaStream_t)stream, p);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
 }
 extern "C" int b200_conv1_direct_wgrad(const float* x, int64_t n, int64_t c, int64_t d, int64_t h, int64_t w,
                                        const b200_act* dy, float* dw, void* stream) {

@@ -5,6 +5,7 @@
 // Reference call sites replaced: nn.BatchNorm3d / nn.ReLU (models/unet3d.py:31-33,37-39), nn.MaxPool3d(2) (:80),
 // outc Conv3d k=1 (:222), DiceLoss / BCEDiceLoss (utils/losses.py:44-92,107-152), optim.Adam (utils/trainer.py:113).
 #include "bandwidth.cuh"
+#include "launch.cuh"
 
 namespace b200 {
 
@@ -65,6 +66,7 @@ static int grid_for(long long work_items, int threads, int sms, int waves) {
 
 // ------------------------------------------------------------------------------------------------ pack input
 __global__ void pack_input_kernel(const float* __restrict__ x, long long nvox_per_n, int c_in, View out) {
+    pdl_wait();
     const long long total = out.n * nvox_per_n;
     for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < total;
          v += (long long)gridDim.x * blockDim.x) {
@@ -82,7 +84,7 @@ __global__ void pack_input_kernel(const float* __restrict__ x, long long nvox_pe
 cudaError_t launch_pack_input(const float* x, long long n, long long c, long long d, long long h, long long w,
                               View out, cudaStream_t s) {
     const long long total = n * d * h * w;
-    pack_input_kernel<<<grid_for(total, 256, 148, 16), 256, 0, s>>>(x, d * h * w, (int)c, out);
+    launch_k(pack_input_kernel, grid_for(total, 256, 148, 16), 256, 0, s, x, d * h * w, (int)c, out);
     return cudaGetLastError();
 }
 
@@ -96,6 +98,7 @@ constexpr int kI2cVox = 128;
 // out as contiguous 4-byte words (rows are contiguous in global memory when ld == kpad).
 __global__ void __launch_bounds__(256) im2col_input_kernel(const float* __restrict__ x, int c_in, int D, int H, int W,
                                                            long long nvox, View out) {
+    pdl_wait();
     extern __shared__ uint32_t i2c_smem[];  // [128][kpad/2 + 1] words
     __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(i2c_smem);
     const int kpad = (int)out.c, pitch = kpad / 2 + 1, pitch16 = 2 * pitch;
@@ -148,6 +151,7 @@ __global__ void __launch_bounds__(256) im2col_input_kernel(const float* __restri
 template <int CIN>
 __global__ void __launch_bounds__(256) im2col_input_fixed_kernel(const float* __restrict__ x, int D, int H, int W,
                                                                  long long nvox, View out) {
+    pdl_wait();
     constexpr int K = 27 * CIN, KPAD = (K + 15) / 16 * 16, WORDS = KPAD / 2, PITCH = WORDS | 1, HW = WORDS / 2;
     extern __shared__ uint32_t i2c_smem[];  // [128][PITCH] words
     const long long v0 = (long long)blockIdx.x * kI2cVox;
@@ -201,16 +205,17 @@ cudaError_t launch_im2col_input(const float* x, long long n, long long c, long l
     const long long blocks = (nvox + kI2cVox - 1) / kI2cVox;
     if (c == 5 && out.c == 144 && d * h * w < (1LL << 31)) {
         const int smem = kI2cVox * 73 * 4;
-        im2col_input_fixed_kernel<5><<<(unsigned)blocks, 256, smem, s>>>(x, (int)d, (int)h, (int)w, nvox, out);
+        launch_k(im2col_input_fixed_kernel<5>, (unsigned)blocks, 256, smem, s, x, (int)d, (int)h, (int)w, nvox, out);
         return cudaGetLastError();
     }
     const int smem = kI2cVox * ((int)out.c / 2 + 1) * 4;
-    im2col_input_kernel<<<(unsigned)blocks, 256, smem, s>>>(x, (int)c, (int)d, (int)h, (int)w, nvox, out);
+    launch_k(im2col_input_kernel, (unsigned)blocks, 256, smem, s, x, (int)c, (int)d, (int)h, (int)w, nvox, out);
     return cudaGetLastError();
 }
 
 // fp32 [rows][k] -> bf16 [rows][kpad] (zero padded): GEMM-form weights of the im2col'd first conv
 __global__ void pack_rows_kernel(const float* __restrict__ w, int rows, int k, int kpad, __nv_bfloat16* out) {
+    pdl_wait();
     const long long total = (long long)rows * kpad;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -219,7 +224,27 @@ __global__ void pack_rows_kernel(const float* __restrict__ w, int rows, int k, i
     }
 }
 cudaError_t launch_pack_rows(const float* w, int rows, int k, int kpad, __nv_bfloat16* out, cudaStream_t s) {
-    pack_rows_kernel<<<grid_for((long long)rows * kpad, 256, 148, 8), 256, 0, s>>>(w, rows, k, kpad, out);
+    launch_k(pack_rows_kernel, grid_for((long long)rows * kpad, 256, 148, 8), 256, 0, s, w, rows, k, kpad, out);
+    return cudaGetLastError();
+}
+
+// first-layer weight (Cout, Cin, 3, 3, 3) fp32 -> bf16 [3 kd][Cout][64]: row k = c*9 + kh*3 + kw of depth tap kd
+// (Cin*9 <= 64 real columns, zero padded) — the K-major B operand of conv1_march.cu
+__global__ void pack_conv1_slices_kernel(const float* __restrict__ w, int cout, int cin, __nv_bfloat16* out) {
+    pdl_wait();
+    const int total = 3 * cout * 64;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int k = i & 63, co = (i >> 6) % cout, kd = (i >> 6) / cout;
+        float v = 0.f;
+        if (k < cin * 9) {
+            const int c = k / 9, r = k - 9 * c;
+            v = __ldg(w + ((long long)(co * cin + c) * 3 + kd) * 9 + r);
+        }
+        out[i] = __float2bfloat16_rn(v);
+    }
+}
+cudaError_t launch_pack_conv1_slices(const float* w, int cout, int cin, __nv_bfloat16* out, cudaStream_t s) {
+    launch_k(pack_conv1_slices_kernel, grid_for(3LL * cout * 64, 256, 148, 8), 256, 0, s, w, cout, cin, out);
     return cudaGetLastError();
 }
 
@@ -230,6 +255,7 @@ cudaError_t launch_pack_rows(const float* w, int rows, int k, int kpad, __nv_bfl
 constexpr int kPackPitch = 34;
 __global__ void __launch_bounds__(256) pack_conv_weight_kernel(const float* __restrict__ w, int cout, int cin,
                                                                int cin_pad, __nv_bfloat16* __restrict__ wf) {
+    pdl_wait();
     extern __shared__ __nv_bfloat16 ptile[];  // [27][32][kPackPitch]
     const int co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
     const int tid = threadIdx.x;
@@ -280,7 +306,7 @@ cudaError_t launch_pack_conv_weight(const float* w, int cout, int cin, int cin_p
         if (e != cudaSuccess) return e;
     }
     dim3 grid((cin_pad + 31) / 32, (cout + 31) / 32);
-    pack_conv_weight_kernel<<<grid, 256, smem, s>>>(w, cout, cin, cin_pad, wf);
+    launch_k(pack_conv_weight_kernel, grid, 256, smem, s, w, cout, cin, cin_pad, wf);
     return cudaGetLastError();
 }
 
@@ -288,6 +314,7 @@ cudaError_t launch_pack_conv_weight(const float* w, int cout, int cin, int cin_p
 __global__ void pack_convt_weight_kernel(const float* __restrict__ w, const float* __restrict__ bias, int cin,
                                          int cout, __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd,
                                          float* __restrict__ bias8) {
+    pdl_wait();
     const long long total = (long long)cin * cout * 8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -308,7 +335,7 @@ __global__ void pack_convt_weight_kernel(const float* __restrict__ w, const floa
 }
 cudaError_t launch_pack_convt_weight(const float* w, const float* bias, int cin, int cout, __nv_bfloat16* wf,
                                      __nv_bfloat16* wd, float* bias8, cudaStream_t s) {
-    pack_convt_weight_kernel<<<grid_for((long long)cin * cout * 8, 256, 148, 8), 256, 0, s>>>(w, bias, cin, cout, wf,
+    launch_k(pack_convt_weight_kernel, grid_for((long long)cin * cout * 8, 256, 148, 8), 256, 0, s, w, bias, cin, cout, wf,
                                                                                              wd, bias8);
     return cudaGetLastError();
 }
@@ -356,6 +383,7 @@ __global__ void __launch_bounds__(32 * kRedSlices) bn_finalize_kernel(const floa
                                                           const float* __restrict__ beta, float eps, float momentum,
                                                           float* rm, float* rv, long long* nbt, float* mean,
                                                           float* rstd, float* scale, float* shift) {
+    pdl_wait();
     __shared__ double red[kRedSlices][32][2];
     if (nbt && blockIdx.x == 0 && threadIdx.x == 0) nbt[0] += 1;   // num_batches_tracked
     const int ch = blockIdx.x * 32 + (threadIdx.x & 31), slice = threadIdx.x >> 5;
@@ -379,13 +407,14 @@ cudaError_t launch_bn_finalize(const float* partial, long long rows, long long c
                                const float* beta, float eps, float momentum, float* rm, float* rv, long long* nbt,
                                float* mean, float* rstd, float* scale, float* shift, cudaStream_t s) {
     const double unbias = count > 1 ? (double)count / (double)(count - 1) : 1.0;
-    bn_finalize_kernel<<<(c + 31) / 32, 32 * kRedSlices, 0, s>>>(partial, (int)rows, 1.0 / (double)count, unbias, c, gamma, beta,
+    launch_k(bn_finalize_kernel, (c + 31) / 32, 32 * kRedSlices, 0, s, partial, (int)rows, 1.0 / (double)count, unbias, c, gamma, beta,
                                                     eps, momentum, rm, rv, nbt, mean, rstd, scale, shift);
     return cudaGetLastError();
 }
 
 __global__ void bn_fold_eval_kernel(const float* gamma, const float* beta, const float* rm, const float* rv,
                                     const float* cbias, float eps, int c, float* scale, float* shift) {
+    pdl_wait();
     const int ch = blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= c) return;
     const float sc = gamma[ch] / sqrtf(rv[ch] + eps);
@@ -394,7 +423,7 @@ __global__ void bn_fold_eval_kernel(const float* gamma, const float* beta, const
 }
 cudaError_t launch_bn_fold_eval(const float* gamma, const float* beta, const float* rm, const float* rv,
                                 const float* cbias, float eps, int c, float* scale, float* shift, cudaStream_t s) {
-    bn_fold_eval_kernel<<<(c + 127) / 128, 128, 0, s>>>(gamma, beta, rm, rv, cbias, eps, c, scale, shift);
+    launch_k(bn_fold_eval_kernel, (c + 127) / 128, 128, 0, s, gamma, beta, rm, rv, cbias, eps, c, scale, shift);
     return cudaGetLastError();
 }
 
@@ -404,6 +433,7 @@ cudaError_t launch_bn_fold_eval(const float* gamma, const float* beta, const flo
 __global__ void __launch_bounds__(256) bn_apply_relu_kernel(View y, const float* __restrict__ scale,
                                                             const float* __restrict__ shift, View out, FastDiv c8d,
                                                             uint32_t total) {
+    pdl_wait();
     constexpr int U = 4;
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += U * stride) {
@@ -435,7 +465,7 @@ __global__ void __launch_bounds__(256) bn_apply_relu_kernel(View y, const float*
 cudaError_t launch_bn_apply_relu(View y, const float* scale, const float* shift, View out, int sms, cudaStream_t s) {
     const long long total = y.voxels() * (y.c / 8);
     if (total >= (1LL << 31)) return cudaErrorInvalidValue;
-    bn_apply_relu_kernel<<<grid_for(total, 256, sms, 16), 256, 0, s>>>(y, scale, shift, out,
+    launch_k(bn_apply_relu_kernel, grid_for(total, 256, sms, 16), 256, 0, s, y, scale, shift, out,
                                                                       FastDiv((uint32_t)(y.c / 8)), (uint32_t)total);
     return cudaGetLastError();
 }
@@ -540,6 +570,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(View dout, View y
                                                                const float* __restrict__ mean,
                                                                const float* __restrict__ rstd, float* partial, int c8,
                                                                int rows, long long nvox) {
+    pdl_wait();
     extern __shared__ float smem[];
     const int row = threadIdx.x / c8, cv = threadIdx.x - row * c8;
     const bool active = row < rows;
@@ -585,7 +616,7 @@ cudaError_t launch_bn_bwd_reduce(View dout, View y, const float* scale, const fl
     if (blocks < 1) blocks = 1;
     *nblk = (int)blocks;
     const size_t smem = reduce_smem_bytes(m, 2);
-    bn_bwd_reduce_kernel<<<(int)blocks, 256, smem, s>>>(dout, y, scale, shift, mean, rstd, partial, m.c8, m.rows,
+    launch_k(bn_bwd_reduce_kernel, (int)blocks, 256, smem, s, dout, y, scale, shift, mean, rstd, partial, m.c8, m.rows,
                                                        nvox);
     return cudaGetLastError();
 }
@@ -593,6 +624,7 @@ cudaError_t launch_bn_bwd_reduce(View dout, View y, const float* scale, const fl
 __global__ void __launch_bounds__(32 * kRedSlices) bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int c,
                                                               double inv_count, float* dgamma, float* dbeta,
                                                               float* coef) {
+    pdl_wait();
     __shared__ double red[kRedSlices][32][2];
     const int ch = blockIdx.x * 32 + (threadIdx.x & 31), slice = threadIdx.x >> 5;
     double s1, s2;
@@ -605,7 +637,7 @@ __global__ void __launch_bounds__(32 * kRedSlices) bn_bwd_finalize_kernel(const 
 }
 cudaError_t launch_bn_bwd_finalize(const float* partial, int nblk, int c, long long count, float* dgamma,
                                    float* dbeta, float* coef, cudaStream_t s) {
-    bn_bwd_finalize_kernel<<<(c + 31) / 32, 32 * kRedSlices, 0, s>>>(partial, nblk, c, 1.0 / (double)count, dgamma, dbeta, coef);
+    launch_k(bn_bwd_finalize_kernel, (c + 31) / 32, 32 * kRedSlices, 0, s, partial, nblk, c, 1.0 / (double)count, dgamma, dbeta, coef);
     return cudaGetLastError();
 }
 
@@ -633,6 +665,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(View dout, View y,
                                                               const float* __restrict__ rstd,
                                                               const float* __restrict__ coef, View dy, float* dbias,
                                                               int c8, int rows, long long nvox) {
+    pdl_wait();
     extern __shared__ float smem[];
     const int row = threadIdx.x / c8, cv = threadIdx.x - row * c8;
     const bool active = row < rows;
@@ -678,7 +711,7 @@ cudaError_t launch_bn_bwd_apply(View dout, View y, const float* scale, const flo
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
     const size_t smem = reduce_smem_bytes(m, 1);
-    bn_bwd_apply_kernel<<<(int)blocks, 256, smem, s>>>(dout, y, scale, shift, mean, rstd, coef, dy, dbias, m.c8, m.rows,
+    launch_k(bn_bwd_apply_kernel, (int)blocks, 256, smem, s, dout, y, scale, shift, mean, rstd, coef, dy, dbias, m.c8, m.rows,
                                                       nvox);
     return cudaGetLastError();
 }
@@ -690,6 +723,7 @@ cudaError_t launch_bn_bwd_apply(View dout, View y, const float* scale, const flo
 __global__ void __launch_bounds__(256) channel_sum_kernel(View v, float* out, int c8, int rows, long long nvox,
                                                           int d0, int h0, int w0, FastDiv bwd, FastDiv bhd,
                                                           FastDiv bdd, int boxed) {
+    pdl_wait();
     extern __shared__ float smem[];
     const int row = threadIdx.x / c8, cv = threadIdx.x - row * c8;
     const bool active = row < rows;
@@ -747,7 +781,7 @@ cudaError_t launch_channel_sum(View v, float* out, const int* box, cudaStream_t 
     if (blocks > 148 * 4) blocks = 148 * 4;
     if (blocks < 1) blocks = 1;
     const size_t smem = reduce_smem_bytes(m, 1);
-    channel_sum_kernel<<<(int)blocks, 256, smem, s>>>(v, out, m.c8, m.rows, nvox, d0, h0, w0, bw, bh, bd, boxed);
+    launch_k(channel_sum_kernel, (int)blocks, 256, smem, s, v, out, m.c8, m.rows, nvox, d0, h0, w0, bw, bh, bd, boxed);
     return cudaGetLastError();
 }
 
@@ -758,6 +792,7 @@ DEV __nv_bfloat162 max2_nan(__nv_bfloat162 a, __nv_bfloat162 b) { return __hmax2
 
 __global__ void __launch_bounds__(256) maxpool_fwd_kernel(View x, View y, FastDiv c8d, FastDiv owd, FastDiv ohd,
                                                           FastDiv odd, uint32_t total) {
+    pdl_wait();
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         uint32_t r = c8d.quot(i);
         const uint32_t c0 = (i - r * c8d.div) * 8;
@@ -785,7 +820,7 @@ cudaError_t launch_maxpool_fwd(View x, View y, int sms, cudaStream_t s) {
     const long long total = y.voxels() * (y.c / 8);
     if (total >= (1LL << 31)) return cudaErrorInvalidValue;
     if (total == 0) return cudaSuccess;
-    maxpool_fwd_kernel<<<grid_for(total, 256, sms, 16), 256, 0, s>>>(x, y, FastDiv((uint32_t)(y.c / 8)),
+    launch_k(maxpool_fwd_kernel, grid_for(total, 256, sms, 16), 256, 0, s, x, y, FastDiv((uint32_t)(y.c / 8)),
                                                                     FastDiv((uint32_t)y.w), FastDiv((uint32_t)y.h),
                                                                     FastDiv((uint32_t)y.d), (uint32_t)total);
     return cudaGetLastError();
@@ -798,6 +833,7 @@ DEV __nv_bfloat162 from_bits(uint32_t u) { return *reinterpret_cast<__nv_bfloat1
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(View x, View dy, View dskip, int has_skip, View dx,
                                                           FastDiv c8d, FastDiv cwd, FastDiv chd, FastDiv cdd,
                                                           uint32_t total) {
+    pdl_wait();
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         uint32_t r = c8d.quot(i);
         const uint32_t c0 = (i - r * c8d.div) * 8;
@@ -868,7 +904,7 @@ cudaError_t launch_maxpool_bwd(View x, View dy, const View* dskip, View dx, int 
     const long long total = x.n * cd * ch * cw * (x.c / 8);
     if (total >= (1LL << 31)) return cudaErrorInvalidValue;
     View sk = dskip ? *dskip : dx;
-    maxpool_bwd_kernel<<<grid_for(total, 256, sms, 16), 256, 0, s>>>(
+    launch_k(maxpool_bwd_kernel, grid_for(total, 256, sms, 16), 256, 0, s, 
         x, dy, sk, dskip ? 1 : 0, dx, FastDiv((uint32_t)(x.c / 8)), FastDiv((uint32_t)cw), FastDiv((uint32_t)ch),
         FastDiv((uint32_t)cd), (uint32_t)total);
     return cudaGetLastError();
@@ -880,6 +916,7 @@ constexpr int kMaxHeadC = 256;
 __global__ void __launch_bounds__(256) head_fwd_kernel(View x, const float* __restrict__ w,
                                                        const float* __restrict__ b, int ncls, float* logits,
                                                        float* probs, long long nvox_per_n) {
+    pdl_wait();
     __shared__ float ws[kMaxCls * kMaxHeadC];
     __shared__ float bs[kMaxCls];
     const int c = (int)x.c;
@@ -923,6 +960,7 @@ template <int NCLS>
 __global__ void __launch_bounds__(256) head_fwd_vec_kernel(View x, const float* __restrict__ w,
                                                            const float* __restrict__ b, float* logits, float* probs,
                                                            int c8, long long nvox, long long nvox_per_n) {
+    pdl_wait();
     constexpr int U = 4;
     const int rows = 256 / c8, g = threadIdx.x / c8, cv = threadIdx.x - g * c8;
     const int c = (int)x.c;
@@ -978,7 +1016,7 @@ static cudaError_t head_fwd_vec_launch(View x, const float* w, const float* b, f
     long long blocks = (nvox + (256 / c8) * 4 - 1) / ((256 / c8) * 4);
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
-    head_fwd_vec_kernel<NCLS><<<(int)blocks, 256, 0, s>>>(x, w, b, logits, probs, c8, nvox, x.d * x.h * x.w);
+    launch_k(head_fwd_vec_kernel<NCLS>, (int)blocks, 256, 0, s, x, w, b, logits, probs, c8, nvox, x.d * x.h * x.w);
     return cudaGetLastError();
 }
 cudaError_t launch_head_fwd(View x, const float* w, const float* b, int ncls, float* logits, float* probs,
@@ -989,7 +1027,7 @@ cudaError_t launch_head_fwd(View x, const float* w, const float* b, int ncls, fl
         return ncls == 1 ? head_fwd_vec_launch<1>(x, w, b, logits, probs, s)
                          : head_fwd_vec_launch<2>(x, w, b, logits, probs, s);
     }
-    head_fwd_kernel<<<grid_for(x.voxels(), 256, 148, 16), 256, 0, s>>>(x, w, b, ncls, logits, probs,
+    launch_k(head_fwd_kernel, grid_for(x.voxels(), 256, 148, 16), 256, 0, s, x, w, b, ncls, logits, probs,
                                                                       x.d * x.h * x.w);
     return cudaGetLastError();
 }
@@ -999,6 +1037,7 @@ template <int NCLS>
 __global__ void __launch_bounds__(256) head_bwd_kernel(View x, const float* __restrict__ w,
                                                        const float* __restrict__ dl, View dx, float* dw, float* db,
                                                        int c8, int rows, long long nvox, long long nvox_per_n) {
+    pdl_wait();
     extern __shared__ float smem[];
     const int row = threadIdx.x / c8, cv = threadIdx.x - row * c8;
     const bool active = row < rows;
@@ -1071,7 +1110,7 @@ static cudaError_t head_bwd_launch(View x, const float* w, const float* dl, View
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
     const size_t smem = (size_t)m.rows * m.c8 * NCLS * 8 * sizeof(float);
-    head_bwd_kernel<NCLS><<<(int)blocks, 256, smem, s>>>(x, w, dl, dx, dw, db, m.c8, m.rows, nvox, x.d * x.h * x.w);
+    launch_k(head_bwd_kernel<NCLS>, (int)blocks, 256, smem, s, x, w, dl, dx, dw, db, m.c8, m.rows, nvox, x.d * x.h * x.w);
     return cudaGetLastError();
 }
 cudaError_t launch_head_bwd(View x, const float* w, int ncls, const float* dlogits, View dx, float* dw, float* db,
@@ -1123,6 +1162,7 @@ __global__ void __launch_bounds__(256) bn_apply_relu_pool_kernel(View y, const f
                                                                  const float* __restrict__ shift, View out,
                                                                  View pooled, FastDiv c8d, FastDiv cwd, FastDiv chd,
                                                                  FastDiv cdd, uint32_t total) {
+    pdl_wait();
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const uint32_t cell = c8d.quot(i);
         const uint32_t c0 = (i - cell * c8d.div) * 8;
@@ -1172,7 +1212,7 @@ cudaError_t launch_bn_apply_relu_pool(View y, const float* scale, const float* s
     const long long total = y.n * cd * ch * cw * (y.c / 8);
     if (total >= (1LL << 31)) return cudaErrorInvalidValue;
     if (total == 0) return cudaSuccess;
-    bn_apply_relu_pool_kernel<<<grid_for(total, 256, sms, 16), 256, 0, s>>>(
+    launch_k(bn_apply_relu_pool_kernel, grid_for(total, 256, sms, 16), 256, 0, s, 
         y, scale, shift, out, pooled, FastDiv((uint32_t)(y.c / 8)), FastDiv((uint32_t)cw), FastDiv((uint32_t)ch),
         FastDiv((uint32_t)cd), (uint32_t)total);
     return cudaGetLastError();
@@ -1215,6 +1255,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_head_kernel(const float* __rest
                                                              const float* __restrict__ coef, float* partial, View dy,
                                                              float* dbias, float* dw, float* db, int c8, int rows,
                                                              long long nvox, long long nvox_per_n) {
+    pdl_wait();
     extern __shared__ float smem[];
     const int row = threadIdx.x / c8, cv = threadIdx.x - row * c8;
     const bool active = row < rows;
@@ -1355,7 +1396,7 @@ static cudaError_t bn_bwd_head_launch(bool apply, const float* dl, const float* 
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     if (apply) {
-        bn_bwd_head_kernel<NCLS, true><<<(int)blocks, 256, reduce_smem_bytes(m, 1), s>>>(
+        launch_k(bn_bwd_head_kernel<NCLS, true>, (int)blocks, 256, reduce_smem_bytes(m, 1), s, 
             dl, w, y, scale, shift, mean, rstd, coef, nullptr, dy, dbias, nullptr, nullptr, m.c8, m.rows, nvox,
             y.d * y.h * y.w);
     } else {
@@ -1363,7 +1404,7 @@ static cudaError_t bn_bwd_head_launch(bool apply, const float* dl, const float* 
         size_t smem = reduce_smem_bytes(m, 2);
         const size_t head = (size_t)m.rows * m.c8 * NCLS * 8 * sizeof(float);
         if (head > smem) smem = head;
-        bn_bwd_head_kernel<NCLS, false><<<(int)blocks, 256, smem, s>>>(dl, w, y, scale, shift, mean, rstd, nullptr,
+        launch_k(bn_bwd_head_kernel<NCLS, false>, (int)blocks, 256, smem, s, dl, w, y, scale, shift, mean, rstd, nullptr,
                                                                       partial, y, nullptr, dw, db, m.c8, m.rows, nvox,
                                                                       y.d * y.h * y.w);
     }
@@ -1397,6 +1438,7 @@ DEV float sigmoidf_(float z) { return 1.f / (1.f + expf(-z)); }
 
 __global__ void __launch_bounds__(256) loss_partial_kernel(const float* __restrict__ z, const float* __restrict__ t,
                                                            long long n, float* ws) {
+    pdl_wait();
     float s[4] = {0.f, 0.f, 0.f, 0.f};
     const long long n4 = n >> 2;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
@@ -1438,6 +1480,7 @@ __global__ void __launch_bounds__(256) loss_partial_kernel(const float* __restri
 }
 __global__ void loss_finalize_kernel(const float* __restrict__ ws, int nblk, double inv_n, float bce_w, float dice_w,
                                      float smooth, float* sums, float* loss) {
+    pdl_wait();
     __shared__ double red[4][4];
     const int j = threadIdx.x & 3, part = threadIdx.x >> 2;  // 16 threads: 4 sums x 4 parts
     double a = 0.0;
@@ -1456,8 +1499,8 @@ cudaError_t launch_loss_fwd(const float* z, const float* t, long long n, float b
                             float* ws, float* sums, float* loss, int sms, cudaStream_t s) {
     int blocks = grid_for(n / 4 + 1, 256, sms, 4);
     if (blocks > kLossMaxBlocks) blocks = kLossMaxBlocks;
-    loss_partial_kernel<<<blocks, 256, 0, s>>>(z, t, n, ws);
-    loss_finalize_kernel<<<1, 16, 0, s>>>(ws, blocks, 1.0 / (double)n, bce_w, dice_w, smooth, sums, loss);
+    launch_k(loss_partial_kernel, blocks, 256, 0, s, z, t, n, ws);
+    launch_k(loss_finalize_kernel, 1, 16, 0, s, ws, blocks, 1.0 / (double)n, bce_w, dice_w, smooth, sums, loss);
     return cudaGetLastError();
 }
 
@@ -1465,6 +1508,7 @@ __global__ void __launch_bounds__(256) loss_bwd_kernel(const float* __restrict__
                                                        long long n, float bce_w, float dice_w, float smooth,
                                                        const float* __restrict__ sums, const float* __restrict__ gout,
                                                        float* dz) {
+    pdl_wait();
     const float g = gout[0];
     const float I = sums[1], P = sums[2], T = sums[3];
     const float B = P + T + smooth, A = 2.f * I + smooth;
@@ -1479,7 +1523,7 @@ __global__ void __launch_bounds__(256) loss_bwd_kernel(const float* __restrict__
 }
 cudaError_t launch_loss_bwd(const float* z, const float* t, long long n, float bce_w, float dice_w, float smooth,
                             const float* sums, const float* gout, float* dz, int sms, cudaStream_t s) {
-    loss_bwd_kernel<<<grid_for(n, 256, sms, 8), 256, 0, s>>>(z, t, n, bce_w, dice_w, smooth, sums, gout, dz);
+    launch_k(loss_bwd_kernel, grid_for(n, 256, sms, 8), 256, 0, s, z, t, n, bce_w, dice_w, smooth, sums, gout, dz);
     return cudaGetLastError();
 }
 
@@ -1489,6 +1533,7 @@ DEV uint32_t pack2(float lo, float hi) {
 }
 __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ x, long long n,
                                                         __nv_bfloat16* __restrict__ out) {
+    pdl_wait();
     const long long n8 = n >> 3;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
          i += (long long)gridDim.x * blockDim.x) {
@@ -1502,7 +1547,7 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
         for (long long i = (n8 << 3) + threadIdx.x; i < n; i += blockDim.x) out[i] = __float2bfloat16_rn(x[i]);
 }
 cudaError_t launch_cast_bf16(const float* x, long long n, __nv_bfloat16* out, int sms, cudaStream_t s) {
-    cast_bf16_kernel<<<grid_for(n / 8 + 1, 256, sms, 8), 256, 0, s>>>(x, n, out);
+    launch_k(cast_bf16_kernel, grid_for(n / 8 + 1, 256, sms, 8), 256, 0, s, x, n, out);
     return cudaGetLastError();
 }
 
@@ -1512,6 +1557,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
                                                    float step_size, float b2, float w1, float w2, float eps,
                                                    float wd, float bc2_sqrt, float gscale, const float* found_inf,
                                                    __nv_bfloat16* __restrict__ shadow, const float* __restrict__ dyn) {
+    pdl_wait();
     // torch.optim.Adam arithmetic: m.lerp_(g, 1-b1); v.mul_(b2).addcmul_(g, g, 1-b2); p.addcdiv_(m, sqrt(v)/bc2+eps)
     if (found_inf && *found_inf != 0.f) return;
     if (dyn) {   // step-dependent scalars from device memory: the launch can be replayed from a CUDA graph
@@ -1564,13 +1610,14 @@ cudaError_t launch_adam(float* p, const float* g, float* m, float* v, long long 
                         __nv_bfloat16* shadow, const float* dyn, int sms, cudaStream_t s) {
     const double bc1 = 1.0 - pow(b1, (double)step);
     const double bc2 = 1.0 - pow(b2, (double)step);
-    adam_kernel<<<grid_for(n / 4 + 1, 256, sms, 8), 256, 0, s>>>(p, g, m, v, n, (float)(lr / bc1), (float)b2,
+    launch_k(adam_kernel, grid_for(n / 4 + 1, 256, sms, 8), 256, 0, s, p, g, m, v, n, (float)(lr / bc1), (float)b2,
                                                                 (float)(1.0 - b1), (float)(1.0 - b2), (float)eps,
                                                                 (float)wd, (float)sqrt(bc2), (float)gscale, found_inf, shadow, dyn);
     return cudaGetLastError();
 }
 
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, long long n, float* out) {
+    pdl_wait();
     float s = 0.f;
     bool bad = false;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
@@ -1592,12 +1639,13 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x,
     }
 }
 cudaError_t launch_sumsq(const float* x, long long n, float* out, int sms, cudaStream_t s) {
-    sumsq_kernel<<<grid_for(n, 256, sms, 4), 256, 0, s>>>(x, n, out);
+    launch_k(sumsq_kernel, grid_for(n, 256, sms, 4), 256, 0, s, x, n, out);
     return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------ helpers
 __global__ void __launch_bounds__(256) fill_zero_kernel(View v, FastDiv c8d, uint32_t total) {
+    pdl_wait();
     const uint4 z = make_uint4(0, 0, 0, 0);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const uint32_t vox = c8d.quot(i);
@@ -1609,11 +1657,12 @@ cudaError_t launch_fill_zero(View v, int sms, cudaStream_t s) {
     const long long total = v.voxels() * (v.c / 8);
     if (total >= (1LL << 31)) return cudaErrorInvalidValue;
     if (total == 0) return cudaSuccess;
-    fill_zero_kernel<<<grid_for(total, 256, sms, 16), 256, 0, s>>>(v, FastDiv((uint32_t)(v.c / 8)), (uint32_t)total);
+    launch_k(fill_zero_kernel, grid_for(total, 256, sms, 16), 256, 0, s, v, FastDiv((uint32_t)(v.c / 8)), (uint32_t)total);
     return cudaGetLastError();
 }
 
 __global__ void unpack_act_kernel(View v, float* out, long long nvox_per_n) {
+    pdl_wait();
     const long long total = v.voxels() * v.c;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -1625,7 +1674,7 @@ __global__ void unpack_act_kernel(View v, float* out, long long nvox_per_n) {
     }
 }
 cudaError_t launch_unpack_act(View v, float* out, cudaStream_t s) {
-    unpack_act_kernel<<<grid_for(v.voxels() * v.c, 256, 148, 16), 256, 0, s>>>(v, out, v.d * v.h * v.w);
+    launch_k(unpack_act_kernel, grid_for(v.voxels() * v.c, 256, 148, 16), 256, 0, s, v, out, v.d * v.h * v.w);
     return cudaGetLastError();
 }
 
@@ -1643,6 +1692,7 @@ cudaError_t launch_unpack_act(View v, float* out, cudaStream_t s) {
 __global__ void __launch_bounds__(256) resample3d_kernel(const float* __restrict__ in, int di, int hi, int wi,
                                                          float* __restrict__ out, int dout, int ho, int wo,
                                                          long long nvol, int nearest, int binarize) {
+    pdl_wait();
     const double sd = (double)di / dout, sh = (double)hi / ho, sw = (double)wi / wo;
     const long long per = (long long)dout * ho * wo, total = nvol * per;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -1680,7 +1730,7 @@ cudaError_t launch_resample3d(const float* in, long long nvol, int di, int hi, i
                               int wo, int nearest, int binarize, int sms, cudaStream_t s) {
     const long long total = nvol * dout * ho * wo;
     if (total == 0) return cudaSuccess;
-    resample3d_kernel<<<grid_for(total, 256, sms, 16), 256, 0, s>>>(in, di, hi, wi, out, dout, ho, wo, nvol, nearest,
+    launch_k(resample3d_kernel, grid_for(total, 256, sms, 16), 256, 0, s, in, di, hi, wi, out, dout, ho, wo, nvol, nearest,
                                                                    binarize);
     return cudaGetLastError();
 }
@@ -1692,10 +1742,12 @@ DEV uint32_t f2key(float f) {
 }
 DEV float key2f(uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
 __global__ void minmax_init_kernel(uint32_t* keys, int nvol) {
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nvol) { keys[2 * i] = 0xffffffffu; keys[2 * i + 1] = 0u; }
 }
 __global__ void __launch_bounds__(256) minmax_reduce_kernel(const float* __restrict__ x, long long per, uint32_t* keys) {
+    pdl_wait();
     const int vol = blockIdx.y;
     const float* src = x + vol * per;
     float lo = INFINITY, hi = -INFINITY;
@@ -1716,6 +1768,7 @@ __global__ void __launch_bounds__(256) minmax_reduce_kernel(const float* __restr
 }
 __global__ void __launch_bounds__(256) minmax_apply_kernel(float* __restrict__ x, long long per,
                                                            const uint32_t* __restrict__ keys) {
+    pdl_wait();
     const int vol = blockIdx.y;
     const float lo = key2f(keys[2 * vol]), hi = key2f(keys[2 * vol + 1]);
     const bool flat = !(hi > lo);          // constant volume -> zeros (predict.py's division guard)
@@ -1726,12 +1779,12 @@ __global__ void __launch_bounds__(256) minmax_apply_kernel(float* __restrict__ x
 }
 cudaError_t launch_minmax_normalize(float* x, long long nvol, long long per, uint32_t* keys, int sms, cudaStream_t s) {
     if (nvol == 0 || per == 0) return cudaSuccess;
-    minmax_init_kernel<<<(int)((nvol + 127) / 128), 128, 0, s>>>(keys, (int)nvol);
+    launch_k(minmax_init_kernel, (int)((nvol + 127) / 128), 128, 0, s, keys, (int)nvol);
     int bx = grid_for(per, 256, sms, 8);
     if (bx * nvol > (long long)sms * 16) bx = (int)((sms * 16 + nvol - 1) / nvol);
     dim3 grid(bx, (unsigned)nvol);
-    minmax_reduce_kernel<<<grid, 256, 0, s>>>(x, per, keys);
-    minmax_apply_kernel<<<grid, 256, 0, s>>>(x, per, keys);
+    launch_k(minmax_reduce_kernel, grid, 256, 0, s, x, per, keys);
+    launch_k(minmax_apply_kernel, grid, 256, 0, s, x, per, keys);
     return cudaGetLastError();
 }
 
@@ -1740,6 +1793,7 @@ cudaError_t launch_minmax_normalize(float* x, long long nvol, long long per, uin
 __global__ void __launch_bounds__(256) seg_counts_kernel(const float* __restrict__ score,
                                                          const float* __restrict__ label, long long per,
                                                          float threshold, unsigned long long* counts) {
+    pdl_wait();
     const int smp = blockIdx.y;
     const float* sc = score + smp * per;
     const float* lb = label + smp * per;
@@ -1765,7 +1819,7 @@ cudaError_t launch_seg_counts(const float* score, const float* label, long long 
     int bx = grid_for(per, 256, sms, 8);
     if (bx * nsmp > (long long)sms * 16) bx = (int)((sms * 16 + nsmp - 1) / nsmp);
     if (bx < 1) bx = 1;
-    seg_counts_kernel<<<dim3(bx, (unsigned)nsmp), 256, 0, s>>>(score, label, per, threshold, counts);
+    launch_k(seg_counts_kernel, dim3(bx, (unsigned)nsmp), 256, 0, s, score, label, per, threshold, counts);
     return cudaGetLastError();
 }
 
@@ -1778,6 +1832,7 @@ __global__ void __launch_bounds__(256) splitk_finalize_kernel(const float* __res
                                                               const float* __restrict__ v0,
                                                               const float* __restrict__ v1, float* partial, int c8,
                                                               int rows, long long nvox) {
+    pdl_wait();
     extern __shared__ float smem[];
     const int row = threadIdx.x / c8, cv = threadIdx.x - row * c8;
     const bool active = row < rows;
@@ -1832,7 +1887,7 @@ cudaError_t launch_splitk_finalize(const float* ws, int splits, View y, int mode
     const LaneMap m = lane_map(y.c);
     const long long nvox = y.voxels();
     const size_t smem = mode == 1 ? reduce_smem_bytes(m, 2) : 0;
-    splitk_finalize_kernel<<<splitk_finalize_blocks(nvox, y.c), 256, smem, s>>>(ws, splits, y, mode, v0, v1, partial,
+    launch_k(splitk_finalize_kernel, splitk_finalize_blocks(nvox, y.c), 256, smem, s, ws, splits, y, mode, v0, v1, partial,
                                                                                 m.c8, m.rows, nvox);
     return cudaGetLastError();
 }
@@ -1846,6 +1901,7 @@ __global__ void __launch_bounds__(256) window_gather_kernel(const float* __restr
                                                             long long H, long long W, const int* __restrict__ org,
                                                             int wd, int wh, int ww, float* __restrict__ out,
                                                             long long per_win) {
+    pdl_wait();
     const int win = blockIdx.y;
     const int v = org[4 * win], d0 = org[4 * win + 1], h0 = org[4 * win + 2], w0 = org[4 * win + 3];
     const float* src = x + (long long)v * C * D * H * W;
@@ -1863,7 +1919,7 @@ cudaError_t launch_window_gather(const float* x, long long c, long long d, long 
                                  int nwin, int wd, int wh, int ww, float* out, int sms, cudaStream_t s) {
     const long long per = c * wd * wh * ww;
     dim3 grid((unsigned)grid_for(per, 256, sms, 8), (unsigned)nwin);
-    window_gather_kernel<<<grid, 256, 0, s>>>(x, c, d, h, w, org, wd, wh, ww, out, per);
+    launch_k(window_gather_kernel, grid, 256, 0, s, x, c, d, h, w, org, wd, wh, ww, out, per);
     return cudaGetLastError();
 }
 // one thread per voxel of the volumes [v_lo, v_lo + v_cnt): the windows of the launch that cover it are added in
@@ -1872,6 +1928,7 @@ __global__ void __launch_bounds__(256) window_accumulate_kernel(const float* __r
                                                                 int nwin, long long K, int wd, int wh, int ww,
                                                                 float* __restrict__ acc, long long D, long long H,
                                                                 long long W, int v_lo, long long total) {
+    pdl_wait();
     extern __shared__ int s_org[];
     for (int i = threadIdx.x; i < 4 * nwin; i += blockDim.x) s_org[i] = org[i];
     __syncthreads();
@@ -1903,7 +1960,7 @@ cudaError_t launch_window_accumulate(const float* lg, const int* org, int nwin, 
                                      float* acc, long long d, long long h, long long w, int v_lo, int v_cnt, int sms,
                                      cudaStream_t s) {
     const long long total = (long long)v_cnt * k * d * h * w;
-    window_accumulate_kernel<<<grid_for(total, 256, sms, 16), 256, 4 * nwin * sizeof(int), s>>>(
+    launch_k(window_accumulate_kernel, grid_for(total, 256, sms, 16), 256, 4 * nwin * sizeof(int), s, 
         lg, org, nwin, k, wd, wh, ww, acc, d, h, w, v_lo, total);
     return cudaGetLastError();
 }
@@ -1911,6 +1968,7 @@ __global__ void __launch_bounds__(256) window_finalize_kernel(float* __restrict_
                                                               long long D, long long H, long long W, float threshold,
                                                               float* __restrict__ probs, float* __restrict__ mask,
                                                               long long total) {
+    pdl_wait();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         long long r = i;
@@ -1928,7 +1986,7 @@ __global__ void __launch_bounds__(256) window_finalize_kernel(float* __restrict_
 cudaError_t launch_window_finalize(float* acc, const int* cover, long long nk, long long d, long long h, long long w,
                                    float threshold, float* probs, float* mask, int sms, cudaStream_t s) {
     const long long total = nk * d * h * w;
-    window_finalize_kernel<<<grid_for(total, 256, sms, 16), 256, 0, s>>>(acc, cover, d, h, w, threshold, probs, mask,
+    launch_k(window_finalize_kernel, grid_for(total, 256, sms, 16), 256, 0, s, acc, cover, d, h, w, threshold, probs, mask,
                                                                         total);
     return cudaGetLastError();
 }

@@ -6,6 +6,7 @@
 // channel block): three kd slabs), TMEM ring (one 64-column slot per output slice).
 #include <cuda_bf16.h>
 #include "igemm.cuh"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace b200 {
@@ -64,6 +65,7 @@ DEV void dmarch_body(const DmarchParams& p) {
     tc_fence_before();
     if (kPair) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
+    pdl_wait();   // launch.cuh: the predecessor's results are complete and visible from here on
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_smem - smem_base));
 
     const int columns = p.nbatch * p.nbw * p.nbh;

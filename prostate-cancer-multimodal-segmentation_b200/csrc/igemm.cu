@@ -8,6 +8,7 @@
 // lane), warp 2 = TMEM allocator, warps 4..7 = epilogue (TMEM lane quarter = warp % 4).
 #include <cuda_bf16.h>
 #include "igemm.cuh"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace b200 {
@@ -196,6 +197,7 @@ DEV void igemm_body(const IgemmParams& p) {
     tc_fence_before();
     if (kPair) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
+    pdl_wait();   // launch.cuh: the predecessor's results are complete and visible from here on
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_smem - smem_base));
 
     // work units: (M tile, N tile), or in pair mode (pair of adjacent M tiles, N tile); a pair walks the same units,
@@ -745,6 +747,7 @@ DEV void wgrad_body(const WgradParams& p) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();   // launch.cuh: the predecessor's results are complete and visible from here on
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_smem - smem_base));
 
     // work decode: blockIdx = (split * n_groups + group) * p_tiles + ptile

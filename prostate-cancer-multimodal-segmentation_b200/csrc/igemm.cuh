@@ -171,4 +171,28 @@ struct alignas(64) WgradHaloParams {
     long long st, sp, sq;
 };
 
+// Depth-marching forward of the 5-modality first layer (conv1_march.cu): slice images of 48 rows (45 real: k = c*9 +
+// kh*3 + kw) x 128 voxels, MN-major, two 64-voxel halves kC1HalfBytes apart
+constexpr int kC1Threads = 512;
+constexpr int kC1Cin = 5;
+constexpr int kC1Rows = 48;
+constexpr int kC1HalfBytes = kC1Rows * 128;
+constexpr int kC1ImgBytes = 2 * kC1HalfBytes;
+constexpr int kC1Imgs = 6;       // slice-image ring
+constexpr int kC1Slots = 8;      // TMEM ring: 64-column accumulators (one output slice each)
+constexpr int kC1Smem = 1024 + kC1Imgs * kC1ImgBytes + 3 * 8192 + 2 * kBoxBytes + 8 * (2 * kC1Imgs + 2 * kC1Slots + 1) +
+                        64 + (8 * 64 * 2 + 2 * 64) * 4;
+struct alignas(64) Conv1MarchParams {
+    CUtensorMap b_map;   // packed weights [3 kd][Cout][64] (k = c*9 + kh*3 + kw, 45 real), box (64, 64, 1)
+    CUtensorMap c_map;   // output store, box (64 ch, 8 w, 16 h, 1, 1)
+    const float* x;      // (N, 5, D, H, W) fp32
+    const float* vec0;
+    const float* vec1;
+    float* stats;        // [gridDim.x][ncols][2]
+    int ncols;           // valid output columns (<= 64; computed as 64 against zero-filled weight rows)
+    int W, H, D, nbatch, nbw, nbh;
+    int seg_len, nseg;
+    int mode;
+};
+
 }  // namespace b200

@@ -2,6 +2,7 @@
 // G[tap][p][q] += sum_voxel P[voxel][p] * Q[voxel + s*off(tap)][q], both operands voxel-major (MN-major UMMA operands).
 #include <cuda_bf16.h>
 #include "igemm.cuh"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace b200 {
@@ -53,6 +54,7 @@ extern "C" __global__ void __launch_bounds__(kThreads, 1) wgrad_halo_kernel(cons
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();   // launch.cuh: the predecessor's results are complete and visible from here on
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_smem - smem_base));
 
     // work decode: CTAs [0, (n_groups-1)*splits*p_tiles) cover the full groups, the rest the last group, which may be

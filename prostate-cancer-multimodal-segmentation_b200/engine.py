@@ -47,6 +47,8 @@ def _slot_view(flat: torch.Tensor, off: int, p) -> torch.Tensor:
 # A/B switch for tools/ab_fused.py only: False runs the unfused chains (bn_apply_relu + maxpool3d_fwd, head_bwd +
 # bn_bwd) the fused BatchNorm passes replace; same results, more HBM traffic.
 FUSE_BN_PASSES = True
+# forward of the 5-modality first layer: depth-marching kernel (csrc/conv1_march.cu) instead of the generic direct one
+USE_CONV1_MARCH = True
 
 _SPLITK_WS = {}   # device -> list of scratch tensors, the last one is the largest
 
@@ -85,6 +87,9 @@ class _ConvPack:
         # the 5-modality first layer reads the fp32 network input directly: its im2col rows are built in shared
         # memory inside the GEMM kernels (ops.conv1_direct_*), never in HBM
         self.direct = self.im2col and ops.conv1_direct_supported(self.cin, self.cout, 4)
+        # ... and its forward marches along depth when the layer is narrow enough (csrc/conv1_march.cu)
+        self.march = USE_CONV1_MARCH and self.direct and ops.conv1_march_supported(self.cin, self.cout)
+        self._slices = (torch.empty(3, self.cout, 64, device=device, dtype=torch.bfloat16) if self.march else None)
         self.shadow = None   # set by the engine: bf16 [27][Cout][Cin] view of its parameter shadow
         self._own = None
         if self.im2col:
@@ -109,6 +114,8 @@ class _ConvPack:
     def pack(self):
         if self.im2col:
             ops.pack_rows(self.conv.weight.data, self.cin_pad, self._own)
+            if self.march:
+                ops.pack_conv1_slices(self.conv.weight.data.contiguous(), self._slices)
         elif not self._phys(self.conv.weight.data):
             ops.pack_conv_weight(self.conv.weight.data.contiguous(), self.cin_pad, self.wf)
 
@@ -123,7 +130,9 @@ class _ConvPack:
         return v
 
     def fprop(self, xin, bias, y, stats, mode, scale=None, shift=None, workspace=None):
-        if isinstance(xin, RawInput):
+        if isinstance(xin, RawInput) and self.march:
+            ops.conv1_march_fprop(xin.t, self._slices, bias, y, stats, mode, scale, shift)
+        elif isinstance(xin, RawInput):
             ops.conv1_direct_fprop(xin.t, self.wf, bias, y, stats, mode, scale, shift)
         elif self.im2col:
             ops.conv1_fprop(xin, self.wf, bias, y, stats, mode, scale, shift, k_real=self.k_real)
@@ -202,7 +211,8 @@ class _DoubleConv:
                              f"{(n, cout, d, h, w)}")
         y = ActView(new_act(n, d, h, w, cout, dev))
         ws = None if pack.im2col else _splitk_workspace(dev, n, d, h, w, cout)
-        rows = (ops.conv1_direct_stat_rows(n, d, h, w, cout) if isinstance(xin, RawInput)
+        rows = ((ops.conv1_march_stat_rows if pack.march else ops.conv1_direct_stat_rows)(n, d, h, w, cout)
+                if isinstance(xin, RawInput)
                 else ops.conv3d_stat_rows(n, d, h, w, cout, 1 if pack.im2col else 27, with_workspace=ws is not None))
         stats = torch.empty(rows, cout, 2, device=dev, dtype=torch.float32)
         pack.fprop(xin, pack.conv.bias.data, y, stats, ops.EPI_BIAS_STATS, workspace=ws)

@@ -85,6 +85,12 @@ def sm_count() -> int:
     return _lib.load().b200_sm_count()
 
 
+def set_pdl(on: bool) -> bool:
+    """process-wide switch of programmatic dependent launch (csrc/launch.cuh; default on); returns the previous value.
+    A CUDA graph keeps the kind of edges it was captured with."""
+    return bool(_lib.load().b200_set_pdl(1 if on else 0))
+
+
 def pack_input(x: torch.Tensor, out: ActView):
     _launched(1)
     n, c, d, h, w = x.shape
@@ -143,6 +149,37 @@ def conv1_direct_fprop(x: torch.Tensor, w_rows, bias, y: ActView, stats=None, mo
     _gemm("igemm_im2col5_kernel", "conv1_fprop", 2.0 * y.voxels * y.c * 27 * c,
           lambda: check(lib.b200_conv1_direct_fprop(ptr(x), n, c, d, h, w, ptr(w_rows), ptr(bias), y.ref, ptr(stats),
                                                     mode, ptr(scale), ptr(shift), stream_ptr()), "conv1_direct_fprop"),
+          shape=(y.voxels, c, y.c))
+
+
+def conv1_march_supported(cin: int, cout: int) -> bool:
+    return bool(_lib.load().b200_conv1_march_supported(cin, cout))
+
+
+def conv1_march_stat_rows(n, d, h, w, cout) -> int:
+    r = _lib.load().b200_conv1_march_stat_rows(n, d, h, w, cout)
+    if r <= 0:
+        raise _lib.B200Error("b200_conv1_march_stat_rows failed (no CUDA device?)")
+    return r
+
+
+def pack_conv1_slices(w: torch.Tensor, out):
+    """(Cout, Cin, 3, 3, 3) fp32 -> bf16 [3][Cout][64] (csrc/conv1_march.cu)"""
+    _launched(1)
+    assert w.dtype == torch.float32 and w.is_contiguous()
+    check(_lib.load().b200_pack_conv1_slices(ptr(w), w.shape[0], w.shape[1], ptr(out), stream_ptr()),
+          "pack_conv1_slices")
+
+
+def conv1_march_fprop(x: torch.Tensor, w_slices, bias, y: ActView, stats=None, mode=EPI_BIAS_STATS, scale=None,
+                      shift=None):
+    """first conv straight from the fp32 (N, C, D, H, W) input, depth-marching form (one slice image per input slice)"""
+    lib = _lib.load()
+    n, c, d, h, w = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    _gemm("conv1_march_kernel", "conv1_fprop", 2.0 * y.voxels * y.c * 27 * c,
+          lambda: check(lib.b200_conv1_march_fprop(ptr(x), n, c, d, h, w, ptr(w_slices), ptr(bias), y.ref, ptr(stats),
+                                                   mode, ptr(scale), ptr(shift), stream_ptr()), "conv1_march_fprop"),
           shape=(y.voxels, c, y.c))
 
 

@@ -571,3 +571,65 @@ def test_first_layer_direct_fprop_and_wgrad(ops, cuda_dev, shape, cout):
     ops.conv1_direct_wgrad(x, to_act(ops, dy), dw)   # accumulates
     torch.cuda.synchronize()
     assert rel_l2(dw, 2 * ref_dw) < 2e-3
+
+
+# (N, D, H, W): full and partial bricks in w / h, depth segments of one slice and of many, unaligned rows, two samples
+FIRST_LAYER_MARCH_CASES = FIRST_LAYER_CASES + [(2, 40, 48, 24), (1, 1, 16, 8), (1, 64, 32, 32)]
+
+
+@pytest.mark.parametrize("shape", FIRST_LAYER_MARCH_CASES)
+@pytest.mark.parametrize("cout", [64, 32, 48])
+def test_first_layer_march_fprop(ops, cuda_dev, shape, cout):
+    """models/unet3d.py:194/29: the depth-marching forward of Conv3d(5 -> C <= 64) (csrc/conv1_march.cu: one slice image
+    per input slice, three output slices each) against F.conv3d on the bf16-rounded operands, its BatchNorm partial sums
+    against the sums of the stored values, and against the generic direct kernel (other K order: equal up to the fp32
+    accumulation order, i.e. at most one bf16 ulp on a few outputs)."""
+    n, d, h, w = shape
+    assert ops.conv1_march_supported(5, cout) and not ops.conv1_march_supported(4, cout)
+    assert not ops.conv1_march_supported(5, 128)
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(n, 5, d, h, w, generator=g).to(cuda_dev)
+    wt = bf16_round(torch.randn(cout, 5, 3, 3, 3, generator=g) * (2.0 / 135) ** 0.5).to(cuda_dev)
+    b = (torch.randn(cout, generator=g) * 0.1).to(cuda_dev)
+    w_slices = torch.full((3, cout, 64), float("nan"), device=cuda_dev, dtype=torch.bfloat16)
+    ops.pack_conv1_slices(wt.contiguous(), w_slices)
+    torch.cuda.synchronize()
+    want = torch.zeros(3, cout, 64, device=cuda_dev)
+    want[:, :, :45] = wt.permute(2, 0, 1, 3, 4).reshape(3, cout, 45)   # [kd][co][c*9 + kh*3 + kw]
+    assert torch.equal(w_slices.float(), want)
+    for ld_extra in (0, 64):   # a plain tensor, and the channel half of a concat buffer
+        yv = empty_act(ops, n, cout, d, h, w, cuda_dev, ld=cout + ld_extra)
+        rows = ops.conv1_march_stat_rows(n, d, h, w, cout)
+        stats = torch.full((rows, cout, 2), float("nan"), device=cuda_dev)
+        ops.conv1_march_fprop(x, w_slices, b, yv, stats, ops.EPI_BIAS_STATS)
+        torch.cuda.synchronize()
+        got = from_act(yv)
+        assert torch.isnan(yv.t[..., cout:]).all()   # the other channel half of the buffer is untouched
+        ref = F.conv3d(bf16_round(x), wt, b, padding=1)
+        assert torch.isfinite(got).all()
+        assert rel_l2(got, ref) < TOL
+        s = stats.double().sum(0)
+        assert torch.allclose(s[:, 0], got.double().sum((0, 2, 3, 4)), rtol=1e-4, atol=1e-2)
+        assert torch.allclose(s[:, 1], (got.double() ** 2).sum((0, 2, 3, 4)), rtol=1e-4, atol=1e-2)
+    if ops.conv1_direct_supported(5, cout, w):
+        w_rows = torch.empty(cout, 144, device=cuda_dev, dtype=torch.bfloat16)
+        ops.pack_rows(wt.contiguous(), 144, w_rows)
+        y2 = empty_act(ops, n, cout, d, h, w, cuda_dev)
+        stats2 = torch.empty(ops.conv1_direct_stat_rows(n, d, h, w, cout), cout, 2, device=cuda_dev)
+        ops.conv1_direct_fprop(x, w_rows, b, y2, stats2, ops.EPI_BIAS_STATS)
+        torch.cuda.synchronize()
+        assert rel_l2(got, from_act(y2)) < 1e-3
+    # eval-mode epilogue (folded BatchNorm + ReLU), plain bias, plain
+    scale, shift = torch.rand(cout, device=cuda_dev) + 0.5, torch.randn(cout, device=cuda_dev) * 0.2
+    ye = empty_act(ops, n, cout, d, h, w, cuda_dev)
+    ops.conv1_march_fprop(x, w_slices, None, ye, None, ops.EPI_AFFINE_RELU, scale, shift)
+    raw = F.conv3d(bf16_round(x), wt, None, padding=1)
+    assert rel_l2(from_act(ye), torch.relu(raw * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1))) < TOL
+    yp = empty_act(ops, n, cout, d, h, w, cuda_dev)
+    ops.conv1_march_fprop(x, w_slices, None, yp, None, ops.EPI_PLAIN)
+    assert rel_l2(from_act(yp), raw) < TOL
+    # run to run identical (static schedule, no atomics)
+    yq = empty_act(ops, n, cout, d, h, w, cuda_dev)
+    ops.conv1_march_fprop(x, w_slices, None, yq, None, ops.EPI_PLAIN)
+    torch.cuda.synchronize()
+    assert torch.equal(from_act(yq), from_act(yp))
