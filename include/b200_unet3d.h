@@ -236,6 +236,11 @@ int b200_pack_conv1_slices(const float* w, int64_t cout, int64_t cin, void* out,
 int b200_conv1_march_fprop(const float* x, int64_t n, int64_t c, int64_t d, int64_t h, int64_t w, const void* w_slices,
                            const float* bias, const b200_act* y, float* stats_partial, int mode, const float* scale,
                            const float* shift, void* stream);
+/* ... and its weight gradient by the same march (autograd of models/unet3d.py:29 for inc): the slice images are the
+ * K-major operand, the 8 x 16 dy bricks the other; dw is fp32 (Cout,5,3,3,3) (+=), accumulated in TMEM over every
+ * slice a CTA visits and added once. */
+int b200_conv1_march_wgrad(const float* x, int64_t n, int64_t c, int64_t d, int64_t h, int64_t w, const b200_act* dy,
+                           float* dw, void* stream);
 
 /* per-channel sum over the box [d0,d0+bd) x [h0,h0+bh) x [w0,w0+bw) of every sample, added to out[c] (fp32): the
  * ConvTranspose3d bias gradient when F.pad (models/unet3d.py:149-151) put a zero border around the upsampled map */

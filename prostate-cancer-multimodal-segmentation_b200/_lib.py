@@ -42,6 +42,7 @@ SIGNATURES = {
     "b200_conv1_march_stat_rows": (_i32, [_i64, _i64, _i64, _i64, _i64]),
     "b200_pack_conv1_slices": (_i32, [_vp, _i64, _i64, _vp, _vp]),
     "b200_conv1_march_fprop": (_i32, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _AP, _vp, _i32, _vp, _vp, _vp]),
+    "b200_conv1_march_wgrad": (_i32, [_vp, _i64, _i64, _i64, _i64, _i64, _AP, _vp, _vp]),
     "b200_pack_conv_weight": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "b200_pack_convt_weight": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "b200_conv3d_mtiles": (_i64, [_i64, _i64, _i64, _i64]),

@@ -25,6 +25,7 @@ extern "C" __global__ void dmarch_kernel(const __grid_constant__ DmarchParams p)
 extern "C" __global__ void dmarch_pair_kernel(const __grid_constant__ DmarchParams p);
 extern "C" __global__ void wgrad_halo_kernel(const __grid_constant__ WgradHaloParams p);
 extern "C" __global__ void conv1_march_kernel(const __grid_constant__ Conv1MarchParams p);
+extern "C" __global__ void conv1_march_wgrad_kernel(const __grid_constant__ Conv1MarchWgradParams p);
 }  // namespace b200
 
 using namespace b200;
@@ -1198,6 +1199,35 @@ extern "C" int b200_conv1_march_fprop(const float* x, int64_t n, int64_t c, int6
     const int rc_attr = ensure_smem(conv1_march_kernel, kC1Smem, optin);
     if (rc_attr) return rc_attr;
     launch_k(conv1_march_kernel, pl.grid, kC1Threads, kC1Smem, (cudaStream_t)stream, p);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+extern "C" int b200_conv1_march_wgrad(const float* x, int64_t n, int64_t c, int64_t d, int64_t h, int64_t w,
+                                      const b200_act* dy, float* dw, void* stream) {
+    CHECK_VIEW(dy);
+    REQUIRE(x && dw, "conv1_march_wgrad: null input / dw");
+    REQUIRE(b200_conv1_march_supported(c, dy->c), "conv1_march_wgrad: needs 5 input channels and 8..64 outputs");
+    REQUIRE(dy->n == n && dy->d == d && dy->h == h && dy->w == w, "conv1_march_wgrad: extent mismatch");
+    REQUIRE(n * d * h * w < (1LL << 31), "conv1_march_wgrad: too many voxels");
+    int rc = get_encode();
+    if (rc) return rc;
+    const int sms = sm_count();
+    if (sms <= 0) return fail(B200_ERR_CUDA, "no CUDA device");
+    Conv1MarchWgradParams p;
+    memset(&p, 0, sizeof(p));
+    rc = make_act_map(&p.p_map, reinterpret_cast<const __nv_bfloat16*>(dy->ptr), dy->c, dy->w, dy->h, dy->d, dy->n,
+                      dy->ld, dy->w, dy->h, dy->d, 1, 8, 16, 1);
+    if (rc) return rc;
+    const C1Plan pl = conv1_march_plan(n, d, h, w, sms);
+    p.x = x;
+    p.dw = dw;
+    p.ncols = (int)dy->c;
+    p.W = (int)w; p.H = (int)h; p.D = (int)d; p.nbatch = (int)n;
+    p.nbw = pl.nbw; p.nbh = pl.nbh; p.seg_len = pl.seg_len; p.nseg = pl.nseg;
+    static SmemOptIn optin;
+    const int rc_attr = ensure_smem(conv1_march_wgrad_kernel, kC1WgSmem, optin);
+    if (rc_attr) return rc_attr;
+    launch_k(conv1_march_wgrad_kernel, pl.grid, kC1WgThreads, kC1WgSmem, (cudaStream_t)stream, p);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

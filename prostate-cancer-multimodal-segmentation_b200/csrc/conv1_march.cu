@@ -366,4 +366,302 @@ extern "C" __global__ void __launch_bounds__(kC1Threads, 1)
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Weight gradient of the same layer:  dW[co][c][kd][kh][kw] += sum over voxels of dy[voxel][co] * x[c][voxel + tap]
+// (autograd of the nn.Conv3d call site models/unet3d.py:29 for inc, models/unet3d.py:194).  Same march: the slice
+// image S(z) (48 rows x 128 voxels) is now the K-major B operand (K = voxels), the 8 x 16 dy brick of output slice d
+// ([128 voxels][64 co], loaded by TMA) the MN-major A operand, and
+//     G[:, kd*48 .. kd*48+47] += dy(d)^T x S(d + kd - 1)^T   for kd = 0..2
+// is ONE MMA chain of N = 144 over the three images of the window: the image ring is laid out [half][slot][48 rows], so
+// consecutive ring slots are consecutive B rows (a window that wraps the ring is issued as two runs).  The 64 x 144
+// accumulator stays in TMEM over every slice the CTA visits and is added to dW once, at the end.
+// Warp roles (384 threads): warp 0 TMA producer (dy bricks), warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7
+// epilogue, warps 8-9 / 10-11 build the even / odd slice images.
+extern "C" __global__ void __launch_bounds__(kC1WgThreads, 1)
+    conv1_march_wgrad_kernel(const __grid_constant__ Conv1MarchWgradParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane = threadIdx.x & 31;
+
+    constexpr uint32_t kHalfAll = kC1Imgs * kC1HalfBytes;   // all slots' rows of one 64-voxel half
+    constexpr uint32_t kPSlot = 2 * kBoxBytes;              // dy brick: channels 0..63 and (zero-filled) 64..127
+    const uint32_t smem_q = smem_base;                      // [2 halves][kC1Imgs slots][48 rows][128 B]
+    const uint32_t smem_p = smem_q + 2 * kHalfAll;
+    const uint32_t bar_base = smem_p + kC1WgPSlots * kPSlot;
+    auto ifull = [&](uint32_t s) { return bar_base + 8 * s; };
+    auto iempty = [&](uint32_t s) { return bar_base + 8 * (kC1Imgs + s); };
+    auto pfull = [&](uint32_t s) { return bar_base + 8 * (2 * kC1Imgs + s); };
+    auto pempty = [&](uint32_t s) { return bar_base + 8 * (2 * kC1Imgs + kC1WgPSlots + s); };
+    const uint32_t tfull = bar_base + 8 * (2 * kC1Imgs + 2 * kC1WgPSlots);
+    const uint32_t tmem_ptr_smem = tfull + 8;
+
+    if (warp == 0 && lane == 0) prefetch_tmap(&p.p_map);
+    if (warp == 1 && lane == 0) {
+        for (uint32_t s = 0; s < kC1Imgs; ++s) { mbar_init(ifull(s), 2); mbar_init(iempty(s), 1); }
+        for (uint32_t s = 0; s < kC1WgPSlots; ++s) { mbar_init(pfull(s), 1); mbar_init(pempty(s), 1); }
+        mbar_init(tfull, 1);
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_ptr_smem, 256);
+        tmem_relinquish();
+    }
+    if (warp >= 8) {
+        // rows 45..47 of every slice image are never written again: zero (finite operands for the unused columns)
+        for (int i = threadIdx.x - 256; i < kC1Imgs * 2 * 3 * 8; i += 128) {
+            const int chunk = i & 7, row = 45 + (i >> 3) % 3, half = (i / 24) & 1, img = i / 48;
+            st_shared_v4(smem_q + half * kHalfAll + img * kC1HalfBytes + row * 128 + (chunk << 4), 0u, 0u, 0u, 0u);
+        }
+        fence_proxy_async_smem();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    pdl_wait();   // launch.cuh: the predecessor's results are complete and visible from here on
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_smem - smem_base));
+
+    const int units = p.nbatch * p.nbw * p.nbh * p.nseg;
+    const int unit0 = blockIdx.x, unit_stride = gridDim.x;
+    auto decode = [&](int unit) {
+        C1Unit u;
+        int col = unit / p.nseg;
+        const int seg = unit - col * p.nseg;
+        const int bw = col % p.nbw; col /= p.nbw;
+        const int bh = col % p.nbh; col /= p.nbh;
+        u.nb = col;
+        u.w0 = bw * 8;
+        u.h0 = bh * 16;
+        u.ds = seg * p.seg_len;
+        u.de = min(p.D, u.ds + p.seg_len);
+        u.z0 = max(u.ds - 1, 0);
+        u.z1 = min(u.de, p.D - 1);
+        return u;
+    };
+
+    if (warp == 0) {
+        // ===================================================================== TMA producer: one dy brick per slice
+        uint32_t pc = 0;
+        for (int unit = unit0; unit < units; unit += unit_stride) {
+            const C1Unit u = decode(unit);
+            for (int d = u.ds; d < u.de; ++d, ++pc) {
+                const uint32_t slot = pc % kC1WgPSlots;
+                mbar_wait(pempty(slot), ((pc / kC1WgPSlots) & 1) ^ 1);
+                if (elect_one()) {
+                    const uint32_t fb = pfull(slot);
+                    mbar_arrive_expect_tx(fb, kPSlot);
+                    tma_load_5d(smem_p + slot * kPSlot, &p.p_map, fb, 0, u.w0, u.h0, d, u.nb);
+                    tma_load_5d(smem_p + slot * kPSlot + kBoxBytes, &p.p_map, fb, 64, u.w0, u.h0, d, u.nb);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================================== MMA issuer
+        // A = dy brick, MN-major (M = co): 64-channel atoms LBO = 16 KB apart, 8-voxel groups SBO = 1 KB apart, one K
+        // step (16 voxels) = 2 KB.  B = slice images, K-major (rows = image rows, 128 B = 64 voxels): one K step = 32 B
+        // inside the swizzle row, voxels 64..127 one half (kHalfAll) further.
+        const uint64_t a_desc0 = make_smem_desc_sw128(smem_p, kBoxBytes, 1024);
+        const uint64_t b_desc0 = make_smem_desc_sw128(smem_q, 0, 1024);
+        const uint32_t idesc0 = make_idesc_bf16(128, 0, 1u, 0u);   // N field added per run
+        uint32_t ibase = 0, iready = 0, pc = 0;
+        uint32_t fresh = 7u;   // depth taps whose 48 accumulator columns have not been written yet
+        for (int unit = unit0; unit < units; unit += unit_stride) {
+            const C1Unit u = decode(unit);
+            for (int d = u.ds; d < u.de; ++d, ++pc) {
+                const uint32_t pslot = pc % kC1WgPSlots;
+                const uint32_t need = ibase + (uint32_t)(min(d + 1, u.z1) - u.z0);
+                while (iready <= need) {
+                    mbar_wait(ifull(iready % kC1Imgs), (iready / kC1Imgs) & 1);
+                    ++iready;
+                }
+                mbar_wait(pfull(pslot), (pc / kC1WgPSlots) & 1);
+                tc_fence_after();
+                // every lane walks the runs (uniform control flow, `fresh` stays warp-uniform); one elected lane issues
+                const uint32_t leader = elect_one();
+                const uint64_t a_desc = a_desc0 + pslot * (kPSlot >> 4);
+                // runs of taps whose images sit in consecutive ring slots (and share their freshness)
+                int kd = 0;
+                while (kd < 3) {
+                    const int z = d + kd - 1;
+                    if (z < 0 || z >= p.D) { ++kd; continue; }   // zero padding along depth
+                    const uint32_t slot = (ibase + (uint32_t)(z - u.z0)) % kC1Imgs;
+                    const bool fr = (fresh >> kd) & 1u;
+                    int len = 1;
+                    while (kd + len < 3 && d + kd + len - 1 < p.D && slot + len < (uint32_t)kC1Imgs &&
+                           (((fresh >> (kd + len)) & 1u) != 0) == fr)
+                        ++len;
+                    if (leader) {
+                        const uint32_t idesc = idesc0 | ((uint32_t)(len * kC1Rows >> 3) << 17);
+                        const uint32_t d_tmem = tmem_base + kd * kC1Rows;
+                        const uint64_t b_desc = b_desc0 + slot * (kC1HalfBytes >> 4);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            umma_f16(d_tmem, a_desc + 128 * j, b_desc + (j >> 2) * (kHalfAll >> 4) + (j & 3) * 2, idesc,
+                                     (fr && j == 0) ? 0u : 1u);
+                    }
+                    fresh &= ~(((1u << len) - 1u) << kd);
+                    kd += len;
+                }
+                if (leader) {
+                    umma_commit(pempty(pslot));
+                    if (d - 1 >= u.z0) umma_commit(iempty((ibase + (uint32_t)(d - 1 - u.z0)) % kC1Imgs));
+                    if (d == u.de - 1)
+                        for (int z = max(u.z0, d); z <= u.z1; ++z)
+                            umma_commit(iempty((ibase + (uint32_t)(z - u.z0)) % kC1Imgs));
+                }
+                __syncwarp();
+            }
+            ibase += (uint32_t)(u.z1 - u.z0 + 1);
+        }
+        if (elect_one()) umma_commit(tfull);
+        __syncwarp();
+    } else if (warp >= 8) {
+        // ===================================================================== slice-image builders (as in the forward)
+        const int g = (warp - 8) >> 1;
+        const int gt = threadIdx.x - 256 - 64 * g;
+        const long long hw = (long long)p.H * p.W;
+        const bool vec_ok = (p.W & 3) == 0 && (reinterpret_cast<uintptr_t>(p.x) & 15) == 0;
+        struct Rows {
+            float f[2][10];
+        };
+        struct Cursor {
+            int unit, z;
+            C1Unit u;
+        };
+        auto start = [&](Cursor& c, int unit) -> bool {
+            if (unit >= units) return false;
+            c.unit = unit;
+            c.u = decode(unit);
+            c.z = c.u.z0;
+            return true;
+        };
+        auto advance = [&](Cursor& c) -> bool {
+            if (c.z < c.u.z1) { ++c.z; return true; }
+            return start(c, c.unit + unit_stride);
+        };
+        auto load = [&](Rows& r, const Cursor& c) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                float (&f)[10] = r.f[i];
+#pragma unroll
+                for (int e = 0; e < 10; ++e) f[e] = 0.f;
+                const int t = gt + 64 * i;
+                if (t >= 18 * kC1Cin) continue;
+                const int ch = t / 18, hr = t - 18 * ch;
+                const int hs = c.u.h0 - 1 + hr, w0 = c.u.w0;
+                if ((unsigned)hs >= (unsigned)p.H || w0 >= p.W) continue;
+                const float* src = p.x + (((long long)c.u.nb * kC1Cin + ch) * p.D + c.z) * hw + (long long)hs * p.W + w0;
+                const int nv = min(8, p.W - w0);
+                if (vec_ok && nv == 8) {
+                    const float4 lo = __ldg(reinterpret_cast<const float4*>(src));
+                    const float4 hi = __ldg(reinterpret_cast<const float4*>(src) + 1);
+                    f[1] = lo.x; f[2] = lo.y; f[3] = lo.z; f[4] = lo.w;
+                    f[5] = hi.x; f[6] = hi.y; f[7] = hi.z; f[8] = hi.w;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        if (e < nv) f[1 + e] = __ldg(src + e);
+                }
+                if (w0 > 0) f[0] = __ldg(src - 1);
+                if (w0 + 8 < p.W) f[9] = __ldg(src + 8);
+            }
+        };
+        uint32_t ic = (uint32_t)g;
+        auto store = [&](const Rows& r) {
+            const uint32_t slot = ic % kC1Imgs;
+            mbar_wait(iempty(slot), ((ic / kC1Imgs) & 1) ^ 1);
+            const uint32_t img = smem_q + slot * kC1HalfBytes;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int t = gt + 64 * i;
+                if (t >= 18 * kC1Cin) continue;
+                const int ch = t / 18, hr = t - 18 * ch;
+                const float (&f)[10] = r.f[i];
+                uint32_t pk[3][4];
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) pk[kw][e] = pack_bf16x2(f[kw + 2 * e], f[kw + 2 * e + 1]);
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh) {
+                    const int cj = hr - kh;
+                    if (cj < 0 || cj >= 16) continue;
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) {
+                        const int k = ch * 9 + kh * 3 + kw;
+                        st_shared_v4(img + (uint32_t)(cj >> 3) * kHalfAll + (uint32_t)k * 128u +
+                                         ((uint32_t)((cj & 7) ^ (k & 7)) << 4),
+                                     pk[kw][0], pk[kw][1], pk[kw][2], pk[kw][3]);
+                    }
+                }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ifull(slot));
+            ic += 2;
+        };
+        auto advance2 = [&](Cursor& c) -> bool { return advance(c) && advance(c); };
+        Rows ra, rb;
+        Cursor cur;
+        bool have = start(cur, unit0);
+        if (have && g == 1) have = advance(cur);
+        if (have) load(ra, cur);
+        while (have) {
+            Cursor nxt = cur;
+            const bool hn = advance2(nxt);
+            if (hn) load(rb, nxt);
+            store(ra);
+            if (!hn) break;
+            cur = nxt;
+            have = advance2(cur);
+            if (have) load(ra, cur);
+            store(rb);
+        }
+    } else if (warp >= 4 && warp < 6) {
+        // ===================================================================== epilogue: dW += accumulator (rows = co;
+        // TMEM lanes 64..127 hold the zero-filled upper channel atom)
+        const int co = (warp - 4) * 32 + lane;
+        // depth taps this CTA's slices contributed to (a tap whose slices all fell outside the volume was never
+        // accumulated: its TMEM columns are not initialised)
+        uint32_t written = 0;
+        for (int unit = unit0; unit < units; unit += unit_stride) {
+            const C1Unit u = decode(unit);
+            if (u.ds >= u.de) continue;
+            written |= 2u;
+            if (u.de >= 2) written |= 1u;          // some slice d >= 1 reads input slice d - 1
+            if (u.ds <= p.D - 2) written |= 4u;    // some slice d <= D - 2 reads input slice d + 1
+        }
+        mbar_wait(tfull, 0);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>((warp - 4) * 32) << 16);
+        for (int kd = 0; kd < 3; ++kd) {
+            if (!((written >> kd) & 1u)) continue;
+#pragma unroll
+            for (int c16 = 0; c16 < 3; ++c16) {
+                uint32_t v[16];
+                tmem_ld16(t_addr + kd * kC1Rows + c16 * 16, v);
+                tmem_ld_wait();
+                if (co < p.ncols) {
+                    float* dst = p.dw + (long long)co * (27 * kC1Cin) + kd * 9;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int k = c16 * 16 + j;   // c*9 + kh*3 + kw
+                        if (k < 9 * kC1Cin) atomicAdd(dst + (k / 9) * 27 + (k % 9), __uint_as_float(v[j]));
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+
 }  // namespace b200

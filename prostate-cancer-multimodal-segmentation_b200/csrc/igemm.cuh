@@ -195,4 +195,18 @@ struct alignas(64) Conv1MarchParams {
     int mode;
 };
 
+// ... and its weight gradient (conv1_march_wgrad_kernel): image ring laid out [half][slot][48 rows], dy bricks by TMA
+constexpr int kC1WgThreads = 384;
+constexpr int kC1WgPSlots = 3;
+constexpr int kC1WgSmem = 1024 + 2 * kC1Imgs * kC1HalfBytes + kC1WgPSlots * 2 * kBoxBytes +
+                          8 * (2 * kC1Imgs + 2 * kC1WgPSlots + 1) + 64;
+struct alignas(64) Conv1MarchWgradParams {
+    CUtensorMap p_map;   // dy, box (64 ch, 8 w, 16 h, 1, 1)
+    const float* x;      // (N, 5, D, H, W) fp32
+    float* dw;           // fp32 [Cout][5][3][3][3] (+=)
+    int ncols;           // Cout <= 64
+    int W, H, D, nbatch, nbw, nbh;
+    int seg_len, nseg;
+};
+
 }  // namespace b200

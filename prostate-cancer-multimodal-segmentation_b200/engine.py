@@ -141,7 +141,9 @@ class _ConvPack:
                              workspace=workspace)
 
     def wgrad(self, xin, dy, dw):
-        if isinstance(xin, RawInput):
+        if isinstance(xin, RawInput) and self.march:
+            ops.conv1_march_wgrad(xin.t, dy, dw.view(self.cout, -1))
+        elif isinstance(xin, RawInput):
             ops.conv1_direct_wgrad(xin.t, dy, dw.view(self.cout, -1))
         elif self.im2col:
             ops.conv1_wgrad(xin, dy, dw.view(self.cout, -1), self.k_real)

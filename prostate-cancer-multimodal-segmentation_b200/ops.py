@@ -183,6 +183,17 @@ def conv1_march_fprop(x: torch.Tensor, w_slices, bias, y: ActView, stats=None, m
           shape=(y.voxels, c, y.c))
 
 
+def conv1_march_wgrad(x: torch.Tensor, dy: ActView, dw: torch.Tensor):
+    """weight gradient of the first conv by the same depth march; dw fp32 (Cout, C*27) / (Cout, C, 3, 3, 3), +="""
+    lib = _lib.load()
+    n, c, d, h, w = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous() and dw.is_contiguous() and dw.dtype == torch.float32
+    _gemm("conv1_march_wgrad_kernel", "conv1_wgrad", 2.0 * dy.voxels * dy.c * 27 * c,
+          lambda: check(lib.b200_conv1_march_wgrad(ptr(x), n, c, d, h, w, dy.ref, ptr(dw), stream_ptr()),
+                        "conv1_march_wgrad"),
+          shape=(dy.voxels, c, dy.c))
+
+
 def conv1_direct_wgrad(x: torch.Tensor, dy: ActView, dw: torch.Tensor):
     lib = _lib.load()
     n, c, d, h, w = x.shape

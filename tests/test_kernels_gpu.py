@@ -633,3 +633,31 @@ def test_first_layer_march_fprop(ops, cuda_dev, shape, cout):
     ops.conv1_march_fprop(x, w_slices, None, yq, None, ops.EPI_PLAIN)
     torch.cuda.synchronize()
     assert torch.equal(from_act(yq), from_act(yp))
+
+
+@pytest.mark.parametrize("shape", FIRST_LAYER_MARCH_CASES + [(1, 21, 16, 8), (1, 17, 20, 12)])
+@pytest.mark.parametrize("cout", [64, 32, 48])
+def test_first_layer_march_wgrad(ops, cuda_dev, shape, cout):
+    """autograd of models/unet3d.py:29 for inc: the depth-marching weight gradient (slice images as the K-major operand,
+    accumulator in TMEM over every slice of a CTA) against torch's conv3d weight gradient on the bf16-rounded operands
+    and against the generic direct kernel; the call accumulates.  (D = 21 / 17: a last depth segment of one slice.)"""
+    n, d, h, w = shape
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(n, 5, d, h, w, generator=g).to(cuda_dev)
+    dy = bf16_round(torch.randn(n, cout, d, h, w, generator=g)).to(cuda_dev)
+    ref_dw = torch.nn.grad.conv3d_weight(bf16_round(x), (cout, 5, 3, 3, 3), dy, padding=1).reshape(cout, 135)
+    for ld_extra in (0, 64):
+        dw = torch.zeros(cout, 135, device=cuda_dev)
+        dyv = to_act(ops, dy, ld=cout + ld_extra)
+        ops.conv1_march_wgrad(x, dyv, dw)
+        torch.cuda.synchronize()
+        assert torch.isfinite(dw).all()
+        assert rel_l2(dw, ref_dw) < 2e-3
+    if ops.conv1_direct_supported(5, cout, w):
+        dw2 = torch.zeros(cout, 135, device=cuda_dev)
+        ops.conv1_direct_wgrad(x, to_act(ops, dy), dw2)
+        torch.cuda.synchronize()
+        assert rel_l2(dw, dw2) < 1e-5   # same products, another order of the fp32 adds
+    ops.conv1_march_wgrad(x, to_act(ops, dy), dw)   # accumulates
+    torch.cuda.synchronize()
+    assert rel_l2(dw, 2 * ref_dw) < 2e-3

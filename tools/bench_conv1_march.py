@@ -1,5 +1,5 @@
 """Dev tool (GPU box): the first layer's forward at 2 x 5 x 128^3 -> 64 (and 1 x 5 x 160^3 -> 32 / 64): generic direct
-kernel vs the depth-marching kernel, event-timed, isolated."""
+kernels vs the depth-marching kernels (forward and weight gradient), event-timed, isolated."""
 import importlib, os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -40,5 +40,11 @@ for (n, d, h, w, cout) in [(2, 128, 128, 128, 64), (1, 160, 160, 160, 64), (1, 1
         t_d = timed(lambda: ops.conv1_direct_fprop(x, w_rows, b, y, st_d if mode == ops.EPI_BIAS_STATS else None, mode, *args))
         t_m = timed(lambda: ops.conv1_march_fprop(x, w_sl, b, y, st_m if mode == ops.EPI_BIAS_STATS else None, mode, *args))
         gb = vox * (20 + 2 * cout) / 1e9
+        if mode == ops.EPI_BIAS_STATS:
+            dw = torch.zeros(cout, 135, device=dev)
+            t_dw = timed(lambda: ops.conv1_direct_wgrad(x, y, dw))
+            t_mw = timed(lambda: ops.conv1_march_wgrad(x, y, dw))
+            print(f"{n}x5x{d}x{h}x{w} -> {cout}, weight gradient: direct {t_dw:.4f} ms, march {t_mw:.4f} ms "
+                  f"({2.0 * vox * cout * 135 / t_mw / 1e9:.0f} TFLOP/s)", flush=True)
         print(f"{n}x5x{d}x{h}x{w} -> {cout}, {name}: direct {t_d:.4f} ms, march {t_m:.4f} ms "
               f"({gb / t_m * 1e3:.0f} GB/s of algorithmic traffic, {2.0 * vox * cout * 135 / t_m / 1e9:.0f} TFLOP/s)", flush=True)
