@@ -45,6 +45,10 @@ int b200_abi_version(void);
    memory; under stream capture the launches become programmatic graph edges.  on = 1 / 0 sets the process-wide
    switch, on < 0 only queries; returns the previous setting.  No reference counterpart (torch launches serialise). */
 int b200_set_pdl(int on);
+/* The 64-column full-resolution convolutions (depth-marching kernels) on CTA pairs with tcgen05.mma.cta_group::2
+   (csrc/dmarch2.cu; default on) or on single-CTA MMAs with a multicast weight stream (csrc/dmarch.cu).  Same results up
+   to the fp32 accumulation order.  on < 0 only queries; returns the previous setting. */
+int b200_set_dmarch_pair_mma(int on);
 /* number of SMs of the current device (grid sizing), or <0 on error */
 int b200_sm_count(void);
 
@@ -93,6 +97,14 @@ int b200_conv3d_fprop(const b200_act* x, const void* w_packed, const float* bias
                       int64_t workspace_bytes, void* stream);
 int b200_conv3d_dgrad(const b200_act* dy, const void* w_packed, const b200_act* dx, void* workspace,
                       int64_t workspace_bytes, void* stream);
+/* The same input gradient for the layers the depth-marching CTA-pair kernel takes (dx of 64 or 32 channels at >= 8 x 16
+ * in-plane; b200_conv3d_dgrad_kmajor_supported), from the TRANSPOSED packed weights w_packed_t = [27][Cin][Cout]
+ * (b200_transpose_taps(w_packed, 27, Cout, Cin, ...)): the two CTAs of a pair split the weight tile by rows, which needs
+ * the GEMM's K (here Cout) contiguous.  Autograd of the nn.Conv3d call sites models/unet3d.py:29,35. */
+int b200_conv3d_dgrad_kmajor_supported(int64_t n, int64_t d, int64_t h, int64_t w, int64_t cin);
+int b200_conv3d_dgrad_kmajor(const b200_act* dy, const void* w_packed_t, const b200_act* dx, void* stream);
+/* bf16 [taps][rows][cols] -> [taps][cols][rows] */
+int b200_transpose_taps(const void* src, int64_t taps, int64_t rows, int64_t cols, void* dst, void* stream);
 /* dw += weight gradient; x->c may exceed cin_real (zero padded channels).
  * packed_layout = 0: dw is torch's (Cout, cin_real, 3,3,3);  1: dw is [27][Cout][cin_real] in the packed tap order
  * of b200_pack_conv_weight (the engine's physical parameter layout: contiguous, coalesced accumulation). */

@@ -28,6 +28,7 @@ SIGNATURES = {
     "b200_last_error": (C.c_char_p, []),
     "b200_abi_version": (_i32, []),
     "b200_set_pdl": (_i32, [_i32]),
+    "b200_set_dmarch_pair_mma": (_i32, [_i32]),
     "b200_sm_count": (_i32, []),
     "b200_pack_input": (_i32, [_vp, _i64, _i64, _i64, _i64, _i64, _AP, _vp]),
     "b200_im2col_input": (_i32, [_vp, _i64, _i64, _i64, _i64, _i64, _AP, _vp]),
@@ -50,6 +51,9 @@ SIGNATURES = {
     "b200_conv3d_workspace_bytes": (_i64, [_i64, _i64, _i64, _i64, _i64]),
     "b200_conv3d_fprop": (_i32, [_AP, _vp, _vp, _AP, _vp, _i32, _vp, _vp, _vp, _i64, _vp]),
     "b200_conv3d_dgrad": (_i32, [_AP, _vp, _AP, _vp, _i64, _vp]),
+    "b200_conv3d_dgrad_kmajor_supported": (_i32, [_i64, _i64, _i64, _i64, _i64]),
+    "b200_conv3d_dgrad_kmajor": (_i32, [_AP, _vp, _AP, _vp]),
+    "b200_transpose_taps": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp]),
     "b200_conv3d_wgrad": (_i32, [_AP, _AP, _vp, _i32, _i32, _vp]),
     "b200_convt2x_fwd": (_i32, [_AP, _vp, _vp, _AP, _i32, _i32, _i32, _vp]),
     "b200_convt2x_dgrad": (_i32, [_AP, _i32, _i32, _i32, _vp, _AP, _vp]),

@@ -18,7 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_NAME = "libb200unet3d.so"
 LIB_PATH = os.path.join(_HERE, LIB_NAME)
 DEV_LIB_PATH = os.path.join(_HERE, "libb200unet3d_dev.so")
-SOURCES = ["api.cu", "igemm.cu", "dmarch.cu", "wgrad_halo.cu", "conv1_march.cu", "bandwidth.cu"]
+SOURCES = ["api.cu", "igemm.cu", "dmarch.cu", "dmarch2.cu", "wgrad_halo.cu", "conv1_march.cu", "bandwidth.cu"]
 DEV_SOURCES = ["probe.cu"]
 HEADERS = ["igemm.cuh", "ptx.cuh", "bandwidth.cuh", "launch.cuh", "../../include/b200_unet3d.h"]
 NVCC_FLAGS = [

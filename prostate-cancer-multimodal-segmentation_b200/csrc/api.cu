@@ -16,6 +16,7 @@
 
 namespace b200 {
 int g_pdl = 1;   // launch.cuh: programmatic dependent launch on every kernel of the library
+int g_dmarch2 = 1;   // CTA-pair MMAs (dmarch2.cu) for the depth-marching convolutions that have K-major weights
 extern "C" __global__ void igemm_kernel(const __grid_constant__ IgemmParams p);
 extern "C" __global__ void wgrad_kernel(const __grid_constant__ WgradParams p);
 extern "C" __global__ void igemm_pair_kernel(const __grid_constant__ IgemmParams p);
@@ -23,6 +24,7 @@ extern "C" __global__ void igemm_im2col5_kernel(const __grid_constant__ IgemmPar
 extern "C" __global__ void wgrad_im2col5_kernel(const __grid_constant__ WgradParams p);
 extern "C" __global__ void dmarch_kernel(const __grid_constant__ DmarchParams p);
 extern "C" __global__ void dmarch_pair_kernel(const __grid_constant__ DmarchParams p);
+extern "C" __global__ void dmarch2_kernel(const __grid_constant__ DmarchParams p);
 extern "C" __global__ void wgrad_halo_kernel(const __grid_constant__ WgradHaloParams p);
 extern "C" __global__ void conv1_march_kernel(const __grid_constant__ Conv1MarchParams p);
 extern "C" __global__ void conv1_march_wgrad_kernel(const __grid_constant__ Conv1MarchWgradParams p);
@@ -51,6 +53,11 @@ static int fail(int code, const char* fmt, ...) {
 
 extern "C" const char* b200_last_error(void) { return g_err; }
 extern "C" int b200_abi_version(void) { return 5; }
+extern "C" int b200_set_dmarch_pair_mma(int on) {
+    const int was = g_dmarch2;
+    if (on >= 0) g_dmarch2 = on ? 1 : 0;
+    return was;
+}
 extern "C" int b200_set_pdl(int on) {
     const int was = g_pdl;
     if (on >= 0) g_pdl = on ? 1 : 0;
@@ -290,6 +297,7 @@ struct DmPlan {
     int nbw, nbh, seg_len, nseg, grid;
 };
 static int dmarch_max_clusters();
+static int dmarch2_max_clusters();
 static DmPlan dmarch_plan(long long n, long long w, long long h, long long d, long long ncols, int ntaps) {
     DmPlan pl{};
     int sms = sm_count();
@@ -328,7 +336,8 @@ static DmPlan dmarch_plan(long long n, long long w, long long h, long long d, lo
 constexpr int kDmSmem = 1024 + kDmAStages * kDmAStageBytes + kDmBStages * kDmBBytes + kBoxBytes +
                         8 * (2 * kDmAStages + 2 * kDmBStages + 2 * kDmSlots) + 64 + (4 * 64 * 2 + 128 + 128) * 4;
 static int launch_dmarch(const b200_act* in, const void* w_packed, const b200_act* out, int sign, int mode,
-                         const float* v0, const float* v1, float* stats, const DmPlan& pl, cudaStream_t s);
+                         const float* v0, const float* v1, float* stats, const DmPlan& pl, cudaStream_t s,
+                         bool w_transposed = false);
 
 static void set_plain_stage(IgemmParams& p) {
     p.group = 1;
@@ -581,14 +590,17 @@ static int conv3_igemm(const b200_act* in, const void* w_packed, const b200_act*
     return launch_igemm(p, s, nullptr);
 }
 
+// w_transposed (dgrad only): w_packed is [27][Cin][Cout] — rows = the GEMM's N, its K contiguous, i.e. a K-major B
+// operand like the forward's, which the CTA-pair kernel needs (its two CTAs split the B tile by rows)
 static int launch_dmarch(const b200_act* in, const void* w_packed, const b200_act* out, int sign, int mode,
-                         const float* v0, const float* v1, float* stats, const DmPlan& pl, cudaStream_t s) {
+                         const float* v0, const float* v1, float* stats, const DmPlan& pl, cudaStream_t s,
+                         bool w_transposed) {
     DmarchParams p;
     memset(&p, 0, sizeof(p));
     int rc = make_act_map(&p.a_map, reinterpret_cast<const __nv_bfloat16*>(in->ptr), in->c, in->w, in->h, in->d,
                           in->n, in->ld, in->w, in->h, in->d, 1, 8, 18, 1);
     if (rc) return rc;
-    p.b_mn = sign < 0 ? 1 : 0;
+    p.b_mn = (sign < 0 && !w_transposed) ? 1 : 0;
     if (p.b_mn)  // [tap][Cout rows = K][Cin = N contiguous]: 64 x 64 boxes
         rc = make_weight_map(&p.b_map, w_packed, out->c, in->c, 27, 64, 1);
     else         // [tap][Cout rows = N][Cin = K contiguous]
@@ -611,10 +623,47 @@ static int launch_dmarch(const b200_act* in, const void* w_packed, const b200_ac
         const int rc_attr = ensure_smem(dmarch_kernel, kDmSmem, optin);
         if (rc_attr) return rc_attr;
     }
+    if (pl.pair && !p.b_mn && g_dmarch2 && dmarch2_max_clusters() * 2 >= pl.grid) {
+        // cta_group::2 form: same plan, each CTA stages half of the (K-major) weight tile in 32-row boxes
+        rc = make_weight_map(&p.b_map, w_packed, in->c, out->c, 27, 32, 1);
+        if (rc) return rc;
+        launch_k(dmarch2_kernel, pl.grid, kThreads, kDm2Smem, s, p);   // __cluster_dims__(2, 1, 1)
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
     if (pl.pair) launch_k(dmarch_pair_kernel, pl.grid, kThreads, kDmSmem, s, p);   // __cluster_dims__(2, 1, 1)
     else launch_k(dmarch_kernel, pl.grid, kThreads, kDmSmem, s, p);
     CUDA_TRY(cudaGetLastError());
     return 0;
+}
+static int pair_kernel_max_clusters(void (*kernel)(DmarchParams), int smem, int* cached) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (cached[dev] != 0) return cached[dev];
+    int n = -1;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(2 * 148);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n <= 0) {
+            cudaGetLastError();
+            n = -1;
+        }
+    }
+    cached[dev] = n;
+    return n;
+}
+static int dmarch2_max_clusters() {
+    static int cached[64];
+    return pair_kernel_max_clusters(dmarch2_kernel, kDm2Smem, cached);
 }
 static int dmarch_max_clusters() {
     static int cached[64];
@@ -715,6 +764,34 @@ extern "C" int b200_conv3d_dgrad(const b200_act* dy, const void* w_packed, const
     // dx[v, ci] = sum_t sum_co dy[v - off(t), co] * w[co, ci, t]; w_packed is the fprop layout [27][Cout][Cin]
     return conv3_igemm(dy, w_packed, dx, -1, B200_EPI_PLAIN, nullptr, nullptr, nullptr, (cudaStream_t)stream, 27,
                        reinterpret_cast<float*>(workspace), workspace_bytes);
+}
+
+// dgrad of the layers the depth-marching CTA-pair kernel takes (dx of 64 / 32 channels), from TRANSPOSED packed weights
+// w_packed_t = [27][Cin][Cout] (b200_transpose_taps of the forward's [27][Cout][Cin])
+extern "C" int b200_conv3d_dgrad_kmajor_supported(int64_t n, int64_t d, int64_t h, int64_t w, int64_t cin) {
+    const DmPlan pl = dmarch_plan(n, w, h, d, cin, 27);
+    return (pl.use && pl.pair && g_dmarch2 && dmarch2_max_clusters() * 2 >= pl.grid) ? 1 : 0;
+}
+extern "C" int b200_conv3d_dgrad_kmajor(const b200_act* dy, const void* w_packed_t, const b200_act* dx, void* stream) {
+    CHECK_VIEW(dy);
+    CHECK_VIEW(dx);
+    REQUIRE(w_packed_t != nullptr, "conv3d_dgrad_kmajor: null weights");
+    int rc = get_encode();
+    if (rc) return rc;
+    REQUIRE(dy->n == dx->n && dy->d == dx->d && dy->h == dx->h && dy->w == dx->w, "conv3d_dgrad_kmajor: extent mismatch");
+    REQUIRE(dy->c % 16 == 0 && dx->c % 16 == 0, "conv3d_dgrad_kmajor: channels must be multiples of 16");
+    REQUIRE(dy->n * dy->d * dy->h * dy->w < (1LL << 31), "conv3d_dgrad_kmajor: too many voxels");
+    REQUIRE(b200_conv3d_dgrad_kmajor_supported(dy->n, dy->d, dy->h, dy->w, dx->c),
+            "conv3d_dgrad_kmajor: this shape does not run on the depth-marching CTA-pair kernel (use b200_conv3d_dgrad)");
+    const DmPlan pl = dmarch_plan(dy->n, dy->w, dy->h, dy->d, dx->c, 27);
+    return launch_dmarch(dy, w_packed_t, dx, -1, B200_EPI_PLAIN, nullptr, nullptr, nullptr, pl, (cudaStream_t)stream,
+                         true);
+}
+extern "C" int b200_transpose_taps(const void* src, int64_t taps, int64_t rows, int64_t cols, void* dst, void* stream) {
+    REQUIRE(src && dst && taps > 0 && rows > 0 && cols > 0, "transpose_taps: bad arguments");
+    CUDA_TRY(launch_transpose_taps(reinterpret_cast<const __nv_bfloat16*>(src), (int)taps, (int)rows, (int)cols,
+                                   reinterpret_cast<__nv_bfloat16*>(dst), (cudaStream_t)stream));
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------------ transposed conv

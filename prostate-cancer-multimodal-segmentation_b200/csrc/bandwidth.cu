@@ -248,6 +248,27 @@ cudaError_t launch_pack_conv1_slices(const float* w, int cout, int cin, __nv_bfl
     return cudaGetLastError();
 }
 
+// bf16 [taps][rows][cols] -> [taps][cols][rows] (32 x 32 tiles through shared memory): the K-major form of a packed
+// conv weight for the other GEMM direction (dgrad on the CTA-pair depth-marching kernel)
+__global__ void __launch_bounds__(256) transpose_taps_kernel(const __nv_bfloat16* __restrict__ src, int rows, int cols,
+                                                             __nv_bfloat16* __restrict__ dst) {
+    pdl_wait();
+    __shared__ __nv_bfloat16 tile[32][33];
+    const long long base = (long long)blockIdx.z * rows * cols;
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 32; i += 8)
+        if (r0 + i < rows && c0 + tx < cols) tile[i][tx] = src[base + (long long)(r0 + i) * cols + c0 + tx];
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8)
+        if (c0 + i < cols && r0 + tx < rows) dst[base + (long long)(c0 + i) * rows + r0 + tx] = tile[tx][i];
+}
+cudaError_t launch_transpose_taps(const __nv_bfloat16* src, int taps, int rows, int cols, __nv_bfloat16* dst,
+                                  cudaStream_t s) {
+    launch_k(transpose_taps_kernel, dim3((cols + 31) / 32, (rows + 31) / 32, taps), 256, 0, s, src, rows, cols, dst);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------ pack weights
 // one block = 32 output channels x 32 input channels x 27 taps; the tile is converted to bf16 on the way into
 // shared memory ([27][32 co][32 ci], row pitch 34 to spread banks), then written out as [27][Cout][Cin] with 64-byte rows

@@ -36,6 +36,8 @@ cudaError_t launch_pack_input(const float* x, long long n, long long c, long lon
 cudaError_t launch_im2col_input(const float* x, long long n, long long c, long long d, long long h, long long w,
                                 View out, cudaStream_t s);
 cudaError_t launch_pack_rows(const float* w, int rows, int k, int kpad, __nv_bfloat16* out, cudaStream_t s);
+cudaError_t launch_transpose_taps(const __nv_bfloat16* src, int taps, int rows, int cols, __nv_bfloat16* dst,
+                                  cudaStream_t s);
 cudaError_t launch_pack_conv1_slices(const float* w, int cout, int cin, __nv_bfloat16* out, cudaStream_t s);
 cudaError_t launch_pack_conv_weight(const float* w, int cout, int cin, int cin_pad, __nv_bfloat16* wf,
                                     cudaStream_t s);

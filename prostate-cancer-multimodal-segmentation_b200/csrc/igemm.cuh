@@ -121,6 +121,14 @@ struct alignas(64) DmarchParams {
                          // shared memory), 2 = no MMAs (loads + epilogue only); results are garbage, timings are not
 };
 
+// CTA-pair form (dmarch2.cu, tcgen05.mma.cta_group::2): each CTA stages HALF of the B tile (96 of the 192 rows, three
+// 32-row boxes — b_map box (64, 32, 1), K-major only); six logical accumulator slots + two mirror slots
+constexpr int kDm2BStages = 6;
+constexpr int kDm2BBytes = 96 * 128;
+constexpr int kDm2Slots = 6;
+constexpr int kDm2Smem = 1024 + kDmAStages * kDmAStageBytes + kDm2BStages * kDm2BBytes + kBoxBytes +
+                         8 * (2 * kDmAStages + 2 * kDm2BStages + 2 * kDm2Slots) + 64 + (4 * 64 * 2 + 128 + 128) * 4;
+
 // Weight-gradient GEMM  G[tap][p][q] += sum_{voxel} P[voxel][p] * Q_tap[voxel][q]
 // Both operands are voxel-major in memory (channel contiguous), i.e. MN-major UMMA operands.
 struct alignas(64) WgradParams {

@@ -92,6 +92,10 @@ class _ConvPack:
         self._slices = (torch.empty(3, self.cout, 64, device=device, dtype=torch.bfloat16) if self.march else None)
         self.shadow = None   # set by the engine: bf16 [27][Cout][Cin] view of its parameter shadow
         self._own = None
+        # input gradients of 64 / 32 channels run on the CTA-pair depth-marching kernel, which reads the weights K-major:
+        # a transposed copy [27][Cin][Cout], refreshed with the other packs (three small layers of the network)
+        self._wt = (torch.empty(27, self.cin, self.cout, device=device, dtype=torch.bfloat16)
+                    if (not self.im2col and self.cin in (32, 64) and self.cin == _pad16(self.cin)) else None)
         if self.im2col:
             self.k_real = 27 * self.cin
             self.cin_pad = _pad16(self.k_real)  # width of the im2col rows
@@ -118,6 +122,8 @@ class _ConvPack:
                 ops.pack_conv1_slices(self.conv.weight.data.contiguous(), self._slices)
         elif not self._phys(self.conv.weight.data):
             ops.pack_conv_weight(self.conv.weight.data.contiguous(), self.cin_pad, self.wf)
+        if self._wt is not None:
+            ops.transpose_taps(self.wf, self._wt)
 
     def make_input(self, x: torch.Tensor):
         """fp32 (N,C,D,H,W) -> the operand this conv reads: channel-padded NDHWC bf16, im2col rows, or (direct first
@@ -157,7 +163,11 @@ class _ConvPack:
     def dgrad(self, dy, dx, workspace=None):
         if self.im2col:
             raise B200Error("input gradient of an im2col'd (thin-input) convolution is not available")
-        ops.conv3d_dgrad(dy, self.wf, dx, workspace=workspace)
+        n, d, h, w, _ = dy.shape
+        if self._wt is not None and ops.conv3d_dgrad_kmajor_supported(n, d, h, w, dx.c):
+            ops.conv3d_dgrad_kmajor(dy, self._wt, dx)
+        else:
+            ops.conv3d_dgrad(dy, self.wf, dx, workspace=workspace)
 
 
 class RawInput:

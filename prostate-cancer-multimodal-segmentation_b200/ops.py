@@ -91,6 +91,11 @@ def set_pdl(on: bool) -> bool:
     return bool(_lib.load().b200_set_pdl(1 if on else 0))
 
 
+def set_dmarch_pair_mma(on: bool) -> bool:
+    """process-wide switch: depth-marching convolutions on cta_group::2 MMAs (csrc/dmarch2.cu; default on)"""
+    return bool(_lib.load().b200_set_dmarch_pair_mma(1 if on else 0))
+
+
 def pack_input(x: torch.Tensor, out: ActView):
     _launched(1)
     n, c, d, h, w = x.shape
@@ -251,7 +256,10 @@ def conv3d_fprop(x: ActView, w_fprop, bias, y: ActView, stats=None, mode=EPI_BIA
     wp, wb = _ws(workspace)
     split = workspace is not None and lib.b200_conv3d_workspace_bytes(*x.shape[:4], y.c) > 0
     _launched(1 if split else 0)   # + the finalize pass
-    _gemm("igemm_pair_kernel" if split else _conv_kernel(lib, x, y.c), "conv3d_fprop",
+    kern = "igemm_pair_kernel" if split else _conv_kernel(lib, x, y.c)
+    if kern == "dmarch_pair_kernel" and lib.b200_set_dmarch_pair_mma(-1):
+        kern = "dmarch2_kernel"   # the forward's weights are K-major: CTA-pair MMAs (csrc/dmarch2.cu)
+    _gemm(kern, "conv3d_fprop",
           2.0 * x.voxels * y.c * (k_real or x.c) * 27,
           lambda: check(lib.b200_conv3d_fprop(x.ref, ptr(w_fprop), ptr(bias), y.ref, ptr(stats), mode, ptr(scale),
                                               ptr(shift), wp, wb, stream_ptr()), "conv3d_fprop"),
@@ -267,6 +275,27 @@ def conv3d_dgrad(dy: ActView, w_packed, dx: ActView, workspace=None):
           2.0 * dy.voxels * dy.c * dx.c * 27,
           lambda: check(lib.b200_conv3d_dgrad(dy.ref, ptr(w_packed), dx.ref, wp, wb, stream_ptr()), "conv3d_dgrad"),
           shape=(dy.voxels, dx.c, dy.c))
+
+
+def conv3d_dgrad_kmajor_supported(n, d, h, w, cin) -> bool:
+    return bool(_lib.load().b200_conv3d_dgrad_kmajor_supported(n, d, h, w, cin))
+
+
+def conv3d_dgrad_kmajor(dy: ActView, w_packed_t, dx: ActView):
+    """input gradient on the CTA-pair depth-marching kernel, from transposed packed weights [27][Cin][Cout]"""
+    lib = _lib.load()
+    _gemm("dmarch2_kernel", "conv3d_dgrad", 2.0 * dy.voxels * dy.c * dx.c * 27,
+          lambda: check(lib.b200_conv3d_dgrad_kmajor(dy.ref, ptr(w_packed_t), dx.ref, stream_ptr()),
+                        "conv3d_dgrad_kmajor"),
+          shape=(dy.voxels, dx.c, dy.c))
+
+
+def transpose_taps(src: torch.Tensor, dst: torch.Tensor):
+    """bf16 [taps][rows][cols] -> [taps][cols][rows]"""
+    _launched(1)
+    taps, rows, cols = src.shape
+    assert src.dtype == torch.bfloat16 and dst.dtype == torch.bfloat16 and src.is_contiguous() and dst.is_contiguous()
+    check(_lib.load().b200_transpose_taps(ptr(src), taps, rows, cols, ptr(dst), stream_ptr()), "transpose_taps")
 
 
 def conv3d_wgrad(x: ActView, dy: ActView, dw: torch.Tensor, cin_real: int, packed: bool = False):

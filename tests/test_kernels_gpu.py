@@ -661,3 +661,65 @@ def test_first_layer_march_wgrad(ops, cuda_dev, shape, cout):
     ops.conv1_march_wgrad(x, to_act(ops, dy), dw)   # accumulates
     torch.cuda.synchronize()
     assert rel_l2(dw, 2 * ref_dw) < 2e-3
+
+
+# (n, cin, cout, d, h, w): 64- and 32-column depth-marching layers; odd column counts (a dummy peer column), depth
+# segments of several lengths, partial bricks in w / h, two channel blocks on the K side
+DMARCH_PAIR_CASES = [(1, 64, 64, 8, 16, 8), (2, 64, 64, 9, 20, 12), (1, 128, 64, 21, 32, 16), (1, 32, 32, 16, 16, 16),
+                     (3, 64, 64, 33, 16, 24), (1, 64, 128, 12, 16, 16), (2, 48, 64, 5, 24, 40)]
+
+
+@pytest.mark.parametrize("case", DMARCH_PAIR_CASES)
+def test_dmarch_cta_pair_mma_fprop_dgrad(ops, cuda_dev, case):
+    """models/unet3d.py:29,35 at full resolution: the depth-marching convolution on CTA pairs (csrc/dmarch2.cu,
+    tcgen05.mma.cta_group::2, mirror accumulator slots, dummy boundary slices) against F.conv3d / conv3d_input and against
+    the single-CTA-MMA kernel it replaces (equal up to the fp32 accumulation order), forward with BatchNorm partial sums
+    and — from transposed weights — the input gradient."""
+    n, cin, cout, d, h, w = case
+    g = torch.Generator().manual_seed(7)
+    x = bf16_round(torch.randn(n, cin, d, h, w, generator=g)).to(cuda_dev)
+    wt = bf16_round(torch.randn(cout, cin, 3, 3, 3, generator=g) * (2.0 / (27 * cin)) ** 0.5).to(cuda_dev)
+    b = (torch.randn(cout, generator=g) * 0.1).to(cuda_dev)
+    wf = torch.empty(27, cout, cin, device=cuda_dev, dtype=torch.bfloat16)
+    ops.pack_conv_weight(wt.contiguous(), cin, wf)
+    wft = torch.full((27, cin, cout), float("nan"), device=cuda_dev, dtype=torch.bfloat16)
+    ops.transpose_taps(wf, wft)
+    torch.cuda.synchronize()
+    assert torch.equal(wft, wf.transpose(1, 2).contiguous())
+    was = ops.set_dmarch_pair_mma(True)
+    try:
+        if cout in (32, 64):
+            got = {}
+            for pm in (True, False):
+                ops.set_dmarch_pair_mma(pm)
+                yv = empty_act(ops, n, cout, d, h, w, cuda_dev, ld=cout + 64)
+                stats = torch.full((ops.conv3d_stat_rows(n, d, h, w, cout), cout, 2), float("nan"), device=cuda_dev)
+                ops.conv3d_fprop(to_act(ops, x), wf, b, yv, stats, ops.EPI_BIAS_STATS)
+                torch.cuda.synchronize()
+                got[pm] = from_act(yv)
+                assert torch.isnan(yv.t[..., cout:].float()).all()
+                s = stats.double().sum(0)
+                assert torch.allclose(s[:, 0], got[pm].double().sum((0, 2, 3, 4)), rtol=1e-4, atol=1e-2)
+                assert torch.allclose(s[:, 1], (got[pm].double() ** 2).sum((0, 2, 3, 4)), rtol=1e-4, atol=1e-2)
+            ref = F.conv3d(x, wt, b, padding=1)
+            assert rel_l2(got[True], ref) < TOL
+            assert rel_l2(got[True], got[False]) < 1e-3
+        if cin in (32, 64):
+            dy = bf16_round(torch.randn(n, cout, d, h, w, generator=g)).to(cuda_dev)
+            ref = torch.nn.grad.conv3d_input((n, cin, d, h, w), wt, dy, padding=1)
+            ops.set_dmarch_pair_mma(True)
+            columns = n * ((w + 7) // 8) * ((h + 15) // 16)
+            assert ops.conv3d_dgrad_kmajor_supported(n, d, h, w, cin) == (columns >= 2)   # a pair needs two columns
+            if columns < 2:
+                return
+            dxv = empty_act(ops, n, cin, d, h, w, cuda_dev)
+            ops.conv3d_dgrad_kmajor(to_act(ops, dy), wft, dxv)
+            dx2 = empty_act(ops, n, cin, d, h, w, cuda_dev)
+            ops.conv3d_dgrad(to_act(ops, dy), wf, dx2)
+            torch.cuda.synchronize()
+            assert rel_l2(from_act(dxv), ref) < TOL
+            assert rel_l2(from_act(dxv), from_act(dx2)) < 1e-3
+            ops.set_dmarch_pair_mma(False)
+            assert not ops.conv3d_dgrad_kmajor_supported(n, d, h, w, cin)
+    finally:
+        ops.set_dmarch_pair_mma(was)
