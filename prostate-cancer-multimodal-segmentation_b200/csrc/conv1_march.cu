@@ -386,21 +386,22 @@ extern "C" __global__ void __launch_bounds__(kC1WgThreads, 1)
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
 
-    constexpr uint32_t kHalfAll = kC1Imgs * kC1HalfBytes;   // all slots' rows of one 64-voxel half
-    constexpr uint32_t kPSlot = 2 * kBoxBytes;              // dy brick: channels 0..63 and (zero-filled) 64..127
-    const uint32_t smem_q = smem_base;                      // [2 halves][kC1Imgs slots][48 rows][128 B]
+    constexpr uint32_t kHalfAll = kC1WgImgs * kC1HalfBytes;   // all slots' rows of one 64-voxel half
+    constexpr uint32_t kPSlot = kBoxBytes;                  // dy brick [128 voxels][64 co]
+    const uint32_t smem_q = smem_base;                      // [2 halves][kC1WgImgs slots][48 rows][128 B]
     const uint32_t smem_p = smem_q + 2 * kHalfAll;
-    const uint32_t bar_base = smem_p + kC1WgPSlots * kPSlot;
+    const uint32_t smem_z = smem_p + kC1WgPSlots * kPSlot;  // one zero box: the upper 64 rows of every MMA (M = 128)
+    const uint32_t bar_base = smem_z + kBoxBytes;
     auto ifull = [&](uint32_t s) { return bar_base + 8 * s; };
-    auto iempty = [&](uint32_t s) { return bar_base + 8 * (kC1Imgs + s); };
-    auto pfull = [&](uint32_t s) { return bar_base + 8 * (2 * kC1Imgs + s); };
-    auto pempty = [&](uint32_t s) { return bar_base + 8 * (2 * kC1Imgs + kC1WgPSlots + s); };
-    const uint32_t tfull = bar_base + 8 * (2 * kC1Imgs + 2 * kC1WgPSlots);
+    auto iempty = [&](uint32_t s) { return bar_base + 8 * (kC1WgImgs + s); };
+    auto pfull = [&](uint32_t s) { return bar_base + 8 * (2 * kC1WgImgs + s); };
+    auto pempty = [&](uint32_t s) { return bar_base + 8 * (2 * kC1WgImgs + kC1WgPSlots + s); };
+    const uint32_t tfull = bar_base + 8 * (2 * kC1WgImgs + 2 * kC1WgPSlots);
     const uint32_t tmem_ptr_smem = tfull + 8;
 
     if (warp == 0 && lane == 0) prefetch_tmap(&p.p_map);
     if (warp == 1 && lane == 0) {
-        for (uint32_t s = 0; s < kC1Imgs; ++s) { mbar_init(ifull(s), 2); mbar_init(iempty(s), 1); }
+        for (uint32_t s = 0; s < kC1WgImgs; ++s) { mbar_init(ifull(s), 2); mbar_init(iempty(s), 1); }
         for (uint32_t s = 0; s < kC1WgPSlots; ++s) { mbar_init(pfull(s), 1); mbar_init(pempty(s), 1); }
         mbar_init(tfull, 1);
         fence_mbar_init();
@@ -411,10 +412,11 @@ extern "C" __global__ void __launch_bounds__(kC1WgThreads, 1)
     }
     if (warp >= 8) {
         // rows 45..47 of every slice image are never written again: zero (finite operands for the unused columns)
-        for (int i = threadIdx.x - 256; i < kC1Imgs * 2 * 3 * 8; i += 128) {
+        for (int i = threadIdx.x - 256; i < kC1WgImgs * 2 * 3 * 8; i += 64 * kC1WgGroups) {
             const int chunk = i & 7, row = 45 + (i >> 3) % 3, half = (i / 24) & 1, img = i / 48;
             st_shared_v4(smem_q + half * kHalfAll + img * kC1HalfBytes + row * 128 + (chunk << 4), 0u, 0u, 0u, 0u);
         }
+        for (int i = threadIdx.x - 256; i < kBoxBytes / 16; i += 64 * kC1WgGroups) st_shared_v4(smem_z + i * 16, 0u, 0u, 0u, 0u);
         fence_proxy_async_smem();
     }
     tc_fence_before();
@@ -453,17 +455,15 @@ extern "C" __global__ void __launch_bounds__(kC1WgThreads, 1)
                     const uint32_t fb = pfull(slot);
                     mbar_arrive_expect_tx(fb, kPSlot);
                     tma_load_5d(smem_p + slot * kPSlot, &p.p_map, fb, 0, u.w0, u.h0, d, u.nb);
-                    tma_load_5d(smem_p + slot * kPSlot + kBoxBytes, &p.p_map, fb, 64, u.w0, u.h0, d, u.nb);
                 }
                 __syncwarp();
             }
         }
     } else if (warp == 1) {
         // ===================================================================== MMA issuer
-        // A = dy brick, MN-major (M = co): 64-channel atoms LBO = 16 KB apart, 8-voxel groups SBO = 1 KB apart, one K
-        // step (16 voxels) = 2 KB.  B = slice images, K-major (rows = image rows, 128 B = 64 voxels): one K step = 32 B
+        // A = dy brick, MN-major (M = co): 8-voxel groups SBO = 1 KB apart, one K step (16 voxels) = 2 KB; the second
+        // 64-channel atom of the M = 128 rows is the shared zero box (LBO = its distance from the slot).  B = slice images, K-major (rows = image rows, 128 B = 64 voxels): one K step = 32 B
         // inside the swizzle row, voxels 64..127 one half (kHalfAll) further.
-        const uint64_t a_desc0 = make_smem_desc_sw128(smem_p, kBoxBytes, 1024);
         const uint64_t b_desc0 = make_smem_desc_sw128(smem_q, 0, 1024);
         const uint32_t idesc0 = make_idesc_bf16(128, 0, 1u, 0u);   // N field added per run
         uint32_t ibase = 0, iready = 0, pc = 0;
@@ -474,23 +474,23 @@ extern "C" __global__ void __launch_bounds__(kC1WgThreads, 1)
                 const uint32_t pslot = pc % kC1WgPSlots;
                 const uint32_t need = ibase + (uint32_t)(min(d + 1, u.z1) - u.z0);
                 while (iready <= need) {
-                    mbar_wait(ifull(iready % kC1Imgs), (iready / kC1Imgs) & 1);
+                    mbar_wait(ifull(iready % kC1WgImgs), (iready / kC1WgImgs) & 1);
                     ++iready;
                 }
                 mbar_wait(pfull(pslot), (pc / kC1WgPSlots) & 1);
                 tc_fence_after();
                 // every lane walks the runs (uniform control flow, `fresh` stays warp-uniform); one elected lane issues
                 const uint32_t leader = elect_one();
-                const uint64_t a_desc = a_desc0 + pslot * (kPSlot >> 4);
+                const uint64_t a_desc = make_smem_desc_sw128(smem_p + pslot * kPSlot, smem_z - (smem_p + pslot * kPSlot), 1024);
                 // runs of taps whose images sit in consecutive ring slots (and share their freshness)
                 int kd = 0;
                 while (kd < 3) {
                     const int z = d + kd - 1;
                     if (z < 0 || z >= p.D) { ++kd; continue; }   // zero padding along depth
-                    const uint32_t slot = (ibase + (uint32_t)(z - u.z0)) % kC1Imgs;
+                    const uint32_t slot = (ibase + (uint32_t)(z - u.z0)) % kC1WgImgs;
                     const bool fr = (fresh >> kd) & 1u;
                     int len = 1;
-                    while (kd + len < 3 && d + kd + len - 1 < p.D && slot + len < (uint32_t)kC1Imgs &&
+                    while (kd + len < 3 && d + kd + len - 1 < p.D && slot + len < (uint32_t)kC1WgImgs &&
                            (((fresh >> (kd + len)) & 1u) != 0) == fr)
                         ++len;
                     if (leader) {
@@ -507,10 +507,10 @@ extern "C" __global__ void __launch_bounds__(kC1WgThreads, 1)
                 }
                 if (leader) {
                     umma_commit(pempty(pslot));
-                    if (d - 1 >= u.z0) umma_commit(iempty((ibase + (uint32_t)(d - 1 - u.z0)) % kC1Imgs));
+                    if (d - 1 >= u.z0) umma_commit(iempty((ibase + (uint32_t)(d - 1 - u.z0)) % kC1WgImgs));
                     if (d == u.de - 1)
                         for (int z = max(u.z0, d); z <= u.z1; ++z)
-                            umma_commit(iempty((ibase + (uint32_t)(z - u.z0)) % kC1Imgs));
+                            umma_commit(iempty((ibase + (uint32_t)(z - u.z0)) % kC1WgImgs));
                 }
                 __syncwarp();
             }
@@ -571,8 +571,8 @@ extern "C" __global__ void __launch_bounds__(kC1WgThreads, 1)
         };
         uint32_t ic = (uint32_t)g;
         auto store = [&](const Rows& r) {
-            const uint32_t slot = ic % kC1Imgs;
-            mbar_wait(iempty(slot), ((ic / kC1Imgs) & 1) ^ 1);
+            const uint32_t slot = ic % kC1WgImgs;
+            mbar_wait(iempty(slot), ((ic / kC1WgImgs) & 1) ^ 1);
             const uint32_t img = smem_q + slot * kC1HalfBytes;
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
@@ -601,22 +601,26 @@ extern "C" __global__ void __launch_bounds__(kC1WgThreads, 1)
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(ifull(slot));
-            ic += 2;
+            ic += kC1WgGroups;
         };
-        auto advance2 = [&](Cursor& c) -> bool { return advance(c) && advance(c); };
+        auto advance_n = [&](Cursor& c) -> bool {   // this group's next image: kC1WgGroups further in the sequence
+            for (int i = 0; i < kC1WgGroups; ++i)
+                if (!advance(c)) return false;
+            return true;
+        };
         Rows ra, rb;
         Cursor cur;
         bool have = start(cur, unit0);
-        if (have && g == 1) have = advance(cur);
+        for (int i = 0; i < g && have; ++i) have = advance(cur);
         if (have) load(ra, cur);
         while (have) {
             Cursor nxt = cur;
-            const bool hn = advance2(nxt);
+            const bool hn = advance_n(nxt);
             if (hn) load(rb, nxt);
             store(ra);
             if (!hn) break;
             cur = nxt;
-            have = advance2(cur);
+            have = advance_n(cur);
             if (have) load(ra, cur);
             store(rb);
         }

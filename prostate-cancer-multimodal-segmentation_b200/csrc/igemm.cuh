@@ -204,10 +204,12 @@ struct alignas(64) Conv1MarchParams {
 };
 
 // ... and its weight gradient (conv1_march_wgrad_kernel): image ring laid out [half][slot][48 rows], dy bricks by TMA
-constexpr int kC1WgThreads = 384;
-constexpr int kC1WgPSlots = 3;
-constexpr int kC1WgSmem = 1024 + 2 * kC1Imgs * kC1HalfBytes + kC1WgPSlots * 2 * kBoxBytes +
-                          8 * (2 * kC1Imgs + 2 * kC1WgPSlots + 1) + 64;
+constexpr int kC1WgGroups = 4;    // builder groups of two warps (an image takes ~1.5 us from loads to arrive)
+constexpr int kC1WgImgs = 8;      // slice-image ring
+constexpr int kC1WgThreads = 256 + 64 * kC1WgGroups;
+constexpr int kC1WgPSlots = 5;    // dy bricks in flight (16 KB each) + one shared zero box
+constexpr int kC1WgSmem = 1024 + 2 * kC1WgImgs * kC1HalfBytes + (kC1WgPSlots + 1) * kBoxBytes +
+                          8 * (2 * kC1WgImgs + 2 * kC1WgPSlots + 1) + 64;
 struct alignas(64) Conv1MarchWgradParams {
     CUtensorMap p_map;   // dy, box (64 ch, 8 w, 16 h, 1, 1)
     const float* x;      // (N, 5, D, H, W) fp32
