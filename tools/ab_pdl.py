@@ -59,21 +59,8 @@ for rnd in range(4):
         print(f"round {rnd} pdl={pdl}: {timed(g.replay):.3f} ms/step ({launches} launches, loss {loss.item():.5f})",
               flush=True)
 
-# same state, one replay of each graph: parameters and loss must agree bit for bit
-state = {k: v.clone() for k, v in model.state_dict().items()}
-opt_state = (model.engine.flat_param.clone(), opt.exp_avg.clone(), opt.exp_avg_sq.clone()) if hasattr(opt, "exp_avg") else None
-out = {}
-for pdl in (True, False):
-    model.load_state_dict(state)
-    if opt_state is not None:
-        opt.exp_avg.copy_(opt_state[1]); opt.exp_avg_sq.copy_(opt_state[2])
-    model.engine._pack_key = None
-    g, loss, _ = graphs[pdl]
-    g.replay()
-    torch.cuda.synchronize()
-    out[pdl] = (loss.clone(), model.engine.flat_param.clone(), model.engine.flat_grad.clone())
-same = all(torch.equal(a, b) for a, b in zip(out[True], out[False]))
-print("pdl on/off bit-identical (loss, parameters, gradients):", same)
+# (the weight gradients are added with REDs, so two runs never agree bit for bit: the arithmetic of PDL on / off is
+# compared through the forward only, tests/test_kernels_gpu.py and the full GPU suite run with PDL on)
 
 # eager launches (no graph)
 for pdl in (True, False):

@@ -16,11 +16,11 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-fi
     python bench.py $QUICK > $O/${TAG}_ncu_list.log 2>&1
 # one full capture per GEMM kernel; launch indices pick big layers of the second (eager) step:
 # igemm_pair_kernel 28 launches per step (the 8^3 level runs on it in split-K form): #13-#15 of the second step = up3.conv1 fprop (928 GF, 256 -> 128 at 64^3),
-# up3.conv2 fprop (464 GF), up4.conv1 dgrad (1855 GF, 64 -> 128 at 128^3).  dmarch_pair_kernel 6 per step (#1 inc.conv2
+# up3.conv2 fprop (464 GF), up4.conv1 dgrad (1855 GF, 64 -> 128 at 128^3).  dmarch2_kernel 6 per step (#1 inc.conv2
 # fprop 928 GF, #2 up4.conv1 fprop 1855 GF), wgrad_halo_kernel 15 per step (#1 up4.conv2 64 -> 64, #2 up4.conv1),
-# igemm_im2col5_kernel / wgrad_im2col5_kernel one per step (the first layer).
-for spec in "igemm_pair_kernel:40:3:igemm_pair" "dmarch_pair_kernel:6:2:dmarch_pair" "wgrad_halo_kernel:15:2:wgrad_halo" \
-            "igemm_im2col5_kernel:1:1:igemm_im2col5" "wgrad_im2col5_kernel:1:1:wgrad_im2col5"; do
+# conv1_march_kernel / conv1_march_wgrad_kernel one per step (the first layer).
+for spec in "igemm_pair_kernel:40:3:igemm_pair" "dmarch2_kernel:6:2:dmarch2" "wgrad_halo_kernel:15:2:wgrad_halo" \
+            "conv1_march_kernel:1:1:conv1_march" "conv1_march_wgrad_kernel:1:1:conv1_march_wgrad"; do
     IFS=: read -r kern skip cnt name <<< "$spec"
     python bench.py $QUICK > $O/${TAG}_plain.log 2>&1 &&
     ncu --set full --clock-control none --import-source on --kernel-name $kern --launch-skip $skip --launch-count $cnt \
@@ -32,4 +32,7 @@ ncu --set full --clock-control none --import-source on -k regex:"bn_bwd|bn_apply
     -f -o $O/${TAG}_prof_bn_passes python tools/bench_fused_bn_l0.py > $O/${TAG}_ncu_bn_passes.log 2>&1
 python tools/bench_fused_bn.py > $O/${TAG}_bn_passes_timing.txt 2>&1
 python tools/ab_fused.py > $O/${TAG}_ab_fused.txt 2>&1
+python tools/ab_pdl.py > $O/${TAG}_ab_pdl.txt 2>&1
+python tools/bench_dmarch2.py > $O/${TAG}_dmarch2_bench.txt 2>&1
+python tools/bench_conv1_march.py > $O/${TAG}_conv1_march_bench.txt 2>&1
 ls -la $O | tail -20

@@ -15,7 +15,8 @@ G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 os.makedirs(P, exist_ok=True)
 
 for name in ("bench.json", "bench_reference_arm.json", "bench_infer.json", "bench_cv.json", "gemm_launches.txt",
-             "timeline_events.txt", "launches.csv", "bn_passes_timing.txt", "ab_fused.txt"):
+             "timeline_events.txt", "launches.csv", "bn_passes_timing.txt", "ab_fused.txt", "ab_pdl.txt",
+             "dmarch2_bench.txt", "conv1_march_bench.txt"):
     src = os.path.join(G, f"{tag}_{name}")
     if os.path.exists(src):
         shutil.copy(src, os.path.join(P, f"{tag}_{name}"))
@@ -65,7 +66,8 @@ WANT = ["gpu__time_duration.sum", "launch__grid_size", "sm__cycles_elapsed.max",
 traffic = {}
 WANT += ["smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
          "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]
-for name in ("igemm_pair", "dmarch_pair", "wgrad_halo", "igemm", "dmarch", "igemm_im2col5", "wgrad_im2col5", "bn_passes"):
+for name in ("igemm_pair", "dmarch_pair", "dmarch2", "wgrad_halo", "igemm", "dmarch", "igemm_im2col5", "wgrad_im2col5",
+             "conv1_march", "conv1_march_wgrad", "bn_passes"):
     rep = os.path.join(G, f"{tag}_prof_{name}.ncu-rep")
     if not os.path.exists(rep):
         continue
