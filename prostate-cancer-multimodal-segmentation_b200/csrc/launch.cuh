@@ -9,7 +9,8 @@
 // kernel does before that (barrier init, TMEM allocation, tensor-map prefetch) overlaps the predecessor's tail.
 // EVERY thread of EVERY kernel launched through launch_k must execute pdl_wait(), also CTAs that have no work: a grid
 // that finishes without waiting would let ITS successor run ahead of the predecessor (ordering is transitive only
-// through the waits).  Under stream capture the attribute becomes a programmatic edge of the graph.
+// through the waits).  Under stream capture the attribute becomes a programmatic edge of the graph — measured 1 % slower
+// to replay than plain edges, so graph.GraphedTrainStep switches it off while it records (tools/ab_pdl.py).
 // b200_set_pdl(0) restores plain launches (the attribute is dropped; the wait is then a no-op).
 #pragma once
 #include <cuda_runtime.h>

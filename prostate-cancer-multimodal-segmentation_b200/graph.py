@@ -41,8 +41,14 @@ class GraphedTrainStep:
         self.model.engine._pack_key = None   # the weight-operand packing kernels must be part of the recorded step
         graph = torch.cuda.CUDAGraph()
         l0 = ops.launch_count
-        with torch.cuda.graph(graph):
-            static_loss = self._eager(static_x, static_y)
+        # recorded without programmatic dependent launch: PDL buys 0.8 ms per step on eager launches, but a graph of
+        # programmatic edges replays 0.2 ms SLOWER than one of plain edges (tools/ab_pdl.py, both orders)
+        pdl_was = ops.set_pdl(False)
+        try:
+            with torch.cuda.graph(graph):
+                static_loss = self._eager(static_x, static_y)
+        finally:
+            ops.set_pdl(pdl_was)
         self._graphs[key] = (graph, static_x, static_y, static_loss, ops.launch_count - l0)
 
     def __call__(self, x, y):

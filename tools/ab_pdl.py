@@ -8,6 +8,7 @@ sys.path.insert(0, ROOT)
 pkg = importlib.import_module("prostate-cancer-multimodal-segmentation_b200")
 dev = torch.device("cuda:0")
 base = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+order = (False, True) if len(sys.argv) > 2 and sys.argv[2] == "off-first" else (True, False)
 torch.manual_seed(0)
 model = pkg.UNet3D(5, 1, init_features=base).to(dev).train()
 opt = pkg.FusedAdam(model, lr=1e-4, weight_decay=1e-5)
@@ -53,7 +54,7 @@ for pdl in (True, False):
         loss = step()
     graphs[pdl] = (g, loss, pkg.ops.launch_count - l0)
 for rnd in range(4):
-    for pdl in (True, False):
+    for pdl in order:
         g, loss, launches = graphs[pdl]
         g.replay()
         print(f"round {rnd} pdl={pdl}: {timed(g.replay):.3f} ms/step ({launches} launches, loss {loss.item():.5f})",
