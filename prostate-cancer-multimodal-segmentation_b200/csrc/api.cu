@@ -995,6 +995,15 @@ extern "C" int b200_conv3d_wgrad(const b200_act* x, const b200_act* dy, float* d
         if (splits > nbricks) splits = nbricks;
         if (splits < 1) splits = 1;
         long long last_splits = short_last ? (splits + 1) / 2 : splits;
+        if (short_last) {
+            // a one-unit CTA reloads the P box for half the MMAs of a two-unit CTA (50 KB of operand fill per 768 MMA
+            // cycles instead of 34 KB) and walks the bricks out of step with the other groups (its loads miss L2): it
+            // needs ~20 % longer per MMA — ncu showed the tensor pipe at 73 % on these launches against 92 % on the
+            // even ones.  The SMs the equal-work split leaves idle go to the last group
+            const long long spare = ((long long)sms - (long long)hp.p_tiles * (hp.n_groups - 1) * splits) / hp.p_tiles;
+            if (spare > last_splits) last_splits = spare < splits ? spare : splits;
+            if (last_splits > nbricks) last_splits = nbricks;
+        }
         if (hp.n_groups == 1) last_splits = splits;
         hp.splits = (int)splits;
         hp.last_splits = (int)last_splits;
