@@ -86,32 +86,38 @@ extern "C" __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads,
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_smem - smem_base));
 
     const int columns = p.nbatch * p.nbw * p.nbh;
-    // a unit is (pair of adjacent columns, depth segment); CTA `rank` owns column 2 * cpair + rank (a column past the
-    // last one has every coordinate out of range: zero-filled loads, clipped stores)
-    const int units = ((columns + 1) / 2) * p.nseg;
-    const int unit0 = blockIdx.x / 2, unit_stride = gridDim.x / 2;
+    // Work = (pair of adjacent columns, output slice) steps in one linear order (column pair major).  Cluster c of n
+    // takes the contiguous range [total * c / n, total * (c + 1) / n) and walks it in pieces that end at column ends:
+    // every cluster gets the same number of slices (no wave of left-over units), and the two boundary input slices are
+    // paid once per piece (~2 pieces per cluster) instead of once per fixed depth segment.  CTA `rank` owns column
+    // 2 * cpair + rank (a column past the last one has every coordinate out of range: zero-filled loads, clipped stores)
+    const long long total = (long long)((columns + 1) / 2) * p.D;
+    const long long ncl = gridDim.x / 2, cl = blockIdx.x / 2;
+    const long long l_begin = total * cl / ncl, l_end = total * (cl + 1) / ncl;
     const int kc_blocks = p.kc_blocks;
     const int sign = p.sign;
 
-    auto decode = [&](int unit, int& nb, int& w0, int& h0, int& ds, int& de) {
-        const int cu = unit / p.nseg, seg = unit - cu * p.nseg;
-        int c = cu * 2 + rank;
+    // next piece of this cluster's range: (batch, brick column origin, output slices [ds, de)); false when done
+    auto next_piece = [&](long long& l, int& nb, int& w0, int& h0, int& ds, int& de) -> bool {
+        if (l >= l_end) return false;
+        const int cp = (int)(l / p.D);
+        ds = (int)(l - (long long)cp * p.D);
+        de = (int)min((long long)p.D, (long long)ds + (l_end - l));
+        l += de - ds;
+        int c = cp * 2 + rank;
         const int bw = c % p.nbw; c /= p.nbw;
         const int bh = c % p.nbh; c /= p.nbh;
         nb = c;
         w0 = bw * 8;
         h0 = bh * 16;
-        ds = seg * p.seg_len;
-        de = min(p.D, ds + p.seg_len);
+        return true;
     };
 
     if (warp == 0) {
         // ===================================================================== TMA producer (both CTAs)
         Ring2 ra, rb;
-        for (int unit = unit0; unit < units; unit += unit_stride) {
-            int nb, w0, h0, ds, de;
-            decode(unit, nb, w0, h0, ds, de);
-            if (ds >= de) continue;
+        int nb, w0, h0, ds, de;
+        for (long long l = l_begin; next_piece(l, nb, w0, h0, ds, de);) {
             for (int dz = ds - 1; dz <= de; dz += kDmG) {
                 const int nin = min(kDmG, de - dz + 1);   // input slices that share this pass over the weights
                 for (int kw = 0; kw < 3; ++kw) {
@@ -160,10 +166,8 @@ extern "C" __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads,
         const int nk_last = ((p.cin - (kc_blocks - 1) * 64) + 15) >> 4;
         uint32_t sbase = 0;      // slices (dummies included) of the units before this one
         uint32_t acquired = 0;   // slices whose slot is known to be zeroed and free
-        for (int unit = unit0; unit < units; unit += unit_stride) {
-            int nb, w0, h0, ds, de;
-            decode(unit, nb, w0, h0, ds, de);
-            if (ds >= de) continue;
+        int nb, w0, h0, ds, de;
+        for (long long l = l_begin; next_piece(l, nb, w0, h0, ds, de);) {
             for (int dz0 = ds - 1; dz0 <= de; dz0 += kDmG) {
                 const int nin = min(kDmG, de - dz0 + 1);
                 // the window of input slice dz starts at slice index f = sbase + (dz - ds + 1) (slice ds-2 is sbase)
@@ -250,10 +254,8 @@ extern "C" __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads,
         for (uint32_t s = 0; s < kDm2Slots; ++s) mbar_arrive_leader(tempty(s));
         named_bar_sync(1, 128);
         uint32_t sidx = 0;   // slice index in the CTA's sequence
-        for (int unit = unit0; unit < units; unit += unit_stride) {
-            int nb, w0, h0, ds, de;
-            decode(unit, nb, w0, h0, ds, de);
-            if (ds >= de) continue;
+        int nb, w0, h0, ds, de;
+        for (long long l = l_begin; next_piece(l, nb, w0, h0, ds, de);) {
             const bool row_ok = (w0 + rw) < p.W && (h0 + rh) < p.H && nb < p.nbatch;
             for (int d = ds - 2; d <= de + 1; ++d, ++sidx) {
                 const uint32_t m = sidx % kDm2Slots, par = (sidx / kDm2Slots) & 1;
