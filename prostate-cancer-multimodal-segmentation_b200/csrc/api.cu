@@ -1281,6 +1281,7 @@ extern "C" int b200_conv1_march_fprop(const float* x, int64_t n, int64_t c, int6
     p.W = (int)w; p.H = (int)h; p.D = (int)d; p.nbatch = (int)n;
     p.nbw = pl.nbw; p.nbh = pl.nbh; p.seg_len = pl.seg_len; p.nseg = pl.nseg;
     p.mode = mode;
+    p.ablate = g_dev_var[4];   // development library only
     static SmemOptIn optin;
     const int rc_attr = ensure_smem(conv1_march_kernel, kC1Smem, optin);
     if (rc_attr) return rc_attr;
@@ -1310,6 +1311,7 @@ extern "C" int b200_conv1_march_wgrad(const float* x, int64_t n, int64_t c, int6
     p.ncols = (int)dy->c;
     p.W = (int)w; p.H = (int)h; p.D = (int)d; p.nbatch = (int)n;
     p.nbw = pl.nbw; p.nbh = pl.nbh; p.seg_len = pl.seg_len; p.nseg = pl.nseg;
+    p.ablate = g_dev_var[4];   // development library only
     static SmemOptIn optin;
     const int rc_attr = ensure_smem(conv1_march_wgrad_kernel, kC1WgSmem, optin);
     if (rc_attr) return rc_attr;

@@ -13,11 +13,11 @@
 //     generic kernel ran 720 tasks per brick.
 //   * output slice d = sum over kd of S(d + kd - 1) x W[kd]  (W[kd]: [Cout][48] K-major, resident in shared memory for
 //     the whole kernel): 9 MMAs of 128 x 64 x 16, every slice image feeds three output slices.
-//   * two epilogue warpgroups take alternate output slices (TMEM ring of eight 64-column slots), each with its own
+//   * two epilogue warpgroups take the output slices in turn (TMEM ring of eight 64-column slots), each with its own
 //     staging tile and TMA store; BatchNorm partial sums stay in registers until the CTA ends.
 //
 // Warp roles (512 threads, 1 CTA / SM): warp 0 loads the weights (once), warp 1 issues the MMAs, warp 2 allocates
-// TMEM, warps 4-7 and 8-11 are the two epilogue warpgroups, warps 12-13 / 14-15 build the even / odd slice images.
+// TMEM, warps 4-11 are the two epilogue warpgroups, warps 12-13 / 14-15 build the even / odd slice images.
 #include <cuda_bf16.h>
 #include "igemm.cuh"
 #include "launch.cuh"
@@ -42,7 +42,7 @@ extern "C" __global__ void __launch_bounds__(kC1Threads, 1)
     const uint32_t smem_img = smem_base;                               // kC1Imgs slice images
     const uint32_t smem_b = smem_img + kC1Imgs * kC1ImgBytes;          // W[kd]: 3 x [64 rows][128 B]
     const uint32_t smem_c = smem_b + 3 * 8192;                         // one 16 KB staging tile per epilogue warpgroup
-    const uint32_t bar_base = smem_c + 2 * kBoxBytes;
+    const uint32_t bar_base = smem_c + kC1EpiWGs * kBoxBytes;
     auto ifull = [&](uint32_t s) { return bar_base + 8 * s; };
     auto iempty = [&](uint32_t s) { return bar_base + 8 * (kC1Imgs + s); };
     auto tfull = [&](uint32_t s) { return bar_base + 8 * (2 * kC1Imgs + s); };
@@ -50,8 +50,8 @@ extern "C" __global__ void __launch_bounds__(kC1Threads, 1)
     const uint32_t bfull = bar_base + 8 * (2 * kC1Imgs + 2 * kC1Slots);
     const uint32_t tmem_ptr_smem = bfull + 8;
     const uint32_t f_off = (tmem_ptr_smem + 16 - smem_base + 15u) & ~15u;
-    float* red = reinterpret_cast<float*>(smem_gen + f_off);   // [8 epilogue warps][64 cols][2]
-    float* colvec = red + 8 * 64 * 2;                          // [2][64]: bias | scale, shift
+    float* red = reinterpret_cast<float*>(smem_gen + f_off);   // [4 * kC1EpiWGs epilogue warps][64 cols][2]
+    float* colvec = red + 4 * kC1EpiWGs * 64 * 2;                          // [2][64]: bias | scale, shift
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&p.b_map);
@@ -67,9 +67,9 @@ extern "C" __global__ void __launch_bounds__(kC1Threads, 1)
         tmem_alloc(tmem_ptr_smem, 512);
         tmem_relinquish();
     }
-    if (warp >= 12) {
+    if (warp >= kC1BuilderWarp0) {
         // rows 45..47 of every slice image are never written again: zero (the MMAs read them against zero weights)
-        for (int i = threadIdx.x - 384; i < kC1Imgs * 2 * 3 * 8; i += 128) {
+        for (int i = threadIdx.x - 32 * kC1BuilderWarp0; i < kC1Imgs * 2 * 3 * 8; i += 128) {
             const int chunk = i & 7, row = 45 + (i >> 3) % 3, half = (i / 24) & 1, img = i / 48;
             st_shared_v4(smem_img + img * kC1ImgBytes + half * kC1HalfBytes + row * 128 + (chunk << 4), 0u, 0u, 0u, 0u);
         }
@@ -141,7 +141,7 @@ extern "C" __global__ void __launch_bounds__(kC1Threads, 1)
                         const uint64_t b_desc = b_desc0 + kd * (8192 >> 4);
 #pragma unroll
                         for (int s = 0; s < kC1Rows / 16; ++s) {
-                            umma_f16(d_tmem, a_desc + s * (2048 >> 4), b_desc + s * 2, idesc, accum);
+                            if (B200_ABLATE(p) != 3) umma_f16(d_tmem, a_desc + s * (2048 >> 4), b_desc + s * 2, idesc, accum);
                             accum = 1u;
                         }
                     }
@@ -156,14 +156,14 @@ extern "C" __global__ void __launch_bounds__(kC1Threads, 1)
             }
             ibase += (uint32_t)(u.z1 - u.z0 + 1);
         }
-    } else if (warp >= 12) {
+    } else if (warp >= kC1BuilderWarp0) {
         // ===================================================================== slice-image builders
         // group g (two warps, 64 threads) builds the images with sequence number = g mod 2.  One task = one input row
         // (channel c, row hs = h0 - 1 + hr, hr = 0..17): 10 floats x[w0 - 1 .. w0 + 8] -> the chunks (8 voxels of
         // output row hr - kh) of the 9 image rows (c, kh, kw).  The loads of a group's next image are in flight while
         // it writes the current one (two register sets, ping-pong).
-        const int g = (warp - 12) >> 1;
-        const int gt = threadIdx.x - 384 - 64 * g;   // 0..63
+        const int g = (warp - kC1BuilderWarp0) >> 1;
+        const int gt = threadIdx.x - 32 * kC1BuilderWarp0 - 64 * g;   // 0..63
         const long long hw = (long long)p.H * p.W;
         const bool vec_ok = (p.W & 3) == 0 && (reinterpret_cast<uintptr_t>(p.x) & 15) == 0;
         struct Rows {
@@ -191,7 +191,7 @@ extern "C" __global__ void __launch_bounds__(kC1Threads, 1)
 #pragma unroll
                 for (int e = 0; e < 10; ++e) f[e] = 0.f;
                 const int t = gt + 64 * i;
-                if (t >= 18 * kC1Cin) continue;
+                if (t >= 18 * kC1Cin || B200_ABLATE(p) == 2) continue;
                 const int ch = t / 18, hr = t - 18 * ch;
                 const int hs = c.u.h0 - 1 + hr, w0 = c.u.w0;
                 if ((unsigned)hs >= (unsigned)p.H || w0 >= p.W) continue;   // outside the volume: zero padding
@@ -263,9 +263,9 @@ extern "C" __global__ void __launch_bounds__(kC1Threads, 1)
             if (have) load(ra, cur);
             store(rb);
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < kC1BuilderWarp0) {
         // ===================================================================== epilogue: warpgroup wg takes output
-        // slices wg, wg + 2, ... of the CTA's sequence (TMEM slot parity = wg)
+        // slices wg, wg + kC1EpiWGs, ... of the CTA's sequence
         const int wg = (warp - 4) >> 2;
         const int q = (warp - 4) & 3;           // == warp % 4: TMEM lane quarter
         const int row = q * 32 + lane;          // voxel of the brick: w = row & 7, h = row >> 3
@@ -281,51 +281,54 @@ extern "C" __global__ void __launch_bounds__(kC1Threads, 1)
             colvec[et] = ok ? __ldg(p.vec0 + et) : 0.f;
             colvec[64 + et] = (ok && mode == EPI_AFFINE_RELU) ? __ldg(p.vec1 + et) : 0.f;
         }
-        named_bar_sync(3, 256);
+        named_bar_sync(1 + kC1EpiWGs, 128 * kC1EpiWGs);
         float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;   // BatchNorm partial sums: columns 2*lane, 2*lane + 1, rows 32q..
         uint32_t ucnt = 0;
+        // 32 accumulator columns -> bias / affine + ReLU -> bf16 -> this row's chunks 4*jj .. 4*jj+3 of the staging tile
+        auto stage_half = [&](const uint32_t (&v)[32], int jj, bool row_ok) {
+            const float* cv = colvec + jj * 32;
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                float a = __uint_as_float(v[2 * i]), b = __uint_as_float(v[2 * i + 1]);
+                if (mode == EPI_AFFINE_RELU) {
+                    a = fmaxf(fmaf(a, cv[2 * i], cv[64 + 2 * i]), 0.f);
+                    b = fmaxf(fmaf(b, cv[2 * i + 1], cv[64 + 2 * i + 1]), 0.f);
+                } else if (mode != EPI_PLAIN) {
+                    a += cv[2 * i];
+                    b += cv[2 * i + 1];
+                }
+                pk[i] = row_ok ? pack_bf16x2(a, b) : 0u;
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                st_shared_v4(row_smem + (((jj * 4 + c) ^ sw) << 4), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        };
         for (int unit = unit0; unit < units; unit += unit_stride) {
             const C1Unit u = decode(unit);
             const bool row_ok = (u.w0 + rw) < p.W && (u.h0 + rh) < p.H;
             for (int d = u.ds; d < u.de; ++d, ++ucnt) {
-                if ((int)(ucnt & 1u) != wg) continue;
+                if ((int)(ucnt % kC1EpiWGs) != wg) continue;
                 const uint32_t slot = ucnt % kC1Slots, par = (ucnt / kC1Slots) & 1;
                 if (et == 0) bulk_wait_read0();   // the previous TMA store has finished reading the staging tile
                 named_bar_sync(bar_id, 128);
                 mbar_wait(tfull(slot), par);
                 tc_fence_after();
                 const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + slot * 64;
-                uint32_t v0[32], v1[32];
-                tmem_ld32(t_addr, v0);
-                tmem_ld32(t_addr + 32, v1);
-                tmem_ld_wait();
-                tc_fence_before();
-                mbar_arrive(tempty(slot));   // accumulator drained into registers
-#pragma unroll
-                for (int jj = 0; jj < 2; ++jj) {
-                    const uint32_t (&v)[32] = jj == 0 ? v0 : v1;
-                    const float* cv = colvec + jj * 32;
-                    uint32_t pk[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        float a = __uint_as_float(v[2 * i]), b = __uint_as_float(v[2 * i + 1]);
-                        if (mode == EPI_AFFINE_RELU) {
-                            a = fmaxf(fmaf(a, cv[2 * i], cv[64 + 2 * i]), 0.f);
-                            b = fmaxf(fmaf(b, cv[2 * i + 1], cv[64 + 2 * i + 1]), 0.f);
-                        } else if (mode != EPI_PLAIN) {
-                            a += cv[2 * i];
-                            b += cv[2 * i + 1];
-                        }
-                        pk[i] = row_ok ? pack_bf16x2(a, b) : 0u;
-                    }
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        st_shared_v4(row_smem + (((jj * 4 + c) ^ sw) << 4), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2],
-                                     pk[4 * c + 3]);
+                {   // (one half of the columns at a time: 640 threads leave 96 registers each)
+                    uint32_t v[32];
+                    tmem_ld32(t_addr, v);
+                    tmem_ld_wait();
+                    stage_half(v, 0, row_ok);
+                    tmem_ld32(t_addr + 32, v);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    mbar_arrive(tempty(slot));   // accumulator drained into registers
+                    stage_half(v, 1, row_ok);
                 }
                 fence_proxy_async_smem();
                 named_bar_sync(bar_id, 128);
-                if (et == 0) {
+                if (et == 0 && B200_ABLATE(p) != 1) {
                     tma_store_5d(&p.c_map, cbuf, 0, u.w0, u.h0, d, u.nb);
                     bulk_commit();
                 }
@@ -345,14 +348,14 @@ extern "C" __global__ void __launch_bounds__(kC1Threads, 1)
         }
         if (et == 0) bulk_wait0();   // every output tile is in global memory before the CTA exits
         if (mode == EPI_BIAS_STATS) {
-            // one partial row per CTA: stats[blockIdx.x][ncols][2], the eight warps' sums added in a fixed order
+            // one partial row per CTA: stats[blockIdx.x][ncols][2], the epilogue warps' sums added in a fixed order
             *reinterpret_cast<float4*>(red + ((wg * 4 + q) * 64 + 2 * lane) * 2) = make_float4(s0, q0, s1, q1);
-            named_bar_sync(3, 256);
-            const int i = threadIdx.x - 128;   // 0..255: (column, sum | sum of squares)
+            named_bar_sync(1 + kC1EpiWGs, 128 * kC1EpiWGs);
+            const int i = threadIdx.x - 128;   // (column, sum | sum of squares)
             if (i < 2 * p.ncols && i < 128) {
                 float a = 0.f;
 #pragma unroll
-                for (int w8 = 0; w8 < 8; ++w8) a += red[w8 * 128 + i];
+                for (int w8 = 0; w8 < 4 * kC1EpiWGs; ++w8) a += red[w8 * 128 + i];
                 p.stats[(long long)blockIdx.x * p.ncols * 2 + i] = a;
             }
         }
@@ -376,7 +379,7 @@ extern "C" __global__ void __launch_bounds__(kC1Threads, 1)
 // is ONE MMA chain of N = 144 over the three images of the window: the image ring is laid out [half][slot][48 rows], so
 // consecutive ring slots are consecutive B rows (a window that wraps the ring is issued as two runs).  The 64 x 144
 // accumulator stays in TMEM over every slice the CTA visits and is added to dW once, at the end.
-// Warp roles (384 threads): warp 0 TMA producer (dy bricks), warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7
+// Warp roles (512 threads): warp 0 TMA producer (dy bricks), warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7
 // epilogue, warps 8-9 / 10-11 build the even / odd slice images.
 extern "C" __global__ void __launch_bounds__(kC1WgThreads, 1)
     conv1_march_wgrad_kernel(const __grid_constant__ Conv1MarchWgradParams p) {
@@ -453,8 +456,12 @@ extern "C" __global__ void __launch_bounds__(kC1WgThreads, 1)
                 mbar_wait(pempty(slot), ((pc / kC1WgPSlots) & 1) ^ 1);
                 if (elect_one()) {
                     const uint32_t fb = pfull(slot);
-                    mbar_arrive_expect_tx(fb, kPSlot);
-                    tma_load_5d(smem_p + slot * kPSlot, &p.p_map, fb, 0, u.w0, u.h0, d, u.nb);
+                    if (B200_ABLATE(p) == 1) {
+                        mbar_arrive(fb);
+                    } else {
+                        mbar_arrive_expect_tx(fb, kPSlot);
+                        tma_load_5d(smem_p + slot * kPSlot, &p.p_map, fb, 0, u.w0, u.h0, d, u.nb);
+                    }
                 }
                 __syncwarp();
             }
@@ -498,7 +505,7 @@ extern "C" __global__ void __launch_bounds__(kC1WgThreads, 1)
                         const uint32_t d_tmem = tmem_base + kd * kC1Rows;
                         const uint64_t b_desc = b_desc0 + slot * (kC1HalfBytes >> 4);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
+                        for (int j = 0; j < 8 && B200_ABLATE(p) != 3; ++j)
                             umma_f16(d_tmem, a_desc + 128 * j, b_desc + (j >> 2) * (kHalfAll >> 4) + (j & 3) * 2, idesc,
                                      (fr && j == 0) ? 0u : 1u);
                     }
@@ -549,7 +556,7 @@ extern "C" __global__ void __launch_bounds__(kC1WgThreads, 1)
 #pragma unroll
                 for (int e = 0; e < 10; ++e) f[e] = 0.f;
                 const int t = gt + 64 * i;
-                if (t >= 18 * kC1Cin) continue;
+                if (t >= 18 * kC1Cin || B200_ABLATE(p) == 2) continue;
                 const int ch = t / 18, hr = t - 18 * ch;
                 const int hs = c.u.h0 - 1 + hr, w0 = c.u.w0;
                 if ((unsigned)hs >= (unsigned)p.H || w0 >= p.W) continue;

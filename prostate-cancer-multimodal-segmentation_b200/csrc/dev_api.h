@@ -18,7 +18,9 @@ int b200_probe_pair(const void* a, const void* b, int n, int k, int iters, float
 /* kernel ablations for timing experiments (results are garbage, timings are not): igemm 1 = no TMA loads, 2 = no MMAs,
  * 3 = loads the MMAs do not wait for; dmarch 1 / 2 likewise; nopair = single-CTA igemm everywhere; stage_cap = ring depth */
 int b200_dev_set_ablation(int igemm_ablate, int dmarch_ablate, int nopair, int stage_cap);
-/* launcher variants under test (tools/bench_variants.py): which = 0 convT forward UMMA N, 1 convT forward staging tiles */
+/* launcher variants under test (tools/bench_variants.py): which = 0 convT forward UMMA N, 1 convT forward staging tiles,
+ * 4 = ablation of the first-layer marching kernels (tools/ablate_conv1_march.py): 1 no output stores / dy loads, 2 no input
+ * loads, 3 no MMAs */
 int b200_dev_set_variant(int which, int value);
 #ifdef __cplusplus
 }

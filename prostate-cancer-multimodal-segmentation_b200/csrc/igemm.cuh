@@ -181,15 +181,17 @@ struct alignas(64) WgradHaloParams {
 
 // Depth-marching forward of the 5-modality first layer (conv1_march.cu): slice images of 48 rows (45 real: k = c*9 +
 // kh*3 + kw) x 128 voxels, MN-major, two 64-voxel halves kC1HalfBytes apart
-constexpr int kC1Threads = 512;
+constexpr int kC1EpiWGs = 2;                         // epilogue warpgroups (warps 4 ..); a third one changes nothing (0.217 vs 0.212 ms)
+constexpr int kC1BuilderWarp0 = 4 + 4 * kC1EpiWGs;   // first of the four builder warps
+constexpr int kC1Threads = 32 * (kC1BuilderWarp0 + 4);
 constexpr int kC1Cin = 5;
 constexpr int kC1Rows = 48;
 constexpr int kC1HalfBytes = kC1Rows * 128;
 constexpr int kC1ImgBytes = 2 * kC1HalfBytes;
 constexpr int kC1Imgs = 6;       // slice-image ring
 constexpr int kC1Slots = 8;      // TMEM ring: 64-column accumulators (one output slice each)
-constexpr int kC1Smem = 1024 + kC1Imgs * kC1ImgBytes + 3 * 8192 + 2 * kBoxBytes + 8 * (2 * kC1Imgs + 2 * kC1Slots + 1) +
-                        64 + (8 * 64 * 2 + 2 * 64) * 4;
+constexpr int kC1Smem = 1024 + kC1Imgs * kC1ImgBytes + 3 * 8192 + kC1EpiWGs * kBoxBytes +
+                        8 * (2 * kC1Imgs + 2 * kC1Slots + 1) + 64 + (4 * kC1EpiWGs * 64 * 2 + 2 * 64) * 4;
 struct alignas(64) Conv1MarchParams {
     CUtensorMap b_map;   // packed weights [3 kd][Cout][64] (k = c*9 + kh*3 + kw, 45 real), box (64, 64, 1)
     CUtensorMap c_map;   // output store, box (64 ch, 8 w, 16 h, 1, 1)
@@ -201,6 +203,7 @@ struct alignas(64) Conv1MarchParams {
     int W, H, D, nbatch, nbw, nbh;
     int seg_len, nseg;
     int mode;
+    int ablate;          // development library only (B200_ABLATE): 1 = no output stores, 2 = builders skip the input loads, 3 = no MMAs
 };
 
 // ... and its weight gradient (conv1_march_wgrad_kernel): image ring laid out [half][slot][48 rows], dy bricks by TMA
@@ -217,6 +220,7 @@ struct alignas(64) Conv1MarchWgradParams {
     int ncols;           // Cout <= 64
     int W, H, D, nbatch, nbw, nbh;
     int seg_len, nseg;
+    int ablate;          // development library only: 1 = dy slots armed without loads, 2 = builders skip the input loads, 3 = no MMAs
 };
 
 }  // namespace b200

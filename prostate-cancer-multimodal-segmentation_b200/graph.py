@@ -33,7 +33,10 @@ class GraphedTrainStep:
         loss = self.criterion(self.model(x), y)
         loss.backward()
         self.optimizer.step()
-        return loss
+        # the step is complete: hand out the value without its (already consumed) autograd graph.  A caller that kept
+        # the previous eager step's loss alive WITH its graph made the capture of the next step fail
+        # (cudaErrorStreamCaptureInvalidated at capture_end; tools/capture_probe.py variants D / K / L)
+        return loss.detach()
 
     def _capture(self, key, x, y):
         static_x, static_y = x.clone(), y.clone()

@@ -425,3 +425,39 @@ def test_graphed_train_step_matches_eager(pkg, cuda_dev):
     assert torch.equal(a, b) and torch.isfinite(a).all()
     with pytest.raises(TypeError):
         pkg.GraphedTrainStep(model, pkg.BCEDiceLoss(), torch.optim.Adam(model.parameters()))
+
+
+def test_launch_switches_do_not_change_results(pkg, cuda_dev):
+    """csrc/launch.cuh: programmatic dependent launch only moves launch times — an eval forward is bit-identical with it
+    on and off; GraphedTrainStep records its graph with plain edges and restores the switch; the CTA-pair depth march
+    (csrc/dmarch2.cu) and its single-CTA-MMA fallback agree up to the fp32 accumulation order."""
+    ops = pkg.ops
+    model, _ = build(pkg, 5, 1, cuda_dev, init_features=64)
+    model.eval()
+    x, _ = synth((1, 5, 32, 32, 48), 9, cuda_dev)
+    was_pdl = ops.set_pdl(True)
+    was_pair = ops.set_dmarch_pair_mma(True)
+    try:
+        with torch.no_grad():
+            a = model(x)
+            ops.set_pdl(False)
+            b = model(x)
+            ops.set_pdl(True)
+            ops.set_dmarch_pair_mma(False)
+            c = model(x)
+            ops.set_dmarch_pair_mma(True)
+        assert torch.equal(a, b)
+        assert rel_l2(c, a) < TOL_LAYER and torch.isfinite(c).all()   # (bf16 roundings flip under another add order)
+        # the switch is back on after a capture
+        model.train()
+        opt = pkg.FusedAdam(model, lr=1e-4)
+        stepper = pkg.GraphedTrainStep(model, pkg.BCEDiceLoss(), opt)
+        y = (torch.rand(1, 1, 32, 32, 48, device=cuda_dev) < 0.2).float()
+        for _ in range(4):
+            loss = stepper(x, y)
+        assert stepper.disabled is None, stepper.disabled
+        assert stepper.replays == 2 and torch.isfinite(loss)
+        assert ops.set_pdl(True) is True
+    finally:
+        ops.set_pdl(was_pdl)
+        ops.set_dmarch_pair_mma(was_pair)
